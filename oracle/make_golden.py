@@ -1,0 +1,367 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the REAL reference modules.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+
+Every fixture stores the seeded inputs and the outputs the reference's own code produced for them
+(``oracle/ref_loader.py`` explains the five stub modules).  ``tests/test_oracle_golden.py`` then pins
+``oracle/kplanes_oracle.py`` to these vectors on any machine; the ``-m gpu`` tests pin the CUDA path
+to the same vectors.  Random draws the reference makes internally (``torch.rand`` in the samplers and
+the random background) are fed from a queue so that they can be stored with the fixture.
+"""
+from __future__ import annotations
+
+import contextlib
+import functools
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import kplanes_oracle as ko  # noqa: E402
+from oracle.ref_loader import load_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+@contextlib.contextmanager
+def rand_queue(queue):
+    """Serve torch.rand / torch.rand_like calls made by the reference from ``queue`` (in order)."""
+    real_rand, real_like = torch.rand, torch.rand_like
+    q = list(queue)
+
+    def fake_rand(*size, **kw):
+        if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)):
+            size = tuple(size[0])
+        t = q.pop(0)
+        assert tuple(t.shape) == tuple(size), (t.shape, size)
+        return t.clone()
+
+    def fake_like(x, **kw):
+        t = q.pop(0)
+        assert t.shape == x.shape, (t.shape, x.shape)
+        return t.clone()
+
+    torch.rand, torch.rand_like = fake_rand, fake_like
+    try:
+        yield q
+    finally:
+        torch.rand, torch.rand_like = real_rand, real_like
+
+
+@contextlib.contextmanager
+def record_searchsorted(store):
+    real = torch.searchsorted
+
+    def rec(*a, **k):
+        r = real(*a, **k)
+        store.append(r.clone())
+        return r
+
+    torch.searchsorted = rec
+    try:
+        yield
+    finally:
+        torch.searchsorted = real
+
+
+def save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    conv = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        conv[k] = np.asarray(v)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **conv)
+    print(f"wrote {path}: {os.path.getsize(path)/1024:.1f} KiB")
+
+
+def load_ref_density_field(R, p: ko.DensityFieldParams, resolution):
+    f = R.kplanes_field.KPlanesDensityField(p.aabb, resolution=resolution, feature_dim=p.grids[0].shape[1], linear_decoder=False)
+    with torch.no_grad():
+        for dst, src in zip(f.grids, p.grids):
+            dst.copy_(src)
+        for lin, w in zip(f.sigma_net.layers, p.sigma_w):
+            lin.weight.copy_(w)
+    return f
+
+
+def load_ref_field(R, p: ko.FieldParams, res, ms, sigma_hidden):
+    f = R.kplanes_field.KPlanesField(
+        p.aabb, spacetime_resolution=res, feat_dim=p.grids[0][0].shape[1], multiscale_res=ms,
+        concat_features_across_scales=p.concat, linear_decoder=False,
+        disable_viewing_dependent=not p.view_dependent, sigma_net_hidden_dim=sigma_hidden,
+    )
+    with torch.no_grad():
+        for gs, ps in zip(f.grids, p.grids):
+            for dst, src in zip(gs, ps):
+                dst.copy_(src)
+        for lin, w in zip(f.sigma_net.layers, p.sigma_w):
+            lin.weight.copy_(w)
+        for lin, w in zip(f.color_net.layers, p.color_w):
+            lin.weight.copy_(w)
+    return f
+
+
+def gen_interp(R):
+    g = torch.Generator().manual_seed(101)
+    res, ms, c = (12, 10, 14, 5), (1, 2), 8
+    grids = []
+    for m in ms:
+        reso = [r * m for r in res[:3]] + [res[3]]
+        grids.append([pl + 0.3 * torch.randn(pl.shape, generator=g) for pl in ko.init_planes(c, reso, 0.1, 0.5, g)])
+    pts = torch.rand(257, 4, generator=g) * 2.4 - 1.2  # includes out-of-range -> border clamp
+    pts[0] = torch.tensor([-1.0, -1.0, -1.0, -1.0])
+    pts[1] = torch.tensor([1.0, 1.0, 1.0, 1.0])
+    pts[2] = torch.tensor([0.0, 0.0, 0.0, 0.0])
+    plist = [torch.nn.ParameterList([torch.nn.Parameter(p.clone()) for p in gs]) for gs in grids]
+    out_cat = R.kplanes_field.interpolate_kplanes(pts, plist, True, False, False)
+    go = torch.randn(out_cat.shape, generator=g)
+    (out_cat * go).sum().backward()
+    grads = [p.grad for gs in plist for p in gs]
+    out_sum = R.kplanes_field.interpolate_kplanes(pts, plist, False, False, False)
+    # static (3-plane) case
+    grids3 = [[pl + 0.3 * torch.randn(pl.shape, generator=g) for pl in ko.init_planes(c, list(res[:3]), 0.1, 0.5, g)]]
+    out3 = R.kplanes_field.interpolate_kplanes(pts[:, :3], grids3, True, False, False)
+    arrs = dict(pts=pts, out_cat=out_cat, out_sum=out_sum, grad_out=go, out_static=out3)
+    for i, gs in enumerate(grids):
+        for j, p in enumerate(gs):
+            arrs[f"grid_{i}_{j}"] = p
+            arrs[f"ggrid_{i}_{j}"] = grads[i * 6 + j]
+    for j, p in enumerate(grids3[0]):
+        arrs[f"grid3_{j}"] = p
+    save("interp", **arrs)
+
+
+def gen_samplers(R):
+    g = torch.Generator().manual_seed(202)
+    n = 64
+    origins, directions, times, aabb = ko.synthetic_rays(n, g)
+    RS = R.ray_samplers
+    box = R.SceneBox(aabb=aabb)
+    col = R.scene_colliders.AABBBoxCollider(box, near_plane=0.05)
+    col.train()
+    rb = R.rays.RayBundle(origins=origins, directions=directions, pixel_area=torch.ones(n, 1), times=times)
+    rb = col(rb)
+    nears_t, fars_t = rb.nears.clone(), rb.fars.clone()
+    col.eval()
+    rb_e = R.rays.RayBundle(origins=origins, directions=directions, pixel_area=torch.ones(n, 1), times=times)
+    rb_e = col(rb_e)
+    arrs = dict(origins=origins, directions=directions, times=times, aabb=aabb, nears_train=nears_t, fars_train=fars_t,
+                nears_eval=rb_e.nears, fars_eval=rb_e.fars)
+    for mode in ("train", "eval"):
+        us = RS.UniformSampler()
+        pdf = RS.PDFSampler(include_original=False)
+        us.train(mode == "train")
+        pdf.train(mode == "train")
+        s0, s1 = 40, 24
+        t_rand = torch.rand(n, s0 + 1, generator=g)
+        u_rand = torch.rand(n, s1 + 1, generator=g)
+        weights = torch.rand(n, s0, 1, generator=g) ** 4
+        weights[3] = 0.0  # all-zero weights row (histogram padding only)
+        weights[4, :, 0] = torch.nn.functional.one_hot(torch.tensor(7), s0).float()  # a spike
+        ss = []
+        with rand_queue([t_rand, u_rand] if mode == "train" else []), record_searchsorted(ss):
+            rs0 = us(rb, num_samples=s0)
+            rs1 = pdf(rb, rs0, weights, num_samples=s1)
+        arrs.update({
+            f"{mode}_t_rand": t_rand, f"{mode}_u_rand": u_rand, f"{mode}_weights": weights,
+            f"{mode}_bins0": torch.cat([rs0.spacing_starts[..., 0], rs0.spacing_ends[..., -1:, 0]], -1),
+            f"{mode}_starts0": rs0.frustums.starts[..., 0], f"{mode}_ends0": rs0.frustums.ends[..., 0],
+            f"{mode}_bins1": torch.cat([rs1.spacing_starts[..., 0], rs1.spacing_ends[..., -1:, 0]], -1),
+            f"{mode}_starts1": rs1.frustums.starts[..., 0], f"{mode}_ends1": rs1.frustums.ends[..., 0],
+            f"{mode}_inds1": ss[0], f"{mode}_positions1": rs1.frustums.get_positions(),
+        })
+    save("samplers", **arrs)
+
+
+def gen_render(R):
+    g = torch.Generator().manual_seed(303)
+    n, s = 48, 37
+    starts = torch.sort(torch.rand(n, s + 1, generator=g) * 4 + 0.1, dim=-1).values
+    fr = R.rays.Frustums(origins=torch.zeros(n, s, 3), directions=torch.ones(n, s, 3), starts=starts[:, :-1, None],
+                         ends=starts[:, 1:, None], pixel_area=torch.ones(n, s, 1))
+    rs = R.rays.RaySamples(frustums=fr, deltas=(starts[:, 1:] - starts[:, :-1])[..., None])
+    density = (torch.rand(n, s, 1, generator=g) ** 3 * 12).requires_grad_(True)
+    with torch.no_grad():
+        density[5] = 0.0
+        density[6, :10] = 1e4  # saturating ray
+    rgb = torch.rand(n, s, 3, generator=g).requires_grad_(True)
+    bg = torch.rand(n, 3, generator=g)
+    w = rs.get_weights(density)
+    rr = R.renderers
+    r_rgb = rr.RGBRenderer(background_color=bg)
+    r_rgb.train()
+    comp = r_rgb(rgb, w)
+    acc = rr.AccumulationRenderer()(w)
+    dmed = rr.DepthRenderer("median")(w, rs)
+    dexp = rr.DepthRenderer("expected")(w, rs)
+    mr = rr.MedianRGBRenderer()
+    mr.train()
+    med_rgb = mr(rgb, w)
+    go_rgb = torch.randn(n, 3, generator=g)
+    go_acc = torch.randn(n, 1, generator=g)
+    go_w = torch.randn(n, s, 1, generator=g) * 0.1
+    ((comp * go_rgb).sum() + (acc * go_acc).sum() + (w * go_w).sum()).backward()
+    r_eval = rr.RGBRenderer(background_color="last_sample")
+    r_eval.eval()
+    comp_eval = r_eval(rgb.detach(), w.detach())
+    save("render", starts=starts, density=density, rgb=rgb, bg=bg, weights=w, comp=comp, acc=acc, depth_median=dmed,
+         depth_expected=dexp, median_rgb=med_rgb, go_rgb=go_rgb, go_acc=go_acc, go_w=go_w, g_density=density.grad,
+         g_rgb=rgb.grad, comp_eval=comp_eval)
+
+
+def gen_losses(R):
+    g = torch.Generator().manual_seed(404)
+    n = 40
+    L = R.losses
+
+    def mk(s):
+        b = torch.sort(torch.rand(n, s + 1, generator=g), dim=-1).values
+        b[:, 0], b[:, -1] = 0.0, 1.0
+        w = torch.rand(n, s, 1, generator=g) ** 2
+        w = w / w.sum(1, keepdim=True) * torch.rand(n, 1, 1, generator=g)
+        return b, w
+
+    class RSamp:  # minimal object with spacing_starts/ends like RaySamples
+        def __init__(self, b):
+            self.spacing_starts = b[:, :-1, None]
+            self.spacing_ends = b[:, 1:, None]
+
+    (b0, w0), (b1, w1), (b2, w2) = mk(32), mk(20), mk(12)
+    w0.requires_grad_(True), w1.requires_grad_(True), w2.requires_grad_(True)
+    il = L.interlevel_loss([w0, w1, w2], [RSamp(b0), RSamp(b1), RSamp(b2)])
+    dl = L.distortion_loss([w0, w1, w2], [RSamp(b0), RSamp(b1), RSamp(b2)])
+    (il + dl).backward()
+    arrs = dict(b0=b0, b1=b1, b2=b2, w0=w0, w1=w1, w2=w2, interlevel=il, distortion=dl, g_w0=w0.grad, g_w1=w1.grad, g_w2=w2.grad)
+    # plane regularisers on a 2-scale dynamic field + static field
+    grids = []
+    for m in (1, 2):
+        reso = [6 * m, 5 * m, 7 * m, 4]
+        grids.append([torch.nn.Parameter(pl + 0.3 * torch.randn(pl.shape, generator=g)) for pl in ko.init_planes(4, reso, 0.1, 0.5, g)])
+    tv, ts, st = L.space_tv_loss(grids), L.time_smoothness_loss(grids), L.sparse_transients_loss(grids)
+    (0.7 * tv + 1.3 * ts + 0.4 * st).backward()
+    arrs.update(space_tv=tv, time_smoothness=ts, sparse_transients=st)
+    for i, gs in enumerate(grids):
+        for j, p in enumerate(gs):
+            arrs[f"grid_{i}_{j}"] = p
+            arrs[f"ggrid_{i}_{j}"] = p.grad
+    grids3 = [[torch.nn.Parameter(pl + 0.3 * torch.randn(pl.shape, generator=g)) for pl in ko.init_planes(4, [6, 5, 7], 0.1, 0.5, g)]]
+    arrs.update(space_tv_static=L.space_tv_loss(grids3), time_smoothness_static=L.time_smoothness_loss(grids3),
+                sparse_transients_static=L.sparse_transients_loss(grids3))
+    for j, p in enumerate(grids3[0]):
+        arrs[f"grid3_{j}"] = p
+    # DS-NeRF depth loss
+    s = 12
+    starts = torch.sort(torch.rand(n, s + 1, generator=g) * 4 + 0.1, dim=-1).values
+    steps = ((starts[:, :-1] + starts[:, 1:]) / 2)[..., None]
+    lengths = (starts[:, 1:] - starts[:, :-1])[..., None]
+    term = torch.rand(n, 1, generator=g) * 4
+    term[:5] = 0.0
+    dsl = L.ds_nerf_depth_loss(w2.detach(), term, steps, lengths, torch.tensor([0.01]))
+    arrs.update(ds_starts=starts, ds_term=term, ds_loss=dsl)
+    save("losses", **arrs)
+
+
+def gen_model(R):
+    """Whole get_outputs + get_loss_dict + backward, composed from the reference's own classes exactly as
+    NS/models/kplanes.py:188-309, 349-388, 414-452 does (the Model class itself drags in torchmetrics /
+    RetinaNet downloads)."""
+    g = torch.Generator().manual_seed(505)
+    n = 96
+    origins, directions, times, aabb = ko.synthetic_rays(n, g)
+    mp = ko.make_model_params("tiny", g, aabb)
+    image = torch.rand(n, 3, generator=g)
+    rand = ko.make_rand(n, mp, g)
+    anneal = 0.37
+
+    field = load_ref_field(R, mp.field, (16, 16, 16, 6), (1, 2), 64)
+    props = [load_ref_density_field(R, mp.proposals[0], [24, 24, 24, 6]), load_ref_density_field(R, mp.proposals[1], [32, 32, 32, 6])]
+    RS = R.ray_samplers
+    sampler = RS.ProposalNetworkSampler(
+        num_nerf_samples_per_ray=mp.num_nerf_samples, num_proposal_samples_per_ray=mp.num_proposal_samples,
+        num_proposal_network_iterations=2, single_jitter=False, update_sched=lambda step: 1,
+        initial_sampler=RS.UniformSampler(single_jitter=False),
+    )
+    sampler.set_anneal(anneal)
+    col = R.scene_colliders.AABBBoxCollider(R.SceneBox(aabb=aabb), near_plane=0.0)
+    rr = R.renderers
+    r_rgb, r_acc, r_depth, r_med = rr.RGBRenderer("random"), rr.AccumulationRenderer(), rr.DepthRenderer(), rr.MedianRGBRenderer()
+    for m in (field, *props, sampler, col, r_rgb, r_med):
+        m.train()
+
+    rb = R.rays.RayBundle(origins=origins, directions=directions, pixel_area=torch.ones(n, 1), times=times)
+    rb = col(rb)
+    ss = []
+    queue = [rand["t_rand"], rand["u1"], rand["u2"], rand["bg"]]
+    with rand_queue(queue), record_searchsorted(ss):
+        density_fns = [functools.partial(p.density_fn, times=rb.times) for p in props]
+        ray_samples, weights_list, ray_samples_list = sampler(rb, density_fns=density_fns)
+        fo = field(ray_samples)
+        FH = R.kplanes_field.FieldHeadNames
+        weights = ray_samples.get_weights(fo[FH.DENSITY])
+        weights_list.append(weights)
+        ray_samples_list.append(ray_samples)
+        rgb = r_rgb(rgb=fo[FH.RGB], weights=weights)
+    inds = ss[:2]
+    acc = r_acc(weights)
+    depth = r_depth(weights, ray_samples)
+    med = r_med(rgb=fo[FH.RGB], weights=weights)
+    pd0 = r_depth(weights=weights_list[0], ray_samples=ray_samples_list[0])
+    pd1 = r_depth(weights=weights_list[1], ray_samples=ray_samples_list[1])
+
+    L = R.losses
+    coef = mp.loss_coefficients
+    nerf_g, prop_g = field.grids, [p.grids for p in props]
+    ld = {
+        "rgb_loss": L.MSELoss()(image, rgb),
+        "distortion_loss": L.distortion_loss(weights_list, ray_samples_list),
+        "interlevel_loss": L.interlevel_loss(weights_list, ray_samples_list),
+        "space_tv_loss": L.space_tv_loss(nerf_g),
+        "space_tv_proposal_loss": L.space_tv_loss(prop_g),
+        "sparse_transients_loss": L.sparse_transients_loss(nerf_g),
+        "sparse_transients_proposal_loss": L.sparse_transients_loss(prop_g),
+        "time_smoothness_loss": L.time_smoothness_loss(nerf_g),
+        "time_smoothness_proposal_loss": L.time_smoothness_loss(prop_g),
+    }
+    ld = {k: v * coef[k] for k, v in ld.items()}
+    loss = sum(ld.values())
+    loss.backward()
+
+    arrs = dict(origins=origins, directions=directions, times=times, aabb=aabb, image=image, anneal=np.float32(anneal),
+                nears=rb.nears, fars=rb.fars, rgb=rgb, accumulation=acc, depth=depth, median_rgb=med, prop_depth_0=pd0,
+                prop_depth_1=pd1, inds1=inds[0], inds2=inds[1], loss=loss, density=fo[FH.DENSITY], rgb_samples=fo[FH.RGB])
+    for k, v in rand.items():
+        arrs["rand_" + k] = v
+    for k, v in ld.items():
+        arrs["loss_" + k] = v
+    for i, (w, rs_) in enumerate(zip(weights_list, ray_samples_list)):
+        arrs[f"weights_{i}"] = w
+        arrs[f"bins_{i}"] = torch.cat([rs_.spacing_starts[..., 0], rs_.spacing_ends[..., -1:, 0]], -1)
+    # parameters in oracle order (ModelParams.tensors()) and their reference gradients
+    ref_params = []
+    for p in props:
+        ref_params += list(p.grids) + [l.weight for l in p.sigma_net.layers]
+    ref_params += [q for gs in field.grids for q in gs] + [l.weight for l in field.sigma_net.layers] + [l.weight for l in field.color_net.layers]
+    for i, (mine, ref) in enumerate(zip(mp.tensors(), ref_params)):
+        assert mine.shape == ref.shape
+        arrs[f"param_{i}"] = mine
+        arrs[f"grad_{i}"] = ref.grad
+    save("model_tiny", **arrs)
+
+
+def main():
+    torch.set_num_threads(1)
+    R = load_reference()
+    gen_interp(R)
+    gen_samplers(R)
+    gen_render(R)
+    gen_losses(R)
+    gen_model(R)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+"""Pins oracle/kplanes_oracle.py to the fixtures produced by the REAL reference (oracle/make_golden.py).
+
+CPU-only; runs everywhere.  Tolerances: integer outputs bit-exact; fp32 outputs identical up to
+reassociation (<= 1e-6 rel).
+"""
+import torch
+
+from oracle import kplanes_oracle as ko
+from tests.conftest import load_golden, rel_err
+
+TOL = 2e-6
+
+
+def _grids(g, prefix, n_scales, n_planes=6):
+    return [[g[f"{prefix}_{i}_{j}"] for j in range(n_planes)] for i in range(n_scales)]
+
+
+def test_interpolate_kplanes_matches_reference():
+    g = load_golden("interp")
+    grids = _grids(g, "grid", 2)
+    for gs in grids:
+        for p in gs:
+            p.requires_grad_(True)
+    out = ko.interpolate_kplanes(g["pts"], grids, True)
+    assert rel_err(out, g["out_cat"]) < TOL
+    (out * g["grad_out"]).sum().backward()
+    for i in range(2):
+        for j in range(6):
+            assert rel_err(grids[i][j].grad, g[f"ggrid_{i}_{j}"]) < TOL
+    assert rel_err(ko.interpolate_kplanes(g["pts"], grids, False), g["out_sum"]) < TOL
+    g3 = [[g[f"grid3_{j}"] for j in range(3)]]
+    assert rel_err(ko.interpolate_kplanes(g["pts"][:, :3], g3, True), g["out_static"]) < TOL
+
+
+def test_manual_bilinear_equals_grid_sample():
+    g = load_golden("interp")
+    for j, comb in enumerate([(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]):
+        plane = g[f"grid_1_{j}"]
+        a = ko.grid_sample_plane(plane, g["pts"][:, list(comb)])
+        b = ko.bilinear_border_manual(plane, g["pts"][:, list(comb)])
+        assert rel_err(b, a) < TOL
+
+
+def test_collider_and_samplers_match_reference():
+    g = load_golden("samplers")
+    o, d, t, aabb = g["origins"], g["directions"], g["times"], g["aabb"]
+    nt, ft = ko.aabb_collider(o, d, aabb, near_plane=0.05)
+    assert torch.equal(nt, g["nears_train"]) and torch.equal(ft, g["fars_train"])
+    ne, fe = ko.aabb_collider(o, d, aabb, near_plane=0.0)
+    assert torch.equal(ne, g["nears_eval"]) and torch.equal(fe, g["fars_eval"])
+    for mode in ("train", "eval"):
+        tr = g[f"{mode}_t_rand"] if mode == "train" else None
+        ur = g[f"{mode}_u_rand"] if mode == "train" else None
+        s0 = ko.uniform_sampler(o, d, nt, ft, t, 40, tr)
+        assert torch.equal(s0.spacing_bins, g[f"{mode}_bins0"])
+        assert torch.equal(s0.starts, g[f"{mode}_starts0"]) and torch.equal(s0.ends, g[f"{mode}_ends0"])
+        s1, inds = ko.pdf_sampler(s0, g[f"{mode}_weights"][..., 0], 24, ur)
+        assert torch.equal(inds, g[f"{mode}_inds1"])  # bit-exact indices
+        assert torch.equal(s1.spacing_bins, g[f"{mode}_bins1"])
+        assert torch.equal(s1.starts, g[f"{mode}_starts1"]) and torch.equal(s1.ends, g[f"{mode}_ends1"])
+        assert rel_err(s1.positions(), g[f"{mode}_positions1"]) < TOL
+
+
+def test_compositing_matches_reference():
+    g = load_golden("render")
+    starts = g["starts"]
+    deltas = (starts[:, 1:] - starts[:, :-1])[..., None]
+    steps = (starts[:, :-1] + starts[:, 1:]) / 2
+    density = g["density"].clone().requires_grad_(True)
+    rgb = g["rgb"].clone().requires_grad_(True)
+    w = ko.get_weights(deltas, density)
+    assert rel_err(w, g["weights"]) < TOL
+    comp = ko.render_rgb(rgb, w, g["bg"], training=True)
+    acc = ko.render_accumulation(w)
+    assert rel_err(comp, g["comp"]) < TOL and rel_err(acc, g["acc"]) < TOL
+    assert torch.equal(ko.render_depth_median(w, steps), g["depth_median"])
+    assert rel_err(ko.render_depth_expected(w, steps), g["depth_expected"]) < TOL
+    assert torch.equal(ko.render_median_rgb(rgb, w), g["median_rgb"])
+    ((comp * g["go_rgb"]).sum() + (acc * g["go_acc"]).sum() + (w * g["go_w"]).sum()).backward()
+    assert rel_err(density.grad, g["g_density"]) < TOL
+    assert rel_err(rgb.grad, g["g_rgb"]) < TOL
+    assert rel_err(ko.render_rgb(g["rgb"], g["weights"], "last_sample", training=False), g["comp_eval"]) < TOL
+
+
+def test_losses_match_reference():
+    g = load_golden("losses")
+    ws = [g[f"w{i}"].clone().requires_grad_(True) for i in range(3)]
+    bs = [g[f"b{i}"] for i in range(3)]
+    il = ko.interlevel_loss(ws, bs)
+    dl = ko.distortion_loss(ws, bs)
+    assert rel_err(il, g["interlevel"]) < TOL and rel_err(dl, g["distortion"]) < TOL
+    (il + dl).backward()
+    for i in range(3):
+        assert rel_err(ws[i].grad, g[f"g_w{i}"]) < TOL
+    grids = _grids(g, "grid", 2)
+    for gs in grids:
+        for p in gs:
+            p.requires_grad_(True)
+    tv, ts, st = ko.space_tv_loss(grids), ko.time_smoothness_loss(grids), ko.sparse_transients_loss(grids)
+    assert rel_err(tv, g["space_tv"]) < TOL and rel_err(ts, g["time_smoothness"]) < TOL and rel_err(st, g["sparse_transients"]) < TOL
+    (0.7 * tv + 1.3 * ts + 0.4 * st).backward()
+    for i in range(2):
+        for j in range(6):
+            assert rel_err(grids[i][j].grad, g[f"ggrid_{i}_{j}"]) < TOL
+    g3 = [[g[f"grid3_{j}"] for j in range(3)]]
+    assert rel_err(ko.space_tv_loss(g3), g["space_tv_static"]) < TOL
+    assert float(ko.time_smoothness_loss(g3)) == float(g["time_smoothness_static"]) == 0.0
+    assert float(ko.sparse_transients_loss(g3)) == float(g["sparse_transients_static"]) == 0.0
+    st_ = g["ds_starts"]
+    steps = ((st_[:, :-1] + st_[:, 1:]) / 2)[..., None]
+    lengths = (st_[:, 1:] - st_[:, :-1])[..., None]
+    assert rel_err(ko.ds_nerf_depth_loss(g["w2"], g["ds_term"], steps, lengths, torch.tensor([0.01])), g["ds_loss"]) < TOL
+
+
+def load_tiny_model(g):
+    """Rebuild oracle ModelParams from the model_tiny fixture (parameters stored in tensors() order)."""
+    aabb = g["aabb"]
+    gen = torch.Generator().manual_seed(0)
+    mp = ko.make_model_params("tiny", gen, aabb)
+    for i, p in enumerate(mp.tensors()):
+        p.data.copy_(g[f"param_{i}"])
+    return mp
+
+
+def test_model_step_matches_reference():
+    g = load_golden("model_tiny")
+    mp = load_tiny_model(g)
+    rand = {k[5:]: v for k, v in g.items() if k.startswith("rand_")}
+    out, ld, grads = ko.train_step(mp, g["origins"], g["directions"], g["times"], g["image"], rand, anneal=float(g["anneal"]))
+    assert torch.equal(out["inds_list"][0], g["inds1"]) and torch.equal(out["inds_list"][1], g["inds2"])
+    for i in range(3):
+        assert torch.equal(out["samples_list"][i].spacing_bins, g[f"bins_{i}"])
+        assert rel_err(out["weights_list"][i], g[f"weights_{i}"]) < TOL
+    for k in ("rgb", "accumulation", "depth", "median_rgb", "prop_depth_0", "prop_depth_1", "density"):
+        assert rel_err(out[k], g[k]) < TOL, k
+    for k, v in ld.items():
+        assert rel_err(v, g["loss_" + k]) < TOL, k
+    for i, gr in enumerate(grads):
+        assert rel_err(gr, g[f"grad_{i}"]) < 1e-5, i
