@@ -1,0 +1,172 @@
+/*
+ * kplanes_b200.h -- C-ABI of libkplanes_b200.so: the B200 (sm_100a) K-Planes train/render hot path.
+ *
+ * Drop-in boundary.  Every entry point takes raw DEVICE pointers, plain sizes and a
+ * cudaStream_t passed as void*; returns 0 on success, non-zero on failure (message via
+ * kp_last_error()).  No torch / C++ types cross this boundary.  The Python host side
+ * (soccernerfs_b200/) binds these with ctypes and wraps them in torch.autograd.Functions that mirror
+ * the reference's nerfstudio plugin surface.  NS = nerfstudio/nerfstudio in the reference checkout.
+ *
+ * Layout conventions
+ *   planes      channel-last fp32 [H][W][C] (the reference keeps [1,C,H,W]; repacked once on load).
+ *               Plane (a,b) of combinations(range(D),2) has W = reso[a], H = reso[b] and is sampled
+ *               at (pts[a] -> W, pts[b] -> H)   (NS/fields/kplanes_field.py:61-67, :113).
+ *   plane_ptrs  HOST array [n_scales*n_planes] of device pointers, scale-major.
+ *   plane_hw    HOST array [n_scales*n_planes*2] of (H, W).
+ *   ray form    origins[N,3], directions[N,3], starts[N,S], ends[N,S], times[N] (may be NULL),
+ *               aabb HOST float[6] = min xyz, max xyz.  Sample position = o + d*(start+end)/2
+ *               (NS/cameras/rays.py:54) normalised by the aabb (NS/data/scene_box.py:56-66) to
+ *               [0,1] (norm_mode 0: KPlanesDensityField quirk, kplanes_field.py:439-440) or to
+ *               [-1,1] (norm_mode 1: KPlanesField, kplanes_field.py:283-284); time -> t*2-1.
+ *   point form  pts[M,D] already in grid_sample's [-1,1] convention (D = 3 or 4).
+ */
+#ifndef KPLANES_B200_H_
+#define KPLANES_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KP_ABI_VERSION 1
+#define KP_MAX_SCALES 8
+#define KP_MAX_PLANES 6
+
+int kp_abi_version(void);
+const char* kp_last_error(void);
+
+/* Where sample coordinates come from (exactly one of pts / ray form is used). */
+typedef struct KpPoints {
+  const float* pts;        /* [M,D] or NULL */
+  const float* origins;    /* [N,3] */
+  const float* directions; /* [N,3] */
+  const float* starts;     /* [N,S] */
+  const float* ends;       /* [N,S] */
+  const float* times;      /* [N] or NULL */
+  int32_t D;               /* 3 (static) or 4 (dynamic) */
+  int32_t S;               /* samples per ray (ray form) */
+  int32_t norm_mode;       /* 0: [0,1], 1: [-1,1] */
+  float aabb[6];
+} KpPoints;
+
+/* ---- (a1-a3) multiscale hexplane field: replaces interpolate_kplanes, NS/fields/kplanes_field.py:77-126
+ *      (6*n_scales F.grid_sample calls + Hadamard + cat, NS/utils/interpolation.py:5-33). ------------- */
+int kp_hexplane_fwd(const float* const* plane_ptrs, const int32_t* plane_hw, int n_scales, int n_planes,
+                    int C, const KpPoints* points, int64_t M, int concat, uint32_t use_mask,
+                    float* out /* [M, n_scales*C] (concat) or [M, C] */, void* stream);
+/* grad_plane_ptrs: HOST array of device pointers (same order); entries may be NULL (frozen plane,
+ * kplanes_field.py:102-110).  Gradients are ACCUMULATED (red.global.add) into the buffers. */
+int kp_hexplane_bwd(const float* const* plane_ptrs, float* const* grad_plane_ptrs, const int32_t* plane_hw,
+                    int n_scales, int n_planes, int C, const KpPoints* points, int64_t M, int concat,
+                    uint32_t use_mask, const float* grad_out, void* stream);
+
+/* ---- (a6) proposal density field: KPlanesDensityField.get_density, kplanes_field.py:434-460:
+ *      single-scale planes (C = 4|8|16) -> Hadamard -> [hidden x C] ReLU (or linear) -> [1 x hidden] ->
+ *      trunc_exp, fused in one kernel.  w1 [hidden,C], w2 [hidden] row-major (torch Linear layout). --- */
+int kp_density_field_fwd(const float* const* plane_ptrs, const int32_t* plane_hw, int n_planes, int C,
+                         const float* w1, const float* w2, int hidden, int relu, const KpPoints* points,
+                         int64_t M, uint32_t use_mask, float* density /* [M] */, void* stream);
+int kp_density_field_bwd(const float* const* plane_ptrs, float* const* grad_plane_ptrs, const int32_t* plane_hw,
+                         int n_planes, int C, const float* w1, const float* w2, int hidden, int relu,
+                         const KpPoints* points, int64_t M, uint32_t use_mask, const float* grad_density /* [M] */,
+                         float* grad_w1, float* grad_w2 /* accumulated */, void* stream);
+
+/* ---- (a4,a5) decoders: sigma_net / color_net (tcnn FullyFusedMLP in the reference, kplanes_field.py:249-273;
+ *      bias-free, ReLU hidden).  sigma: feats[M,K] -> h1[M,H] -> o[M,16]; density = trunc_exp(o[:,15])
+ *      (kplanes_field.py:307-311, NS/field_components/activations.py:25-41).
+ *      color: cin = [SH4((d+1)/2 *2-1) (16, if dirs!=NULL) | geo o[:,0:15]] -> H2 -> H2 -> 3, sigmoid
+ *      (kplanes_field.py:314-358, NS/utils/math.py:25-86).  Hidden activations are written to caller
+ *      buffers and re-read by the backward. -------------------------------------------------------- */
+int kp_sigma_net_fwd(const float* feats, const float* w1, const float* w2, int64_t M, int K, int H,
+                     float* h1 /* [M,H] */, float* o /* [M,16] */, float* density /* [M] */, void* stream);
+int kp_sigma_net_bwd(const float* feats, const float* w1, const float* w2, int64_t M, int K, int H,
+                     const float* h1, const float* o, const float* grad_density /* [M] or NULL */,
+                     const float* grad_o /* [M,16] upstream grad of o (col 15 added to the density path), or NULL */, float* grad_feats /* [M,K] */,
+                     float* grad_w1, float* grad_w2 /* accumulated */, float* scratch /* [M,H] */, void* stream);
+int kp_color_net_fwd(const float* directions /* [N,3] or NULL */, int S, const float* geo /* [M,>=15] */,
+                     int ldgeo /* row stride of geo: 16 for a view of o, 15 if packed */, const float* w3, const float* w4, const float* w5, int64_t M, int H2,
+                     float* cin /* [M,32|16] */, float* h2, float* h3 /* [M,H2] */, float* rgb /* [M,3] */,
+                     void* stream);
+int kp_color_net_bwd(int view_dependent, const float* cin, const float* h2, const float* h3, const float* rgb,
+                     const float* w3, const float* w4, const float* w5, int64_t M, int H2,
+                     const float* grad_rgb /* [M,3] */, float* grad_o /* [M,16], cols 0..14 written, col 15 zeroed */,
+                     float* grad_w3, float* grad_w4, float* grad_w5 /* accumulated */,
+                     float* scratch_a, float* scratch_b /* [M,H2] each */, void* stream);
+
+/* ---- (a13) AABBBoxCollider._intersect_with_aabb, NS/model_components/scene_colliders.py:57-95 ---- */
+int kp_aabb_intersect(const float* origins, const float* directions, int64_t N, const float* aabb_host6,
+                      float near_plane, float* nears, float* fars, void* stream);
+
+/* ---- (a7) SpacedSampler / UniformSampler, NS/model_components/ray_samplers.py:79-126.
+ *      lin_bins [S+1] = torch.linspace(0,1,S+1) (device).  t_rand [N,S+1] or [N,1] (rand_stride 0)
+ *      or NULL (eval).  spacing: 0 uniform (x), 1 UniformLinDispPiecewise (ray_samplers.py:236-246).
+ *      Outputs spacing bins [N,S+1] and euclidean bins [N,S+1]. ------------------------------------- */
+int kp_uniform_bins(const float* lin_bins, const float* t_rand, int rand_stride, const float* nears,
+                    const float* fars, int64_t N, int S, int spacing, float* spacing_bins, float* euclid_bins,
+                    void* stream);
+
+/* ---- (a8) PDFSampler.generate_ray_samples (include_original=False), ray_samplers.py:274-369:
+ *      warp-per-ray inverse-CDF search.  weights [N,S_in] (already annealed), existing spacing bins
+ *      [N,S_in+1], u_base [S_out+1] = torch.linspace(0, 1-1/nb, nb) (device), rand [N,S_out+1] | [N,1]
+ *      (rand_stride 0) | NULL (eval: u_base + 1/(2 nb)).  Outputs spacing bins, euclidean bins [N,S_out+1]
+ *      and the int64 searchsorted(side="right") indices (bit-exact target). ------------------------- */
+int kp_pdf_resample(const float* weights, const float* existing_bins, int S_in, const float* u_base,
+                    const float* rand, int rand_stride, const float* nears, const float* fars, int64_t N,
+                    int S_out, float histogram_padding, float eps, int spacing, float* cdf_out /* [N,S_in+1] or NULL */,
+                    float* spacing_bins, float* euclid_bins, int64_t* inds /* [N,S_out+1] or NULL */, void* stream);
+
+/* ---- (a10) RaySamples.get_weights, NS/cameras/rays.py:127-149: warp-per-ray transmittance scan ---- */
+int kp_weights_fwd(const float* deltas, const float* densities, int64_t N, int S, float* weights, void* stream);
+int kp_weights_bwd(const float* deltas, const float* densities, const float* grad_weights, int64_t N, int S,
+                   float* grad_densities, void* stream);
+
+/* ---- (a11,a12) renderers, NS/model_components/renderers.py:58-140, 197-223, 226-287, 290-362.
+ *      One pass per ray: comp_rgb = sum w*rgb + bg*(1-sum w), accumulation = sum w,
+ *      median_index = clamp(searchsorted(cumsum(w), 0.5, "left")), expected depth numerator/denominator.
+ *      bg_mode: 0 tensor bg[N,3], 1 last_sample.  nan_to_num_rgb: eval-mode RGBRenderer (renderers.py:133). */
+int kp_render_fwd(const float* weights, const float* rgb /* [N,S,3] or NULL */, const float* steps /* [N,S] or NULL */,
+                  const float* bg /* [N,3] or NULL */, int bg_mode, int nan_to_num_rgb, int64_t N, int S,
+                  float* comp_rgb /* [N,3] or NULL */, float* accumulation /* [N] or NULL */,
+                  int64_t* median_index /* [N] or NULL */, float* expected_depth /* [N] or NULL (unclipped) */,
+                  void* stream);
+int kp_render_bwd(const float* weights, const float* rgb, const float* bg, int bg_mode, int64_t N, int S,
+                  const float* grad_comp /* [N,3] or NULL */, const float* grad_acc /* [N] or NULL */,
+                  float* grad_weights /* [N,S] */, float* grad_rgb /* [N,S,3] or NULL */, void* stream);
+
+/* ---- (a14) mip-NeRF-360 losses, NS/model_components/losses.py:46-144 ------------------------------
+ *      distortion: per-ray loss [N] (mean taken by caller) and grad wrt w.  interlevel: per-(ray,sample)
+ *      loss [N,S] for one proposal level and grad wrt the proposal weights. */
+int kp_distortion_fwd(const float* sdist /* [N,S+1] */, const float* w /* [N,S] */, int64_t N, int S,
+                      float* loss_per_ray, void* stream);
+int kp_distortion_bwd(const float* sdist, const float* w, const float* grad_per_ray, int64_t N, int S,
+                      float* grad_w, void* stream);
+int kp_interlevel_fwd(const float* c /* [N,S+1] */, const float* w /* [N,S] */, const float* cp /* [N,Sp+1] */,
+                      const float* wp /* [N,Sp] */, int64_t N, int S, int Sp, float* loss /* [N,S] */, void* stream);
+int kp_interlevel_bwd(const float* c, const float* w, const float* cp, const float* wp, const float* grad_loss /* [N,S] */,
+                      int64_t N, int S, int Sp, float* grad_wp /* [N,Sp] */, void* stream);
+
+/* ---- (a15) plane regularisers, losses.py:356-452: for ONE channel-last plane [H,W,C]:
+ *      sums[0] = sum (t[h+1]-t[h])^2, sums[1] = sum (t[w+1]-t[w])^2, sums[2] = sum (second diff along H)^2,
+ *      sums[3] = sum |1-t|  (double accumulators, device, ACCUMULATED).  The backward writes / adds
+ *      sum_i coef[i] * d(sums[i])/dt (coef read from device memory so no host sync is needed). */
+int kp_plane_reg_fwd(const float* plane, int H, int W, int C, uint32_t terms /* bit i: compute sums[i] */,
+                     double* sums4, void* stream);
+int kp_plane_reg_bwd(const float* plane, int H, int W, int C, const float* coef_dev4 /* DEVICE float[4] */,
+                     uint32_t terms /* bit i: include term i */, int accumulate /* 0: grad = g, 1: grad += g */,
+                     float* grad, void* stream);
+
+/* ---- (f1) Adam over a flat fp32 buffer (torch.optim.Adam math; NS/engine/optimizers.py:74-160,
+ *      method_configs.py:546-557: lr 1e-2, eps 1e-12).  step is 1-based. ---------------------------- */
+int kp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                 void* stream);
+
+/* Repack between the reference's NCHW [1,C,H,W] checkpoint layout and channel-last [H,W,C]. */
+int kp_repack_nchw_to_hwc(const float* src, float* dst, int C, int H, int W, void* stream);
+int kp_repack_hwc_to_nchw(const float* src, float* dst, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KPLANES_B200_H_ */

@@ -1,0 +1,533 @@
+// Multiscale hexplane field kernels (sm_100a).
+//
+// Replaces NS/fields/kplanes_field.py:77-126 (interpolate_kplanes: 6*K F.grid_sample launches + Hadamard +
+// cat) and the ATen grid_sampler_2d fwd/bwd underneath it (NS/utils/interpolation.py:24-30) with ONE gather
+// kernel and ONE scatter kernel over channel-last planes:
+//   * a sample is owned by C/4 adjacent lanes, each lane moving 16-byte float4 slices, so the C/4 lanes of a
+//     texel read/reduce one contiguous 4*C-byte run (C=32: exactly one 128-byte line);
+//   * all plane corners of a scale are issued before first use (24 independent 16-B loads per lane);
+//   * the Hadamard product across planes and the concat across scales happen in registers and the
+//     features are written once;
+//   * the backward re-gathers the six interpolants (product rule needs the other five) instead of saving
+//     6*K [M,C] tensors, and scatter-adds with red.global.add.v4.f32 (16-byte L2 reductions).
+// Also here: the fused proposal density field (kplanes_field.py:434-460): gather (C=8) -> Hadamard ->
+// 8->64->1 MLP -> trunc_exp in one kernel, and its backward.
+#include "common.cuh"
+
+namespace kp {
+
+struct PlaneRef {
+  const float* p;
+  float* g;
+  int H, W, ca, cb;
+};
+struct FieldRef {
+  PlaneRef pl[KP_MAX_SCALES * KP_MAX_PLANES];
+  int n_scales, n_planes;
+  uint32_t use_mask;
+  int concat;
+};
+
+static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const* grad_ptrs, const int32_t* plane_hw,
+                      int n_scales, int n_planes, int D, uint32_t use_mask, int concat) {
+  KP_CHECK(n_scales >= 1 && n_scales <= KP_MAX_SCALES, "n_scales=%d out of range [1,%d]", n_scales, KP_MAX_SCALES);
+  KP_CHECK((n_planes == 3 && D == 3) || (n_planes == 6 && D == 4), "n_planes=%d / D=%d must be 3/3 or 6/4", n_planes, D);
+  static const int comb4[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  static const int comb3[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+  for (int k = 0; k < n_scales; ++k)
+    for (int p = 0; p < n_planes; ++p) {
+      PlaneRef& r = F.pl[k * KP_MAX_PLANES + p];
+      r.p = plane_ptrs[k * n_planes + p];
+      r.g = grad_ptrs ? grad_ptrs[k * n_planes + p] : nullptr;
+      r.H = plane_hw[(k * n_planes + p) * 2 + 0];
+      r.W = plane_hw[(k * n_planes + p) * 2 + 1];
+      r.ca = (D == 4) ? comb4[p][0] : comb3[p][0];
+      r.cb = (D == 4) ? comb4[p][1] : comb3[p][1];
+      KP_CHECK(r.p != nullptr && r.H >= 1 && r.W >= 1, "plane (%d,%d) invalid", k, p);
+    }
+  F.n_scales = n_scales;
+  F.n_planes = n_planes;
+  F.use_mask = use_mask;
+  F.concat = concat;
+  return 0;
+}
+
+// Sample coordinate in grid_sample's [-1,1] convention.  Ray form follows the reference's op order with
+// non-contracted IEEE ops so that coordinates (hence floor() decisions) equal the torch CPU path bit for bit:
+//   pos = o + d*(start+end)/2 (rays.py:54);  (pos-aabb0)/(aabb1-aabb0) (scene_box.py:64-65);  [*2-1];  t*2-1.
+__device__ __forceinline__ void load_point(const KpPoints& P, int64_t m, float pt[4]) {
+  if (P.pts != nullptr) {
+#pragma unroll
+    for (int d = 0; d < 4; ++d) pt[d] = d < P.D ? P.pts[m * P.D + d] : 0.f;
+    return;
+  }
+  const int64_t n = m / P.S;
+  const float t = __fadd_rn(P.starts[m], P.ends[m]);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float v = __fdiv_rn(__fmul_rn(P.directions[n * 3 + d], t), 2.f);
+    float pos = __fadd_rn(P.origins[n * 3 + d], v);
+    float q = __fdiv_rn(__fsub_rn(pos, P.aabb[d]), __fsub_rn(P.aabb[3 + d], P.aabb[d]));
+    pt[d] = P.norm_mode ? __fsub_rn(__fmul_rn(q, 2.f), 1.f) : q;
+  }
+  pt[3] = (P.D == 4 && P.times != nullptr) ? __fsub_rn(__fmul_rn(P.times[n], 2.f), 1.f) : 0.f;
+}
+
+// ATen grid_sampler_2d, bilinear / padding border / align_corners=True.
+struct Bilerp {
+  int o00, o01, o10, o11;  // texel indices (y*W+x)
+  float w00, w01, w10, w11;
+};
+__device__ __forceinline__ Bilerp bilerp_setup(float x, float y, int W, int H) {
+  float ix = __fmul_rn(__fdiv_rn(__fadd_rn(x, 1.f), 2.f), (float)(W - 1));
+  float iy = __fmul_rn(__fdiv_rn(__fadd_rn(y, 1.f), 2.f), (float)(H - 1));
+  ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+  const float fx = floorf(ix), fy = floorf(iy);
+  int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+  float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  if (x1 > W - 1) { x1 = W - 1; wx1 = 0.f; }  // out-of-range corner contributes nothing
+  if (y1 > H - 1) { y1 = H - 1; wy1 = 0.f; }
+  Bilerp b;
+  b.o00 = y0 * W + x0; b.o01 = y0 * W + x1; b.o10 = y1 * W + x0; b.o11 = y1 * W + x1;
+  b.w00 = wx0 * wy0; b.w01 = wx1 * wy0; b.w10 = wx0 * wy1; b.w11 = wx1 * wy1;
+  return b;
+}
+
+__device__ __forceinline__ float4 bilerp_combine(const Bilerp& b, float4 v00, float4 v01, float4 v10, float4 v11) {
+  float4 r = scale4(v00, b.w00);
+  r = fma4(v01, b.w01, r);
+  r = fma4(v10, b.w10, r);
+  r = fma4(v11, b.w11, r);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Forward gather.  C/4 lanes per sample, float4 per lane.
+// ---------------------------------------------------------------------------------------------------
+template <int C, int NP>
+__global__ void __launch_bounds__(256) hexplane_fwd_kernel(const __grid_constant__ FieldRef F,
+                                                            const __grid_constant__ KpPoints P, int64_t M,
+                                                            float* __restrict__ out) {
+  constexpr int LPS = C / 4;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = gt / LPS;
+  const int c4 = (int)(gt % LPS) * 4;
+  if (m >= M) return;
+  float pt[4];
+  load_point(P, m, pt);
+  const int out_stride = F.concat ? F.n_scales * C : C;
+  float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < F.n_scales; ++k) {
+    Bilerp b[NP];
+    float4 v[NP][4];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const PlaneRef& pr = F.pl[k * KP_MAX_PLANES + p];
+      b[p] = bilerp_setup(pt[pr.ca], pt[pr.cb], pr.W, pr.H);
+      if ((F.use_mask >> p) & 1u) {
+        const float* base = pr.p + c4;
+        v[p][0] = ldg4(base + (int64_t)b[p].o00 * C);
+        v[p][1] = ldg4(base + (int64_t)b[p].o01 * C);
+        v[p][2] = ldg4(base + (int64_t)b[p].o10 * C);
+        v[p][3] = ldg4(base + (int64_t)b[p].o11 * C);
+      }
+    }
+    float4 acc = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if ((F.use_mask >> p) & 1u) acc = mul4(acc, bilerp_combine(b[p], v[p][0], v[p][1], v[p][2], v[p][3]));
+    if (F.concat) {
+      *reinterpret_cast<float4*>(out + m * out_stride + k * C + c4) = acc;
+    } else {
+      total.x += acc.x; total.y += acc.y; total.z += acc.z; total.w += acc.w;
+    }
+  }
+  if (!F.concat) *reinterpret_cast<float4*>(out + m * out_stride + c4) = total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward scatter: d plane_p[corner] += w_corner * g * prod_{q != p} interp_q.
+// ---------------------------------------------------------------------------------------------------
+template <int C, int NP>
+__global__ void __launch_bounds__(256) hexplane_bwd_kernel(const __grid_constant__ FieldRef F,
+                                                            const __grid_constant__ KpPoints P, int64_t M,
+                                                            const float* __restrict__ grad_out) {
+  constexpr int LPS = C / 4;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = gt / LPS;
+  const int c4 = (int)(gt % LPS) * 4;
+  if (m >= M) return;
+  float pt[4];
+  load_point(P, m, pt);
+  const int out_stride = F.concat ? F.n_scales * C : C;
+  for (int k = 0; k < F.n_scales; ++k) {
+    const float4 g = ldg4(grad_out + m * out_stride + (F.concat ? k * C : 0) + c4);
+    Bilerp b[NP];
+    float4 val[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const PlaneRef& pr = F.pl[k * KP_MAX_PLANES + p];
+      b[p] = bilerp_setup(pt[pr.ca], pt[pr.cb], pr.W, pr.H);
+      val[p] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if ((F.use_mask >> p) & 1u) {
+        const float* base = pr.p + c4;
+        val[p] = bilerp_combine(b[p], ldg4(base + (int64_t)b[p].o00 * C), ldg4(base + (int64_t)b[p].o01 * C),
+                                ldg4(base + (int64_t)b[p].o10 * C), ldg4(base + (int64_t)b[p].o11 * C));
+      }
+    }
+    // prefix/suffix products: others[p] = prod_{q != p} val[q]
+    float4 pre[NP], suf[NP];
+    pre[0] = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int p = 1; p < NP; ++p) pre[p] = mul4(pre[p - 1], val[p - 1]);
+    suf[NP - 1] = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int p = NP - 2; p >= 0; --p) suf[p] = mul4(suf[p + 1], val[p + 1]);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const PlaneRef& pr = F.pl[k * KP_MAX_PLANES + p];
+      if (!((F.use_mask >> p) & 1u) || pr.g == nullptr) continue;
+      const float4 gp = mul4(g, mul4(pre[p], suf[p]));
+      float* gb = pr.g + c4;
+      if (b[p].w00 != 0.f) red_add_v4(gb + (int64_t)b[p].o00 * C, scale4(gp, b[p].w00));
+      if (b[p].w01 != 0.f) red_add_v4(gb + (int64_t)b[p].o01 * C, scale4(gp, b[p].w01));
+      if (b[p].w10 != 0.f) red_add_v4(gb + (int64_t)b[p].o10 * C, scale4(gp, b[p].w10));
+      if (b[p].w11 != 0.f) red_add_v4(gb + (int64_t)b[p].o11 * C, scale4(gp, b[p].w11));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused proposal density field (single scale, small C): one thread per sample.
+// ---------------------------------------------------------------------------------------------------
+template <int C, int NP>
+__device__ __forceinline__ void density_features(const FieldRef& F, const float pt[4], float val[NP][C], Bilerp b[NP]) {
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const PlaneRef& pr = F.pl[p];
+    b[p] = bilerp_setup(pt[pr.ca], pt[pr.cb], pr.W, pr.H);
+    if ((F.use_mask >> p) & 1u) {
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q) {
+        const float* base = pr.p + q * 4;
+        float4 r = bilerp_combine(b[p], ldg4(base + (int64_t)b[p].o00 * C), ldg4(base + (int64_t)b[p].o01 * C),
+                                  ldg4(base + (int64_t)b[p].o10 * C), ldg4(base + (int64_t)b[p].o11 * C));
+        val[p][q * 4 + 0] = r.x; val[p][q * 4 + 1] = r.y; val[p][q * 4 + 2] = r.z; val[p][q * 4 + 3] = r.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) val[p][c] = 1.f;
+    }
+  }
+}
+
+template <int C, int NP>
+__global__ void __launch_bounds__(128) density_field_fwd_kernel(const __grid_constant__ FieldRef F,
+                                                                 const __grid_constant__ KpPoints P, int64_t M,
+                                                                 const float* __restrict__ w1, const float* __restrict__ w2,
+                                                                 int hidden, int relu, float* __restrict__ density) {
+  extern __shared__ float smem[];
+  float* s_w1 = smem;               // [hidden][C]
+  float* s_w2 = smem + hidden * C;  // [hidden]
+  for (int i = threadIdx.x; i < hidden * C; i += blockDim.x) s_w1[i] = w1[i];
+  for (int i = threadIdx.x; i < hidden; i += blockDim.x) s_w2[i] = w2[i];
+  __syncthreads();
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float pt[4];
+    load_point(P, m, pt);
+    float val[NP][C];
+    Bilerp b[NP];
+    density_features<C, NP>(F, pt, val, b);
+    float f[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float a = 1.f;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) a *= val[p][c];
+      f[c] = a;
+    }
+    float raw = 0.f;
+    for (int j = 0; j < hidden; ++j) {
+      float pre = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) pre = fmaf(s_w1[j * C + c], f[c], pre);
+      if (relu) pre = fmaxf(pre, 0.f);
+      raw = fmaf(s_w2[j], pre, raw);
+    }
+    density[m] = expf(raw);
+  }
+}
+
+// Backward.  Weight gradients: each warp stages its 32 samples' pre-activations / features / upstream
+// gradients in shared memory, then lane l owns hidden units {2l, 2l+1} (for hidden=64) and reduces over the
+// 32 samples into registers; registers are flushed with one atomicAdd per weight per block at the end.
+template <int C, int NP, int HIDDEN>
+__global__ void __launch_bounds__(128) density_field_bwd_kernel(const __grid_constant__ FieldRef F,
+                                                                 const __grid_constant__ KpPoints P, int64_t M,
+                                                                 const float* __restrict__ w1, const float* __restrict__ w2,
+                                                                 int relu, const float* __restrict__ grad_density,
+                                                                 float* __restrict__ grad_w1, float* __restrict__ grad_w2) {
+  constexpr int WARPS = 4;
+  constexpr int JPL = HIDDEN / 32;  // hidden units per lane
+  extern __shared__ float smem[];
+  float* s_w1 = smem;                            // [HIDDEN][C]
+  float* s_w2 = s_w1 + HIDDEN * C;               // [HIDDEN]
+  float* s_pre = s_w2 + HIDDEN;                  // [WARPS][32][HIDDEN+1]
+  float* s_f = s_pre + WARPS * 32 * (HIDDEN + 1);  // [WARPS][32][C]
+  float* s_g = s_f + WARPS * 32 * C;             // [WARPS][32]
+  float* s_acc = s_g + WARPS * 32;               // [HIDDEN*C + HIDDEN] block accumulators
+  for (int i = threadIdx.x; i < HIDDEN * C; i += blockDim.x) s_w1[i] = w1[i];
+  for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s_w2[i] = w2[i];
+  for (int i = threadIdx.x; i < HIDDEN * C + HIDDEN; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my_pre = s_pre + warp * 32 * (HIDDEN + 1);
+  float* my_f = s_f + warp * 32 * C;
+  float* my_g = s_g + warp * 32;
+  float acc_w1[JPL][C], acc_w2[JPL];
+#pragma unroll
+  for (int j = 0; j < JPL; ++j) {
+    acc_w2[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc_w1[j][c] = 0.f;
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t M_pad = (M + 31) / 32 * 32;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M_pad; m += stride) {
+    const bool valid = m < M;
+    float pt[4] = {0.f, 0.f, 0.f, 0.f};
+    float val[NP][C];
+    Bilerp b[NP];
+    float f[C], df[C];
+    float graw = 0.f;
+    if (valid) {
+      load_point(P, m, pt);
+      density_features<C, NP>(F, pt, val, b);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float a = 1.f;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) a *= val[p][c];
+        f[c] = a;
+        df[c] = 0.f;
+      }
+      float raw = 0.f;
+      for (int j = 0; j < HIDDEN; ++j) {
+        float pre = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) pre = fmaf(s_w1[j * C + c], f[c], pre);
+        my_pre[lane * (HIDDEN + 1) + j] = pre;
+        raw = fmaf(s_w2[j], relu ? fmaxf(pre, 0.f) : pre, raw);
+      }
+      // trunc_exp backward (activations.py:37-39)
+      graw = grad_density[m] * expf(fminf(fmaxf(raw, -15.f), 15.f));
+      for (int j = 0; j < HIDDEN; ++j) {
+        const float pre = my_pre[lane * (HIDDEN + 1) + j];
+        const float dpre = (relu && !(pre > 0.f)) ? 0.f : graw * s_w2[j];
+#pragma unroll
+        for (int c = 0; c < C; ++c) df[c] = fmaf(dpre, s_w1[j * C + c], df[c]);
+      }
+    } else {
+      for (int j = 0; j < HIDDEN; ++j) my_pre[lane * (HIDDEN + 1) + j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) f[c] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) my_f[lane * C + c] = f[c];
+    my_g[lane] = graw;
+    __syncwarp();
+    // weight-gradient reduction over the warp's 32 samples
+    for (int s = 0; s < 32; ++s) {
+      const float gs = my_g[s];
+      float fs[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) fs[c] = my_f[s * C + c];
+#pragma unroll
+      for (int j = 0; j < JPL; ++j) {
+        const int jj = lane + 32 * j;
+        const float pre = my_pre[s * (HIDDEN + 1) + jj];
+        const float h = relu ? fmaxf(pre, 0.f) : pre;
+        const float dpre = (relu && !(pre > 0.f)) ? 0.f : gs * s_w2[jj];
+        acc_w2[j] = fmaf(gs, h, acc_w2[j]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc_w1[j][c] = fmaf(dpre, fs[c], acc_w1[j][c]);
+      }
+    }
+    __syncwarp();
+    // plane gradients
+    if (valid) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const PlaneRef& pr = F.pl[p];
+        if (!((F.use_mask >> p) & 1u) || pr.g == nullptr) continue;
+        float gp[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float a = df[c];
+#pragma unroll
+          for (int q = 0; q < NP; ++q)
+            if (q != p) a *= val[q][c];
+          gp[c] = a;
+        }
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+          const float4 g4 = make_float4(gp[q * 4], gp[q * 4 + 1], gp[q * 4 + 2], gp[q * 4 + 3]);
+          float* gb = pr.g + q * 4;
+          if (b[p].w00 != 0.f) red_add_v4(gb + (int64_t)b[p].o00 * C, scale4(g4, b[p].w00));
+          if (b[p].w01 != 0.f) red_add_v4(gb + (int64_t)b[p].o01 * C, scale4(g4, b[p].w01));
+          if (b[p].w10 != 0.f) red_add_v4(gb + (int64_t)b[p].o10 * C, scale4(g4, b[p].w10));
+          if (b[p].w11 != 0.f) red_add_v4(gb + (int64_t)b[p].o11 * C, scale4(g4, b[p].w11));
+        }
+      }
+    }
+  }
+  // flush register accumulators: warps -> block smem -> global
+#pragma unroll
+  for (int j = 0; j < JPL; ++j) {
+    const int jj = lane + 32 * j;
+    atomicAdd(&s_acc[HIDDEN * C + jj], acc_w2[j]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) atomicAdd(&s_acc[jj * C + c], acc_w1[j][c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HIDDEN * C; i += blockDim.x) red_add_f32(grad_w1 + i, s_acc[i]);
+  for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) red_add_f32(grad_w2 + i, s_acc[HIDDEN * C + i]);
+}
+
+template <int C>
+static int launch_hexplane(bool bwd, const FieldRef& F, const KpPoints& P, int64_t M, const float* grad_out, float* out,
+                           cudaStream_t st) {
+  constexpr int LPS = C / 4;
+  const int64_t blocks = ceil_div(M * LPS, 256);
+  if (blocks == 0) return 0;
+  KP_CHECK(blocks < (1ll << 31), "hexplane: M too large");
+  if (F.n_planes == 6) {
+    if (!bwd) hexplane_fwd_kernel<C, 6><<<(unsigned)blocks, 256, 0, st>>>(F, P, M, out);
+    else hexplane_bwd_kernel<C, 6><<<(unsigned)blocks, 256, 0, st>>>(F, P, M, grad_out);
+  } else {
+    if (!bwd) hexplane_fwd_kernel<C, 3><<<(unsigned)blocks, 256, 0, st>>>(F, P, M, out);
+    else hexplane_bwd_kernel<C, 3><<<(unsigned)blocks, 256, 0, st>>>(F, P, M, grad_out);
+  }
+  KP_LAUNCH_CHECK("hexplane");
+  return 0;
+}
+
+static int dispatch_hexplane(bool bwd, int C, const FieldRef& F, const KpPoints& P, int64_t M, const float* grad_out,
+                             float* out, cudaStream_t st) {
+  switch (C) {
+    case 4: return launch_hexplane<4>(bwd, F, P, M, grad_out, out, st);
+    case 8: return launch_hexplane<8>(bwd, F, P, M, grad_out, out, st);
+    case 16: return launch_hexplane<16>(bwd, F, P, M, grad_out, out, st);
+    case 32: return launch_hexplane<32>(bwd, F, P, M, grad_out, out, st);
+    case 64: return launch_hexplane<64>(bwd, F, P, M, grad_out, out, st);
+    default: set_error("hexplane: feature dim C=%d unsupported (4,8,16,32,64)", C); return 1;
+  }
+}
+
+static int check_points(const KpPoints* P, int64_t M) {
+  KP_CHECK(P != nullptr, "points is NULL");
+  KP_CHECK(P->D == 3 || P->D == 4, "points.D=%d must be 3 or 4", P->D);
+  if (P->pts == nullptr) {
+    KP_CHECK(P->origins && P->directions && P->starts && P->ends, "ray-form points need origins/directions/starts/ends");
+    KP_CHECK(P->S >= 1 && M % P->S == 0, "M=%lld not a multiple of S=%d", (long long)M, P->S);
+    KP_CHECK(P->D == 3 || P->times != nullptr, "dynamic field (D=4) needs times");
+  }
+  return 0;
+}
+
+}  // namespace kp
+
+using namespace kp;
+
+extern "C" int kp_hexplane_fwd(const float* const* plane_ptrs, const int32_t* plane_hw, int n_scales, int n_planes,
+                               int C, const KpPoints* points, int64_t M, int concat, uint32_t use_mask, float* out,
+                               void* stream) {
+  if (check_points(points, M)) return 1;
+  KP_CHECK(out != nullptr || M == 0, "hexplane_fwd: out is NULL");
+  FieldRef F;
+  if (fill_field(F, plane_ptrs, nullptr, plane_hw, n_scales, n_planes, points->D, use_mask, concat)) return 1;
+  return dispatch_hexplane(false, C, F, *points, M, nullptr, out, as_stream(stream));
+}
+
+extern "C" int kp_hexplane_bwd(const float* const* plane_ptrs, float* const* grad_plane_ptrs, const int32_t* plane_hw,
+                               int n_scales, int n_planes, int C, const KpPoints* points, int64_t M, int concat,
+                               uint32_t use_mask, const float* grad_out, void* stream) {
+  if (check_points(points, M)) return 1;
+  KP_CHECK(grad_out != nullptr || M == 0, "hexplane_bwd: grad_out is NULL");
+  KP_CHECK(grad_plane_ptrs != nullptr, "hexplane_bwd: grad_plane_ptrs is NULL");
+  FieldRef F;
+  if (fill_field(F, plane_ptrs, grad_plane_ptrs, plane_hw, n_scales, n_planes, points->D, use_mask, concat)) return 1;
+  return dispatch_hexplane(true, C, F, *points, M, grad_out, nullptr, as_stream(stream));
+}
+
+template <int C>
+static int launch_density(bool bwd, const FieldRef& F, const KpPoints& P, int64_t M, const float* w1, const float* w2,
+                          int hidden, int relu, float* density, const float* grad_density, float* gw1, float* gw2,
+                          cudaStream_t st) {
+  if (M == 0) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!bwd) {
+    const size_t smem = (size_t)(hidden * C + hidden) * sizeof(float);
+    const int64_t blocks = std::min<int64_t>(ceil_div(M, 128), (int64_t)sms * 16);
+    if (F.n_planes == 6)
+      density_field_fwd_kernel<C, 6><<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, hidden, relu, density);
+    else
+      density_field_fwd_kernel<C, 3><<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, hidden, relu, density);
+  } else {
+    KP_CHECK(hidden == 64, "density_field_bwd: hidden=%d unsupported (64)", hidden);
+    constexpr int HIDDEN = 64;
+    const size_t smem =
+        (size_t)(HIDDEN * C + HIDDEN + 4 * 32 * (HIDDEN + 1) + 4 * 32 * C + 4 * 32 + HIDDEN * C + HIDDEN) * sizeof(float);
+    const int64_t blocks = std::min<int64_t>(ceil_div(M, 128), (int64_t)sms * 4);
+    if (F.n_planes == 6) {
+      auto kern = density_field_bwd_kernel<C, 6, HIDDEN>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, relu, grad_density, gw1, gw2);
+    } else {
+      auto kern = density_field_bwd_kernel<C, 3, HIDDEN>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, relu, grad_density, gw1, gw2);
+    }
+  }
+  KP_LAUNCH_CHECK("density_field");
+  return 0;
+}
+
+static int dispatch_density(bool bwd, int C, const FieldRef& F, const KpPoints& P, int64_t M, const float* w1,
+                            const float* w2, int hidden, int relu, float* density, const float* grad_density, float* gw1,
+                            float* gw2, cudaStream_t st) {
+  switch (C) {
+    case 4: return launch_density<4>(bwd, F, P, M, w1, w2, hidden, relu, density, grad_density, gw1, gw2, st);
+    case 8: return launch_density<8>(bwd, F, P, M, w1, w2, hidden, relu, density, grad_density, gw1, gw2, st);
+    case 16: return launch_density<16>(bwd, F, P, M, w1, w2, hidden, relu, density, grad_density, gw1, gw2, st);
+    default: set_error("density_field: feature dim C=%d unsupported (4,8,16)", C); return 1;
+  }
+}
+
+extern "C" int kp_density_field_fwd(const float* const* plane_ptrs, const int32_t* plane_hw, int n_planes, int C,
+                                    const float* w1, const float* w2, int hidden, int relu, const KpPoints* points,
+                                    int64_t M, uint32_t use_mask, float* density, void* stream) {
+  if (check_points(points, M)) return 1;
+  KP_CHECK(w1 && w2 && hidden >= 1 && hidden <= 256, "density_field_fwd: bad MLP arguments");
+  FieldRef F;
+  if (fill_field(F, plane_ptrs, nullptr, plane_hw, 1, n_planes, points->D, use_mask, 0)) return 1;
+  return dispatch_density(false, C, F, *points, M, w1, w2, hidden, relu, density, nullptr, nullptr, nullptr,
+                          as_stream(stream));
+}
+
+extern "C" int kp_density_field_bwd(const float* const* plane_ptrs, float* const* grad_plane_ptrs,
+                                    const int32_t* plane_hw, int n_planes, int C, const float* w1, const float* w2,
+                                    int hidden, int relu, const KpPoints* points, int64_t M, uint32_t use_mask,
+                                    const float* grad_density, float* grad_w1, float* grad_w2, void* stream) {
+  if (check_points(points, M)) return 1;
+  KP_CHECK(w1 && w2 && grad_w1 && grad_w2 && grad_density, "density_field_bwd: NULL argument");
+  KP_CHECK(grad_plane_ptrs != nullptr, "density_field_bwd: grad_plane_ptrs is NULL");
+  FieldRef F;
+  if (fill_field(F, plane_ptrs, grad_plane_ptrs, plane_hw, 1, n_planes, points->D, use_mask, 0)) return 1;
+  return dispatch_density(true, C, F, *points, M, w1, w2, hidden, relu, nullptr, grad_density, grad_w1, grad_w2,
+                          as_stream(stream));
+}

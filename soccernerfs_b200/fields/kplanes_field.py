@@ -1,0 +1,289 @@
+"""K-Planes field and proposal density field on the B200 kernels.
+
+Same constructor arguments, parameter names/shapes and method surface as NS/fields/kplanes_field.py:129-463
+(``KPlanesField.get_density/get_outputs/forward``, ``KPlanesDensityField.density_fn/get_density``,
+``interpolate_kplanes``, ``init_kplanes_field``), so the reference's ``KPlanesModel`` can use them unchanged.
+Differences, all internal:
+  * plane parameters keep the logical shape [1,C,H,W] but are stored channel-last ([H][W][C] in memory);
+  * the 6*K ``F.grid_sample`` calls + Hadamard + cat run as one gather kernel (one scatter kernel backward);
+  * the tiny-cuda-nn decoders are bias-free fp32 MLPs (``FusedMLP``) executed by the decoder kernels.
+There is no CPU path: calling these modules with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Collection, Iterable, List, Optional, Sequence
+
+import torch
+from torch import nn
+from torch.nn.parameter import Parameter
+
+from .. import ops
+from ..cameras.rays import Frustums, RaySamples
+from ..data.scene_box import SceneBox
+from .base_field import Field, FieldHeadNames
+
+TIME_PLANES = (2, 4, 5)  # XT, YT, ZT in combinations(range(4), 2) order (kplanes_field.py:62-64)
+
+
+def get_normalized_directions(directions: torch.Tensor) -> torch.Tensor:
+    """SH encoding input range [0,1] (kplanes_field.py:39-44)."""
+    return (directions + 1.0) / 2.0
+
+
+def init_kplanes_field(out_dim: int, reso: Sequence[int], a: float = 0.1, b: float = 0.5) -> nn.ParameterList:
+    """k-choose-2 planes of one scale: plane (i,j) has shape [1, out_dim, reso[j], reso[i]]; time planes = 1,
+    space planes ~ U(a,b) (kplanes_field.py:47-74).  Memory is channel-last."""
+    has_time = len(reso) == 4
+    grids = nn.ParameterList()
+    for comb in itertools.combinations(range(len(reso)), 2):
+        plane = ops.new_plane(out_dim, reso[comb[1]], reso[comb[0]])
+        if has_time and 3 in comb:
+            nn.init.ones_(plane)
+        else:
+            nn.init.uniform_(plane, a=a, b=b)
+        grids.append(nn.Parameter(plane))
+    return grids
+
+
+def _use_mask(n_planes: int, freeze_time_planes: bool) -> int:
+    mask = (1 << n_planes) - 1
+    if freeze_time_planes and n_planes == 6:
+        for p in TIME_PLANES:  # frozen time planes are skipped entirely (kplanes_field.py:97-100)
+            mask &= ~(1 << p)
+    return mask
+
+
+def _maybe_frozen(grids: Iterable[torch.Tensor], freeze_space_planes: bool) -> List[torch.Tensor]:
+    grids = list(grids)
+    if not freeze_space_planes:
+        return grids
+    n = len(grids)  # space planes get no gradient (kplanes_field.py:102-105)
+    return [g.detach() if (n == 3 or i not in TIME_PLANES) else g for i, g in enumerate(grids)]
+
+
+def interpolate_kplanes(pts: torch.Tensor, ms_grids: Collection[Iterable[nn.Module]], concat_features: bool,
+                        freeze_time_planes: bool = False, freeze_space_planes: bool = False) -> torch.Tensor:
+    """Query multi-scale planes at ``pts`` [M, 3|4] in [-1,1] -> [M, K*C] / [M, C] (kplanes_field.py:77-126)."""
+    ms = [_maybe_frozen(g, freeze_space_planes) for g in ms_grids]
+    if not torch.is_grad_enabled():
+        ms = [[p.detach() for p in g] for g in ms]
+    return ops.hexplane_features(ms, ops.points_from_pts(pts), concat_features, _use_mask(len(ms[0]), freeze_time_planes))
+
+
+class FusedMLP(nn.Module):
+    """Bias-free dense stack (tcnn ``FullyFusedMLP`` semantics, fp32): ``weights[i]`` is [out_i, in_i]."""
+
+    def __init__(self, n_input_dims: int, n_output_dims: int, n_neurons: int, n_hidden_layers: int,
+                 activation: str = "ReLU", output_activation: str = "None") -> None:
+        super().__init__()
+        dims = [n_input_dims] + [n_neurons] * n_hidden_layers + [n_output_dims]
+        self.weights = nn.ParameterList()
+        for i, o in zip(dims[:-1], dims[1:]):
+            w = torch.empty(o, i)
+            nn.init.xavier_uniform_(w)
+            self.weights.append(nn.Parameter(w))
+        self.n_input_dims, self.n_output_dims = n_input_dims, n_output_dims
+        self.activation, self.output_activation = activation, output_activation
+
+
+def _ray_form(ray_samples: RaySamples):
+    """(origins [N,3], directions [N,3], starts [N,S], ends [N,S], times [N]|None) if the samples are the usual
+    per-ray broadcast of a RayBundle (RayBundle.get_ray_samples), else None."""
+    fr = ray_samples.frustums
+    if fr.offsets is not None or fr.origins.dim() < 2 or len(fr.shape) < 2:
+        return None
+    s = fr.shape[-1]
+    if s > 1 and (fr.origins.stride(-2) != 0 or fr.directions.stride(-2) != 0):
+        return None
+    times = ray_samples.times
+    if times is not None:
+        if s > 1 and times.stride(-2) != 0:
+            return None
+        times = times[..., 0, 0].reshape(-1)
+    return (fr.origins[..., 0, :].reshape(-1, 3), fr.directions[..., 0, :].reshape(-1, 3),
+            fr.starts[..., 0].reshape(-1, s), fr.ends[..., 0].reshape(-1, s), times)
+
+
+class _AabbHostMixin:
+    """Keeps a host copy of the aabb so kernel launches never sync on a device->host read."""
+
+    def _aabb6(self):
+        key = (self.aabb.data_ptr(), self.aabb._version)
+        if getattr(self, "_aabb_key", None) != key:
+            self._aabb_host = tuple(float(v) for v in self.aabb.detach().flatten().tolist())
+            self._aabb_key = key
+        return self._aabb_host
+
+
+class KPlanesField(Field, _AabbHostMixin):
+    """Multiscale hexplane radiance field (kplanes_field.py:129-370)."""
+
+    def __init__(
+        self,
+        aabb,
+        spacetime_resolution: Sequence[int] = (256, 256, 256, 150),
+        feat_dim: int = 16,
+        appearance_dim: int = 27,
+        spatial_distortion=None,
+        num_images: int = 0,
+        multiscale_res: Optional[Sequence[int]] = None,
+        concat_features_across_scales: bool = False,
+        linear_decoder: bool = True,
+        linear_decoder_layers: Optional[int] = None,
+        use_appearance_embedding: bool = False,
+        disable_viewing_dependent: bool = False,
+        sigma_net_layers: int = 1,
+        sigma_net_hidden_dim: int = 64,
+        rgb_net_layers: int = 2,
+        rgb_net_hidden_dim: int = 64,
+        freeze_time_planes: bool = False,
+        freeze_space_planes: bool = False,
+    ) -> None:
+        super().__init__()
+        # Out-of-scope branches of the reference: fail loudly instead of falling back.
+        if linear_decoder:
+            raise NotImplementedError("KPlanesField(linear_decoder=True) is not built yet (kplanes_field.py:219-246)")
+        if spatial_distortion is not None:
+            raise NotImplementedError("SceneContraction (bounded=False) is not built yet (kplanes_field.py:278-280)")
+        if use_appearance_embedding:
+            raise NotImplementedError("appearance embeddings are not built yet (kplanes_field.py:326-345)")
+        if sigma_net_layers != 1 or rgb_net_layers != 2:
+            raise NotImplementedError("decoder kernels are built for sigma_net_layers=1, rgb_net_layers=2")
+        self.aabb = Parameter(aabb, requires_grad=False)
+        self.spatial_distortion = None
+        self.multiscale_res_multipliers: Sequence[int] = multiscale_res or [1]
+        self.concat_features_across_scales = concat_features_across_scales
+        self.linear_decoder = False
+        self.has_time_planes = len(spacetime_resolution) == 4
+        self.feature_dim = feat_dim * len(self.multiscale_res_multipliers) if concat_features_across_scales else feat_dim
+        self.freeze_time_planes = freeze_time_planes
+        self.freeze_space_planes = freeze_space_planes
+        self.use_appearance_embedding = False
+        self.appearance_embedding = None
+        self.appearance_embedding_dim = 0
+        self.disable_viewing_dependent = disable_viewing_dependent
+
+        self.grids = nn.ModuleList()
+        for res in self.multiscale_res_multipliers:
+            resolution = [r * res for r in spacetime_resolution[:3]]
+            if len(spacetime_resolution) > 3:  # time does not get the multi-scale treatment (:181-182)
+                resolution.append(spacetime_resolution[3])
+            self.grids.append(init_kplanes_field(out_dim=feat_dim, reso=resolution))
+
+        self.geo_feat_dim = 15
+        self.sigma_net = FusedMLP(self.feature_dim, self.geo_feat_dim + 1, sigma_net_hidden_dim, sigma_net_layers)
+        self.in_dim_color = self.geo_feat_dim + (0 if disable_viewing_dependent else 16)
+        self.color_net = FusedMLP(self.in_dim_color, 3, rgb_net_hidden_dim, rgb_net_layers, output_activation="Sigmoid")
+
+    # -- helpers ---------------------------------------------------------------------------------------
+    def _points(self, ray_samples: RaySamples) -> ops.Points:
+        rf = _ray_form(ray_samples)
+        if rf is not None:
+            o, d, st, en, t = rf
+            return ops.points_from_rays(o, d, st, en, t, self._aabb6(), norm_mode=1, dynamic=self.has_time_planes and t is not None)
+        positions = ray_samples.frustums.get_positions()
+        positions = SceneBox.get_normalized_positions(positions, self.aabb) * 2.0 - 1.0
+        if self.has_time_planes and ray_samples.times is not None:
+            positions = torch.cat((positions, ray_samples.times * 2 - 1), dim=-1)
+        return ops.points_from_pts(positions.reshape(-1, positions.shape[-1]))
+
+    def _planes(self):
+        ms = [_maybe_frozen(g, self.freeze_space_planes) for g in self.grids]
+        if not torch.is_grad_enabled():
+            ms = [[p.detach() for p in g] for g in ms]
+        return ms
+
+    # -- Field surface ---------------------------------------------------------------------------------
+    def get_density(self, ray_samples: RaySamples):
+        """-> (density [N,S,1], geometry features [M,15]).  kplanes_field.py:275-312."""
+        batch = ray_samples.frustums.shape
+        points = self._points(ray_samples)
+        ms = self._planes()
+        if points.D != (4 if len(ms[0]) == 6 else 3):
+            raise RuntimeError("dynamic K-Planes field needs ray_samples.times")
+        feats = ops.hexplane_features(ms, points, self.concat_features_across_scales,
+                                      _use_mask(len(ms[0]), self.freeze_time_planes))
+        o, density = ops.sigma_net(feats, self.sigma_net.weights[0], self.sigma_net.weights[1])
+        return density.view(*batch, 1), o[:, : self.geo_feat_dim]
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-> rgb [N,S,3] (bare tensor, like kplanes_field.py:314-358)."""
+        assert density_embedding is not None
+        batch = ray_samples.frustums.shape
+        n_samples = batch[-1]
+        w3, w4, w5 = self.color_net.weights
+        if self.disable_viewing_dependent:
+            rgb = ops.color_net(None, n_samples, density_embedding, w3, w4, w5)
+        else:
+            dirs = ray_samples.frustums.directions
+            if n_samples > 1 and dirs.stride(-2) == 0:
+                rgb = ops.color_net(dirs[..., 0, :].reshape(-1, 3), n_samples, density_embedding, w3, w4, w5)
+            else:
+                rgb = ops.color_net(dirs.reshape(-1, 3), 1, density_embedding, w3, w4, w5)
+        return rgb.view(*batch, 3)
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False, mask=None, bg_color=None):
+        density, density_features = self.get_density(ray_samples)
+        rgb = self.get_outputs(ray_samples, density_features)
+        return {FieldHeadNames.DENSITY: density, FieldHeadNames.RGB: rgb}
+
+
+class KPlanesDensityField(Field, _AabbHostMixin):
+    """Proposal density field (kplanes_field.py:373-463): one fused gather + 8->64->1 MLP + trunc_exp kernel."""
+
+    def __init__(self, aabb, resolution, feature_dim, spatial_distortion=None, linear_decoder: bool = True,
+                 freeze_time_planes: bool = False, freeze_space_planes: bool = False) -> None:
+        super().__init__()
+        if spatial_distortion is not None:
+            raise NotImplementedError("SceneContraction (bounded=False) is not built yet (kplanes_field.py:436-438)")
+        self.aabb = Parameter(aabb, requires_grad=False)
+        self.spatial_distortion = None
+        self.has_time_planes = len(resolution) == 4
+        self.freeze_time_planes = freeze_time_planes
+        self.freeze_space_planes = freeze_space_planes
+        self.relu = not linear_decoder  # activation "None" when linear_decoder (:391-393)
+        self.grids = init_kplanes_field(out_dim=feature_dim, reso=resolution, a=0.1, b=0.15)
+        self.sigma_net = FusedMLP(feature_dim, 1, 64, 1, activation="ReLU" if self.relu else "None")
+
+    def density_fn(self, positions: torch.Tensor, times: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """positions [..., 3] (world), times [N,1] -> density [..., 1].  kplanes_field.py:410-432."""
+        if times is not None and len(positions.shape) == 3 and len(times.shape) == 2:
+            times = times[:, None]
+        ray_samples = RaySamples(
+            frustums=Frustums(
+                origins=positions,
+                directions=torch.ones_like(positions),
+                starts=torch.zeros_like(positions[..., :1]),
+                ends=torch.zeros_like(positions[..., :1]),
+                pixel_area=torch.ones_like(positions[..., :1]),
+            ),
+            times=times,
+        )
+        density, _ = self.get_density(ray_samples)
+        return density
+
+    def get_density(self, ray_samples: RaySamples):
+        """-> (density [N,S,1], None).  NOTE: positions are normalised to [0,1] only, not [-1,1], exactly like
+        the reference (kplanes_field.py:439-440; SURVEY.md finding 3)."""
+        batch = ray_samples.frustums.shape
+        rf = _ray_form(ray_samples)
+        if rf is not None:
+            o, d, st, en, t = rf
+            points = ops.points_from_rays(o, d, st, en, t, self._aabb6(), norm_mode=0, dynamic=self.has_time_planes and t is not None)
+        else:
+            positions = SceneBox.get_normalized_positions(ray_samples.frustums.get_positions(), self.aabb)
+            if self.has_time_planes and ray_samples.times is not None:
+                positions = torch.cat((positions, ray_samples.times * 2 - 1), dim=-1)
+            points = ops.points_from_pts(positions.reshape(-1, positions.shape[-1]))
+        grids = _maybe_frozen(self.grids, self.freeze_space_planes)
+        if not torch.is_grad_enabled():
+            grids = [p.detach() for p in grids]
+        if points.D != (4 if len(grids) == 6 else 3):
+            raise RuntimeError("dynamic K-Planes density field needs times")
+        density = ops.density_field(grids, self.sigma_net.weights[0], self.sigma_net.weights[1], points, relu=self.relu,
+                                    use_mask=_use_mask(len(grids), self.freeze_time_planes))
+        return density.view(*batch, 1), None
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None):
+        return {}

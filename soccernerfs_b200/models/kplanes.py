@@ -1,0 +1,313 @@
+"""K-Planes model on the B200 hot path.
+
+``KPlanesModelConfig`` has the reference's fields and defaults (NS/models/kplanes.py:67-177) and ``KPlanesModel``
+its surface: ``populate_modules`` :188-309, ``get_param_groups`` :311-316, ``get_training_callbacks`` :318-347,
+``get_outputs`` :349-388, ``get_metrics_dict`` :390-412, ``get_loss_dict`` :414-452.  Image-quality metrics
+(torchmetrics PSNR/SSIM/LPIPS, the RetinaNet-based DynMetric, colour maps) are evaluation tooling outside the hot
+path and are not rebuilt; ``psnr`` is computed inline.
+"""
+from __future__ import annotations
+
+import functools
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Type
+
+import numpy as np
+import torch
+from torch.nn import Parameter
+
+from ..cameras.rays import RayBundle
+from ..fields.base_field import FieldHeadNames
+from ..fields.kplanes_field import KPlanesDensityField, KPlanesField
+from ..model_components.losses import (
+    DepthLossType,
+    MSELoss,
+    depth_loss,
+    distortion_loss,
+    interlevel_loss,
+    space_tv_loss,
+    sparse_transients_loss,
+    time_smoothness_loss,
+)
+from ..model_components.ray_samplers import ProposalNetworkSampler, UniformSampler
+from ..model_components.renderers import AccumulationRenderer, DepthRenderer, MedianRGBRenderer, RGBRenderer
+from ..model_components.scene_colliders import AABBBoxCollider, NearFarCollider
+from .base_model import Model, ModelConfig, to_immutable_dict
+
+
+class TrainingCallbackLocation:
+    """NS/engine/callbacks.py:44-48."""
+
+    BEFORE_TRAIN_ITERATION = 1
+    AFTER_TRAIN_ITERATION = 2
+
+
+@dataclass
+class TrainingCallback:
+    """Callback run by the trainer before/after each iteration (NS/engine/callbacks.py:51-103)."""
+
+    where_to_run: List[int]
+    func: callable
+    update_every_num_iters: Optional[int] = None
+    iters: Optional[Tuple[int, ...]] = None
+    args: Optional[List] = None
+    kwargs: Optional[Dict] = None
+
+    def run_callback(self, step: int):
+        args, kwargs = self.args or [], self.kwargs or {}
+        if self.update_every_num_iters is not None:
+            if step % self.update_every_num_iters == 0:
+                self.func(*args, **kwargs, step=step)
+        elif self.iters is not None:
+            if step in self.iters:
+                self.func(*args, **kwargs, step=step)
+
+    def run_callback_at_location(self, step: int, location: int):
+        if location in self.where_to_run:
+            self.run_callback(step=step)
+
+
+@dataclass
+class KPlanesModelConfig(ModelConfig):
+    """K-Planes model config: field names, types and defaults of NS/models/kplanes.py:67-177."""
+
+    _target: Type = field(default_factory=lambda: KPlanesModel)
+    near_plane: float = 0.05
+    far_plane: float = 1000.0
+    bounded: bool = True
+    spacetime_resolution: Sequence[int] = (64, 64, 64, 50)
+    feature_dim: int = 32
+    multiscale_res: Sequence[int] = (1, 2, 4, 8)
+    concat_features_across_scales: bool = True
+    linear_decoder: bool = False
+    linear_decoder_layers: Optional[int] = 1
+    sigma_net_layers: int = 1
+    sigma_net_hidden_dim: int = 64
+    rgb_net_layers: int = 2
+    rgb_net_hidden_dim: int = 64
+    background_color_train: str = "random"
+    background_color_eval: str = "last_sample"
+    num_proposal_iterations: int = 2
+    use_same_proposal_network: bool = False
+    proposal_net_args_list: List[Dict] = field(
+        default_factory=lambda: [
+            {"feature_dim": 8, "resolution": [128, 128, 128, 150]},
+            {"feature_dim": 8, "resolution": [256, 256, 256, 150]},
+        ]
+    )
+    num_nerf_samples_per_ray: int = 48
+    num_proposal_samples_per_ray: Tuple[int, ...] = (256, 128)
+    use_single_jitter: bool = False
+    proposal_warmup: int = 5000
+    proposal_update_every: int = 5
+    use_proposal_weight_anneal: bool = True
+    proposal_weights_anneal_max_num_iters: int = 1000
+    proposal_weights_anneal_slope: float = 10.0
+    use_appearance_embedding: bool = False
+    appearance_embedding_dim: int = 0
+    disable_viewing_dependent: bool = False
+    loss_coefficients: Dict[str, float] = to_immutable_dict(
+        {
+            "rgb_loss": 1.0,
+            "interlevel_loss": 1.0,
+            "distortion_loss": 0.001,
+            "space_tv_loss": 0.0002,
+            "time_smoothness_loss": 0.001,
+            "sparse_transients_loss": 0.0001,
+            "space_tv_proposal_loss": 0.0002,
+            "time_smoothness_proposal_loss": 0.00001,
+            "sparse_transients_proposal_loss": 0.0001,
+            "depth_loss": 0.05,
+        }
+    )
+    is_euclidean_depth: bool = True
+    depth_sigma: float = 0.01
+    should_decay_sigma: bool = False
+    starting_depth_sigma: float = 0.2
+    sigma_decay_rate: float = 0.99985
+    depth_loss_type: DepthLossType = DepthLossType.DS_NERF
+    freeze_time_planes: bool = False
+    freeze_space_planes: bool = False
+
+
+def scale_dict(dictionary: Dict, coefficients: Dict[str, float]) -> Dict:
+    """NS/utils/misc.py:116-129."""
+    for key in dictionary:
+        if key in coefficients:
+            dictionary[key] *= coefficients[key]
+    return dictionary
+
+
+class KPlanesModel(Model):
+    config: KPlanesModelConfig
+
+    def populate_modules(self):
+        super().populate_modules()
+        cfg = self.config
+        if not cfg.bounded:
+            raise NotImplementedError("bounded=False (SceneContraction + NearFarCollider sampling) is not built yet")
+        self.field = KPlanesField(
+            self.scene_box.aabb,
+            feat_dim=cfg.feature_dim,
+            spacetime_resolution=cfg.spacetime_resolution,
+            concat_features_across_scales=cfg.concat_features_across_scales,
+            multiscale_res=cfg.multiscale_res,
+            use_appearance_embedding=cfg.use_appearance_embedding,
+            appearance_dim=cfg.appearance_embedding_dim,
+            spatial_distortion=None,
+            linear_decoder=cfg.linear_decoder,
+            linear_decoder_layers=cfg.linear_decoder_layers,
+            num_images=self.num_train_data,
+            disable_viewing_dependent=cfg.disable_viewing_dependent,
+            sigma_net_layers=cfg.sigma_net_layers,
+            sigma_net_hidden_dim=cfg.sigma_net_hidden_dim,
+            rgb_net_layers=cfg.rgb_net_layers,
+            rgb_net_hidden_dim=cfg.rgb_net_hidden_dim,
+            freeze_time_planes=cfg.freeze_time_planes,
+            freeze_space_planes=cfg.freeze_space_planes,
+        )
+        self.depth_sigma = torch.tensor([cfg.starting_depth_sigma if cfg.should_decay_sigma else cfg.depth_sigma])
+
+        self.density_fns = []
+        num_prop_nets = cfg.num_proposal_iterations
+        self.proposal_networks = torch.nn.ModuleList()
+        common = dict(spatial_distortion=None, linear_decoder=cfg.linear_decoder, freeze_time_planes=cfg.freeze_time_planes,
+                      freeze_space_planes=cfg.freeze_space_planes)
+        if cfg.use_same_proposal_network:
+            assert len(cfg.proposal_net_args_list) == 1, "Only one proposal network is allowed."
+            network = KPlanesDensityField(self.scene_box.aabb, **common, **cfg.proposal_net_args_list[0])
+            self.proposal_networks.append(network)
+            self.density_fns.extend([network.density_fn for _ in range(num_prop_nets)])
+        else:
+            for i in range(num_prop_nets):
+                args = cfg.proposal_net_args_list[min(i, len(cfg.proposal_net_args_list) - 1)]
+                self.proposal_networks.append(KPlanesDensityField(self.scene_box.aabb, **common, **args))
+            self.density_fns.extend([network.density_fn for network in self.proposal_networks])
+
+        def update_schedule(step):
+            return np.clip(np.interp(step, [0, cfg.proposal_warmup], [0, cfg.proposal_update_every]), 1,
+                           cfg.proposal_update_every)
+
+        initial_sampler = UniformSampler(single_jitter=cfg.use_single_jitter)  # bounded => uniform (kplanes.py:262-264)
+        self.proposal_sampler = ProposalNetworkSampler(
+            num_nerf_samples_per_ray=cfg.num_nerf_samples_per_ray,
+            num_proposal_samples_per_ray=cfg.num_proposal_samples_per_ray,
+            num_proposal_network_iterations=cfg.num_proposal_iterations,
+            single_jitter=cfg.use_single_jitter,
+            update_sched=update_schedule,
+            initial_sampler=initial_sampler,
+        )
+        self.collider = AABBBoxCollider(scene_box=self.scene_box)
+        self.renderer_rgb = RGBRenderer(background_color=cfg.background_color_train)
+        self.renderer_accumulation = AccumulationRenderer()
+        self.renderer_depth = DepthRenderer()
+        self.medianrgb_renderer = MedianRGBRenderer()
+        self.rgb_loss = MSELoss()
+        self.temporal_distortion = len(cfg.spacetime_resolution) == 4  # viewer flag (kplanes.py:297)
+
+    def get_param_groups(self) -> Dict[str, List[Parameter]]:
+        return {
+            "proposal_networks": list(self.proposal_networks.parameters()),
+            "fields": list(self.field.parameters()),
+        }
+
+    def get_training_callbacks(self, training_callback_attributes=None) -> List[TrainingCallback]:
+        callbacks = []
+        if self.config.use_proposal_weight_anneal:
+            n_iters = self.config.proposal_weights_anneal_max_num_iters
+
+            def set_anneal(step):  # https://arxiv.org/pdf/2111.12077.pdf eq. 18 (kplanes.py:326-331)
+                train_frac = np.clip(step / n_iters, 0, 1)
+                b = self.config.proposal_weights_anneal_slope
+                self.proposal_sampler.set_anneal((b * train_frac) / ((b - 1) * train_frac + 1))
+
+            callbacks.append(TrainingCallback(where_to_run=[TrainingCallbackLocation.BEFORE_TRAIN_ITERATION],
+                                              update_every_num_iters=1, func=set_anneal))
+            callbacks.append(TrainingCallback(where_to_run=[TrainingCallbackLocation.AFTER_TRAIN_ITERATION],
+                                              update_every_num_iters=1, func=self.proposal_sampler.step_cb))
+        return callbacks
+
+    def get_outputs(self, ray_bundle: RayBundle):
+        density_fns = self.density_fns
+        if ray_bundle.times is not None:
+            density_fns = [functools.partial(f, times=ray_bundle.times) for f in density_fns]
+        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=density_fns)
+        field_out = self.field(ray_samples)
+        weights = ray_samples.get_weights(field_out[FieldHeadNames.DENSITY])
+        weights_list.append(weights)
+        ray_samples_list.append(ray_samples)
+
+        self.renderer_rgb.background_color = (
+            self.config.background_color_train if self.training else self.config.background_color_eval
+        )
+        rgb = self.renderer_rgb(rgb=field_out[FieldHeadNames.RGB], weights=weights)
+        accumulation = self.renderer_accumulation(weights)
+        depth = self.renderer_depth(weights, ray_samples)
+        median_rgb = self.medianrgb_renderer(rgb=field_out[FieldHeadNames.RGB], weights=weights)
+        outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth, "median_rgb": median_rgb}
+        if self.training:
+            outputs["weights_list"] = weights_list
+            outputs["ray_samples_list"] = ray_samples_list
+        for i in range(self.config.num_proposal_iterations):
+            outputs[f"prop_depth_{i}"] = self.renderer_depth(weights=weights_list[i], ray_samples=ray_samples_list[i])
+        if ray_bundle.metadata is not None and "directions_norm" in ray_bundle.metadata:
+            outputs["directions_norm"] = ray_bundle.metadata["directions_norm"]
+        return outputs
+
+    def get_metrics_dict(self, outputs, batch):
+        metrics_dict = {}
+        image = batch["image"].to(self.device)
+        with torch.no_grad():  # PSNR with data_range 1.0 (torchmetrics.PeakSignalNoiseRatio in the reference)
+            metrics_dict["psnr"] = -10.0 * torch.log10(torch.mean((outputs["rgb"] - image) ** 2))
+        if "depth_image" in batch.keys() and self.training and self.config.loss_coefficients["depth_loss"] > 0:
+            metrics_dict["depth_loss"] = 0.0
+            sigma = self._get_sigma().to(self.device)
+            termination_depth = batch["depth_image"].to(self.device)
+            for i in range(len(outputs["weights_list"])):
+                metrics_dict["depth_loss"] += depth_loss(
+                    weights=outputs["weights_list"][i],
+                    ray_samples=outputs["ray_samples_list"][i],
+                    termination_depth=termination_depth,
+                    predicted_depth=outputs["depth"],
+                    sigma=sigma,
+                    directions_norm=outputs["directions_norm"],
+                    is_euclidean=self.config.is_euclidean_depth,
+                    depth_loss_type=self.config.depth_loss_type,
+                ) / len(outputs["weights_list"])
+        return metrics_dict
+
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
+        device = outputs["rgb"].device
+        image = batch["image"].to(device)
+        loss_dict = {"rgb_loss": self.rgb_loss(image, outputs["rgb"])}
+        loss_coef = self.config.loss_coefficients
+        if self.training:
+            if "distortion_loss" in loss_coef:
+                loss_dict["distortion_loss"] = distortion_loss(outputs["weights_list"], outputs["ray_samples_list"])
+            if "interlevel_loss" in loss_coef:
+                loss_dict["interlevel_loss"] = interlevel_loss(outputs["weights_list"], outputs["ray_samples_list"])
+            ms_grids_nerf = self.field.grids
+            ms_grids_prop = [p.grids for p in self.proposal_networks]
+            if "space_tv_loss" in loss_coef:
+                loss_dict["space_tv_loss"] = space_tv_loss(ms_grids_nerf)
+            if "space_tv_proposal_loss" in loss_coef:
+                loss_dict["space_tv_proposal_loss"] = space_tv_loss(ms_grids_prop)
+            if len(self.config.spacetime_resolution) > 3 and not self.config.freeze_time_planes:
+                if "sparse_transients_loss" in loss_coef:
+                    loss_dict["sparse_transients_loss"] = sparse_transients_loss(ms_grids_nerf)
+                if "sparse_transients_proposal_loss" in loss_coef:
+                    loss_dict["sparse_transients_proposal_loss"] = sparse_transients_loss(ms_grids_prop)
+                if "time_smoothness_loss" in loss_coef:
+                    loss_dict["time_smoothness_loss"] = time_smoothness_loss(ms_grids_nerf)
+                if "time_smoothness_proposal_loss" in loss_coef:
+                    loss_dict["time_smoothness_proposal_loss"] = time_smoothness_loss(ms_grids_prop)
+            if "depth_image" in batch.keys() and loss_coef["depth_loss"] > 0:
+                loss_dict["depth_loss"] = metrics_dict["depth_loss"]
+        return scale_dict(loss_dict, loss_coef)
+
+    def _get_sigma(self):
+        if not self.config.should_decay_sigma:
+            return self.depth_sigma
+        self.depth_sigma = torch.maximum(self.config.sigma_decay_rate * self.depth_sigma,
+                                         torch.tensor([self.config.depth_sigma]))
+        return self.depth_sigma

@@ -1,0 +1,540 @@
+"""torch.autograd.Function shims over the C-ABI kernels (one Function per fused op).
+
+Planes keep the reference's logical shape ``[1, C, H, W]`` (state-dict compatible with
+NS/fields/kplanes_field.py:67) but live in ``torch.channels_last`` memory, i.e. physically ``[H][W][C]`` --
+the layout the gather/scatter kernels need for 16-byte feature loads.  All kernels run in fp32 on the
+current CUDA stream; under ``torch.autocast`` inputs are promoted to fp32 exactly as the reference's
+``_TruncExp`` does with ``custom_fwd(cast_inputs=torch.float32)`` (NS/field_components/activations.py:29).
+"""
+from __future__ import annotations
+
+from ctypes import c_float, c_int32, c_void_p
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, f32c, ptr, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# plane layout helpers
+# ------------------------------------------------------------------------------------------------
+def new_plane(c: int, h: int, w: int, device=None) -> torch.Tensor:
+    """Empty fp32 plane of logical shape [1,C,H,W], physical layout [H][W][C]."""
+    return torch.empty((1, h, w, c), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+
+
+def is_channel_last(p: torch.Tensor) -> bool:
+    return p.dim() == 4 and p.shape[0] == 1 and p.permute(0, 2, 3, 1).is_contiguous()
+
+
+def as_channel_last(p: torch.Tensor) -> torch.Tensor:
+    """Return ``p`` (logical [1,C,H,W]) with physical [H][W][C] memory; copies only if it is not already."""
+    if p.dtype != torch.float32:
+        p = p.float()
+    if is_channel_last(p):
+        return p
+    return p.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def _plane_ptrs(planes: Sequence[Optional[torch.Tensor]]):
+    arr = (c_void_p * len(planes))()
+    for i, p in enumerate(planes):
+        arr[i] = 0 if p is None else p.data_ptr()
+    return arr
+
+
+def _plane_hw(planes: Sequence[torch.Tensor]):
+    arr = (c_int32 * (2 * len(planes)))()
+    for i, p in enumerate(planes):
+        arr[2 * i], arr[2 * i + 1] = p.shape[2], p.shape[3]
+    return arr
+
+
+def zeros_like_planes(planes: Sequence[torch.Tensor], need: Sequence[bool]) -> List[Optional[torch.Tensor]]:
+    """One flat zero-filled buffer carved into channel-last views (a single memset for all plane gradients)."""
+    total = sum(p.numel() for p, n in zip(planes, need) if n)
+    if total == 0:
+        return [None] * len(planes)
+    flat = torch.zeros(total, dtype=torch.float32, device=planes[0].device)
+    out, off = [], 0
+    for p, n in zip(planes, need):
+        if not n:
+            out.append(None)
+            continue
+        _, c, h, w = p.shape
+        out.append(flat[off: off + p.numel()].view(1, h, w, c).permute(0, 3, 1, 2))
+        off += p.numel()
+    return out
+
+
+@dataclass
+class Points:
+    """Sample coordinates: explicit ``pts`` [M,D] in [-1,1], or ray form (see include/kplanes_b200.h)."""
+
+    D: int
+    pts: Optional[torch.Tensor] = None
+    origins: Optional[torch.Tensor] = None  # [N,3]
+    directions: Optional[torch.Tensor] = None  # [N,3]
+    starts: Optional[torch.Tensor] = None  # [N,S]
+    ends: Optional[torch.Tensor] = None  # [N,S]
+    times: Optional[torch.Tensor] = None  # [N]
+    S: int = 1
+    norm_mode: int = 1
+    aabb: Tuple[float, ...] = (0.0,) * 6
+
+    @property
+    def M(self) -> int:
+        return self.pts.shape[0] if self.pts is not None else self.starts.numel()
+
+    def tensors(self) -> List[Optional[torch.Tensor]]:
+        return [self.pts, self.origins, self.directions, self.starts, self.ends, self.times]
+
+    def struct(self) -> _lib.KpPoints:
+        return _lib.make_points(pts=self.pts, origins=self.origins, directions=self.directions, starts=self.starts,
+                                ends=self.ends, times=self.times, D=self.D, S=self.S, norm_mode=self.norm_mode,
+                                aabb=self.aabb)
+
+
+def points_from_pts(pts: torch.Tensor) -> Points:
+    pts = f32c(pts.detach())
+    return Points(D=pts.shape[-1], pts=pts.view(-1, pts.shape[-1]))
+
+
+def points_from_rays(origins, directions, starts, ends, times, aabb, norm_mode: int, dynamic: bool) -> Points:
+    """origins/directions [N,3], starts/ends [N,S], times [N] or None."""
+    return Points(
+        D=4 if dynamic else 3, origins=f32c(origins.detach()), directions=f32c(directions.detach()),
+        starts=f32c(starts.detach()), ends=f32c(ends.detach()),
+        times=None if (times is None or not dynamic) else f32c(times.detach()).view(-1),
+        S=starts.shape[-1], norm_mode=norm_mode, aabb=tuple(aabb),
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# (a1-a3) multiscale hexplane features
+# ------------------------------------------------------------------------------------------------
+class _Hexplane(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points: Points, n_scales: int, concat: bool, use_mask: int, *planes):
+        planes = [as_channel_last(p.detach()) for p in planes]
+        n_planes = len(planes) // n_scales
+        c = planes[0].shape[1]
+        m = points.M
+        out = torch.empty((m, n_scales * c if concat else c), dtype=torch.float32, device=planes[0].device)
+        pstruct = points.struct()
+        call("kp_hexplane_fwd", _plane_ptrs(planes), _plane_hw(planes), n_scales, n_planes, c, pstruct, m, int(concat),
+             use_mask, ptr(out), stream_ptr())
+        ctx.points, ctx.cfg, ctx.planes = points, (n_scales, n_planes, c, concat, use_mask), planes
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        n_scales, n_planes, c, concat, use_mask = ctx.cfg
+        planes, points = ctx.planes, ctx.points
+        need = [ctx.needs_input_grad[4 + i] and bool((use_mask >> (i % n_planes)) & 1) for i in range(len(planes))]
+        grads = zeros_like_planes(planes, need)
+        if any(need):
+            call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(grads), _plane_hw(planes), n_scales, n_planes, c,
+                 points.struct(), points.M, int(concat), use_mask, ptr(f32c(grad_out)), stream_ptr())
+        return (None, None, None, None, *grads)
+
+
+def hexplane_features(ms_planes: Sequence[Sequence[torch.Tensor]], points: Points, concat: bool,
+                      use_mask: int = 0x3F) -> torch.Tensor:
+    """interpolate_kplanes (NS/fields/kplanes_field.py:77-126) -> [M, K*C] (concat) or [M, C] (sum)."""
+    flat = [p for grids in ms_planes for p in grids]
+    return _Hexplane.apply(points, len(ms_planes), concat, use_mask, *flat)
+
+
+# ------------------------------------------------------------------------------------------------
+# (a6) fused proposal density field
+# ------------------------------------------------------------------------------------------------
+class _DensityField(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points: Points, relu: bool, use_mask: int, w1, w2, *planes):
+        planes = [as_channel_last(p.detach()) for p in planes]
+        w1c, w2c = f32c(w1.detach()), f32c(w2.detach()).view(-1)
+        c, hidden, m = planes[0].shape[1], w1c.shape[0], points.M
+        density = torch.empty((m,), dtype=torch.float32, device=w1c.device)
+        call("kp_density_field_fwd", _plane_ptrs(planes), _plane_hw(planes), len(planes), c, ptr(w1c), ptr(w2c), hidden,
+             int(relu), points.struct(), m, use_mask, ptr(density), stream_ptr())
+        ctx.points, ctx.cfg, ctx.planes, ctx.w = points, (relu, use_mask, c, hidden), planes, (w1c, w2c, w2.shape)
+        return density
+
+    @staticmethod
+    def backward(ctx, grad_density):
+        relu, use_mask, c, hidden = ctx.cfg
+        planes, points = ctx.planes, ctx.points
+        w1c, w2c, w2_shape = ctx.w
+        n_planes = len(planes)
+        need = [ctx.needs_input_grad[5 + i] and bool((use_mask >> i) & 1) for i in range(n_planes)]
+        grads = zeros_like_planes(planes, need)
+        gw = torch.zeros(w1c.numel() + w2c.numel(), dtype=torch.float32, device=w1c.device)
+        gw1, gw2 = gw[: w1c.numel()].view_as(w1c), gw[w1c.numel():]
+        call("kp_density_field_bwd", _plane_ptrs(planes), _plane_ptrs(grads), _plane_hw(planes), n_planes, c, ptr(w1c),
+             ptr(w2c), hidden, int(relu), points.struct(), points.M, use_mask, ptr(f32c(grad_density)), ptr(gw1), ptr(gw2),
+             stream_ptr())
+        return (None, None, None, gw1, gw2.view(w2_shape), *grads)
+
+
+def density_field(planes: Sequence[torch.Tensor], w1: torch.Tensor, w2: torch.Tensor, points: Points, relu: bool = True,
+                  use_mask: int = 0x3F) -> torch.Tensor:
+    """KPlanesDensityField.get_density (kplanes_field.py:434-460) fused: -> density [M]."""
+    return _DensityField.apply(points, relu, use_mask, w1, w2, *planes)
+
+
+# ------------------------------------------------------------------------------------------------
+# (a4, a5) decoders
+# ------------------------------------------------------------------------------------------------
+class _SigmaNet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, w1, w2):
+        x, w1c, w2c = f32c(feats.detach()), f32c(w1.detach()), f32c(w2.detach())
+        m, k = x.shape
+        h = w1c.shape[0]
+        assert w1c.shape == (h, k) and w2c.shape == (16, h), "sigma_net: w1 [H,K], w2 [16,H]"
+        h1 = torch.empty((m, h), dtype=torch.float32, device=x.device)
+        o = torch.empty((m, 16), dtype=torch.float32, device=x.device)
+        density = torch.empty((m,), dtype=torch.float32, device=x.device)
+        call("kp_sigma_net_fwd", ptr(x), ptr(w1c), ptr(w2c), m, k, h, ptr(h1), ptr(o), ptr(density), stream_ptr())
+        ctx.save_for_backward(x, w1c, w2c, h1, o)
+        ctx.mark_non_differentiable()
+        return o, density
+
+    @staticmethod
+    def backward(ctx, grad_o, grad_density):
+        x, w1c, w2c, h1, o = ctx.saved_tensors
+        m, k = x.shape
+        h = w1c.shape[0]
+        gx = torch.empty_like(x)
+        gw = torch.zeros(w1c.numel() + w2c.numel(), dtype=torch.float32, device=x.device)
+        gw1, gw2 = gw[: w1c.numel()].view_as(w1c), gw[w1c.numel():].view_as(w2c)
+        scratch = torch.empty_like(h1)
+        call("kp_sigma_net_bwd", ptr(x), ptr(w1c), ptr(w2c), m, k, h, ptr(h1), ptr(o),
+             ptr(None if grad_density is None else f32c(grad_density)), ptr(None if grad_o is None else f32c(grad_o)),
+             ptr(gx), ptr(gw1), ptr(gw2), ptr(scratch), stream_ptr())
+        return gx, gw1, gw2
+
+
+def sigma_net(feats: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (o [M,16] = [geo 15 | sigma_raw], density [M] = trunc_exp(sigma_raw)).  kplanes_field.py:302-311."""
+    return _SigmaNet.apply(feats, w1, w2)
+
+
+class _ColorNet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, directions, samples_per_ray: int, geo, w3, w4, w5):
+        w3c, w4c, w5c = f32c(w3.detach()), f32c(w4.detach()), f32c(w5.detach())
+        g = geo.detach()
+        if g.dtype != torch.float32:
+            g = g.float()
+        # geo may be the [:, :15] view of the sigma net's [M,16] output: pass the row stride instead of copying
+        if not (g.dim() == 2 and g.shape[1] == 15 and g.stride(1) == 1 and g.stride(0) in (15, 16)):
+            g = g.reshape(-1, 15).contiguous()
+        m, ldgeo = g.shape[0], g.stride(0)
+        h2d = w3c.shape[0]
+        view_dep = directions is not None
+        d = f32c(directions.detach()) if view_dep else None
+        assert w3c.shape == (h2d, 31 if view_dep else 15) and w4c.shape == (h2d, h2d) and w5c.shape == (3, h2d)
+        dev = g.device
+        cin = torch.empty((m, 32 if view_dep else 16), dtype=torch.float32, device=dev)
+        h2 = torch.empty((m, h2d), dtype=torch.float32, device=dev)
+        h3 = torch.empty((m, h2d), dtype=torch.float32, device=dev)
+        rgb = torch.empty((m, 3), dtype=torch.float32, device=dev)
+        call("kp_color_net_fwd", ptr(d), samples_per_ray, c_void_p(g.data_ptr()), ldgeo, ptr(w3c), ptr(w4c), ptr(w5c), m,
+             h2d, ptr(cin), ptr(h2), ptr(h3), ptr(rgb), stream_ptr())
+        ctx.save_for_backward(cin, h2, h3, rgb, w3c, w4c, w5c)
+        ctx.view_dep = view_dep
+        return rgb
+
+    @staticmethod
+    def backward(ctx, grad_rgb):
+        cin, h2, h3, rgb, w3c, w4c, w5c = ctx.saved_tensors
+        m, h2d = h2.shape
+        dev = h2.device
+        go = torch.empty((m, 16), dtype=torch.float32, device=dev)
+        gw = torch.zeros(w3c.numel() + w4c.numel() + w5c.numel(), dtype=torch.float32, device=dev)
+        a, b = w3c.numel(), w3c.numel() + w4c.numel()
+        gw3, gw4, gw5 = gw[:a].view_as(w3c), gw[a:b].view_as(w4c), gw[b:].view_as(w5c)
+        sa, sb = torch.empty_like(h2), torch.empty_like(h2)
+        call("kp_color_net_bwd", int(ctx.view_dep), ptr(cin), ptr(h2), ptr(h3), ptr(rgb), ptr(w3c), ptr(w4c), ptr(w5c), m,
+             h2d, ptr(f32c(grad_rgb)), ptr(go), ptr(gw3), ptr(gw4), ptr(gw5), ptr(sa), ptr(sb), stream_ptr())
+        return None, None, go[:, :15], gw3, gw4, gw5
+
+
+def color_net(directions: Optional[torch.Tensor], samples_per_ray: int, geo: torch.Tensor, w3, w4, w5) -> torch.Tensor:
+    """[SH4(dir) | geo] -> rgb [M,3] (sigmoid).  directions [N,3] per ray or None (disable_viewing_dependent)."""
+    return _ColorNet.apply(directions, samples_per_ray, geo, w3, w4, w5)
+
+
+# ------------------------------------------------------------------------------------------------
+# (a13, a7, a8) ray setup and resampling (no gradients: bins are detached, ray_samplers.py:357)
+# ------------------------------------------------------------------------------------------------
+def aabb_intersect(origins, directions, aabb6: Sequence[float], near_plane: float):
+    o, d = f32c(origins), f32c(directions)
+    n = o.shape[0]
+    nears = torch.empty((n,), dtype=torch.float32, device=o.device)
+    fars = torch.empty_like(nears)
+    call("kp_aabb_intersect", ptr(o), ptr(d), n, (c_float * 6)(*[float(v) for v in aabb6]), float(near_plane), ptr(nears),
+         ptr(fars), stream_ptr())
+    return nears, fars
+
+
+_LINSPACE_CACHE = {}
+
+
+def _cached_linspace(key, start, end, steps, device):
+    k = (key, steps, str(device))
+    if k not in _LINSPACE_CACHE:
+        _LINSPACE_CACHE[k] = torch.linspace(start, end, steps, device="cpu").to(device)
+    return _LINSPACE_CACHE[k]
+
+
+def uniform_bins(nears, fars, num_samples: int, t_rand: Optional[torch.Tensor], spacing: int = 0):
+    """-> (spacing_bins [N,S+1], euclidean_bins [N,S+1]).  ray_samplers.py:79-126."""
+    nears, fars = f32c(nears).view(-1), f32c(fars).view(-1)
+    n = nears.shape[0]
+    lin = _cached_linspace("uni", 0.0, 1.0, num_samples + 1, nears.device)
+    sb = torch.empty((n, num_samples + 1), dtype=torch.float32, device=nears.device)
+    eb = torch.empty_like(sb)
+    stride = 0
+    if t_rand is not None:
+        t_rand = f32c(t_rand)
+        stride = 0 if t_rand.shape[-1] == 1 else num_samples + 1
+    call("kp_uniform_bins", ptr(lin), ptr(t_rand), stride, ptr(nears), ptr(fars), n, num_samples, spacing, ptr(sb), ptr(eb),
+         stream_ptr())
+    return sb, eb
+
+
+def pdf_resample(weights, existing_bins, nears, fars, num_samples: int, rand: Optional[torch.Tensor],
+                 histogram_padding: float = 0.01, eps: float = 1e-5, spacing: int = 0, want_inds: bool = False,
+                 want_cdf: bool = False):
+    """-> (spacing_bins [N,S_out+1], euclidean_bins, inds int64 | None, cdf | None).  ray_samplers.py:274-369."""
+    w, eb_in = f32c(weights.detach()), f32c(existing_bins.detach())
+    nears, fars = f32c(nears).view(-1), f32c(fars).view(-1)
+    n, s_in = w.shape
+    nb = num_samples + 1
+    u_base = _cached_linspace("pdf", 0.0, 1.0 - (1.0 / nb), nb, w.device)
+    sb = torch.empty((n, nb), dtype=torch.float32, device=w.device)
+    eb = torch.empty_like(sb)
+    inds = torch.empty((n, nb), dtype=torch.int64, device=w.device) if want_inds else None
+    cdf = torch.empty((n, s_in + 1), dtype=torch.float32, device=w.device) if want_cdf else None
+    stride = 0
+    if rand is not None:
+        rand = f32c(rand)
+        stride = 0 if rand.shape[-1] == 1 else nb
+    call("kp_pdf_resample", ptr(w), ptr(eb_in), s_in, ptr(u_base), ptr(rand), stride, ptr(nears), ptr(fars), n, num_samples,
+         float(histogram_padding), float(eps), spacing, ptr(cdf), ptr(sb), ptr(eb), ptr(inds), stream_ptr())
+    return sb, eb, inds, cdf
+
+
+# ------------------------------------------------------------------------------------------------
+# (a10-a12) compositing
+# ------------------------------------------------------------------------------------------------
+class _Weights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, deltas, densities):
+        d, s = f32c(deltas.detach()), f32c(densities.detach())
+        n, ns = d.shape
+        w = torch.empty_like(d)
+        call("kp_weights_fwd", ptr(d), ptr(s), n, ns, ptr(w), stream_ptr())
+        ctx.save_for_backward(d, s)
+        return w
+
+    @staticmethod
+    def backward(ctx, gw):
+        d, s = ctx.saved_tensors
+        gs = torch.empty_like(s)
+        call("kp_weights_bwd", ptr(d), ptr(s), ptr(f32c(gw)), d.shape[0], d.shape[1], ptr(gs), stream_ptr())
+        return None, gs
+
+
+def get_weights(deltas: torch.Tensor, densities: torch.Tensor) -> torch.Tensor:
+    """[N,S] x [N,S] -> [N,S].  RaySamples.get_weights, NS/cameras/rays.py:127-149."""
+    return _Weights.apply(deltas, densities)
+
+
+class _CompositeRGB(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, rgb, bg, bg_mode: int, nan_to_num: bool):
+        w, c = f32c(weights.detach()), f32c(rgb.detach())
+        n, s = w.shape
+        b = None if bg is None else f32c(bg.detach().expand(n, 3))
+        comp = torch.empty((n, 3), dtype=torch.float32, device=w.device)
+        call("kp_render_fwd", ptr(w), ptr(c), ptr(None), ptr(b), bg_mode, int(nan_to_num), n, s, ptr(comp), ptr(None), ptr(None),
+             ptr(None), stream_ptr())
+        ctx.save_for_backward(w, c, b)
+        ctx.bg_mode = bg_mode
+        return comp
+
+    @staticmethod
+    def backward(ctx, gcomp):
+        w, c, b = ctx.saved_tensors
+        n, s = w.shape
+        gw = torch.empty_like(w)
+        grgb = torch.empty_like(c) if ctx.needs_input_grad[1] else None
+        call("kp_render_bwd", ptr(w), ptr(c), ptr(b), ctx.bg_mode, n, s, ptr(f32c(gcomp)), ptr(None), ptr(gw), ptr(grgb),
+             stream_ptr())
+        return gw, grgb, None, None, None
+
+
+def composite_rgb(weights, rgb, background, nan_to_num: bool = False) -> torch.Tensor:
+    """weights [N,S], rgb [N,S,3], background: "last_sample" or tensor [N,3]/[3] -> [N,3].  renderers.py:71-116."""
+    if isinstance(background, str):
+        assert background == "last_sample"
+        return _CompositeRGB.apply(weights, rgb, None, 1, nan_to_num)
+    return _CompositeRGB.apply(weights, rgb, background, 0, nan_to_num)
+
+
+class _Accumulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights):
+        w = f32c(weights.detach())
+        n, s = w.shape
+        acc = torch.empty((n,), dtype=torch.float32, device=w.device)
+        call("kp_render_fwd", ptr(w), ptr(None), ptr(None), ptr(None), 0, 0, n, s, ptr(None), ptr(acc), ptr(None), ptr(None),
+             stream_ptr())
+        ctx.shape = (n, s)
+        return acc
+
+    @staticmethod
+    def backward(ctx, gacc):
+        return f32c(gacc).view(-1, 1).expand(*ctx.shape)
+
+
+def accumulate(weights: torch.Tensor) -> torch.Tensor:
+    """sum_s w -> [N].  AccumulationRenderer, renderers.py:197-223."""
+    return _Accumulate.apply(weights)
+
+
+def median_index(weights: torch.Tensor) -> torch.Tensor:
+    """clamp(searchsorted(cumsum(w), 0.5, "left"), 0, S-1) -> int64 [N].  renderers.py:260-263."""
+    w = f32c(weights.detach())
+    n, s = w.shape
+    idx = torch.empty((n,), dtype=torch.int64, device=w.device)
+    call("kp_render_fwd", ptr(w), ptr(None), ptr(None), ptr(None), 0, 0, n, s, ptr(None), ptr(None), ptr(idx), ptr(None),
+         stream_ptr())
+    return idx
+
+
+def expected_depth(weights: torch.Tensor, steps: torch.Tensor) -> torch.Tensor:
+    """sum w*steps / (sum w + 1e-10), unclipped, no grad -> [N].  renderers.py:266-281."""
+    w, st = f32c(weights.detach()), f32c(steps.detach())
+    n, s = w.shape
+    out = torch.empty((n,), dtype=torch.float32, device=w.device)
+    call("kp_render_fwd", ptr(w), ptr(None), ptr(st), ptr(None), 0, 0, n, s, ptr(None), ptr(None), ptr(None), ptr(out),
+         stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# (a14) distortion / interlevel losses
+# ------------------------------------------------------------------------------------------------
+class _Distortion(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sdist, w):
+        t, wc = f32c(sdist.detach()), f32c(w.detach())
+        n, s = wc.shape
+        loss = torch.empty((n,), dtype=torch.float32, device=wc.device)
+        call("kp_distortion_fwd", ptr(t), ptr(wc), n, s, ptr(loss), stream_ptr())
+        ctx.save_for_backward(t, wc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        t, wc = ctx.saved_tensors
+        gw = torch.empty_like(wc)
+        call("kp_distortion_bwd", ptr(t), ptr(wc), ptr(f32c(g)), wc.shape[0], wc.shape[1], ptr(gw), stream_ptr())
+        return None, gw
+
+
+def distortion_per_ray(sdist: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """lossfun_distortion (losses.py:125-136): sdist [N,S+1], w [N,S] -> [N]."""
+    return _Distortion.apply(sdist, w)
+
+
+class _Interlevel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c, w, cp, wp):
+        cc, wc, cpc, wpc = f32c(c.detach()), f32c(w.detach()), f32c(cp.detach()), f32c(wp.detach())
+        n, s = wc.shape
+        sp = wpc.shape[1]
+        loss = torch.empty((n, s), dtype=torch.float32, device=wc.device)
+        call("kp_interlevel_fwd", ptr(cc), ptr(wc), ptr(cpc), ptr(wpc), n, s, sp, ptr(loss), stream_ptr())
+        ctx.save_for_backward(cc, wc, cpc, wpc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        cc, wc, cpc, wpc = ctx.saved_tensors
+        gwp = torch.empty_like(wpc)
+        call("kp_interlevel_bwd", ptr(cc), ptr(wc), ptr(cpc), ptr(wpc), ptr(f32c(g)), wc.shape[0], wc.shape[1], wpc.shape[1],
+             ptr(gwp), stream_ptr())
+        return None, None, None, gwp
+
+
+def lossfun_outer(c, w, cp, wp) -> torch.Tensor:
+    """lossfun_outer (losses.py:78-95): final-level (c [N,S+1], w [N,S]) vs proposal (cp [N,Sp+1], wp [N,Sp]) -> [N,S]."""
+    return _Interlevel.apply(c, w, cp, wp)
+
+
+# ------------------------------------------------------------------------------------------------
+# (a15) plane regularisers
+# ------------------------------------------------------------------------------------------------
+class _PlaneReg(torch.autograd.Function):
+    """sums[p] = (sum dh^2, sum dw^2, sum (d2h)^2, sum |1-t|) for each plane p, masked by terms[p]."""
+
+    @staticmethod
+    def forward(ctx, terms: Tuple[int, ...], *planes):
+        planes = [as_channel_last(p.detach()) for p in planes]
+        sums = torch.zeros((len(planes), 4), dtype=torch.float64, device=planes[0].device)
+        st = stream_ptr()
+        for i, (p, t) in enumerate(zip(planes, terms)):
+            if t:
+                _, c, h, w = p.shape
+                call("kp_plane_reg_fwd", ptr_cl(p), h, w, c, t, c_void_p(sums.data_ptr() + 32 * i), st)
+        ctx.planes, ctx.terms = planes, terms
+        return sums.float()
+
+    @staticmethod
+    def backward(ctx, gsums):
+        g = f32c(gsums)
+        st = stream_ptr()
+        grads = []
+        for i, (p, t) in enumerate(zip(ctx.planes, ctx.terms)):
+            if not t or not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            _, c, h, w = p.shape
+            gp = new_plane(c, h, w, p.device)
+            call("kp_plane_reg_bwd", ptr_cl(p), h, w, c, c_void_p(g.data_ptr() + 16 * i), t, 0, ptr_cl(gp), st)
+            grads.append(gp)
+        return (None, *grads)
+
+
+def ptr_cl(p: torch.Tensor) -> c_void_p:
+    if not p.is_cuda:
+        raise RuntimeError("soccernerfs_b200 kernels need CUDA tensors (there is no CPU path)")
+    return c_void_p(p.data_ptr())
+
+
+def plane_reg_sums(planes: Sequence[torch.Tensor], terms: Sequence[int]) -> torch.Tensor:
+    """-> [P,4] raw sums; bit i of terms[p] selects sum i (see include/kplanes_b200.h)."""
+    return _PlaneReg.apply(tuple(int(t) for t in terms), *planes)
+
+
+# ------------------------------------------------------------------------------------------------
+# (f1) Adam
+# ------------------------------------------------------------------------------------------------
+def adam_step_(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
+    """In-place torch.optim.Adam update on (possibly channel-last) dense fp32 tensors sharing one memory layout."""
+    n = param.numel()
+    for t in (grad, exp_avg, exp_avg_sq):
+        if t.stride() != param.stride() or t.numel() != n:
+            raise RuntimeError("adam_step_: param/grad/state must share one dense layout")
+    call("kp_adam_step", c_void_p(param.data_ptr()), c_void_p(grad.data_ptr()), c_void_p(exp_avg.data_ptr()),
+         c_void_p(exp_avg_sq.data_ptr()), n, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+         float(grad_scale), stream_ptr())

@@ -1,0 +1,96 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels involved)."""
+import numpy as np
+import pytest
+import torch
+
+from soccernerfs_b200.cameras.rays import Frustums, RayBundle, RaySamples
+from soccernerfs_b200.data.scene_box import SceneBox
+from soccernerfs_b200.models.kplanes import KPlanesModelConfig
+
+
+def test_frustum_positions_known_answer():
+    """Reference KAT: REF/nerfstudio/tests/cameras/test_rays.py:11-30."""
+    fr = Frustums(origins=torch.ones((5, 3)), directions=torch.tensor([[0.0, 1.0, 0.0]] * 5) * torch.tensor([1.0, 2.5, 1.0]),
+                  starts=torch.ones((5, 1)), ends=torch.ones((5, 1)), pixel_area=torch.ones((5, 1)))
+    fr = Frustums(origins=torch.tensor([0.0, 1.0, 2.0]).expand(5, 3), directions=torch.tensor([0.0, 1.0, 0.0]).expand(5, 3),
+                  starts=torch.full((5, 1), 2.0), ends=torch.full((5, 1), 3.0), pixel_area=torch.ones((5, 1)))
+    assert torch.allclose(fr.get_positions(), torch.tensor([0.0, 3.5, 2.0]).expand(5, 3))
+
+
+def test_tensor_dataclass_broadcast_and_index():
+    rb = RayBundle(origins=torch.zeros(4, 3), directions=torch.ones(4, 3), pixel_area=torch.ones(1, 1), times=torch.rand(4, 1))
+    assert rb.shape == (4,) and rb.pixel_area.shape == (4, 1) and len(rb) == 4
+    rs = rb.get_ray_samples(bin_starts=torch.zeros(4, 7, 1), bin_ends=torch.ones(4, 7, 1))
+    assert rs.shape == (4, 7) and rs.frustums.origins.shape == (4, 7, 3) and rs.times.shape == (4, 7, 1)
+    assert rs.frustums.origins.stride(-2) == 0  # per-ray broadcast is a view (the kernels rely on this)
+    assert rs[1:3].shape == (2, 7) and rs[..., 0].shape == (4,)
+    assert rb.flatten()[1:3].origins.shape == (2, 3)
+    img = RayBundle(origins=torch.zeros(2, 3, 3), directions=torch.ones(2, 3, 3), pixel_area=torch.ones(2, 3, 1))
+    assert len(img) == 6 and img.get_row_major_sliced_ray_bundle(1, 5).shape == (4,)
+    with pytest.raises(RuntimeError):
+        rb[0] = rb[1]
+
+
+def test_config_defaults_match_reference():
+    """NS/models/kplanes.py:67-177."""
+    c = KPlanesModelConfig()
+    assert c.spacetime_resolution == (64, 64, 64, 50) and c.feature_dim == 32 and c.multiscale_res == (1, 2, 4, 8)
+    assert c.num_proposal_samples_per_ray == (256, 128) and c.num_nerf_samples_per_ray == 48
+    assert c.proposal_net_args_list[0] == {"feature_dim": 8, "resolution": [128, 128, 128, 150]}
+    assert c.loss_coefficients["distortion_loss"] == 0.001 and c.loss_coefficients["time_smoothness_proposal_loss"] == 0.00001
+    assert c.background_color_train == "random" and c.background_color_eval == "last_sample" and c.bounded
+
+
+def test_model_surface_and_state_dict_layout():
+    m = KPlanesModelConfig(spacetime_resolution=(8, 8, 8, 4), multiscale_res=(1, 2),
+                           proposal_net_args_list=[{"feature_dim": 8, "resolution": [8, 8, 8, 4]}]).setup(
+        scene_box=SceneBox(aabb=torch.tensor([[-1.0] * 3, [1.0] * 3])), num_train_data=3)
+    groups = m.get_param_groups()
+    assert set(groups) == {"proposal_networks", "fields"}
+    sd = m.state_dict()
+    # reference checkpoint layout: field.grids.<scale>.<plane> of logical shape [1,C,H,W]
+    assert sd["field.grids.1.2"].shape == (1, 32, 4, 16) and sd["proposal_networks.0.grids.5"].shape == (1, 8, 4, 8)
+    assert sd["field.grids.0.0"].permute(0, 2, 3, 1).is_contiguous()  # channel-last memory
+    assert float(sd["field.grids.0.2"].min()) == 1.0  # time planes initialised to 1
+    assert 0.1 <= float(sd["field.grids.0.0"].min()) and float(sd["field.grids.0.0"].max()) <= 0.5
+    assert 0.1 <= float(sd["proposal_networks.0.grids.0"].min()) and float(sd["proposal_networks.0.grids.0"].max()) <= 0.15
+    # loading a reference-layout (NCHW-contiguous) checkpoint keeps channel-last storage
+    ref_like = {k: v.contiguous() for k, v in sd.items()}
+    m.load_state_dict(ref_like)
+    assert m.field.grids[0][0].permute(0, 2, 3, 1).is_contiguous()
+
+
+def test_proposal_schedule_and_anneal_callbacks():
+    """update schedule kplanes.py:254-259; anneal kplanes.py:326-331; sampler state ray_samplers.py:546-557, :573."""
+    m = KPlanesModelConfig(spacetime_resolution=(8, 8, 8, 4), multiscale_res=(1,),
+                           proposal_net_args_list=[{"feature_dim": 8, "resolution": [8, 8, 8, 4]}]).setup(
+        scene_box=SceneBox(aabb=torch.tensor([[-1.0] * 3, [1.0] * 3])), num_train_data=3)
+    cbs = m.get_training_callbacks(None)
+    assert len(cbs) == 2
+    cbs[0].run_callback_at_location(step=100, location=1)
+    frac = 100 / 1000
+    assert m.proposal_sampler._anneal == pytest.approx(10 * frac / (9 * frac + 1))
+    cbs[1].run_callback_at_location(step=100, location=2)
+    assert m.proposal_sampler._step == 100 and m.proposal_sampler._steps_since_update == 1
+    sched = m.proposal_sampler.update_sched
+    assert sched(0) == 1 and sched(5000) == 5 and sched(2500) == pytest.approx(2.5) and sched(10**6) == 5
+
+
+def test_cosine_schedule():
+    from soccernerfs_b200.engine.optimizers import cosine_decay_factor
+
+    assert cosine_decay_factor(0, 512, 30000) == 0.0 and cosine_decay_factor(256, 512, 30000) == 0.5
+    assert cosine_decay_factor(512, 512, 30000) == pytest.approx(1.0)
+    assert cosine_decay_factor(30000, 512, 30000) == pytest.approx(0.0, abs=1e-12)
+    mid = (30000 + 512) // 2
+    assert cosine_decay_factor(mid, 512, 30000) == pytest.approx(0.5, abs=1e-3)
+
+
+def test_unbuilt_branches_fail_loudly():
+    from soccernerfs_b200.fields.kplanes_field import KPlanesField
+
+    aabb = torch.tensor([[-1.0] * 3, [1.0] * 3])
+    with pytest.raises(NotImplementedError):
+        KPlanesField(aabb, linear_decoder=True, linear_decoder_layers=1)
+    with pytest.raises(NotImplementedError):
+        KPlanesField(aabb, linear_decoder=False, use_appearance_embedding=True)
