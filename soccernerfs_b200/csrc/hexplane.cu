@@ -429,6 +429,7 @@ static int dispatch_hexplane(bool bwd, int C, const FieldRef& F, const KpPoints&
 static int check_points(const KpPoints* P, int64_t M) {
   KP_CHECK(P != nullptr, "points is NULL");
   KP_CHECK(P->D == 3 || P->D == 4, "points.D=%d must be 3 or 4", P->D);
+  if (M == 0) return 0;
   if (P->pts == nullptr) {
     KP_CHECK(P->origins && P->directions && P->starts && P->ends, "ray-form points need origins/directions/starts/ends");
     KP_CHECK(P->S >= 1 && M % P->S == 0, "M=%lld not a multiple of S=%d", (long long)M, P->S);

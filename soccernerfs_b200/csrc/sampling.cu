@@ -66,6 +66,47 @@ __global__ void uniform_bins_kernel(const float* __restrict__ lin, const float* 
   ebins[idx] = to_euclid(b, spacing_fn(nears[n], mode), spacing_fn(fars[n], mode), mode);
 }
 
+// sum_i (x[i] + pad) over one fp32 row, reproducing BIT FOR BIT what torch.sum(dim=-1) returns on CPU for a
+// contiguous fp32 row (ATen SumKernel.cpp: vectorized_inner_sum -> row_sum -> multi_row_sum with 8-lane vectors,
+// ILP factor 4 and a 4-level cascade; verified against torch 2.11 for S = 40..4096, DESIGN.md "bit-exactness").
+// The cdf that decides the searchsorted indices is normalised by this sum, so its rounding must match.
+// Lane t of the warp plays vector lane (t & 7) of ILP accumulator (t >> 3).  All lanes return the result.
+__device__ __forceinline__ float torch_cpu_row_sum(const float* __restrict__ x, int S, float pad, int lane) {
+  constexpr int V = 8, ILP = 4, LEVELS = 4;
+  const int l = lane & 7, k = lane >> 3;
+  const int vec_size = S / V, size_ilp = vec_size / ILP;
+  int clog = 0;
+  while ((1 << clog) < size_ilp) ++clog;  // CeilLog2
+  const int level_power = max(4, clog / LEVELS);
+  const int level_step = 1 << level_power, level_mask = level_step - 1;
+  float acc[LEVELS] = {0.f, 0.f, 0.f, 0.f};
+  int i = 0;
+  for (; i + level_step <= size_ilp;) {
+    for (int j = 0; j < level_step; ++j, ++i) acc[0] = __fadd_rn(acc[0], __fadd_rn(x[(i * ILP + k) * V + l], pad));
+#pragma unroll
+    for (int j = 1; j < LEVELS; ++j) {
+      acc[j] = __fadd_rn(acc[j], acc[j - 1]);
+      acc[j - 1] = 0.f;
+      if ((i & (level_mask << (j * level_power))) != 0) break;
+    }
+  }
+  for (; i < size_ilp; ++i) acc[0] = __fadd_rn(acc[0], __fadd_rn(x[(i * ILP + k) * V + l], pad));
+#pragma unroll
+  for (int j = 1; j < LEVELS; ++j) acc[0] = __fadd_rn(acc[0], acc[j]);
+  float p = acc[0];
+  // leftover whole vectors go to ILP accumulator 0, then accumulators 1..3 are folded into 0 in order
+  if (k == 0)
+    for (int v = size_ilp * ILP; v < vec_size; ++v) p = __fadd_rn(p, __fadd_rn(x[v * V + l], pad));
+  const float p1 = __shfl_sync(0xffffffffu, p, l + 8), p2 = __shfl_sync(0xffffffffu, p, l + 16),
+              p3 = __shfl_sync(0xffffffffu, p, l + 24);
+  const float q = __fadd_rn(__fadd_rn(__fadd_rn(p, p1), p2), p3);  // valid on lanes 0..7
+  float fin = 0.f;
+  for (int t = vec_size * V; t < S; ++t) fin = __fadd_rn(fin, __fadd_rn(x[t], pad));  // scalar tail first
+#pragma unroll
+  for (int v = 0; v < V; ++v) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, q, v));
+  return fin;
+}
+
 // One warp per ray.  Dynamic smem per warp: cdf[S_in+1] + existing bins[S_in+1].
 __global__ void __launch_bounds__(128) pdf_resample_kernel(
     const float* __restrict__ weights, const float* __restrict__ existing, int S_in, const float* __restrict__ u_base,
@@ -82,10 +123,9 @@ __global__ void __launch_bounds__(128) pdf_resample_kernel(
   const float* w_row = weights + n * S_in;
   const int epl = (S_in + 31) / 32;  // contiguous elements per lane
   const int i0 = lane * epl, i1 = min(S_in, i0 + epl);
-  // weights + histogram_padding (ray_samplers.py:302), row sum
+  // weights + histogram_padding (ray_samplers.py:302), row sum in torch's CPU summation order (see below)
+  float w_sum = torch_cpu_row_sum(w_row, S_in, hist_pad, lane);
   double part = 0.0;
-  for (int i = i0; i < i1; ++i) part += (double)__fadd_rn(w_row[i], hist_pad);
-  float w_sum = (float)warp_sum_d(part);
   const float padding = fmaxf(__fsub_rn(eps, w_sum), 0.f);  // relu(eps - sum)
   const float pad_each = __fdiv_rn(padding, (float)S_in);
   w_sum = __fadd_rn(w_sum, padding);
