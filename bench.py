@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- train rays/sec of the K-Planes training step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # our arm (CUDA path through the C-ABI)
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU torch path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one full training iteration on one batch of synthetic rays of the broadcast-style scene shape:
+AABB collider -> proposal sampling (256 + 128 samples, both proposal fields evaluated and trained every step)
+-> K-Planes field (48 samples) -> compositing -> rgb / distortion / interlevel / plane regularisers ->
+backward -> [NCCL all-reduce of the flat gradient bucket when N>1] -> Adam (lr 1e-2, eps 1e-12) -> cosine LR.
+Workload at N=1 = BASELINE.json configs[1] ("K-Planes default": multiscale-res 1 2 4 8, C=32, proposal sampler,
+4096 rays/step).  N>1: weak scaling, every rank owns its own 4096-ray slice of a global N*4096-ray batch.
+
+The JSON line carries: value (inputs resident in HBM), e2e (host buffers: pinned H2D of the batch and a D2H read
+of the loss inside the timed region, every step), roofline (dominant kernel, timed live with CUDA events),
+cpu_baseline (oracle port on the host cores, rank 0, N=1 only), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+RAYS_PER_RANK = 4096
+WORKLOAD = "kplanes-default(cfg2): multiscale-res 1 2 4 8, C=32, T=50, proposals [128^3,150]+[256^3,150] C=8, 256/128/48 samples, 4096 rays/rank"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist_setup(n_gpus: int):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def _make_batches(n_steps: int, n_rays: int, seed: int):
+    """Pinned host batches: (origins, directions, times, image) per step; one packed [n_rays,10] tensor each."""
+    from soccernerfs_b200.data.synthetic import synthetic_rays
+
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_steps):
+        o, d, t, _ = synthetic_rays(n_rays, gen)
+        img = torch.rand(n_rays, 3, generator=gen)
+        out.append(torch.cat([o, d, t, img], dim=-1).contiguous().pin_memory())
+    return out
+
+
+def _bundle(packed_dev):
+    from soccernerfs_b200.cameras.rays import RayBundle
+
+    n = packed_dev.shape[0]
+    rb = RayBundle(origins=packed_dev[:, 0:3].contiguous(), directions=packed_dev[:, 3:6].contiguous(),
+                   pixel_area=torch.ones(n, 1, device=packed_dev.device), times=packed_dev[:, 6:7].contiguous())
+    return rb, {"image": packed_dev[:, 7:10].contiguous()}
+
+
+ALGO_BYTES = {  # algorithmic bytes per launch at cfg2 / 4096 rays (DESIGN.md "roofline")
+    "kp_hexplane_fwd": 4096 * 48 * 4 * 6 * 4 * 32 * 4,          # K*P*4 corners*C*4 B per field sample
+    "kp_hexplane_bwd": 2 * 4096 * 48 * 4 * 6 * 4 * 32 * 4,      # re-read + reduction payload
+    "kp_density_field_fwd": 4096 * 6 * 4 * 8 * 4,                # per proposal sample: 768 B (x S below)
+    "kp_density_field_bwd": 2 * 4096 * 6 * 4 * 8 * 4,
+}
+
+
+def run_ours(args):
+    rank, world, local = _dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: the product path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+
+    from soccernerfs_b200 import _lib
+    from soccernerfs_b200.data.scene_box import SceneBox
+    from soccernerfs_b200.data.synthetic import perturb_time_planes, synthetic_rays
+    from soccernerfs_b200.engine.trainer import TrainStep
+    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
+
+    _lib.load()
+    torch.manual_seed(42 + rank)
+    _, _, _, aabb = synthetic_rays(4, torch.Generator().manual_seed(0))
+    model = KPlanesModelConfig().setup(scene_box=SceneBox(aabb=aabb), num_train_data=19 * 25).to(dev)
+    perturb_time_planes(model)
+    model.proposal_sampler.update_sched = lambda step: 0  # proposal networks evaluated with grad + trained EVERY step
+    trainer = TrainStep(model, data_parallel=True)
+    n_steps = args.warmup + args.steps
+    host = _make_batches(n_steps, RAYS_PER_RANK, seed=1000 + rank)
+    resident = [h.to(dev) for h in host]
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(step_fn, record_kernels=False):
+        for i in range(args.warmup):
+            step_fn(i)
+        barrier()
+        launches0 = _lib.launch_count()
+        if record_kernels:
+            _lib.TIMED.update(ALGO_BYTES.keys())
+            _lib.EVENTS.clear()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
+            ev[i][0].record()
+            step_fn(args.warmup + i)
+            ev[i][1].record()
+        barrier()
+        _lib.TIMED.clear()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.launch_count() - launches0
+
+    # ---- arm 1: inputs resident in HBM --------------------------------------------------------------
+    def step_resident(i):
+        rb, batch = _bundle(resident[i])
+        trainer(rb, batch)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, launches = timed_region(step_resident, record_kernels=True)
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = {}
+    for name, a, b in _lib.EVENTS:
+        kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
+
+    # ---- arm 2: end to end through the public API with host buffers -----------------------------------
+    last_loss = [0.0]
+
+    def step_e2e(i):
+        packed = host[i].to(dev, non_blocking=True)  # pinned H2D inside the timed region
+        rb, batch = _bundle(packed)
+        out = trainer(rb, batch)
+        last_loss[0] = float(out["loss"].item())  # D2H read of the step's result
+
+    e2e_ms, _ = timed_region(step_e2e)
+
+    if rank != 0:
+        return
+    rays = RAYS_PER_RANK * world * args.steps
+    peaks, peak_kind = _peaks()
+    # dominant kernel = largest total time among the field gather/scatter kernels
+    per_kernel = {}
+    for name, ms_list in kernel_ms.items():
+        calls_per_step = len(ms_list) / args.steps
+        per_kernel[name] = {"ms_per_step": sum(ms_list) / args.steps, "launches_per_step": calls_per_step}
+    top = max(("kp_hexplane_fwd", "kp_hexplane_bwd"), key=lambda k: per_kernel.get(k, {"ms_per_step": 0})["ms_per_step"])
+    top_ms = per_kernel[top]["ms_per_step"] / per_kernel[top]["launches_per_step"]
+    achieved = ALGO_BYTES[top] / (top_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(top)
+    line = {
+        "metric": "train rays/sec (fwd+bwd+optimizer)",
+        "value": rays / (total_ms * 1e-3),
+        "unit": "rays/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch_rays": RAYS_PER_RANK * world, "parallelism": f"ray-sharded dp{world}",
+                   "proposal_update": "every step", "l2": "flushed between timed iterations (160 MB write)"},
+        "e2e": {"value": rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": host[0].numel() * 4 * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss[0]},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES[top], "kernel_ms": top_ms,
+                     "note": "planes of cfg2 (152 MB) are mostly L2-resident: algorithmic bytes are served by L2, so frac is "
+                             "relative to the measured HBM copy peak, see DESIGN.md"},
+        "kernels": per_kernel,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(rays_per_step=RAYS_PER_RANK, steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(rays_per_step: int, steps: int, warmup: int):
+    """The oracle port of the reference's CPU torch path (oracle/kplanes_oracle.py) timed on the host cores:
+    same cfg2 model and scene shape, full fwd+bwd+Adam steps on a bounded number of steps."""
+    from oracle import kplanes_oracle as ko
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(42)
+    origins, directions, times, aabb = ko.synthetic_rays(rays_per_step, gen)
+    mp = ko.make_model_params("cfg2", gen, aabb)
+    opt = torch.optim.Adam(mp.tensors(), lr=1e-2, eps=1e-12)
+    image = torch.rand(rays_per_step, 3, generator=gen)
+    t_total = 0.0
+    for i in range(warmup + steps):
+        rand = ko.make_rand(rays_per_step, mp, gen)
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        ko.train_step(mp, origins, directions, times, image, rand)
+        opt.step()
+        if i >= warmup:
+            t_total += time.perf_counter() - t0
+    return {"value": rays_per_step * steps / t_total, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} full training steps of {rays_per_step} rays (cfg2), after {warmup} warm-up; torch CPU fp32, "
+                      f"{cores} threads", "ms_per_step": 1e3 * t_total / steps}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: the reference is
+    Python and cannot travel to the GPU box), all host threads, same config / metric / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = 1024  # bounded sample per step so that K steps finish within minutes on the host cores
+    res = cpu_baseline(rays_per_step=rays, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference",
+        "metric": "train rays/sec (fwd+bwd+optimizer)",
+        "value": res["value"],
+        "unit": "rays/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{rays} rays per step (bounded CPU sample of the 4096-ray step)"},
+        "cpu_baseline": {**res, "sample": f"{args.steps} steps of {rays} rays"},
+        "e2e": {"value": res["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

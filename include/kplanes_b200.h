@@ -35,6 +35,7 @@ extern "C" {
 
 int kp_abi_version(void);
 const char* kp_last_error(void);
+long long kp_launch_count(void); /* kernels launched through this library since load */
 
 /* Where sample coordinates come from (exactly one of pts / ray form is used). */
 typedef struct KpPoints {
@@ -155,6 +156,20 @@ int kp_plane_reg_fwd(const float* plane, int H, int W, int C, uint32_t terms /* 
 int kp_plane_reg_bwd(const float* plane, int H, int W, int C, const float* coef_dev4 /* DEVICE float[4] */,
                      uint32_t terms /* bit i: include term i */, int accumulate /* 0: grad = g, 1: grad += g */,
                      float* grad, void* stream);
+
+/* Multi-plane variants: one launch for a whole list of planes.  planes/grads: HOST arrays [P] of device pointers,
+ * hwc: HOST int32 [P*3] = (H, W, C) per plane, terms: HOST uint32 [P]; sums / coef_dev: DEVICE [P,4]. */
+int kp_plane_reg_multi_fwd(const float* const* planes, const int32_t* hwc, const uint32_t* terms, int P,
+                           double* sums /* [P,4], accumulated */, void* stream);
+int kp_plane_reg_multi_bwd(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms,
+                           int P, const float* coef_dev /* [P,4] */, int accumulate, void* stream);
+
+/* Adam over a list of dense fp32 tensors in one launch.  hyper_dev (optional, DEVICE float[3] = lr/bias_corr1,
+ * 1/sqrt(bias_corr2), grad_scale) overrides the host-computed scalars so a captured CUDA graph can be replayed
+ * with fresh per-step values. */
+int kp_adam_multi(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                  const int64_t* sizes, int P, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int64_t step, float grad_scale, const float* hyper_dev, void* stream);
 
 /* ---- (f1) Adam over a flat fp32 buffer (torch.optim.Adam math; NS/engine/optimizers.py:74-160,
  *      method_configs.py:546-557: lr 1e-2, eps 1e-12).  step is 1-based. ---------------------------- */

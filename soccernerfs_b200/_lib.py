@@ -33,6 +33,7 @@ _P = c_void_p
 SIGNATURES = {
     "kp_abi_version": ([], c_int),
     "kp_last_error": ([], c_char_p),
+    "kp_launch_count": ([], ctypes.c_longlong),
     "kp_hexplane_fwd": ([_P, _P, c_int, c_int, c_int, POINTER(KpPoints), c_int64, c_int, c_uint32, _P, _P], c_int),
     "kp_hexplane_bwd": ([_P, _P, _P, c_int, c_int, c_int, POINTER(KpPoints), c_int64, c_int, c_uint32, _P, _P], c_int),
     "kp_density_field_fwd": ([_P, _P, c_int, c_int, _P, _P, c_int, c_int, POINTER(KpPoints), c_int64, c_uint32, _P, _P], c_int),
@@ -54,6 +55,9 @@ SIGNATURES = {
     "kp_interlevel_bwd": ([_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P], c_int),
     "kp_plane_reg_fwd": ([_P, c_int, c_int, c_int, c_uint32, _P, _P], c_int),
     "kp_plane_reg_bwd": ([_P, c_int, c_int, c_int, _P, c_uint32, c_int, _P, _P], c_int),
+    "kp_plane_reg_multi_fwd": ([_P, _P, _P, c_int, _P, _P], c_int),
+    "kp_plane_reg_multi_bwd": ([_P, _P, _P, _P, c_int, _P, c_int, _P], c_int),
+    "kp_adam_multi": ([_P, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P, _P], c_int),
     "kp_adam_step": ([_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P], c_int),
     "kp_repack_nchw_to_hwc": ([_P, _P, c_int, c_int, c_int, _P], c_int),
     "kp_repack_hwc_to_nchw": ([_P, _P, c_int, c_int, c_int, _P], c_int),
@@ -82,14 +86,32 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+# bench.py's live per-kernel timing: names in TIMED get a CUDA-event pair recorded around the call on the
+# launching (current) stream; (name, start, end) tuples are appended to EVENTS.
+TIMED = set()
+EVENTS = []
+
+
 def call(name: str, *args) -> None:
     """Invoke a C-ABI entry point and raise RuntimeError(kp_last_error()) on a non-zero status."""
     global LAUNCH_COUNT
     lib = load()
-    status = getattr(lib, name)(*args)
+    if name in TIMED:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        status = getattr(lib, name)(*args)
+        end.record()
+        EVENTS.append((name, start, end))
+    else:
+        status = getattr(lib, name)(*args)
     LAUNCH_COUNT += 1
     if status != 0:
         raise RuntimeError(f"{name} failed ({status}): {lib.kp_last_error().decode()}")
+
+
+def launch_count() -> int:
+    """Kernels launched through the library so far (counted inside the .so)."""
+    return int(load().kp_launch_count())
 
 
 def stream_ptr() -> c_void_p:

@@ -13,6 +13,7 @@
 namespace kp {
 
 void set_error(const char* fmt, ...);
+extern long long g_launches;  // number of kernels launched through the C-ABI (reported by kp_launch_count)
 
 #define KP_CHECK(cond, ...)          \
   do {                               \
@@ -24,6 +25,7 @@ void set_error(const char* fmt, ...);
 
 #define KP_LAUNCH_CHECK(name)                                                      \
   do {                                                                             \
+    kp::g_launches += 1;                                                           \
     cudaError_t e__ = cudaGetLastError();                                          \
     if (e__ != cudaSuccess) {                                                      \
       kp::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));       \

@@ -199,6 +199,7 @@ extern "C" int kp_sigma_net_fwd(const float* feats, const float* w1, const float
   gemm_fwd<EPI_RELU>(feats, K, w1, K, h1, H, M, H, K, st);
   gemm_fwd<EPI_NONE>(h1, H, w2, H, o, 16, M, 16, H, st);
   density_from_o_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(o, M, density);
+  kp::g_launches += 2;
   KP_LAUNCH_CHECK("sigma_net_fwd");
   return 0;
 }
@@ -219,6 +220,7 @@ extern "C" int kp_sigma_net_bwd(const float* feats, const float* w1, const float
   gemm_dx<EPI_RELU_MASK>(d_o, 16, w2, H, scratch, H, M, 16, H, h1, H, st);   // d_h1
   gemm_dw(scratch, H, feats, K, grad_w1, K, M, H, K, st);
   gemm_dx<EPI_NONE>(scratch, H, w1, K, grad_feats, K, M, H, K, nullptr, 0, st);
+  kp::g_launches += 4;
   KP_LAUNCH_CHECK("sigma_net_bwd");
   return 0;
 }
@@ -235,6 +237,7 @@ extern "C" int kp_color_net_fwd(const float* directions, int S, const float* o, 
   gemm_fwd<EPI_RELU>(cin, ldc, w3, kin, h2, H2, M, H2, kin, st);
   gemm_fwd<EPI_RELU>(h2, H2, w4, H2, h3, H2, M, H2, H2, st);
   gemm_fwd<EPI_SIGMOID>(h3, H2, w5, H2, rgb, 3, M, 3, H2, st);
+  kp::g_launches += 3;
   KP_LAUNCH_CHECK("color_net_fwd");
   return 0;
 }
@@ -258,6 +261,7 @@ extern "C" int kp_color_net_bwd(int view_dependent, const float* cin, const floa
   gemm_dw(scratch_b, H2, cin, ldc, grad_w3, kin, M, H2, kin, st);
   cudaMemsetAsync(grad_o, 0, (size_t)M * 16 * sizeof(float), st);
   gemm_dx<EPI_NONE>(scratch_b, H2, w3 + geo_off, kin, grad_o, 16, M, H2, 15, nullptr, 0, st);  // d_geo
+  kp::g_launches += 6;
   KP_LAUNCH_CHECK("color_net_bwd");
   return 0;
 }

@@ -1,0 +1,264 @@
+// Multi-tensor streaming kernels (sm_100a): one launch covers every plane / parameter of a group.
+//   kp_plane_reg_multi_fwd/bwd : the K-Planes regularisers (NS/model_components/losses.py:356-452) over a list of
+//                                channel-last planes -- 2 launches per loss term instead of 2 per plane (the
+//                                default model has 36 planes; per-plane launches were launch-latency bound).
+//   kp_adam_multi              : torch.optim.Adam over a list of dense fp32 tensors (NS/engine/optimizers.py:74-160,
+//                                method_configs.py:546-557); hyper-parameters may come from device memory so the
+//                                step can be replayed from a CUDA graph.
+// Work is split into fixed-size chunks; a block finds its (tensor, chunk) by a short scan of a prefix table that
+// travels in the kernel parameters.
+#include "common.cuh"
+
+namespace kp {
+
+constexpr int kMaxTensors = 64;
+constexpr int kChunk = 2048;  // float4 elements per block (256 threads x 8)
+
+struct RegPlane {
+  const float* t;
+  float* g;
+  int H, W, C4;
+  uint32_t terms;
+};
+struct RegTable {
+  RegPlane pl[kMaxTensors];
+  int first_block[kMaxTensors + 1];
+  int n;
+};
+
+__device__ __forceinline__ int find_tensor(const int* first_block, int n, int b) {
+  int p = 0;
+  while (p + 1 < n && first_block[p + 1] <= b) ++p;
+  return p;
+}
+
+__device__ __forceinline__ float4 sub4m(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float sq4m(float4 a) { return a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w; }
+__device__ __forceinline__ float sgnm(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(256) plane_reg_multi_fwd_kernel(const __grid_constant__ RegTable T,
+                                                                  double* __restrict__ sums) {
+  const int p = find_tensor(T.first_block, T.n, blockIdx.x);
+  const RegPlane& P = T.pl[p];
+  const float* __restrict__ t = P.t;
+  const int H = P.H, W = P.W, C4 = P.C4;
+  const uint32_t terms = P.terms;
+  const int64_t total = (int64_t)H * W * C4, row = (int64_t)W * C4;
+  const int64_t base = (int64_t)(blockIdx.x - T.first_block[p]) * kChunk;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 2
+  for (int it = 0; it < kChunk / 256; ++it) {
+    const int64_t idx = base + it * 256 + threadIdx.x;
+    if (idx >= total) break;
+    const int h = (int)(idx / row);
+    const int wcol = (int)(idx % row) / C4;
+    const float4 v = ldg4(t + idx * 4);
+    if ((terms & 1u) && h + 1 < H) s0 += sq4m(sub4m(ldg4(t + (idx + row) * 4), v));
+    if ((terms & 2u) && wcol + 1 < W) s1 += sq4m(sub4m(ldg4(t + (idx + C4) * 4), v));
+    if ((terms & 4u) && h + 2 < H) {
+      const float4 v1 = ldg4(t + (idx + row) * 4), v2 = ldg4(t + (idx + 2 * row) * 4);
+      s2 += sq4m(sub4m(sub4m(v2, v1), sub4m(v1, v)));
+    }
+    if (terms & 8u) s3 += fabsf(1.f - v.x) + fabsf(1.f - v.y) + fabsf(1.f - v.z) + fabsf(1.f - v.w);
+  }
+  __shared__ double red[4][8];
+  const double d[4] = {warp_sum_d((double)s0), warp_sum_d((double)s1), warp_sum_d((double)s2), warp_sum_d((double)s3)};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int k = 0; k < 4; ++k) red[k][warp] = d[k];
+  __syncthreads();
+  if (threadIdx.x < 4 && ((terms >> threadIdx.x) & 1u)) {
+    double a = 0.0;
+    for (int wv = 0; wv < 8; ++wv) a += red[threadIdx.x][wv];
+    atomicAdd(&sums[p * 4 + threadIdx.x], a);
+  }
+}
+
+__global__ void __launch_bounds__(256) plane_reg_multi_bwd_kernel(const __grid_constant__ RegTable T,
+                                                                  const float* __restrict__ coef, int accumulate) {
+  const int p = find_tensor(T.first_block, T.n, blockIdx.x);
+  const RegPlane& P = T.pl[p];
+  const float* __restrict__ t = P.t;
+  const int H = P.H, W = P.W, C4 = P.C4;
+  const uint32_t terms = P.terms;
+  const float k0 = (terms & 1u) ? coef[p * 4 + 0] : 0.f, k1 = (terms & 2u) ? coef[p * 4 + 1] : 0.f;
+  const float k2 = (terms & 4u) ? coef[p * 4 + 2] : 0.f, k3 = (terms & 8u) ? coef[p * 4 + 3] : 0.f;
+  const int64_t total = (int64_t)H * W * C4, row = (int64_t)W * C4;
+  const int64_t base = (int64_t)(blockIdx.x - T.first_block[p]) * kChunk;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = 0; it < kChunk / 256; ++it) {
+    const int64_t idx = base + it * 256 + threadIdx.x;
+    if (idx >= total) break;
+    const int h = (int)(idx / row);
+    const int wcol = (int)(idx % row) / C4;
+    const float4 v = ldg4(t + idx * 4);
+    float4 g = zero, up1 = zero, up2 = zero, dn1 = zero, dn2 = zero;
+    if (k0 != 0.f || k2 != 0.f) {
+      if (h + 1 < H) up1 = ldg4(t + (idx + row) * 4);
+      if (h >= 1) dn1 = ldg4(t + (idx - row) * 4);
+    }
+    if (k0 != 0.f) {
+      if (h >= 1) g = fma4(sub4m(v, dn1), 2.f * k0, g);
+      if (h + 1 < H) g = fma4(sub4m(up1, v), -2.f * k0, g);
+    }
+    if (k1 != 0.f) {
+      if (wcol >= 1) g = fma4(sub4m(v, ldg4(t + (idx - C4) * 4)), 2.f * k1, g);
+      if (wcol + 1 < W) g = fma4(sub4m(ldg4(t + (idx + C4) * 4), v), -2.f * k1, g);
+    }
+    if (k2 != 0.f) {
+      if (h + 2 < H) up2 = ldg4(t + (idx + 2 * row) * 4);
+      if (h >= 2) dn2 = ldg4(t + (idx - 2 * row) * 4);
+      if (h >= 2) g = fma4(sub4m(sub4m(v, dn1), sub4m(dn1, dn2)), 2.f * k2, g);
+      if (h >= 1 && h + 1 < H) g = fma4(sub4m(sub4m(up1, v), sub4m(v, dn1)), -4.f * k2, g);
+      if (h + 2 < H) g = fma4(sub4m(sub4m(up2, up1), sub4m(up1, v)), 2.f * k2, g);
+    }
+    if (k3 != 0.f) {
+      g.x -= k3 * sgnm(1.f - v.x); g.y -= k3 * sgnm(1.f - v.y); g.z -= k3 * sgnm(1.f - v.z); g.w -= k3 * sgnm(1.f - v.w);
+    }
+    float4* gp = reinterpret_cast<float4*>(P.g + idx * 4);
+    if (accumulate) {
+      const float4 cur = *gp;
+      g.x += cur.x; g.y += cur.y; g.z += cur.z; g.w += cur.w;
+    }
+    *gp = g;
+  }
+}
+
+struct AdamTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+};
+struct AdamTable {
+  AdamTensor t[kMaxTensors];
+  int first_block[kMaxTensors + 1];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamTable T,
+                                                         const float* __restrict__ hyper_dev, float lr_over_bc1,
+                                                         float inv_sqrt_bc2, float beta1, float beta2, float eps, float wd,
+                                                         float grad_scale) {
+  if (hyper_dev != nullptr) {  // graph-replayable path: per-step scalars live in device memory
+    lr_over_bc1 = hyper_dev[0];
+    inv_sqrt_bc2 = hyper_dev[1];
+    grad_scale = hyper_dev[2];
+  }
+  const int ti = find_tensor(T.first_block, T.n, blockIdx.x);
+  const AdamTensor& A = T.t[ti];
+  const int64_t base = (int64_t)(blockIdx.x - T.first_block[ti]) * kChunk * 4;
+  const bool vec_ok = ((((uintptr_t)A.p | (uintptr_t)A.g | (uintptr_t)A.m | (uintptr_t)A.v) & 15) == 0);
+#pragma unroll 2
+  for (int it = 0; it < kChunk / 256; ++it) {
+    const int64_t i4 = base + ((int64_t)it * 256 + threadIdx.x) * 4;
+    if (i4 >= A.n) break;
+    if (vec_ok && i4 + 4 <= A.n) {
+      float4 pp = *reinterpret_cast<float4*>(A.p + i4);
+      const float4 gg = *reinterpret_cast<const float4*>(A.g + i4);
+      float4 mm = *reinterpret_cast<float4*>(A.m + i4), vv = *reinterpret_cast<float4*>(A.v + i4);
+      float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gr = ga[k] * grad_scale + wd * pa[k];
+        ma[k] = ma[k] + (gr - ma[k]) * (1.f - beta1);
+        va[k] = va[k] * beta2 + (1.f - beta2) * gr * gr;
+        pa[k] -= lr_over_bc1 * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+      }
+      *reinterpret_cast<float4*>(A.p + i4) = pp;
+      *reinterpret_cast<float4*>(A.m + i4) = mm;
+      *reinterpret_cast<float4*>(A.v + i4) = vv;
+    } else {
+      for (int64_t i = i4; i < A.n && i < i4 + 4; ++i) {
+        const float gr = A.g[i] * grad_scale + wd * A.p[i];
+        A.m[i] = A.m[i] + (gr - A.m[i]) * (1.f - beta1);
+        A.v[i] = A.v[i] * beta2 + (1.f - beta2) * gr * gr;
+        A.p[i] -= lr_over_bc1 * A.m[i] / (sqrtf(A.v[i]) * inv_sqrt_bc2 + eps);
+      }
+    }
+  }
+}
+
+static int fill_reg_table(RegTable& T, const float* const* planes, float* const* grads, const int32_t* hwc,
+                          const uint32_t* terms, int begin, int end, bool need_grad) {
+  int nb = 0, k = 0;
+  for (int i = begin; i < end; ++i, ++k) {
+    RegPlane& r = T.pl[k];
+    r.t = planes[i];
+    r.g = grads ? grads[i] : nullptr;
+    r.H = hwc[i * 3 + 0];
+    r.W = hwc[i * 3 + 1];
+    const int C = hwc[i * 3 + 2];
+    KP_CHECK(r.t != nullptr && r.H >= 1 && r.W >= 1 && C >= 4 && C % 4 == 0, "plane_reg_multi: plane %d invalid (C %% 4 != 0?)", i);
+    KP_CHECK(!need_grad || r.g != nullptr, "plane_reg_multi: grad pointer %d is NULL", i);
+    r.C4 = C / 4;
+    r.terms = terms[i];
+    T.first_block[k] = nb;
+    nb += (int)ceil_div((int64_t)r.H * r.W * r.C4, kChunk);
+  }
+  T.first_block[k] = nb;
+  T.n = k;
+  return 0;
+}
+
+}  // namespace kp
+
+using namespace kp;
+
+extern "C" int kp_plane_reg_multi_fwd(const float* const* planes, const int32_t* hwc, const uint32_t* terms, int P,
+                                      double* sums, void* stream) {
+  KP_CHECK(planes && hwc && terms && sums && P >= 0, "plane_reg_multi_fwd: bad arguments");
+  for (int begin = 0; begin < P; begin += kMaxTensors) {
+    const int end = std::min(P, begin + kMaxTensors);
+    RegTable T;
+    if (fill_reg_table(T, planes, nullptr, hwc, terms, begin, end, false)) return 1;
+    const int nb = T.first_block[T.n];
+    if (nb == 0) continue;
+    plane_reg_multi_fwd_kernel<<<nb, 256, 0, as_stream(stream)>>>(T, sums + (size_t)begin * 4);
+    KP_LAUNCH_CHECK("plane_reg_multi_fwd");
+  }
+  return 0;
+}
+
+extern "C" int kp_plane_reg_multi_bwd(const float* const* planes, float* const* grads, const int32_t* hwc,
+                                      const uint32_t* terms, int P, const float* coef_dev, int accumulate, void* stream) {
+  KP_CHECK(planes && grads && hwc && terms && coef_dev && P >= 0, "plane_reg_multi_bwd: bad arguments");
+  for (int begin = 0; begin < P; begin += kMaxTensors) {
+    const int end = std::min(P, begin + kMaxTensors);
+    RegTable T;
+    if (fill_reg_table(T, planes, grads, hwc, terms, begin, end, true)) return 1;
+    const int nb = T.first_block[T.n];
+    if (nb == 0) continue;
+    plane_reg_multi_bwd_kernel<<<nb, 256, 0, as_stream(stream)>>>(T, coef_dev + (size_t)begin * 4, accumulate);
+    KP_LAUNCH_CHECK("plane_reg_multi_bwd");
+  }
+  return 0;
+}
+
+extern "C" int kp_adam_multi(float* const* params, const float* const* grads, float* const* exp_avg,
+                             float* const* exp_avg_sq, const int64_t* sizes, int P, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int64_t step, float grad_scale, const float* hyper_dev,
+                             void* stream) {
+  KP_CHECK(params && grads && exp_avg && exp_avg_sq && sizes && P >= 0 && step >= 1, "adam_multi: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  for (int begin = 0; begin < P; begin += kMaxTensors) {
+    const int end = std::min(P, begin + kMaxTensors);
+    AdamTable T;
+    int nb = 0, k = 0;
+    for (int i = begin; i < end; ++i, ++k) {
+      KP_CHECK(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i], "adam_multi: NULL tensor %d", i);
+      T.t[k] = AdamTensor{params[i], grads[i], exp_avg[i], exp_avg_sq[i], sizes[i]};
+      T.first_block[k] = nb;
+      nb += (int)ceil_div(ceil_div(sizes[i], 4), kChunk);
+    }
+    T.first_block[k] = nb;
+    T.n = k;
+    if (nb == 0) continue;
+    adam_multi_kernel<<<nb, 256, 0, as_stream(stream)>>>(T, hyper_dev, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1,
+                                                         beta2, eps, weight_decay, grad_scale);
+    KP_LAUNCH_CHECK("adam_multi");
+  }
+  return 0;
+}

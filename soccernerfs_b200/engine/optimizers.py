@@ -28,6 +28,7 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         for group in self.param_groups:
             b1, b2 = group["betas"]
+            ps, gs, ms, vs = [], [], [], []
             for p in group["params"]:
                 if p.grad is None or p.numel() == 0:
                     continue
@@ -40,8 +41,16 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
-                ops.adam_step_(p, g, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
-                               group["weight_decay"], st["step"], grad_scale)
+                ps.append(p), gs.append(g), ms.append(st["exp_avg"]), vs.append(st["exp_avg_sq"])
+            if ps:
+                steps = {self.state[p]["step"] for p in ps}
+                if len(steps) != 1:  # parameters joined the optimizer at different times: per-tensor launches
+                    for p, g, m, v in zip(ps, gs, ms, vs):
+                        ops.adam_step_(p, g, m, v, group["lr"], b1, b2, group["eps"], group["weight_decay"],
+                                       self.state[p]["step"], grad_scale)
+                else:
+                    ops.adam_multi_(ps, gs, ms, vs, group["lr"], b1, b2, group["eps"], group["weight_decay"], steps.pop(),
+                                    grad_scale, hyper_dev=group.get("hyper_dev"))
         return loss
 
 

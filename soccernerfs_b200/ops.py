@@ -484,34 +484,52 @@ def lossfun_outer(c, w, cp, wp) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # (a15) plane regularisers
 # ------------------------------------------------------------------------------------------------
+def _reg_tables(planes, terms):
+    from ctypes import c_uint32
+
+    hwc = (c_int32 * (3 * len(planes)))()
+    tm = (c_uint32 * len(planes))()
+    for i, (p, t) in enumerate(zip(planes, terms)):
+        hwc[3 * i], hwc[3 * i + 1], hwc[3 * i + 2] = p.shape[2], p.shape[3], p.shape[1]
+        tm[i] = t
+    return hwc, tm
+
+
 class _PlaneReg(torch.autograd.Function):
-    """sums[p] = (sum dh^2, sum dw^2, sum (d2h)^2, sum |1-t|) for each plane p, masked by terms[p]."""
+    """sums[p] = (sum dh^2, sum dw^2, sum (d2h)^2, sum |1-t|) for each plane p, masked by terms[p].
+    One kernel launch for the whole plane list in each direction."""
 
     @staticmethod
     def forward(ctx, terms: Tuple[int, ...], *planes):
         planes = [as_channel_last(p.detach()) for p in planes]
+        for p in planes:
+            ptr_cl(p)
         sums = torch.zeros((len(planes), 4), dtype=torch.float64, device=planes[0].device)
-        st = stream_ptr()
-        for i, (p, t) in enumerate(zip(planes, terms)):
-            if t:
-                _, c, h, w = p.shape
-                call("kp_plane_reg_fwd", ptr_cl(p), h, w, c, t, c_void_p(sums.data_ptr() + 32 * i), st)
+        hwc, tm = _reg_tables(planes, terms)
+        call("kp_plane_reg_multi_fwd", _plane_ptrs(planes), hwc, tm, len(planes), ptr(sums), stream_ptr())
         ctx.planes, ctx.terms = planes, terms
         return sums.float()
 
     @staticmethod
     def backward(ctx, gsums):
+        planes = ctx.planes
+        need = [bool(t) and ctx.needs_input_grad[1 + i] for i, t in enumerate(ctx.terms)]
+        idx = [i for i, n in enumerate(need) if n]
+        if not idx:
+            return (None,) * (1 + len(planes))
         g = f32c(gsums)
-        st = stream_ptr()
-        grads = []
-        for i, (p, t) in enumerate(zip(ctx.planes, ctx.terms)):
-            if not t or not ctx.needs_input_grad[1 + i]:
-                grads.append(None)
-                continue
-            _, c, h, w = p.shape
-            gp = new_plane(c, h, w, p.device)
-            call("kp_plane_reg_bwd", ptr_cl(p), h, w, c, c_void_p(g.data_ptr() + 16 * i), t, 0, ptr_cl(gp), st)
-            grads.append(gp)
+        sel = [planes[i] for i in idx]
+        total = sum(p.numel() for p in sel)
+        flat = torch.empty(total, dtype=torch.float32, device=g.device)
+        grads, off = [None] * len(planes), 0
+        for i in idx:
+            _, c, h, w = planes[i].shape
+            grads[i] = flat[off: off + planes[i].numel()].view(1, h, w, c).permute(0, 3, 1, 2)
+            off += planes[i].numel()
+        coef = g if len(idx) == len(planes) else g[idx].contiguous()
+        hwc, tm = _reg_tables(sel, [ctx.terms[i] for i in idx])
+        call("kp_plane_reg_multi_bwd", _plane_ptrs(sel), _plane_ptrs([grads[i] for i in idx]), hwc, tm, len(sel), ptr(coef),
+             0, stream_ptr())
         return (None, *grads)
 
 
@@ -538,3 +556,21 @@ def adam_step_(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
     call("kp_adam_step", c_void_p(param.data_ptr()), c_void_p(grad.data_ptr()), c_void_p(exp_avg.data_ptr()),
          c_void_p(exp_avg_sq.data_ptr()), n, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
          float(grad_scale), stream_ptr())
+
+
+def adam_multi_(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+                hyper_dev: Optional[torch.Tensor] = None) -> None:
+    """One launch of torch.optim.Adam's update over a list of dense fp32 tensors (same layout per tuple)."""
+    from ctypes import c_int64
+
+    n = len(params)
+    if n == 0:
+        return
+    sizes = (c_int64 * n)()
+    for i, (p, g, m, v) in enumerate(zip(params, grads, exp_avgs, exp_avg_sqs)):
+        if not (g.stride() == p.stride() == m.stride() == v.stride()) or g.dtype != torch.float32:
+            raise RuntimeError("adam_multi_: param/grad/state must share one dense fp32 layout")
+        sizes[i] = p.numel()
+    call("kp_adam_multi", _plane_ptrs(params), _plane_ptrs(grads), _plane_ptrs(exp_avgs), _plane_ptrs(exp_avg_sqs), sizes, n,
+         float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
+         ptr(hyper_dev), stream_ptr())
