@@ -149,7 +149,7 @@ def run_ours(args):
     model = KPlanesModelConfig().setup(scene_box=SceneBox(aabb=aabb), num_train_data=19 * 25).to(dev)
     perturb_time_planes(model)
     model.proposal_sampler.update_sched = lambda step: 0  # proposal networks evaluated with grad + trained EVERY step
-    trainer = TrainStep(model, data_parallel=True)
+    trainer = TrainStep(model, data_parallel=True, use_cuda_graph=not args.eager)
     n_steps = args.warmup + args.steps
     host = _make_batches(n_steps, RAYS_PER_RANK, seed=1000 + rank)
     resident = [h.to(dev) for h in host]
@@ -160,14 +160,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(step_fn, record_kernels=False):
+    def timed_region(step_fn):
         for i in range(args.warmup):
             step_fn(i)
         barrier()
         launches0 = _lib.launch_count()
-        if record_kernels:
-            _lib.TIMED.update(ALGO_BYTES.keys())
-            _lib.EVENTS.clear()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         for i in range(args.steps):
             flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
@@ -175,7 +172,6 @@ def run_ours(args):
             step_fn(args.warmup + i)
             ev[i][1].record()
         barrier()
-        _lib.TIMED.clear()
         ms = sum(a.elapsed_time(b) for a, b in ev)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -190,11 +186,16 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms, launches = timed_region(step_resident, record_kernels=True)
+    total_ms, launches = timed_region(step_resident)
     clocks = sampler.stop() if rank == 0 else None
-    kernel_ms = {}
-    for name, a, b in _lib.EVENTS:
-        kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
+    if not args.eager:
+        # a graph replay launches the kernels captured once; count them from one eager iteration of the same step
+        trainer.use_cuda_graph = False
+        k0 = _lib.launch_count()
+        step_resident(0)
+        torch.cuda.synchronize()
+        launches = (_lib.launch_count() - k0) * args.steps
+        trainer.use_cuda_graph = True
 
     # ---- arm 2: end to end through the public API with host buffers -----------------------------------
     last_loss = [0.0]
@@ -206,6 +207,20 @@ def run_ours(args):
         last_loss[0] = float(out["loss"].item())  # D2H read of the step's result
 
     e2e_ms, _ = timed_region(step_e2e)
+
+    # ---- per-kernel durations for the roofline: CUDA events around the field kernels on their launch stream,
+    #      measured live in eager mode (events cannot be timed inside a graph replay), L2 flushed per step ------
+    trainer.use_cuda_graph = False
+    _lib.TIMED.update(ALGO_BYTES.keys())
+    _lib.EVENTS.clear()
+    for i in range(args.steps):
+        flush.zero_()
+        step_resident(i % n_steps)
+    torch.cuda.synchronize()
+    _lib.TIMED.clear()
+    kernel_ms = {}
+    for name, a, b in _lib.EVENTS:
+        kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
 
     if rank != 0:
         return
@@ -238,7 +253,8 @@ def run_ours(args):
         "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch_rays": RAYS_PER_RANK * world, "parallelism": f"ray-sharded dp{world}",
-                   "proposal_update": "every step", "l2": "flushed between timed iterations (160 MB write)"},
+                   "proposal_update": "every step", "l2": "flushed between timed iterations (160 MB write)",
+                   "launch": "eager" if args.eager else "whole step replayed from a CUDA graph"},
         "e2e": {"value": rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": host[0].numel() * 4 * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss[0]},
         "gpu_launches": launches,
@@ -317,6 +333,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch kernels from Python each step instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

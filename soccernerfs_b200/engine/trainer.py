@@ -1,22 +1,31 @@
 """One K-Planes training iteration, mirroring ``Trainer.train_iteration`` (NS/engine/trainer.py:382-412) and the
 callback calls around it (:212, :221): callbacks BEFORE -> zero_grad -> forward (collider + get_outputs) ->
-metrics -> loss dict -> backward -> [gradient all-reduce] -> Adam -> scheduler -> callbacks AFTER."""
+metrics -> loss dict -> backward -> [gradient all-reduce] -> Adam -> scheduler -> callbacks AFTER.
+
+``use_cuda_graph=True`` captures that whole iteration (≈250 kernel launches) in a CUDA graph per sampler mode
+("proposal networks updated" / "not updated") and replays it: the launch-bound Python/autograd dispatch then
+costs one ``cudaGraphLaunch``.  Per-step scalars that the eager loop keeps on the host (Adam bias corrections,
+cosine LR, proposal-weight anneal exponent) are looked up on the device from tables indexed by a device-resident
+step counter, so a replay needs nothing from the host but the batch.
+"""
 from __future__ import annotations
 
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 
 from ..cameras.rays import RayBundle
 from ..distributed import GradBucket, world_info
 from ..models.kplanes import KPlanesModel, TrainingCallbackLocation
-from .optimizers import Optimizers
+from .optimizers import Optimizers, cosine_decay_factor
 
 
 class TrainStep:
     def __init__(self, model: KPlanesModel, max_steps: int = 30000, lr: float = 1e-2, eps: float = 1e-12,
-                 warm_up_end: int = 512, data_parallel: bool = False) -> None:
+                 warm_up_end: int = 512, data_parallel: bool = False, use_cuda_graph: bool = False) -> None:
         self.model = model
+        self.max_steps, self.base_lr, self.warm_up_end = max_steps, lr, warm_up_end
         self.optimizers = Optimizers(model.get_param_groups(), lr=lr, eps=eps, warm_up_end=warm_up_end, max_steps=max_steps)
         self.callbacks = model.get_training_callbacks(None)
         self.step = 0
@@ -24,12 +33,15 @@ class TrainStep:
         self.bucket: Optional[GradBucket] = None
         if data_parallel and self.world > 1:
             self.bucket = GradBucket([p for ps in model.get_param_groups().values() for p in ps])
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
+        self._graph_out: Dict[bool, Dict[str, torch.Tensor]] = {}
+        self._seen: Dict[bool, int] = {}
+        self._static: Optional[Dict[str, torch.Tensor]] = None
 
-    def __call__(self, ray_bundle: RayBundle, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    # ---- the iteration body (eager, or recorded into a graph) ------------------------------------------
+    def _iteration(self, ray_bundle: RayBundle, batch: Dict[str, torch.Tensor], grad_scale_override=None):
         model = self.model
-        model.train()
-        for cb in self.callbacks:
-            cb.run_callback_at_location(self.step, TrainingCallbackLocation.BEFORE_TRAIN_ITERATION)
         if self.bucket is not None:
             self.bucket.attach_zeroed()
         else:
@@ -44,9 +56,95 @@ class TrainStep:
             self.bucket.all_reduce()
             grad_scale = 1.0 / self.world
         self.optimizers.optimizer_step_all(grad_scale=grad_scale)
-        self.optimizers.scheduler_step_all(self.step)
-        for cb in self.callbacks:
-            cb.run_callback_at_location(self.step, TrainingCallbackLocation.AFTER_TRAIN_ITERATION)
-        self.step += 1
+        loss_dict = {k: v.detach() for k, v in loss_dict.items()}
         loss_dict["loss"] = loss.detach()
+        loss_dict["psnr"] = metrics["psnr"]
         return loss_dict
+
+    def _run_callbacks(self, location: int) -> None:
+        for cb in self.callbacks:
+            cb.run_callback_at_location(self.step, location)
+
+    def __call__(self, ray_bundle: RayBundle, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        self.model.train()
+        self._run_callbacks(TrainingCallbackLocation.BEFORE_TRAIN_ITERATION)
+        if self.use_cuda_graph:
+            out = self._graphed(ray_bundle, batch)
+        else:
+            out = self._iteration(ray_bundle, batch)
+        self.optimizers.scheduler_step_all(self.step)
+        self._run_callbacks(TrainingCallbackLocation.AFTER_TRAIN_ITERATION)
+        self.step += 1
+        return out
+
+    # ---- CUDA-graph path ----------------------------------------------------------------------------------
+    def _setup_graph_state(self, ray_bundle: RayBundle, batch) -> None:
+        dev = ray_bundle.origins.device
+        n = ray_bundle.origins.shape[0]
+        self._static = {
+            "origins": torch.empty(n, 3, device=dev), "directions": torch.empty(n, 3, device=dev),
+            "pixel_area": torch.ones(n, 1, device=dev), "times": torch.empty(n, 1, device=dev),
+            "image": torch.empty(n, 3, device=dev),
+        }
+        steps = np.arange(self.max_steps + 1)
+        lr = np.array([self.base_lr * cosine_decay_factor(int(s), self.warm_up_end, self.max_steps) for s in steps])
+        cfg = self.model.config
+        frac = np.clip(steps / cfg.proposal_weights_anneal_max_num_iters, 0, 1)
+        b = cfg.proposal_weights_anneal_slope
+        anneal = (b * frac) / ((b - 1) * frac + 1) if cfg.use_proposal_weight_anneal else np.ones_like(frac)
+        self._lr_table = torch.tensor(lr, dtype=torch.float64, device=dev)
+        self._anneal_table = torch.tensor(anneal, dtype=torch.float32, device=dev)
+        self._step_t = torch.full((), self.step, dtype=torch.int64, device=dev)
+        self._anneal_t = torch.ones((), dtype=torch.float32, device=dev)
+        self._grad_scale = 1.0 / self.world if self.bucket is not None else 1.0
+        for opt in self.optimizers.optimizers.values():
+            for group in opt.param_groups:
+                group["hyper_dev"] = torch.zeros(3, dtype=torch.float32, device=dev)
+
+    def _device_scalars(self) -> None:
+        """In-graph prologue: anneal exponent and Adam scalars for the device-resident step counter."""
+        idx = self._step_t.clamp(max=self.max_steps).view(1)  # 1-d index: a 0-d tensor index would .item() (host sync)
+        self._anneal_t.copy_(self._anneal_table.gather(0, idx).view(()))
+        t = (self._step_t + 1).double()
+        lr = self._lr_table.gather(0, idx).view(())
+        for opt in self.optimizers.optimizers.values():
+            for group in opt.param_groups:
+                b1, b2 = group["betas"]
+                bc1 = 1.0 - torch.pow(torch.full_like(t, b1), t)
+                bc2 = 1.0 - torch.pow(torch.full_like(t, b2), t)
+                hyper = torch.stack([lr / bc1, torch.rsqrt(bc2), torch.full_like(t, self._grad_scale)]).float()
+                group["hyper_dev"].copy_(hyper)
+
+    def _graph_body(self):
+        s = self._static
+        self._device_scalars()
+        rb = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"], times=s["times"])
+        out = self._iteration(rb, {"image": s["image"]})
+        self._step_t += 1
+        return out
+
+    def _graphed(self, ray_bundle: RayBundle, batch) -> Dict[str, torch.Tensor]:
+        sampler = self.model.proposal_sampler
+        if self._static is None:
+            self._setup_graph_state(ray_bundle, batch)
+        updated = bool(sampler._steps_since_update > sampler.update_sched(sampler._step) or sampler._step < 10)
+        s = self._static
+        s["origins"].copy_(ray_bundle.origins, non_blocking=True)
+        s["directions"].copy_(ray_bundle.directions, non_blocking=True)
+        s["times"].copy_(ray_bundle.times, non_blocking=True)
+        s["image"].copy_(batch["image"], non_blocking=True)
+        sampler._anneal = self._anneal_t  # device-resident exponent (the host callback's float is ignored here)
+        seen = self._seen.get(updated, 0)
+        self._seen[updated] = seen + 1
+        if seen < 2:  # first two visits of a mode run eagerly (lazy initialisations, allocator warm-up)
+            return self._graph_body()
+        if updated not in self._graphs:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._graph_out[updated] = self._graph_body()
+            self._graphs[updated] = g
+        self._graphs[updated].replay()
+        if updated:
+            sampler._steps_since_update = 0  # host-side state the captured Python would have set
+        return self._graph_out[updated]

@@ -211,7 +211,11 @@ class ProposalNetworkSampler(Sampler):
                 ray_samples = self.initial_sampler(ray_bundle, num_samples=num_samples)
             else:
                 assert weights is not None
-                annealed_weights = weights if self._anneal == 1.0 else torch.pow(weights, self._anneal)
+                # _anneal may be a device scalar tensor (CUDA-graph training step) or the reference's python float
+                if isinstance(self._anneal, torch.Tensor) or self._anneal != 1.0:
+                    annealed_weights = torch.pow(weights, self._anneal)
+                else:
+                    annealed_weights = weights  # pow(w, 1.0) == w
                 ray_samples = self.pdf_sampler(ray_bundle, ray_samples, annealed_weights, num_samples=num_samples)
             if is_prop:
                 with torch.set_grad_enabled(updated and torch.is_grad_enabled()):

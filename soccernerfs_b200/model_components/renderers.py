@@ -25,6 +25,7 @@ COLORS_DICT = {  # NS/utils/colors.py
     "green": torch.tensor([0.0, 1.0, 0.0]),
     "blue": torch.tensor([0.0, 0.0, 1.0]),
 }
+_DEVICE_COLORS = {}
 
 
 @contextlib.contextmanager
@@ -65,7 +66,10 @@ class RGBRenderer(nn.Module):
         if isinstance(background_color, str) and background_color == "random":
             background_color = torch.rand((w2.shape[0], 3), dtype=torch.float32, device=rgb.device)  # renderers.py:104-105
         if isinstance(background_color, str) and background_color in COLORS_DICT:
-            background_color = COLORS_DICT[background_color].to(rgb.device)
+            key = (background_color, str(rgb.device))
+            if key not in _DEVICE_COLORS:  # cached per device: no H2D copy in the steady state (CUDA-graph safe)
+                _DEVICE_COLORS[key] = COLORS_DICT[background_color].to(rgb.device)
+            background_color = _DEVICE_COLORS[key]
         assert isinstance(background_color, torch.Tensor)
         bg = background_color.to(rgb.device).reshape(-1, 3)
         return ops.composite_rgb(w2, rgb3, bg, nan_to_num).view(*batch, 3)
