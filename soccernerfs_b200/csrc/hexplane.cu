@@ -23,6 +23,7 @@ struct PlaneRef {
 };
 struct FieldRef {
   PlaneRef pl[KP_MAX_SCALES * KP_MAX_PLANES];
+  int reso[KP_MAX_SCALES][4];  // per-scale resolution of coordinates x,y,z,(t): plane (a,b) is [reso[b]][reso[a]][C]
   int n_scales, n_planes;
   uint32_t use_mask;
   int concat;
@@ -45,6 +46,22 @@ static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const*
       r.cb = (D == 4) ? comb4[p][1] : comb3[p][1];
       KP_CHECK(r.p != nullptr && r.H >= 1 && r.W >= 1, "plane (%d,%d) invalid", k, p);
     }
+  // K-Planes structure (kplanes_field.py:61-67): within a scale every plane's W / H is the resolution of the
+  // coordinate it is indexed by, so the bilinear set-up is done once per coordinate, not once per plane.
+  for (int k = 0; k < n_scales; ++k) {
+    int* reso = F.reso[k];
+    reso[0] = reso[1] = reso[2] = reso[3] = 0;
+    for (int p = 0; p < n_planes; ++p) {
+      const PlaneRef& r = F.pl[k * KP_MAX_PLANES + p];
+      KP_CHECK(reso[r.ca] == 0 || reso[r.ca] == r.W, "scale %d: plane %d has W=%d but coordinate %d has resolution %d", k, p,
+               r.W, r.ca, reso[r.ca]);
+      reso[r.ca] = r.W;
+      KP_CHECK(reso[r.cb] == 0 || reso[r.cb] == r.H, "scale %d: plane %d has H=%d but coordinate %d has resolution %d", k, p,
+               r.H, r.cb, reso[r.cb]);
+      reso[r.cb] = r.H;
+    }
+    if (reso[3] == 0) reso[3] = 1;
+  }
   F.n_scales = n_scales;
   F.n_planes = n_planes;
   F.use_mask = use_mask;
@@ -65,7 +82,7 @@ __device__ __forceinline__ void load_point(const KpPoints& P, int64_t m, float p
   const float t = __fadd_rn(P.starts[m], P.ends[m]);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    float v = __fdiv_rn(__fmul_rn(P.directions[n * 3 + d], t), 2.f);
+    float v = __fmul_rn(__fmul_rn(P.directions[n * 3 + d], t), 0.5f);  // x/2 == x*0.5 exactly
     float pos = __fadd_rn(P.origins[n * 3 + d], v);
     float q = __fdiv_rn(__fsub_rn(pos, P.aabb[d]), __fsub_rn(P.aabb[3 + d], P.aabb[d]));
     pt[d] = P.norm_mode ? __fsub_rn(__fmul_rn(q, 2.f), 1.f) : q;
@@ -73,26 +90,47 @@ __device__ __forceinline__ void load_point(const KpPoints& P, int64_t m, float p
   pt[3] = (P.D == 4 && P.times != nullptr) ? __fsub_rn(__fmul_rn(P.times[n], 2.f), 1.f) : 0.f;
 }
 
-// ATen grid_sampler_2d, bilinear / padding border / align_corners=True.
+// ATen grid_sampler_2d, bilinear / padding border / align_corners=True, factored per coordinate axis:
+//   i = ((x+1)/2)*(R-1) clamped to [0,R-1]; i0 = floor(i); weights (i0+1-i), (i-i0); corner i0+1 == R is dropped.
+struct Axis {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Axis axis_setup(float x, int R) {
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(x, 1.f), 0.5f), (float)(R - 1));
+  ix = fminf((float)(R - 1), fmaxf(ix, 0.f));
+  const float fx = floorf(ix);
+  Axis a;
+  a.i0 = (int)fx;
+  a.i1 = a.i0 + 1;
+  a.w1 = ix - fx;
+  a.w0 = (fx + 1.f) - ix;
+  if (a.i1 > R - 1) { a.i1 = R - 1; a.w1 = 0.f; }  // out-of-range corner contributes nothing
+  return a;
+}
 struct Bilerp {
   int o00, o01, o10, o11;  // texel indices (y*W+x)
   float w00, w01, w10, w11;
 };
-__device__ __forceinline__ Bilerp bilerp_setup(float x, float y, int W, int H) {
-  float ix = __fmul_rn(__fdiv_rn(__fadd_rn(x, 1.f), 2.f), (float)(W - 1));
-  float iy = __fmul_rn(__fdiv_rn(__fadd_rn(y, 1.f), 2.f), (float)(H - 1));
-  ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
-  iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
-  const float fx = floorf(ix), fy = floorf(iy);
-  int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
-  float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
-  float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
-  if (x1 > W - 1) { x1 = W - 1; wx1 = 0.f; }  // out-of-range corner contributes nothing
-  if (y1 > H - 1) { y1 = H - 1; wy1 = 0.f; }
+__device__ __forceinline__ Bilerp bilerp_from_axes(const Axis& ax, const Axis& ay, int W) {
   Bilerp b;
-  b.o00 = y0 * W + x0; b.o01 = y0 * W + x1; b.o10 = y1 * W + x0; b.o11 = y1 * W + x1;
-  b.w00 = wx0 * wy0; b.w01 = wx1 * wy0; b.w10 = wx0 * wy1; b.w11 = wx1 * wy1;
+  b.o00 = ay.i0 * W + ax.i0; b.o01 = ay.i0 * W + ax.i1; b.o10 = ay.i1 * W + ax.i0; b.o11 = ay.i1 * W + ax.i1;
+  b.w00 = ax.w0 * ay.w0; b.w01 = ax.w1 * ay.w0; b.w10 = ax.w0 * ay.w1; b.w11 = ax.w1 * ay.w1;
   return b;
+}
+// plane p of combinations(range(D),2) samples coordinate CA (-> W) and CB (-> H); compile-time so that the per-axis
+// set-up stays in registers
+template <int NP>
+__host__ __device__ constexpr int plane_ca(int p) {
+  return NP == 6 ? (p < 3 ? 0 : (p < 5 ? 1 : 2)) : (p < 2 ? 0 : 1);
+}
+template <int NP>
+__host__ __device__ constexpr int plane_cb(int p) {
+  return NP == 6 ? (p < 3 ? p + 1 : (p < 5 ? p - 1 : 3)) : (p < 1 ? 1 : 2);
+}
+__device__ __forceinline__ void axes_setup(const FieldRef& F, int k, const float pt[4], Axis ax[4]) {
+#pragma unroll
+  for (int d = 0; d < 4; ++d) ax[d] = axis_setup(pt[d], F.reso[k][d]);
 }
 
 __device__ __forceinline__ float4 bilerp_combine(const Bilerp& b, float4 v00, float4 v01, float4 v10, float4 v11) {
@@ -107,7 +145,7 @@ __device__ __forceinline__ float4 bilerp_combine(const Bilerp& b, float4 v00, fl
 // Forward gather.  C/4 lanes per sample, float4 per lane.
 // ---------------------------------------------------------------------------------------------------
 template <int C, int NP>
-__global__ void __launch_bounds__(256) hexplane_fwd_kernel(const __grid_constant__ FieldRef F,
+__global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_constant__ FieldRef F,
                                                             const __grid_constant__ KpPoints P, int64_t M,
                                                             float* __restrict__ out) {
   constexpr int LPS = C / 4;
@@ -120,12 +158,14 @@ __global__ void __launch_bounds__(256) hexplane_fwd_kernel(const __grid_constant
   const int out_stride = F.concat ? F.n_scales * C : C;
   float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < F.n_scales; ++k) {
+    Axis ax[4];
+    axes_setup(F, k, pt, ax);
     Bilerp b[NP];
     float4 v[NP][4];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const PlaneRef& pr = F.pl[k * KP_MAX_PLANES + p];
-      b[p] = bilerp_setup(pt[pr.ca], pt[pr.cb], pr.W, pr.H);
+      b[p] = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
       if ((F.use_mask >> p) & 1u) {
         const float* base = pr.p + c4;
         v[p][0] = ldg4(base + (int64_t)b[p].o00 * C);
@@ -151,7 +191,7 @@ __global__ void __launch_bounds__(256) hexplane_fwd_kernel(const __grid_constant
 // Backward scatter: d plane_p[corner] += w_corner * g * prod_{q != p} interp_q.
 // ---------------------------------------------------------------------------------------------------
 template <int C, int NP>
-__global__ void __launch_bounds__(256) hexplane_bwd_kernel(const __grid_constant__ FieldRef F,
+__global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_constant__ FieldRef F,
                                                             const __grid_constant__ KpPoints P, int64_t M,
                                                             const float* __restrict__ grad_out) {
   constexpr int LPS = C / 4;
@@ -164,12 +204,14 @@ __global__ void __launch_bounds__(256) hexplane_bwd_kernel(const __grid_constant
   const int out_stride = F.concat ? F.n_scales * C : C;
   for (int k = 0; k < F.n_scales; ++k) {
     const float4 g = ldg4(grad_out + m * out_stride + (F.concat ? k * C : 0) + c4);
+    Axis ax[4];
+    axes_setup(F, k, pt, ax);
     Bilerp b[NP];
     float4 val[NP];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const PlaneRef& pr = F.pl[k * KP_MAX_PLANES + p];
-      b[p] = bilerp_setup(pt[pr.ca], pt[pr.cb], pr.W, pr.H);
+      b[p] = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
       val[p] = make_float4(1.f, 1.f, 1.f, 1.f);
       if ((F.use_mask >> p) & 1u) {
         const float* base = pr.p + c4;
@@ -203,17 +245,18 @@ __global__ void __launch_bounds__(256) hexplane_bwd_kernel(const __grid_constant
 // Fused proposal density field (single scale, small C): one thread per sample.
 // ---------------------------------------------------------------------------------------------------
 template <int C, int NP>
-__device__ __forceinline__ void density_features(const FieldRef& F, const float pt[4], float val[NP][C], Bilerp b[NP]) {
+__device__ __forceinline__ void density_features(const FieldRef& F, const float pt[4], float val[NP][C], Axis ax[4]) {
+  axes_setup(F, 0, pt, ax);
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
     const PlaneRef& pr = F.pl[p];
-    b[p] = bilerp_setup(pt[pr.ca], pt[pr.cb], pr.W, pr.H);
+    const Bilerp b = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
     if ((F.use_mask >> p) & 1u) {
 #pragma unroll
       for (int q = 0; q < C / 4; ++q) {
         const float* base = pr.p + q * 4;
-        float4 r = bilerp_combine(b[p], ldg4(base + (int64_t)b[p].o00 * C), ldg4(base + (int64_t)b[p].o01 * C),
-                                  ldg4(base + (int64_t)b[p].o10 * C), ldg4(base + (int64_t)b[p].o11 * C));
+        float4 r = bilerp_combine(b, ldg4(base + (int64_t)b.o00 * C), ldg4(base + (int64_t)b.o01 * C),
+                                  ldg4(base + (int64_t)b.o10 * C), ldg4(base + (int64_t)b.o11 * C));
         val[p][q * 4 + 0] = r.x; val[p][q * 4 + 1] = r.y; val[p][q * 4 + 2] = r.z; val[p][q * 4 + 3] = r.w;
       }
     } else {
@@ -238,8 +281,8 @@ __global__ void __launch_bounds__(128) density_field_fwd_kernel(const __grid_con
     float pt[4];
     load_point(P, m, pt);
     float val[NP][C];
-    Bilerp b[NP];
-    density_features<C, NP>(F, pt, val, b);
+    Axis ax[4];
+    density_features<C, NP>(F, pt, val, ax);
     float f[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -264,7 +307,7 @@ __global__ void __launch_bounds__(128) density_field_fwd_kernel(const __grid_con
 // gradients in shared memory, then lane l owns hidden units {2l, 2l+1} (for hidden=64) and reduces over the
 // 32 samples into registers; registers are flushed with one atomicAdd per weight per block at the end.
 template <int C, int NP, int HIDDEN>
-__global__ void __launch_bounds__(128) density_field_bwd_kernel(const __grid_constant__ FieldRef F,
+__global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_constant__ FieldRef F,
                                                                  const __grid_constant__ KpPoints P, int64_t M,
                                                                  const float* __restrict__ w1, const float* __restrict__ w2,
                                                                  int relu, const float* __restrict__ grad_density,
@@ -299,12 +342,12 @@ __global__ void __launch_bounds__(128) density_field_bwd_kernel(const __grid_con
     const bool valid = m < M;
     float pt[4] = {0.f, 0.f, 0.f, 0.f};
     float val[NP][C];
-    Bilerp b[NP];
+    Axis ax[4];
     float f[C], df[C];
     float graw = 0.f;
     if (valid) {
       load_point(P, m, pt);
-      density_features<C, NP>(F, pt, val, b);
+      density_features<C, NP>(F, pt, val, ax);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         float a = 1.f;
@@ -314,6 +357,7 @@ __global__ void __launch_bounds__(128) density_field_bwd_kernel(const __grid_con
         df[c] = 0.f;
       }
       float raw = 0.f;
+#pragma unroll 4
       for (int j = 0; j < HIDDEN; ++j) {
         float pre = 0.f;
 #pragma unroll
@@ -323,6 +367,7 @@ __global__ void __launch_bounds__(128) density_field_bwd_kernel(const __grid_con
       }
       // trunc_exp backward (activations.py:37-39)
       graw = grad_density[m] * expf(fminf(fmaxf(raw, -15.f), 15.f));
+#pragma unroll 4
       for (int j = 0; j < HIDDEN; ++j) {
         const float pre = my_pre[lane * (HIDDEN + 1) + j];
         const float dpre = (relu && !(pre > 0.f)) ? 0.f : graw * s_w2[j];
@@ -339,6 +384,7 @@ __global__ void __launch_bounds__(128) density_field_bwd_kernel(const __grid_con
     my_g[lane] = graw;
     __syncwarp();
     // weight-gradient reduction over the warp's 32 samples
+#pragma unroll 2
     for (int s = 0; s < 32; ++s) {
       const float gs = my_g[s];
       float fs[C];
@@ -362,6 +408,7 @@ __global__ void __launch_bounds__(128) density_field_bwd_kernel(const __grid_con
       for (int p = 0; p < NP; ++p) {
         const PlaneRef& pr = F.pl[p];
         if (!((F.use_mask >> p) & 1u) || pr.g == nullptr) continue;
+        const Bilerp bp = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
         float gp[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -375,10 +422,10 @@ __global__ void __launch_bounds__(128) density_field_bwd_kernel(const __grid_con
         for (int q = 0; q < C / 4; ++q) {
           const float4 g4 = make_float4(gp[q * 4], gp[q * 4 + 1], gp[q * 4 + 2], gp[q * 4 + 3]);
           float* gb = pr.g + q * 4;
-          if (b[p].w00 != 0.f) red_add_v4(gb + (int64_t)b[p].o00 * C, scale4(g4, b[p].w00));
-          if (b[p].w01 != 0.f) red_add_v4(gb + (int64_t)b[p].o01 * C, scale4(g4, b[p].w01));
-          if (b[p].w10 != 0.f) red_add_v4(gb + (int64_t)b[p].o10 * C, scale4(g4, b[p].w10));
-          if (b[p].w11 != 0.f) red_add_v4(gb + (int64_t)b[p].o11 * C, scale4(g4, b[p].w11));
+          if (bp.w00 != 0.f) red_add_v4(gb + (int64_t)bp.o00 * C, scale4(g4, bp.w00));
+          if (bp.w01 != 0.f) red_add_v4(gb + (int64_t)bp.o01 * C, scale4(g4, bp.w01));
+          if (bp.w10 != 0.f) red_add_v4(gb + (int64_t)bp.o10 * C, scale4(g4, bp.w10));
+          if (bp.w11 != 0.f) red_add_v4(gb + (int64_t)bp.o11 * C, scale4(g4, bp.w11));
         }
       }
     }
@@ -400,15 +447,15 @@ template <int C>
 static int launch_hexplane(bool bwd, const FieldRef& F, const KpPoints& P, int64_t M, const float* grad_out, float* out,
                            cudaStream_t st) {
   constexpr int LPS = C / 4;
-  const int64_t blocks = ceil_div(M * LPS, 256);
+  const int64_t blocks = ceil_div(M * LPS, 128);
   if (blocks == 0) return 0;
   KP_CHECK(blocks < (1ll << 31), "hexplane: M too large");
   if (F.n_planes == 6) {
-    if (!bwd) hexplane_fwd_kernel<C, 6><<<(unsigned)blocks, 256, 0, st>>>(F, P, M, out);
-    else hexplane_bwd_kernel<C, 6><<<(unsigned)blocks, 256, 0, st>>>(F, P, M, grad_out);
+    if (!bwd) hexplane_fwd_kernel<C, 6><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, out);
+    else hexplane_bwd_kernel<C, 6><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, grad_out);
   } else {
-    if (!bwd) hexplane_fwd_kernel<C, 3><<<(unsigned)blocks, 256, 0, st>>>(F, P, M, out);
-    else hexplane_bwd_kernel<C, 3><<<(unsigned)blocks, 256, 0, st>>>(F, P, M, grad_out);
+    if (!bwd) hexplane_fwd_kernel<C, 3><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, out);
+    else hexplane_bwd_kernel<C, 3><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, grad_out);
   }
   KP_LAUNCH_CHECK("hexplane");
   return 0;

@@ -30,11 +30,20 @@ class GradBucket:
             self.views.append(v)
             off += p.numel()
 
-    def attach_zeroed(self) -> None:
-        """Zero the bucket and install the views as ``.grad`` so autograd accumulates in place."""
+    def attach_zeroed(self, sink: bool = False) -> None:
+        """Zero the bucket and install the views as ``.grad`` so autograd accumulates in place.  ``sink=True``
+        additionally publishes every view as the parameter's gradient sink (ops.grad_sink): the backward kernels
+        then accumulate straight into the bucket."""
         self.flat.zero_()
         for p, v in zip(self.params, self.views):
             p.grad = v
+            if sink:
+                p._kp_grad_sink = v
+
+    def detach_sinks(self) -> None:
+        for p in self.params:
+            if hasattr(p, "_kp_grad_sink"):
+                del p._kp_grad_sink
 
     def all_reduce(self, group=None, async_op: bool = False):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -23,7 +23,8 @@ from .optimizers import Optimizers, cosine_decay_factor
 
 class TrainStep:
     def __init__(self, model: KPlanesModel, max_steps: int = 30000, lr: float = 1e-2, eps: float = 1e-12,
-                 warm_up_end: int = 512, data_parallel: bool = False, use_cuda_graph: bool = False) -> None:
+                 warm_up_end: int = 512, data_parallel: bool = False, use_cuda_graph: bool = False,
+                 fuse_grad_accumulation: bool = True) -> None:
         self.model = model
         self.max_steps, self.base_lr, self.warm_up_end = max_steps, lr, warm_up_end
         self.optimizers = Optimizers(model.get_param_groups(), lr=lr, eps=eps, warm_up_end=warm_up_end, max_steps=max_steps)
@@ -31,7 +32,9 @@ class TrainStep:
         self.step = 0
         self.rank, self.world = world_info()
         self.bucket: Optional[GradBucket] = None
-        if data_parallel and self.world > 1:
+        self.reduce_grads = data_parallel and self.world > 1
+        self.fuse_grad_accumulation = fuse_grad_accumulation
+        if self.reduce_grads or fuse_grad_accumulation:
             self.bucket = GradBucket([p for ps in model.get_param_groups().values() for p in ps])
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
@@ -43,7 +46,7 @@ class TrainStep:
     def _iteration(self, ray_bundle: RayBundle, batch: Dict[str, torch.Tensor], grad_scale_override=None):
         model = self.model
         if self.bucket is not None:
-            self.bucket.attach_zeroed()
+            self.bucket.attach_zeroed(sink=self.fuse_grad_accumulation)
         else:
             self.optimizers.zero_grad_all()
         outputs = model(ray_bundle)
@@ -52,7 +55,7 @@ class TrainStep:
         loss = sum(loss_dict.values())
         loss.backward()
         grad_scale = 1.0
-        if self.bucket is not None:
+        if self.reduce_grads:
             self.bucket.all_reduce()
             grad_scale = 1.0 / self.world
         self.optimizers.optimizer_step_all(grad_scale=grad_scale)
@@ -96,7 +99,7 @@ class TrainStep:
         self._anneal_table = torch.tensor(anneal, dtype=torch.float32, device=dev)
         self._step_t = torch.full((), self.step, dtype=torch.int64, device=dev)
         self._anneal_t = torch.ones((), dtype=torch.float32, device=dev)
-        self._grad_scale = 1.0 / self.world if self.bucket is not None else 1.0
+        self._grad_scale = 1.0 / self.world if self.reduce_grads else 1.0
         for opt in self.optimizers.optimizers.values():
             for group in opt.param_groups:
                 group["hyper_dev"] = torch.zeros(3, dtype=torch.float32, device=dev)

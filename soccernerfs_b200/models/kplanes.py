@@ -25,6 +25,7 @@ from ..model_components.losses import (
     depth_loss,
     distortion_loss,
     interlevel_loss,
+    kplanes_regularizers,
     space_tv_loss,
     sparse_transients_loss,
     time_smoothness_loss,
@@ -288,19 +289,26 @@ class KPlanesModel(Model):
                 loss_dict["interlevel_loss"] = interlevel_loss(outputs["weights_list"], outputs["ray_samples_list"])
             ms_grids_nerf = self.field.grids
             ms_grids_prop = [p.grids for p in self.proposal_networks]
-            if "space_tv_loss" in loss_coef:
-                loss_dict["space_tv_loss"] = space_tv_loss(ms_grids_nerf)
-            if "space_tv_proposal_loss" in loss_coef:
-                loss_dict["space_tv_proposal_loss"] = space_tv_loss(ms_grids_prop)
-            if len(self.config.spacetime_resolution) > 3 and not self.config.freeze_time_planes:
-                if "sparse_transients_loss" in loss_coef:
-                    loss_dict["sparse_transients_loss"] = sparse_transients_loss(ms_grids_nerf)
-                if "sparse_transients_proposal_loss" in loss_coef:
-                    loss_dict["sparse_transients_proposal_loss"] = sparse_transients_loss(ms_grids_prop)
-                if "time_smoothness_loss" in loss_coef:
-                    loss_dict["time_smoothness_loss"] = time_smoothness_loss(ms_grids_nerf)
-                if "time_smoothness_proposal_loss" in loss_coef:
-                    loss_dict["time_smoothness_proposal_loss"] = time_smoothness_loss(ms_grids_prop)
+            dynamic = len(self.config.spacetime_resolution) > 3 and not self.config.freeze_time_planes
+            reg_keys = ("space_tv_loss", "space_tv_proposal_loss", "sparse_transients_loss", "sparse_transients_proposal_loss",
+                        "time_smoothness_loss", "time_smoothness_proposal_loss")
+            if dynamic and all(k in loss_coef for k in reg_keys):
+                # the six regularisers of kplanes.py:430-446 from one pass over the planes (same values)
+                loss_dict.update(kplanes_regularizers(ms_grids_nerf, ms_grids_prop))
+            else:
+                if "space_tv_loss" in loss_coef:
+                    loss_dict["space_tv_loss"] = space_tv_loss(ms_grids_nerf)
+                if "space_tv_proposal_loss" in loss_coef:
+                    loss_dict["space_tv_proposal_loss"] = space_tv_loss(ms_grids_prop)
+                if dynamic:
+                    if "sparse_transients_loss" in loss_coef:
+                        loss_dict["sparse_transients_loss"] = sparse_transients_loss(ms_grids_nerf)
+                    if "sparse_transients_proposal_loss" in loss_coef:
+                        loss_dict["sparse_transients_proposal_loss"] = sparse_transients_loss(ms_grids_prop)
+                    if "time_smoothness_loss" in loss_coef:
+                        loss_dict["time_smoothness_loss"] = time_smoothness_loss(ms_grids_nerf)
+                    if "time_smoothness_proposal_loss" in loss_coef:
+                        loss_dict["time_smoothness_proposal_loss"] = time_smoothness_loss(ms_grids_prop)
             if "depth_image" in batch.keys() and loss_coef["depth_loss"] > 0:
                 loss_dict["depth_loss"] = metrics_dict["depth_loss"]
         return scale_dict(loss_dict, loss_coef)

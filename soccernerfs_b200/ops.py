@@ -53,6 +53,27 @@ def _plane_hw(planes: Sequence[torch.Tensor]):
     return arr
 
 
+def grad_sink(p: torch.Tensor) -> Optional[torch.Tensor]:
+    """Gradient-accumulation fusion: a parameter may carry ``_kp_grad_sink`` -- a persistent, caller-zeroed buffer
+    with the parameter's layout (normally the tensor installed as ``p.grad``, see distributed.GradBucket).  Kernels
+    then accumulate their gradient straight into it (all of them are red/+= kernels) and autograd receives ``None``
+    for that input: no per-op gradient tensors, no zero fills and no autograd ``add`` passes over the planes."""
+    sink = getattr(p, "_kp_grad_sink", None)
+    if sink is None or not p.requires_grad or not torch.is_grad_enabled():
+        return None
+    return sink
+
+
+def _targets(tensors, sinks, need):
+    """Per input: the buffer a backward kernel accumulates into (the sink or a fresh zero tensor) and what is
+    returned to autograd (None when sunk)."""
+    fresh_need = [n and s is None for n, s in zip(need, sinks)]
+    fresh = zeros_like_planes(tensors, fresh_need)
+    targets = [s if (n and s is not None) else f for s, f, n in zip(sinks, fresh, need)]
+    returned = [None if (s is not None) else f for s, f in zip(sinks, fresh)]
+    return targets, returned
+
+
 def zeros_like_planes(planes: Sequence[torch.Tensor], need: Sequence[bool]) -> List[Optional[torch.Tensor]]:
     """One flat zero-filled buffer carved into channel-last views (a single memset for all plane gradients)."""
     total = sum(p.numel() for p, n in zip(planes, need) if n)
@@ -119,6 +140,7 @@ def points_from_rays(origins, directions, starts, ends, times, aabb, norm_mode: 
 class _Hexplane(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points: Points, n_scales: int, concat: bool, use_mask: int, *planes):
+        ctx.sinks = [grad_sink(p) for p in planes]
         planes = [as_channel_last(p.detach()) for p in planes]
         n_planes = len(planes) // n_scales
         c = planes[0].shape[1]
@@ -135,9 +157,9 @@ class _Hexplane(torch.autograd.Function):
         n_scales, n_planes, c, concat, use_mask = ctx.cfg
         planes, points = ctx.planes, ctx.points
         need = [ctx.needs_input_grad[4 + i] and bool((use_mask >> (i % n_planes)) & 1) for i in range(len(planes))]
-        grads = zeros_like_planes(planes, need)
+        targets, grads = _targets(planes, ctx.sinks, need)
         if any(need):
-            call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(grads), _plane_hw(planes), n_scales, n_planes, c,
+            call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(targets), _plane_hw(planes), n_scales, n_planes, c,
                  points.struct(), points.M, int(concat), use_mask, ptr(f32c(grad_out)), stream_ptr())
         return (None, None, None, None, *grads)
 
@@ -155,6 +177,8 @@ def hexplane_features(ms_planes: Sequence[Sequence[torch.Tensor]], points: Point
 class _DensityField(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points: Points, relu: bool, use_mask: int, w1, w2, *planes):
+        ctx.sinks = [grad_sink(p) for p in planes]
+        ctx.wsinks = (grad_sink(w1), grad_sink(w2))
         planes = [as_channel_last(p.detach()) for p in planes]
         w1c, w2c = f32c(w1.detach()), f32c(w2.detach()).view(-1)
         c, hidden, m = planes[0].shape[1], w1c.shape[0], points.M
@@ -171,13 +195,18 @@ class _DensityField(torch.autograd.Function):
         w1c, w2c, w2_shape = ctx.w
         n_planes = len(planes)
         need = [ctx.needs_input_grad[5 + i] and bool((use_mask >> i) & 1) for i in range(n_planes)]
-        grads = zeros_like_planes(planes, need)
-        gw = torch.zeros(w1c.numel() + w2c.numel(), dtype=torch.float32, device=w1c.device)
-        gw1, gw2 = gw[: w1c.numel()].view_as(w1c), gw[w1c.numel():]
-        call("kp_density_field_bwd", _plane_ptrs(planes), _plane_ptrs(grads), _plane_hw(planes), n_planes, c, ptr(w1c),
+        targets, grads = _targets(planes, ctx.sinks, need)
+        s1, s2 = ctx.wsinks
+        if s1 is not None and s2 is not None and s1.is_contiguous() and s2.is_contiguous():
+            gw1, gw2, ret1, ret2 = s1, s2.view(-1), None, None
+        else:
+            gw = torch.zeros(w1c.numel() + w2c.numel(), dtype=torch.float32, device=w1c.device)
+            gw1, gw2 = gw[: w1c.numel()].view_as(w1c), gw[w1c.numel():]
+            ret1, ret2 = gw1, gw2.view(w2_shape)
+        call("kp_density_field_bwd", _plane_ptrs(planes), _plane_ptrs(targets), _plane_hw(planes), n_planes, c, ptr(w1c),
              ptr(w2c), hidden, int(relu), points.struct(), points.M, use_mask, ptr(f32c(grad_density)), ptr(gw1), ptr(gw2),
              stream_ptr())
-        return (None, None, None, gw1, gw2.view(w2_shape), *grads)
+        return (None, None, None, ret1, ret2, *grads)
 
 
 def density_field(planes: Sequence[torch.Tensor], w1: torch.Tensor, w2: torch.Tensor, points: Points, relu: bool = True,
@@ -192,6 +221,7 @@ def density_field(planes: Sequence[torch.Tensor], w1: torch.Tensor, w2: torch.Te
 class _SigmaNet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, w1, w2):
+        ctx.wsinks = (grad_sink(w1), grad_sink(w2))
         x, w1c, w2c = f32c(feats.detach()), f32c(w1.detach()), f32c(w2.detach())
         m, k = x.shape
         h = w1c.shape[0]
@@ -201,7 +231,6 @@ class _SigmaNet(torch.autograd.Function):
         density = torch.empty((m,), dtype=torch.float32, device=x.device)
         call("kp_sigma_net_fwd", ptr(x), ptr(w1c), ptr(w2c), m, k, h, ptr(h1), ptr(o), ptr(density), stream_ptr())
         ctx.save_for_backward(x, w1c, w2c, h1, o)
-        ctx.mark_non_differentiable()
         return o, density
 
     @staticmethod
@@ -210,13 +239,18 @@ class _SigmaNet(torch.autograd.Function):
         m, k = x.shape
         h = w1c.shape[0]
         gx = torch.empty_like(x)
-        gw = torch.zeros(w1c.numel() + w2c.numel(), dtype=torch.float32, device=x.device)
-        gw1, gw2 = gw[: w1c.numel()].view_as(w1c), gw[w1c.numel():].view_as(w2c)
+        s1, s2 = ctx.wsinks
+        if s1 is not None and s2 is not None and s1.is_contiguous() and s2.is_contiguous():
+            gw1, gw2, ret = s1, s2, (None, None)
+        else:
+            gw = torch.zeros(w1c.numel() + w2c.numel(), dtype=torch.float32, device=x.device)
+            gw1, gw2 = gw[: w1c.numel()].view_as(w1c), gw[w1c.numel():].view_as(w2c)
+            ret = (gw1, gw2)
         scratch = torch.empty_like(h1)
         call("kp_sigma_net_bwd", ptr(x), ptr(w1c), ptr(w2c), m, k, h, ptr(h1), ptr(o),
              ptr(None if grad_density is None else f32c(grad_density)), ptr(None if grad_o is None else f32c(grad_o)),
              ptr(gx), ptr(gw1), ptr(gw2), ptr(scratch), stream_ptr())
-        return gx, gw1, gw2
+        return (gx, *ret)
 
 
 def sigma_net(feats: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -227,6 +261,7 @@ def sigma_net(feats: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> Tuple[
 class _ColorNet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, directions, samples_per_ray: int, geo, w3, w4, w5):
+        ctx.wsinks = (grad_sink(w3), grad_sink(w4), grad_sink(w5))
         w3c, w4c, w5c = f32c(w3.detach()), f32c(w4.detach()), f32c(w5.detach())
         g = geo.detach()
         if g.dtype != torch.float32:
@@ -256,13 +291,18 @@ class _ColorNet(torch.autograd.Function):
         m, h2d = h2.shape
         dev = h2.device
         go = torch.empty((m, 16), dtype=torch.float32, device=dev)
-        gw = torch.zeros(w3c.numel() + w4c.numel() + w5c.numel(), dtype=torch.float32, device=dev)
-        a, b = w3c.numel(), w3c.numel() + w4c.numel()
-        gw3, gw4, gw5 = gw[:a].view_as(w3c), gw[a:b].view_as(w4c), gw[b:].view_as(w5c)
+        if all(s is not None and s.is_contiguous() for s in ctx.wsinks):
+            gw3, gw4, gw5 = ctx.wsinks
+            ret = (None, None, None)
+        else:
+            gw = torch.zeros(w3c.numel() + w4c.numel() + w5c.numel(), dtype=torch.float32, device=dev)
+            a, b = w3c.numel(), w3c.numel() + w4c.numel()
+            gw3, gw4, gw5 = gw[:a].view_as(w3c), gw[a:b].view_as(w4c), gw[b:].view_as(w5c)
+            ret = (gw3, gw4, gw5)
         sa, sb = torch.empty_like(h2), torch.empty_like(h2)
         call("kp_color_net_bwd", int(ctx.view_dep), ptr(cin), ptr(h2), ptr(h3), ptr(rgb), ptr(w3c), ptr(w4c), ptr(w5c), m,
              h2d, ptr(f32c(grad_rgb)), ptr(go), ptr(gw3), ptr(gw4), ptr(gw5), ptr(sa), ptr(sb), stream_ptr())
-        return None, None, go[:, :15], gw3, gw4, gw5
+        return (None, None, go[:, :15], *ret)
 
 
 def color_net(directions: Optional[torch.Tensor], samples_per_ray: int, geo: torch.Tensor, w3, w4, w5) -> torch.Tensor:
@@ -501,6 +541,7 @@ class _PlaneReg(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, terms: Tuple[int, ...], *planes):
+        ctx.sinks = [grad_sink(p) for p in planes]
         planes = [as_channel_last(p.detach()) for p in planes]
         for p in planes:
             ptr_cl(p)
@@ -518,18 +559,26 @@ class _PlaneReg(torch.autograd.Function):
         if not idx:
             return (None,) * (1 + len(planes))
         g = f32c(gsums)
-        sel = [planes[i] for i in idx]
-        total = sum(p.numel() for p in sel)
-        flat = torch.empty(total, dtype=torch.float32, device=g.device)
-        grads, off = [None] * len(planes), 0
-        for i in idx:
-            _, c, h, w = planes[i].shape
-            grads[i] = flat[off: off + planes[i].numel()].view(1, h, w, c).permute(0, 3, 1, 2)
-            off += planes[i].numel()
-        coef = g if len(idx) == len(planes) else g[idx].contiguous()
-        hwc, tm = _reg_tables(sel, [ctx.terms[i] for i in idx])
-        call("kp_plane_reg_multi_bwd", _plane_ptrs(sel), _plane_ptrs([grads[i] for i in idx]), hwc, tm, len(sel), ptr(coef),
-             0, stream_ptr())
+        grads = [None] * len(planes)
+        for accumulate in (1, 0):  # sunk planes: accumulate into the sink; others: write a fresh gradient tensor
+            sub = [i for i in idx if (ctx.sinks[i] is not None) == bool(accumulate)]
+            if not sub:
+                continue
+            sel = [planes[i] for i in sub]
+            if accumulate:
+                tgt = [ctx.sinks[i] for i in sub]
+            else:
+                flat = torch.empty(sum(p.numel() for p in sel), dtype=torch.float32, device=g.device)
+                tgt, off = [], 0
+                for i in sub:
+                    _, c, h, w = planes[i].shape
+                    grads[i] = flat[off: off + planes[i].numel()].view(1, h, w, c).permute(0, 3, 1, 2)
+                    tgt.append(grads[i])
+                    off += planes[i].numel()
+            coef = g if len(sub) == len(planes) else g[sub].contiguous()
+            hwc, tm = _reg_tables(sel, [ctx.terms[i] for i in sub])
+            call("kp_plane_reg_multi_bwd", _plane_ptrs(sel), _plane_ptrs(tgt), hwc, tm, len(sel), ptr(coef), accumulate,
+                 stream_ptr())
         return (None, *grads)
 
 
