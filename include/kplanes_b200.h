@@ -95,6 +95,11 @@ int kp_color_net_bwd(int view_dependent, const float* cin, const float* h2, cons
                      float* grad_w3, float* grad_w4, float* grad_w5 /* accumulated */,
                      float* scratch_a, float* scratch_b /* [M,H2] each */, void* stream);
 
+/* Dense layer on tcgen05 tensor cores, fp32-accurate through 3xTF32 (building block of the decoders):
+ * Y[M,N] = act(X[M,K] W[N,K]^T), act 0 none / 1 ReLU / 2 sigmoid; N <= 64, K <= 128. */
+int kp_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t M, int N,
+                     int K, int act, void* stream);
+
 /* ---- (a13) AABBBoxCollider._intersect_with_aabb, NS/model_components/scene_colliders.py:57-95 ---- */
 int kp_aabb_intersect(const float* origins, const float* directions, int64_t N, const float* aabb_host6,
                       float near_plane, float* nears, float* fars, void* stream);
