@@ -99,6 +99,13 @@ int kp_color_net_bwd(int view_dependent, const float* cin, const float* h2, cons
  * Y[M,N] = act(X[M,K] W[N,K]^T), act 0 none / 1 ReLU / 2 sigmoid; N <= 64, K <= 128. */
 int kp_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t M, int N,
                      int K, int act, void* stream);
+/* dX[M,K] = (dY[M,N] W[N,K]) masked by (aux[M,K] > 0) when aux != NULL (ReLU backward of the producing layer). */
+int kp_tc_linear_bwd_data(const float* dY, int64_t lddy, const float* W, int64_t ldw, float* dX, int64_t lddx, int64_t M,
+                          int N, int K, const float* aux, int64_t ldaux, void* stream);
+/* dW[N,K] += dY[M,N]^T X[M,K]: persistent CTAs accumulate in TMEM over their sample tiles, one atomic flush each. */
+int kp_tc_linear_bwd_weight(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t lddw, int64_t M,
+                            int N, int K, void* stream);
+int kp_tc_supported(int N, int K); /* 1 if the tensor-core path covers a layer with N outputs and K inputs */
 
 /* ---- (a13) AABBBoxCollider._intersect_with_aabb, NS/model_components/scene_colliders.py:57-95 ---- */
 int kp_aabb_intersect(const float* origins, const float* directions, int64_t N, const float* aabb_host6,

@@ -92,26 +92,43 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   }
 }
 
+// The three products of a dense layer.  Shapes covered by the tcgen05 kernels (tc_linear.cu) run on the tensor cores
+// (3xTF32, fp32-accurate); the rest (e.g. the 192->128 first layer of the 32x config) use the SIMT SGEMM above.
 // Y[M,N] = act(X[M,K] W[N,K]^T)
 template <int EPI>
 static void gemm_fwd(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int64_t M, int N, int K,
                      cudaStream_t st) {
+  if (kp_tc_supported(N, K)) {
+    kp_tc_linear_fwd(X, ldx, W, ldw, Y, ldy, M, N, K, EPI == EPI_RELU ? 1 : (EPI == EPI_SIGMOID ? 2 : 0), st);
+    return;
+  }
   dim3 grid((unsigned)ceil_div(M, TI), (unsigned)ceil_div(N, TJ), 1);
   sgemm_kernel<0, 0, EPI><<<grid, 256, 0, st>>>(X, ldx, W, ldw, Y, ldy, M, N, K, K, nullptr, 0);
+  kp::g_launches += 1;
 }
 // dX[M,K] = (dY[M,N] W[N,K]) (* mask(aux > 0))
 template <int EPI>
 static void gemm_dx(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int64_t M, int N, int K,
                     const float* aux, int ldaux, cudaStream_t st) {
+  if (kp_tc_supported(N, K)) {
+    kp_tc_linear_bwd_data(dY, lddy, W, ldw, dX, lddx, M, N, K, EPI == EPI_RELU_MASK ? aux : nullptr, ldaux, st);
+    return;
+  }
   dim3 grid((unsigned)ceil_div(M, TI), (unsigned)ceil_div(K, TJ), 1);
   sgemm_kernel<0, 1, EPI><<<grid, 256, 0, st>>>(dY, lddy, W, ldw, dX, lddx, M, K, N, N, aux, ldaux);
+  kp::g_launches += 1;
 }
 // dW[N,K] += dY[M,N]^T X[M,K]   (reduction over M split across blockIdx.z)
 static void gemm_dw(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int64_t M, int N, int K,
                     cudaStream_t st) {
+  if (N <= 128 && K <= 128 && !(N > 64 && K > 64)) {  // operand tiles of both widths must fit shared memory
+    kp_tc_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, M, N, K, st);
+    return;
+  }
   const int64_t chunk = 1024;
   dim3 grid((unsigned)ceil_div(N, TI), (unsigned)ceil_div(K, TJ), (unsigned)ceil_div(M, chunk));
   sgemm_kernel<1, 1, EPI_ATOMIC><<<grid, 256, 0, st>>>(dY, lddy, X, ldx, dW, lddw, N, K, M, chunk, nullptr, 0);
+  kp::g_launches += 1;
 }
 
 __global__ void density_from_o_kernel(const float* __restrict__ o, int64_t M, float* __restrict__ density) {
@@ -199,7 +216,6 @@ extern "C" int kp_sigma_net_fwd(const float* feats, const float* w1, const float
   gemm_fwd<EPI_RELU>(feats, K, w1, K, h1, H, M, H, K, st);
   gemm_fwd<EPI_NONE>(h1, H, w2, H, o, 16, M, 16, H, st);
   density_from_o_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(o, M, density);
-  kp::g_launches += 2;
   KP_LAUNCH_CHECK("sigma_net_fwd");
   return 0;
 }
@@ -220,7 +236,6 @@ extern "C" int kp_sigma_net_bwd(const float* feats, const float* w1, const float
   gemm_dx<EPI_RELU_MASK>(d_o, 16, w2, H, scratch, H, M, 16, H, h1, H, st);   // d_h1
   gemm_dw(scratch, H, feats, K, grad_w1, K, M, H, K, st);
   gemm_dx<EPI_NONE>(scratch, H, w1, K, grad_feats, K, M, H, K, nullptr, 0, st);
-  kp::g_launches += 4;
   KP_LAUNCH_CHECK("sigma_net_bwd");
   return 0;
 }
@@ -237,7 +252,6 @@ extern "C" int kp_color_net_fwd(const float* directions, int S, const float* o, 
   gemm_fwd<EPI_RELU>(cin, ldc, w3, kin, h2, H2, M, H2, kin, st);
   gemm_fwd<EPI_RELU>(h2, H2, w4, H2, h3, H2, M, H2, H2, st);
   gemm_fwd<EPI_SIGMOID>(h3, H2, w5, H2, rgb, 3, M, 3, H2, st);
-  kp::g_launches += 3;
   KP_LAUNCH_CHECK("color_net_fwd");
   return 0;
 }
@@ -261,7 +275,6 @@ extern "C" int kp_color_net_bwd(int view_dependent, const float* cin, const floa
   gemm_dw(scratch_b, H2, cin, ldc, grad_w3, kin, M, H2, kin, st);
   cudaMemsetAsync(grad_o, 0, (size_t)M * 16 * sizeof(float), st);
   gemm_dx<EPI_NONE>(scratch_b, H2, w3 + geo_off, kin, grad_o, 16, M, H2, 15, nullptr, 0, st);  // d_geo
-  kp::g_launches += 6;
   KP_LAUNCH_CHECK("color_net_bwd");
   return 0;
 }

@@ -1,18 +1,24 @@
-// Dense layer on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate via 3xTF32.
+// Dense layers of the decoders on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate via 3xTF32.
 //
-//   Y[M,N] = act( X[M,K] * W[N,K]^T )        X, W, Y fp32 row-major, bias-free (tcnn FullyFusedMLP semantics)
+//   forward        Y[M,N]   = act( X[M,K] W[N,K]^T )
+//   backward data  dX[M,K]  = ( dY[M,N] W[N,K] ) * (aux > 0)
+//   backward wgt   dW[N,K] += dY[M,N]^T X[M,K]
 //
-// The decoders' parity bar is 1e-4 relative in fp32, which a single TF32 pass (10-bit mantissa) cannot meet, so each
-// operand is split x = hi + lo (both exactly representable in TF32, cvt.rna) and the product is accumulated as
-// hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (error ~2^-21, the dropped lo*lo term).  The MLP is tiny in
-// FLOPs, so the 3x MMA count is irrelevant; what matters is that no FFMA / LDS issue slots are spent on it.
+// all fp32 row-major, bias-free (tcnn FullyFusedMLP semantics, NS/fields/kplanes_field.py:249-273).  The decoders'
+// parity bar is 1e-4 relative in fp32, which a single TF32 pass (10-bit mantissa) cannot meet, so each operand is
+// split x = hi + lo (both exactly representable in TF32, cvt.rna) and the product accumulated as
+// hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (error ~2^-21: the dropped lo*lo term).  The MLPs are tiny in
+// FLOPs, so the 3x MMA count is irrelevant; what matters is that no FFMA / LDS issue slots are spent on them.
 //
-// One CTA (4 warps) per 128-row tile:
-//   1. all threads stage the X tile and W into shared memory as K-major SWIZZLE_128B UMMA operands
-//      (blocks of [rows x 32 tf32]; 8-row x 128-byte atoms, 16-byte chunk c of row r stored at chunk c ^ (r & 7));
-//   2. one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N, K=8 per instruction) into TMEM and
-//      commits to an mbarrier;
-//   3. each warp reads its 32 TMEM lanes (= 32 rows) with tcgen05.ld.32x32b, applies the activation, stores Y.
+// Shared-memory operand tiles: a [ROWS x COLS] fp32 tile is stored as COLS/32 blocks of [ROWS x 32]; each block is
+// ROWS/8 atoms of 8 rows x 128 bytes with the 128-byte swizzle (16-byte chunk c of row r at chunk c ^ (r & 7)).
+// Two UMMA views of such a tile are used, so no transposed copy of any operand is ever made:
+//   K-major  view (SWIZZLE_128B):          MN = tile rows, K = tile cols  (forward A = X tile, B = W)
+//   MN-major view (SWIZZLE_128B_BASE32B):  MN = tile cols, K = tile rows  (backward-data B = W "transposed";
+//                  weight-gradient A = X tile, B = dY tile with K = the 128 samples of the tile)
+// For 32-bit operands the tensor core only accepts the 32-byte-base swizzle in the MN-major view (atoms of 4 rows x
+// 128 bytes, 32-byte chunk q of row r at chunk q ^ (r & 3)), so a tile is staged in the swizzle of the view it is
+// consumed in.
 #include "common.cuh"
 
 namespace kp {
@@ -27,20 +33,30 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B, dense 8-row atoms (SBO = 1024 B), version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+// UMMA shared-memory descriptor (sm_100 version 1), SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major; canonical 1)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                    // descriptor version
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);         // start address, 16-byte units
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset
+  d |= (uint64_t)1 << 46;                           // descriptor version
+  d |= (uint64_t)layout_type << 61;                 // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
+// K-major view of a staged tile with `rows` rows: 32-col block kb, 8-col step ks.  LBO unused (canonical 1).
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int rows, int kb, int ks) {
+  return umma_desc(base + kb * rows * 128 + ks * 32, 16, 1024, 2);
+}
+// MN-major view: K-step r8 = rows [8*r8, 8*r8+8) = two 4-row atoms 512 bytes apart (SBO); MN blocks of 32 cols are
+// rows*128 bytes apart (LBO).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int rows, int r8) {
+  return umma_desc(base + r8 * 1024, rows * 128, 512, 1);
+}
 
-// kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, M x N.
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::tf32 instruction descriptor: D=F32, A=B=TF32, M x N, operand majors (0 = K-major, 1 = MN-major).
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -53,160 +69,451 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t b = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(b), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 
-// Stage a [rows x K] fp32 row-major matrix (leading dim ld, rows >= n_valid and cols >= k_valid zero-filled) as hi/lo
-// TF32 operands: K/32 blocks of [ROWS x 32], each block ROWS/8 atoms of 1024 B.
-template <int ROWS>
-__device__ __forceinline__ void stage_operand(const float* __restrict__ src, int64_t ld, int n_valid, int k_valid, int K,
-                                              float* __restrict__ s_hi, float* __restrict__ s_lo) {
-  const int chunks_per_row = K / 4;  // 16-byte chunks
-  for (int idx = threadIdx.x; idx < ROWS * chunks_per_row; idx += blockDim.x) {
-    const int row = idx / chunks_per_row, ch = idx % chunks_per_row;
-    const int kb = ch / 8, c = ch % 8;  // 32-column block, chunk within the 128-byte row
-    float v[4];
+// Stage a [ROWS x cols_pad] tile from a row-major fp32 matrix (rows >= rows_valid / cols >= cols_valid zero-filled)
+// as hi / lo TF32 operands in the blocked swizzled layout described above.
+template <int MN_VIEW>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t ld, int rows, int rows_valid,
+                                           int cols_valid, int cols_pad, float* __restrict__ s_hi, float* __restrict__ s_lo) {
+  constexpr int U = 8;                      // independent 16-byte loads in flight per thread
+  const int chunks_per_row = cols_pad / 4;  // 16-byte chunks
+  const int total = rows * chunks_per_row;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
+    float4 v[U];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int k = ch * 4 + e;
-      v[e] = (row < n_valid && k < k_valid) ? __ldg(src + (int64_t)row * ld + k) : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < total) {
+        const int row = idx / chunks_per_row, ch = idx % chunks_per_row;
+        if (row < rows_valid) {
+          const float* p = src + (int64_t)row * ld + ch * 4;
+          if (vec && ch * 4 + 4 <= cols_valid) {
+            v[u] = __ldg(reinterpret_cast<const float4*>(p));
+          } else {
+            if (ch * 4 + 0 < cols_valid) v[u].x = __ldg(p + 0);
+            if (ch * 4 + 1 < cols_valid) v[u].y = __ldg(p + 1);
+            if (ch * 4 + 2 < cols_valid) v[u].z = __ldg(p + 2);
+            if (ch * 4 + 3 < cols_valid) v[u].w = __ldg(p + 3);
+          }
+        }
+      }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x;
+      if (idx >= total) break;
+      const int row = idx / chunks_per_row, ch = idx % chunks_per_row;
+      const int kb = ch >> 3, c = ch & 7;
+      float4 hi, lo;
+      hi.x = to_tf32(v[u].x); hi.y = to_tf32(v[u].y); hi.z = to_tf32(v[u].z); hi.w = to_tf32(v[u].w);
+      lo.x = to_tf32(v[u].x - hi.x); lo.y = to_tf32(v[u].y - hi.y); lo.z = to_tf32(v[u].z - hi.z); lo.w = to_tf32(v[u].w - hi.w);
+      const int cs = MN_VIEW ? ((((c >> 1) ^ (row & 3)) << 1) | (c & 1)) : (c ^ (row & 7));  // swizzled 16-byte chunk
+      const int off = kb * (rows * 32) + row * 32 + (cs << 2);  // in floats
+      *reinterpret_cast<float4*>(s_hi + off) = hi;
+      *reinterpret_cast<float4*>(s_lo + off) = lo;
+    }
+  }
+}
+
+// Two-phase staging of a 128-row activation tile so that the global loads of tile i+1 can be issued BEFORE the MMA /
+// epilogue of tile i and their latency hides behind them: tile_load keeps up to 16 x 16 bytes per thread in registers
+// (128 rows x 128 cols with 256 threads), tile_store converts to hi/lo TF32 and writes the swizzled operand.
+// COLS_PAD (32 | 64 | 128) is a template parameter so that all index arithmetic folds to constants: thread t always
+// owns 16-byte chunk (t % CPR) of rows (t / CPR) + u * (256 / CPR); since 256/CPR is a multiple of 8 the swizzle
+// phase (row & 7) is the same for every u.  hi = x with the 13 low mantissa bits cleared (what the tensor core reads
+// of an fp32 word anyway), lo = x - hi (exact); the tensor core's own truncation of lo costs 2^-22 relative.
+template <int COLS_PAD>
+struct TileRegs {
+  static constexpr int CPR = COLS_PAD / 4;  // chunks per row
+  static constexpr int U = CPR / 2;         // chunks per thread (128 rows, 256 threads)
+  float4 v[U];
+};
+template <int COLS_PAD>
+__device__ __forceinline__ void tile_load(TileRegs<COLS_PAD>& t, const float* __restrict__ src, int64_t ld, int rows_valid,
+                                          int cols_valid) {
+  constexpr int CPR = COLS_PAD / 4, U = CPR / 2, ROWSTEP = 256 / CPR;
+  const int r0 = threadIdx.x / CPR, ch = threadIdx.x % CPR;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ch * 4 + 4 <= cols_valid);
+  const float* p = src + (int64_t)r0 * ld + ch * 4;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int row = r0 + u * ROWSTEP;
+    t.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_valid) {
+      const float* q = p + (int64_t)u * ROWSTEP * ld;
+      if (vec) {
+        t.v[u] = __ldg(reinterpret_cast<const float4*>(q));
+      } else {
+        if (ch * 4 + 0 < cols_valid) t.v[u].x = __ldg(q + 0);
+        if (ch * 4 + 1 < cols_valid) t.v[u].y = __ldg(q + 1);
+        if (ch * 4 + 2 < cols_valid) t.v[u].z = __ldg(q + 2);
+        if (ch * 4 + 3 < cols_valid) t.v[u].w = __ldg(q + 3);
+      }
+    }
+  }
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+template <int MN_VIEW, int COLS_PAD>
+__device__ __forceinline__ void tile_store(const TileRegs<COLS_PAD>& t, float* __restrict__ s_hi, float* __restrict__ s_lo) {
+  constexpr int CPR = COLS_PAD / 4, U = CPR / 2, ROWSTEP = 256 / CPR;
+  const int r0 = threadIdx.x / CPR, ch = threadIdx.x % CPR;
+  const int kb = ch >> 3, c = ch & 7;
+  const int cs = MN_VIEW ? ((((c >> 1) ^ (r0 & 3)) << 1) | (c & 1)) : (c ^ (r0 & 7));  // (row & 7) == (r0 & 7) for all u
+  const int off0 = kb * (128 * 32) + r0 * 32 + (cs << 2);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float4 x = t.v[u];
     float4 hi, lo;
-    hi.x = to_tf32(v[0]); hi.y = to_tf32(v[1]); hi.z = to_tf32(v[2]); hi.w = to_tf32(v[3]);
-    lo.x = to_tf32(v[0] - hi.x); lo.y = to_tf32(v[1] - hi.y); lo.z = to_tf32(v[2] - hi.z); lo.w = to_tf32(v[3] - hi.w);
-    const int off = kb * (ROWS * 32) + (row >> 3) * 256 + (row & 7) * 32 + ((c ^ (row & 7)) << 2);  // in floats
+    hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+    lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+    const int off = off0 + u * ROWSTEP * 32;
     *reinterpret_cast<float4*>(s_hi + off) = hi;
     *reinterpret_cast<float4*>(s_lo + off) = lo;
   }
 }
 
-template <int N_PAD>  // N padded to a multiple of 16 (UMMA N for M=128), <= 64
-__global__ void __launch_bounds__(128) tc_linear_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W,
-                                                        int64_t ldw, float* __restrict__ Y, int64_t ldy, int64_t M, int N,
-                                                        int K_valid, int K, int act) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve (1024-byte aligned blocks): A_hi, A_lo [128 x K], B_hi, B_lo [N_PAD x K]
-  float* a_hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* a_lo = a_hi + 128 * K;
-  float* b_hi = a_lo + 128 * K;
-  float* b_lo = b_hi + N_PAD * K;
+__device__ __forceinline__ float* align1024(uint8_t* p) {
+  return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, int warp) {
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+}
+__device__ __forceinline__ void tmem_free(uint32_t taddr, int warp) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(128));
+}
+__device__ __forceinline__ void publish_smem_and_sync() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> async (tensor core) proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-tile GEMM:  OUT[128 rows, N] = A[128, R] * B      (R = reduction depth, padded to 32; N padded to 32 for MN-B)
+//   B_MN == 0 (forward):        B = W [N x R]  K-major            ; epilogue act
+//   B_MN == 1 (backward data):  B = W [R x N]  MN-major view      ; epilogue (aux > 0) mask
+// ---------------------------------------------------------------------------------------------------------------
+template <int B_MN, int R_pad>
+__global__ void __launch_bounds__(256) tc_rowtile_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W,
+                                                         int64_t ldw, float* __restrict__ OUT, int64_t ldo, int64_t M, int N,
+                                                         int N_pad, int R, int act, const float* __restrict__ aux,
+                                                         int64_t ldaux) {
+  extern __shared__ uint8_t smem_raw[];
+  const int b_rows = B_MN ? R_pad : N_pad, b_cols = B_MN ? N_pad : R_pad;
+  float* a_hi = align1024(smem_raw);
+  float* a_lo = a_hi + 128 * R_pad;
+  float* b_hi = a_lo + 128 * R_pad;
+  float* b_lo = b_hi + b_rows * b_cols;
   __shared__ __align__(8) uint64_t mma_bar;
-  __shared__ uint32_t tmem_base_slot;
-
+  __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * 128;
-  const int rows_valid = (int)min((int64_t)128, M - row0);
-
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {  // TMEM allocation: one warp, power-of-two columns >= 32
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(64));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  stage_operand<128>(X + row0 * ldx, ldx, rows_valid, K_valid, K, a_hi, a_lo);
-  stage_operand<N_PAD>(W, ldw, N, K_valid, K, b_hi, b_lo);
-  // generic-proxy smem writes -> visible to the tensor core's async proxy
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_base_slot;
-
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_tf32(128, N_PAD);
-    const uint32_t a_addr[2] = {smem_u32(a_hi), smem_u32(a_lo)};
-    const uint32_t b_addr[2] = {smem_u32(b_hi), smem_u32(b_lo)};
-    const int term_a[3] = {0, 1, 0}, term_b[3] = {0, 0, 1};  // hi*hi + lo*hi + hi*lo
-    uint32_t accumulate = 0;
-    for (int t = 0; t < 3; ++t) {
-      for (int kb = 0; kb < K / 32; ++kb) {
-        const uint64_t ad = umma_desc_k_sw128(a_addr[term_a[t]] + kb * (128 * 32 * 4));
-        const uint64_t bd = umma_desc_k_sw128(b_addr[term_b[t]] + kb * (N_PAD * 32 * 4));
+  tmem_alloc(&tmem_slot, warp);
+  // weights are staged ONCE per (persistent) CTA
+  if (B_MN) stage_tile<1>(W, ldw, b_rows, R, N, b_cols, b_hi, b_lo);
+  else stage_tile<0>(W, ldw, b_rows, N, R, b_cols, b_hi, b_lo);
+  const uint32_t idesc = umma_idesc_tf32(128, N_pad, 0, B_MN);
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const int64_t n_tiles = (M + 127) / 128;
+  uint32_t parity = 0;
+  TileRegs<R_pad> pre;
+  if ((int64_t)blockIdx.x < n_tiles)
+    tile_load<R_pad>(pre, A + (int64_t)blockIdx.x * 128 * lda, lda, (int)min((int64_t)128, M - (int64_t)blockIdx.x * 128), R);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * 128;
+    const int rows_valid = (int)min((int64_t)128, M - row0);
+    tile_store<0, R_pad>(pre, a_hi, a_lo);
+    publish_smem_and_sync();
+    {  // issue the next tile's global loads now; they complete while the MMAs and the epilogue below run
+      const int64_t nxt = tile + gridDim.x;
+      if (nxt < n_tiles) tile_load<R_pad>(pre, A + nxt * 128 * lda, lda, (int)min((int64_t)128, M - nxt * 128), R);
+    }
+    const uint32_t tmem_d = tmem_slot;
+    if (threadIdx.x == 0) {
+      // One thread issues every MMA: keep its instruction stream short -- base descriptors once, then only the
+      // 14-bit start-address field advances by compile-time constants (fully unrolled).
+      const uint64_t a_d[2] = {desc_kmajor(smem_u32(a_hi), 128, 0, 0), desc_kmajor(smem_u32(a_lo), 128, 0, 0)};
+      const uint64_t b_d[2] = {B_MN ? desc_mnmajor(smem_u32(b_hi), b_rows, 0) : desc_kmajor(smem_u32(b_hi), b_rows, 0, 0),
+                               B_MN ? desc_mnmajor(smem_u32(b_lo), b_rows, 0) : desc_kmajor(smem_u32(b_lo), b_rows, 0, 0)};
+      const uint32_t b_blk = (uint32_t)(b_rows * 128) >> 4;  // K-major B: 16-byte units between 32-col blocks
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
-          umma_tf32(tmem_d, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, accumulate);
-          accumulate = 1;
+      for (int t = 0; t < 3; ++t) {  // hi*hi + lo*hi + hi*lo
+        const uint64_t ad0 = a_d[t == 1], bd0 = b_d[t == 2];
+#pragma unroll
+        for (int k8 = 0; k8 < R_pad / 8; ++k8) {
+          const uint32_t a_off = (uint32_t)(((k8 >> 2) * 128 * 128 + (k8 & 3) * 32) >> 4);
+          const uint32_t b_off = B_MN ? (uint32_t)((k8 * 1024) >> 4) : (uint32_t)(k8 >> 2) * b_blk + (uint32_t)(((k8 & 3) * 32) >> 4);
+          umma_tf32(tmem_d, ad0 + a_off, bd0 + b_off, idesc, (t | k8) != 0);
+        }
+      }
+      umma_commit(&mma_bar);
+    }
+    mbar_wait(&mma_bar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warps w and w+4 share TMEM lane quadrant (w & 3) and split the columns
+    const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
+    for (int c0 = half * 16; c0 < N_pad; c0 += 32) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < rows_valid && c0 < N) {
+        float* dst = OUT + (row0 + row) * ldo + c0;
+        const float* ax = aux ? aux + (row0 + row) * ldaux + c0 : nullptr;
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          x[j] = __uint_as_float(v[j]);
+          if (!B_MN) {
+            if (act == ACT_RELU) x[j] = fmaxf(x[j], 0.f);
+            else if (act == ACT_SIGMOID) x[j] = 1.f / (1.f + expf(-x[j]));
+          }
+        }
+        const bool full = (c0 + 16 <= N) && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(OUT) & 15) == 0);
+        if (full && (ax == nullptr || ((ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0))) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o4 = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            if (B_MN && ax != nullptr) {
+              const float4 m4 = __ldg(reinterpret_cast<const float4*>(ax + 4 * q));
+              if (!(m4.x > 0.f)) o4.x = 0.f;
+              if (!(m4.y > 0.f)) o4.y = 0.f;
+              if (!(m4.z > 0.f)) o4.z = 0.f;
+              if (!(m4.w > 0.f)) o4.w = 0.f;
+            }
+            *reinterpret_cast<float4*>(dst + 4 * q) = o4;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c0 + j < N) {
+              float o1 = x[j];
+              if (B_MN && ax != nullptr && !(ax[j] > 0.f)) o1 = 0.f;
+              dst[j] = o1;
+            }
+          }
         }
       }
     }
-    // arrive on the mbarrier when all MMAs above have completed (implicit tcgen05.fence::before_thread_sync)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar)) : "memory");
+    // all TMEM reads of this tile done before the next tile's MMAs overwrite the accumulator
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  // wait for the accumulator
-  {
-    uint32_t done = 0;
-    const uint32_t bar = smem_u32(&mma_bar);
-    while (!done) {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t"
-          "}\n"
-          : "=r"(done)
-          : "r"(bar), "r"(0u)
-          : "memory");
-    }
-  }
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tmem_free(tmem_slot, warp);
+}
 
-  // epilogue: warp w owns TMEM lanes [32w, 32w+32) = rows row0 + 32w + lane
-  uint32_t acc[N_PAD];
-  const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-#pragma unroll
-  for (int c0 = 0; c0 < N_PAD; c0 += 16) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(acc[c0 + 0]), "=r"(acc[c0 + 1]), "=r"(acc[c0 + 2]), "=r"(acc[c0 + 3]), "=r"(acc[c0 + 4]), "=r"(acc[c0 + 5]),
-          "=r"(acc[c0 + 6]), "=r"(acc[c0 + 7]), "=r"(acc[c0 + 8]), "=r"(acc[c0 + 9]), "=r"(acc[c0 + 10]), "=r"(acc[c0 + 11]),
-          "=r"(acc[c0 + 12]), "=r"(acc[c0 + 13]), "=r"(acc[c0 + 14]), "=r"(acc[c0 + 15])
-        : "r"(taddr + (uint32_t)c0));
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient, persistent: each CTA walks its 128-sample tiles, accumulating
+//   D[k, n] += sum_{s in tile} X[s, k] * dY[s, n]         (D = dW^T, M = 128 >= K_in, N = N_out padded to 32)
+// in ONE TMEM accumulator (both operands are MN-major views with K = samples), then adds D into dW once.
+// ---------------------------------------------------------------------------------------------------------------
+template <int K_pad, int N_pad>
+__global__ void __launch_bounds__(256) tc_wgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY,
+                                                       int64_t lddy, float* __restrict__ dW, int64_t lddw, int64_t M,
+                                                       int K_in, int N_out) {
+  extern __shared__ uint8_t smem_raw[];
+  float* x_hi = align1024(smem_raw);
+  float* x_lo = x_hi + 128 * K_pad;
+  float* y_hi = x_lo + 128 * K_pad;
+  float* y_lo = y_hi + 128 * N_pad;
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  const int row = warp * 32 + lane;
-  if (row < rows_valid) {
-    float* dst = Y + (row0 + row) * ldy;
+  tmem_alloc(&tmem_slot, warp);
+  const int64_t n_tiles = (M + 127) / 128;
+  uint32_t parity = 0, accumulate = 0;
+  uint32_t tmem_d = 0;
+  TileRegs<K_pad> px;
+  TileRegs<N_pad> py;
+  if ((int64_t)blockIdx.x < n_tiles) {
+    const int rv = (int)min((int64_t)128, M - (int64_t)blockIdx.x * 128);
+    tile_load<K_pad>(px, X + (int64_t)blockIdx.x * 128 * ldx, ldx, rv, K_in);
+    tile_load<N_pad>(py, dY + (int64_t)blockIdx.x * 128 * lddy, lddy, rv, N_out);
+  }
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    tile_store<1, K_pad>(px, x_hi, x_lo);
+    tile_store<1, N_pad>(py, y_hi, y_lo);
+    publish_smem_and_sync();
+    {
+      const int64_t nxt = tile + gridDim.x;
+      if (nxt < n_tiles) {
+        const int rv = (int)min((int64_t)128, M - nxt * 128);
+        tile_load<K_pad>(px, X + nxt * 128 * ldx, ldx, rv, K_in);
+        tile_load<N_pad>(py, dY + nxt * 128 * lddy, lddy, rv, N_out);
+      }
+    }
+    tmem_d = tmem_slot;
+    if (threadIdx.x == 0) {
+      // M = 128 rows of D; when K_pad < 128 the MN blocks beyond the X tile read whatever follows in shared memory:
+      // those D rows (k >= K_in) are never read back.
+      const uint32_t idesc = umma_idesc_tf32(128, N_pad, 1, 1);
+      const uint64_t a_d[2] = {desc_mnmajor(smem_u32(x_hi), 128, 0), desc_mnmajor(smem_u32(x_lo), 128, 0)};
+      const uint64_t b_d[2] = {desc_mnmajor(smem_u32(y_hi), 128, 0), desc_mnmajor(smem_u32(y_lo), 128, 0)};
 #pragma unroll
-    for (int j = 0; j < N_PAD; ++j) {
-      if (j < N) {
-        float v = __uint_as_float(acc[j]);
-        if (act == ACT_RELU) v = fmaxf(v, 0.f);
-        else if (act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
-        dst[j] = v;
+      for (int t = 0; t < 3; ++t) {
+        const uint64_t ad0 = a_d[t == 1], bd0 = b_d[t == 2];
+#pragma unroll
+        for (int r8 = 0; r8 < 16; ++r8) {  // 128 samples = 16 K-steps of 8 rows (1024 bytes each)
+          umma_tf32(tmem_d, ad0 + (uint32_t)(r8 * 64), bd0 + (uint32_t)(r8 * 64), idesc, accumulate | (uint32_t)((t | r8) != 0));
+        }
+      }
+      accumulate = 1;
+      umma_commit(&mma_bar);
+    }
+    mbar_wait(&mma_bar, parity);  // operands consumed: the staging buffers may be overwritten
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  if (blockIdx.x < n_tiles) {
+    const int quad = warp & 3, half = warp >> 2;
+    const int k = quad * 32 + lane;  // D row = input feature index
+    const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
+    for (int c0 = half * 16; c0 < N_pad; c0 += 32) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (k < K_in) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < N_out) red_add_f32(dW + (int64_t)(c0 + j) * lddw + k, __uint_as_float(v[j]));
       }
     }
   }
-  // release TMEM
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(64));
+  tmem_free(tmem_slot, warp);
+}
+
+static int pad_dim(int x) { return x <= 32 ? 32 : (x <= 64 ? 64 : 128); }  // operand tile widths: 32 | 64 | 128
+
+template <typename Kern>
+static unsigned persistent_grid(Kern kern, int64_t n_tiles, size_t smem) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;  // 4 x 128 TMEM columns
+  return (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
+}
+
+template <int B_MN, int R_PAD>
+static void launch_rowtile(const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo, int64_t M, int N,
+                           int N_pad, int R, int act, const float* aux, int64_t ldaux, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * 128 * R_PAD + 2 * N_pad * R_PAD) * sizeof(float) + 1024;
+  auto kern = tc_rowtile_kernel<B_MN, R_PAD>;
+  kern<<<persistent_grid(kern, ceil_div(M, 128), smem), 256, smem, st>>>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux);
+}
+template <int B_MN>
+static void dispatch_rowtile(int R_pad, const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo,
+                             int64_t M, int N, int N_pad, int R, int act, const float* aux, int64_t ldaux, cudaStream_t st) {
+  if (R_pad == 32) launch_rowtile<B_MN, 32>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, st);
+  else if (R_pad == 64) launch_rowtile<B_MN, 64>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, st);
+  else launch_rowtile<B_MN, 128>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, st);
+}
+
+template <int K_PAD, int N_PAD>
+static void launch_wgrad(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dW, int64_t lddw, int64_t M, int K,
+                         int N, cudaStream_t st) {
+  // the A operand always spans 4 MN blocks (M = 128): keep 4 blocks of slack after x_lo inside the allocation
+  size_t smem = (size_t)(2 * 128 * K_PAD + 2 * 128 * N_PAD) * sizeof(float);
+  const size_t need = (size_t)(128 * K_PAD + 128 * 128) * sizeof(float);
+  if (smem < need) smem = need;
+  smem += 1024;
+  auto kern = tc_wgrad_kernel<K_PAD, N_PAD>;
+  kern<<<persistent_grid(kern, ceil_div(M, 128), smem), 256, smem, st>>>(X, ldx, dY, lddy, dW, lddw, M, K, N);
+}
+template <int K_PAD>
+static void dispatch_wgrad(int N_pad, const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dW, int64_t lddw,
+                           int64_t M, int K, int N, cudaStream_t st) {
+  if (N_pad == 32) launch_wgrad<K_PAD, 32>(X, ldx, dY, lddy, dW, lddw, M, K, N, st);
+  else if (N_pad == 64) launch_wgrad<K_PAD, 64>(X, ldx, dY, lddy, dW, lddw, M, K, N, st);
+  else launch_wgrad<K_PAD, 128>(X, ldx, dY, lddy, dW, lddw, M, K, N, st);
 }
 
 }  // namespace kp
 
 using namespace kp;
 
-// Y[M,N] = act(X[M,K] W[N,K]^T) on tcgen05.  Supported: K <= 128 (padded up to a multiple of 32), N <= 64.
+// Which shapes the tensor-core path covers (others use the SIMT SGEMM in mlp.cu): operand tiles must fit shared memory.
+extern "C" int kp_tc_supported(int N, int K) {
+  return (N >= 1 && N <= 128 && K >= 1 && K <= 128 && pad_dim(N) * pad_dim(K) <= 128 * 64) ? 1 : 0;
+}
+
 extern "C" int kp_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t M,
                                 int N, int K, int act, void* stream) {
   if (M == 0) return 0;
-  KP_CHECK(X && W && Y && N >= 1 && N <= 64 && K >= 1 && K <= 128, "tc_linear_fwd: unsupported shape N=%d K=%d", N, K);
+  KP_CHECK(X && W && Y && kp_tc_supported(N, K), "tc_linear_fwd: unsupported shape N=%d K=%d", N, K);
   KP_CHECK(act >= 0 && act <= 2, "tc_linear_fwd: act=%d", act);
-  const int Kp = (K + 31) / 32 * 32;
-  const int Np = N <= 16 ? 16 : (N <= 32 ? 32 : 64);
-  const size_t smem = (size_t)(2 * 128 * Kp + 2 * Np * Kp) * sizeof(float) + 1024;
-  const unsigned grid = (unsigned)ceil_div(M, 128);
-  cudaStream_t st = as_stream(stream);
-#define KP_TC_LAUNCH(NP)                                                                                      \
-  do {                                                                                                        \
-    cudaFuncSetAttribute(tc_linear_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    tc_linear_kernel<NP><<<grid, 128, smem, st>>>(X, ldx, W, ldw, Y, ldy, M, N, K, Kp, act);                   \
-  } while (0)
-  if (Np == 16) KP_TC_LAUNCH(16);
-  else if (Np == 32) KP_TC_LAUNCH(32);
-  else KP_TC_LAUNCH(64);
-#undef KP_TC_LAUNCH
+  dispatch_rowtile<0>(pad_dim(K), X, ldx, W, ldw, Y, ldy, M, N, pad_dim(N), K, act, nullptr, 0, as_stream(stream));
   KP_LAUNCH_CHECK("tc_linear_fwd");
+  return 0;
+}
+
+// dX[M,K] = (dY[M,N] W[N,K]) masked by (aux[M,K] > 0) when aux != NULL.
+extern "C" int kp_tc_linear_bwd_data(const float* dY, int64_t lddy, const float* W, int64_t ldw, float* dX, int64_t lddx,
+                                     int64_t M, int N, int K, const float* aux, int64_t ldaux, void* stream) {
+  if (M == 0) return 0;
+  KP_CHECK(dY && W && dX && kp_tc_supported(N, K), "tc_linear_bwd_data: unsupported shape N=%d K=%d", N, K);
+  // reduction over N_out (R), output width K_in
+  dispatch_rowtile<1>(pad_dim(N), dY, lddy, W, ldw, dX, lddx, M, K, pad_dim(K), N, 0, aux, ldaux, as_stream(stream));
+  KP_LAUNCH_CHECK("tc_linear_bwd_data");
+  return 0;
+}
+
+// dW[N,K] += dY[M,N]^T X[M,K]
+extern "C" int kp_tc_linear_bwd_weight(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t lddw,
+                                       int64_t M, int N, int K, void* stream) {
+  if (M == 0) return 0;
+  KP_CHECK(dY && X && dW && N >= 1 && N <= 128 && K >= 1 && K <= 128 && pad_dim(N) + pad_dim(K) <= 192,
+           "tc_linear_bwd_weight: unsupported shape N=%d K=%d", N, K);
+  const int Kp = pad_dim(K), Np = pad_dim(N);
+  cudaStream_t st = as_stream(stream);
+  if (Kp == 32) dispatch_wgrad<32>(Np, X, ldx, dY, lddy, dW, lddw, M, K, N, st);
+  else if (Kp == 64) dispatch_wgrad<64>(Np, X, ldx, dY, lddy, dW, lddw, M, K, N, st);
+  else dispatch_wgrad<128>(Np, X, ldx, dY, lddy, dW, lddw, M, K, N, st);
+  KP_LAUNCH_CHECK("tc_linear_bwd_weight");
   return 0;
 }
