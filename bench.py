@@ -340,9 +340,12 @@ def main():
     else:
         run_ours(args)
         if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            import torch.distributed as dist
-
-            dist.destroy_process_group()
+            # CUDA graphs that captured NCCL work keep the communicator busy at interpreter shutdown: finish all GPU
+            # work, then leave without the (hanging) communicator teardown.
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
 
 if __name__ == "__main__":

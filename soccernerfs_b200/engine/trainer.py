@@ -31,11 +31,18 @@ class TrainStep:
         self.callbacks = model.get_training_callbacks(None)
         self.step = 0
         self.rank, self.world = world_info()
-        self.bucket: Optional[GradBucket] = None
+        self.buckets: Dict[str, GradBucket] = {}
         self.reduce_grads = data_parallel and self.world > 1
         self.fuse_grad_accumulation = fuse_grad_accumulation
         if self.reduce_grads or fuse_grad_accumulation:
-            self.bucket = GradBucket([p for ps in model.get_param_groups().values() for p in ps])
+            # one flat gradient bucket per parameter group: the field bucket is complete as soon as the field's scatter
+            # kernel has run, so its all-reduce overlaps the back-propagation through the proposal networks
+            self.buckets = {name: GradBucket(ps) for name, ps in model.get_param_groups().items()}
+        self._field_ready = None
+        self._comm_stream = None
+        if self.reduce_grads:
+            model.field._kp_post_backward = self._start_field_allreduce
+            self._comm_stream = torch.cuda.Stream()
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self._graph_out: Dict[bool, Dict[str, torch.Tensor]] = {}
@@ -45,10 +52,15 @@ class TrainStep:
     # ---- the iteration body (eager, or recorded into a graph) ------------------------------------------
     def _iteration(self, ray_bundle: RayBundle, batch: Dict[str, torch.Tensor], grad_scale_override=None):
         model = self.model
-        if self.bucket is not None:
-            self.bucket.attach_zeroed(sink=self.fuse_grad_accumulation)
+        if self.buckets:
+            for b in self.buckets.values():
+                b.attach_zeroed(sink=self.fuse_grad_accumulation)
         else:
             self.optimizers.zero_grad_all()
+        self._field_ready = None
+        from .. import ops
+
+        self._reg_mark = ops.PLANE_REG_BACKWARDS
         outputs = model(ray_bundle)
         metrics = model.get_metrics_dict(outputs, batch)
         loss_dict = model.get_loss_dict(outputs, batch, metrics)
@@ -56,13 +68,37 @@ class TrainStep:
         loss.backward()
         grad_scale = 1.0
         if self.reduce_grads:
-            self.bucket.all_reduce()
+            main = torch.cuda.current_stream()
+            if self._field_ready is not None:
+                self._comm_stream.wait_event(self._field_ready)  # fork: depends on the field scatter only
+                with torch.cuda.stream(self._comm_stream):
+                    self.buckets["fields"].all_reduce()
+                self.buckets["proposal_networks"].all_reduce()
+                main.wait_stream(self._comm_stream)  # join
+            else:
+                self.buckets["fields"].all_reduce()
+                self.buckets["proposal_networks"].all_reduce()
             grad_scale = 1.0 / self.world
         self.optimizers.optimizer_step_all(grad_scale=grad_scale)
         loss_dict = {k: v.detach() for k, v in loss_dict.items()}
         loss_dict["loss"] = loss.detach()
         loss_dict["psnr"] = metrics["psnr"]
         return loss_dict
+
+    def _start_field_allreduce(self) -> None:
+        """Called from the field's backward (autograd thread) right after its scatter kernel was enqueued: every
+        gradient of the "fields" group (plane regularisers, decoder weights, scatter) is then in the stream, so an
+        event recorded here marks the point from which the field bucket may be all-reduced.  The collective itself is
+        issued by the main thread on a communication stream that waits only on this event, so -- eagerly and in the
+        captured graph alike -- it overlaps the back-propagation through the proposal networks."""
+        from .. import ops
+
+        # only if the plane-regulariser backward (an independent autograd branch that also writes the field planes'
+        # gradients) has already been enqueued; otherwise the bucket is reduced after the whole backward
+        if self.reduce_grads and self._field_ready is None and ops.PLANE_REG_BACKWARDS > self._reg_mark:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._field_ready = ev
 
     def _run_callbacks(self, location: int) -> None:
         for cb in self.callbacks:

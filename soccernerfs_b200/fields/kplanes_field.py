@@ -203,7 +203,8 @@ class KPlanesField(Field, _AabbHostMixin):
         if points.D != (4 if len(ms[0]) == 6 else 3):
             raise RuntimeError("dynamic K-Planes field needs ray_samples.times")
         feats = ops.hexplane_features(ms, points, self.concat_features_across_scales,
-                                      _use_mask(len(ms[0]), self.freeze_time_planes))
+                                      _use_mask(len(ms[0]), self.freeze_time_planes),
+                                      post_backward=getattr(self, "_kp_post_backward", None))
         o, density = ops.sigma_net(feats, self.sigma_net.weights[0], self.sigma_net.weights[1])
         return density.view(*batch, 1), o[:, : self.geo_feat_dim]
 

@@ -139,8 +139,9 @@ def points_from_rays(origins, directions, starts, ends, times, aabb, norm_mode: 
 # ------------------------------------------------------------------------------------------------
 class _Hexplane(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, points: Points, n_scales: int, concat: bool, use_mask: int, *planes):
+    def forward(ctx, points: Points, n_scales: int, concat: bool, use_mask: int, post_backward, *planes):
         ctx.sinks = [grad_sink(p) for p in planes]
+        ctx.post_backward = post_backward
         planes = [as_channel_last(p.detach()) for p in planes]
         n_planes = len(planes) // n_scales
         c = planes[0].shape[1]
@@ -156,19 +157,22 @@ class _Hexplane(torch.autograd.Function):
     def backward(ctx, grad_out):
         n_scales, n_planes, c, concat, use_mask = ctx.cfg
         planes, points = ctx.planes, ctx.points
-        need = [ctx.needs_input_grad[4 + i] and bool((use_mask >> (i % n_planes)) & 1) for i in range(len(planes))]
+        need = [ctx.needs_input_grad[5 + i] and bool((use_mask >> (i % n_planes)) & 1) for i in range(len(planes))]
         targets, grads = _targets(planes, ctx.sinks, need)
         if any(need):
             call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(targets), _plane_hw(planes), n_scales, n_planes, c,
                  points.struct(), points.M, int(concat), use_mask, ptr(f32c(grad_out)), stream_ptr())
-        return (None, None, None, None, *grads)
+        if ctx.post_backward is not None:
+            ctx.post_backward()  # e.g. start the gradient all-reduce of the field bucket while the proposals back-propagate
+        return (None, None, None, None, None, *grads)
 
 
 def hexplane_features(ms_planes: Sequence[Sequence[torch.Tensor]], points: Points, concat: bool,
-                      use_mask: int = 0x3F) -> torch.Tensor:
-    """interpolate_kplanes (NS/fields/kplanes_field.py:77-126) -> [M, K*C] (concat) or [M, C] (sum)."""
+                      use_mask: int = 0x3F, post_backward=None) -> torch.Tensor:
+    """interpolate_kplanes (NS/fields/kplanes_field.py:77-126) -> [M, K*C] (concat) or [M, C] (sum).
+    ``post_backward``: optional callable run right after the scatter kernel has been enqueued in the backward."""
     flat = [p for grids in ms_planes for p in grids]
-    return _Hexplane.apply(points, len(ms_planes), concat, use_mask, *flat)
+    return _Hexplane.apply(points, len(ms_planes), concat, use_mask, post_backward, *flat)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -524,6 +528,9 @@ def lossfun_outer(c, w, cp, wp) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # (a15) plane regularisers
 # ------------------------------------------------------------------------------------------------
+PLANE_REG_BACKWARDS = 0  # number of regulariser backward passes run so far (the trainer orders its all-reduce after it)
+
+
 def _reg_tables(planes, terms):
     from ctypes import c_uint32
 
@@ -553,6 +560,8 @@ class _PlaneReg(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gsums):
+        global PLANE_REG_BACKWARDS
+        PLANE_REG_BACKWARDS += 1
         planes = ctx.planes
         need = [bool(t) and ctx.needs_input_grad[1 + i] for i, t in enumerate(ctx.terms)]
         idx = [i for i, n in enumerate(need) if n]
