@@ -339,7 +339,13 @@ __global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t M_pad = (M + 31) / 32 * 32;
   for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M_pad; m += stride) {
-    const bool valid = m < M;
+    // The gradient reaching a proposal field comes from the interlevel loss, clip(w - w_outer, 0)^2 / (w + eps)
+    // (NS/model_components/losses.py:95), which is EXACTLY zero wherever the proposal histogram already bounds the
+    // field's: typically 70-90 % of the samples.  A sample with zero upstream gradient contributes nothing to any
+    // plane or weight gradient, so a warp whose 32 samples are all zero skips the gather and the MLP altogether.
+    const float g_up = (m < M) ? grad_density[m] : 0.f;
+    if (__all_sync(0xffffffffu, g_up == 0.f)) continue;
+    const bool valid = (m < M) && (g_up != 0.f);
     float pt[4] = {0.f, 0.f, 0.f, 0.f};
     float val[NP][C];
     Axis ax[4];
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_
         raw = fmaf(s_w2[j], relu ? fmaxf(pre, 0.f) : pre, raw);
       }
       // trunc_exp backward (activations.py:37-39)
-      graw = grad_density[m] * expf(fminf(fmaxf(raw, -15.f), 15.f));
+      graw = g_up * expf(fminf(fmaxf(raw, -15.f), 15.f));
 #pragma unroll 4
       for (int j = 0; j < HIDDEN; ++j) {
         const float pre = my_pre[lane * (HIDDEN + 1) + j];

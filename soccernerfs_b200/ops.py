@@ -58,8 +58,8 @@ def grad_sink(p: torch.Tensor) -> Optional[torch.Tensor]:
     with the parameter's layout (normally the tensor installed as ``p.grad``, see distributed.GradBucket).  Kernels
     then accumulate their gradient straight into it (all of them are red/+= kernels) and autograd receives ``None``
     for that input: no per-op gradient tensors, no zero fills and no autograd ``add`` passes over the planes."""
-    sink = getattr(p, "_kp_grad_sink", None)
-    if sink is None or not p.requires_grad or not torch.is_grad_enabled():
+    sink = getattr(p, "_kp_grad_sink", None)  # (called inside Function.forward, where grad mode is always off)
+    if sink is None or not p.requires_grad:
         return None
     return sink
 
