@@ -6,9 +6,11 @@
 //
 // all fp32 row-major, bias-free (tcnn FullyFusedMLP semantics, NS/fields/kplanes_field.py:249-273).  The decoders'
 // parity bar is 1e-4 relative in fp32, which a single TF32 pass (10-bit mantissa) cannot meet, so each operand is
-// split x = hi + lo (both exactly representable in TF32, cvt.rna) and the product accumulated as
-// hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (error ~2^-21: the dropped lo*lo term).  The MLPs are tiny in
-// FLOPs, so the 3x MMA count is irrelevant; what matters is that no FFMA / LDS issue slots are spent on them.
+// split x = hi + lo (hi = cvt.rna.tf32(x), lo = x - hi exactly) and all four partial products
+// lo*lo + lo*hi + hi*lo + hi*hi are accumulated in the fp32 TMEM accumulator; the only loss is the tensor core's
+// truncation of lo to 11 bits (~2^-23 relative), i.e. fp32-class accuracy -- which matters because a ReLU whose
+// pre-activation is rounded across zero flips a sample's whole gradient.  The MLPs are tiny in FLOPs, so the 4x MMA
+// count is irrelevant; what matters is that no FFMA / LDS issue slots are spent on them.
 //
 // Shared-memory operand tiles: a [ROWS x COLS] fp32 tile is stored as COLS/32 blocks of [ROWS x 32]; each block is
 // ROWS/8 atoms of 8 rows x 128 bytes with the 128-byte swizzle (16-byte chunk c of row r at chunk c ^ (r & 7)).
@@ -180,7 +182,7 @@ __device__ __forceinline__ void tile_load(TileRegs<COLS_PAD>& t, const float* __
     }
   }
 }
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_hi(float x) { return to_tf32(x); }  // round-to-nearest: |x - hi| <= 2^-12 |x|
 template <int MN_VIEW, int COLS_PAD>
 __device__ __forceinline__ void tile_store(const TileRegs<COLS_PAD>& t, float* __restrict__ s_hi, float* __restrict__ s_lo) {
   constexpr int CPR = COLS_PAD / 4, U = CPR / 2, ROWSTEP = 256 / CPR;
@@ -275,8 +277,8 @@ __global__ void __launch_bounds__(256) tc_rowtile_kernel(const float* __restrict
                                B_MN ? desc_mnmajor(smem_u32(b_lo), b_rows, 0) : desc_kmajor(smem_u32(b_lo), b_rows, 0, 0)};
       const uint32_t b_blk = (uint32_t)(b_rows * 128) >> 4;  // K-major B: 16-byte units between 32-col blocks
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {  // hi*hi + lo*hi + hi*lo
-        const uint64_t ad0 = a_d[t == 1], bd0 = b_d[t == 2];
+      for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi (small terms first)
+        const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
 #pragma unroll
         for (int k8 = 0; k8 < R_pad / 8; ++k8) {
           const uint32_t a_off = (uint32_t)(((k8 >> 2) * 128 * 128 + (k8 & 3) * 32) >> 4);
@@ -394,8 +396,8 @@ __global__ void __launch_bounds__(256) tc_wgrad_kernel(const float* __restrict__
       const uint64_t a_d[2] = {desc_mnmajor(smem_u32(x_hi), 128, 0), desc_mnmajor(smem_u32(x_lo), 128, 0)};
       const uint64_t b_d[2] = {desc_mnmajor(smem_u32(y_hi), 128, 0), desc_mnmajor(smem_u32(y_lo), 128, 0)};
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const uint64_t ad0 = a_d[t == 1], bd0 = b_d[t == 2];
+      for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi
+        const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
 #pragma unroll
         for (int r8 = 0; r8 < 16; ++r8) {  // 128 samples = 16 K-steps of 8 rows (1024 bytes each)
           umma_tf32(tmem_d, ad0 + (uint32_t)(r8 * 64), bd0 + (uint32_t)(r8 * 64), idesc, accumulate | (uint32_t)((t | r8) != 0));

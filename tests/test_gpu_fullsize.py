@@ -1,0 +1,137 @@
+"""Full-size checks (BASELINE.json configs 2 and 3): whole training step vs the CPU oracle on a bounded number of rays,
+and size-independent properties of the kernels at the real 4096-ray shapes."""
+import pytest
+import torch
+
+from oracle import kplanes_oracle as ko
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _step_vs_oracle(cfg, n_rays, seed):
+    from tests.helpers import build_model, train_step_cuda
+
+    gen = torch.Generator().manual_seed(seed)
+    origins, directions, times, aabb = ko.synthetic_rays(n_rays, gen)
+    mp = ko.make_model_params(cfg, gen, aabb)
+    image = torch.rand(n_rays, 3, generator=gen)
+    rand = ko.make_rand(n_rays, mp, gen)
+    model = build_model(cfg, mp, aabb, DEV)
+    out, ld, grads = train_step_cuda(model, origins, directions, times, image, rand, 0.6, DEV)
+    ref_out, ref_ld, ref_grads = ko.train_step(mp, origins, directions, times, image, rand, anneal=0.6)
+    for k in ("rgb", "accumulation", "depth"):
+        assert rel_err(out[k].cpu(), ref_out[k].detach()) < 3e-4, k
+    for k, v in ld.items():
+        assert rel_err(v.detach().cpu(), ref_ld[k].detach()) < 3e-4, k
+    # Gradients: the decoders are ReLU networks, so a sample whose hidden pre-activation lies within fp32 rounding of 0
+    # (|pre| ~ 1e-7; a handful out of ~10^4 samples x 192 units) takes the other branch on the GPU than on the CPU and
+    # its whole feature gradient changes -- an O(1) difference on the few texels only that sample touches (verified:
+    # every deviating sample has min|pre| < 2e-6, scripts/debug_cfg2b.py).  The bar is therefore: almost all entries
+    # within 1e-4 of the tensor's max, the median relative error of the significant entries below 1e-4, and the tensor
+    # as a whole within 2e-2 in relative L2 (one flipped sample of a 128-ray batch already moves the L2 norm by ~5e-3).
+    for i, (a, b) in enumerate(zip(grads, ref_grads)):
+        a, b = a.cpu().double(), b.double()
+        mx = b.abs().max().clamp_min(1e-30)
+        frac_bad = float(((a - b).abs() > 1e-4 * mx).double().mean())
+        l2 = float((a - b).norm() / b.norm().clamp_min(1e-30))
+        big = b.abs() > 0.01 * mx
+        median_rel = float(((a - b).abs()[big] / b.abs()[big]).median()) if bool(big.any()) else 0.0
+        assert median_rel < 1e-4 or b.numel() < 100000, (i, median_rel)  # the typical plane-gradient entry meets the fp32 bar
+        assert l2 < 2e-2 and (frac_bad < 2e-2 or b.numel() < 100000), (i, frac_bad, l2)
+
+
+def test_cfg2_step_vs_oracle():
+    _step_vs_oracle("cfg2", 256, 11)
+
+
+def test_cfg3_32x_step_vs_oracle():
+    """K-Planes 32x: six scales up to 2048^2 planes (2.3 GB), sigma hidden 128 (SIMT first layer), no view dependence."""
+    _step_vs_oracle("cfg3", 128, 12)
+
+
+def test_weights_partition_of_unity_full_size():
+    from soccernerfs_b200 import ops
+
+    gen = torch.Generator().manual_seed(1)
+    for s in (48, 64, 128, 256, 257, 31):
+        d = (torch.rand(4096, s, generator=gen) * 0.05).to(DEV)
+        sig = (torch.rand(4096, s, generator=gen) ** 4 * 50).to(DEV)
+        w = ops.get_weights(d, sig)
+        total = w.double().sum(-1)
+        expect = 1.0 - torch.exp(-(d.double() * sig.double()).sum(-1))
+        assert (total - expect).abs().max() < 2e-6
+        assert (w >= 0).all()
+
+
+def test_pdf_resample_properties_full_size():
+    from soccernerfs_b200 import ops
+
+    gen = torch.Generator().manual_seed(2)
+    n, s_in, s_out = 4096, 256, 128
+    bins = torch.sort(torch.rand(n, s_in + 1, generator=gen), -1).values.to(DEV)
+    w = (torch.rand(n, s_in, generator=gen) ** 6).to(DEV)
+    nears, fars = torch.zeros(n, device=DEV), torch.full((n,), 4.0, device=DEV)
+    rand = torch.rand(n, s_out + 1, generator=gen).to(DEV)
+    sb, eb, inds, cdf = ops.pdf_resample(w, bins, nears, fars, s_out, rand, want_inds=True, want_cdf=True)
+    assert (sb[:, 1:] >= sb[:, :-1]).all() and (eb[:, 1:] >= eb[:, :-1]).all()  # sorted
+    assert (sb >= bins[:, :1]).all() and (sb <= bins[:, -1:]).all()  # inside the support
+    assert (inds[:, 1:] >= inds[:, :-1]).all() and inds.min() >= 1 and inds.max() <= s_in + 1
+    assert (cdf[:, 0] == 0).all() and (cdf[:, 1:] >= cdf[:, :-1]).all() and cdf.max() <= 1.0
+    # a delta histogram puts every sample in that bin
+    w2 = torch.zeros(n, s_in, device=DEV)
+    w2[:, 100] = 1e6
+    sb2, _, _, _ = ops.pdf_resample(w2, bins, nears, fars, s_out, None)
+    inside = (sb2 >= bins[:, 100:101]) & (sb2 <= bins[:, 101:102])
+    assert inside.float().mean() > 0.97
+
+
+def test_hexplane_multilinearity_full_size():
+    """features are linear in every single plane: scaling plane p of scale k by a scales that scale's features by a."""
+    from soccernerfs_b200.fields.kplanes_field import init_kplanes_field, interpolate_kplanes
+
+    torch.manual_seed(0)
+    grids = [init_kplanes_field(32, [64 * m, 64 * m, 64 * m, 50]).to(DEV) for m in (1, 2, 4, 8)]
+    pts = (torch.rand(4096 * 48, 4, device=DEV) * 2 - 1)
+    with torch.no_grad():
+        base = interpolate_kplanes(pts, grids, True)
+        grids[2][4].mul_(3.0)
+        scaled = interpolate_kplanes(pts, grids, True)
+    assert rel_err(scaled[:, 64:96], 3.0 * base[:, 64:96]) < 1e-6
+    assert torch.equal(scaled[:, :64], base[:, :64]) and torch.equal(scaled[:, 96:], base[:, 96:])
+
+
+def test_hexplane_gradient_checksum_full_size():
+    """sum over all texels of d(sum features)/d plane_p = sum over samples of prod_{q != p} interp_q (bilinear weights
+    sum to 1): a checksum of the scatter that does not need the oracle."""
+    from soccernerfs_b200.fields.kplanes_field import init_kplanes_field, interpolate_kplanes
+
+    torch.manual_seed(1)
+    grids = [init_kplanes_field(32, [64 * m, 64 * m, 64 * m, 50]).to(DEV) for m in (1, 8)]
+    pts = (torch.rand(4096 * 48, 4, device=DEV) * 2 - 1)
+    out = interpolate_kplanes(pts, grids, True)
+    out.sum().backward()
+    with torch.no_grad():
+        # with all planes but p set to ones the feature equals interp_p; use the time planes (init = 1): for p a space
+        # plane, prod_{q != p} interp_q = features / interp_p; check instead the simplest identity on a time plane:
+        k, p = 1, 2  # scale 8x, plane XT (time planes are exactly 1 => prod of others = product of the 3 space planes)
+        others = [g.clone() for g in grids[k]]
+        ones = torch.ones_like(others[p])
+        feats_without_p = interpolate_kplanes(pts, [[others[0], others[1], ones, others[3], others[4], others[5]]], True)
+        expect = feats_without_p.double().sum()
+        got = grids[k][p].grad.double().sum()
+    assert abs(float(got - expect)) / abs(float(expect)) < 1e-5
+
+
+def test_render_constant_colour_full_size():
+    from soccernerfs_b200 import ops
+
+    gen = torch.Generator().manual_seed(3)
+    w = (torch.rand(4096, 48, generator=gen) / 60).to(DEV)
+    c = torch.tensor([0.2, 0.5, 0.9], device=DEV)
+    rgb = c.expand(4096, 48, 3).contiguous()
+    bg = torch.rand(4096, 3, generator=gen).to(DEV)
+    comp = ops.composite_rgb(w, rgb, bg)
+    acc = ops.accumulate(w)
+    assert rel_err(comp, c[None] * acc[:, None] + bg * (1 - acc[:, None])) < 1e-6
