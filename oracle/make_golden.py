@@ -361,6 +361,73 @@ def main():
     gen_render(R)
     gen_losses(R)
     gen_model(R)
+    gen_importance(R)
+
+
+
+def _reference_method(path, class_name, method_name, extra_globals):
+    """Compile ONE method of a reference class straight from its source file (the module itself cannot be imported on
+    Python 3.12: its dataparser imports hit the mutable-dataclass-default error), so the fixture is still produced by
+    the reference's own code."""
+    import ast
+
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == method_name:
+                    fn.returns = None
+                    for a in fn.args.args:
+                        a.annotation = None
+                    mod = ast.Module(body=[fn], type_ignores=[])
+                    ast.fix_missing_locations(mod)
+                    ns = dict(extra_globals)
+                    exec(compile(mod, path, "exec"), ns)
+                    return ns[method_name]
+    raise KeyError(method_name)
+
+
+def gen_importance(R):
+    """a18: IST / ISG weight maps and the importance pixel sampler (NS/data/datasets/dynamic_dataset.py:215-470,
+    NS/data/pixel_samplers.py:51-128, 340-426)."""
+    import random
+    import time
+    import types
+
+    from nerfstudio.data import pixel_samplers as ps
+
+    g = torch.Generator().manual_seed(606)
+    b, h, w = 12, 18, 24
+    cam_ids = torch.tensor([0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3])
+    cam_times = torch.tensor([0.0, 0.1, 0.2, 0.6, 0.0, 0.005, 0.3, 0.31, 0.5, 0.5, 0.9, 0.4])[:, None]
+    images = torch.rand(b, h, w, 3, generator=g) * 0.2
+    for i in range(b):  # a moving blob per image so that temporal differences are sparse and non-trivial
+        y, x = (3 + i) % (h - 4), (5 + 2 * i) % (w - 4)
+        images[i, y:y + 4, x:x + 4] += 0.7
+    path = os.path.join(os.environ.get("KPLANES_REFERENCE_ROOT", "/root/reference"), "nerfstudio", "nerfstudio", "data",
+                        "datasets", "dynamic_dataset.py")
+    glb = dict(torch=torch, time=time, DEBUG_IST_MAPS=False, tqdm=lambda x: x, str=str, print=lambda *a, **k: None)
+    fake = types.SimpleNamespace(eval_dataset=False, ist_range=0.25, isg_gamma=5e-2,
+                                 cameras=types.SimpleNamespace(times=cam_times, ids=cam_ids[:, None]))
+    batch = {"image": images, "image_idx": torch.arange(b)}
+    ist = _reference_method(path, "DynamicDataset", "compute_ist", glb)(fake, batch, "cpu")
+    fake_isg = types.SimpleNamespace(eval_dataset=False, ist_range=0.25, isg_gamma=5e-2,
+                                     cameras=types.SimpleNamespace(times=cam_times, ids=cam_ids))
+    isg = _reference_method(path, "DynamicDataset", "compute_isg", glb)(fake_isg, batch, "cpu")
+
+    ds = types.SimpleNamespace(iters_to_start_ist=100, is_pixel_ratio=0.3)
+    sampler = ps.DynamicBasedPixelSampler(64, dataset=ds)
+    out = {}
+    for name, steps, weights in (("ist_on", 500, ist.float()), ("ist_off", 50, ist.float()), ("no_weights", 500, None)):
+        torch.manual_seed(1234)
+        random.seed(99)
+        bt = {"image": images, "image_idx": torch.arange(b) + 100, "iter_steps": steps, "ist_weights": weights}
+        col = sampler.collate_image_dataset_batch(bt, 64)
+        out[f"{name}_indices"] = col["indices"]
+        out[f"{name}_image"] = col["image"]
+    torch.manual_seed(4321)
+    uni = ps.PixelSampler(32).sample_method(32, b, h, w)
+    save("importance", images=images, cam_ids=cam_ids, cam_times=cam_times, ist=ist.float(), isg=isg.float(), uniform=uni, **out)
 
 
 if __name__ == "__main__":

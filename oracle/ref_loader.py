@@ -143,7 +143,7 @@ def _install_stubs() -> None:
         sys.modules["nerfstudio"] = pkg
     if "nerfstudio.configs" not in sys.modules:
         cfg = types.ModuleType("nerfstudio.configs")
-        cfg.__path__ = []
+        cfg.__path__ = [os.path.join(REF_PKG, "nerfstudio", "configs")]  # other submodules (config_utils) are the real ones
         sys.modules["nerfstudio.configs"] = cfg
         base = types.ModuleType("nerfstudio.configs.base_config")
 

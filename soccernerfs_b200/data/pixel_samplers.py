@@ -1,0 +1,102 @@
+"""Pixel samplers: which (image, y, x) triples make up a ray batch.
+
+``PixelSampler.sample_method`` / ``collate_image_dataset_batch`` (NS/data/pixel_samplers.py:51-128) and the
+importance sampler ``DynamicBasedPixelSampler.sample_method`` (:340-426).  Bit-exactness with the reference comes from
+making the SAME random calls in the SAME order (``random.shuffle``, ``torch.multinomial`` per image, ``torch.rand`` for
+the uniform remainder), so a shared seed reproduces the reference's indices exactly.  Host-side by design (SURVEY.md
+8a, row a18).
+"""
+from __future__ import annotations
+
+import random
+from math import floor
+from typing import Dict, Optional, Union
+
+import torch
+
+
+class PixelSampler:
+    def __init__(self, num_rays_per_batch: int, keep_full_image: bool = False, **kwargs) -> None:
+        self.kwargs = kwargs
+        self.num_rays_per_batch = num_rays_per_batch
+        self.keep_full_image = keep_full_image
+
+    def set_num_rays_per_batch(self, num_rays_per_batch: int):
+        self.num_rays_per_batch = num_rays_per_batch
+
+    def sample_method(self, batch_size: int, num_images: int, image_height: int, image_width: int,
+                      mask: Optional[torch.Tensor] = None, batch: Optional[Dict] = None,
+                      device: Union[torch.device, str] = "cpu") -> torch.Tensor:
+        """Uniform over all pixels of all images (or over the mask's non-zero pixels) -> int64 [batch_size, 3]."""
+        if isinstance(mask, torch.Tensor):
+            nonzero_indices = torch.nonzero(mask[..., 0], as_tuple=False)
+            chosen = random.sample(range(len(nonzero_indices)), k=batch_size)
+            return nonzero_indices[chosen]
+        return torch.floor(
+            torch.rand((batch_size, 3), device=device) * torch.tensor([num_images, image_height, image_width], device=device)
+        ).long()
+
+    def collate_image_dataset_batch(self, batch: Dict, num_rays_per_batch: int, keep_full_image: bool = False):
+        device = batch["image"].device
+        num_images, image_height, image_width, _ = batch["image"].shape
+        kwargs = dict(batch=batch, device=device)
+        if "mask" in batch:
+            kwargs["mask"] = batch["mask"]
+        indices = self.sample_method(num_rays_per_batch, num_images, image_height, image_width, **kwargs)
+        c, y, x = (i.flatten() for i in torch.split(indices, 1, dim=-1))
+        collated = {k: v[c, y, x] for k, v in batch.items() if k not in ("image_idx", "iter_steps") and v is not None}
+        assert collated["image"].shape == (num_rays_per_batch, 3), collated["image"].shape
+        indices[:, 0] = batch["image_idx"][c]  # random image slots -> absolute camera indices
+        collated["indices"] = indices
+        if keep_full_image:
+            collated["full_image"] = batch["image"]
+        return collated
+
+    def sample(self, image_batch: Dict):
+        if isinstance(image_batch["image"], torch.Tensor):
+            return self.collate_image_dataset_batch(image_batch, self.num_rays_per_batch, keep_full_image=self.keep_full_image)
+        raise ValueError("image_batch['image'] must be a torch.Tensor")
+
+
+class DynamicBasedPixelSampler(PixelSampler):
+    """Samples ``is_pixel_ratio`` of the batch proportionally to the IST/ISG weight maps, the rest uniformly."""
+
+    def __init__(self, num_rays_per_batch: int, keep_full_image: bool = False, **kwargs) -> None:
+        self.dataset = kwargs["dataset"]
+        super().__init__(num_rays_per_batch, keep_full_image, **kwargs)
+
+    def sample_method(self, batch_size: int, num_images: int, image_height: int, image_width: int,
+                      mask: Optional[torch.Tensor] = None, batch: Optional[Dict] = None,
+                      device: Union[torch.device, str] = "cpu") -> torch.Tensor:
+        assert batch is not None, "Batch information must be provided for DynamicBasedPixelSampler"
+        if "ist_weights" not in batch or batch["ist_weights"] is None:
+            return super().sample_method(batch_size, num_images, image_height, image_width, mask=mask, device=device)
+        sampled = 0
+        use_ist = batch["iter_steps"] > self.dataset.iters_to_start_ist and batch["ist_weights"] is not None
+        if use_ist:
+            num_ist = floor(self.dataset.is_pixel_ratio * batch_size)
+            per_image = 10 * (-(-num_ist // num_images))
+            weights = batch["ist_weights"]
+            indices = torch.zeros((num_ist, 3), device=device)
+            order = list(range(num_images))
+            random.shuffle(order)  # usually only part of the images is needed: shuffle so all maps get used over time
+            for i in order:
+                if sampled >= num_ist:
+                    break
+                wmap = weights[i]
+                k = per_image if sampled + per_image <= num_ist else num_ist - sampled
+                nnz = len(torch.nonzero(wmap))
+                if nnz == 0:  # camera that sees no motion
+                    continue
+                samples = torch.multinomial(wmap.flatten(), k, replacement=(nnz < k))
+                h, w = torch.div(samples, image_width, rounding_mode="floor"), samples % image_width
+                indices[sampled: sampled + k, 0] = i
+                indices[sampled: sampled + k, 1] = h
+                indices[sampled: sampled + k, 2] = w
+                sampled += k
+            if sampled < num_ist:
+                indices = indices[:sampled]
+        uniform = super().sample_method(batch_size - sampled, num_images, image_height, image_width, mask=mask, device=device)
+        if use_ist:
+            return torch.cat((indices, uniform), dim=0).long()
+        return uniform

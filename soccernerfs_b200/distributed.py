@@ -71,3 +71,29 @@ def world_info() -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+@torch.no_grad()
+def render_frame_sharded(model, camera_ray_bundle, rank: int, world: int, chunk: Optional[int] = None):
+    """Evaluation sharding (BASELINE config 5): this rank renders the ray chunks ``i % world == rank`` of a
+    full [H,W] camera ray bundle -- the chunking of ``Model.get_outputs_for_camera_ray_bundle``
+    (NS/models/base_model.py:162-186) distributed round-robin, with NO collective on the data path.
+    Returns ``{(start, end): outputs_dict}`` for the owned chunks; ``assemble_frame`` stitches the pieces of all ranks
+    (after e.g. ``dist.gather_object`` or peer copies to the writer rank)."""
+    chunk = chunk or model.config.eval_num_rays_per_chunk
+    flat = camera_ray_bundle.flatten()
+    pieces = {}
+    for start, end in round_robin_chunks(len(flat), chunk, rank, world):
+        pieces[(start, end)] = {k: v for k, v in model.forward(ray_bundle=flat[start:end]).items() if torch.is_tensor(v)}
+    return pieces
+
+
+def assemble_frame(pieces_per_rank, image_height: int, image_width: int):
+    """Concatenate the chunk outputs of all ranks in ray order -> {name: [H,W,C]}."""
+    merged = {}
+    for pieces in pieces_per_rank:
+        merged.update(pieces)
+    keys = sorted(merged)
+    assert keys[0][0] == 0 and all(a[1] == b[0] for a, b in zip(keys, keys[1:])) and keys[-1][1] == image_height * image_width
+    names = merged[keys[0]].keys()
+    return {n: torch.cat([merged[k][n] for k in keys]).view(image_height, image_width, -1) for n in names}

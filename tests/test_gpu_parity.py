@@ -410,3 +410,26 @@ def test_grad_sinks_match_autograd_accumulation():
         grads[mode] = [p.grad.detach().clone() for p in model_params_in_oracle_order(model)]
     for a, b in zip(grads["autograd"], grads["sink"]):
         assert rel_err(b, a) < 1e-5
+
+
+def test_tile_sharded_eval_equals_unsharded():
+    """config 5: a frame rendered as round-robin ray chunks by 3 'ranks' equals the single-process chunked render."""
+    from soccernerfs_b200.cameras.rays import RayBundle
+    from soccernerfs_b200.distributed import assemble_frame, render_frame_sharded
+    from tests.helpers import build_model
+    from tests.test_oracle_golden import load_tiny_model
+
+    g = load_golden("model_tiny")
+    model = build_model("tiny", load_tiny_model(g), g["aabb"], DEV)
+    model.eval()
+    model.config.eval_num_rays_per_chunk = 17
+    n = g["origins"].shape[0]
+    h, w = 8, n // 8
+    rb = RayBundle(origins=g["origins"].view(h, w, 3).to(DEV), directions=g["directions"].view(h, w, 3).to(DEV),
+                   pixel_area=torch.ones(h, w, 1, device=DEV), times=g["times"].view(h, w, 1).to(DEV))
+    full = model.get_outputs_for_camera_ray_bundle(rb)
+    pieces = [render_frame_sharded(model, rb, r, 3) for r in range(3)]
+    assert sum(len(p) for p in pieces) == -(-n // 17) and all(len(p) > 0 for p in pieces)
+    frame = assemble_frame(pieces, h, w)
+    for k in ("rgb", "depth", "accumulation", "median_rgb"):
+        assert torch.equal(frame[k], full[k]), k

@@ -1,0 +1,56 @@
+"""a18: IST/ISG weight maps and importance pixel sampling vs the fixture produced by the reference's own code
+(oracle/make_golden.py::gen_importance).  Host-side logic: runs on CPU.  Indices are bit-exact given the seeds."""
+import random
+
+import torch
+
+from soccernerfs_b200.data.datamanagers.dynamic_datamanager import (
+    DynamicDataManagerConfig,
+    importance_weights,
+    make_pixel_sampler,
+)
+from soccernerfs_b200.data.pixel_samplers import DynamicBasedPixelSampler, PixelSampler
+from tests.conftest import load_golden
+
+
+def test_datamanager_option_defaults_match_reference():
+    """NS/data/datamanagers/dynamic_datamanager.py:34-59."""
+    c = DynamicDataManagerConfig()
+    assert (c.use_importance_sampling, c.is_pixel_ratio, c.ist_range, c.isg, c.isg_gamma, c.iters_to_start_is, c.pick_mode) == (
+        True, 0.1, 0.25, False, 5e-2, 5000, "normal")
+
+
+def test_ist_and_isg_weight_maps_match_reference():
+    g = load_golden("importance")
+    cfg = DynamicDataManagerConfig(ist_range=0.25)
+    ist = importance_weights(cfg, g["images"], g["cam_ids"], g["cam_times"])
+    assert ist.dtype == torch.float16 and torch.equal(ist.float(), g["ist"])
+    isg = importance_weights(DynamicDataManagerConfig(isg=True), g["images"], g["cam_ids"], g["cam_times"])
+    assert torch.equal(isg.float(), g["isg"])
+    assert importance_weights(DynamicDataManagerConfig(use_importance_sampling=False), g["images"], g["cam_ids"], g["cam_times"]) is None
+    # image 11 is the only frame of camera 3 -> uniform map; frames closer than 0.01 are not compared
+    assert bool((g["ist"][11] == 1).all())
+
+
+def test_importance_pixel_sampler_bit_exact():
+    g = load_golden("importance")
+    cfg = DynamicDataManagerConfig(is_pixel_ratio=0.3, iters_to_start_is=100)
+    sampler = make_pixel_sampler(cfg, 64)
+    assert isinstance(sampler, DynamicBasedPixelSampler)
+    b = g["images"].shape[0]
+    for name, steps, weights in (("ist_on", 500, g["ist"]), ("ist_off", 50, g["ist"]), ("no_weights", 500, None)):
+        torch.manual_seed(1234)
+        random.seed(99)
+        batch = {"image": g["images"], "image_idx": torch.arange(b) + 100, "iter_steps": steps, "ist_weights": weights}
+        col = sampler.collate_image_dataset_batch(batch, 64)
+        assert torch.equal(col["indices"], g[f"{name}_indices"]), name
+        assert torch.equal(col["image"], g[f"{name}_image"]), name
+    # with IST on, the importance share of the batch lands on moving pixels only
+    idx = g["ist_on_indices"]
+    n_ist = int(0.3 * 64)
+    w = g["ist"][idx[:n_ist, 0] - 100, idx[:n_ist, 1], idx[:n_ist, 2]]
+    assert bool((w > 0).all())
+    torch.manual_seed(4321)
+    h, wd = g["images"].shape[1:3]
+    assert torch.equal(PixelSampler(32).sample_method(32, b, h, wd), g["uniform"])
+    assert isinstance(make_pixel_sampler(DynamicDataManagerConfig(use_importance_sampling=False), 8), PixelSampler)
