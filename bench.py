@@ -211,7 +211,8 @@ def run_ours(args):
     # ---- per-kernel durations for the roofline: CUDA events around the field kernels on their launch stream,
     #      measured live in eager mode (events cannot be timed inside a graph replay), L2 flushed per step ------
     trainer.use_cuda_graph = False
-    _lib.TIMED.update(ALGO_BYTES.keys())
+    _lib.TIMED.update(list(ALGO_BYTES.keys()) + ["kp_decoder_fwd_fused", "kp_color_net_bwd", "kp_sigma_net_bwd", "kp_adam_multi",
+                                                 "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd"])
     _lib.EVENTS.clear()
     for i in range(args.steps):
         flush.zero_()

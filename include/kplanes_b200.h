@@ -107,6 +107,15 @@ int kp_tc_linear_bwd_weight(const float* dY, int64_t lddy, const float* X, int64
                             int N, int K, void* stream);
 int kp_tc_supported(int N, int K); /* 1 if the tensor-core path covers a layer with N outputs and K inputs */
 
+/* Fused decoder forward (sigma_net + SH + color_net for hidden widths 64, feature width <= 128) in ONE tcgen05 kernel:
+ * weights resident in shared memory, activations never leave the SM between layers.  h1/cin/h2/h3 may be NULL
+ * (inference): then only o [M,16], density [M] and rgb [M,3] are written.  Replaces kp_sigma_net_fwd + kp_color_net_fwd
+ * (NS/fields/kplanes_field.py:302-311, 314-358). */
+int kp_decoder_fused_supported(int K0, int H1, int H2);
+int kp_decoder_fwd_fused(const float* feats, int K0, const float* directions /* [N,3] or NULL */, int S, const float* w1,
+                         const float* w2, const float* w3, const float* w4, const float* w5, int64_t M, int H1, int H2,
+                         float* h1, float* cin, float* h2, float* h3, float* o, float* density, float* rgb, void* stream);
+
 /* ---- (a13) AABBBoxCollider._intersect_with_aabb, NS/model_components/scene_colliders.py:57-95 ---- */
 int kp_aabb_intersect(const float* origins, const float* directions, int64_t N, const float* aabb_host6,
                       float near_plane, float* nears, float* fars, void* stream);

@@ -225,9 +225,37 @@ class KPlanesField(Field, _AabbHostMixin):
         return rgb.view(*batch, 3)
 
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False, mask=None, bg_color=None):
+        fused = self._forward_fused(ray_samples)
+        if fused is not None:
+            return fused
         density, density_features = self.get_density(ray_samples)
         rgb = self.get_outputs(ray_samples, density_features)
         return {FieldHeadNames.DENSITY: density, FieldHeadNames.RGB: rgb}
+
+    def _forward_fused(self, ray_samples: RaySamples):
+        """get_density + get_outputs with both decoders in ONE tensor-core kernel (same numbers as the two-call path);
+        None when the decoder shape is not covered (e.g. the 192 -> 128 sigma net of the 32x config)."""
+        w1, w2 = self.sigma_net.weights
+        w3, w4, w5 = self.color_net.weights
+        if not ops.decoder_fused_supported(self.feature_dim, w1.shape[0], w3.shape[0]):
+            return None
+        batch = ray_samples.frustums.shape
+        n_samples = batch[-1]
+        dirs = None
+        if not self.disable_viewing_dependent:
+            d = ray_samples.frustums.directions
+            if not (n_samples > 1 and d.stride(-2) == 0):
+                return None
+            dirs = d[..., 0, :].reshape(-1, 3)
+        points = self._points(ray_samples)
+        ms = self._planes()
+        if points.D != (4 if len(ms[0]) == 6 else 3):
+            raise RuntimeError("dynamic K-Planes field needs ray_samples.times")
+        feats = ops.hexplane_features(ms, points, self.concat_features_across_scales,
+                                      _use_mask(len(ms[0]), self.freeze_time_planes),
+                                      post_backward=getattr(self, "_kp_post_backward", None))
+        _, density, rgb = ops.decoder_fused(feats, dirs, n_samples, w1, w2, w3, w4, w5)
+        return {FieldHeadNames.DENSITY: density.view(*batch, 1), FieldHeadNames.RGB: rgb.view(*batch, 3)}
 
 
 class KPlanesDensityField(Field, _AabbHostMixin):

@@ -314,6 +314,75 @@ def color_net(directions: Optional[torch.Tensor], samples_per_ray: int, geo: tor
     return _ColorNet.apply(directions, samples_per_ray, geo, w3, w4, w5)
 
 
+class _DecoderFused(torch.autograd.Function):
+    """sigma_net + SH + color_net in one tcgen05 kernel (forward); the backward runs the per-layer tensor-core kernels
+    on the activations the forward saved (none are saved, and none written, when no gradient is needed)."""
+
+    @staticmethod
+    def forward(ctx, feats, directions, samples_per_ray: int, w1, w2, w3, w4, w5):
+        ctx.wsinks = tuple(grad_sink(w) for w in (w1, w2, w3, w4, w5))
+        x = f32c(feats.detach())
+        ws = [f32c(w.detach()) for w in (w1, w2, w3, w4, w5)]
+        m, k = x.shape
+        view_dep = directions is not None
+        d = f32c(directions.detach()) if view_dep else None
+        dev = x.device
+        need_grad = any(ctx.needs_input_grad)
+        h1 = torch.empty((m, 64), dtype=torch.float32, device=dev) if need_grad else None
+        h2 = torch.empty((m, 64), dtype=torch.float32, device=dev) if need_grad else None
+        h3 = torch.empty((m, 64), dtype=torch.float32, device=dev) if need_grad else None
+        cin = torch.empty((m, 32 if view_dep else 16), dtype=torch.float32, device=dev) if need_grad else None
+        o = torch.empty((m, 16), dtype=torch.float32, device=dev)
+        density = torch.empty((m,), dtype=torch.float32, device=dev)
+        rgb = torch.empty((m, 3), dtype=torch.float32, device=dev)
+        call("kp_decoder_fwd_fused", ptr(x), k, ptr(d), samples_per_ray, *[ptr(w) for w in ws], m, 64, 64, ptr(h1), ptr(cin),
+             ptr(h2), ptr(h3), ptr(o), ptr(density), ptr(rgb), stream_ptr())
+        if need_grad:
+            ctx.save_for_backward(x, h1, o, cin, h2, h3, rgb, *ws)
+        ctx.view_dep = view_dep
+        return o, density, rgb
+
+    @staticmethod
+    def backward(ctx, grad_o, grad_density, grad_rgb):
+        x, h1, o, cin, h2, h3, rgb, w1c, w2c, w3c, w4c, w5c = ctx.saved_tensors
+        m, k = x.shape
+        dev = x.device
+        sinks = ctx.wsinks
+        if all(s is not None and s.is_contiguous() for s in sinks):
+            gws, ret = list(sinks), (None,) * 5
+        else:
+            flat = torch.zeros(sum(w.numel() for w in (w1c, w2c, w3c, w4c, w5c)), dtype=torch.float32, device=dev)
+            gws, off = [], 0
+            for w in (w1c, w2c, w3c, w4c, w5c):
+                gws.append(flat[off: off + w.numel()].view_as(w))
+                off += w.numel()
+            ret = tuple(gws)
+        go = torch.empty((m, 16), dtype=torch.float32, device=dev)
+        if grad_rgb is not None:
+            sa, sb = torch.empty_like(h2), torch.empty_like(h2)
+            call("kp_color_net_bwd", int(ctx.view_dep), ptr(cin), ptr(h2), ptr(h3), ptr(rgb), ptr(w3c), ptr(w4c), ptr(w5c), m, 64,
+                 ptr(f32c(grad_rgb)), ptr(go), ptr(gws[2]), ptr(gws[3]), ptr(gws[4]), ptr(sa), ptr(sb), stream_ptr())
+            if grad_o is not None:
+                go = go + f32c(grad_o)
+        else:
+            go = f32c(grad_o) if grad_o is not None else None
+        gx = torch.empty_like(x)
+        scratch = torch.empty_like(h1)
+        call("kp_sigma_net_bwd", ptr(x), ptr(w1c), ptr(w2c), m, k, 64, ptr(h1), ptr(o),
+             ptr(None if grad_density is None else f32c(grad_density)), ptr(go), ptr(gx), ptr(gws[0]), ptr(gws[1]), ptr(scratch),
+             stream_ptr())
+        return (gx, None, None, *ret)
+
+
+def decoder_fused_supported(k0: int, h1: int, h2: int) -> bool:
+    return bool(_lib.load().kp_decoder_fused_supported(int(k0), int(h1), int(h2)))
+
+
+def decoder_fused(feats, directions, samples_per_ray: int, w1, w2, w3, w4, w5):
+    """-> (o [M,16], density [M], rgb [M,3]).  KPlanesField.get_density + get_outputs in one kernel."""
+    return _DecoderFused.apply(feats, directions, samples_per_ray, w1, w2, w3, w4, w5)
+
+
 # ------------------------------------------------------------------------------------------------
 # (a13, a7, a8) ray setup and resampling (no gradients: bins are detached, ray_samplers.py:357)
 # ------------------------------------------------------------------------------------------------

@@ -219,7 +219,7 @@ def test_decoders_and_density_field_vs_oracle():
     gen = torch.Generator().manual_seed(11)
     n, s = 37, 9
     origins, directions, times, aabb = ko.synthetic_rays(n, gen)
-    for view_dep, hid in ((True, 64), (False, 128)):
+    for view_dep, hid in ((True, 64), (False, 128), (False, 64)):
         fp = ko.make_field_params(aabb, (12, 10, 14, 5), 32, (1, 2, 4), gen, sigma_hidden=hid, view_dependent=view_dep)
         nears, fars = ko.aabb_collider(origins, directions, aabb)
         smp = ko.uniform_sampler(origins, directions, nears, fars, times, s, torch.rand(n, s + 1, generator=gen))
