@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 1
+#define KP_ABI_VERSION 2
 #define KP_MAX_SCALES 8
 #define KP_MAX_PLANES 6
 
@@ -126,7 +126,7 @@ int kp_aabb_intersect(const float* origins, const float* directions, int64_t N, 
  *      Outputs spacing bins [N,S+1] and euclidean bins [N,S+1]. ------------------------------------- */
 int kp_uniform_bins(const float* lin_bins, const float* t_rand, int rand_stride, const float* nears,
                     const float* fars, int64_t N, int S, int spacing, float* spacing_bins, float* euclid_bins,
-                    void* stream);
+                    float* starts, float* ends, float* deltas /* [N,S] each, all three or none */, void* stream);
 
 /* ---- (a8) PDFSampler.generate_ray_samples (include_original=False), ray_samplers.py:274-369:
  *      warp-per-ray inverse-CDF search.  weights [N,S_in] (already annealed), existing spacing bins
@@ -136,7 +136,10 @@ int kp_uniform_bins(const float* lin_bins, const float* t_rand, int rand_stride,
 int kp_pdf_resample(const float* weights, const float* existing_bins, int S_in, const float* u_base,
                     const float* rand, int rand_stride, const float* nears, const float* fars, int64_t N,
                     int S_out, float histogram_padding, float eps, int spacing, float* cdf_out /* [N,S_in+1] or NULL */,
-                    float* spacing_bins, float* euclid_bins, int64_t* inds /* [N,S_out+1] or NULL */, void* stream);
+                    float* spacing_bins, float* euclid_bins, int64_t* inds /* [N,S_out+1] or NULL */,
+                    const float* anneal_dev /* DEVICE scalar or NULL */, float anneal_host /* used if anneal_dev NULL:
+                    weights are raised to this power first, ray_samplers.py:584 */,
+                    float* starts, float* ends, float* deltas /* [N,S_out] each or NULL */, void* stream);
 
 /* ---- (a10) RaySamples.get_weights, NS/cameras/rays.py:127-149: warp-per-ray transmittance scan ---- */
 int kp_weights_fwd(const float* deltas, const float* densities, int64_t N, int S, float* weights, void* stream);
@@ -151,7 +154,8 @@ int kp_render_fwd(const float* weights, const float* rgb /* [N,S,3] or NULL */, 
                   const float* bg /* [N,3] or NULL */, int bg_mode, int nan_to_num_rgb, int64_t N, int S,
                   float* comp_rgb /* [N,3] or NULL */, float* accumulation /* [N] or NULL */,
                   int64_t* median_index /* [N] or NULL */, float* expected_depth /* [N] or NULL (unclipped) */,
-                  void* stream);
+                  const float* starts, const float* ends /* [N,S], for median_depth */,
+                  float* median_depth /* [N] or NULL: (starts+ends)/2 at the median index */, void* stream);
 int kp_render_bwd(const float* weights, const float* rgb, const float* bg, int bg_mode, int64_t N, int S,
                   const float* grad_comp /* [N,3] or NULL */, const float* grad_acc /* [N] or NULL */,
                   float* grad_weights /* [N,S] */, float* grad_rgb /* [N,S,3] or NULL */, void* stream);

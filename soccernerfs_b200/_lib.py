@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkplanes_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 LAUNCH_COUNT = 0  # number of C-ABI kernel-launching calls made (bench.py reports it as gpu_launches evidence)
@@ -49,11 +49,12 @@ SIGNATURES = {
     "kp_decoder_fused_supported": ([c_int, c_int, c_int], c_int),
     "kp_decoder_fwd_fused": ([_P, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P], c_int),
     "kp_aabb_intersect": ([_P, _P, c_int64, POINTER(c_float), c_float, _P, _P, _P], c_int),
-    "kp_uniform_bins": ([_P, _P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P], c_int),
-    "kp_pdf_resample": ([_P, _P, c_int, _P, _P, c_int, _P, _P, c_int64, c_int, c_float, c_float, c_int, _P, _P, _P, _P, _P], c_int),
+    "kp_uniform_bins": ([_P, _P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P], c_int),
+    "kp_pdf_resample": ([_P, _P, c_int, _P, _P, c_int, _P, _P, c_int64, c_int, c_float, c_float, c_int, _P, _P, _P, _P, _P, c_float,
+                         _P, _P, _P, _P], c_int),
     "kp_weights_fwd": ([_P, _P, c_int64, c_int, _P, _P], c_int),
     "kp_weights_bwd": ([_P, _P, _P, c_int64, c_int, _P, _P], c_int),
-    "kp_render_fwd": ([_P, _P, _P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _P, _P], c_int),
+    "kp_render_fwd": ([_P, _P, _P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P], c_int),
     "kp_render_bwd": ([_P, _P, _P, c_int, c_int64, c_int, _P, _P, _P, _P, _P], c_int),
     "kp_distortion_fwd": ([_P, _P, c_int64, c_int, _P, _P], c_int),
     "kp_distortion_bwd": ([_P, _P, _P, c_int64, c_int, _P, _P], c_int),

@@ -97,15 +97,16 @@ class RayBundle(TensorDataclass):
         return self.flatten()[start_idx:end_idx]
 
     def get_ray_samples(self, bin_starts, bin_ends, spacing_starts=None, spacing_ends=None,
-                        spacing_to_euclidean_fn: Optional[Callable] = None) -> RaySamples:
-        """Frustums for bins [bin_starts, bin_ends] ([..., S, 1]) along every ray.  rays.py:233-277."""
+                        spacing_to_euclidean_fn: Optional[Callable] = None, deltas=None) -> RaySamples:
+        """Frustums for bins [bin_starts, bin_ends] ([..., S, 1]) along every ray.  rays.py:233-277.
+        ``deltas`` (extension): bin_ends - bin_starts when the sampler kernel already produced it."""
         shaped = self[..., None]
         frustums = Frustums(origins=shaped.origins, directions=shaped.directions, starts=bin_starts, ends=bin_ends,
                             pixel_area=shaped.pixel_area)
         return RaySamples(
             frustums=frustums,
             camera_indices=None if self.camera_indices is None else self.camera_indices[..., None],
-            deltas=bin_ends - bin_starts,
+            deltas=bin_ends - bin_starts if deltas is None else deltas,
             spacing_starts=spacing_starts,
             spacing_ends=spacing_ends,
             spacing_to_euclidean_fn=spacing_to_euclidean_fn,

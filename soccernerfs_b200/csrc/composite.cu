@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) weights_bwd_kernel(const f
 __global__ void __launch_bounds__(32 * kRaysPerBlock) render_fwd_kernel(
     const float* __restrict__ weights, const float* __restrict__ rgb, const float* __restrict__ steps,
     const float* __restrict__ bg, int bg_mode, int nan_rgb, int64_t N, int S, float* __restrict__ comp,
-    float* __restrict__ acc_out, int64_t* __restrict__ median, float* __restrict__ exp_depth) {
+    float* __restrict__ acc_out, int64_t* __restrict__ median, float* __restrict__ exp_depth,
+    const float* __restrict__ starts, const float* __restrict__ ends, float* __restrict__ median_depth) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) render_fwd_kernel(
     if (steps != nullptr) dsum = fmaf(wi, steps[n * S + i], dsum);
   }
   // median index: first i with cumsum(w)[i] >= 0.5  == count(cumsum < 0.5), clamped (renderers.py:260-263)
-  if (median != nullptr) {
+  if (median != nullptr || median_depth != nullptr) {
     double run = warp_incl_scan_d(part, lane) - part;
     int cnt = 0;
     for (int i = i0; i < i1; ++i) {
@@ -113,7 +114,12 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) render_fwd_kernel(
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) median[n] = (int64_t)min(cnt, S - 1);
+    if (lane == 0) {
+      const int mi = min(cnt, S - 1);
+      if (median != nullptr) median[n] = (int64_t)mi;
+      // DepthRenderer "median": steps = (starts + ends) / 2 gathered at the median index (renderers.py:256-264)
+      if (median_depth != nullptr) median_depth[n] = __fdiv_rn(__fadd_rn(starts[n * S + mi], ends[n * S + mi]), 2.f);
+    }
   }
   a = warp_sum(a);
   if (rgb != nullptr) { r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); }
@@ -203,14 +209,17 @@ extern "C" int kp_weights_bwd(const float* deltas, const float* densities, const
 
 extern "C" int kp_render_fwd(const float* weights, const float* rgb, const float* steps, const float* bg, int bg_mode,
                              int nan_to_num_rgb, int64_t N, int S, float* comp_rgb, float* accumulation,
-                             int64_t* median_index, float* expected_depth, void* stream) {
+                             int64_t* median_index, float* expected_depth, const float* starts, const float* ends,
+                             float* median_depth, void* stream) {
   if (N == 0) return 0;
   KP_CHECK(weights && S >= 1, "render_fwd: bad arguments");
   KP_CHECK(comp_rgb == nullptr || rgb != nullptr, "render_fwd: comp_rgb needs rgb");
   KP_CHECK(comp_rgb == nullptr || bg_mode == 1 || bg != nullptr, "render_fwd: tensor background is NULL");
   KP_CHECK(expected_depth == nullptr || steps != nullptr, "render_fwd: expected_depth needs steps");
+  KP_CHECK(median_depth == nullptr || (starts != nullptr && ends != nullptr), "render_fwd: median_depth needs starts/ends");
   render_fwd_kernel<<<(unsigned)ceil_div(N, kRaysPerBlock), 32 * kRaysPerBlock, 0, as_stream(stream)>>>(
-      weights, rgb, steps, bg, bg_mode, nan_to_num_rgb, N, S, comp_rgb, accumulation, median_index, expected_depth);
+      weights, rgb, steps, bg, bg_mode, nan_to_num_rgb, N, S, comp_rgb, accumulation, median_index, expected_depth, starts,
+      ends, median_depth);
   KP_LAUNCH_CHECK("render_fwd");
   return 0;
 }

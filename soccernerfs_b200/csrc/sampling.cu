@@ -47,14 +47,8 @@ __device__ __forceinline__ float to_euclid(float x, float s_near, float s_far, i
   return spacing_fn_inv(v, mode);
 }
 
-__global__ void uniform_bins_kernel(const float* __restrict__ lin, const float* __restrict__ t_rand, int rand_stride,
-                                    const float* __restrict__ nears, const float* __restrict__ fars, int64_t N, int S,
-                                    int mode, float* __restrict__ sbins, float* __restrict__ ebins) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nb = S + 1;
-  if (idx >= N * nb) return;
-  const int64_t n = idx / nb;
-  const int j = (int)(idx % nb);
+__device__ __forceinline__ float uniform_bin(const float* __restrict__ lin, const float* __restrict__ t_rand, int rand_stride,
+                                             int64_t n, int j, int S) {
   float b = lin[j];
   if (t_rand != nullptr) {
     const float upper = j < S ? __fdiv_rn(__fadd_rn(lin[j + 1], lin[j]), 2.f) : lin[S];
@@ -62,8 +56,29 @@ __global__ void uniform_bins_kernel(const float* __restrict__ lin, const float* 
     const float r = rand_stride ? t_rand[n * rand_stride + j] : t_rand[n];
     b = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), r));
   }
+  return b;
+}
+
+__global__ void uniform_bins_kernel(const float* __restrict__ lin, const float* __restrict__ t_rand, int rand_stride,
+                                    const float* __restrict__ nears, const float* __restrict__ fars, int64_t N, int S,
+                                    int mode, float* __restrict__ sbins, float* __restrict__ ebins,
+                                    float* __restrict__ starts, float* __restrict__ ends, float* __restrict__ deltas) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = S + 1;
+  if (idx >= N * nb) return;
+  const int64_t n = idx / nb;
+  const int j = (int)(idx % nb);
+  const float s_near = spacing_fn(nears[n], mode), s_far = spacing_fn(fars[n], mode);
+  const float b = uniform_bin(lin, t_rand, rand_stride, n, j, S);
+  const float e = to_euclid(b, s_near, s_far, mode);
   sbins[idx] = b;
-  ebins[idx] = to_euclid(b, spacing_fn(nears[n], mode), spacing_fn(fars[n], mode), mode);
+  ebins[idx] = e;
+  if (starts != nullptr && j < S) {  // frustum starts / ends / deltas (rays.py:254-262) written contiguously
+    const float e1 = to_euclid(uniform_bin(lin, t_rand, rand_stride, n, j + 1, S), s_near, s_far, mode);
+    starts[n * S + j] = e;
+    ends[n * S + j] = e1;
+    deltas[n * S + j] = __fsub_rn(e1, e);
+  }
 }
 
 // sum_i (x[i] + pad) over one fp32 row, reproducing BIT FOR BIT what torch.sum(dim=-1) returns on CPU for a
@@ -112,15 +127,25 @@ __global__ void __launch_bounds__(128) pdf_resample_kernel(
     const float* __restrict__ weights, const float* __restrict__ existing, int S_in, const float* __restrict__ u_base,
     const float* __restrict__ rand, int rand_stride, float eval_offset, const float* __restrict__ nears,
     const float* __restrict__ fars, int64_t N, int S_out, float hist_pad, float eps, int mode,
-    float* __restrict__ cdf_out, float* __restrict__ sbins, float* __restrict__ ebins, int64_t* __restrict__ inds_out) {
+    float* __restrict__ cdf_out, float* __restrict__ sbins, float* __restrict__ ebins, int64_t* __restrict__ inds_out,
+    const float* __restrict__ anneal_dev, float anneal_host, float* __restrict__ starts, float* __restrict__ ends,
+    float* __restrict__ deltas) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (n >= N) return;
   const int nb_in = S_in + 1;
-  float* s_cdf = smem + (size_t)warp * 2 * nb_in;
+  float* s_cdf = smem + (size_t)warp * 3 * nb_in;
   float* s_bins = s_cdf + nb_in;
-  const float* w_row = weights + n * S_in;
+  float* s_w = s_bins + nb_in;
+  // proposal-weight annealing, torch.pow(weights, anneal) (ray_samplers.py:584), folded in; anneal == 1 is a no-op
+  const float anneal = anneal_dev != nullptr ? *anneal_dev : anneal_host;
+  for (int i = lane; i < S_in; i += 32) {
+    const float wv = weights[n * S_in + i];
+    s_w[i] = (anneal == 1.0f) ? wv : powf(wv, anneal);
+  }
+  __syncwarp();
+  const float* w_row = s_w;
   const int epl = (S_in + 31) / 32;  // contiguous elements per lane
   const int i0 = lane * epl, i1 = min(S_in, i0 + epl);
   // weights + histogram_padding (ray_samplers.py:302), row sum in torch's CPU summation order (see below)
@@ -168,6 +193,15 @@ __global__ void __launch_bounds__(128) pdf_resample_kernel(
     ebins[n * nb_out + j] = to_euclid(b, s_near, s_far, mode);
     if (inds_out != nullptr) inds_out[n * nb_out + j] = (int64_t)lo;
   }
+  if (starts != nullptr) {
+    __syncwarp();  // the warp's euclidean bins are visible to all its lanes
+    for (int j = lane; j < S_out; j += 32) {
+      const float e0 = ebins[n * nb_out + j], e1 = ebins[n * nb_out + j + 1];
+      starts[n * S_out + j] = e0;
+      ends[n * S_out + j] = e1;
+      deltas[n * S_out + j] = __fsub_rn(e1, e0);
+    }
+  }
 }
 
 }  // namespace kp
@@ -186,15 +220,17 @@ extern "C" int kp_aabb_intersect(const float* origins, const float* directions, 
 
 extern "C" int kp_uniform_bins(const float* lin_bins, const float* t_rand, int rand_stride, const float* nears,
                                const float* fars, int64_t N, int S, int spacing, float* spacing_bins, float* euclid_bins,
-                               void* stream) {
+                               float* starts, float* ends, float* deltas, void* stream) {
   if (N == 0) return 0;
   KP_CHECK(lin_bins && nears && fars && spacing_bins && euclid_bins, "uniform_bins: NULL argument");
   KP_CHECK(S >= 1, "uniform_bins: S=%d", S);
   KP_CHECK(spacing == 0 || spacing == 1, "uniform_bins: spacing=%d unsupported", spacing);
   KP_CHECK(t_rand == nullptr || rand_stride == 0 || rand_stride == S + 1, "uniform_bins: t_rand must be [N,S+1] or [N,1]");
+  KP_CHECK((starts == nullptr) == (ends == nullptr) && (starts == nullptr) == (deltas == nullptr),
+           "uniform_bins: starts/ends/deltas must be given together");
   const int64_t total = N * (S + 1);
   uniform_bins_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
-      lin_bins, t_rand, rand_stride, nears, fars, N, S, spacing, spacing_bins, euclid_bins);
+      lin_bins, t_rand, rand_stride, nears, fars, N, S, spacing, spacing_bins, euclid_bins, starts, ends, deltas);
   KP_LAUNCH_CHECK("uniform_bins");
   return 0;
 }
@@ -202,19 +238,20 @@ extern "C" int kp_uniform_bins(const float* lin_bins, const float* t_rand, int r
 extern "C" int kp_pdf_resample(const float* weights, const float* existing_bins, int S_in, const float* u_base,
                                const float* rand, int rand_stride, const float* nears, const float* fars, int64_t N,
                                int S_out, float histogram_padding, float eps, int spacing, float* cdf_out,
-                               float* spacing_bins, float* euclid_bins, int64_t* inds, void* stream) {
+                               float* spacing_bins, float* euclid_bins, int64_t* inds, const float* anneal_dev,
+                               float anneal_host, float* starts, float* ends, float* deltas, void* stream) {
   if (N == 0) return 0;
   KP_CHECK(weights && existing_bins && u_base && nears && fars && spacing_bins && euclid_bins, "pdf_resample: NULL argument");
   KP_CHECK(S_in >= 1 && S_out >= 1, "pdf_resample: S_in=%d S_out=%d", S_in, S_out);
   KP_CHECK(spacing == 0 || spacing == 1, "pdf_resample: spacing=%d unsupported", spacing);
   KP_CHECK(rand == nullptr || rand_stride == 0 || rand_stride == S_out + 1, "pdf_resample: rand must be [N,S_out+1] or [N,1]");
-  const size_t smem = (size_t)4 * 2 * (S_in + 1) * sizeof(float);
+  const size_t smem = (size_t)4 * 3 * (S_in + 1) * sizeof(float);
   KP_CHECK(smem <= 200 * 1024, "pdf_resample: S_in=%d too large", S_in);
   if (smem > 48 * 1024) cudaFuncSetAttribute(pdf_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const float eval_offset = (float)(1.0 / (2.0 * (S_out + 1)));
   pdf_resample_kernel<<<(unsigned)ceil_div(N, 4), 128, smem, as_stream(stream)>>>(
       weights, existing_bins, S_in, u_base, rand, rand_stride, eval_offset, nears, fars, N, S_out, histogram_padding, eps,
-      spacing, cdf_out, spacing_bins, euclid_bins, inds);
+      spacing, cdf_out, spacing_bins, euclid_bins, inds, anneal_dev, anneal_host, starts, ends, deltas);
   KP_LAUNCH_CHECK("pdf_resample");
   return 0;
 }

@@ -41,7 +41,9 @@ def lossfun_outer(t: torch.Tensor, w: torch.Tensor, t_env: torch.Tensor, w_env: 
 
 def ray_samples_to_sdist(ray_samples: RaySamples) -> torch.Tensor:
     """[N,S+1] bin edges in the normalised spacing domain (losses.py:98-103)."""
-    return torch.cat([ray_samples.spacing_starts[..., 0], ray_samples.spacing_ends[..., -1:, 0]], dim=-1)
+    from .ray_samplers import spacing_edges
+
+    return spacing_edges(ray_samples)
 
 
 def interlevel_loss(weights_list: List[torch.Tensor], ray_samples_list: List[RaySamples]) -> torch.Tensor:

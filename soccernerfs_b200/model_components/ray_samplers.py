@@ -44,17 +44,35 @@ class Sampler(nn.Module):
         return self.generate_ray_samples(*args, **kwargs)
 
 
-def _to_ray_samples(ray_bundle: RayBundle, spacing_bins, euclid_bins, spacing_to_euclidean_fn) -> RaySamples:
+def _to_ray_samples(ray_bundle: RayBundle, spacing_bins, euclid_bins, spacing_to_euclidean_fn, frustums=None) -> RaySamples:
+    """``frustums`` = contiguous (starts, ends, deltas) [N,S] written by the sampler kernel; without it they are
+    strided views of ``euclid_bins`` like in the reference."""
     shape = ray_bundle.origins.shape[:-1]
     sb = spacing_bins.view(*shape, -1)
-    eb = euclid_bins.view(*shape, -1)
-    return ray_bundle.get_ray_samples(
-        bin_starts=eb[..., :-1, None],
-        bin_ends=eb[..., 1:, None],
+    if frustums is None:
+        eb = euclid_bins.view(*shape, -1)
+        starts, ends, deltas = eb[..., :-1, None], eb[..., 1:, None], None
+    else:
+        starts, ends, deltas = (x.view(*shape, -1, 1) for x in frustums)
+    rs = ray_bundle.get_ray_samples(
+        bin_starts=starts,
+        bin_ends=ends,
         spacing_starts=sb[..., :-1, None],
         spacing_ends=sb[..., 1:, None],
         spacing_to_euclidean_fn=spacing_to_euclidean_fn,
+        deltas=deltas,
     )
+    rs._kp_sdist = sb  # the [.., S+1] edges spacing_starts/ends are views of (saves re-concatenating them)
+    return rs
+
+
+def spacing_edges(ray_samples: RaySamples) -> torch.Tensor:
+    """[..., S+1] spacing-domain bin edges: cat(spacing_starts, spacing_ends[-1]) (ray_samplers.py:331-338,
+    losses.py:98-103), taken from the sampler's own edge tensor when the samples came from one of ours."""
+    sb = getattr(ray_samples, "_kp_sdist", None)
+    if sb is not None and sb.shape[:-1] == ray_samples.spacing_starts.shape[:-2]:
+        return sb
+    return torch.cat([ray_samples.spacing_starts[..., 0], ray_samples.spacing_ends[..., -1:, 0]], dim=-1)
 
 
 class SpacedSampler(Sampler):
@@ -83,12 +101,13 @@ class SpacedSampler(Sampler):
                 t_rand = torch.rand((num_rays, 1), dtype=torch.float32, device=device)
             else:
                 t_rand = torch.rand((num_rays, num_samples + 1), dtype=torch.float32, device=device)
-        sb, eb = ops.uniform_bins(ray_bundle.nears, ray_bundle.fars, num_samples, t_rand, self.spacing_mode)
+        sb, eb, *fr = ops.uniform_bins(ray_bundle.nears, ray_bundle.fars, num_samples, t_rand, self.spacing_mode,
+                                       want_frustums=True)
         s_near, s_far = (self.spacing_fn(x) for x in (ray_bundle.nears, ray_bundle.fars))
         spacing_to_euclidean_fn = lambda x: self.spacing_fn_inv(x * s_far + (1 - x) * s_near)  # noqa: E731
         # tag the closure so PDFSampler can evaluate the same function inside its kernel instead of calling it
         spacing_to_euclidean_fn._kp_spacing = (self.spacing_mode, ray_bundle.nears, ray_bundle.fars)
-        return _to_ray_samples(ray_bundle, sb, eb, spacing_to_euclidean_fn)
+        return _to_ray_samples(ray_bundle, sb, eb, spacing_to_euclidean_fn, fr)
 
 
 class UniformSampler(SpacedSampler):
@@ -119,7 +138,10 @@ class PDFSampler(Sampler):
         self.record_inds = False
 
     def generate_ray_samples(self, ray_bundle: Optional[RayBundle] = None, ray_samples: Optional[RaySamples] = None,
-                             weights: torch.Tensor = None, num_samples: Optional[int] = None, eps: float = 1e-5) -> RaySamples:
+                             weights: torch.Tensor = None, num_samples: Optional[int] = None, eps: float = 1e-5,
+                             anneal=1.0) -> RaySamples:
+        """``anneal`` (extension): exponent applied to ``weights`` inside the kernel -- the proposal sampler's
+        torch.pow(weights, anneal) of ray_samplers.py:584 without a separate pass."""
         if ray_samples is None or ray_bundle is None:
             raise ValueError("ray_samples and ray_bundle must be provided")
         num_samples = num_samples or self.num_samples
@@ -137,19 +159,21 @@ class PDFSampler(Sampler):
                 rand = torch.rand((n, 1), device=w.device)
             else:
                 rand = torch.rand((n, num_samples + 1), device=w.device)
-        existing_bins = torch.cat([ray_samples.spacing_starts[..., 0], ray_samples.spacing_ends[..., -1:, 0]], dim=-1)
+        existing_bins = spacing_edges(ray_samples)
         tag = getattr(ray_samples.spacing_to_euclidean_fn, "_kp_spacing", None)
         kernel_euclid = tag is not None and not self.include_original
         mode, nears, fars = tag if kernel_euclid else (0, torch.zeros(n, device=w.device), torch.ones(n, device=w.device))
-        sb, eb, inds, _ = ops.pdf_resample(w, existing_bins.reshape(n, s_in + 1), nears, fars, num_samples, rand,
-                                           self.histogram_padding, eps, spacing=mode, want_inds=self.record_inds)
+        sb, eb, inds, _, *fr = ops.pdf_resample(w, existing_bins.reshape(n, s_in + 1), nears, fars, num_samples, rand,
+                                                self.histogram_padding, eps, spacing=mode, want_inds=self.record_inds,
+                                                anneal=anneal, want_frustums=kernel_euclid)
         self.last_inds = inds
         if self.include_original:
             sb, _ = torch.sort(torch.cat([existing_bins.reshape(n, -1), sb], -1), -1)
         if not kernel_euclid:  # foreign spacing function: evaluate its closure like the reference (:359)
             shape = ray_bundle.origins.shape[:-1]
             eb = ray_samples.spacing_to_euclidean_fn(sb.view(*shape, -1))
-        return _to_ray_samples(ray_bundle, sb, eb, ray_samples.spacing_to_euclidean_fn)
+            fr = None
+        return _to_ray_samples(ray_bundle, sb, eb, ray_samples.spacing_to_euclidean_fn, fr)
 
 
 def _density_field_of(fn: Callable):
@@ -211,12 +235,9 @@ class ProposalNetworkSampler(Sampler):
                 ray_samples = self.initial_sampler(ray_bundle, num_samples=num_samples)
             else:
                 assert weights is not None
+                # annealed_weights = pow(weights, _anneal) (ray_samplers.py:584) is applied inside the PDF kernel;
                 # _anneal may be a device scalar tensor (CUDA-graph training step) or the reference's python float
-                if isinstance(self._anneal, torch.Tensor) or self._anneal != 1.0:
-                    annealed_weights = torch.pow(weights, self._anneal)
-                else:
-                    annealed_weights = weights  # pow(w, 1.0) == w
-                ray_samples = self.pdf_sampler(ray_bundle, ray_samples, annealed_weights, num_samples=num_samples)
+                ray_samples = self.pdf_sampler(ray_bundle, ray_samples, weights, num_samples=num_samples, anneal=self._anneal)
             if is_prop:
                 with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
                     fast = _density_field_of(density_fns[i_level])

@@ -102,12 +102,12 @@ class DepthRenderer(nn.Module):
 
     def forward(self, weights: torch.Tensor, ray_samples: RaySamples, ray_indices=None, num_rays=None) -> torch.Tensor:
         _no_packed(ray_indices, num_rays)
-        steps = (ray_samples.frustums.starts + ray_samples.frustums.ends) / 2
         s = weights.shape[-2]
         batch = weights.shape[:-2]
-        if self.method == "median":
-            idx = ops.median_index(weights.reshape(-1, s)).view(*batch, 1)
-            return torch.gather(steps[..., 0], dim=-1, index=idx)
+        if self.method == "median":  # (starts + ends)/2 gathered at the median index, in one kernel
+            fr = ray_samples.frustums
+            return ops.median_depth(weights.reshape(-1, s), fr.starts.reshape(-1, s), fr.ends.reshape(-1, s)).view(*batch, 1)
+        steps = (ray_samples.frustums.starts + ray_samples.frustums.ends) / 2
         if self.method == "expected":
             if weights.requires_grad and torch.is_grad_enabled():  # differentiable variant: plain torch (not on the k-planes path)
                 depth = torch.sum(weights * steps, dim=-2) / (torch.sum(weights, -2) + 1e-10)

@@ -406,26 +406,32 @@ def _cached_linspace(key, start, end, steps, device):
     return _LINSPACE_CACHE[k]
 
 
-def uniform_bins(nears, fars, num_samples: int, t_rand: Optional[torch.Tensor], spacing: int = 0):
-    """-> (spacing_bins [N,S+1], euclidean_bins [N,S+1]).  ray_samplers.py:79-126."""
+def uniform_bins(nears, fars, num_samples: int, t_rand: Optional[torch.Tensor], spacing: int = 0, want_frustums: bool = False):
+    """-> (spacing_bins [N,S+1], euclidean_bins [N,S+1][, starts, ends, deltas [N,S]]).  ray_samplers.py:79-126."""
     nears, fars = f32c(nears).view(-1), f32c(fars).view(-1)
     n = nears.shape[0]
     lin = _cached_linspace("uni", 0.0, 1.0, num_samples + 1, nears.device)
     sb = torch.empty((n, num_samples + 1), dtype=torch.float32, device=nears.device)
     eb = torch.empty_like(sb)
+    fr = torch.empty((3, n, num_samples), dtype=torch.float32, device=nears.device) if want_frustums else None
     stride = 0
     if t_rand is not None:
         t_rand = f32c(t_rand)
         stride = 0 if t_rand.shape[-1] == 1 else num_samples + 1
     call("kp_uniform_bins", ptr(lin), ptr(t_rand), stride, ptr(nears), ptr(fars), n, num_samples, spacing, ptr(sb), ptr(eb),
+         ptr(fr[0] if want_frustums else None), ptr(fr[1] if want_frustums else None), ptr(fr[2] if want_frustums else None),
          stream_ptr())
+    if want_frustums:
+        return sb, eb, fr[0], fr[1], fr[2]
     return sb, eb
 
 
 def pdf_resample(weights, existing_bins, nears, fars, num_samples: int, rand: Optional[torch.Tensor],
                  histogram_padding: float = 0.01, eps: float = 1e-5, spacing: int = 0, want_inds: bool = False,
-                 want_cdf: bool = False):
-    """-> (spacing_bins [N,S_out+1], euclidean_bins, inds int64 | None, cdf | None).  ray_samplers.py:274-369."""
+                 want_cdf: bool = False, anneal=1.0, want_frustums: bool = False):
+    """-> (spacing_bins [N,S_out+1], euclidean_bins, inds int64 | None, cdf | None[, starts, ends, deltas]).
+    ``anneal``: python float or 0-d device tensor; weights are raised to this power first (ray_samplers.py:584).
+    ray_samplers.py:274-369."""
     w, eb_in = f32c(weights.detach()), f32c(existing_bins.detach())
     nears, fars = f32c(nears).view(-1), f32c(fars).view(-1)
     n, s_in = w.shape
@@ -435,12 +441,18 @@ def pdf_resample(weights, existing_bins, nears, fars, num_samples: int, rand: Op
     eb = torch.empty_like(sb)
     inds = torch.empty((n, nb), dtype=torch.int64, device=w.device) if want_inds else None
     cdf = torch.empty((n, s_in + 1), dtype=torch.float32, device=w.device) if want_cdf else None
+    fr = torch.empty((3, n, num_samples), dtype=torch.float32, device=w.device) if want_frustums else None
     stride = 0
     if rand is not None:
         rand = f32c(rand)
         stride = 0 if rand.shape[-1] == 1 else nb
+    anneal_dev, anneal_host = (anneal.detach().float().reshape(1), 1.0) if isinstance(anneal, torch.Tensor) else (None, float(anneal))
     call("kp_pdf_resample", ptr(w), ptr(eb_in), s_in, ptr(u_base), ptr(rand), stride, ptr(nears), ptr(fars), n, num_samples,
-         float(histogram_padding), float(eps), spacing, ptr(cdf), ptr(sb), ptr(eb), ptr(inds), stream_ptr())
+         float(histogram_padding), float(eps), spacing, ptr(cdf), ptr(sb), ptr(eb), ptr(inds), ptr(anneal_dev), anneal_host,
+         ptr(fr[0] if want_frustums else None), ptr(fr[1] if want_frustums else None), ptr(fr[2] if want_frustums else None),
+         stream_ptr())
+    if want_frustums:
+        return sb, eb, inds, cdf, fr[0], fr[1], fr[2]
     return sb, eb, inds, cdf
 
 
@@ -478,7 +490,7 @@ class _CompositeRGB(torch.autograd.Function):
         b = None if bg is None else f32c(bg.detach().expand(n, 3))
         comp = torch.empty((n, 3), dtype=torch.float32, device=w.device)
         call("kp_render_fwd", ptr(w), ptr(c), ptr(None), ptr(b), bg_mode, int(nan_to_num), n, s, ptr(comp), ptr(None), ptr(None),
-             ptr(None), stream_ptr())
+             ptr(None), ptr(None), ptr(None), ptr(None), stream_ptr())
         ctx.save_for_backward(w, c, b)
         ctx.bg_mode = bg_mode
         return comp
@@ -509,7 +521,7 @@ class _Accumulate(torch.autograd.Function):
         n, s = w.shape
         acc = torch.empty((n,), dtype=torch.float32, device=w.device)
         call("kp_render_fwd", ptr(w), ptr(None), ptr(None), ptr(None), 0, 0, n, s, ptr(None), ptr(acc), ptr(None), ptr(None),
-             stream_ptr())
+             ptr(None), ptr(None), ptr(None), stream_ptr())
         ctx.shape = (n, s)
         return acc
 
@@ -529,8 +541,18 @@ def median_index(weights: torch.Tensor) -> torch.Tensor:
     n, s = w.shape
     idx = torch.empty((n,), dtype=torch.int64, device=w.device)
     call("kp_render_fwd", ptr(w), ptr(None), ptr(None), ptr(None), 0, 0, n, s, ptr(None), ptr(None), ptr(idx), ptr(None),
-         stream_ptr())
+         ptr(None), ptr(None), ptr(None), stream_ptr())
     return idx
+
+
+def median_depth(weights: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor) -> torch.Tensor:
+    """(starts + ends)/2 at the median index, one kernel (DepthRenderer "median", renderers.py:256-264) -> [N]."""
+    w, st, en = f32c(weights.detach()), f32c(starts.detach()), f32c(ends.detach())
+    n, s = w.shape
+    out = torch.empty((n,), dtype=torch.float32, device=w.device)
+    call("kp_render_fwd", ptr(w), ptr(None), ptr(None), ptr(None), 0, 0, n, s, ptr(None), ptr(None), ptr(None), ptr(None),
+         ptr(st), ptr(en), ptr(out), stream_ptr())
+    return out
 
 
 def expected_depth(weights: torch.Tensor, steps: torch.Tensor) -> torch.Tensor:
@@ -539,7 +561,7 @@ def expected_depth(weights: torch.Tensor, steps: torch.Tensor) -> torch.Tensor:
     n, s = w.shape
     out = torch.empty((n,), dtype=torch.float32, device=w.device)
     call("kp_render_fwd", ptr(w), ptr(None), ptr(st), ptr(None), 0, 0, n, s, ptr(None), ptr(None), ptr(None), ptr(out),
-         stream_ptr())
+         ptr(None), ptr(None), ptr(None), stream_ptr())
     return out
 
 

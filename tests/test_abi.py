@@ -36,7 +36,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.kp_abi_version() == 1
+    assert lib.kp_abi_version() == 2
     assert isinstance(lib.kp_last_error(), bytes)
 
 
@@ -49,7 +49,8 @@ def test_argument_validation_without_gpu(lib):
     pts = _lib.make_points(D=5)
     rc = lib.kp_hexplane_fwd(c_void_p(0), c_void_p(0), 1, 6, 32, pts, 0, 1, 0x3F, c_void_p(0), c_void_p(0))
     assert rc != 0 and b"points.D" in lib.kp_last_error()
-    rc = lib.kp_uniform_bins(c_void_p(0), c_void_p(0), 0, c_void_p(0), c_void_p(0), 4, 8, 0, c_void_p(0), c_void_p(0), c_void_p(0))
+    rc = lib.kp_uniform_bins(c_void_p(0), c_void_p(0), 0, c_void_p(0), c_void_p(0), 4, 8, 0, c_void_p(0), c_void_p(0), c_void_p(0),
+                             c_void_p(0), c_void_p(0), c_void_p(0))
     assert rc != 0 and b"NULL" in lib.kp_last_error()
 
 

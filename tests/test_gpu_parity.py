@@ -26,7 +26,7 @@ def test_library_loaded_and_abi():
     from soccernerfs_b200 import _lib
 
     lib = _lib.load()
-    assert lib.kp_abi_version() == 1
+    assert lib.kp_abi_version() == 2
 
 
 def test_hexplane_vs_reference_fixture():
@@ -123,6 +123,30 @@ def test_pdf_search_bit_exact_given_cdf():
     del prev
 
 
+def test_sampler_frustum_outputs_and_in_kernel_anneal():
+    """The extra kernel outputs are exactly the views the reference takes: starts = bins[:-1], ends = bins[1:],
+    deltas = ends - starts; pow(weights, anneal) inside the PDF kernel == torch.pow before it."""
+    from soccernerfs_b200 import ops
+
+    gen = torch.Generator().manual_seed(11)
+    n, s0, s1 = 300, 64, 48
+    nears, fars = torch.rand(n, 1, generator=gen).to(DEV), (2 + torch.rand(n, 1, generator=gen)).to(DEV)
+    for mode in (0, 1):
+        t_rand = torch.rand(n, s0 + 1, generator=gen).to(DEV)
+        sb, eb, st, en, de = ops.uniform_bins(nears, fars, s0, t_rand, mode, want_frustums=True)
+        sb2, eb2 = ops.uniform_bins(nears, fars, s0, t_rand, mode)
+        assert torch.equal(sb, sb2) and torch.equal(eb, eb2)
+        assert torch.equal(st, eb[:, :-1]) and torch.equal(en, eb[:, 1:]) and torch.equal(de, eb[:, 1:] - eb[:, :-1])
+        w = torch.rand(n, s0, generator=gen).to(DEV)
+        rand = torch.rand(n, s1 + 1, generator=gen).to(DEV)
+        for anneal in (0.37, torch.tensor(0.37, device=DEV)):
+            a = ops.pdf_resample(w, sb, nears, fars, s1, rand, spacing=mode, anneal=anneal, want_frustums=True, want_inds=True)
+            b = ops.pdf_resample(torch.pow(w, 0.37), sb, nears, fars, s1, rand, spacing=mode, want_inds=True)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+            assert torch.equal(a[4], a[1][:, :-1]) and torch.equal(a[5], a[1][:, 1:])
+            assert torch.equal(a[6], a[1][:, 1:] - a[1][:, :-1])
+
+
 def test_compositing_vs_reference_fixture():
     from soccernerfs_b200 import ops
 
@@ -140,6 +164,8 @@ def test_compositing_vs_reference_fixture():
     idx = ops.median_index(w)
     assert torch.equal(idx.cpu(), ko.median_index(g["weights"])[:, 0])  # int64, bit-exact
     assert torch.equal(torch.gather(steps, -1, idx[:, None]).cpu(), g["depth_median"])
+    md = ops.median_depth(w, starts[:, :-1].to(DEV), starts[:, 1:].to(DEV))  # same thing, one kernel
+    assert torch.equal(md.cpu(), g["depth_median"][:, 0])
     ed = ops.expected_depth(w, steps)
     assert rel_err(torch.clip(ed, steps.min(), steps.max()).cpu(), g["depth_expected"][:, 0]) < TOL
     ((comp * g["go_rgb"].to(DEV)).sum() + (acc * g["go_acc"][:, 0].to(DEV)).sum() + (w * g["go_w"][..., 0].to(DEV)).sum()).backward()
