@@ -149,7 +149,9 @@ def run_ours(args):
     model = KPlanesModelConfig().setup(scene_box=SceneBox(aabb=aabb), num_train_data=19 * 25).to(dev)
     perturb_time_planes(model)
     model.proposal_sampler.update_sched = lambda step: 0  # proposal networks evaluated with grad + trained EVERY step
-    trainer = TrainStep(model, data_parallel=True, use_cuda_graph=not args.eager)
+    prop_overlap = {"auto": None, "on": True, "off": False}[args.prop_overlap]
+    trainer = TrainStep(model, data_parallel=True, use_cuda_graph=not args.eager, overlap_branches=not args.no_overlap,
+                        overlap_proposal_backward=prop_overlap)
     n_steps = args.warmup + args.steps
     host = _make_batches(n_steps, RAYS_PER_RANK, seed=1000 + rank)
     resident = [h.to(dev) for h in host]
@@ -334,6 +336,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="keep the regulariser / proposal branches on the main stream")
+    ap.add_argument("--prop-overlap", choices=["auto", "on", "off"], default="auto",
+                    help="proposal-network backward on a side stream (auto: on for 1 GPU, off under data parallelism)")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python each step instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -17,14 +17,21 @@ import torch
 
 from ..cameras.rays import RayBundle
 from ..distributed import GradBucket, world_info
-from ..models.kplanes import KPlanesModel, TrainingCallbackLocation
+from ..models.kplanes import KPlanesModel, TrainingCallbackLocation, scale_dict
 from .optimizers import Optimizers, cosine_decay_factor
 
 
 class TrainStep:
     def __init__(self, model: KPlanesModel, max_steps: int = 30000, lr: float = 1e-2, eps: float = 1e-12,
                  warm_up_end: int = 512, data_parallel: bool = False, use_cuda_graph: bool = False,
-                 fuse_grad_accumulation: bool = True) -> None:
+                 fuse_grad_accumulation: bool = True, overlap_branches: bool = True,
+                 overlap_proposal_backward: Optional[bool] = None) -> None:
+        """``overlap_branches``: run the two branches of the step that do not depend on the main field's backward on
+        their own CUDA streams (same arithmetic, same results): the plane regularisers (forward AND backward depend on
+        the planes only) during the forward pass, and the back-propagation through the proposal networks (depends on
+        the interlevel loss only) next to the decoder/scatter backward.  Needs the gradient sinks.
+        ``overlap_proposal_backward``: None = automatic -- on for a single process; off under data parallelism, where
+        the proposal backward is instead kept AFTER the field scatter so that it hides the field bucket's all-reduce."""
         self.model = model
         self.max_steps, self.base_lr, self.warm_up_end = max_steps, lr, warm_up_end
         self.optimizers = Optimizers(model.get_param_groups(), lr=lr, eps=eps, warm_up_end=warm_up_end, max_steps=max_steps)
@@ -43,6 +50,13 @@ class TrainStep:
         if self.reduce_grads:
             model.field._kp_post_backward = self._start_field_allreduce
             self._comm_stream = torch.cuda.Stream()
+        on_cuda = next(model.parameters()).is_cuda
+        self.overlap = bool(overlap_branches and fuse_grad_accumulation and on_cuda)
+        self._reg_stream = torch.cuda.Stream() if self.overlap else None
+        if overlap_proposal_backward is None:
+            overlap_proposal_backward = not self.reduce_grads
+        self._prop_stream = torch.cuda.Stream() if (self.overlap and overlap_proposal_backward) else None
+        model.proposal_sampler.side_stream = self._prop_stream
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self._graph_out: Dict[bool, Dict[str, torch.Tensor]] = {}
@@ -61,11 +75,27 @@ class TrainStep:
         from .. import ops
 
         self._reg_mark = ops.PLANE_REG_BACKWARDS
+        regs = None
+        main = torch.cuda.current_stream() if self.overlap else None
+        if self.overlap:
+            # regulariser branch: values and gradients (straight into the zeroed sinks) on its own stream, under the
+            # forward pass; joined before the main backward, whose scatter kernels update the same gradients atomically
+            self._reg_stream.wait_stream(main)
+            with torch.cuda.stream(self._reg_stream):
+                regs = model.regularizer_losses()
+                if regs:
+                    regs = scale_dict(regs, model.config.loss_coefficients)
+                    sum(regs.values()).backward()
+                    regs = {k: v.detach() for k, v in regs.items()}
         outputs = model(ray_bundle)
         metrics = model.get_metrics_dict(outputs, batch)
-        loss_dict = model.get_loss_dict(outputs, batch, metrics)
+        if self.overlap:
+            main.wait_stream(self._reg_stream)
+        loss_dict = model.get_loss_dict(outputs, batch, metrics, regularizers=regs)
         loss = sum(loss_dict.values())
         loss.backward()
+        if self._prop_stream is not None:
+            main.wait_stream(self._prop_stream)  # proposal-network backward ran on the sampler's side stream
         grad_scale = 1.0
         if self.reduce_grads:
             main = torch.cuda.current_stream()

@@ -10,6 +10,7 @@ nerfplayer-nerfacto and are not built.
 """
 from __future__ import annotations
 
+import contextlib
 import functools
 from abc import abstractmethod
 from typing import Callable, List, Optional, Tuple
@@ -212,6 +213,10 @@ class ProposalNetworkSampler(Sampler):
         self._anneal = 1.0
         self._steps_since_update = 0
         self._step = 0
+        # extension: a CUDA stream the proposal fields' density + weights are evaluated on.  Autograd replays a node's
+        # backward on the stream its forward ran on, so the back-propagation through the proposal networks (which
+        # depends only on the interlevel loss) then runs concurrently with the main field's backward.
+        self.side_stream: Optional["torch.cuda.Stream"] = None
 
     def set_anneal(self, anneal: float) -> None:
         self._anneal = anneal
@@ -239,14 +244,22 @@ class ProposalNetworkSampler(Sampler):
                 # _anneal may be a device scalar tensor (CUDA-graph training step) or the reference's python float
                 ray_samples = self.pdf_sampler(ray_bundle, ray_samples, weights, num_samples=num_samples, anneal=self._anneal)
             if is_prop:
-                with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
-                    fast = _density_field_of(density_fns[i_level])
-                    if fast is not None and (fast[1] is None or fast[1] is ray_bundle.times):
-                        # same numbers as density_fn(get_positions()), without materialising positions
-                        density, _ = fast[0].get_density(ray_samples)
-                    else:
-                        density = density_fns[i_level](ray_samples.frustums.get_positions())
-                weights = ray_samples.get_weights(density)
+                side = self.side_stream if (updated and torch.is_grad_enabled() and ray_bundle.origins.is_cuda) else None
+                if side is not None:
+                    main = torch.cuda.current_stream()
+                    side.wait_stream(main)
+                with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                    with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
+                        fast = _density_field_of(density_fns[i_level])
+                        if fast is not None and (fast[1] is None or fast[1] is ray_bundle.times):
+                            # same numbers as density_fn(get_positions()), without materialising positions
+                            density, _ = fast[0].get_density(ray_samples)
+                        else:
+                            density = density_fns[i_level](ray_samples.frustums.get_positions())
+                    weights = ray_samples.get_weights(density)
+                if side is not None:
+                    main.wait_stream(side)
+                    weights.record_stream(main)
                 weights_list.append(weights)
                 ray_samples_list.append(ray_samples)
         if updated:

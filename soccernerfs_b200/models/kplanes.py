@@ -277,7 +277,38 @@ class KPlanesModel(Model):
                 ) / len(outputs["weights_list"])
         return metrics_dict
 
-    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
+    def regularizer_losses(self) -> Dict[str, torch.Tensor]:
+        """The plane regularisers of the loss dict (kplanes.py:430-446), UNSCALED.  They depend on the planes only,
+        not on the batch, which lets a training step evaluate them off the critical path."""
+        loss_coef = self.config.loss_coefficients
+        out: Dict[str, torch.Tensor] = {}
+        ms_grids_nerf = self.field.grids
+        ms_grids_prop = [p.grids for p in self.proposal_networks]
+        dynamic = len(self.config.spacetime_resolution) > 3 and not self.config.freeze_time_planes
+        reg_keys = ("space_tv_loss", "space_tv_proposal_loss", "sparse_transients_loss", "sparse_transients_proposal_loss",
+                    "time_smoothness_loss", "time_smoothness_proposal_loss")
+        if dynamic and all(k in loss_coef for k in reg_keys):
+            # the six regularisers of kplanes.py:430-446 from one pass over the planes (same values)
+            out.update(kplanes_regularizers(ms_grids_nerf, ms_grids_prop))
+            return out
+        if "space_tv_loss" in loss_coef:
+            out["space_tv_loss"] = space_tv_loss(ms_grids_nerf)
+        if "space_tv_proposal_loss" in loss_coef:
+            out["space_tv_proposal_loss"] = space_tv_loss(ms_grids_prop)
+        if dynamic:
+            if "sparse_transients_loss" in loss_coef:
+                out["sparse_transients_loss"] = sparse_transients_loss(ms_grids_nerf)
+            if "sparse_transients_proposal_loss" in loss_coef:
+                out["sparse_transients_proposal_loss"] = sparse_transients_loss(ms_grids_prop)
+            if "time_smoothness_loss" in loss_coef:
+                out["time_smoothness_loss"] = time_smoothness_loss(ms_grids_nerf)
+            if "time_smoothness_proposal_loss" in loss_coef:
+                out["time_smoothness_proposal_loss"] = time_smoothness_loss(ms_grids_prop)
+        return out
+
+    def get_loss_dict(self, outputs, batch, metrics_dict=None, regularizers=None) -> Dict[str, torch.Tensor]:
+        """kplanes.py:410-452.  ``regularizers`` (extension): already SCALED regulariser terms computed (and possibly
+        already back-propagated) by the caller; they are merged instead of being evaluated here."""
         device = outputs["rgb"].device
         image = batch["image"].to(device)
         loss_dict = {"rgb_loss": self.rgb_loss(image, outputs["rgb"])}
@@ -287,31 +318,14 @@ class KPlanesModel(Model):
                 loss_dict["distortion_loss"] = distortion_loss(outputs["weights_list"], outputs["ray_samples_list"])
             if "interlevel_loss" in loss_coef:
                 loss_dict["interlevel_loss"] = interlevel_loss(outputs["weights_list"], outputs["ray_samples_list"])
-            ms_grids_nerf = self.field.grids
-            ms_grids_prop = [p.grids for p in self.proposal_networks]
-            dynamic = len(self.config.spacetime_resolution) > 3 and not self.config.freeze_time_planes
-            reg_keys = ("space_tv_loss", "space_tv_proposal_loss", "sparse_transients_loss", "sparse_transients_proposal_loss",
-                        "time_smoothness_loss", "time_smoothness_proposal_loss")
-            if dynamic and all(k in loss_coef for k in reg_keys):
-                # the six regularisers of kplanes.py:430-446 from one pass over the planes (same values)
-                loss_dict.update(kplanes_regularizers(ms_grids_nerf, ms_grids_prop))
-            else:
-                if "space_tv_loss" in loss_coef:
-                    loss_dict["space_tv_loss"] = space_tv_loss(ms_grids_nerf)
-                if "space_tv_proposal_loss" in loss_coef:
-                    loss_dict["space_tv_proposal_loss"] = space_tv_loss(ms_grids_prop)
-                if dynamic:
-                    if "sparse_transients_loss" in loss_coef:
-                        loss_dict["sparse_transients_loss"] = sparse_transients_loss(ms_grids_nerf)
-                    if "sparse_transients_proposal_loss" in loss_coef:
-                        loss_dict["sparse_transients_proposal_loss"] = sparse_transients_loss(ms_grids_prop)
-                    if "time_smoothness_loss" in loss_coef:
-                        loss_dict["time_smoothness_loss"] = time_smoothness_loss(ms_grids_nerf)
-                    if "time_smoothness_proposal_loss" in loss_coef:
-                        loss_dict["time_smoothness_proposal_loss"] = time_smoothness_loss(ms_grids_prop)
+            if regularizers is None:
+                loss_dict.update(self.regularizer_losses())
             if "depth_image" in batch.keys() and loss_coef["depth_loss"] > 0:
                 loss_dict["depth_loss"] = metrics_dict["depth_loss"]
-        return scale_dict(loss_dict, loss_coef)
+        loss_dict = scale_dict(loss_dict, loss_coef)
+        if self.training and regularizers is not None:
+            loss_dict.update(regularizers)
+        return loss_dict
 
     def _get_sigma(self):
         if not self.config.should_decay_sigma:

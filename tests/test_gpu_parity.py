@@ -406,6 +406,42 @@ def test_cuda_graph_train_step_matches_eager():
     del copy
 
 
+def test_branch_overlap_streams_do_not_change_the_step():
+    """Regularisers and proposal-network backward on side streams (TrainStep(overlap_branches=True)) vs everything
+    on one stream: same losses and parameters, eagerly and from the captured graph."""
+    from soccernerfs_b200.engine.trainer import TrainStep
+    from tests.helpers import build_model, ray_bundle
+    from tests.test_oracle_golden import load_tiny_model
+
+    g = load_golden("model_tiny")
+    mp = load_tiny_model(g)
+    runs = {}
+    for mode in ("serial", "overlap", "overlap-graph"):
+        model = build_model("tiny", mp, g["aabb"], DEV)
+        model.config.background_color_train = "black"
+        model.proposal_sampler.initial_sampler.train_stratified = False
+        model.proposal_sampler.pdf_sampler.train_stratified = False
+        step = TrainStep(model, max_steps=100, warm_up_end=4, use_cuda_graph=mode.endswith("graph"),
+                         overlap_branches=mode != "serial")
+        assert step.overlap == (mode != "serial")
+        losses, regs = [], []
+        for i in range(6):
+            rb = ray_bundle(g["origins"], g["directions"], g["times"], DEV)
+            out = step(rb, {"image": g["image"].to(DEV)})
+            losses.append(float(out["loss"]))
+            regs.append(float(out["space_tv_loss"]))
+        torch.cuda.synchronize()
+        runs[mode] = (losses, regs, [p.detach().clone() for p in model.parameters()])
+    for mode in ("overlap", "overlap-graph"):
+        for a, b in zip(runs["serial"][0], runs[mode][0]):
+            assert abs(a - b) <= 2e-4 * abs(a), (mode, runs["serial"][0], runs[mode][0])
+        for a, b in zip(runs["serial"][1], runs[mode][1]):
+            assert abs(a - b) <= 2e-4 * abs(a) and a > 0
+        for a, b in zip(runs["serial"][2], runs[mode][2]):
+            if a.numel():
+                assert rel_err(b, a) < 1e-2
+
+
 def test_grad_sinks_match_autograd_accumulation():
     """Gradient-accumulation fusion (kernels accumulate straight into the flat bucket, autograd gets None) must give
     the same gradients as the plain autograd path, and must actually be active."""
