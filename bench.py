@@ -150,8 +150,10 @@ def run_ours(args):
     perturb_time_planes(model)
     model.proposal_sampler.update_sched = lambda step: 0  # proposal networks evaluated with grad + trained EVERY step
     prop_overlap = {"auto": None, "on": True, "off": False}[args.prop_overlap]
-    trainer = TrainStep(model, data_parallel=True, use_cuda_graph=not args.eager, overlap_branches=not args.no_overlap,
-                        overlap_proposal_backward=prop_overlap)
+    trainer = TrainStep(model, data_parallel=args.allreduce != "none", use_cuda_graph=not args.eager,
+                        overlap_branches=not args.no_overlap, overlap_proposal_backward=prop_overlap,
+                        allreduce_mode=args.allreduce if args.allreduce != "none" else "overlap",
+                        allreduce_backend=args.allreduce_backend)
     n_steps = args.warmup + args.steps
     host = _make_batches(n_steps, RAYS_PER_RANK, seed=1000 + rank)
     resident = [h.to(dev) for h in host]
@@ -257,7 +259,9 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch_rays": RAYS_PER_RANK * world, "parallelism": f"ray-sharded dp{world}",
                    "proposal_update": "every step", "l2": "flushed between timed iterations (160 MB write)",
-                   "launch": "eager" if args.eager else "whole step replayed from a CUDA graph"},
+                   "launch": "eager" if args.eager else "whole step replayed from a CUDA graph",
+                   "grad_allreduce": ("none (single rank)" if world == 1 else
+                                      f"{trainer.allreduce_backend} ({args.allreduce})" if args.allreduce != "none" else "disabled")},
         "e2e": {"value": rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": host[0].numel() * 4 * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss[0]},
         "gpu_launches": launches,
@@ -339,6 +343,10 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="keep the regulariser / proposal branches on the main stream")
     ap.add_argument("--prop-overlap", choices=["auto", "on", "off"], default="auto",
                     help="proposal-network backward on a side stream (auto: on for 1 GPU, off under data parallelism)")
+    ap.add_argument("--allreduce", choices=["overlap", "overlap-per-scale", "after-backward", "none"], default="overlap",
+                    help="gradient all-reduce scheduling under data parallelism ('none' is a diagnostic: ranks do not sync)")
+    ap.add_argument("--allreduce-backend", choices=["peer", "nccl"], default="peer",
+                    help="peer: our in-place NVLink peer-memory kernel; nccl: torch.distributed.all_reduce")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python each step instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

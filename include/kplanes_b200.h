@@ -206,6 +206,25 @@ int kp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
 int kp_repack_nchw_to_hwc(const float* src, float* dst, int C, int H, int W, void* stream);
 int kp_repack_hwc_to_nchw(const float* src, float* dst, int C, int H, int W, void* stream);
 
+/* ---- (e) data-parallel gradient all-reduce over NVLink peer memory (replaces the NCCL all-reduce torch DDP issues
+ *      around NS/engine/trainer.py:382-412).  Every rank allocates one ARENA = [KP_PEER_SIGNAL_BYTES of flag words |
+ *      data], exports its CUDA-IPC handle, and opens the arenas of the other ranks of the node.  kp_peer_allreduce
+ *      sums floats [begin, begin+count) of the data regions of all ranks IN PLACE (every rank ends with the same,
+ *      bit-identical sums; addition order is rank 0..N-1).  It must be enqueued by every rank, with the same
+ *      (begin, count, blocks), in the same order; cross-GPU synchronisation is inside the kernel, which is
+ *      CUDA-graph capturable. ---- */
+#define KP_PEER_MAX_WORLD 8
+#define KP_PEER_MAX_BLOCKS 160
+#define KP_PEER_SIGNAL_BYTES 16384
+int kp_peer_alloc(int64_t data_bytes, void** arena, void* ipc_handle64 /* out: 64-byte cudaIpcMemHandle_t */);
+int kp_peer_open(const void* ipc_handle64, void** arena /* out: this process' mapping of a peer's arena */);
+int kp_peer_close(void* arena /* from kp_peer_open */);
+int kp_peer_free(void* arena /* from kp_peer_alloc */);
+int kp_peer_error(const void* own_arena, uint32_t* error_word /* host; non-zero: a cross-GPU barrier timed out */);
+int kp_peer_allreduce(void* const* arenas /* HOST array [world]: arenas[rank] = own, others = opened */, int rank,
+                      int world, int64_t begin /* float index, multiple of 4 */, int64_t count, int blocks /* <=0: 64 */,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,12 @@ SIGNATURES = {
     "kp_plane_reg_multi_bwd": ([_P, _P, _P, _P, c_int, _P, c_int, _P], c_int),
     "kp_adam_multi": ([_P, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P, _P], c_int),
     "kp_adam_step": ([_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P], c_int),
+    "kp_peer_alloc": ([c_int64, POINTER(c_void_p), _P], c_int),
+    "kp_peer_open": ([_P, POINTER(c_void_p)], c_int),
+    "kp_peer_close": ([_P], c_int),
+    "kp_peer_free": ([_P], c_int),
+    "kp_peer_error": ([_P, POINTER(c_uint32)], c_int),
+    "kp_peer_allreduce": ([_P, c_int, c_int, c_int64, c_int64, c_int, _P], c_int),
     "kp_repack_nchw_to_hwc": ([_P, _P, c_int, c_int, c_int, _P], c_int),
     "kp_repack_hwc_to_nchw": ([_P, _P, c_int, c_int, c_int, _P], c_int),
 }

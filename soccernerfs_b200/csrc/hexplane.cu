@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
   load_point(P, m, pt);
   const int out_stride = F.concat ? F.n_scales * C : C;
   for (int k = 0; k < F.n_scales; ++k) {
+    // a scale without any gradient target is skipped whole (per-scale launches: the caller scatters one scale at a
+    // time so that a finished scale can be all-reduced while the next one is scattered)
+    bool any_target = false;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) any_target |= (((F.use_mask >> p) & 1u) != 0) && F.pl[k * KP_MAX_PLANES + p].g != nullptr;
+    if (!any_target) continue;
     const float4 g = ldg4(grad_out + m * out_stride + (F.concat ? k * C : 0) + c4);
     Axis ax[4];
     axes_setup(F, k, pt, ax);

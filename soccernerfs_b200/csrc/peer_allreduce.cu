@@ -1,0 +1,211 @@
+// Gradient all-reduce over NVLink / NVSwitch peer memory (sm_100a), for the data-parallel training step
+// (ray-sharded data parallelism; replaces the NCCL all-reduce that DDP issues for the reference,
+// NS/engine/trainer.py:382-412 under torch DDP).
+//
+// Every rank keeps its flat gradient bucket in a cudaMalloc'ed arena whose CUDA-IPC handle is opened by all other
+// ranks of the node, so every GPU can load from and store to every other GPU's bucket through NVLink.
+// One kernel per rank does the whole all-reduce IN PLACE ("two-shot", pull-reduce + push-broadcast):
+//     rank r owns the r-th 1/N of the range.  For every 16-byte element of its part it loads the N copies
+//     (N-1 of them over NVLink), adds them in rank order 0..N-1 (so the result is bit-identical everywhere and
+//     independent of which rank computed it) and stores the sum into all N buckets (N-1 stores over NVLink).
+// Nobody else touches that part of any bucket, so no staging buffer is needed.  NVLink carries (N-1)/N of the
+// bucket in each direction per GPU, which is the minimum for an all-reduce without in-switch reduction.
+// Cross-GPU ordering uses per-block flag words in the arenas (release/acquire at system scope): a start barrier
+// ("every rank's backward has written its gradients") and an end barrier ("every push has landed").  The flags are
+// monotonically increasing and the counter lives in device memory, so the kernel can be replayed from a CUDA graph.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace kp {
+
+constexpr int kPeerMaxWorld = KP_PEER_MAX_WORLD;
+constexpr int kPeerMaxBlocks = KP_PEER_MAX_BLOCKS;
+constexpr int kPeerThreads = 512;
+// signal region layout (uint32 words), at the start of every arena:
+//   [0 .. 2*B*W)          flags[phase][block][src_rank]    written by the peers
+//   [2*B*W .. 2*B*W + B)  counter[block]                   written by the owner only
+//   [2*B*W + B]           error word (non-zero: a barrier timed out)
+constexpr int kSigFlags = 2 * kPeerMaxBlocks * kPeerMaxWorld;
+constexpr int kSigCounter = kSigFlags;
+constexpr int kSigError = kSigFlags + kPeerMaxBlocks;
+static_assert((kSigError + 1) * 4 <= KP_PEER_SIGNAL_BYTES, "signal region too small");
+
+struct PeerArgs {
+  float* buf[kPeerMaxWorld];      // data region of every rank's arena (index = rank)
+  uint32_t* sig[kPeerMaxWorld];   // signal region of every rank's arena
+  int rank, world;
+  int64_t begin4, n4;             // range in float4 units
+  int64_t tail_begin, tail_n;     // < 4 trailing floats, reduced by rank 0
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer_v4(float* p, float4 v) {
+  asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// All ranks' block `blockIdx.x` meet here.  A bounded spin (a few seconds) turns a lost peer into an error word
+// instead of a hung GPU.
+__device__ __forceinline__ void peer_barrier(const PeerArgs& a, int phase, uint32_t flag) {
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < a.world) {
+    const int slot = (phase * kPeerMaxBlocks + (int)blockIdx.x) * kPeerMaxWorld;
+    st_release_sys(a.sig[threadIdx.x] + slot + a.rank, flag);
+    const uint32_t* mine = a.sig[a.rank] + slot + threadIdx.x;
+    unsigned long long spins = 0;
+    while ((int32_t)(ld_acquire_sys(mine) - flag) < 0) {
+      if (++spins > (1ull << 25)) {
+        a.sig[a.rank][kSigError] = 1u + (uint32_t)phase;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <int N>
+__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const __grid_constant__ PeerArgs a) {
+  __shared__ uint32_t s_flag;
+  uint32_t* counter = a.sig[a.rank] + kSigCounter + blockIdx.x;
+  if (threadIdx.x == 0) s_flag = *counter + 1u;
+  __syncthreads();
+  const uint32_t flag = s_flag;
+  peer_barrier(a, 0, flag);  // everybody's gradients are in memory
+
+  const int64_t lo = a.begin4 + a.n4 * a.rank / N, hi = a.begin4 + a.n4 * (a.rank + 1) / N;
+  const int64_t stride = (int64_t)gridDim.x * kPeerThreads;
+  constexpr int U = N <= 4 ? 4 : 2;  // independent elements in flight per thread: U*N 16-byte loads (<= 64 registers)
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; i0 < hi; i0 += U * stride) {
+    float4 v[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < hi) {
+#pragma unroll
+        for (int p = 0; p < N; ++p) v[u][p] = ld_peer_v4(a.buf[p] + 4 * i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < hi) {
+        float4 s = v[u][0];
+#pragma unroll
+        for (int p = 1; p < N; ++p) {
+          s.x += v[u][p].x; s.y += v[u][p].y; s.z += v[u][p].z; s.w += v[u][p].w;
+        }
+#pragma unroll
+        for (int p = 0; p < N; ++p) st_peer_v4(a.buf[p] + 4 * i, s);
+      }
+    }
+  }
+  if (a.rank == 0 && blockIdx.x == 0 && (int64_t)threadIdx.x < a.tail_n) {
+    const int64_t i = a.tail_begin + threadIdx.x;
+    float s = 0.f;
+    for (int p = 0; p < N; ++p) s += *(volatile float*)(a.buf[p] + i);
+    for (int p = 0; p < N; ++p) *(volatile float*)(a.buf[p] + i) = s;
+  }
+  peer_barrier(a, 1, flag);  // every push has landed
+  if (threadIdx.x == 0) *counter = flag;
+}
+
+}  // namespace kp
+
+using namespace kp;
+
+extern "C" int kp_peer_alloc(int64_t data_bytes, void** arena, void* ipc_handle64) {
+  KP_CHECK(data_bytes > 0 && arena != nullptr && ipc_handle64 != nullptr, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  const size_t total = (size_t)KP_PEER_SIGNAL_BYTES + (size_t)data_bytes;
+  cudaError_t e = cudaMalloc(&p, total);
+  KP_CHECK(e == cudaSuccess, "peer_alloc: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+  e = cudaMemset(p, 0, total);
+  KP_CHECK(e == cudaSuccess, "peer_alloc: cudaMemset failed: %s", cudaGetErrorString(e));
+  e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle64), p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("peer_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  e = cudaDeviceSynchronize();
+  KP_CHECK(e == cudaSuccess, "peer_alloc: sync failed: %s", cudaGetErrorString(e));
+  *arena = p;
+  return 0;
+}
+
+extern "C" int kp_peer_open(const void* ipc_handle64, void** arena) {
+  KP_CHECK(ipc_handle64 != nullptr && arena != nullptr, "peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle64, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(arena, h, cudaIpcMemLazyEnablePeerAccess);
+  KP_CHECK(e == cudaSuccess, "peer_open: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int kp_peer_close(void* arena) {
+  cudaError_t e = cudaIpcCloseMemHandle(arena);
+  KP_CHECK(e == cudaSuccess, "peer_close: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int kp_peer_free(void* arena) {
+  cudaError_t e = cudaFree(arena);
+  KP_CHECK(e == cudaSuccess, "peer_free: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int kp_peer_error(const void* arena, uint32_t* error_word) {
+  KP_CHECK(arena != nullptr && error_word != nullptr, "peer_error: bad arguments");
+  cudaError_t e = cudaMemcpy(error_word, reinterpret_cast<const uint32_t*>(arena) + kSigError, 4, cudaMemcpyDeviceToHost);
+  KP_CHECK(e == cudaSuccess, "peer_error: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int kp_peer_allreduce(void* const* arenas, int rank, int world, int64_t begin, int64_t count, int blocks,
+                                 void* stream) {
+  KP_CHECK(arenas != nullptr, "peer_allreduce: arenas is NULL");
+  KP_CHECK(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "peer_allreduce: rank %d / world %d", rank, world);
+  KP_CHECK(begin >= 0 && count >= 0 && begin % 4 == 0, "peer_allreduce: begin=%lld must be a multiple of 4", (long long)begin);
+  if (count == 0 || world == 1) return 0;
+  if (blocks <= 0) blocks = 64;
+  KP_CHECK(blocks <= kPeerMaxBlocks, "peer_allreduce: blocks=%d > %d", blocks, kPeerMaxBlocks);
+  PeerArgs a;
+  for (int p = 0; p < world; ++p) {
+    KP_CHECK(arenas[p] != nullptr, "peer_allreduce: arena %d is NULL", p);
+    a.sig[p] = reinterpret_cast<uint32_t*>(arenas[p]);
+    a.buf[p] = reinterpret_cast<float*>(reinterpret_cast<char*>(arenas[p]) + KP_PEER_SIGNAL_BYTES);
+  }
+  a.rank = rank;
+  a.world = world;
+  a.begin4 = begin / 4;
+  a.n4 = count / 4;
+  a.tail_begin = begin + (count / 4) * 4;
+  a.tail_n = count % 4;
+  cudaStream_t st = as_stream(stream);
+  switch (world) {
+    case 2: peer_allreduce_kernel<2><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 3: peer_allreduce_kernel<3><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 4: peer_allreduce_kernel<4><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 5: peer_allreduce_kernel<5><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 6: peer_allreduce_kernel<6><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 7: peer_allreduce_kernel<7><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 8: peer_allreduce_kernel<8><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    default: set_error("peer_allreduce: world=%d unsupported", world); return 1;
+  }
+  KP_LAUNCH_CHECK("peer_allreduce");
+  return 0;
+}

@@ -19,14 +19,22 @@ import torch.distributed as dist
 class GradBucket:
     """All gradients of a parameter list as views into one flat fp32 buffer (one memset, one all-reduce)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]) -> None:
+    def __init__(self, params: Iterable[torch.nn.Parameter], arena: Optional["PeerArena"] = None) -> None:
+        """``arena``: keep the bucket in NVLink peer memory (PeerArena) so that ``all_reduce`` runs our in-place
+        peer-memory kernel instead of NCCL."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad and p.numel() > 0]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.arena, self.arena_offset = arena, 0
+        if arena is not None:
+            self.flat, self.arena_offset = arena.take(total)
+        else:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views, off = [], 0
         for p in self.params:
-            v = torch.as_strided(self.flat, p.shape, p.stride(), storage_offset=off)  # same dense layout as the param
+            # same dense layout as the param (as_strided offsets are absolute in the storage: the flat buffer may itself
+            # be a slice of a peer-memory arena)
+            v = torch.as_strided(self.flat, p.shape, p.stride(), storage_offset=self.flat.storage_offset() + off)
             self.views.append(v)
             off += p.numel()
 
@@ -45,10 +53,137 @@ class GradBucket:
             if hasattr(p, "_kp_grad_sink"):
                 del p._kp_grad_sink
 
-    def all_reduce(self, group=None, async_op: bool = False):
+    def all_reduce(self, group=None, async_op: bool = False, span: Optional[Tuple[int, int]] = None):
+        """Sum the bucket (or its [begin, end) element range ``span``) over the process group."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
-        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        begin, end = (0, self.flat.numel()) if span is None else span
+        if end <= begin:
+            return None
+        if self.arena is not None:
+            self.arena.all_reduce(self.arena_offset + begin, end - begin)
+            return None
+        return dist.all_reduce(self.flat[begin:end], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+    def span_of(self, params: Iterable[torch.nn.Parameter]) -> Optional[Tuple[int, int]]:
+        """[begin, end) element range covered by ``params`` if they are adjacent in the bucket, else None."""
+        wanted = {id(p) for p in params}
+        begin, end, covered, off = None, None, 0, 0
+        for p in self.params:
+            if id(p) in wanted:
+                begin = off if begin is None else begin
+                end = off + p.numel()
+                covered += p.numel()
+            off += p.numel()
+        if begin is None or covered != end - begin or len(wanted) != sum(1 for p in self.params if id(p) in wanted):
+            return None
+        return begin, end
+
+
+class PeerMemoryUnavailable(RuntimeError):
+    """Raised (on every rank alike) when the peer-memory arenas cannot be set up on this node."""
+
+
+class _RawCudaMemory:
+    """``__cuda_array_interface__`` holder for memory the C library allocated (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, address: int, n_floats: int) -> None:
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (address, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerArena:
+    """One cudaMalloc'ed region per rank ([flag words | fp32 data]) that every other rank of the node maps through
+    CUDA IPC, plus the in-place all-reduce kernel over it (csrc/peer_allreduce.cu).  Handles travel through the
+    existing process group (``all_gather_object``); the data path itself is NVLink loads/stores issued by our kernel.
+    Collective calls must be made by all ranks in the same order -- like any collective."""
+
+    SIGNAL_BYTES = 16384  # KP_PEER_SIGNAL_BYTES
+
+    def __init__(self, n_floats: int, group=None, blocks: int = 64) -> None:
+        from ctypes import byref, c_void_p, create_string_buffer
+
+        from . import _lib
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerArena needs an initialised process group")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise RuntimeError("PeerArena: one NVLink node, at most 8 ranks")
+        self.blocks = int(blocks)
+        self.n_floats = (int(n_floats) + 63) // 64 * 64
+        self._lib = _lib
+        # set-up failures (CUDA IPC not permitted in this container, no peer access, ...) are agreed on by ALL ranks
+        # before anybody raises, so that the caller can fall back to NCCL consistently
+        own, handle, err = c_void_p(), create_string_buffer(64), ""
+        try:
+            _lib.call("kp_peer_alloc", self.n_floats * 4, byref(own), handle)
+        except RuntimeError as e:
+            err = str(e)
+        self._own = own.value or 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.rank, err, handle.raw), group=group)
+        self._ptrs = (c_void_p * self.world)()
+        self._opened = []
+        err = "; ".join(f"rank {r}: {e}" for r, e, _ in handles if e)
+        if not err:
+            for r, _e, raw in handles:
+                if r == self.rank:
+                    self._ptrs[r] = self._own
+                    continue
+                p = c_void_p()
+                try:
+                    _lib.call("kp_peer_open", create_string_buffer(raw, 64), byref(p))
+                except RuntimeError as e:
+                    err = str(e)
+                    break
+                self._ptrs[r] = p.value
+                self._opened.append(p.value)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err, group=group)
+        if any(errs):
+            self.close()
+            raise PeerMemoryUnavailable("; ".join(e for e in errs if e))
+        self._holder = _RawCudaMemory(self._own + self.SIGNAL_BYTES, self.n_floats)
+        self.data = torch.as_tensor(self._holder, device=torch.device("cuda", torch.cuda.current_device()))
+        self._used = 0
+        dist.barrier(group=group)  # every rank has mapped every arena before anybody's kernel touches one
+
+    def take(self, n_floats: int) -> Tuple[torch.Tensor, int]:
+        """Carve the next ``n_floats`` (rounded up to 64) out of the data region -> (tensor view, element offset)."""
+        off = self._used
+        if off + n_floats > self.n_floats:
+            raise RuntimeError("PeerArena exhausted")
+        self._used = off + (n_floats + 63) // 64 * 64
+        return self.data[off: off + n_floats], off
+
+    def all_reduce(self, begin: int, count: int) -> None:
+        """Sum data[begin:begin+count] over all ranks, in place, on the current stream (one kernel launch)."""
+        from ctypes import c_void_p
+
+        self._lib.call("kp_peer_allreduce", self._ptrs, self.rank, self.world, int(begin), int(count), self.blocks,
+                       c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def error_word(self) -> int:
+        """Non-zero if a cross-GPU barrier inside the kernel ever timed out (synchronises the device)."""
+        from ctypes import byref, c_uint32, c_void_p
+
+        torch.cuda.synchronize()
+        w = c_uint32(0)
+        self._lib.call("kp_peer_error", c_void_p(self._own), byref(w))
+        return int(w.value)
+
+    def close(self) -> None:
+        from ctypes import c_void_p
+
+        torch.cuda.synchronize()
+        for p in self._opened:
+            self._lib.call("kp_peer_close", c_void_p(p))
+        self._opened = []
+        if self._own:
+            self.data = None
+            self._lib.call("kp_peer_free", c_void_p(self._own))
+            self._own = 0
 
 
 def shard_slice(n_items: int, rank: int, world: int) -> Tuple[int, int]:

@@ -10,13 +10,15 @@ step counter, so a replay needs nothing from the host but the batch.
 """
 from __future__ import annotations
 
+import os
+import sys
 from typing import Dict, Optional
 
 import numpy as np
 import torch
 
 from ..cameras.rays import RayBundle
-from ..distributed import GradBucket, world_info
+from ..distributed import GradBucket, PeerArena, PeerMemoryUnavailable, world_info
 from ..models.kplanes import KPlanesModel, TrainingCallbackLocation, scale_dict
 from .optimizers import Optimizers, cosine_decay_factor
 
@@ -25,13 +27,20 @@ class TrainStep:
     def __init__(self, model: KPlanesModel, max_steps: int = 30000, lr: float = 1e-2, eps: float = 1e-12,
                  warm_up_end: int = 512, data_parallel: bool = False, use_cuda_graph: bool = False,
                  fuse_grad_accumulation: bool = True, overlap_branches: bool = True,
-                 overlap_proposal_backward: Optional[bool] = None) -> None:
+                 overlap_proposal_backward: Optional[bool] = None, allreduce_mode: str = "overlap",
+                 allreduce_backend: str = "peer") -> None:
         """``overlap_branches``: run the two branches of the step that do not depend on the main field's backward on
         their own CUDA streams (same arithmetic, same results): the plane regularisers (forward AND backward depend on
         the planes only) during the forward pass, and the back-propagation through the proposal networks (depends on
         the interlevel loss only) next to the decoder/scatter backward.  Needs the gradient sinks.
         ``overlap_proposal_backward``: None = automatic -- on for a single process; off under data parallelism, where
-        the proposal backward is instead kept AFTER the field scatter so that it hides the field bucket's all-reduce."""
+        the proposal backward is instead kept AFTER the field scatter so that it hides the field bucket's all-reduce.
+        ``allreduce_mode``: "overlap" (field bucket reduced on a communication stream as soon as the scatter is enqueued),
+        "overlap-per-scale" (scatter launched per scale, finest first, and the finest scale reduced under the others),
+        "after-backward" (both buckets reduced on the main stream after the whole backward).
+        ``allreduce_backend``: "peer" -- gradient buckets live in NVLink peer memory and are summed by our in-place
+        kernel (csrc/peer_allreduce.cu); "nccl" -- ``torch.distributed.all_reduce``.  If the peer arenas cannot be set
+        up on this node (all ranks agree), a warning is printed and NCCL is used; ``self.allreduce_backend`` says which."""
         self.model = model
         self.max_steps, self.base_lr, self.warm_up_end = max_steps, lr, warm_up_end
         self.optimizers = Optimizers(model.get_param_groups(), lr=lr, eps=eps, warm_up_end=warm_up_end, max_steps=max_steps)
@@ -39,19 +48,43 @@ class TrainStep:
         self.step = 0
         self.rank, self.world = world_info()
         self.buckets: Dict[str, GradBucket] = {}
+        self.arena, self.allreduce_backend = None, "nccl"
         self.reduce_grads = data_parallel and self.world > 1
         self.fuse_grad_accumulation = fuse_grad_accumulation
         if self.reduce_grads or fuse_grad_accumulation:
             # one flat gradient bucket per parameter group: the field bucket is complete as soon as the field's scatter
             # kernel has run, so its all-reduce overlaps the back-propagation through the proposal networks
-            self.buckets = {name: GradBucket(ps) for name, ps in model.get_param_groups().items()}
-        self._field_ready = None
-        self._comm_stream = None
-        if self.reduce_grads:
-            model.field._kp_post_backward = self._start_field_allreduce
-            self._comm_stream = torch.cuda.Stream()
+            on_cuda = next(model.parameters()).is_cuda
+            arena = None
+            assert allreduce_backend in ("peer", "nccl")
+            if self.reduce_grads and on_cuda and allreduce_backend == "peer":
+                groups = model.get_param_groups()
+                n = sum((sum(p.numel() for p in ps if p.requires_grad) + 63) // 64 * 64 for ps in groups.values())
+                try:
+                    arena = PeerArena(n, blocks=int(os.environ.get("KP_PEER_BLOCKS", "64")))
+                except PeerMemoryUnavailable as e:
+                    if self.rank == 0:
+                        print(f"[soccernerfs_b200] peer-memory all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+            self.arena = arena
+            self.allreduce_backend = "peer" if arena is not None else "nccl"
+            self.buckets = {name: GradBucket(ps, arena=arena) for name, ps in model.get_param_groups().items()}
         on_cuda = next(model.parameters()).is_cuda
         self.overlap = bool(overlap_branches and fuse_grad_accumulation and on_cuda)
+        self._field_ready = None
+        self._scale_ready: Dict[int, "torch.cuda.Event"] = {}
+        self._comm_stream = None
+        self._first_span = None  # bucket range of the finest scale's planes: all-reduced first, under the other scatters
+        assert allreduce_mode in ("overlap", "overlap-per-scale", "after-backward")
+        if self.reduce_grads:
+            self._comm_stream = torch.cuda.Stream() if on_cuda else None
+        if self.reduce_grads and allreduce_mode != "after-backward":
+            hook = self._start_field_allreduce
+            grids = getattr(model.field, "grids", None)
+            if allreduce_mode == "overlap-per-scale" and self.overlap and grids is not None and len(grids) > 1:
+                self._first_span = self.buckets["fields"].span_of(list(grids[len(grids) - 1]))
+            if self._first_span is not None:
+                hook = self._scale_scattered
+            model.field._kp_post_backward = hook
         self._reg_stream = torch.cuda.Stream() if self.overlap else None
         if overlap_proposal_backward is None:
             overlap_proposal_backward = not self.reduce_grads
@@ -72,6 +105,7 @@ class TrainStep:
         else:
             self.optimizers.zero_grad_all()
         self._field_ready = None
+        self._scale_ready = {}
         from .. import ops
 
         self._reg_mark = ops.PLANE_REG_BACKWARDS
@@ -99,17 +133,46 @@ class TrainStep:
         grad_scale = 1.0
         if self.reduce_grads:
             main = torch.cuda.current_stream()
-            if self._field_ready is not None:
-                self._comm_stream.wait_event(self._field_ready)  # fork: depends on the field scatter only
-                with torch.cuda.stream(self._comm_stream):
-                    self.buckets["fields"].all_reduce()
-                self.buckets["proposal_networks"].all_reduce()
-                main.wait_stream(self._comm_stream)  # join
+            fields, comm = self.buckets["fields"], self._comm_stream
+            n_scales = len(getattr(model.field, "grids", ()))
+            prop = self.buckets["proposal_networks"]
+            # every collective goes through the communication stream, in one order on all ranks (the peer-memory
+            # kernel's flag words, like an NCCL communicator, serve one collective at a time)
+            if comm is None:  # CPU process group (gloo): nothing to overlap
+                fields.all_reduce()
+                prop.all_reduce()
+                grad_scale = 1.0 / self.world
+                self.optimizers.optimizer_step_all(grad_scale=grad_scale)
+                return self._finish(loss_dict, loss, metrics)
+            if self._first_span is not None and len(self._scale_ready) == n_scales:
+                # finest scale (most of the bytes) while the other scales are still being scattered, the rest of the
+                # bucket as soon as the last scatter is in the stream; both under the proposal networks' backward
+                a, b = self._first_span
+                comm.wait_event(self._scale_ready[n_scales - 1])
+                with torch.cuda.stream(comm):
+                    fields.all_reduce(span=(a, b))
+                comm.wait_event(self._scale_ready[0])
+                with torch.cuda.stream(comm):
+                    fields.all_reduce(span=(0, a))
+                    fields.all_reduce(span=(b, fields.flat.numel()))
+            elif self._field_ready is not None:
+                comm.wait_event(self._field_ready)  # fork: depends on the field scatter only
+                with torch.cuda.stream(comm):
+                    fields.all_reduce()
             else:
-                self.buckets["fields"].all_reduce()
-                self.buckets["proposal_networks"].all_reduce()
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    fields.all_reduce()
+            comm.wait_stream(main)  # the proposal networks' backward is complete
+            with torch.cuda.stream(comm):
+                prop.all_reduce()
+            main.wait_stream(comm)  # join
             grad_scale = 1.0 / self.world
         self.optimizers.optimizer_step_all(grad_scale=grad_scale)
+        return self._finish(loss_dict, loss, metrics)
+
+    @staticmethod
+    def _finish(loss_dict, loss, metrics):
         loss_dict = {k: v.detach() for k, v in loss_dict.items()}
         loss_dict["loss"] = loss.detach()
         loss_dict["psnr"] = metrics["psnr"]
@@ -129,6 +192,16 @@ class TrainStep:
             ev = torch.cuda.Event()
             ev.record()
             self._field_ready = ev
+
+    def _scale_scattered(self, scale: int) -> None:
+        """Per-scale variant of ``_start_field_allreduce``: the scatter of ``scale`` has just been enqueued (scales are
+        scattered finest first).  Only used with the regulariser branch joined before the backward, so the planes'
+        gradients of that scale are complete at this point of the stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self._scale_ready[scale] = ev
+
+    _scale_scattered.per_scale = True
 
     def _run_callbacks(self, location: int) -> None:
         for cb in self.callbacks:

@@ -159,11 +159,23 @@ class _Hexplane(torch.autograd.Function):
         planes, points = ctx.planes, ctx.points
         need = [ctx.needs_input_grad[5 + i] and bool((use_mask >> (i % n_planes)) & 1) for i in range(len(planes))]
         targets, grads = _targets(planes, ctx.sinks, need)
+        hook = ctx.post_backward
         if any(need):
-            call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(targets), _plane_hw(planes), n_scales, n_planes, c,
-                 points.struct(), points.M, int(concat), use_mask, ptr(f32c(grad_out)), stream_ptr())
-        if ctx.post_backward is not None:
-            ctx.post_backward()  # e.g. start the gradient all-reduce of the field bucket while the proposals back-propagate
+            g = f32c(grad_out)
+            if hook is not None and getattr(hook, "per_scale", False) and n_scales > 1:
+                # one scatter launch per scale, finest (largest planes) first: hook(k) can start reducing scale k's
+                # gradients while the remaining scales are scattered
+                for k in reversed(range(n_scales)):
+                    sub = [t if i // n_planes == k else None for i, t in enumerate(targets)]
+                    call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(sub), _plane_hw(planes), n_scales, n_planes, c,
+                         points.struct(), points.M, int(concat), use_mask, ptr(g), stream_ptr())
+                    hook(k)
+                hook = None
+            else:
+                call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(targets), _plane_hw(planes), n_scales, n_planes, c,
+                     points.struct(), points.M, int(concat), use_mask, ptr(g), stream_ptr())
+        if hook is not None:
+            hook()  # e.g. start the gradient all-reduce of the field bucket while the proposals back-propagate
         return (None, None, None, None, None, *grads)
 
 

@@ -59,6 +59,32 @@ def test_hexplane_freeze_flags():
     assert all(grids[i][j].grad is None for i in range(2) for j in range(6))  # time skipped, space frozen
 
 
+def test_per_scale_scatter_equals_single_launch():
+    """Scatter launched one scale at a time (finest first, hook after each) == the one-launch scatter."""
+    from soccernerfs_b200 import ops
+
+    gen = torch.Generator().manual_seed(5)
+    reso = [(8, 8, 8, 5), (16, 16, 16, 5), (32, 32, 32, 5)]
+    combos = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+    pts = (torch.rand(3000, 4, generator=gen) * 2.2 - 1.1).to(DEV)
+    gout = torch.randn(3000, 3 * 8, generator=gen).to(DEV)
+    base = [[torch.rand(1, 8, r[b], r[a], generator=gen) for a, b in combos] for r in reso]
+    grads, calls = {}, []
+    for mode in ("single", "per_scale"):
+        ms = [[ops.as_channel_last(p.to(DEV)).clone(memory_format=torch.preserve_format).requires_grad_(True) for p in g] for g in base]
+        hook = None
+        if mode == "per_scale":
+            def hook(k=None):
+                calls.append(k)
+            hook.per_scale = True
+        out = ops.hexplane_features(ms, ops.points_from_pts(pts), True, post_backward=hook)
+        out.backward(gout)
+        grads[mode] = [p.grad.clone() for g in ms for p in g]
+    assert calls == [2, 1, 0]
+    for a, b in zip(grads["single"], grads["per_scale"]):
+        assert rel_err(b, a) < 1e-5 and float(a.abs().sum()) > 0
+
+
 def test_empty_input():
     from soccernerfs_b200.fields.kplanes_field import interpolate_kplanes
 

@@ -94,3 +94,17 @@ def test_unbuilt_branches_fail_loudly():
         KPlanesField(aabb, linear_decoder=True, linear_decoder_layers=1)
     with pytest.raises(NotImplementedError):
         KPlanesField(aabb, linear_decoder=False, use_appearance_embedding=True)
+
+
+def test_grad_bucket_span_of():
+    """GradBucket.span_of: element range of adjacent parameters, None when they are not adjacent."""
+    import torch
+
+    from soccernerfs_b200.distributed import GradBucket
+
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (3, 5, 7, 2)]
+    b = GradBucket(ps)
+    assert b.span_of([ps[1], ps[2]]) == (3, 15)
+    assert b.span_of([ps[3]]) == (15, 17)
+    assert b.span_of([ps[0], ps[2]]) is None
+    assert b.span_of([torch.nn.Parameter(torch.zeros(1))]) is None
