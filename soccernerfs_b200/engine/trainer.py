@@ -61,7 +61,7 @@ class TrainStep:
                 groups = model.get_param_groups()
                 n = sum((sum(p.numel() for p in ps if p.requires_grad) + 63) // 64 * 64 for ps in groups.values())
                 try:
-                    arena = PeerArena(n, blocks=int(os.environ.get("KP_PEER_BLOCKS", "64")))
+                    arena = PeerArena(n, blocks=int(os.environ.get("KP_PEER_BLOCKS", "32")))
                 except PeerMemoryUnavailable as e:
                     if self.rank == 0:
                         print(f"[soccernerfs_b200] peer-memory all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
@@ -76,7 +76,9 @@ class TrainStep:
         self._first_span = None  # bucket range of the finest scale's planes: all-reduced first, under the other scatters
         assert allreduce_mode in ("overlap", "overlap-per-scale", "after-backward")
         if self.reduce_grads:
-            self._comm_stream = torch.cuda.Stream() if on_cuda else None
+            # high priority: when the scatter finishes, the all-reduce kernel's blocks are placed BEFORE the proposal
+            # backward's persistent blocks fill every SM (they would otherwise keep it out until they retire)
+            self._comm_stream = torch.cuda.Stream(priority=-1) if on_cuda else None
         if self.reduce_grads and allreduce_mode != "after-backward":
             hook = self._start_field_allreduce
             grids = getattr(model.field, "grids", None)
