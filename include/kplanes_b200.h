@@ -206,6 +206,24 @@ int kp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
 int kp_repack_nchw_to_hwc(const float* src, float* dst, int C, int H, int W, void* stream);
 int kp_repack_hwc_to_nchw(const float* src, float* dst, int C, int H, int W, void* stream);
 
+/* ---- (a14b) loss head: the reductions, coefficients, total and PSNR that KPlanesModel.get_loss_dict /
+ *      get_metrics_dict (NS/models/kplanes.py:392-452) and the trainer's sum(loss_dict.values())
+ *      (NS/engine/trainer.py:398-400) apply to the per-ray / per-sample loss kernels' outputs, one launch per
+ *      direction.  vals3 = (coef_rgb * mse, coef_dist * mean(dist_per_ray), coef_il * sum_l mean(il_l));
+ *      total = vals3[0..2] + sum(extra) (extra: already scaled terms, e.g. the plane regularisers);
+ *      psnr = -10 log10(mse).  workspace4: 4 doubles, zero before the FIRST call (the kernel re-zeroes it). ---- */
+#define KP_LOSS_HEAD_MAX_LEVELS 4
+int kp_loss_head_fwd(const float* pred /* [N,3] */, const float* image /* [N,3] */, int64_t N,
+                     const float* dist_per_ray /* [N] or NULL */, const float* const* il_ptrs /* HOST array [n_levels] */,
+                     const int64_t* il_counts /* HOST: elements per level */, int n_levels, float coef_rgb, float coef_dist,
+                     float coef_il, const float* extra /* device [n_extra] or NULL */, int n_extra, double* workspace4,
+                     float* vals3, float* total, float* psnr, void* stream);
+int kp_loss_head_bwd(const float* pred, const float* image, int64_t N, const int64_t* il_counts, int n_levels,
+                     float coef_rgb, float coef_dist, float coef_il, const float* grad_total /* device scalar or NULL */,
+                     const float* grad_vals3 /* device [3] or NULL */, float* grad_pred /* [N,3] or NULL */,
+                     float* grad_dist /* [N] or NULL */, float* const* grad_il_ptrs /* HOST array [n_levels] or NULL */,
+                     void* stream);
+
 /* ---- (e) data-parallel gradient all-reduce over NVLink peer memory (replaces the NCCL all-reduce torch DDP issues
  *      around NS/engine/trainer.py:382-412).  Every rank allocates one ARENA = [KP_PEER_SIGNAL_BYTES of flag words |
  *      data], exports its CUDA-IPC handle, and opens the arenas of the other ranks of the node.  kp_peer_allreduce

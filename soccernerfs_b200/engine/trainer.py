@@ -123,12 +123,17 @@ class TrainStep:
                     regs = scale_dict(regs, model.config.loss_coefficients)
                     sum(regs.values()).backward()
                     regs = {k: v.detach() for k, v in regs.items()}
+                    regs_vec = torch.stack(list(regs.values()))  # the loss head adds these into the total
         outputs = model(ray_bundle)
-        metrics = model.get_metrics_dict(outputs, batch)
         if self.overlap:
             main.wait_stream(self._reg_stream)
+            if regs:
+                outputs["_scaled_regularizers_vec"] = regs_vec
+        metrics = model.get_metrics_dict(outputs, batch)
         loss_dict = model.get_loss_dict(outputs, batch, metrics, regularizers=regs)
-        loss = sum(loss_dict.values())
+        loss = getattr(loss_dict, "total", None)
+        if loss is None:
+            loss = sum(loss_dict.values())
         loss.backward()
         if self._prop_stream is not None:
             main.wait_stream(self._prop_stream)  # proposal-network backward ran on the sampler's side stream

@@ -58,16 +58,28 @@ def interlevel_loss(weights_list: List[torch.Tensor], ray_samples_list: List[Ray
     return loss_interlevel
 
 
+def interlevel_terms(weights_list: List[torch.Tensor], ray_samples_list: List[RaySamples]) -> List[torch.Tensor]:
+    """The per-level [N,S] tensors whose means ``interlevel_loss`` adds up (for the fused loss head)."""
+    c = ray_samples_to_sdist(ray_samples_list[-1]).detach()
+    w = weights_list[-1][..., 0].detach()
+    return [lossfun_outer(c, w, ray_samples_to_sdist(rs), ws[..., 0]) for rs, ws in zip(ray_samples_list[:-1], weights_list[:-1])]
+
+
 def lossfun_distortion(t: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """Per-ray distortion (inter + intra terms), t [..., S+1], w [..., S] -> [...]."""
     s = w.shape[-1]
     return ops.distortion_per_ray(t.reshape(-1, s + 1), w.reshape(-1, s)).view(w.shape[:-1])
 
 
-def distortion_loss(weights_list, ray_samples_list) -> torch.Tensor:
+def distortion_per_ray(weights_list, ray_samples_list) -> torch.Tensor:
+    """[N] per-ray distortion of the last level; ``distortion_loss`` is its mean."""
     c = ray_samples_to_sdist(ray_samples_list[-1])
     w = weights_list[-1][..., 0]
-    return torch.mean(lossfun_distortion(c, w))
+    return lossfun_distortion(c, w)
+
+
+def distortion_loss(weights_list, ray_samples_list) -> torch.Tensor:
+    return torch.mean(distortion_per_ray(weights_list, ray_samples_list))
 
 
 # ---- K-Planes plane regularisers ----------------------------------------------------------------------

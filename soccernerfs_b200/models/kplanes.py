@@ -16,6 +16,7 @@ import numpy as np
 import torch
 from torch.nn import Parameter
 
+from .. import ops
 from ..cameras.rays import RayBundle
 from ..fields.base_field import FieldHeadNames
 from ..fields.kplanes_field import KPlanesDensityField, KPlanesField
@@ -24,7 +25,9 @@ from ..model_components.losses import (
     MSELoss,
     depth_loss,
     distortion_loss,
+    distortion_per_ray,
     interlevel_loss,
+    interlevel_terms,
     kplanes_regularizers,
     space_tv_loss,
     sparse_transients_loss,
@@ -129,6 +132,13 @@ class KPlanesModelConfig(ModelConfig):
     depth_loss_type: DepthLossType = DepthLossType.DS_NERF
     freeze_time_planes: bool = False
     freeze_space_planes: bool = False
+
+
+class LossDict(dict):
+    """Loss dictionary (same keys / scaled scalar tensors as the reference's) that may also carry ``total``: the sum of
+    its values when the fused loss head already produced it (saves the trainer's sum(loss_dict.values()) kernels)."""
+
+    total: Optional[torch.Tensor] = None
 
 
 def scale_dict(dictionary: Dict, coefficients: Dict[str, float]) -> Dict:
@@ -258,8 +268,12 @@ class KPlanesModel(Model):
     def get_metrics_dict(self, outputs, batch):
         metrics_dict = {}
         image = batch["image"].to(self.device)
-        with torch.no_grad():  # PSNR with data_range 1.0 (torchmetrics.PeakSignalNoiseRatio in the reference)
-            metrics_dict["psnr"] = -10.0 * torch.log10(torch.mean((outputs["rgb"] - image) ** 2))
+        head = self._loss_head(outputs, image)
+        if head is not None:
+            metrics_dict["psnr"] = head[2]
+        else:
+            with torch.no_grad():  # PSNR with data_range 1.0 (torchmetrics.PeakSignalNoiseRatio in the reference)
+                metrics_dict["psnr"] = -10.0 * torch.log10(torch.mean((outputs["rgb"] - image) ** 2))
         if "depth_image" in batch.keys() and self.training and self.config.loss_coefficients["depth_loss"] > 0:
             metrics_dict["depth_loss"] = 0.0
             sigma = self._get_sigma().to(self.device)
@@ -276,6 +290,25 @@ class KPlanesModel(Model):
                     depth_loss_type=self.config.depth_loss_type,
                 ) / len(outputs["weights_list"])
         return metrics_dict
+
+    def _loss_head(self, outputs, image):
+        """Training on CUDA: rgb / distortion / interlevel losses (scaled), their total and the PSNR from ONE kernel
+        (ops.loss_head), computed once per forward and cached in ``outputs``.  None when not applicable."""
+        if "_loss_head" in outputs:
+            return outputs["_loss_head"]
+        head = None
+        coef = self.config.loss_coefficients
+        rgb = outputs["rgb"]
+        if (self.training and rgb.is_cuda and "weights_list" in outputs and "rgb_loss" in coef
+                and len(outputs["weights_list"]) - 1 <= 4 and image.shape == rgb.shape):
+            wl, rl = outputs["weights_list"], outputs["ray_samples_list"]
+            dist = distortion_per_ray(wl, rl) if "distortion_loss" in coef else None
+            il = interlevel_terms(wl, rl) if "interlevel_loss" in coef else []
+            extra = outputs.get("_scaled_regularizers_vec")
+            head = ops.loss_head(rgb, image, dist, il, coef["rgb_loss"], coef.get("distortion_loss", 0.0),
+                                 coef.get("interlevel_loss", 0.0), extra) + (extra is not None,)
+        outputs["_loss_head"] = head
+        return head
 
     def regularizer_losses(self) -> Dict[str, torch.Tensor]:
         """The plane regularisers of the loss dict (kplanes.py:430-446), UNSCALED.  They depend on the planes only,
@@ -311,8 +344,31 @@ class KPlanesModel(Model):
         already back-propagated) by the caller; they are merged instead of being evaluated here."""
         device = outputs["rgb"].device
         image = batch["image"].to(device)
-        loss_dict = {"rgb_loss": self.rgb_loss(image, outputs["rgb"])}
         loss_coef = self.config.loss_coefficients
+        head = self._loss_head(outputs, image)
+        if head is not None:
+            vals, total, _psnr, has_extra = head
+            loss_dict = LossDict(rgb_loss=vals[0])
+            if "distortion_loss" in loss_coef:
+                loss_dict["distortion_loss"] = vals[1]
+            if "interlevel_loss" in loss_coef:
+                loss_dict["interlevel_loss"] = vals[2]
+            rest: Dict[str, torch.Tensor] = {}
+            if regularizers is None:
+                rest.update(self.regularizer_losses())
+            if "depth_image" in batch.keys() and loss_coef["depth_loss"] > 0:
+                rest["depth_loss"] = metrics_dict["depth_loss"]
+            rest = scale_dict(rest, loss_coef)
+            if regularizers is not None and not has_extra:
+                rest.update(regularizers)
+            for v in rest.values():
+                total = total + v
+            loss_dict.update(rest)
+            if regularizers is not None and has_extra:
+                loss_dict.update(regularizers)
+            loss_dict.total = total
+            return loss_dict
+        loss_dict = {"rgb_loss": self.rgb_loss(image, outputs["rgb"])}
         if self.training:
             if "distortion_loss" in loss_coef:
                 loss_dict["distortion_loss"] = distortion_loss(outputs["weights_list"], outputs["ray_samples_list"])

@@ -8,9 +8,9 @@ current CUDA stream; under ``torch.autocast`` inputs are promoted to fp32 exactl
 """
 from __future__ import annotations
 
-from ctypes import c_float, c_int32, c_void_p
+from ctypes import c_float, c_int32, c_int64, c_void_p
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -643,6 +643,64 @@ def _reg_tables(planes, terms):
         hwc[3 * i], hwc[3 * i + 1], hwc[3 * i + 2] = p.shape[2], p.shape[3], p.shape[1]
         tm[i] = t
     return hwc, tm
+
+
+_HEAD_WS: Dict = {}
+
+
+def _head_workspace(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    if key not in _HEAD_WS:
+        _HEAD_WS[key] = torch.zeros(4, dtype=torch.float64, device=device)
+    return _HEAD_WS[key]
+
+
+class _LossHead(torch.autograd.Function):
+    """(vals3, total, psnr) from the per-ray / per-sample loss tensors; see csrc/loss_head.cu."""
+
+    @staticmethod
+    def forward(ctx, coefs, extra, pred, image, dist, *il):
+        pred_c, image_c = f32c(pred.detach()), f32c(image.detach())
+        n = pred_c.shape[0]
+        dist_c = None if dist is None else f32c(dist.detach()).view(-1)
+        il_c = [f32c(t.detach()) for t in il]
+        counts = (c_int64 * max(1, len(il_c)))(*[t.numel() for t in il_c])
+        ptrs = (c_void_p * max(1, len(il_c)))(*[t.data_ptr() for t in il_c])
+        dev = pred_c.device
+        vals = torch.empty(3, dtype=torch.float32, device=dev)
+        total, psnr = torch.empty((), dtype=torch.float32, device=dev), torch.empty((), dtype=torch.float32, device=dev)
+        extra_c = None if extra is None else f32c(extra.detach()).view(-1)
+        call("kp_loss_head_fwd", ptr(pred_c), ptr(image_c), n, ptr(dist_c), ptrs, counts, len(il_c), float(coefs[0]),
+             float(coefs[1]), float(coefs[2]), ptr(extra_c), 0 if extra_c is None else extra_c.numel(),
+             ptr(_head_workspace(dev)), ptr(vals), ptr(total), ptr(psnr), stream_ptr())
+        ctx.save_for_backward(pred_c, image_c)
+        ctx.meta = (coefs, n, dist is not None, [tuple(t.shape) for t in il], counts)
+        ctx.mark_non_differentiable(psnr)
+        return vals, total, psnr
+
+    @staticmethod
+    def backward(ctx, g_vals, g_total, _g_psnr):
+        pred_c, image_c = ctx.saved_tensors
+        coefs, n, has_dist, il_shapes, counts = ctx.meta
+        dev = pred_c.device
+        need = ctx.needs_input_grad
+        g_pred = torch.empty_like(pred_c) if need[2] else None
+        g_dist = torch.empty(n, dtype=torch.float32, device=dev) if (has_dist and need[4]) else None
+        g_il = [torch.empty(sh, dtype=torch.float32, device=dev) if need[5 + i] else None for i, sh in enumerate(il_shapes)]
+        gptrs = (c_void_p * max(1, len(g_il)))(*[0 if t is None else t.data_ptr() for t in g_il])
+        call("kp_loss_head_bwd", ptr(pred_c), ptr(image_c), n, counts, len(il_shapes), float(coefs[0]), float(coefs[1]),
+             float(coefs[2]), ptr(None if g_total is None else f32c(g_total)), ptr(None if g_vals is None else f32c(g_vals)),
+             ptr(g_pred), ptr(g_dist), gptrs, stream_ptr())
+        return (None, None, g_pred, None, g_dist, *g_il)
+
+
+def loss_head(pred: torch.Tensor, image: torch.Tensor, dist_per_ray: Optional[torch.Tensor], interlevel: Sequence[torch.Tensor],
+              coef_rgb: float, coef_dist: float, coef_il: float, extra: Optional[torch.Tensor] = None):
+    """-> (vals [3] = scaled rgb / distortion / interlevel losses, total = their sum + sum(extra), psnr), one kernel.
+    ``dist_per_ray`` [N] from lossfun_distortion, ``interlevel`` = per-level lossfun_outer outputs [N,S_l]."""
+    pred2 = pred.reshape(-1, 3)
+    dist = None if dist_per_ray is None else dist_per_ray.reshape(-1)
+    return _LossHead.apply((coef_rgb, coef_dist, coef_il), extra, pred2, image.reshape(-1, 3), dist, *interlevel)
 
 
 class _PlaneReg(torch.autograd.Function):

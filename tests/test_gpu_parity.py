@@ -265,6 +265,36 @@ def test_losses_vs_reference_fixture():
     assert rel_err(L.compute_plane_smoothness(p).cpu(), ko.compute_plane_smoothness(g["grid_0_2"])) < TOL
 
 
+def test_loss_head_matches_torch_formulas():
+    """ops.loss_head == coef * mse / mean / sum-of-means, total and PSNR as get_loss_dict / get_metrics_dict write
+    them (kplanes.py:392-452), forward and backward, twice in a row (the kernel re-zeroes its workspace)."""
+    from soccernerfs_b200 import ops
+
+    gen = torch.Generator().manual_seed(3)
+    n = 1000
+    for rep in range(2):
+        pred = torch.rand(n, 3, generator=gen).to(DEV).requires_grad_(True)
+        image = torch.rand(n, 3, generator=gen).to(DEV)
+        dist = torch.rand(n, generator=gen).to(DEV).requires_grad_(True)
+        il = [torch.rand(n, s, generator=gen).to(DEV).requires_grad_(True) for s in (48, 37)]
+        extra = torch.rand(6, generator=gen).to(DEV)
+        c = (1.0, 0.001, 1.0)
+        vals, total, psnr = ops.loss_head(pred, image, dist, il, *c, extra=extra)
+        mse = torch.nn.functional.mse_loss(image, pred)
+        ref_vals = torch.stack([c[0] * mse, c[1] * dist.mean(), c[2] * (il[0].mean() + il[1].mean())])
+        ref_total = ref_vals.sum() + extra.sum()
+        assert rel_err(vals, ref_vals) < 1e-6 and abs(float(total - ref_total)) < 1e-6 * abs(float(ref_total))
+        assert abs(float(psnr) - float(-10.0 * torch.log10(mse))) < 1e-4
+        inputs = [pred, dist, *il]
+        g = torch.autograd.grad(total + 0.5 * vals[1], inputs)
+        g_ref = torch.autograd.grad(ref_total + 0.5 * ref_vals[1], inputs)
+        for a, b in zip(g, g_ref):
+            assert rel_err(a, b) < 1e-6
+    # without distortion / interlevel terms
+    vals, total, _ = ops.loss_head(pred.detach(), image, None, [], 2.0, 0.0, 0.0)
+    assert abs(float(total) - 2.0 * float(torch.nn.functional.mse_loss(image, pred))) < 1e-6
+
+
 def test_decoders_and_density_field_vs_oracle():
     from soccernerfs_b200.fields.kplanes_field import KPlanesDensityField, KPlanesField
 
