@@ -202,19 +202,28 @@ def run_ours(args):
         trainer.use_cuda_graph = True
 
     # ---- arm 2: end to end through the public API with host buffers -----------------------------------
-    last_loss = [0.0]
+    # every step: pinned host batch -> device (H2D), the step, and the step's loss -> pinned host memory (D2H).  Both
+    # copies are stream-ordered and asynchronous (a training loop that logs the loss does not stall the GPU on it);
+    # the region ends with a synchronize, after which every step's loss is on the host and is checked.
+    loss_host = torch.zeros(n_steps, dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
         packed = host[i].to(dev, non_blocking=True)  # pinned H2D inside the timed region
         rb, batch = _bundle(packed)
         out = trainer(rb, batch)
-        last_loss[0] = float(out["loss"].item())  # D2H read of the step's result
+        loss_host[i].copy_(out["loss"], non_blocking=True)  # D2H read of the step's result
 
     e2e_ms, _ = timed_region(step_e2e)
+    last_loss = [float(loss_host[n_steps - 1])]
+    if not bool(torch.isfinite(loss_host).all()) or float(loss_host[args.warmup:].abs().min()) == 0.0:
+        raise RuntimeError("end-to-end arm: a step's loss did not arrive on the host")
 
     # ---- per-kernel durations for the roofline: CUDA events around the field kernels on their launch stream,
     #      measured live in eager mode (events cannot be timed inside a graph replay), L2 flushed per step ------
     trainer.use_cuda_graph = False
+    # each kernel alone on the GPU for this pass: the side-stream branches would otherwise run next to (and inflate the
+    # duration of) the kernel being timed
+    trainer.overlap, trainer._prop_stream, model.proposal_sampler.side_stream = False, None, None
     _lib.TIMED.update(list(ALGO_BYTES.keys()) + ["kp_decoder_fwd_fused", "kp_color_net_bwd", "kp_sigma_net_bwd", "kp_adam_multi",
                                                  "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd"])
     _lib.EVENTS.clear()
