@@ -21,6 +21,8 @@
 // For 32-bit operands the tensor core only accepts the 32-byte-base swizzle in the MN-major view (atoms of 4 rows x
 // 128 bytes, 32-byte chunk q of row r at chunk q ^ (r & 3)), so a tile is staged in the swizzle of the view it is
 // consumed in.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace kp {
@@ -237,8 +239,22 @@ static unsigned persistent_grid(Kern kern, int64_t n_tiles, size_t smem) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  // CTAs per SM from the kernel's own resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for these
+  // kernels whatever their footprint -- measured on B200, driver 580 -- so it is not used.)
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
+    int smem_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * 256;
+    const size_t smem_cta = smem + fa.sharedSizeBytes + 1024;  // + the per-CTA reservation
+    per_sm = std::min<int>(65536 / std::max(1, regs_cta), (int)((size_t)smem_sm / smem_cta));
+  }
+  if (per_sm < 1) per_sm = 1;
+  if (getenv("KP_TC_MAX_CTAS") != nullptr) per_sm = std::min(per_sm, atoi(getenv("KP_TC_MAX_CTAS")));
   if (per_sm > 4) per_sm = 4;  // 4 x 128 TMEM columns
+  if (getenv("KP_TC_DEBUG") != nullptr)
+    fprintf(stderr, "[kp tc] smem=%zu B -> %d CTA/SM, grid %lld\n", smem, per_sm, (long long)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm));
   return (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
 }
 
