@@ -313,6 +313,82 @@ def cpu_baseline(rays_per_step: int, steps: int, warmup: int):
                       f"{cores} threads", "ms_per_step": 1e3 * t_total / steps}
 
 
+def run_eval(args):
+    """Extra (not the headline metric): BASELINE config 5 -- full-frame inference with the 32x field of config 3,
+    1920x1080 rays per frame in chunks of 32768, rays generated on the device and finished tiles copied to pinned host
+    frames (engine/frame_renderer.py).  One "step" = one frame; with N ranks the tiles are shared round-robin."""
+    rank, world, local = _dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --mode eval needs a CUDA device")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+
+    from soccernerfs_b200 import _lib
+    from soccernerfs_b200.cameras.cameras import Cameras
+    from soccernerfs_b200.data.scene_box import SceneBox
+    from soccernerfs_b200.data.synthetic import perturb_time_planes, synthetic_rays
+    from soccernerfs_b200.engine.frame_renderer import FrameRenderer
+    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
+
+    torch.manual_seed(7)  # the same field on every rank
+    _, _, _, aabb = synthetic_rays(4, torch.Generator().manual_seed(0))
+    cfg = KPlanesModelConfig(
+        spacetime_resolution=(64, 64, 64, 100), multiscale_res=(1, 2, 4, 8, 16, 32), sigma_net_hidden_dim=128,
+        disable_viewing_dependent=True, num_nerf_samples_per_ray=64, num_proposal_samples_per_ray=(256, 128),
+        proposal_net_args_list=[{"feature_dim": 8, "resolution": [128, 128, 128, 100]},
+                                {"feature_dim": 8, "resolution": [256, 256, 256, 100]}], eval_num_rays_per_chunk=32768)
+    model = cfg.setup(scene_box=SceneBox(aabb=aabb), num_train_data=19 * 25).to(dev)
+    perturb_time_planes(model)
+    model.eval()
+    h, w = 1080, 1920
+    n_frames = args.warmup + args.steps
+    ang = torch.linspace(0.0, 1.0, n_frames) * 0.6  # a short camera path on the broadcast ring, looking at the origin
+    pos = torch.stack([torch.cos(ang), torch.sin(ang), torch.full_like(ang, 0.35)], dim=-1)
+    fwd = -pos / pos.norm(dim=-1, keepdim=True)
+    right = torch.cross(fwd, torch.tensor([0.0, 0.0, 1.0]).expand_as(fwd), dim=-1)
+    right = right / right.norm(dim=-1, keepdim=True)
+    up = torch.cross(right, fwd, dim=-1)
+    c2w = torch.cat([torch.stack([right, up, -fwd], dim=-1), pos[..., None]], dim=-1)  # camera looks along -z
+    cams = Cameras(c2w.to(dev), 1600.0, 1600.0, w / 2, h / 2, w, h, times=torch.linspace(0, 1, n_frames).to(dev))
+    renderer = FrameRenderer(model, cams, rank=rank, world=world)
+    for i in range(args.warmup):
+        renderer.render(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    k0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    checksum = 0.0
+    for i in range(args.steps):
+        frame = renderer.render(args.warmup + i)  # ends with the copy stream's synchronize: the frame is on the host
+        checksum += float(frame["rgb"][::97, ::89].sum())
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - k0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    ms = float(t.item())
+    rays = h * w * args.steps
+    out_bytes = h * w * (3 + 1 + 1) * 4
+    print(json.dumps({
+        "metric": "eval rays/sec (full-frame inference, device ray generation -> pinned host frames)",
+        "value": rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "kplanes-32x(cfg3 field) full-frame inference (BASELINE config 5): 1920x1080 rays/frame, chunk "
+                               "32768, 256/128/64 samples, rays generated on the device", "frames": args.steps,
+                   "parallelism": f"tile-sharded x{world} (round-robin chunks, no collective)", "l2": "inputs larger than L2 (2.3 GB of planes)"},
+        "e2e": {"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": out_bytes,
+                "checksum": checksum},
+        "gpu_launches": launches,
+    }))
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (the oracle port: the reference is
     Python and cannot travel to the GPU box), all host threads, same config / metric / unit."""
@@ -348,6 +424,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--mode", choices=["train", "eval"], default="train",
+                    help="train: the headline metric (default); eval: full-frame inference, BASELINE config 5 (extra line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="keep the regulariser / proposal branches on the main stream")
     ap.add_argument("--prop-overlap", choices=["auto", "on", "off"], default="auto",
@@ -361,7 +439,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        if args.mode == "eval":
+            run_eval(args)
+        else:
+            run_ours(args)
         if int(os.environ.get("WORLD_SIZE", "1")) > 1:
             # CUDA graphs that captured NCCL work keep the communicator busy at interpreter shutdown: finish all GPU
             # work, then leave without the (hanging) communicator teardown.

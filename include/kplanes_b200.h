@@ -206,6 +206,18 @@ int kp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
 int kp_repack_nchw_to_hwc(const float* src, float* dst, int C, int H, int W, void* stream);
 int kp_repack_hwc_to_nchw(const float* src, float* dst, int C, int H, int W, void* stream);
 
+/* ---- (f2) pixel -> ray generation: Cameras._generate_rays_from_coords, NS/cameras/cameras.py:505-741 (perspective,
+ *      no distortion), as driven by RayGenerator.forward (NS/model_components/ray_generators.py:43-59) when
+ *      ray_indices [N,3] = (camera,row,col) is given, or by Cameras.generate_rays(camera_indices=cam) for the
+ *      row-major pixel range [first_pixel, first_pixel+N) of camera `cam` (image width `width`) when it is NULL.
+ *      pixel_offset is get_image_coords' 0.5.  Outputs as in the reference's RayBundle: origins/directions [N,3],
+ *      pixel_area [N], directions_norm [N] (metadata), times [N] (cameras.times[cam]). ---- */
+int kp_generate_rays(const float* c2w /* [n_cams,3,4] */, const float* intrinsics /* [n_cams,4] fx,fy,cx,cy */,
+                     const float* cam_times /* [n_cams] or NULL */, int n_cams, const int64_t* ray_indices /* or NULL */,
+                     int cam, int width, int64_t first_pixel, int64_t N, float pixel_offset, float* origins,
+                     float* directions, float* pixel_area, float* directions_norm /* or NULL */, float* times /* or NULL */,
+                     void* stream);
+
 /* ---- (a14b) loss head: the reductions, coefficients, total and PSNR that KPlanesModel.get_loss_dict /
  *      get_metrics_dict (NS/models/kplanes.py:392-452) and the trainer's sum(loss_dict.values())
  *      (NS/engine/trainer.py:398-400) apply to the per-ray / per-sample loss kernels' outputs, one launch per

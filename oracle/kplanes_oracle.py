@@ -23,6 +23,7 @@ import itertools
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -653,6 +654,34 @@ def model_loss_dict(mp: ModelParams, out: Dict, image: torch.Tensor, training: b
 # --------------------------------------------------------------------------------------------
 # Synthetic scene shapes -- shared by tests, smoke and bench so inputs are identical
 # --------------------------------------------------------------------------------------------
+def generate_rays(c2w, fx, fy, cx, cy, cam_times, cam_idx, y_idx, x_idx, pixel_offset: float = 0.5):
+    """Perspective, undistorted case of Cameras._generate_rays_from_coords (NS/cameras/cameras.py:505-741), for rays
+    given as (camera, row, col) like RayGenerator.forward (NS/model_components/ray_generators.py:43-59).
+    c2w [C,3,4]; fx,fy,cx,cy [C,1]; cam_times [C,1] | None; indices int64 [N].
+    -> origins [N,3], directions [N,3], pixel_area [N,1], directions_norm [N,1], times [N,1] | None."""
+    y = y_idx.float() + pixel_offset  # get_image_coords(pixel_offset=0.5), cameras.py:299-326
+    x = x_idx.float() + pixel_offset
+    fx_, fy_, cx_, cy_ = (t[cam_idx, 0] for t in (fx, fy, cx, cy))
+    coord = torch.stack([(x - cx_) / fx_, -(y - cy_) / fy_], -1)  # cameras.py:624-627
+    coord_x = torch.stack([(x - cx_ + 1) / fx_, -(y - cy_) / fy_], -1)
+    coord_y = torch.stack([(x - cx_) / fx_, -(y - cy_ + 1) / fy_], -1)
+    coord_stack = torch.stack([coord, coord_x, coord_y], dim=0)  # [3,N,2]
+    dirs = torch.cat([coord_stack, -torch.ones_like(coord_stack[..., :1])], dim=-1)  # perspective: (u, v, -1), :665-670
+    c2w_r = c2w[cam_idx]  # [N,3,4]
+    rotation = c2w_r[..., :3, :3]
+    dirs = torch.sum(dirs[..., None, :] * rotation, dim=-1)  # :708-710
+    eps = torch.tensor([np.finfo(float).eps * 4.0]).to(dirs)  # camera_utils._EPS, camera_utils.py:28
+    norm = torch.maximum(torch.linalg.vector_norm(dirs, dim=-1, keepdims=True), eps)  # normalize_with_norm :240-252
+    dirs = dirs / norm
+    origins = c2w_r[..., :3, 3]
+    directions = dirs[0]
+    dx = torch.sqrt(torch.sum((directions - dirs[1]) ** 2, dim=-1))  # :722-723
+    dy = torch.sqrt(torch.sum((directions - dirs[2]) ** 2, dim=-1))
+    pixel_area = (dx * dy)[..., None]
+    times = cam_times[cam_idx, 0][..., None] if cam_times is not None else None
+    return origins, directions, pixel_area, norm[0], times
+
+
 def synthetic_rays(n: int, gen: torch.Generator, scene: str = "broadcast", n_frames: int = 25):
     """Broadcast-style scene: cameras on a ring of radius ~1 around the origin looking inward, aabb
     +-1.5 (broadcaststyle_dataparser.py:449-463); stadium: aabb +-1.  Returns origins, directions

@@ -362,6 +362,7 @@ def main():
     gen_losses(R)
     gen_model(R)
     gen_importance(R)
+    gen_raygen(R)
 
 
 
@@ -428,6 +429,40 @@ def gen_importance(R):
     torch.manual_seed(4321)
     uni = ps.PixelSampler(32).sample_method(32, b, h, w)
     save("importance", images=images, cam_ids=cam_ids, cam_times=cam_times, ist=ist.float(), isg=isg.float(), uniform=uni, **out)
+
+
+def gen_raygen(R):
+    """(f2) pixel -> ray generation by the reference's own Cameras (NS/cameras/cameras.py:327-741), driven the two ways
+    the hot path's callers do: RayGenerator.forward (ray_generators.py:43-59: coords = image_coords[y, x],
+    generate_rays(camera_indices=c[:, None], coords=coords)) and generate_rays(camera_indices=i, keep_shape=True) for a
+    whole frame (scripts/render.py, base_model.py:162-186)."""
+    from nerfstudio.cameras.cameras import Cameras
+
+    g = torch.Generator().manual_seed(606)
+    n_cams, h, w = 5, 36, 64
+    # random rigid poses: QR of a random matrix, det forced to +1
+    rot = torch.linalg.qr(torch.randn(n_cams, 3, 3, generator=g)).Q
+    rot = rot * torch.sign(torch.linalg.det(rot))[:, None, None]
+    pos = torch.randn(n_cams, 3, 1, generator=g) * 2.0
+    c2w = torch.cat([rot, pos], dim=-1).float()
+    fx = 50.0 + 20.0 * torch.rand(n_cams, 1, generator=g)
+    fy = 50.0 + 20.0 * torch.rand(n_cams, 1, generator=g)
+    cx = w / 2 + torch.randn(n_cams, 1, generator=g)
+    cy = h / 2 + torch.randn(n_cams, 1, generator=g)
+    times = torch.rand(n_cams, 1, generator=g)
+    cams = Cameras(camera_to_worlds=c2w, fx=fx, fy=fy, cx=cx, cy=cy, width=w, height=h, times=times)
+    n = 257
+    ray_indices = torch.stack([torch.randint(0, n_cams, (n,), generator=g), torch.randint(0, h, (n,), generator=g),
+                               torch.randint(0, w, (n,), generator=g)], dim=-1)
+    image_coords = cams.get_image_coords()
+    coords = image_coords[ray_indices[:, 1], ray_indices[:, 2]]
+    rb = cams.generate_rays(camera_indices=ray_indices[:, 0].unsqueeze(-1), coords=coords)
+    frame = cams.generate_rays(camera_indices=3, keep_shape=True)
+    save("raygen", c2w=c2w, fx=fx, fy=fy, cx=cx, cy=cy, times=times, hw=torch.tensor([h, w]), ray_indices=ray_indices,
+         origins=rb.origins, directions=rb.directions, pixel_area=rb.pixel_area, ray_times=rb.times,
+         directions_norm=rb.metadata["directions_norm"], frame_cam=torch.tensor(3),
+         frame_origins=frame.origins, frame_directions=frame.directions, frame_pixel_area=frame.pixel_area,
+         frame_times=frame.times, frame_directions_norm=frame.metadata["directions_norm"])
 
 
 if __name__ == "__main__":

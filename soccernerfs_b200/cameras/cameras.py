@@ -1,0 +1,165 @@
+"""Cameras: the subset of NS/cameras/cameras.py the K-Planes path's callers use -- a flat batch of PERSPECTIVE cameras
+without lens distortion -- with ray generation on the device (``kp_generate_rays``).
+
+Same constructor argument names, attribute names (``camera_to_worlds, fx, fy, cx, cy, width, height, times``) and
+``generate_rays`` call forms as the reference (cameras.py:38-120, 327-502):
+  * ``generate_rays(camera_indices=c[:, None], coords=coords)`` -- RayGenerator.forward, ray_generators.py:43-59
+  * ``generate_rays(camera_indices=i, keep_shape=True)``          -- a whole frame (scripts/render.py, eval)
+plus ``generate_tile(camera_index, start, end)`` (a row-major pixel range of a frame without materialising coords).
+Fisheye / equirectangular cameras, non-zero distortion parameters, camera-optimizer deltas and multi-dimensional
+camera batches are not built: they raise NotImplementedError instead of taking another route.
+"""
+from __future__ import annotations
+
+from enum import Enum, auto
+from typing import Optional, Union
+
+import torch
+
+from .. import ops
+from ..data.scene_box import SceneBox
+from .rays import RayBundle
+
+
+class CameraType(Enum):
+    """cameras.py:28-33."""
+
+    PERSPECTIVE = auto()
+    FISHEYE = auto()
+    EQUIRECTANGULAR = auto()
+
+
+def _col(v, n: int, device, dtype=torch.float32) -> torch.Tensor:
+    if not torch.is_tensor(v):
+        v = torch.tensor([float(v)], dtype=dtype)
+    v = v.to(device=device, dtype=dtype).reshape(-1, 1)
+    return v.expand(n, 1).contiguous() if v.shape[0] == 1 else v.contiguous()
+
+
+class Cameras:
+    def __init__(self, camera_to_worlds: torch.Tensor, fx, fy, cx, cy, width=None, height=None,
+                 distortion_params: Optional[torch.Tensor] = None, camera_type=CameraType.PERSPECTIVE,
+                 times: Optional[torch.Tensor] = None, ids: Optional[torch.Tensor] = None) -> None:
+        c2w = camera_to_worlds
+        if c2w.dim() == 2:
+            c2w = c2w[None]
+        if c2w.dim() != 3 or c2w.shape[-2:] != (3, 4):
+            raise NotImplementedError("Cameras: a flat batch [num_cameras, 3, 4] of camera-to-world matrices is supported")
+        if isinstance(camera_type, CameraType):
+            if camera_type != CameraType.PERSPECTIVE:
+                raise NotImplementedError(f"camera type {camera_type} is not built (perspective only)")
+        elif torch.is_tensor(camera_type):
+            if bool((camera_type != CameraType.PERSPECTIVE.value).any()):
+                raise NotImplementedError("non-perspective cameras are not built")
+        if distortion_params is not None and bool((distortion_params != 0).any()):
+            raise NotImplementedError("lens distortion is not built (all distortion parameters must be zero)")
+        dev = c2w.device
+        n = c2w.shape[0]
+        self.camera_to_worlds = c2w.float().contiguous()
+        self.fx, self.fy, self.cx, self.cy = (_col(v, n, dev) for v in (fx, fy, cx, cy))
+        h = height if height is not None else (self.cy * 2).to(torch.int64)
+        w = width if width is not None else (self.cx * 2).to(torch.int64)
+        self.height, self.width = _col(h, n, dev, torch.int64), _col(w, n, dev, torch.int64)
+        self.times = None if times is None else times.to(dev).float().reshape(n, 1).contiguous()
+        self.ids = ids
+        self.distortion_params = None
+        self.camera_type = torch.full((n, 1), CameraType.PERSPECTIVE.value, dtype=torch.int64, device=dev)
+        self._intrinsics = None
+
+    # -- bookkeeping -----------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.camera_to_worlds.device
+
+    @property
+    def image_height(self) -> torch.Tensor:
+        return self.height
+
+    @property
+    def image_width(self) -> torch.Tensor:
+        return self.width
+
+    @property
+    def shape(self):
+        return self.camera_to_worlds.shape[:-2]
+
+    @property
+    def size(self) -> int:
+        return self.camera_to_worlds.shape[0]
+
+    def __len__(self) -> int:
+        return self.size
+
+    def to(self, device) -> "Cameras":
+        out = Cameras(self.camera_to_worlds.to(device), self.fx.to(device), self.fy.to(device), self.cx.to(device),
+                      self.cy.to(device), self.width.to(device), self.height.to(device), times=self.times, ids=self.ids)
+        return out
+
+    def get_image_coords(self, pixel_offset: float = 0.5, index=None) -> torch.Tensor:
+        """[H,W,2] (y, x) pixel-centre coordinates (cameras.py:299-326)."""
+        if index is None:
+            h, w = int(self.height.max()), int(self.width.max())
+        else:
+            h, w = int(self.height[index]), int(self.width[index])
+        yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        return torch.stack([yy, xx], dim=-1) + pixel_offset
+
+    def _packed_intrinsics(self) -> torch.Tensor:
+        if self._intrinsics is None:
+            self._intrinsics = torch.cat([self.fx, self.fy, self.cx, self.cy], dim=-1).contiguous()
+        return self._intrinsics
+
+    def _bundle(self, out, camera_indices: torch.Tensor, shape, aabb_box: Optional[SceneBox]) -> RayBundle:
+        origins, directions, pixel_area, norm, times = out
+        rb = RayBundle(origins=origins.view(*shape, 3), directions=directions.view(*shape, 3),
+                       pixel_area=pixel_area.view(*shape, 1), camera_indices=camera_indices,
+                       times=None if times is None else times.view(*shape, 1),
+                       metadata={"directions_norm": norm.view(*shape, 1)})
+        if aabb_box is not None:
+            # cameras.py:478-497 fills nears/fars with utils.math.intersect_aabb; the K-Planes path sets them with its
+            # own collider (AABBBoxCollider) afterwards, so this option is not built
+            raise NotImplementedError("generate_rays(aabb_box=...) is not built; apply the model's collider to the bundle")
+        return rb
+
+    # -- ray generation -------------------------------------------------------------------------------
+    def generate_rays(self, camera_indices: Union[torch.Tensor, int], coords: Optional[torch.Tensor] = None,
+                      camera_opt_to_camera: Optional[torch.Tensor] = None, distortion_params_delta: Optional[torch.Tensor] = None,
+                      keep_shape: Optional[bool] = None, disable_distortion: bool = False,
+                      aabb_box: Optional[SceneBox] = None) -> RayBundle:
+        if camera_opt_to_camera is not None or distortion_params_delta is not None:
+            raise NotImplementedError("camera-optimizer deltas are not built")
+        if isinstance(camera_indices, int):
+            cam = camera_indices
+            if coords is None:  # the whole frame of one camera, [H,W] rays (cameras.py:405-440 case 1)
+                h, w = int(self.height[cam]), int(self.width[cam])
+                rb = self.generate_tile(cam, 0, h * w, aabb_box=aabb_box)
+                return rb.reshape((h, w)) if keep_shape in (None, True) else rb
+            camera_indices = torch.full((*coords.shape[:-1], 1), cam, dtype=torch.int64, device=coords.device)
+        if coords is None:
+            raise NotImplementedError("tensor camera_indices without coords (stacked full frames) is not built")
+        shape = camera_indices.shape[:-1]
+        if camera_indices.shape[-1] != 1 or coords.shape[:-1] != shape:
+            raise ValueError("camera_indices must be [..., 1] and coords [..., 2] with the same batch shape")
+        dev = self.device
+        # coords are (y, x) pixel-centre coordinates = integer index + 0.5 (image_coords[y, x]); the kernel adds the
+        # offset itself, so hand it the integer part
+        yx = torch.floor(coords.to(dev)).to(torch.int64).reshape(-1, 2)
+        if not bool(((coords.to(dev).reshape(-1, 2) - yx) == 0.5).all()):
+            raise NotImplementedError("generate_rays: coords must be pixel centres (integer + 0.5)")
+        tri = torch.cat([camera_indices.to(dev).reshape(-1, 1).to(torch.int64), yx], dim=-1).contiguous()
+        out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, ray_indices=tri)
+        return self._bundle(out, camera_indices.to(dev), shape, aabb_box)
+
+    def generate_rays_from_indices(self, ray_indices: torch.Tensor, aabb_box: Optional[SceneBox] = None) -> RayBundle:
+        """(camera,row,col) triplets -> rays, what RayGenerator.forward computes, without building coords."""
+        tri = ray_indices.to(self.device).to(torch.int64).contiguous()
+        out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, ray_indices=tri)
+        return self._bundle(out, tri[:, 0:1], (tri.shape[0],), aabb_box)
+
+    def generate_tile(self, camera_index: int, start: int, end: int, aabb_box: Optional[SceneBox] = None) -> RayBundle:
+        """Rays of the row-major pixels [start, end) of one camera's frame (flat)."""
+        w = int(self.width[camera_index])
+        out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, cam=int(camera_index), width=w,
+                                first_pixel=int(start), n=int(end - start))
+        ci = torch.full((end - start, 1), int(camera_index), dtype=torch.int64, device=self.device)
+        return self._bundle(out, ci, (end - start,), aabb_box)

@@ -645,6 +645,30 @@ def _reg_tables(planes, terms):
     return hwc, tm
 
 
+def generate_rays(c2w: torch.Tensor, intrinsics: torch.Tensor, cam_times: Optional[torch.Tensor],
+                  ray_indices: Optional[torch.Tensor] = None, cam: int = 0, width: int = 1, first_pixel: int = 0,
+                  n: Optional[int] = None, pixel_offset: float = 0.5):
+    """Pixel -> ray generation (cameras.py:505-741, perspective / undistorted).  Either ``ray_indices`` int64 [N,3]
+    (camera,row,col) or a row-major pixel range of camera ``cam``.  -> origins [N,3], directions [N,3], pixel_area [N],
+    directions_norm [N], times [N] | None."""
+    c2w_c, intr = f32c(c2w), f32c(intrinsics)
+    if ray_indices is not None:
+        if ray_indices.dtype != torch.int64 or not ray_indices.is_contiguous():
+            ray_indices = ray_indices.to(torch.int64).contiguous()
+        n = ray_indices.shape[0]
+    dev = c2w_c.device
+    origins = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    directions = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    pixel_area = torch.empty((n,), dtype=torch.float32, device=dev)
+    norm = torch.empty((n,), dtype=torch.float32, device=dev)
+    times = None if cam_times is None else torch.empty((n,), dtype=torch.float32, device=dev)
+    ct = None if cam_times is None else f32c(cam_times).view(-1)
+    call("kp_generate_rays", ptr(c2w_c), ptr(intr), ptr(ct), c2w_c.shape[0], ptr(ray_indices), int(cam), int(width),
+         int(first_pixel), int(n), float(pixel_offset), ptr(origins), ptr(directions), ptr(pixel_area), ptr(norm), ptr(times),
+         stream_ptr())
+    return origins, directions, pixel_area, norm, times
+
+
 _HEAD_WS: Dict = {}
 
 

@@ -551,3 +551,65 @@ def test_tile_sharded_eval_equals_unsharded():
     frame = assemble_frame(pieces, h, w)
     for k in ("rgb", "depth", "accumulation", "median_rgb"):
         assert torch.equal(frame[k], full[k]), k
+
+
+def test_ray_generation_vs_reference_fixture():
+    """(f2) kp_generate_rays vs rays produced by the reference's own Cameras: explicit (camera,row,col) triplets through
+    the RayGenerator mirror, the generate_rays(camera_indices, coords) form, and one whole frame."""
+    from soccernerfs_b200.cameras.cameras import Cameras
+    from soccernerfs_b200.model_components.ray_generators import RayGenerator
+
+    g = load_golden("raygen")
+    h, w = (int(v) for v in g["hw"])
+    cams = Cameras(g["c2w"].to(DEV), g["fx"].to(DEV), g["fy"].to(DEV), g["cx"].to(DEV), g["cy"].to(DEV), w, h,
+                   times=g["times"].to(DEV))
+    ri = g["ray_indices"].to(DEV)
+    gen = RayGenerator(cams)
+    coords = gen.image_coords.to(DEV)[ri[:, 1], ri[:, 2]]
+    for rb in (gen(ri), cams.generate_rays(camera_indices=ri[:, 0:1], coords=coords)):
+        assert torch.equal(rb.origins.cpu(), g["origins"]) and torch.equal(rb.times.cpu(), g["ray_times"])
+        assert rel_err(rb.directions.cpu(), g["directions"]) < 1e-6
+        assert rel_err(rb.pixel_area.cpu(), g["pixel_area"]) < 1e-5
+        assert rel_err(rb.metadata["directions_norm"].cpu(), g["directions_norm"]) < 1e-6
+        assert torch.equal(rb.camera_indices.cpu(), g["ray_indices"][:, 0:1])
+    frame = cams.generate_rays(camera_indices=int(g["frame_cam"]), keep_shape=True)
+    assert frame.origins.shape == (h, w, 3)
+    assert torch.equal(frame.origins.cpu(), g["frame_origins"]) and torch.equal(frame.times.cpu(), g["frame_times"])
+    assert rel_err(frame.directions.cpu(), g["frame_directions"]) < 1e-6
+    assert rel_err(frame.pixel_area.cpu(), g["frame_pixel_area"]) < 1e-5
+    # fraction of bit-identical direction components (the arithmetic follows the reference's order)
+    same = (frame.directions.cpu() == g["frame_directions"]).float().mean()
+    assert same > 0.9, float(same)
+    with pytest.raises(NotImplementedError):
+        Cameras(g["c2w"], 50.0, 50.0, 32.0, 18.0, w, h, distortion_params=torch.ones(5, 6))
+
+
+def test_frame_renderer_equals_chunked_camera_bundle():
+    """config 5: the tile queue (device ray generation + chunked forward + async copies to pinned frames) gives the
+    same image as generate_rays(keep_shape=True) -> get_outputs_for_camera_ray_bundle, also when 3 ranks share it."""
+    from soccernerfs_b200.cameras.cameras import Cameras
+    from soccernerfs_b200.engine.frame_renderer import FrameRenderer
+    from tests.helpers import build_model
+    from tests.test_oracle_golden import load_tiny_model
+
+    gm = load_golden("model_tiny")
+    model = build_model("tiny", load_tiny_model(gm), gm["aabb"], DEV)
+    model.eval()
+    h, w = 24, 40
+    c2w = torch.tensor([[[1.0, 0, 0, 0.1], [0, 1.0, 0, -0.2], [0, 0, 1.0, 2.5]]])
+    cams = Cameras(c2w.to(DEV), 40.0, 40.0, w / 2, h / 2, w, h, times=torch.tensor([0.4]).to(DEV))
+    full = cams.generate_rays(camera_indices=0, keep_shape=True)
+    model.config.eval_num_rays_per_chunk = 200
+    with torch.no_grad():
+        ref = model.get_outputs_for_camera_ray_bundle(full)
+    one = FrameRenderer(model, cams, chunk=200).render(0)
+    for k in ("rgb", "depth", "accumulation"):
+        assert one[k].shape[:2] == (h, w) and one[k].is_pinned()
+        assert torch.equal(one[k], ref[k].cpu()), k
+    total = {k: torch.zeros_like(v) for k, v in one.items()}
+    for r in range(3):
+        part = FrameRenderer(model, cams, chunk=200, rank=r, world=3).render(0)
+        for k in total:
+            total[k] += part[k]
+    for k in total:
+        assert torch.equal(total[k], one[k]), k

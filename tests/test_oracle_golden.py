@@ -137,3 +137,21 @@ def test_model_step_matches_reference():
         assert rel_err(v, g["loss_" + k]) < TOL, k
     for i, gr in enumerate(grads):
         assert rel_err(gr, g[f"grad_{i}"]) < 1e-5, i
+
+
+def test_ray_generation_matches_reference():
+    """(f2) the oracle's pixel -> ray restatement vs rays produced by the reference's own Cameras (explicit
+    (camera,row,col) triplets as RayGenerator issues them, and one whole frame)."""
+    g = load_golden("raygen")
+    cam = (g["c2w"], g["fx"], g["fy"], g["cx"], g["cy"], g["times"])
+    ri = g["ray_indices"]
+    o, d, pa, nrm, t = ko.generate_rays(*cam, ri[:, 0], ri[:, 1], ri[:, 2])
+    assert torch.equal(o, g["origins"]) and torch.equal(t, g["ray_times"])
+    assert rel_err(d, g["directions"]) < 1e-6 and rel_err(pa, g["pixel_area"]) < 1e-5 and rel_err(nrm, g["directions_norm"]) < 1e-6
+    h, w = (int(v) for v in g["hw"])
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    c = torch.full((h * w,), int(g["frame_cam"]), dtype=torch.int64)
+    o, d, pa, nrm, t = ko.generate_rays(*cam, c, yy.reshape(-1), xx.reshape(-1))
+    assert torch.equal(o.view(h, w, 3), g["frame_origins"]) and torch.equal(t.view(h, w, 1), g["frame_times"])
+    assert rel_err(d.view(h, w, 3), g["frame_directions"]) < 1e-6
+    assert rel_err(pa.view(h, w, 1), g["frame_pixel_area"]) < 1e-5
