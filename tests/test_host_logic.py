@@ -108,3 +108,51 @@ def test_grad_bucket_span_of():
     assert b.span_of([ps[3]]) == (15, 17)
     assert b.span_of([ps[0], ps[2]]) is None
     assert b.span_of([torch.nn.Parameter(torch.zeros(1))]) is None
+
+
+def test_tcnn_param_layout_round_trip():
+    """utils/checkpoint.py: flat tcnn params <-> our weight matrices (first-layer input and last-layer output padded
+    to 16, row-major [out, in], layer order)."""
+    import torch
+
+    from soccernerfs_b200.utils.checkpoint import tcnn_layer_shapes, tcnn_params_to_weights, weights_to_tcnn_params
+
+    assert tcnn_layer_shapes([31, 64, 64, 3]) == [(64, 32), (64, 64), (16, 64)]
+    assert tcnn_layer_shapes([8, 64, 1]) == [(64, 16), (16, 64)]
+    gen = torch.Generator().manual_seed(0)
+    ws = [torch.randn(64, 31, generator=gen), torch.randn(64, 64, generator=gen), torch.randn(3, 64, generator=gen)]
+    flat = weights_to_tcnn_params(ws)
+    assert flat.numel() == 64 * 32 + 64 * 64 + 16 * 64
+    assert float(flat[:32][31]) == 0.0 and torch.equal(flat[:31], ws[0][0])  # row 0 of layer 0, then its padding column
+    back = tcnn_params_to_weights(flat, [31, 64, 64, 3])
+    assert all(torch.equal(a, b) for a, b in zip(ws, back))
+    import pytest
+
+    with pytest.raises(ValueError):
+        tcnn_params_to_weights(flat[:-1], [31, 64, 64, 3])
+
+
+def test_reference_checkpoint_round_trip():
+    """A pipeline state dict in the reference's naming / layouts (planes NCHW-contiguous under ``_model.``, MLPs as flat
+    tcnn ``params``) loads into the channel-last model and back without loss."""
+    import torch
+
+    from soccernerfs_b200 import ops
+    from soccernerfs_b200.utils.checkpoint import load_reference_state_dict, to_reference_state_dict
+    from tests.helpers import model_config
+    from soccernerfs_b200.data.scene_box import SceneBox
+
+    aabb = torch.tensor([[-1.5] * 3, [1.5] * 3])
+    torch.manual_seed(1)
+    a = model_config("tiny").setup(scene_box=SceneBox(aabb=aabb), num_train_data=1)
+    torch.manual_seed(2)
+    b = model_config("tiny").setup(scene_box=SceneBox(aabb=aabb), num_train_data=1)
+    sd = to_reference_state_dict(a)
+    assert "_model.field.grids.0.0" in sd and sd["_model.field.grids.0.0"].is_contiguous()
+    assert "_model.field.sigma_net.params" in sd and "_model.proposal_networks.1.sigma_net.params" in sd
+    sd["_datamanager.train_camera_optimizer.pose_adjustment"] = torch.zeros(3, 6)
+    unused = load_reference_state_dict(b, {"step": 7, "pipeline": sd})
+    assert unused == ["_datamanager.train_camera_optimizer.pose_adjustment"]
+    for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert na == nb and torch.equal(pa, pb), na
+    assert ops.is_channel_last(b.field.grids[0][0])  # storage layout untouched by the load
