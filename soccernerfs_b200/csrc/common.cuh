@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/kplanes_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -13,7 +15,8 @@
 namespace kp {
 
 void set_error(const char* fmt, ...);
-extern long long g_launches;  // number of kernels launched through the C-ABI (reported by kp_launch_count)
+extern std::atomic<long long> g_launches;  // kernels launched through the C-ABI (kp_launch_count); the autograd
+                                            // thread and the main thread both launch
 
 #define KP_CHECK(cond, ...)          \
   do {                               \

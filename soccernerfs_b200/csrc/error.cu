@@ -5,7 +5,7 @@
 
 namespace kp {
 static thread_local char g_err[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -16,4 +16,4 @@ void set_error(const char* fmt, ...) {
 
 extern "C" const char* kp_last_error(void) { return kp::g_err; }
 extern "C" int kp_abi_version(void) { return KP_ABI_VERSION; }
-extern "C" long long kp_launch_count(void) { return kp::g_launches; }
+extern "C" long long kp_launch_count(void) { return kp::g_launches.load(); }
