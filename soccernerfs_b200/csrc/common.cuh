@@ -78,6 +78,14 @@ __device__ __forceinline__ double warp_incl_scan_d(double v, int lane) {
   return v;
 }
 
+// exclusive warp scan (double).  NOT "inclusive - own value": with an infinite element that would be inf - inf = NaN
+// for the lane holding it, while torch's cumsum gives the finite prefix (e.g. an infinite density in get_weights).
+__device__ __forceinline__ double warp_excl_scan_d(double v, int lane) {
+  const double incl = warp_incl_scan_d(v, lane);
+  const double up = __shfl_up_sync(0xffffffffu, incl, 1);
+  return lane == 0 ? 0.0 : up;
+}
+
 // torch.nan_to_num defaults: nan -> 0, +inf -> FLT_MAX, -inf -> -FLT_MAX
 __device__ __forceinline__ float nan_to_num(float x) {
   if (isnan(x)) return 0.f;

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) weights_fwd_kernel(const f
   const float* s = sigma + n * S;
   double part = 0.0;
   for (int i = i0; i < i1; ++i) part += (double)__fmul_rn(d[i], s[i]);
-  double run = warp_incl_scan_d(part, lane) - part;
+  double run = warp_excl_scan_d(part, lane);
   for (int i = i0; i < i1; ++i) {
     const float x = __fmul_rn(d[i], s[i]);
     const float alpha = 1.f - expf(-x);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) weights_bwd_kernel(const f
   // pass 1: prefix of x (for T_i) and per-lane totals of g*w
   double part = 0.0;
   for (int i = i0; i < i1; ++i) part += (double)__fmul_rn(d[i], s[i]);
-  const double run0 = warp_incl_scan_d(part, lane) - part;
+  const double run0 = warp_excl_scan_d(part, lane);
   double run = run0, gw_part = 0.0;
   for (int i = i0; i < i1; ++i) {
     const float x = __fmul_rn(d[i], s[i]);
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) render_fwd_kernel(
   }
   // median index: first i with cumsum(w)[i] >= 0.5  == count(cumsum < 0.5), clamped (renderers.py:260-263)
   if (median != nullptr || median_depth != nullptr) {
-    double run = warp_incl_scan_d(part, lane) - part;
+    double run = warp_excl_scan_d(part, lane);
     int cnt = 0;
     for (int i = i0; i < i1; ++i) {
       run += (double)w[i];

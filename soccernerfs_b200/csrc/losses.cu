@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(32 * kRaysPerBlock) interlevel_kernel(const fl
   const int i0 = lane * epl, i1 = min(Sp, i0 + epl);
   double part = 0.0;
   for (int i = i0; i < i1; ++i) part += (double)wp[n * Sp + i];
-  double run = warp_incl_scan_d(part, lane) - part;
+  double run = warp_excl_scan_d(part, lane);
   for (int i = i0; i < i1; ++i) {
     run += (double)wp[n * Sp + i];
     s_cy[i + 1] = (float)run;

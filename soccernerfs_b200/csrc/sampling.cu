@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) pdf_resample_kernel(
   part = 0.0;
   for (int i = i0; i < i1; ++i)
     part += (double)__fdiv_rn(__fadd_rn(__fadd_rn(w_row[i], hist_pad), pad_each), w_sum);
-  double run = warp_incl_scan_d(part, lane) - part;  // exclusive prefix of lane totals
+  double run = warp_excl_scan_d(part, lane);  // exclusive prefix of lane totals
   for (int i = i0; i < i1; ++i) {
     run += (double)__fdiv_rn(__fadd_rn(__fadd_rn(w_row[i], hist_pad), pad_each), w_sum);
     s_cdf[i + 1] = fminf(1.f, (float)run);
