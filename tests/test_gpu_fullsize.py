@@ -28,7 +28,7 @@ def _step_vs_oracle(cfg, n_rays, seed):
     # Gradients: the decoders are ReLU networks, so a sample whose hidden pre-activation lies within fp32 rounding of 0
     # (|pre| ~ 1e-7; a handful out of ~10^4 samples x 192 units) takes the other branch on the GPU than on the CPU and
     # its whole feature gradient changes -- an O(1) difference on the few texels only that sample touches (verified:
-    # every deviating sample has min|pre| < 2e-6, scripts/debug_cfg2b.py).  The bar is therefore: almost all entries
+    # every deviating sample has min|pre| < 2e-6, tests/tools/debug_cfg2b.py).  The bar is therefore: almost all entries
     # within 1e-4 of the tensor's max, the median relative error of the significant entries below 1e-4, and the tensor
     # as a whole within 2e-2 in relative L2 (one flipped sample of a 128-ray batch already moves the L2 norm by ~5e-3).
     for i, (a, b) in enumerate(zip(grads, ref_grads)):
