@@ -85,9 +85,9 @@ class Model(nn.Module):
         """ray bundle -> outputs."""
 
     def forward(self, ray_bundle: RayBundle) -> Dict[str, torch.Tensor]:
-        if self.collider is not None:
-            ray_bundle = self.collider(ray_bundle)
-        return self.get_outputs(ray_bundle)
+        """Collider (near / far planes) first, then the model's ``get_outputs`` (base_model.py:131-143)."""
+        bundle = ray_bundle if self.collider is None else self.collider(ray_bundle)
+        return self.get_outputs(bundle)
 
     def get_metrics_dict(self, outputs, batch) -> Dict[str, torch.Tensor]:
         return {}
@@ -98,26 +98,22 @@ class Model(nn.Module):
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, torch.Tensor]:
-        """Full-image inference in ``eval_num_rays_per_chunk`` chunks (base_model.py:162-186)."""
-        num_rays_per_chunk = self.config.eval_num_rays_per_chunk
-        image_height, image_width = camera_ray_bundle.origins.shape[:2]
-        num_rays = len(camera_ray_bundle)
-        outputs_lists = defaultdict(list)
-        for i in range(0, num_rays, num_rays_per_chunk):
-            ray_bundle = camera_ray_bundle.get_row_major_sliced_ray_bundle(i, i + num_rays_per_chunk)
-            outputs = self.forward(ray_bundle=ray_bundle)
-            for output_name, output in outputs.items():
-                outputs_lists[output_name].append(output)
-        outputs = {}
-        for output_name, outputs_list in outputs_lists.items():
-            if not torch.is_tensor(outputs_list[0]):
-                continue
-            outputs[output_name] = torch.cat(outputs_list).view(image_height, image_width, -1)
-        return outputs
+        """Full-image inference: the [H,W] bundle is rendered in row-major chunks of ``eval_num_rays_per_chunk`` rays
+        and every tensor output is stitched back to [H,W,C] (base_model.py:162-186).  ``engine.frame_renderer`` is the
+        pipelined variant that also generates the rays on the device."""
+        chunk = self.config.eval_num_rays_per_chunk
+        height, width = camera_ray_bundle.origins.shape[:2]
+        pieces: Dict[str, List[torch.Tensor]] = defaultdict(list)
+        for begin in range(0, len(camera_ray_bundle), chunk):
+            part = self.forward(ray_bundle=camera_ray_bundle.get_row_major_sliced_ray_bundle(begin, begin + chunk))
+            for name, value in part.items():
+                if torch.is_tensor(value):
+                    pieces[name].append(value)
+        return {name: torch.cat(values).view(height, width, -1) for name, values in pieces.items()}
 
     def get_image_metrics_and_images(self, outputs, batch) -> Tuple[Dict[str, float], Dict[str, torch.Tensor]]:
         raise NotImplementedError
 
     def load_model(self, loaded_state: Dict[str, Any]) -> None:
-        state = {key.replace("module.", ""): value for key, value in loaded_state["model"].items()}
-        self.load_state_dict(state)
+        """Load ``loaded_state["model"]``, tolerating a DDP ``module.`` prefix (base_model.py:201-208)."""
+        self.load_state_dict({k.replace("module.", ""): v for k, v in loaded_state["model"].items()})
