@@ -226,6 +226,46 @@ class TrainStep:
         self.step += 1
         return out
 
+    # ---- checkpoint / resume (NS/engine/trainer.py:326-380) ----------------------------------------------------
+    def state_dict(self) -> Dict:
+        """``{"step", "pipeline", "optimizers", "schedulers"}``: the layout ``Trainer.save_checkpoint`` writes
+        (trainer.py:362-373), model tensors under the pipeline's ``_model.`` prefix with OUR parameter names
+        (``utils.checkpoint.to_reference_state_dict`` converts the MLPs to tcnn's flat layout if a reference-format file
+        is wanted).  Optimizer step counts are taken from the trainer: a replayed graph advances them on the device."""
+        optimizers = {}
+        for name, opt in self.optimizers.optimizers.items():
+            sd = opt.state_dict()
+            for st in sd["state"].values():
+                st["step"] = self.step
+            sd["param_groups"] = [{k: v for k, v in g.items() if k != "hyper_dev"} for g in sd["param_groups"]]
+            optimizers[name] = sd
+        return {
+            "step": self.step,
+            "pipeline": {f"_model.{k}": v for k, v in self.model.state_dict().items()},
+            "optimizers": optimizers,
+            "schedulers": {name: sch.state_dict() for name, sch in self.optimizers.schedulers.items()},
+        }
+
+    def load_state_dict(self, state: Dict) -> None:
+        """Resume from ``state_dict()`` (trainer.py:326-350).  Captured graphs are dropped: they hold the addresses of
+        the optimizer state they were recorded with, and are re-captured on the next steps."""
+        self.model.load_state_dict({k[len("_model."):]: v for k, v in state["pipeline"].items() if k.startswith("_model.")})
+        for name, opt in self.optimizers.optimizers.items():
+            keep = [g.get("hyper_dev") for g in opt.param_groups]
+            opt.load_state_dict(state["optimizers"][name])
+            for g, h in zip(opt.param_groups, keep):
+                if h is not None:
+                    g["hyper_dev"] = h
+        for name, sch in self.optimizers.schedulers.items():
+            if name in state.get("schedulers", {}):
+                sch.load_state_dict(state["schedulers"][name])
+        self.step = int(state["step"])
+        self._graphs.clear()
+        self._graph_out.clear()
+        self._seen.clear()
+        if self._static is not None:
+            self._step_t.fill_(self.step)
+
     # ---- CUDA-graph path ----------------------------------------------------------------------------------
     def _setup_graph_state(self, ray_bundle: RayBundle, batch) -> None:
         dev = ray_bundle.origins.device
