@@ -284,12 +284,26 @@ def aabb_collider(origins, directions, aabb, near_plane: float = 0.0) -> Tuple[t
     return nears[:, None], fars[:, None]
 
 
-def _make_samples(origins, directions, nears, fars, times, bins) -> Samples:
-    euclid = bins * fars + (1 - bins) * nears  # ray_samplers.py:114-116 with identity spacing fn
-    return Samples(origins, directions, euclid[:, :-1], euclid[:, 1:], bins, nears, fars, times)
+def spacing_fns(spacing: str):
+    """(spacing_fn, spacing_fn_inv): "uniform" (UniformSampler, ray_samplers.py:129-150) or "piecewise"
+    (UniformLinDispPiecewiseSampler, ray_samplers.py:221-246: uniform up to distance 1, linear in disparity beyond)."""
+    if spacing == "uniform":
+        return (lambda x: x), (lambda x: x)
+    assert spacing == "piecewise"
+    return (lambda x: torch.where(x < 1, x / 2, 1 - 1 / (2 * x))), (lambda x: torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x)))
 
 
-def uniform_sampler(origins, directions, nears, fars, times, num_samples: int, t_rand: Optional[torch.Tensor]):
+def _make_samples(origins, directions, nears, fars, times, bins, spacing: str = "uniform") -> Samples:
+    fn, fn_inv = spacing_fns(spacing)
+    s_near, s_far = fn(nears), fn(fars)  # ray_samplers.py:114-116
+    euclid = fn_inv(bins * s_far + (1 - bins) * s_near)
+    smp = Samples(origins, directions, euclid[:, :-1], euclid[:, 1:], bins, nears, fars, times)
+    smp.spacing = spacing
+    return smp
+
+
+def uniform_sampler(origins, directions, nears, fars, times, num_samples: int, t_rand: Optional[torch.Tensor],
+                    spacing: str = "uniform"):
     """UniformSampler / SpacedSampler.generate_ray_samples, NS/model_components/ray_samplers.py:79-126.
     t_rand [N,S+1] (or [N,1] for single_jitter) is the reference's ``torch.rand`` draw; None = eval."""
     bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, :]
@@ -300,7 +314,7 @@ def uniform_sampler(origins, directions, nears, fars, times, num_samples: int, t
         bins = lower + (upper - lower) * t_rand
     else:
         bins = bins.expand(origins.shape[0], -1)
-    return _make_samples(origins, directions, nears, fars, times, bins)
+    return _make_samples(origins, directions, nears, fars, times, bins, spacing)
 
 
 def pdf_cdf(weights: torch.Tensor, histogram_padding: float = 0.01, eps: float = 1e-5) -> torch.Tensor:
@@ -341,7 +355,9 @@ def pdf_sampler(prev: Samples, weights: torch.Tensor, num_samples: int, rand: Op
     bins_g1 = torch.gather(existing, -1, above)
     t = torch.clip(torch.nan_to_num((u - cdf_g0) / (cdf_g1 - cdf_g0), 0), 0, 1)
     bins = (bins_g0 + t * (bins_g1 - bins_g0)).detach()
-    return _make_samples(prev.origins, prev.directions, prev.nears, prev.fars, prev.times, bins), inds
+    # the euclidean positions come from the level-0 sampler's closure (ray_samplers.py:359): same spacing function
+    return _make_samples(prev.origins, prev.directions, prev.nears, prev.fars, prev.times, bins,
+                         getattr(prev, "spacing", "uniform")), inds
 
 
 # --------------------------------------------------------------------------------------------

@@ -363,6 +363,7 @@ def main():
     gen_model(R)
     gen_importance(R)
     gen_raygen(R)
+    gen_samplers_cfg4(R)
 
 
 
@@ -463,6 +464,48 @@ def gen_raygen(R):
          directions_norm=rb.metadata["directions_norm"], frame_cam=torch.tensor(3),
          frame_origins=frame.origins, frame_directions=frame.directions, frame_pixel_area=frame.pixel_area,
          frame_times=frame.times, frame_directions_norm=frame.metadata["directions_norm"])
+
+
+def gen_samplers_cfg4(R):
+    """BASELINE config 4 (nerfplayer-nerfacto: only the sampler + compositing are shared with the path): the piecewise
+    uniform / linear-in-disparity initial sampler and PDF resampling with single_jitter=True (nerfacto.py:125,
+    nerfplayer_nerfacto.py:173-179), and DepthRenderer("expected") (:190), all by the reference's own classes."""
+    g = torch.Generator().manual_seed(707)
+    n = 48
+    origins, directions, times, aabb = ko.synthetic_rays(n, g)
+    RS = R.ray_samplers
+    nears = 0.05 + 0.1 * torch.rand(n, 1, generator=g)
+    fars = 2.0 + 4.0 * torch.rand(n, 1, generator=g)  # beyond distance 1: both branches of the piecewise spacing
+    nears[5], fars[5] = 1.2, 1.9  # a ray entirely in the disparity branch
+    nears[6], fars[6] = 0.1, 0.8  # and one entirely in the uniform branch
+    arrs = dict(origins=origins, directions=directions, times=times, nears=nears, fars=fars)
+    for mode in ("train", "eval"):
+        ini = RS.UniformLinDispPiecewiseSampler(single_jitter=True)
+        pdf = RS.PDFSampler(include_original=False, single_jitter=True)
+        ini.train(mode == "train")
+        pdf.train(mode == "train")
+        s0, s1 = 64, 24
+        t_rand = torch.rand(n, 1, generator=g)
+        u_rand = torch.rand(n, 1, generator=g)
+        weights = torch.rand(n, s0, 1, generator=g) ** 3
+        rb = R.rays.RayBundle(origins=origins, directions=directions, pixel_area=torch.ones(n, 1), times=times,
+                              nears=nears.clone(), fars=fars.clone())
+        ss = []
+        with rand_queue([t_rand, u_rand] if mode == "train" else []), record_searchsorted(ss):
+            rs0 = ini(rb, num_samples=s0)
+            rs1 = pdf(rb, rs0, weights, num_samples=s1)
+        w1 = torch.rand(n, s1, 1, generator=g)
+        w1 = w1 / w1.sum(-2, keepdim=True)
+        depth = R.renderers.DepthRenderer(method="expected")(weights=w1, ray_samples=rs1)
+        arrs.update({
+            f"{mode}_t_rand": t_rand, f"{mode}_u_rand": u_rand, f"{mode}_weights": weights,
+            f"{mode}_bins0": torch.cat([rs0.spacing_starts[..., 0], rs0.spacing_ends[..., -1:, 0]], -1),
+            f"{mode}_starts0": rs0.frustums.starts[..., 0], f"{mode}_ends0": rs0.frustums.ends[..., 0],
+            f"{mode}_bins1": torch.cat([rs1.spacing_starts[..., 0], rs1.spacing_ends[..., -1:, 0]], -1),
+            f"{mode}_starts1": rs1.frustums.starts[..., 0], f"{mode}_ends1": rs1.frustums.ends[..., 0],
+            f"{mode}_inds1": ss[0], f"{mode}_w1": w1, f"{mode}_depth_expected": depth,
+        })
+    save("samplers_cfg4", **arrs)
 
 
 if __name__ == "__main__":

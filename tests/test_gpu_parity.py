@@ -293,7 +293,7 @@ def test_loss_head_matches_torch_formulas():
             assert rel_err(a, b) < 1e-6
     # without distortion / interlevel terms
     vals, total, _ = ops.loss_head(pred.detach(), image, None, [], 2.0, 0.0, 0.0)
-    assert abs(float(total) - 2.0 * float(torch.nn.functional.mse_loss(image, pred))) < 1e-6
+    assert abs(float(total) - 2.0 * float(torch.nn.functional.mse_loss(image, pred.detach()))) < 1e-6
 
 
 def test_decoders_and_density_field_vs_oracle():
@@ -684,3 +684,40 @@ def test_trainer_checkpoint_resume():
         for pa, pb in zip(model_a.parameters(), model_b.parameters()):
             if pa.numel():
                 assert rel_err(pb, pa) < 1e-2
+
+
+def test_cfg4_piecewise_single_jitter_samplers_vs_reference_fixture():
+    """BASELINE config 4 (nerfplayer-nerfacto shares only the samplers + compositing): piecewise initial sampler and
+    PDF resampling with one jitter per ray, through the sampler modules, vs the reference's own classes; expected depth."""
+    from soccernerfs_b200.cameras.rays import RayBundle
+    from soccernerfs_b200.model_components.ray_samplers import PDFSampler, UniformLinDispPiecewiseSampler
+    from soccernerfs_b200.model_components.renderers import DepthRenderer
+    from tests.helpers import rand_queue
+
+    g = load_golden("samplers_cfg4")
+    n = g["origins"].shape[0]
+    for mode in ("train", "eval"):
+        ini = UniformLinDispPiecewiseSampler(single_jitter=True)
+        pdf = PDFSampler(include_original=False, single_jitter=True)
+        ini.train(mode == "train")
+        pdf.train(mode == "train")
+        pdf.record_inds = True
+        rb = RayBundle(origins=g["origins"].to(DEV), directions=g["directions"].to(DEV), pixel_area=torch.ones(n, 1, device=DEV),
+                       times=g["times"].to(DEV), nears=g["nears"].to(DEV), fars=g["fars"].to(DEV))
+        queue = [g[f"{mode}_t_rand"], g[f"{mode}_u_rand"]] if mode == "train" else []
+        with rand_queue(queue, DEV):
+            rs0 = ini(rb, num_samples=64)
+            rs1 = pdf(rb, rs0, g[f"{mode}_weights"].to(DEV), num_samples=24)
+        bins0 = torch.cat([rs0.spacing_starts[..., 0], rs0.spacing_ends[..., -1:, 0]], -1).cpu()
+        assert torch.equal(bins0, g[f"{mode}_bins0"])
+        # euclidean edges: 1 / (2 - 2x) etc. with IEEE division, like torch's CPU ops
+        assert (rs0.frustums.starts[..., 0].cpu() - g[f"{mode}_starts0"]).abs().max() < 1e-6
+        assert (rs0.frustums.starts[..., 0].cpu() == g[f"{mode}_starts0"]).float().mean() > 0.99
+        assert (rs0.frustums.ends[..., 0].cpu() - g[f"{mode}_ends0"]).abs().max() < 1e-6
+        bins1 = torch.cat([rs1.spacing_starts[..., 0], rs1.spacing_ends[..., -1:, 0]], -1).cpu()
+        assert (pdf.last_inds.cpu() != g[f"{mode}_inds1"]).float().mean() < 2e-3
+        assert (bins1 - g[f"{mode}_bins1"]).abs().max() < 2e-6
+        rel = (rs1.frustums.starts[..., 0].cpu() - g[f"{mode}_starts1"]).abs() / g[f"{mode}_starts1"].abs().clamp_min(1e-3)
+        assert rel.max() < 2e-5  # the disparity branch amplifies a 1-ulp spacing difference near the far plane
+        depth = DepthRenderer(method="expected")(weights=g[f"{mode}_w1"].to(DEV), ray_samples=rs1)
+        assert rel_err(depth.cpu(), g[f"{mode}_depth_expected"]) < 1e-4

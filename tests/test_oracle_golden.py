@@ -155,3 +155,22 @@ def test_ray_generation_matches_reference():
     assert torch.equal(o.view(h, w, 3), g["frame_origins"]) and torch.equal(t.view(h, w, 1), g["frame_times"])
     assert rel_err(d.view(h, w, 3), g["frame_directions"]) < 1e-6
     assert rel_err(pa.view(h, w, 1), g["frame_pixel_area"]) < 1e-5
+
+
+def test_cfg4_piecewise_single_jitter_samplers_match_reference():
+    """BASELINE config 4: UniformLinDispPiecewiseSampler + PDFSampler with single_jitter=True and the expected-depth
+    renderer, vs the reference's own classes (fixture samplers_cfg4)."""
+    g = load_golden("samplers_cfg4")
+    o, d, t, nears, fars = g["origins"], g["directions"], g["times"], g["nears"], g["fars"]
+    for mode in ("train", "eval"):
+        tr = g[f"{mode}_t_rand"] if mode == "train" else None  # [N,1]: one jitter per ray
+        ur = g[f"{mode}_u_rand"] if mode == "train" else None
+        s0 = ko.uniform_sampler(o, d, nears, fars, t, 64, tr, spacing="piecewise")
+        assert torch.equal(s0.spacing_bins, g[f"{mode}_bins0"])
+        assert torch.equal(s0.starts, g[f"{mode}_starts0"]) and torch.equal(s0.ends, g[f"{mode}_ends0"])
+        s1, inds = ko.pdf_sampler(s0, g[f"{mode}_weights"][..., 0], 24, ur)
+        assert torch.equal(inds, g[f"{mode}_inds1"])
+        assert torch.equal(s1.spacing_bins, g[f"{mode}_bins1"])
+        assert torch.equal(s1.starts, g[f"{mode}_starts1"]) and torch.equal(s1.ends, g[f"{mode}_ends1"])
+        depth = ko.render_depth_expected(g[f"{mode}_w1"], s1.steps())
+        assert rel_err(depth, g[f"{mode}_depth_expected"]) < 1e-6
