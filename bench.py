@@ -8,7 +8,8 @@
 A "step" = one full training iteration on one batch of synthetic rays of the broadcast-style scene shape:
 AABB collider -> proposal sampling (256 + 128 samples, both proposal fields evaluated and trained every step)
 -> K-Planes field (48 samples) -> compositing -> rgb / distortion / interlevel / plane regularisers ->
-backward -> [NCCL all-reduce of the flat gradient bucket when N>1] -> Adam (lr 1e-2, eps 1e-12) -> cosine LR.
+backward -> [all-reduce of the flat gradient buckets when N>1: our NVLink peer-memory kernel, NCCL if the peer arenas
+cannot be set up] -> Adam (lr 1e-2, eps 1e-12) -> cosine LR.
 Workload at N=1 = BASELINE.json configs[1] ("K-Planes default": multiscale-res 1 2 4 8, C=32, proposal sampler,
 4096 rays/step).  N>1: weak scaling, every rank owns its own 4096-ray slice of a global N*4096-ray batch.
 

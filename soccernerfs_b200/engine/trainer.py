@@ -2,7 +2,7 @@
 callback calls around it (:212, :221): callbacks BEFORE -> zero_grad -> forward (collider + get_outputs) ->
 metrics -> loss dict -> backward -> [gradient all-reduce] -> Adam -> scheduler -> callbacks AFTER.
 
-``use_cuda_graph=True`` captures that whole iteration (≈250 kernel launches) in a CUDA graph per sampler mode
+``use_cuda_graph=True`` captures that whole iteration (≈100 kernel launches) in a CUDA graph per sampler mode
 ("proposal networks updated" / "not updated") and replays it: the launch-bound Python/autograd dispatch then
 costs one ``cudaGraphLaunch``.  Per-step scalars that the eager loop keeps on the host (Adam bias corrections,
 cosine LR, proposal-weight anneal exponent) are looked up on the device from tables indexed by a device-resident
