@@ -218,6 +218,13 @@ int kp_generate_rays(const float* c2w /* [n_cams,3,4] */, const float* intrinsic
                      float* directions, float* pixel_area, float* directions_norm /* or NULL */, float* times /* or NULL */,
                      void* stream);
 
+/* ---- (f4) IST importance map: DynamicDataset.compute_ist, NS/data/datasets/dynamic_dataset.py:328-470.
+ *      images [B,H*W,3] fp32; nbr_offsets [B+1] / nbrs: DEVICE int32 CSR lists of each image's temporal neighbours
+ *      (same camera, 0.01 < |dt| <= ist_range, built by the host); out [B,H*W] fp16: mean over channels of the max abs
+ *      difference to the neighbours, <= alpha zeroed; ones for an image without neighbours. ---- */
+int kp_ist_map(const float* images, int B, int64_t HW, const int32_t* nbr_offsets, const int32_t* nbrs, float alpha,
+               void* out_fp16, void* stream);
+
 /* ---- (a14b) loss head: the reductions, coefficients, total and PSNR that KPlanesModel.get_loss_dict /
  *      get_metrics_dict (NS/models/kplanes.py:392-452) and the trainer's sum(loss_dict.values())
  *      (NS/engine/trainer.py:398-400) apply to the per-ray / per-sample loss kernels' outputs, one launch per

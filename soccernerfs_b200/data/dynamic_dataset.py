@@ -1,8 +1,8 @@
 """Importance-sampling weight maps of the dynamic dataset: IST (temporal difference) and ISG (global median).
 
 Arithmetic of ``DynamicDataset.compute_ist`` (NS/data/datasets/dynamic_dataset.py:328-470) and ``compute_isg``
-(:215-326) on an image batch, without the file caching / tqdm / debug-map code around it.  Host-side torch ops (the
-reference runs them once per image-cache reload, not per training step; SURVEY.md 8a row a18 keeps them off the kernels).
+(:215-326) on an image batch, without the file caching / tqdm / debug-map code around it.  Host-side torch ops like the reference's (it runs them once per image-cache reload, not per training step); IST also
+has a device path (``compute_ist_cuda`` -> ``kp_ist_map``) used when the images are on the GPU.
 """
 from __future__ import annotations
 
@@ -11,11 +11,37 @@ import torch
 IST_ALPHA = 0.15  # dynamic_dataset.py:420: differences below this are camera shake / noise
 
 
+def temporal_neighbours(cam_ids: torch.Tensor, cam_times: torch.Tensor, ist_range: float):
+    """Per image the indices of the SAME camera's images whose time differs by (0.01, ist_range]
+    (dynamic_dataset.py:398-407), as CSR lists (offsets int32 [B+1], neighbours int32) on the host."""
+    cam_ids = cam_ids.reshape(-1).cpu()
+    cam_times = cam_times.reshape(-1).cpu()
+    offsets, nbrs = [0], []
+    for i in range(cam_ids.shape[0]):
+        same_cam = torch.where(cam_ids == cam_ids[i])[0]
+        dt = torch.abs(cam_times[same_cam] - cam_times[i])
+        close = same_cam[torch.where((dt <= ist_range) & (dt > 0.01))[0]]
+        nbrs += close.tolist()
+        offsets.append(len(nbrs))
+    return torch.tensor(offsets, dtype=torch.int32), torch.tensor(nbrs, dtype=torch.int32)
+
+
+def compute_ist_cuda(images: torch.Tensor, cam_ids: torch.Tensor, cam_times: torch.Tensor, ist_range: float) -> torch.Tensor:
+    """``compute_ist`` with the per-pixel work in ``kp_ist_map`` (images on the GPU, [B,H,W,3] fp32) -> fp16 [B,H,W] on
+    the GPU, bit-identical to the host version."""
+    from .. import ops
+
+    offsets, nbrs = temporal_neighbours(cam_ids, cam_times, ist_range)
+    return ops.ist_map(images, offsets.to(images.device), nbrs.to(images.device), IST_ALPHA)
+
+
 def compute_ist(images: torch.Tensor, cam_ids: torch.Tensor, cam_times: torch.Tensor, ist_range: float,
                 device="cpu") -> torch.Tensor:
     """images [B,H,W,3], cam_ids [B] or [B,1], cam_times [B] or [B,1] -> fp16 [B,H,W].
     For every image: max abs difference to the images of the SAME camera whose time differs by (0.01, ist_range],
     mean over channels, values <= 0.15 zeroed; an image without such neighbours gets a uniform map."""
+    if images.is_cuda:
+        return compute_ist_cuda(images, cam_ids, cam_times, ist_range)
     b, h, w = images.shape[:3]
     cam_ids = cam_ids.reshape(-1)
     cam_times = cam_times.reshape(-1)

@@ -669,6 +669,23 @@ def generate_rays(c2w: torch.Tensor, intrinsics: torch.Tensor, cam_times: Option
     return origins, directions, pixel_area, norm, times
 
 
+def ist_map(images: torch.Tensor, nbr_offsets: torch.Tensor, nbrs: torch.Tensor, alpha: float) -> torch.Tensor:
+    """IST importance map (dynamic_dataset.py:328-470): images [B,H,W,3] fp32 (CUDA), CSR neighbour lists int32 (CUDA)
+    -> fp16 [B,H,W]."""
+    img = f32c(images)
+    b, h, w = img.shape[:3]
+    if img.shape[-1] != 3:
+        raise ValueError("ist_map: images must be [B,H,W,3]")
+    off = nbr_offsets.to(device=img.device, dtype=torch.int32).contiguous()
+    nb = nbrs.to(device=img.device, dtype=torch.int32).contiguous()
+    if off.numel() != b + 1:
+        raise ValueError("ist_map: nbr_offsets must have B+1 entries")
+    out = torch.empty((b, h, w), dtype=torch.float16, device=img.device)
+    call("kp_ist_map", ptr(img), b, h * w, c_void_p(off.data_ptr()), c_void_p(nb.data_ptr() if nb.numel() else 0), float(alpha),
+         c_void_p(out.data_ptr()), stream_ptr())
+    return out
+
+
 _HEAD_WS: Dict = {}
 
 

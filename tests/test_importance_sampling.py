@@ -54,3 +54,30 @@ def test_importance_pixel_sampler_bit_exact():
     h, wd = g["images"].shape[1:3]
     assert torch.equal(PixelSampler(32).sample_method(32, b, h, wd), g["uniform"])
     assert isinstance(make_pixel_sampler(DynamicDataManagerConfig(use_importance_sampling=False), 8), PixelSampler)
+
+
+def test_temporal_neighbour_lists():
+    """The CSR neighbour lists handed to kp_ist_map: same camera, 0.01 < |dt| <= ist_range (host logic)."""
+    from soccernerfs_b200.data.dynamic_dataset import temporal_neighbours
+
+    cam_ids = torch.tensor([0, 0, 0, 1, 0])
+    cam_times = torch.tensor([0.0, 0.1, 0.105, 0.1, 0.5])
+    off, nb = temporal_neighbours(cam_ids, cam_times, 0.25)
+    assert off.tolist() == [0, 2, 3, 4, 4, 4]  # image 1 and 2 are only 0.005 apart; image 3 is another camera; 4 too far
+    assert nb.tolist() == [1, 2, 0, 0]
+    assert off.dtype == torch.int32 and nb.dtype == torch.int32
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_ist_map_kernel_bit_exact_vs_reference_fixture():
+    """(f4) kp_ist_map == the IST map the reference's own compute_ist produced (fp16, every pixel identical)."""
+    from soccernerfs_b200.data.dynamic_dataset import compute_ist
+
+    g = load_golden("importance")
+    ist = compute_ist(g["images"].cuda(), g["cam_ids"], g["cam_times"], 0.25)
+    assert ist.is_cuda and ist.dtype == torch.float16 and ist.shape == g["ist"].shape
+    assert torch.equal(ist.float().cpu(), g["ist"])
+    assert bool((ist[11] == 1).all())  # the only frame of its camera: uniform map
