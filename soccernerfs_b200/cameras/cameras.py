@@ -151,7 +151,17 @@ class Cameras:
         return self._bundle(out, camera_indices.to(dev), shape, aabb_box)
 
     def generate_rays_from_indices(self, ray_indices: torch.Tensor, aabb_box: Optional[SceneBox] = None) -> RayBundle:
-        """(camera,row,col) triplets -> rays, what RayGenerator.forward computes, without building coords."""
+        """(camera,row,col) triplets -> rays, what RayGenerator.forward computes, without building coords.
+        Indices that arrive on the host (the pixel samplers produce them there) are range-checked like the reference's
+        tensor indexing would; device-resident indices are trusted (checking them would cost a synchronisation) and the
+        kernel clamps the camera index."""
+        if not ray_indices.is_cuda and ray_indices.numel():
+            cam, row, col = ray_indices[:, 0], ray_indices[:, 1], ray_indices[:, 2]
+            if int(cam.min()) < 0 or int(cam.max()) >= self.size:
+                raise IndexError(f"camera index out of range [0, {self.size})")
+            h, w = self.height.cpu()[cam.long(), 0], self.width.cpu()[cam.long(), 0]
+            if bool((row < 0).any() or (col < 0).any() or (row >= h).any() or (col >= w).any()):
+                raise IndexError("pixel index outside its camera's image")
         tri = ray_indices.to(self.device).to(torch.int64).contiguous()
         out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, ray_indices=tri)
         return self._bundle(out, tri[:, 0:1], (tri.shape[0],), aabb_box)

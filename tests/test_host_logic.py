@@ -156,3 +156,27 @@ def test_reference_checkpoint_round_trip():
     for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
         assert na == nb and torch.equal(pa, pb), na
     assert ops.is_channel_last(b.field.grids[0][0])  # storage layout untouched by the load
+
+
+def test_cameras_reject_unsupported_and_out_of_range():
+    """cameras/cameras.py host-side contract: only undistorted perspective cameras; host indices are range-checked."""
+    import pytest
+    import torch
+
+    from soccernerfs_b200.cameras.cameras import Cameras, CameraType
+
+    c2w = torch.eye(4)[:3].repeat(2, 1, 1)
+    cams = Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, times=torch.tensor([0.1, 0.2]))
+    assert cams.shape == (2,) and len(cams) == 2 and cams.get_image_coords().shape == (36, 64, 2)
+    assert float(cams.get_image_coords()[3, 5, 0]) == 3.5 and float(cams.get_image_coords()[3, 5, 1]) == 5.5
+    with pytest.raises(NotImplementedError):
+        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, camera_type=CameraType.FISHEYE)
+    with pytest.raises(NotImplementedError):
+        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, distortion_params=torch.full((2, 6), 0.1))
+    Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, distortion_params=torch.zeros(2, 6))  # all-zero distortion is fine
+    with pytest.raises(IndexError):
+        cams.generate_rays_from_indices(torch.tensor([[2, 0, 0]]))
+    with pytest.raises(IndexError):
+        cams.generate_rays_from_indices(torch.tensor([[0, 36, 0]]))
+    with pytest.raises(NotImplementedError):
+        cams.generate_rays(camera_indices=0, coords=torch.tensor([[0.25, 0.5]]))  # not a pixel centre
