@@ -9,7 +9,7 @@ this package alone (synthetic data, tests).
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, Dict, Literal, Optional
+from typing import Any, Literal, Optional
 
 import torch
 

@@ -8,7 +8,7 @@ to the common batch shape; indexing / reshape / flatten / to apply to the batch 
 from __future__ import annotations
 
 import dataclasses
-from typing import Any, Callable, Dict, Optional, Tuple
+from typing import Any, Callable, Tuple
 
 import numpy as np
 import torch
