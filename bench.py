@@ -250,6 +250,15 @@ def run_ours(args):
     for name, ms_list in kernel_ms.items():
         calls_per_step = len(ms_list) / args.steps
         per_kernel[name] = {"ms_per_step": sum(ms_list) / args.steps, "launches_per_step": calls_per_step}
+    # algorithmic bandwidth of every field kernel (bytes per STEP of that entry point / its time per step): the gather and
+    # the scatter are one launch each; the proposal fields are two launches per step (256 + 128 samples per ray)
+    step_bytes = {"kp_hexplane_fwd": ALGO_BYTES["kp_hexplane_fwd"], "kp_hexplane_bwd": ALGO_BYTES["kp_hexplane_bwd"],
+                  "kp_density_field_fwd": ALGO_BYTES["kp_density_field_fwd"] * (256 + 128),
+                  "kp_density_field_bwd": ALGO_BYTES["kp_density_field_bwd"] * (256 + 128)}
+    for name, nbytes in step_bytes.items():
+        if name in per_kernel and per_kernel[name]["ms_per_step"] > 0:
+            gbs = nbytes / (per_kernel[name]["ms_per_step"] * 1e-3) / 1e9
+            per_kernel[name].update({"algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
     top = max(("kp_hexplane_fwd", "kp_hexplane_bwd"), key=lambda k: per_kernel.get(k, {"ms_per_step": 0})["ms_per_step"])
     top_ms = per_kernel[top]["ms_per_step"] / per_kernel[top]["launches_per_step"]
     achieved = ALGO_BYTES[top] / (top_ms * 1e-3) / 1e9
