@@ -7,19 +7,26 @@
 
 A "step" = one full training iteration on one batch of synthetic rays of the broadcast-style scene shape:
 AABB collider -> proposal sampling (256 + 128 samples, both proposal fields evaluated and trained every step)
--> K-Planes field (48 samples) -> compositing -> rgb / distortion / interlevel / plane regularisers ->
-backward -> [all-reduce of the flat gradient buckets when N>1: our NVLink peer-memory kernel, NCCL if the peer arenas
-cannot be set up] -> Adam (lr 1e-2, eps 1e-12) -> cosine LR.
-Workload at N=1 = BASELINE.json configs[1] ("K-Planes default": multiscale-res 1 2 4 8, C=32, proposal sampler,
-4096 rays/step).  N>1: weak scaling, every rank owns its own 4096-ray slice of a global N*4096-ray batch.
+-> K-Planes field -> compositing -> rgb / distortion / interlevel / plane regularisers -> backward ->
+[all-reduce of the flat gradient buckets when N>1] -> Adam (lr 1e-2, eps 1e-12) -> cosine LR.
 
-The JSON line carries: value (inputs resident in HBM), e2e (host buffers: pinned H2D of the batch and a D2H read
-of the loss inside the timed region, every step), roofline (dominant kernel, timed live with CUDA events),
-cpu_baseline (oracle port on the host cores, rank 0, N=1 only), clocks, gpu_launches.
+Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[1] ("K-Planes default", cfg2: multiscale-res 1 2 4 8,
+4096 rays/step, 48 samples).  The same JSON line also carries
+  "cfg3"               the 32x preset (configs[2]: multiscale-res 1..32, T=100, sigma hidden 128, 64 samples; 2.3 GB of
+                       planes, the HBM-bound regime) with its own value / e2e / per-scale roofline;
+  "eval"               configs[4]: full 1920x1080 frames from the cfg3 field, tile-sharded over the ranks;
+  "l2_peaks"           the achievable rate of the field kernels' own access pattern (random 128-byte lines) in L2 and in
+                       HBM, measured live with kp_line_probe: the denominators of the per-scale fractions;
+  "gpu_torch_baseline" the reference's own step as plain torch ops on the same GPU (N=1 only): the like-for-like "before";
+  "cpu_baseline"       the oracle port on the host cores (N=1 only);
+  "dp_check"           (N>1) parameters bit-identical across ranks after all steps, and the all-reduced gradient equal to
+                       a single-rank gradient on the concatenated batch.
+N>1: weak scaling, every rank owns its own 4096-ray slice of a global N*4096-ray batch.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -33,7 +40,31 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 RAYS_PER_RANK = 4096
-WORKLOAD = "kplanes-default(cfg2): multiscale-res 1 2 4 8, C=32, T=50, proposals [128^3,150]+[256^3,150] C=8, 256/128/48 samples, 4096 rays/rank"
+L2_BYTES = 126 * 1024 * 1024
+
+WORKLOADS = {
+    "cfg2": {
+        "label": "kplanes-default(cfg2): multiscale-res 1 2 4 8, C=32, T=50, proposals [128^3,150]+[256^3,150] C=8, "
+                 "256/128/48 samples, 4096 rays/rank",
+        "oracle": "cfg2",
+        "model": {},
+    },
+    "cfg3": {
+        "label": "kplanes-32x(cfg3): multiscale-res 1 2 4 8 16 32, C=32, T=100, sigma hidden 128, no view dependence, "
+                 "proposals [128^3,100]+[256^3,100] C=8, 256/128/64 samples, 4096 rays/rank",
+        "oracle": "cfg3",
+        "model": dict(spacetime_resolution=(64, 64, 64, 100), multiscale_res=(1, 2, 4, 8, 16, 32), sigma_net_hidden_dim=128,
+                      disable_viewing_dependent=True, num_nerf_samples_per_ray=64, num_proposal_samples_per_ray=(256, 128),
+                      proposal_net_args_list=[{"feature_dim": 8, "resolution": [128, 128, 128, 100]},
+                                              {"feature_dim": 8, "resolution": [256, 256, 256, 100]}],
+                      eval_num_rays_per_chunk=32768),
+    },
+}
+WORKLOAD = WORKLOADS["cfg2"]["label"]
+FIELD_KERNELS = ("kp_hexplane_fwd", "kp_hexplane_bwd", "kp_density_field_fwd", "kp_density_field_bwd")
+OTHER_TIMED = ("kp_decoder_fwd_fused", "kp_decoder_bwd_fused", "kp_color_net_bwd", "kp_sigma_net_bwd", "kp_sigma_net_fwd",
+               "kp_color_net_fwd", "kp_adam_multi", "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd", "kp_plane_reg_grad_write",
+               "kp_peer_allreduce", "kp_peer_reduce_scatter", "kp_peer_allgather")
 
 
 def _peaks():
@@ -84,11 +115,12 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        # median of the samples taken UNDER LOAD (the idle samples before / after the timed region sit at the idle clock)
+        busy = sorted(s for s in sm if mx is None or s >= 0.5 * mx) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _dist_setup(n_gpus: int):
+def _dist_setup():
     import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -122,33 +154,198 @@ def _bundle(packed_dev):
     return rb, {"image": packed_dev[:, 7:10].contiguous()}
 
 
-ALGO_BYTES = {  # algorithmic bytes per launch at cfg2 / 4096 rays (DESIGN.md "roofline")
-    "kp_hexplane_fwd": 4096 * 48 * 4 * 6 * 4 * 32 * 4,          # K*P*4 corners*C*4 B per field sample
-    "kp_hexplane_bwd": 2 * 4096 * 48 * 4 * 6 * 4 * 32 * 4,      # re-read + reduction payload
-    "kp_density_field_fwd": 4096 * 6 * 4 * 8 * 4,                # per proposal sample: 768 B (x S below)
-    "kp_density_field_bwd": 2 * 4096 * 6 * 4 * 8 * 4,
-}
+def build_model(name: str, dev):
+    """Same parameters on every rank (seed 42, like the reference's DDP broadcast of rank 0's model)."""
+    from soccernerfs_b200.data.scene_box import SceneBox
+    from soccernerfs_b200.data.synthetic import perturb_time_planes, synthetic_rays
+    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
+
+    torch.manual_seed(42)
+    _, _, _, aabb = synthetic_rays(4, torch.Generator().manual_seed(0))
+    model = KPlanesModelConfig(**WORKLOADS[name]["model"]).setup(scene_box=SceneBox(aabb=aabb), num_train_data=19 * 25).to(dev)
+    perturb_time_planes(model)
+    return model
 
 
-def run_ours(args):
-    rank, world, local = _dist_setup(args.gpus)
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (our arm) needs a CUDA device: the product path has no CPU fallback")
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
+# ----------------------------------------------------------------------------------------------------------------------
+# memory-hierarchy probe: achievable rate of the field kernels' access pattern in L2 and in HBM
+# ----------------------------------------------------------------------------------------------------------------------
+def line_probe_peaks(dev):
+    """kp_line_probe over an L2-resident (64 MB) and an HBM-resident (4 GB) buffer, loads and red.v4 -> GB/s."""
+    from ctypes import c_int64, byref, c_void_p
+
+    from soccernerfs_b200 import _lib
+
+    out = {"pattern": "8 lanes x 16 B = one 128-byte line at a pseudo-random texel, 8 independent lines in flight per lane",
+           "l2_buffer_mb": 64, "hbm_buffer_mb": 4096}
+    sink = torch.zeros(1, device=dev)
+    blocks, iters = 148 * 8, 256
+    for level, mb in (("l2", 64), ("hbm", 4096)):
+        buf = torch.zeros(mb * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+        n_lines = buf.numel() // 32
+        for mode, mname in ((0, "gather"), (1, "red")):
+            best = None
+            for rep in range(4):
+                touched = c_int64(0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.call("kp_line_probe", c_void_p(buf.data_ptr()), n_lines, mode, blocks, iters, 1234 + rep, c_void_p(sink.data_ptr()),
+                          byref(touched), _lib.stream_ptr())
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                if rep > 0:  # first launch warms the buffer into L2 (l2 level) / the TLBs
+                    best = ms if best is None else min(best, ms)
+            out[f"{level}_{mname}_gbs"] = touched.value * 128 / (best * 1e-3) / 1e9
+        del buf
+        torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# per-scale gather / scatter on the step's own samples
+# ----------------------------------------------------------------------------------------------------------------------
+def per_scale_probe(model, flush, peaks, probe, reps=3):
+    from ctypes import c_void_p
+
+    from soccernerfs_b200 import _lib, ops
+
+    field = model.field
+    pts = field._last_points
+    ms_planes = [[ops.as_channel_last(p.detach()) for p in g] for g in field.grids]
+    flat = [p for g in ms_planes for p in g]
+    n_scales, n_planes = len(ms_planes), len(ms_planes[0])
+    c, m = flat[0].shape[1], pts.M
+    dev = flat[0].device
+    gout = torch.randn(m, n_scales * c, device=dev)
+    out1 = torch.empty(m, c, device=dev)
+    pstruct = pts.struct()
+    rows = []
+
+    def timed(fn):
+        best = None
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+        return best
+
+    for k in range(n_scales):
+        planes = ms_planes[k]
+        plane_bytes = sum(p.numel() * 4 for p in planes)
+        grads = [p.grad if (p.grad is not None and p.grad.stride() == q.stride()) else torch.zeros_like(q)
+                 for p, q in zip(field.grids[k], planes)]
+        targets = [None] * (n_scales * n_planes)
+        targets[k * n_planes:(k + 1) * n_planes] = grads
+        t_f = timed(lambda: _lib.call("kp_hexplane_fwd", ops._plane_ptrs(planes), ops._plane_hw(planes), 1, n_planes, c, pstruct, m, 1,
+                                      0x3F, c_void_p(out1.data_ptr()), _lib.stream_ptr()))
+        t_b = timed(lambda: _lib.call("kp_hexplane_bwd", ops._plane_ptrs(flat), ops._plane_ptrs(targets), ops._plane_hw(flat), n_scales,
+                                      n_planes, c, pstruct, m, 1, 0x3F, c_void_p(gout.data_ptr()), _lib.stream_ptr()))
+        algo_f = m * n_planes * 4 * c * 4
+        row = {"scale": int(field.multiscale_res_multipliers[k]), "plane_mb": plane_bytes / 2**20}
+        for tag, t, algo, ws, l2key in (("gather", t_f, algo_f, plane_bytes, "l2_gather_gbs"),
+                                        ("scatter", t_b, 2 * algo_f, 2 * plane_bytes, "l2_red_gbs")):
+            level = "l2" if ws <= 0.6 * L2_BYTES else ("hbm" if ws >= 2 * L2_BYTES else "l2+hbm")
+            gbs = algo / (t * 1e-3) / 1e9
+            row[tag] = {"ms": t, "algorithmic_gbs": gbs, "working_set_mb": ws / 2**20, "level": level,
+                        "frac_of_l2_probe": gbs / probe[l2key] if probe else None, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+        rows.append(row)
+    return rows
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# data-parallel correctness (N>1): the driver never runs tests/test_gpu_multi.py, so the bench asserts it
+# ----------------------------------------------------------------------------------------------------------------------
+@contextlib.contextmanager
+def _global_rand(rank, world, seed, dev):
+    """torch.rand([n, ...]) -> this rank's rows of a [world*n, ...] draw every rank generates identically (rank<0: all rows)."""
+    real = torch.rand
+    gen = torch.Generator(device=dev).manual_seed(seed)
+
+    def fake(*size, **kw):
+        if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)):
+            size = tuple(size[0])
+        n = size[0] if rank >= 0 else size[0] // world
+        full = real((n * world,) + tuple(size[1:]), generator=gen, device=dev)
+        return full if rank < 0 else full[rank * n:(rank + 1) * n].contiguous()
+
+    torch.rand = fake
+    try:
+        yield
+    finally:
+        torch.rand = real
+
+
+def dp_check(trainer, model, rank, world, dev):
+    import torch.distributed as dist
+
+    def checksum():
+        acc = torch.zeros((), dtype=torch.int64, device=dev)
+        for p in model.parameters():
+            if p.numel():
+                acc += p.detach().contiguous().view(-1).view(torch.int32).to(torch.int64).sum()
+        return acc
+
+    # (1) after every step so far the replicas must hold the same bits
+    sums = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sums, checksum())
+    identical = all(int(s) == int(sums[0]) for s in sums)
+    # (2) all-reduced gradient of one more DP step == gradient of ONE rank on the concatenated batch
+    from soccernerfs_b200.data.synthetic import synthetic_rays
+
+    gen = torch.Generator().manual_seed(777)
+    o, d, t, _ = synthetic_rays(RAYS_PER_RANK * world, gen)
+    img = torch.rand(RAYS_PER_RANK * world, 3, generator=gen)
+    packed = torch.cat([o, d, t, img], dim=-1).to(dev)
+    keep = [p.detach().clone() for p in model.parameters()]
+    was_graph, trainer.use_cuda_graph = trainer.use_cuda_graph, False
+    sl = slice(rank * RAYS_PER_RANK, (rank + 1) * RAYS_PER_RANK)
+    with _global_rand(rank, world, 99, dev):
+        rb, batch = _bundle(packed[sl].contiguous())
+        trainer(rb, batch)
+    g_dp = {k: (b.flat / world).clone() for k, b in trainer.buckets.items()}
+    with torch.no_grad():
+        for p, q in zip(model.parameters(), keep):
+            p.copy_(q)
+    saved = (trainer.reduce_grads, trainer.optimizers.optimizer_step_all)
+    trainer.reduce_grads, trainer.optimizers.optimizer_step_all = False, (lambda grad_scale=1.0: None)
+    try:
+        with _global_rand(-1, world, 99, dev):
+            rb, batch = _bundle(packed)
+            trainer(rb, batch)
+    finally:
+        trainer.reduce_grads, trainer.optimizers.optimizer_step_all = saved
+    rel = {}
+    for k, b in trainer.buckets.items():
+        ref = b.flat
+        rel[k] = float((g_dp[k] - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    with torch.no_grad():
+        for p, q in zip(model.parameters(), keep):
+            p.copy_(q)
+    trainer.use_cuda_graph = was_graph
+    worst = torch.tensor([max(rel.values())], dtype=torch.float64, device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    ok = bool(identical and float(worst) < 1e-5)
+    return {"ok": ok, "params_bit_identical_across_ranks": identical, "grad_vs_single_rank_on_concatenated_batch_rel": float(worst),
+            "tolerance": 1e-5, "per_group": rel}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one training leg (cfg2 or cfg3)
+# ----------------------------------------------------------------------------------------------------------------------
+def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=False):
     import torch.distributed as dist
 
     from soccernerfs_b200 import _lib
-    from soccernerfs_b200.data.scene_box import SceneBox
-    from soccernerfs_b200.data.synthetic import perturb_time_planes, synthetic_rays
     from soccernerfs_b200.engine.trainer import TrainStep
-    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
 
-    _lib.load()
-    torch.manual_seed(42 + rank)
-    _, _, _, aabb = synthetic_rays(4, torch.Generator().manual_seed(0))
-    model = KPlanesModelConfig().setup(scene_box=SceneBox(aabb=aabb), num_train_data=19 * 25).to(dev)
-    perturb_time_planes(model)
+    model = build_model(name, dev)
+    torch.manual_seed(42 + rank)  # per-rank sampling randomness (NS/scripts/train.py:84)
     model.proposal_sampler.update_sched = lambda step: 0  # proposal networks evaluated with grad + trained EVERY step
     prop_overlap = {"auto": None, "on": True, "off": False}[args.prop_overlap]
     trainer = TrainStep(model, data_parallel=args.allreduce != "none", use_cuda_graph=not args.eager,
@@ -165,27 +362,32 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(step_fn):
+    def timed_region(step_fn, steps=None, warmup=None):
+        steps = args.steps if steps is None else steps
+        warmup = args.warmup if warmup is None else warmup
         # the CUDA graph is captured on the third visit of a sampler mode: never let that fall into the timed steps,
         # whatever --warmup says (the contract asks for W >= 3 anyway)
-        for i in range(max(0, 3 - args.warmup)):
+        for i in range(max(0, 3 - warmup)):
             step_fn(i % n_steps)
-        for i in range(args.warmup):
-            step_fn(i)
+        for i in range(warmup):
+            step_fn(i % n_steps)
         barrier()
-        launches0 = _lib.launch_count()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for i in range(args.steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
             flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
             ev[i][0].record()
-            step_fn(args.warmup + i)
+            step_fn((warmup + i) % n_steps)
             ev[i][1].record()
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in ev)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        per_rank = [ms]
         if world > 1:
+            allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(allms, t)
+            per_rank = [float(x) for x in allms]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), _lib.launch_count() - launches0
+        return float(t.item()), sorted(p / steps for p in per_rank)
 
     # ---- arm 1: inputs resident in HBM --------------------------------------------------------------
     def step_resident(i):
@@ -195,16 +397,15 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms, launches = timed_region(step_resident)
+    total_ms, rank_ms = timed_region(step_resident)
     clocks = sampler.stop() if rank == 0 else None
-    if not args.eager:
-        # a graph replay launches the kernels captured once; count them from one eager iteration of the same step
-        trainer.use_cuda_graph = False
-        k0 = _lib.launch_count()
-        step_resident(0)
-        torch.cuda.synchronize()
-        launches = (_lib.launch_count() - k0) * args.steps
-        trainer.use_cuda_graph = True
+    # a graph replay launches the kernels captured once; count them from one eager iteration of the same step
+    was_graph, trainer.use_cuda_graph = trainer.use_cuda_graph, False
+    k0 = _lib.launch_count()
+    step_resident(0)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - k0
+    trainer.use_cuda_graph = was_graph
 
     # ---- arm 2: end to end through the public API with host buffers -----------------------------------
     # every step: pinned host batch -> device (H2D), the step, and the step's loss -> pinned host memory (D2H).  Both
@@ -219,86 +420,217 @@ def run_ours(args):
         loss_host[i].copy_(out["loss"], non_blocking=True)  # D2H read of the step's result
 
     e2e_ms, _ = timed_region(step_e2e)
-    last_loss = [float(loss_host[n_steps - 1])]
     if not bool(torch.isfinite(loss_host).all()) or float(loss_host[args.warmup:].abs().min()) == 0.0:
         raise RuntimeError("end-to-end arm: a step's loss did not arrive on the host")
+    last_loss = float(loss_host[n_steps - 1])
 
-    # ---- per-kernel durations for the roofline: CUDA events around the field kernels on their launch stream,
-    #      measured live in eager mode (events cannot be timed inside a graph replay), L2 flushed per step ------
+    leg = {}
+    # ---- N>1: a longer run (the 20-step region is too short to separate ranks' skew from the collective) --------
+    if world > 1 and not args.no_long_run:
+        long_ms, long_rank = timed_region(step_resident, steps=100, warmup=3)
+        leg["long_run"] = {"steps": 100, "ms_per_step": long_ms / 100, "rank_ms_per_step": {"min": long_rank[0], "median": long_rank[len(long_rank) // 2], "max": long_rank[-1]},
+                           "value": RAYS_PER_RANK * world * 100 / (long_ms * 1e-3)}
+
+    # ---- the reference's own proposal schedule after warm-up: proposal networks updated every 6th step ----------
+    if not args.no_ref_schedule:
+        model.proposal_sampler.update_sched = lambda step: 5
+        model.proposal_sampler._step = max(model.proposal_sampler._step, 10)
+        sched_steps = max(args.steps, 18)
+        sched_ms, _ = timed_region(step_resident, steps=sched_steps, warmup=18)
+        leg["reference_schedule"] = {"value": RAYS_PER_RANK * world * sched_steps / (sched_ms * 1e-3), "ms_per_step": sched_ms / sched_steps,
+                                     "steps": sched_steps, "proposal_update": "every 6th step (update_sched = 5: NS/models/kplanes.py:254-259 after proposal_warmup)"}
+        model.proposal_sampler.update_sched = lambda step: 0
+
+    if world > 1 and trainer.reduce_grads:
+        leg["dp_check"] = dp_check(trainer, model, rank, world, dev)
+
+    # ---- per-kernel durations: CUDA events around the C-ABI calls on their launch stream, measured live in eager mode
+    #      (events cannot be timed inside a graph replay), L2 flushed per step, each kernel alone on the GPU ------
     trainer.use_cuda_graph = False
-    # each kernel alone on the GPU for this pass: the side-stream branches would otherwise run next to (and inflate the
-    # duration of) the kernel being timed
     trainer.overlap, trainer._prop_stream, model.proposal_sampler.side_stream = False, None, None
-    _lib.TIMED.update(list(ALGO_BYTES.keys()) + ["kp_decoder_fwd_fused", "kp_color_net_bwd", "kp_sigma_net_bwd", "kp_adam_multi",
-                                                 "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd"])
+    _lib.TIMED.update(FIELD_KERNELS + OTHER_TIMED)
     _lib.EVENTS.clear()
-    for i in range(args.steps):
+    k_steps = min(args.steps, 10)
+    for i in range(k_steps):
         flush.zero_()
         step_resident(i % n_steps)
     torch.cuda.synchronize()
     _lib.TIMED.clear()
     kernel_ms = {}
-    for name, a, b in _lib.EVENTS:
-        kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
+    for kname, a, b in _lib.EVENTS:
+        kernel_ms.setdefault(kname, []).append(a.elapsed_time(b))
+    _lib.EVENTS.clear()
+    scales = per_scale_probe(model, flush, peaks, probe) if rank == 0 else None
 
-    if rank != 0:
-        return
-    rays = RAYS_PER_RANK * world * args.steps
-    peaks, peak_kind = _peaks()
-    # dominant kernel = largest total time among the field gather/scatter kernels
+    cfg = model.config
+    n_field = RAYS_PER_RANK * cfg.num_nerf_samples_per_ray
+    n_prop = RAYS_PER_RANK * sum(cfg.num_proposal_samples_per_ray)
+    k_scales = len(cfg.multiscale_res)
+    step_bytes = {"kp_hexplane_fwd": n_field * k_scales * 6 * 4 * cfg.feature_dim * 4,
+                  "kp_hexplane_bwd": 2 * n_field * k_scales * 6 * 4 * cfg.feature_dim * 4,
+                  "kp_density_field_fwd": n_prop * 6 * 4 * 8 * 4, "kp_density_field_bwd": 2 * n_prop * 6 * 4 * 8 * 4}
     per_kernel = {}
-    for name, ms_list in kernel_ms.items():
-        calls_per_step = len(ms_list) / args.steps
-        per_kernel[name] = {"ms_per_step": sum(ms_list) / args.steps, "launches_per_step": calls_per_step}
-    # algorithmic bandwidth of every field kernel (bytes per STEP of that entry point / its time per step): the gather and
-    # the scatter are one launch each; the proposal fields are two launches per step (256 + 128 samples per ray)
-    step_bytes = {"kp_hexplane_fwd": ALGO_BYTES["kp_hexplane_fwd"], "kp_hexplane_bwd": ALGO_BYTES["kp_hexplane_bwd"],
-                  "kp_density_field_fwd": ALGO_BYTES["kp_density_field_fwd"] * (256 + 128),
-                  "kp_density_field_bwd": ALGO_BYTES["kp_density_field_bwd"] * (256 + 128)}
-    for name, nbytes in step_bytes.items():
-        if name in per_kernel and per_kernel[name]["ms_per_step"] > 0:
-            gbs = nbytes / (per_kernel[name]["ms_per_step"] * 1e-3) / 1e9
-            per_kernel[name].update({"algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
+    for kname, ms_list in kernel_ms.items():
+        per_kernel[kname] = {"ms_per_step": sum(ms_list) / k_steps, "launches_per_step": len(ms_list) / k_steps}
+    for kname, nbytes in step_bytes.items():
+        if kname in per_kernel and per_kernel[kname]["ms_per_step"] > 0:
+            per_kernel[kname]["algorithmic_gbs"] = nbytes / (per_kernel[kname]["ms_per_step"] * 1e-3) / 1e9
+    rays = RAYS_PER_RANK * world * args.steps
+    leg.update({
+        "workload": WORKLOADS[name]["label"], "value": rays / (total_ms * 1e-3), "unit": "rays/s", "ms_per_step": total_ms / args.steps,
+        "rank_ms_per_step": {"min": rank_ms[0], "median": rank_ms[len(rank_ms) // 2], "max": rank_ms[-1]},
+        "e2e": {"value": rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": host[0].numel() * 4 * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss},
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "kernels": per_kernel, "per_scale": scales, "clocks": clocks,
+        "plane_mb": sum(p.numel() for g in model.field.grids for p in g) * 4 / 2**20,
+        "grad_allreduce": ("none (single rank)" if world == 1 else
+                           f"{trainer.allreduce_backend} ({args.allreduce})" if args.allreduce != "none" else "disabled"),
+    })
+    if rank == 0 and scales:
+        leg["roofline"] = _roofline(name, per_kernel, step_bytes, scales, peaks, probe)
+    trainer.close()
+    if keep_model:
+        return leg, model
+    del trainer, model, resident, flush
+    torch.cuda.empty_cache()
+    return leg, None
+
+
+def _roofline(name, per_kernel, step_bytes, scales, peaks, probe):
+    """Dominant field kernel (the larger of gather / scatter).  The level of the hierarchy that bounds it differs per
+    scale, so the bound is derived from the working sets: `peak` is the blended rate at which the kernel's
+    algorithmic bytes could be served if every scale ran at the measured rate of the level its working set lives in
+    (kp_line_probe for L2-resident scales, MEASURED_PEAKS hbm_gbs for HBM-resident ones, a hit-ratio mix in between)."""
     top = max(("kp_hexplane_fwd", "kp_hexplane_bwd"), key=lambda k: per_kernel.get(k, {"ms_per_step": 0})["ms_per_step"])
-    top_ms = per_kernel[top]["ms_per_step"] / per_kernel[top]["launches_per_step"]
-    achieved = ALGO_BYTES[top] / (top_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    tag, l2key = ("gather", "l2_gather_gbs") if top == "kp_hexplane_fwd" else ("scatter", "l2_red_gbs")
+    top_ms = per_kernel[top]["ms_per_step"] / max(1.0, per_kernel[top]["launches_per_step"])
+    algo = step_bytes[top]
+    t_floor, t_hbm_part = 0.0, 0.0
+    per_scale_bytes = algo / len(scales)
+    for row in scales:
+        ws = row[tag]["working_set_mb"] * 2**20
+        hit = min(1.0, 0.75 * L2_BYTES / ws)
+        t_l2 = per_scale_bytes * hit / (probe[l2key] * 1e9)
+        t_hbm = per_scale_bytes * (1.0 - hit) / (peaks["hbm_gbs"] * 1e9)
+        t_floor += t_l2 + t_hbm
+        t_hbm_part += t_hbm
+    achieved = algo / (top_ms * 1e-3) / 1e9
+    blended_peak = algo / t_floor / 1e9
+    traffic, tsrc = None, None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic_r2.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(top)
-    line = {
-        "metric": "train rays/sec (fwd+bwd+optimizer)",
-        "value": rays / (total_ms * 1e-3),
-        "unit": "rays/s",
-        "n_gpus": world,
-        "steps": args.steps,
-        "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch_rays": RAYS_PER_RANK * world, "parallelism": f"ray-sharded dp{world}",
-                   "proposal_update": "every step", "l2": "flushed between timed iterations (160 MB write)",
-                   "launch": "eager" if args.eager else "whole step replayed from a CUDA graph",
-                   "grad_allreduce": ("none (single rank)" if world == 1 else
-                                      f"{trainer.allreduce_backend} ({args.allreduce})" if args.allreduce != "none" else "disabled")},
-        "e2e": {"value": rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": host[0].numel() * 4 * world,
-                "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss[0]},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                     "algorithmic_bytes_per_launch": ALGO_BYTES[top], "kernel_ms": top_ms,
-                     "note": "planes of cfg2 (152 MB) are mostly L2-resident: algorithmic bytes are served by L2, so frac is "
-                             "relative to the measured HBM copy peak, see DESIGN.md"},
-        "kernels": per_kernel,
-        "clocks": clocks,
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(rays_per_step=RAYS_PER_RANK, steps=2, warmup=1)
-    print(json.dumps(line), flush=True)
+            tj = json.load(f)
+        traffic, tsrc = tj.get(name, {}).get(top), tj.get("source")
+    finest = scales[-1][tag]
+    return {"bound": "hbm" if t_hbm_part > 0.5 * t_floor else "l2", "kernel": top, "achieved": achieved, "peak": blended_peak,
+            "unit": "GB/s", "frac": achieved / blended_peak, "traffic": traffic, "traffic_source": tsrc,
+            "peak_source": "per-scale blend of kp_line_probe L2 rate (%s = %.0f GB/s, measured in this run) and MEASURED_PEAKS.json hbm_gbs "
+                           "(%.0f GB/s) by working-set size; L2 hit ratio = min(1, 0.75*126 MB / working set)" % (l2key, probe[l2key], peaks["hbm_gbs"]),
+            "algorithmic_bytes_per_launch": algo, "kernel_ms": top_ms,
+            "finest_scale": {"scale": scales[-1]["scale"], "kernel_ms": finest["ms"], "achieved": finest["algorithmic_gbs"],
+                             "level": finest["level"], "frac_of_hbm_peak": finest["frac_of_hbm_peak"],
+                             "frac_of_l2_probe": finest["frac_of_l2_probe"]}}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# eval leg: BASELINE configs[4]
+# ----------------------------------------------------------------------------------------------------------------------
+def eval_leg(model, frames, warmup, rank, world, dev):
+    """Full-frame inference with the 32x field: 1920x1080 rays per frame in chunks of 32768, rays generated on the device
+    and finished tiles copied to pinned host frames (engine/frame_renderer.py).  One "step" = one frame; with N ranks the
+    tiles are shared round-robin (no collective)."""
+    import torch.distributed as dist
+
+    from soccernerfs_b200 import _lib
+    from soccernerfs_b200.cameras.cameras import Cameras
+    from soccernerfs_b200.engine.frame_renderer import FrameRenderer
+
+    model.eval()
+    h, w = 1080, 1920
+    n_frames = warmup + frames
+    ang = torch.linspace(0.0, 1.0, n_frames) * 0.6  # a short camera path on the broadcast ring, looking at the origin
+    pos = torch.stack([torch.cos(ang), torch.sin(ang), torch.full_like(ang, 0.35)], dim=-1)
+    fwd = -pos / pos.norm(dim=-1, keepdim=True)
+    right = torch.cross(fwd, torch.tensor([0.0, 0.0, 1.0]).expand_as(fwd), dim=-1)
+    right = right / right.norm(dim=-1, keepdim=True)
+    up = torch.cross(right, fwd, dim=-1)
+    c2w = torch.cat([torch.stack([right, up, -fwd], dim=-1), pos[..., None]], dim=-1)  # camera looks along -z
+    cams = Cameras(c2w.to(dev), 1600.0, 1600.0, w / 2, h / 2, w, h, times=torch.linspace(0, 1, n_frames).to(dev))
+    renderer = FrameRenderer(model, cams, rank=rank, world=world)
+    for i in range(warmup):
+        renderer.render(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    k0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    checksum = 0.0
+    for i in range(frames):
+        frame = renderer.render(warmup + i)  # ends with the copy stream's synchronize: the frame is on the host
+        checksum += float(frame["rgb"][::97, ::89].sum())
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - k0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    rays = h * w * frames
+    return {"metric": "eval rays/sec (full-frame inference, device ray generation -> pinned host frames)",
+            "value": rays / (ms * 1e-3), "unit": "rays/s", "frames": frames, "warmup": warmup, "ms_per_frame": ms / frames,
+            "scaling": "strong", "workload": "kplanes-32x(cfg3 field) full-frame inference (BASELINE config 5): 1920x1080 rays/frame, "
+                                             "chunk 32768, 256/128/64 samples, rays generated on the device",
+            "parallelism": f"tile-sharded x{world} (round-robin chunks, no collective)",
+            "d2h_bytes_per_frame": h * w * (3 + 1 + 1) * 4, "checksum": checksum, "gpu_launches": launches}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# baselines
+# ----------------------------------------------------------------------------------------------------------------------
+def gpu_torch_baseline(dev, steps=5, warmup=3, rays=RAYS_PER_RANK):
+    """The reference's own step restated as plain torch ops (grid_sample / searchsorted / cumsum / autograd /
+    torch.optim.Adam; the oracle, which follows the reference line by line) with every tensor on THIS GPU: what the
+    reference's code path costs on a B200 without our kernels (and with an fp32 torch MLP for tiny-cuda-nn).  A reported
+    baseline, never a product path."""
+    from oracle import kplanes_oracle as ko
+
+    gen = torch.Generator().manual_seed(42)
+    origins, directions, times, aabb = ko.synthetic_rays(rays, gen)
+    mp = ko.make_model_params("cfg2", gen, aabb)
+    image = torch.rand(rays, 3, generator=gen)
+    rands = [ko.make_rand(rays, mp, gen) for _ in range(steps + warmup)]
+    for t in mp.tensors():
+        t.data = t.data.to(dev)
+    for obj in [mp.field] + list(mp.proposals):
+        obj.aabb = obj.aabb.to(dev)
+    origins, directions, times, image = (x.to(dev) for x in (origins, directions, times, image))
+    rands = [{k: v.to(dev) for k, v in r.items()} for r in rands]
+    opt = torch.optim.Adam(mp.tensors(), lr=1e-2, eps=1e-12)
+    torch.set_default_device(dev)  # the oracle's factory calls (linspace / zeros / ones) then land on the GPU too
+    try:
+        def step(i):
+            opt.zero_grad(set_to_none=True)
+            ko.train_step(mp, origins, directions, times, image, rands[i])
+            opt.step()
+
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.set_default_device("cpu")
+    return {"value": rays / ms * 1e3, "unit": "rays/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "what": "reference step as plain torch CUDA ops on the same B200 (cfg2, fp32, eager; torch grid_sample / searchsorted / "
+                    "cumsum / autograd / torch.optim.Adam; fp32 torch MLP in place of tiny-cuda-nn)"}
 
 
 def cpu_baseline(rays_per_step: int, steps: int, warmup: int):
@@ -327,80 +659,64 @@ def cpu_baseline(rays_per_step: int, steps: int, warmup: int):
                       f"{cores} threads", "ms_per_step": 1e3 * t_total / steps}
 
 
-def run_eval(args):
-    """Extra (not the headline metric): BASELINE config 5 -- full-frame inference with the 32x field of config 3,
-    1920x1080 rays per frame in chunks of 32768, rays generated on the device and finished tiles copied to pinned host
-    frames (engine/frame_renderer.py).  One "step" = one frame; with N ranks the tiles are shared round-robin."""
-    rank, world, local = _dist_setup(args.gpus)
+def _config(world: int, extra=None):
+    cfg = {"workload": WORKLOAD, "global_batch_rays": RAYS_PER_RANK * world, "parallelism": f"ray-sharded dp{world}",
+           "proposal_update": "every step", "l2": "flushed between timed iterations (160 MB write)"}
+    cfg.update(extra or {})
+    return cfg
+
+
+def run_ours(args):
+    rank, world, local = _dist_setup()
     if not torch.cuda.is_available():
-        raise RuntimeError("bench.py --mode eval needs a CUDA device")
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: the product path has no CPU fallback")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    import torch.distributed as dist
-
     from soccernerfs_b200 import _lib
-    from soccernerfs_b200.cameras.cameras import Cameras
-    from soccernerfs_b200.data.scene_box import SceneBox
-    from soccernerfs_b200.data.synthetic import perturb_time_planes, synthetic_rays
-    from soccernerfs_b200.engine.frame_renderer import FrameRenderer
-    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
 
-    torch.manual_seed(7)  # the same field on every rank
-    _, _, _, aabb = synthetic_rays(4, torch.Generator().manual_seed(0))
-    cfg = KPlanesModelConfig(
-        spacetime_resolution=(64, 64, 64, 100), multiscale_res=(1, 2, 4, 8, 16, 32), sigma_net_hidden_dim=128,
-        disable_viewing_dependent=True, num_nerf_samples_per_ray=64, num_proposal_samples_per_ray=(256, 128),
-        proposal_net_args_list=[{"feature_dim": 8, "resolution": [128, 128, 128, 100]},
-                                {"feature_dim": 8, "resolution": [256, 256, 256, 100]}], eval_num_rays_per_chunk=32768)
-    model = cfg.setup(scene_box=SceneBox(aabb=aabb), num_train_data=19 * 25).to(dev)
-    perturb_time_planes(model)
-    model.eval()
-    h, w = 1080, 1920
-    n_frames = args.warmup + args.steps
-    ang = torch.linspace(0.0, 1.0, n_frames) * 0.6  # a short camera path on the broadcast ring, looking at the origin
-    pos = torch.stack([torch.cos(ang), torch.sin(ang), torch.full_like(ang, 0.35)], dim=-1)
-    fwd = -pos / pos.norm(dim=-1, keepdim=True)
-    right = torch.cross(fwd, torch.tensor([0.0, 0.0, 1.0]).expand_as(fwd), dim=-1)
-    right = right / right.norm(dim=-1, keepdim=True)
-    up = torch.cross(right, fwd, dim=-1)
-    c2w = torch.cat([torch.stack([right, up, -fwd], dim=-1), pos[..., None]], dim=-1)  # camera looks along -z
-    cams = Cameras(c2w.to(dev), 1600.0, 1600.0, w / 2, h / 2, w, h, times=torch.linspace(0, 1, n_frames).to(dev))
-    renderer = FrameRenderer(model, cams, rank=rank, world=world)
-    for i in range(args.warmup):
-        renderer.render(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    k0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    checksum = 0.0
-    for i in range(args.steps):
-        frame = renderer.render(args.warmup + i)  # ends with the copy stream's synchronize: the frame is on the host
-        checksum += float(frame["rgb"][::97, ::89].sum())
-    e1.record()
-    torch.cuda.synchronize()
-    launches = _lib.launch_count() - k0
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    _lib.load()
+    peaks, peak_kind = _peaks()
+    legs = set(args.legs.split(","))
+    probe = line_probe_peaks(dev) if rank == 0 else None
+    cfg2, _ = train_leg("cfg2", args, rank, world, local, dev, peaks, probe)
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "train rays/sec (fwd+bwd+optimizer)", "value": cfg2["value"], "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cfg2["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(world, {"launch": "eager" if args.eager else "whole step replayed from a CUDA graph",
+                                      "grad_allreduce": cfg2["grad_allreduce"]}),
+            "e2e": cfg2["e2e"], "gpu_launches": cfg2["gpu_launches"], "roofline": cfg2.get("roofline"), "kernels": cfg2["kernels"],
+            "per_scale": cfg2["per_scale"], "rank_ms_per_step": cfg2["rank_ms_per_step"], "clocks": cfg2["clocks"],
+            "l2_peaks": probe, "hbm_peak": {"gbs": peaks["hbm_gbs"], "source": peak_kind},
+        }
+        for k in ("long_run", "reference_schedule", "dp_check"):
+            if k in cfg2:
+                line[k] = cfg2[k]
+    if "cfg3" in legs:
+        cfg3, model3 = train_leg("cfg3", args, rank, world, local, dev, peaks, probe, keep_model="eval" in legs)
+        if rank == 0:
+            cfg3.pop("clocks", None)
+            line["cfg3"] = cfg3
+        if model3 is not None:
+            ev = eval_leg(model3, frames=args.eval_frames, warmup=1, rank=rank, world=world, dev=dev)
+            if rank == 0:
+                line["eval"] = ev
+            del model3
+            torch.cuda.empty_cache()
     if rank != 0:
         return
-    ms = float(t.item())
-    rays = h * w * args.steps
-    out_bytes = h * w * (3 + 1 + 1) * 4
-    print(json.dumps({
-        "metric": "eval rays/sec (full-frame inference, device ray generation -> pinned host frames)",
-        "value": rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "kplanes-32x(cfg3 field) full-frame inference (BASELINE config 5): 1920x1080 rays/frame, chunk "
-                               "32768, 256/128/64 samples, rays generated on the device", "frames": args.steps,
-                   "parallelism": f"tile-sharded x{world} (round-robin chunks, no collective)", "l2": "inputs larger than L2 (2.3 GB of planes)"},
-        "e2e": {"value": rays / (ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": out_bytes,
-                "checksum": checksum},
-        "gpu_launches": launches,
-    }))
+    if world == 1 and "torch" in legs:
+        line["gpu_torch_baseline"] = gpu_torch_baseline(dev)
+        line["gpu_torch_baseline"]["speedup_of_value"] = line["value"] / line["gpu_torch_baseline"]["value"]
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(rays_per_step=RAYS_PER_RANK, steps=2, warmup=1)
+    for leg in (line, line.get("cfg3") or {}):
+        dp = leg.get("dp_check")
+        if dp is not None and not dp["ok"]:
+            raise RuntimeError(f"data-parallel check failed: {dp}")
+    print(json.dumps(line), flush=True)
 
 
 def run_reference(args):
@@ -409,6 +725,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     # The full 4096-ray step (about 2.3 s on 16 host cores: the plane regularisers and Adam stream all parameters every
     # step, so a smaller ray sample would under-state the CPU path's rays/s).  Only if the requested run would exceed
     # ~5 minutes is the number of timed steps bounded; the step itself is never shrunk.
@@ -430,8 +747,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{steps} full steps of {rays} rays timed (of {args.steps} requested)"},
-        "cpu_baseline": {**res, "sample": f"{steps} steps of {rays} rays after {warmup} warm-up"},
+        "config": _config(world),
+        "cpu_baseline": {**res, "sample": f"{steps} steps of {rays} rays after {warmup} warm-up (of {args.steps} requested)"},
         "e2e": {"value": res["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -443,9 +760,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--mode", choices=["train", "eval"], default="train",
-                    help="train: the headline metric (default); eval: full-frame inference, BASELINE config 5 (extra line)")
+    ap.add_argument("--legs", default="cfg2,cfg3,eval,torch",
+                    help="comma list of the extra objects of the JSON line: cfg3 (32x training leg), eval (full-frame inference, "
+                         "needs cfg3), torch (reference step as torch CUDA ops, N=1).  cfg2 (the headline) always runs.")
+    ap.add_argument("--eval-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-long-run", action="store_true")
+    ap.add_argument("--no-ref-schedule", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="keep the regulariser / proposal branches on the main stream")
     ap.add_argument("--prop-overlap", choices=["auto", "on", "off"], default="auto",
                     help="proposal-network backward on a side stream (auto: on for 1 GPU, off under data parallelism)")
@@ -458,10 +779,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        if args.mode == "eval":
-            run_eval(args)
-        else:
-            run_ours(args)
+        run_ours(args)
         if int(os.environ.get("WORLD_SIZE", "1")) > 1:
             # CUDA graphs that captured NCCL work keep the communicator busy at interpreter shutdown: finish all GPU
             # work, then leave without the (hanging) communicator teardown.

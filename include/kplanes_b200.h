@@ -262,6 +262,14 @@ int kp_peer_allreduce(void* const* arenas /* HOST array [world]: arenas[rank] = 
                       int world, int64_t begin /* float index, multiple of 4 */, int64_t count, int blocks /* <=0: 64 */,
                       void* stream);
 
+/* ---- (d) measurement: memory-hierarchy probe with the field kernels' own access pattern (8 lanes = one 128-byte
+ *      line of a pseudo-random texel; mode 0: 16-byte read-only loads, mode 1: red.global.add.v4.f32).  One launch
+ *      touches blocks*32*iters lines of buf[0 : n_lines*32] (iters rounded up to a multiple of 8); bench.py times it
+ *      over an L2-resident and an HBM-resident buffer to get the achievable L2 / random-line HBM rates the gather
+ *      and the scatter are reported against. ---- */
+int kp_line_probe(float* buf, int64_t n_lines, int mode, int blocks, int iters, uint32_t seed, float* sink /* device [1] */,
+                  int64_t* lines_touched /* host, or NULL */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,8 +56,8 @@ __device__ __forceinline__ void st_peer_v4(float* p, float4 v) {
   asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// All ranks' block `blockIdx.x` meet here.  A bounded spin (a few seconds) turns a lost peer into an error word
-// instead of a hung GPU.
+// All ranks' block `blockIdx.x` meet here.  A bounded spin (tens of seconds) turns a lost peer into an error word plus
+// a trapped kernel instead of a hung GPU -- never into a reduction over incomplete buckets.
 __device__ __forceinline__ void peer_barrier(const PeerArgs& a, int phase, uint32_t flag) {
   __threadfence_system();
   __syncthreads();
@@ -67,9 +67,13 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, int phase, uint3
     const uint32_t* mine = a.sig[a.rank] + slot + threadIdx.x;
     unsigned long long spins = 0;
     while ((int32_t)(ld_acquire_sys(mine) - flag) < 0) {
-      if (++spins > (1ull << 25)) {
+      if (++spins > (1ull << 27)) {
+        // A peer never arrived.  Reducing anyway would sum buckets that are still being written and let the replicas
+        // diverge silently, so: record it (kp_peer_error / TrainStep.check_collective_health) and abort the kernel --
+        // the host sees a launch failure at its next synchronisation, like a failed NCCL collective.
         a.sig[a.rank][kSigError] = 1u + (uint32_t)phase;
-        break;
+        __threadfence_system();
+        __trap();
       }
     }
   }

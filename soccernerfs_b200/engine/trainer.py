@@ -51,6 +51,15 @@ class TrainStep:
         self.arena, self.allreduce_backend = None, "nccl"
         self.reduce_grads = data_parallel and self.world > 1
         self.fuse_grad_accumulation = fuse_grad_accumulation
+        if self.reduce_grads:
+            # replicas start from rank 0's parameters, as DistributedDataParallel does for the reference
+            # (NS/pipelines/base_pipeline.py:244-246)
+            import torch.distributed as dist
+
+            with torch.no_grad():
+                for p in model.parameters():
+                    if p.numel():
+                        dist.broadcast(p.data, 0)
         if self.reduce_grads or fuse_grad_accumulation:
             # one flat gradient bucket per parameter group: the field bucket is complete as soon as the field's scatter
             # kernel has run, so its all-reduce overlaps the back-propagation through the proposal networks
@@ -79,7 +88,10 @@ class TrainStep:
             # high priority: when the scatter finishes, the all-reduce kernel's blocks are placed BEFORE the proposal
             # backward's persistent blocks fill every SM (they would otherwise keep it out until they retire)
             self._comm_stream = torch.cuda.Stream(priority=-1) if on_cuda else None
-        if self.reduce_grads and allreduce_mode != "after-backward":
+        # The overlap hook marks "every gradient of the field bucket is in the stream" right after the scatter kernel was
+        # enqueued.  That is only true with the gradient sinks (the kernels write the bucket themselves); without them
+        # autograd's AccumulateGrad adds the returned gradients AFTER the hook, so the bucket is reduced after the backward.
+        if self.reduce_grads and allreduce_mode != "after-backward" and fuse_grad_accumulation:
             hook = self._start_field_allreduce
             grids = getattr(model.field, "grids", None)
             if allreduce_mode == "overlap-per-scale" and self.overlap and grids is not None and len(grids) > 1:
@@ -93,6 +105,7 @@ class TrainStep:
         self._prop_stream = torch.cuda.Stream() if (self.overlap and overlap_proposal_backward) else None
         model.proposal_sampler.side_stream = self._prop_stream
         self.use_cuda_graph = use_cuda_graph
+        self.health_check_every = 1000  # steps between polls of the peer all-reduce's error word (a device sync)
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self._graph_out: Dict[bool, Dict[str, torch.Tensor]] = {}
         self._seen: Dict[bool, int] = {}
@@ -210,6 +223,33 @@ class TrainStep:
 
     _scale_scattered.per_scale = True
 
+    def check_collective_health(self) -> None:
+        """Raise if a cross-GPU barrier of the peer all-reduce ever timed out (the kernel traps in that case; this is the
+        host-side report for the ranks that were not the one that trapped).  Synchronises the device."""
+        if self.arena is not None and self.arena.error_word() != 0:
+            raise RuntimeError("peer-memory all-reduce: a cross-GPU barrier timed out -- a rank fell behind by more than the "
+                               "spin limit; gradients of this step are not trustworthy")
+
+    def close(self) -> None:
+        """Detach the gradient sinks from the parameters (another trainer / a plain torch optimizer may own the model
+        next), report a failed collective, and release the peer arena."""
+        for b in self.buckets.values():
+            b.detach_sinks()
+        if getattr(self.model.field, "_kp_post_backward", None) is not None:
+            self.model.field._kp_post_backward = None
+        self.model.proposal_sampler.side_stream = None
+        self._graphs.clear()
+        self._graph_out.clear()
+        if self.arena is not None:
+            try:
+                self.check_collective_health()
+            finally:
+                for p in self.model.parameters():
+                    p.grad = None
+                self.buckets = {}
+                self.arena.close()
+                self.arena = None
+
     def _run_callbacks(self, location: int) -> None:
         for cb in self.callbacks:
             cb.run_callback_at_location(self.step, location)
@@ -224,14 +264,19 @@ class TrainStep:
         self.optimizers.scheduler_step_all(self.step)
         self._run_callbacks(TrainingCallbackLocation.AFTER_TRAIN_ITERATION)
         self.step += 1
+        if self.arena is not None and self.step % self.health_check_every == 0:
+            self.check_collective_health()
         return out
 
     # ---- checkpoint / resume (NS/engine/trainer.py:326-380) ----------------------------------------------------
     def state_dict(self) -> Dict:
-        """``{"step", "pipeline", "optimizers", "schedulers"}``: the layout ``Trainer.save_checkpoint`` writes
-        (trainer.py:362-373), model tensors under the pipeline's ``_model.`` prefix with OUR parameter names
-        (``utils.checkpoint.to_reference_state_dict`` converts the MLPs to tcnn's flat layout if a reference-format file
-        is wanted).  Optimizer step counts are taken from the trainer: a replayed graph advances them on the device."""
+        """``{"step", "pipeline", "optimizers", "schedulers", "scalers"}``: the top-level keys ``Trainer.save_checkpoint``
+        writes (trainer.py:362-373), model tensors under the pipeline's ``_model.`` prefix with OUR parameter names.  This
+        is this repo's resume format, NOT a reference checkpoint: ``step`` counts completed steps (the reference stores the
+        last step index and resumes at step+1, trainer.py:343), the MLP keys are ours, and the reference's strict
+        ``load_pipeline`` wants keys this path does not have (lpips, datamanager).  ``utils.checkpoint`` converts model
+        tensors and optimizer state in both directions.  Optimizer step counts are taken from the trainer: a replayed
+        graph advances them on the device."""
         optimizers = {}
         for name, opt in self.optimizers.optimizers.items():
             sd = opt.state_dict()
@@ -244,6 +289,7 @@ class TrainStep:
             "pipeline": {f"_model.{k}": v for k, v in self.model.state_dict().items()},
             "optimizers": optimizers,
             "schedulers": {name: sch.state_dict() for name, sch in self.optimizers.schedulers.items()},
+            "scalers": {},  # fp32 path: no GradScaler state (the reference stores its GradScaler's here)
         }
 
     def load_state_dict(self, state: Dict) -> None:
@@ -260,6 +306,7 @@ class TrainStep:
             if name in state.get("schedulers", {}):
                 sch.load_state_dict(state["schedulers"][name])
         self.step = int(state["step"])
+        self.model.proposal_sampler._step = self.step  # the first `updated` decision after a resume uses the right step
         self._graphs.clear()
         self._graph_out.clear()
         self._seen.clear()
@@ -312,8 +359,21 @@ class TrainStep:
         self._step_t += 1
         return out
 
+    def _graphable(self, ray_bundle: RayBundle, batch) -> bool:
+        """The captured step has static buffers for origins / directions / times / image only.  Anything else a batch or
+        bundle may carry and the model would USE (depth supervision, masks, per-ray metadata, camera indices for an
+        appearance embedding, real pixel areas, a static scene without times) runs through the eager iteration instead
+        of being dropped silently."""
+        if set(batch.keys()) - {"image"}:
+            return False
+        if ray_bundle.times is None or ray_bundle.metadata:
+            return False
+        return True
+
     def _graphed(self, ray_bundle: RayBundle, batch) -> Dict[str, torch.Tensor]:
         sampler = self.model.proposal_sampler
+        if not self._graphable(ray_bundle, batch):
+            return self._iteration(ray_bundle, batch)
         if self._static is None:
             self._setup_graph_state(ray_bundle, batch)
         updated = bool(sampler._steps_since_update > sampler.update_sched(sampler._step) or sampler._step < 10)

@@ -202,6 +202,7 @@ class KPlanesField(Field, _AabbHostMixin):
         ms = self._planes()
         if points.D != (4 if len(ms[0]) == 6 else 3):
             raise RuntimeError("dynamic K-Planes field needs ray_samples.times")
+        self._last_points = points  # (bench.py's per-scale probe re-runs the gather / scatter on the step's own samples)
         feats = ops.hexplane_features(ms, points, self.concat_features_across_scales,
                                       _use_mask(len(ms[0]), self.freeze_time_planes),
                                       post_backward=getattr(self, "_kp_post_backward", None))
@@ -251,6 +252,7 @@ class KPlanesField(Field, _AabbHostMixin):
         ms = self._planes()
         if points.D != (4 if len(ms[0]) == 6 else 3):
             raise RuntimeError("dynamic K-Planes field needs ray_samples.times")
+        self._last_points = points  # (bench.py's per-scale probe re-runs the gather / scatter on the step's own samples)
         feats = ops.hexplane_features(ms, points, self.concat_features_across_scales,
                                       _use_mask(len(ms[0]), self.freeze_time_planes),
                                       post_backward=getattr(self, "_kp_post_backward", None))

@@ -39,10 +39,19 @@ class AABBBoxCollider(SceneCollider):
     def __init__(self, scene_box: SceneBox, near_plane: float = 0.0, **kwargs) -> None:
         super().__init__(**kwargs)
         self.scene_box, self.near_plane = scene_box, near_plane
-        self._box = _as_six_floats(scene_box.aabb)  # host copy: a launch never waits on a device read
+        self._box_key, self._box = None, None
+
+    def _host_box(self):
+        """Host copy of the scene box (a launch never waits on a device read), refreshed when ``scene_box.aabb`` is
+        replaced or modified in place (e.g. a render crop)."""
+        aabb = self.scene_box.aabb
+        key = (aabb.data_ptr(), aabb._version)
+        if key != self._box_key:
+            self._box_key, self._box = key, _as_six_floats(aabb)
+        return self._box
 
     def _intersect_with_aabb(self, rays_o: torch.Tensor, rays_d: torch.Tensor, aabb: Optional[torch.Tensor] = None):
-        box = self._box if aabb is None else _as_six_floats(aabb)
+        box = self._host_box() if aabb is None else _as_six_floats(aabb)
         return ops.aabb_intersect(rays_o, rays_d, box, self.near_plane if self.training else 0)
 
     def set_nears_and_fars(self, ray_bundle: RayBundle) -> RayBundle:

@@ -61,6 +61,11 @@ def grad_sink(p: torch.Tensor) -> Optional[torch.Tensor]:
     sink = getattr(p, "_kp_grad_sink", None)  # (called inside Function.forward, where grad mode is always off)
     if sink is None or not p.requires_grad:
         return None
+    # a sink is only honoured while it still IS the parameter's .grad: after someone else's zero_grad(set_to_none=True)
+    # or a new .grad tensor (another trainer / a plain torch optimizer took over the model) autograd gets real gradients
+    g = p.grad
+    if g is None or g.data_ptr() != sink.data_ptr():
+        return None
     return sink
 
 
