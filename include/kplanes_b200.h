@@ -189,6 +189,13 @@ int kp_plane_reg_multi_fwd(const float* const* planes, const int32_t* hwc, const
 int kp_plane_reg_multi_bwd(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms,
                            int P, const float* coef_dev /* [P,4] */, int accumulate, void* stream);
 
+/* Values AND gradients of the regularisers in ONE sweep per plane (the training step's form): sums as above (may be
+ * NULL), and grads[p] (may be NULL) = or += sum_i coef_dev[p,i] * d(sums[p,i])/d(plane).  With accumulate = 0 the sweep
+ * also stands in for the gradient buffer's memset: every element of grads[p] is written. */
+int kp_plane_reg_fused(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms, int P,
+                       const float* coef_dev /* [P,4] */, int accumulate, double* sums /* [P,4] accumulated, or NULL */,
+                       void* stream);
+
 /* Adam over a list of dense fp32 tensors in one launch.  hyper_dev (optional, DEVICE float[3] = lr/bias_corr1,
  * 1/sqrt(bias_corr2), grad_scale) overrides the host-computed scalars so a captured CUDA graph can be replayed
  * with fresh per-step values. */

@@ -38,11 +38,32 @@ class GradBucket:
             self.views.append(v)
             off += p.numel()
 
-    def attach_zeroed(self, sink: bool = False) -> None:
+    def _zero_spans(self, skip) -> List[Tuple[int, int]]:
+        """Element ranges of the bucket NOT covered by the parameters in ``skip`` (ids), merged."""
+        key = frozenset(skip)
+        cache = self.__dict__.setdefault("_span_cache", {})
+        if key not in cache:
+            spans, off = [], 0
+            for p in self.params:
+                if id(p) not in key:
+                    if spans and spans[-1][1] == off:
+                        spans[-1] = (spans[-1][0], off + p.numel())
+                    else:
+                        spans.append((off, off + p.numel()))
+                off += p.numel()
+            cache[key] = spans
+        return cache[key]
+
+    def attach_zeroed(self, sink: bool = False, skip=None) -> None:
         """Zero the bucket and install the views as ``.grad`` so autograd accumulates in place.  ``sink=True``
         additionally publishes every view as the parameter's gradient sink (ops.grad_sink): the backward kernels
-        then accumulate straight into the bucket."""
-        self.flat.zero_()
+        then accumulate straight into the bucket.  ``skip``: ids of parameters whose gradient is about to be WRITTEN in
+        full by a kernel (the fused regulariser sweep) -- their part of the bucket is not memset."""
+        if skip:
+            for a, b in self._zero_spans(skip):
+                self.flat[a:b].zero_()
+        else:
+            self.flat.zero_()
         for p, v in zip(self.params, self.views):
             p.grad = v
             if sink:

@@ -10,6 +10,7 @@ step counter, so a replay needs nothing from the host but the batch.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import sys
 from typing import Dict, Optional
@@ -28,7 +29,7 @@ class TrainStep:
                  warm_up_end: int = 512, data_parallel: bool = False, use_cuda_graph: bool = False,
                  fuse_grad_accumulation: bool = True, overlap_branches: bool = True,
                  overlap_proposal_backward: Optional[bool] = None, allreduce_mode: str = "overlap",
-                 allreduce_backend: str = "peer") -> None:
+                 allreduce_backend: str = "peer", fuse_regularizers: bool = True) -> None:
         """``overlap_branches``: run the two branches of the step that do not depend on the main field's backward on
         their own CUDA streams (same arithmetic, same results): the plane regularisers (forward AND backward depend on
         the planes only) during the forward pass, and the back-propagation through the proposal networks (depends on
@@ -79,6 +80,11 @@ class TrainStep:
             self.buckets = {name: GradBucket(ps, arena=arena) for name, ps in model.get_param_groups().items()}
         on_cuda = next(model.parameters()).is_cuda
         self.overlap = bool(overlap_branches and fuse_grad_accumulation and on_cuda)
+        # fused regulariser sweep (values + gradient written into the sinks, no memset of the planes): ids of the planes
+        # it writes in full, or None when not applicable
+        self._reg_written = None
+        if fuse_grad_accumulation and self.buckets and on_cuda and model.fused_regularizers_applicable() and fuse_regularizers:
+            self._reg_written = frozenset(id(p) for p in model.regularized_planes() if p.requires_grad)
         self._field_ready = None
         self._scale_ready: Dict[int, "torch.cuda.Event"] = {}
         self._comm_stream = None
@@ -116,7 +122,7 @@ class TrainStep:
         model = self.model
         if self.buckets:
             for b in self.buckets.values():
-                b.attach_zeroed(sink=self.fuse_grad_accumulation)
+                b.attach_zeroed(sink=self.fuse_grad_accumulation, skip=self._reg_written)
         else:
             self.optimizers.zero_grad_all()
         self._field_ready = None
@@ -126,20 +132,27 @@ class TrainStep:
         self._reg_mark = ops.PLANE_REG_BACKWARDS
         regs = None
         main = torch.cuda.current_stream() if self.overlap else None
-        if self.overlap:
-            # regulariser branch: values and gradients (straight into the zeroed sinks) on its own stream, under the
-            # forward pass; joined before the main backward, whose scatter kernels update the same gradients atomically
-            self._reg_stream.wait_stream(main)
-            with torch.cuda.stream(self._reg_stream):
-                regs = model.regularizer_losses()
+        if self.overlap or self._reg_written:
+            # regulariser branch: values and gradients (straight into the sinks) on its own stream, under the forward
+            # pass; joined before the main backward, whose scatter kernels update the same gradients atomically
+            if self.overlap:
+                self._reg_stream.wait_stream(main)
+            with torch.cuda.stream(self._reg_stream) if self.overlap else contextlib.nullcontext():
+                if self._reg_written:
+                    # one sweep per plane: loss values + gradient WRITTEN into the bucket (which was not memset there)
+                    regs = model.regularizers_into_grads(accumulate=False)
+                else:
+                    regs = model.regularizer_losses()
+                    if regs:
+                        regs = scale_dict(regs, model.config.loss_coefficients)
+                        sum(regs.values()).backward()
+                        regs = {k: v.detach() for k, v in regs.items()}
                 if regs:
-                    regs = scale_dict(regs, model.config.loss_coefficients)
-                    sum(regs.values()).backward()
-                    regs = {k: v.detach() for k, v in regs.items()}
                     regs_vec = torch.stack(list(regs.values()))  # the loss head adds these into the total
         outputs = model(ray_bundle)
-        if self.overlap:
-            main.wait_stream(self._reg_stream)
+        if self.overlap or self._reg_written:
+            if self.overlap:
+                main.wait_stream(self._reg_stream)
             if regs:
                 outputs["_scaled_regularizers_vec"] = regs_vec
         metrics = model.get_metrics_dict(outputs, batch)
@@ -148,7 +161,7 @@ class TrainStep:
         if loss is None:
             loss = sum(loss_dict.values())
         loss.backward()
-        if self._prop_stream is not None:
+        if self._prop_stream is not None and getattr(model.proposal_sampler, "side_stream_used", False):
             main.wait_stream(self._prop_stream)  # proposal-network backward ran on the sampler's side stream
         grad_scale = 1.0
         if self.reduce_grads:

@@ -195,6 +195,52 @@ def depth_loss(weights, ray_samples, termination_depth, predicted_depth, sigma, 
     raise NotImplementedError("Provided depth loss type not implemented.")
 
 
+REG_NAMES = ["space_tv_loss", "time_smoothness_loss", "sparse_transients_loss",
+             "space_tv_proposal_loss", "time_smoothness_proposal_loss", "sparse_transients_proposal_loss"]
+
+
+def regularizer_plan(ms_grids_nerf, ms_grids_prop):
+    """(planes, terms, norm rows [P][6][4]) of the six plane regularisers of NS/models/kplanes.py:430-446: which sums of
+    which plane enter which loss, with the reference's mean normalisers (losses.py:356-452)."""
+    planes, terms, rows = [], [], []
+    for group, ms in enumerate((_flatten_grids(ms_grids_nerf), _flatten_grids(ms_grids_prop))):
+        for grids in ms:
+            dynamic = len(grids) == 6
+            spatial = [0, 1, 3] if dynamic else [0, 1, 2]
+            for gid, g in enumerate(grids):
+                _, c, h, w = g.shape
+                row = [[0.0] * 4 for _ in range(6)]
+                if gid in spatial:
+                    t = T_H | T_W
+                    row[3 * group + 0][0] = 1.0 / (c * (h - 1) * w)
+                    row[3 * group + 0][1] = 1.0 / (c * h * (w - 1))
+                else:
+                    t = T_W | T_SMOOTH | T_L1
+                    row[3 * group + 0][1] = 1.0 / (c * h * (w - 1))
+                    row[3 * group + 1][2] = 1.0 / (c * (h - 2) * w)
+                    row[3 * group + 2][3] = 1.0 / g.numel()
+                planes.append(g)
+                terms.append(t)
+                rows.append(row)
+    return planes, terms, rows
+
+
+def kplanes_regularizers_into_grads(ms_grids_nerf, ms_grids_prop, loss_coefficients, accumulate: bool = False):
+    """The training step's form of ``kplanes_regularizers``: ONE sweep per plane that returns the six SCALED loss values
+    (detached; keyed like the reference's loss dict) and writes (``accumulate=False``: the sweep replaces the gradient
+    buffer's memset) or adds the scaled regularisers' gradient into every plane's gradient sink (``ops.grad_sink``).
+    Planes without a sink (frozen / no bucket attached) only contribute their value."""
+    planes, terms, rows = regularizer_plan(ms_grids_nerf, ms_grids_prop)
+    dev = planes[0].device
+    scale = [float(loss_coefficients.get(n, 0.0)) for n in REG_NAMES]
+    norm = _const(rows, dev)  # [P,6,4]
+    coef = _const([[sum(scale[j] * r[j][i] for j in range(6)) for i in range(4)] for r in rows], dev)  # [P,4]
+    targets = [ops.grad_sink(p) for p in planes]
+    sums = ops.plane_reg_fused(planes, terms, coef, targets, accumulate)
+    vals = (sums.float()[:, None, :] * norm).sum(dim=(0, 2)) * _const(scale, dev)  # [6], already scaled
+    return {name: vals[i] for i, name in enumerate(REG_NAMES) if name in loss_coefficients}, targets
+
+
 def kplanes_regularizers(ms_grids_nerf, ms_grids_prop):
     """All six plane regularisers of ``KPlanesModel.get_loss_dict`` (NS/models/kplanes.py:430-446) from ONE pass over
     the planes: identical values to ``space_tv_loss`` / ``time_smoothness_loss`` / ``sparse_transients_loss`` called on

@@ -233,6 +233,7 @@ class ProposalNetworkSampler(Sampler):
         n = self.num_proposal_network_iterations
         weights, ray_samples = None, None
         updated = self._steps_since_update > self.update_sched(self._step) or self._step < 10
+        self.side_stream_used = False  # whether this call put work on ``side_stream`` (the trainer joins it only then)
         for i_level in range(n + 1):
             is_prop = i_level < n
             num_samples = self.num_proposal_samples_per_ray[i_level] if is_prop else self.num_nerf_samples_per_ray
@@ -248,6 +249,7 @@ class ProposalNetworkSampler(Sampler):
                 if side is not None:
                     main = torch.cuda.current_stream()
                     side.wait_stream(main)
+                    self.side_stream_used = True
                 with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
                     with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
                         fast = _density_field_of(density_fns[i_level])

@@ -339,6 +339,28 @@ class KPlanesModel(Model):
                 out["time_smoothness_proposal_loss"] = time_smoothness_loss(ms_grids_prop)
         return out
 
+    def fused_regularizers_applicable(self) -> bool:
+        """Whether ``regularizers_into_grads`` covers this configuration (dynamic scene, all six regulariser keys)."""
+        loss_coef = self.config.loss_coefficients
+        dynamic = len(self.config.spacetime_resolution) > 3 and not self.config.freeze_time_planes
+        reg_keys = ("space_tv_loss", "space_tv_proposal_loss", "sparse_transients_loss", "sparse_transients_proposal_loss",
+                    "time_smoothness_loss", "time_smoothness_proposal_loss")
+        return dynamic and all(k in loss_coef for k in reg_keys) and not self.config.freeze_space_planes
+
+    def regularized_planes(self) -> List[Parameter]:
+        return [p for g in self.field.grids for p in g] + [p for net in self.proposal_networks for p in net.grids]
+
+    def regularizers_into_grads(self, accumulate: bool = False) -> Dict[str, torch.Tensor]:
+        """Training-step form of ``regularizer_losses`` (kplanes.py:430-446): the six SCALED, detached loss values from
+        ONE sweep per plane that also writes (or adds) the scaled regularisers' gradient into every plane's gradient
+        sink -- no autograd graph, no separate backward sweep, and no memset of the planes' part of the bucket."""
+        from ..model_components.losses import kplanes_regularizers_into_grads
+
+        vals, _ = kplanes_regularizers_into_grads(self.field.grids, [p.grids for p in self.proposal_networks],
+                                                  self.config.loss_coefficients, accumulate=accumulate)
+        ops.PLANE_REG_BACKWARDS += 1
+        return vals
+
     def get_loss_dict(self, outputs, batch, metrics_dict=None, regularizers=None) -> Dict[str, torch.Tensor]:
         """kplanes.py:410-452.  ``regularizers`` (extension): already SCALED regulariser terms computed (and possibly
         already back-propagated) by the caller; they are merged instead of being evaluated here."""

@@ -798,6 +798,24 @@ class _PlaneReg(torch.autograd.Function):
         return (None, *grads)
 
 
+def plane_reg_fused(planes: Sequence[torch.Tensor], terms: Sequence[int], coef_dev: torch.Tensor,
+                    targets: Sequence[Optional[torch.Tensor]], accumulate: bool, want_sums: bool = True) -> Optional[torch.Tensor]:
+    """One sweep per plane: -> sums [P,4] (float64) of the regulariser terms, and targets[p] (channel-last gradient
+    buffers, entries may be None) = / += sum_i coef_dev[p,i] * d(sums[p,i])/d(plane).  No autograd: this is the training
+    step's form, where the gradient goes straight into the parameter's bucket (and, with accumulate=False, replaces the
+    bucket's memset)."""
+    planes = [as_channel_last(p.detach()) for p in planes]
+    for p, t in zip(planes, targets):
+        ptr_cl(p)
+        if t is not None and (t.shape != p.shape or t.stride() != p.stride() or t.dtype != torch.float32):
+            raise RuntimeError("plane_reg_fused: a gradient target must have the plane's channel-last layout")
+    sums = torch.zeros((len(planes), 4), dtype=torch.float64, device=planes[0].device) if want_sums else None
+    hwc, tm = _reg_tables(planes, terms)
+    call("kp_plane_reg_fused", _plane_ptrs(planes), _plane_ptrs(list(targets)), hwc, tm, len(planes), ptr(f32c(coef_dev)),
+         int(accumulate), ptr(sums), stream_ptr())
+    return sums
+
+
 def ptr_cl(p: torch.Tensor) -> c_void_p:
     if not p.is_cuda:
         raise RuntimeError("soccernerfs_b200 kernels need CUDA tensors (there is no CPU path)")

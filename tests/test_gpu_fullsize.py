@@ -10,7 +10,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _step_vs_oracle(cfg, n_rays, seed):
+def _step_vs_oracle(cfg, n_rays, seed, max_fragile=0.5):
+    """Whole training step at the BASELINE config's own batch size vs the CPU oracle, at the stated bar: outputs, every
+    loss term and EVERY gradient tensor within 1e-4 (max |a-b| / max |b|).
+
+    The step is piecewise smooth: a ray with a ReLU pre-activation, an interlevel bin-edge lookup or a median index
+    within fp32 rounding of a tie can take the other branch in two correct fp32 implementations (an O(1) change of that
+    ray's gradient that no precision fixes).  oracle/fragility.py identifies those rays from fp64 pre-activations of the
+    ORACLE forward (windows = small multiples of the fp32 error bound, independent of the CUDA path); they are removed
+    from the batch of BOTH implementations -- rays are independent through the whole step -- and the bar is asserted,
+    unmasked, on everything that is left.  The flagged fraction is printed and bounded."""
+    from oracle.fragility import fragile_rays
     from tests.helpers import build_model, train_step_cuda
 
     gen = torch.Generator().manual_seed(seed)
@@ -18,37 +28,37 @@ def _step_vs_oracle(cfg, n_rays, seed):
     mp = ko.make_model_params(cfg, gen, aabb)
     image = torch.rand(n_rays, 3, generator=gen)
     rand = ko.make_rand(n_rays, mp, gen)
+    fragile, stats = fragile_rays(mp, origins, directions, times, rand, anneal=0.6)
+    keep = ~fragile
+    print(f"[{cfg}] {n_rays} rays, fragile fractions {stats}; comparing {int(keep.sum())} rays at 1e-4")
+    assert stats["any"] < max_fragile, stats
+    origins, directions, times, image = origins[keep], directions[keep], times[keep], image[keep]
+    rand = {k: v[keep] for k, v in rand.items()}
     model = build_model(cfg, mp, aabb, DEV)
     out, ld, grads = train_step_cuda(model, origins, directions, times, image, rand, 0.6, DEV)
     ref_out, ref_ld, ref_grads = ko.train_step(mp, origins, directions, times, image, rand, anneal=0.6)
-    for k in ("rgb", "accumulation", "depth"):
-        assert rel_err(out[k].cpu(), ref_out[k].detach()) < 3e-4, k
+    errs = {}
+    for k in ("rgb", "accumulation", "depth", "prop_depth_0", "prop_depth_1"):
+        errs[k] = rel_err(out[k].cpu(), ref_out[k].detach())
     for k, v in ld.items():
-        assert rel_err(v.detach().cpu(), ref_ld[k].detach()) < 3e-4, k
-    # Gradients: the decoders are ReLU networks, so a sample whose hidden pre-activation lies within fp32 rounding of 0
-    # (|pre| ~ 1e-7; a handful out of ~10^4 samples x 192 units) takes the other branch on the GPU than on the CPU and
-    # its whole feature gradient changes -- an O(1) difference on the few texels only that sample touches (verified:
-    # every deviating sample has min|pre| < 2e-6, tests/tools/debug_cfg2b.py).  The bar is therefore: almost all entries
-    # within 1e-4 of the tensor's max, the median relative error of the significant entries below 1e-4, and the tensor
-    # as a whole within 2e-2 in relative L2 (one flipped sample of a 128-ray batch already moves the L2 norm by ~5e-3).
+        errs["loss:" + k] = rel_err(v.detach().cpu(), ref_ld[k].detach())
     for i, (a, b) in enumerate(zip(grads, ref_grads)):
-        a, b = a.cpu().double(), b.double()
-        mx = b.abs().max().clamp_min(1e-30)
-        frac_bad = float(((a - b).abs() > 1e-4 * mx).double().mean())
-        l2 = float((a - b).norm() / b.norm().clamp_min(1e-30))
-        big = b.abs() > 0.01 * mx
-        median_rel = float(((a - b).abs()[big] / b.abs()[big]).median()) if bool(big.any()) else 0.0
-        assert median_rel < 1e-4 or b.numel() < 100000, (i, median_rel)  # the typical plane-gradient entry meets the fp32 bar
-        assert l2 < 2e-2 and (frac_bad < 2e-2 or b.numel() < 100000), (i, frac_bad, l2)
+        errs[f"grad:{i}"] = rel_err(a.cpu(), b)
+    bad = {k: v for k, v in errs.items() if not v < 1e-4}
+    print(f"[{cfg}] max rel err outputs/losses {max(v for k, v in errs.items() if not k.startswith('grad')):.2e}, "
+          f"gradients {max(v for k, v in errs.items() if k.startswith('grad')):.2e}")
+    assert not bad, bad
 
 
-def test_cfg2_step_vs_oracle():
-    _step_vs_oracle("cfg2", 256, 11)
+def test_cfg2_step_vs_oracle_full_batch():
+    """BASELINE configs[1] at its own size: 4096 rays, 256/128/48 samples, 152 MB of planes."""
+    _step_vs_oracle("cfg2", 4096, 11)
 
 
-def test_cfg3_32x_step_vs_oracle():
-    """K-Planes 32x: six scales up to 2048^2 planes (2.3 GB), sigma hidden 128 (SIMT first layer), no view dependence."""
-    _step_vs_oracle("cfg3", 128, 12)
+def test_cfg3_32x_step_vs_oracle_full_batch():
+    """BASELINE configs[2] at its own size: K-Planes 32x, six scales up to 2048^2 planes (2.3 GB), sigma hidden 128,
+    no view dependence, 4096 rays x 64 samples."""
+    _step_vs_oracle("cfg3", 4096, 12)
 
 
 def test_weights_partition_of_unity_full_size():

@@ -112,17 +112,12 @@ def test_samplers_bit_exact_vs_reference_fixture():
         w = g[f"{mode}_weights"][..., 0].to(DEV)
         sb1, eb1, inds, cdf = ops.pdf_resample(w, sb, nears, fars, 24, ur, want_inds=True, want_cdf=True)
         ref_cdf = ko.pdf_cdf(g[f"{mode}_weights"][..., 0])
-        # searchsorted indices: bit-exact whenever the kernel's cdf equals the CPU cdf (it is computed with a double
-        # prefix sum like torch's CPU cumsum; the row *sum* may differ in the last bit from torch's vectorised sum)
-        same_cdf = (cdf.cpu() == ref_cdf).all(dim=-1)
-        assert same_cdf.float().mean() > 0.9
-        assert torch.equal(inds.cpu()[same_cdf], g[f"{mode}_inds1"][same_cdf])
-        assert torch.equal(sb1.cpu()[same_cdf], g[f"{mode}_bins1"][same_cdf])
-        assert torch.equal(eb1.cpu()[same_cdf][:, :-1], g[f"{mode}_starts1"][same_cdf])
-        # and every ray within fp32 rounding
-        assert (cdf.cpu() - ref_cdf).abs().max() < 5e-7
-        assert (sb1.cpu() - g[f"{mode}_bins1"]).abs().max() < 2e-6
-        assert (inds.cpu() != g[f"{mode}_inds1"]).float().mean() < 1e-3
+        # the stated bar: cdf, searchsorted indices, resampled bins and euclidean edges bit-identical on EVERY ray (the
+        # kernel reproduces torch's CPU row-sum order and its double-accumulated cumsum)
+        assert torch.equal(cdf.cpu(), ref_cdf)
+        assert torch.equal(inds.cpu(), g[f"{mode}_inds1"])
+        assert torch.equal(sb1.cpu(), g[f"{mode}_bins1"])
+        assert torch.equal(eb1.cpu()[:, :-1], g[f"{mode}_starts1"]) and torch.equal(eb1.cpu()[:, 1:], g[f"{mode}_ends1"])
 
 
 def test_pdf_search_bit_exact_given_cdf():
@@ -143,9 +138,8 @@ def test_pdf_search_bit_exact_given_cdf():
     ref_inds = torch.searchsorted(cdf, u, side="right")
     _, _, inds, kcdf = ops.pdf_resample(w.to(DEV), bins.to(DEV), nears.to(DEV), fars.to(DEV), s_out, rand.to(DEV),
                                         histogram_padding=0.25, want_inds=True, want_cdf=True)
-    same = (kcdf.cpu() == cdf).all(-1)
-    assert same.float().mean() > 0.95
-    assert torch.equal(inds.cpu()[same], ref_inds[same])
+    assert torch.equal(kcdf.cpu(), cdf)
+    assert torch.equal(inds.cpu(), ref_inds)
     del prev
 
 
@@ -365,6 +359,10 @@ def test_model_step_vs_reference_fixture():
     rand = {k[5:]: v for k, v in g.items() if k.startswith("rand_")}
     out, ld, grads = train_step_cuda(model, g["origins"], g["directions"], g["times"], g["image"], rand, float(g["anneal"]), DEV)
     # sampling: bins / indices
+    # sampling: level 0 is bit-exact; levels 1-2 resample UPSTREAM densities that differ from the CPU's in the last bit
+    # (expf, fused multiply-adds), so an index may differ where u is within an ulp of a cdf edge -- the resampled bin is a
+    # continuous function across that edge and must still agree to fp32 rounding
+    assert torch.equal(out["ray_samples_list"][0].spacing_starts[..., 0].cpu(), g["bins_0"][:, :-1])
     for lvl, key in ((0, "inds1"), (1, "inds2")):
         mism = (out["inds_list"][lvl].cpu() != g[key]).float().mean()
         assert mism < 2e-3, (lvl, float(mism))
@@ -372,14 +370,14 @@ def test_model_step_vs_reference_fixture():
         rs = out["ray_samples_list"][i]
         bins = torch.cat([rs.spacing_starts[..., 0], rs.spacing_ends[..., -1:, 0]], -1).cpu()
         assert (bins - g[f"bins_{i}"]).abs().max() < 5e-6, i
-        assert rel_err(out["weights_list"][i].cpu(), g[f"weights_{i}"]) < 2e-4, i
-    assert torch.equal(out["ray_samples_list"][0].spacing_starts[..., 0].cpu(), g["bins_0"][:, :-1])  # level 0 bit-exact
+        assert rel_err(out["weights_list"][i].cpu(), g[f"weights_{i}"]) < 1e-4, i
+    # the stated fp32 bar, 1e-4, on outputs, every loss term and every gradient tensor
     for k in ("rgb", "accumulation", "depth", "prop_depth_0", "prop_depth_1"):
-        assert rel_err(out[k].cpu(), g[k]) < 2e-4, k
+        assert rel_err(out[k].cpu(), g[k]) < 1e-4, k
     for k, v in ld.items():
-        assert rel_err(v.detach().cpu(), g["loss_" + k]) < 2e-4, k
+        assert rel_err(v.detach().cpu(), g["loss_" + k]) < 1e-4, k
     for i, gr in enumerate(grads):
-        assert rel_err(gr.cpu(), g[f"grad_{i}"]) < 5e-4, i
+        assert rel_err(gr.cpu(), g[f"grad_{i}"]) < 1e-4, i
 
 
 def test_fused_adam_matches_torch_adam():
@@ -715,9 +713,72 @@ def test_cfg4_piecewise_single_jitter_samplers_vs_reference_fixture():
         assert (rs0.frustums.starts[..., 0].cpu() == g[f"{mode}_starts0"]).float().mean() > 0.99
         assert (rs0.frustums.ends[..., 0].cpu() - g[f"{mode}_ends0"]).abs().max() < 1e-6
         bins1 = torch.cat([rs1.spacing_starts[..., 0], rs1.spacing_ends[..., -1:, 0]], -1).cpu()
-        assert (pdf.last_inds.cpu() != g[f"{mode}_inds1"]).float().mean() < 2e-3
-        assert (bins1 - g[f"{mode}_bins1"]).abs().max() < 2e-6
+        assert torch.equal(pdf.last_inds.cpu(), g[f"{mode}_inds1"])  # bit-exact indices and spacing bins on every ray
+        assert torch.equal(bins1, g[f"{mode}_bins1"])
         rel = (rs1.frustums.starts[..., 0].cpu() - g[f"{mode}_starts1"]).abs() / g[f"{mode}_starts1"].abs().clamp_min(1e-3)
         assert rel.max() < 2e-5  # the disparity branch amplifies a 1-ulp spacing difference near the far plane
         depth = DepthRenderer(method="expected")(weights=g[f"{mode}_w1"].to(DEV), ray_samples=rs1)
         assert rel_err(depth.cpu(), g[f"{mode}_depth_expected"]) < 1e-4
+
+
+def test_fused_regularizer_sweep_matches_autograd_path():
+    """kp_plane_reg_fused (one sweep: values + gradient written into the sinks) vs the two-sweep autograd path
+    (kp_plane_reg_multi_fwd/bwd): same six scaled loss values, same plane gradients; accumulate mode adds on top."""
+    from soccernerfs_b200.distributed import GradBucket
+    from soccernerfs_b200.models.kplanes import scale_dict
+    from tests.helpers import build_model
+    from tests.test_oracle_golden import load_tiny_model
+
+    g = load_golden("model_tiny")
+    model = build_model("tiny", load_tiny_model(g), g["aabb"], DEV)
+    planes = model.regularized_planes()
+    ref = scale_dict(model.regularizer_losses(), model.config.loss_coefficients)
+    sum(ref.values()).backward()
+    ref_grads = [p.grad.detach().clone() for p in planes]
+    for p in model.parameters():
+        p.grad = None
+    bucket = GradBucket([p for ps in model.get_param_groups().values() for p in ps])
+    bucket.attach_zeroed(sink=True, skip=frozenset(id(p) for p in planes))
+    bucket.flat.fill_(123.0)  # the sweep must overwrite every plane element (it replaces the memset)
+    vals = model.regularizers_into_grads(accumulate=False)
+    for k, v in ref.items():
+        assert rel_err(vals[k], v.detach()) < 1e-6, k
+    for p, r in zip(planes, ref_grads):
+        assert rel_err(p.grad, r) < 1e-6
+    model.regularizers_into_grads(accumulate=True)
+    for p, r in zip(planes, ref_grads):
+        assert rel_err(p.grad, 2 * r) < 1e-6
+
+
+def test_train_step_with_and_without_fused_regularizers():
+    """TrainStep(fuse_regularizers=True) (no memset of the planes' gradients, one regulariser sweep) follows the
+    two-sweep step: same losses over 6 steps, eagerly and from the graph."""
+    from soccernerfs_b200.engine.trainer import TrainStep
+    from tests.helpers import build_model, ray_bundle
+    from tests.test_oracle_golden import load_tiny_model
+
+    g = load_golden("model_tiny")
+    mp = load_tiny_model(g)
+    runs = {}
+    for mode in ("two-sweep", "fused", "fused-serial", "fused-graph"):
+        model = build_model("tiny", mp, g["aabb"], DEV)
+        model.config.background_color_train = "black"
+        model.proposal_sampler.initial_sampler.train_stratified = False
+        model.proposal_sampler.pdf_sampler.train_stratified = False
+        step = TrainStep(model, max_steps=100, warm_up_end=4, use_cuda_graph=mode.endswith("graph"),
+                         overlap_branches=mode != "fused-serial", fuse_regularizers=mode != "two-sweep")
+        assert (step._reg_written is not None) == (mode != "two-sweep")
+        losses = []
+        for i in range(6):
+            out = step(ray_bundle(g["origins"], g["directions"], g["times"], DEV), {"image": g["image"].to(DEV)})
+            losses.append((float(out["loss"]), float(out["space_tv_loss"]), float(out["time_smoothness_proposal_loss"])))
+        torch.cuda.synchronize()
+        runs[mode] = (losses, [p.detach().clone() for p in model.parameters()])
+        step.close()
+    for mode in ("fused", "fused-serial", "fused-graph"):
+        for a, b in zip(runs["two-sweep"][0], runs[mode][0]):
+            for x, y in zip(a, b):
+                assert abs(x - y) <= 2e-4 * abs(x) and x > 0, (mode, a, b)
+        for a, b in zip(runs["two-sweep"][1], runs[mode][1]):
+            if a.numel():
+                assert rel_err(b, a) < 1e-2
