@@ -193,16 +193,38 @@ class DensityFieldParams:
         return list(self.grids) + list(self.sigma_w)
 
 
-def init_planes(c: int, reso: Sequence[int], a: float, b: float, gen: torch.Generator) -> List[torch.Tensor]:
-    """NS/fields/kplanes_field.py:47-74 (time planes = 1, space planes U(a,b))."""
+def _band_limited(shape, coarse: int, draw) -> torch.Tensor:
+    """A [1,C,H,W] field whose spatial axes (those longer than ``coarse``) are the bilinear upsampling of a
+    ``coarse``-resolution random field: smooth at texel scale, like planes after TV-regularised training."""
+    h, w = shape[2], shape[3]
+    ch, cw = min(h, coarse), min(w, coarse)
+    low = draw([shape[0], shape[1], ch, cw])
+    if (ch, cw) == (h, w):
+        return low
+    return torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=True).contiguous()
+
+
+def init_planes(c: int, reso: Sequence[int], a: float, b: float, gen: torch.Generator, smooth_res: int = 0) -> List[torch.Tensor]:
+    """NS/fields/kplanes_field.py:47-74 (time planes = 1, space planes U(a,b)).  ``smooth_res`` > 0 (test inputs only):
+    the uniform noise is drawn at that resolution and bilinearly upsampled (see ``_band_limited``)."""
     planes = []
     for comb in itertools.combinations(range(len(reso)), 2):
         shape = [1, c] + [reso[cc] for cc in comb[::-1]]
         if len(reso) == 4 and 3 in comb:
             planes.append(torch.ones(shape))
+        elif smooth_res > 0:
+            planes.append(_band_limited(shape, smooth_res, lambda sh: torch.empty(sh).uniform_(a, b, generator=gen)))
         else:
             planes.append(torch.empty(shape).uniform_(a, b, generator=gen))
     return planes
+
+
+def _time_noise(shape, time_noise: float, gen: torch.Generator, smooth_res: int = 0) -> torch.Tensor:
+    """N(0, time_noise) on a space-time plane [1,C,T,R]; band-limited along the spatial axis when ``smooth_res`` > 0."""
+    if smooth_res > 0 and shape[3] > smooth_res:
+        low = time_noise * torch.randn([shape[0], shape[1], shape[2], smooth_res], generator=gen)
+        return torch.nn.functional.interpolate(low, size=(shape[2], shape[3]), mode="bilinear", align_corners=True).contiguous()
+    return time_noise * torch.randn(shape, generator=gen)
 
 
 def xavier(out_d: int, in_d: int, gen: torch.Generator) -> torch.Tensor:
@@ -212,15 +234,15 @@ def xavier(out_d: int, in_d: int, gen: torch.Generator) -> torch.Tensor:
 
 def make_field_params(
     aabb, spacetime_resolution, feat_dim, multiscale_res, gen, sigma_hidden=64, rgb_hidden=64,
-    view_dependent=True, time_noise=0.05, concat=True,
+    view_dependent=True, time_noise=0.05, concat=True, smooth_res=0,
 ) -> FieldParams:
     grids = []
     for m in multiscale_res:
         reso = [r * m for r in spacetime_resolution[:3]] + list(spacetime_resolution[3:])
-        planes = init_planes(feat_dim, reso, 0.1, 0.5, gen)
+        planes = init_planes(feat_dim, reso, 0.1, 0.5, gen, smooth_res)
         if len(reso) == 4 and time_noise > 0:
             for i in (2, 4, 5):  # N(0,0.05) noise on time planes so grads are non-degenerate
-                planes[i] = planes[i] + time_noise * torch.randn(planes[i].shape, generator=gen)
+                planes[i] = planes[i] + _time_noise(planes[i].shape, time_noise, gen, smooth_res)
         grids.append(planes)
     k = feat_dim * len(multiscale_res) if concat else feat_dim
     in_color = 15 + (16 if view_dependent else 0)
@@ -234,11 +256,11 @@ def make_field_params(
     )
 
 
-def make_density_params(aabb, resolution, feat_dim, gen, time_noise=0.05) -> DensityFieldParams:
-    planes = init_planes(feat_dim, resolution, 0.1, 0.15, gen)
+def make_density_params(aabb, resolution, feat_dim, gen, time_noise=0.05, smooth_res=0) -> DensityFieldParams:
+    planes = init_planes(feat_dim, resolution, 0.1, 0.15, gen, smooth_res)
     if len(resolution) == 4 and time_noise > 0:
         for i in (2, 4, 5):
-            planes[i] = planes[i] + time_noise * torch.randn(planes[i].shape, generator=gen)
+            planes[i] = planes[i] + _time_noise(planes[i].shape, time_noise, gen, smooth_res)
     return DensityFieldParams(aabb=aabb, grids=planes, sigma_w=[xavier(64, feat_dim, gen), xavier(1, 64, gen)])
 
 
@@ -716,8 +738,10 @@ def synthetic_rays(n: int, gen: torch.Generator, scene: str = "broadcast", n_fra
     return origins, directions, times, aabb
 
 
-def make_model_params(cfg: str, gen: torch.Generator, aabb: torch.Tensor) -> ModelParams:
-    """BASELINE.json configs resolved as in SURVEY.md 8 table."""
+def make_model_params(cfg: str, gen: torch.Generator, aabb: torch.Tensor, smooth_res: int = 0) -> ModelParams:
+    """BASELINE.json configs resolved as in SURVEY.md 8 table.  ``smooth_res`` > 0: band-limited planes (noise drawn
+    at that spatial resolution and bilinearly upsampled) instead of per-texel white noise -- the conditioning of a
+    TV-regularised, trained field rather than of the random initialisation."""
     if cfg == "cfg1":
         res, ms, hid, vd, nerf_s, prop_t = (64, 64, 64, 16), (1, 2, 4), 64, True, 48, 16
     elif cfg == "cfg2":
@@ -728,12 +752,13 @@ def make_model_params(cfg: str, gen: torch.Generator, aabb: torch.Tensor) -> Mod
         res, ms, hid, vd, nerf_s, prop_t = (16, 16, 16, 6), (1, 2), 64, True, 16, 6
     else:
         raise ValueError(cfg)
-    fieldp = make_field_params(aabb, res, 32, ms, gen, sigma_hidden=hid, view_dependent=vd)
+    fieldp = make_field_params(aabb, res, 32, ms, gen, sigma_hidden=hid, view_dependent=vd, smooth_res=smooth_res)
     if cfg == "tiny":
         props = [make_density_params(aabb, [24, 24, 24, prop_t], 8, gen), make_density_params(aabb, [32, 32, 32, prop_t], 8, gen)]
         nprop = (32, 24)
     else:
-        props = [make_density_params(aabb, [128, 128, 128, prop_t], 8, gen), make_density_params(aabb, [256, 256, 256, prop_t], 8, gen)]
+        props = [make_density_params(aabb, [128, 128, 128, prop_t], 8, gen, smooth_res=smooth_res),
+                 make_density_params(aabb, [256, 256, 256, prop_t], 8, gen, smooth_res=smooth_res)]
         nprop = (256, 128)
     return ModelParams(field=fieldp, proposals=props, num_proposal_samples=nprop, num_nerf_samples=nerf_s)
 

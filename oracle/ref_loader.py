@@ -198,3 +198,30 @@ def load_reference():
     )
     _REF = ns
     return ns
+
+
+def load_reference_model_module():
+    """``nerfstudio.models.kplanes`` of the reference (KPlanesModelConfig / KPlanesModel), for the drop-in boundary test.
+    On top of ``load_reference``'s stubs it needs import-only stand-ins for the evaluation metrics the module pulls in at
+    import time (torchmetrics PSNR / SSIM / LPIPS and the RetinaNet-based DynMetric, which downloads weights)."""
+    ns = load_reference()
+
+    class _Metric(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    def _stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+
+    _stub("torchmetrics", PeakSignalNoiseRatio=_Metric)
+    _stub("torchmetrics.functional", structural_similarity_index_measure=lambda *a, **k: None)
+    _stub("torchmetrics.image")
+    _stub("torchmetrics.image.lpip", LearnedPerceptualImagePatchSimilarity=_Metric)
+    _stub("nerfstudio.utils.dynmetric", DynMetric=_Metric)
+    from nerfstudio.models import kplanes as ref_kplanes
+
+    ns.models_kplanes = ref_kplanes
+    return ns

@@ -2,9 +2,9 @@
 
 ``KPlanesModelConfig`` has the reference's fields and defaults (NS/models/kplanes.py:67-177) and ``KPlanesModel``
 its surface: ``populate_modules`` :188-309, ``get_param_groups`` :311-316, ``get_training_callbacks`` :318-347,
-``get_outputs`` :349-388, ``get_metrics_dict`` :390-412, ``get_loss_dict`` :414-452.  Image-quality metrics
-(torchmetrics PSNR/SSIM/LPIPS, the RetinaNet-based DynMetric, colour maps) are evaluation tooling outside the hot
-path and are not rebuilt; ``psnr`` is computed inline.
+``get_outputs`` :349-388, ``get_metrics_dict`` :390-412, ``get_loss_dict`` :414-452,
+``get_image_metrics_and_images`` :454-515 (PSNR / SSIM restated in torch, colour maps in ``utils/colormaps.py``; the
+pretrained-network metrics LPIPS and DynMetric are used through the reference's objects when importable).
 """
 from __future__ import annotations
 
@@ -404,6 +404,43 @@ class KPlanesModel(Model):
         if self.training and regularizers is not None:
             loss_dict.update(regularizers)
         return loss_dict
+
+    def get_image_metrics_and_images(self, outputs: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor]
+                                     ) -> Tuple[Dict[str, float], Dict[str, torch.Tensor]]:
+        """Eval-image metrics and visualisations (kplanes.py:454-515; called by the pipeline every ``steps_per_eval_image``).
+        ``psnr`` / ``ssim`` always; ``lpips`` and the dynamic-region ``dpsnr/dssim/dlpips`` + ``bbox`` image when the
+        reference's pretrained-network metrics are importable (their keys are absent otherwise, never an exception)."""
+        from ..utils import colormaps, image_metrics
+
+        image = batch["image"].to(outputs["rgb"].device)
+        rgb = outputs["rgb"]
+        acc = colormaps.apply_colormap(outputs["accumulation"])
+        depth = colormaps.apply_depth_colormap(outputs["depth"], accumulation=outputs["accumulation"])
+        combined_rgb = torch.cat([image, rgb], dim=1)
+        # [H, W, C] -> [1, C, H, W] for the metrics
+        image_m = torch.moveaxis(image, -1, 0)[None, ...]
+        rgb_m = torch.moveaxis(rgb, -1, 0)[None, ...]
+        metrics_dict = {"psnr": float(image_metrics.psnr(image_m, rgb_m)), "ssim": float(image_metrics.ssim(image_m, rgb_m))}
+        images_dict = {"img": combined_rgb, "accumulation": acc, "depth": depth}
+        if not hasattr(self, "_lpips"):
+            self._lpips = image_metrics.optional_lpips(rgb.device)
+            self._dynmetric = image_metrics.optional_dynmetric(rgb.device)
+        if self._lpips is not None:
+            metrics_dict["lpips"] = float(self._lpips(image_m, rgb_m))
+        if self._dynmetric is not None:
+            bbox_img, dpsnr, dssim, dlpips = self._dynmetric(image_m, rgb_m)
+            metrics_dict.update({"dpsnr": float(dpsnr), "dssim": float(dssim), "dlpips": float(dlpips)})
+            images_dict["bbox"] = bbox_img
+        for i in range(self.config.num_proposal_iterations):
+            key = f"prop_depth_{i}"
+            images_dict[key] = colormaps.apply_depth_colormap(outputs[key], accumulation=outputs["accumulation"])
+        if "depth_image" in batch.keys():  # ground-truth depth beside the prediction (kplanes.py:503-510)
+            ground_truth_depth = batch["depth_image"].to(rgb.device)
+            if not self.config.is_euclidean_depth:
+                ground_truth_depth = ground_truth_depth * outputs["directions_norm"]
+            images_dict["depth"] = torch.cat([colormaps.apply_depth_colormap(ground_truth_depth), depth], dim=1)
+        images_dict["median_rgb"] = outputs["median_rgb"]
+        return metrics_dict, images_dict
 
     def _get_sigma(self):
         if not self.config.should_decay_sigma:

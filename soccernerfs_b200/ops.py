@@ -816,6 +816,15 @@ def plane_reg_fused(planes: Sequence[torch.Tensor], terms: Sequence[int], coef_d
     return sums
 
 
+def repack(src: torch.Tensor, dst: torch.Tensor, to_channel_last: bool) -> None:
+    """One plane [1,C,H,W]: NCHW-contiguous ``src`` -> channel-last ``dst`` (or the reverse), on the device."""
+    _, c, h, w = src.shape
+    if dst.shape != src.shape:
+        raise RuntimeError("repack: shape mismatch")
+    call("kp_repack_nchw_to_hwc" if to_channel_last else "kp_repack_hwc_to_nchw", c_void_p(src.data_ptr()),
+         c_void_p(dst.data_ptr()), c, h, w, stream_ptr())
+
+
 def ptr_cl(p: torch.Tensor) -> c_void_p:
     if not p.is_cuda:
         raise RuntimeError("soccernerfs_b200 kernels need CUDA tensors (there is no CPU path)")

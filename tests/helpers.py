@@ -78,8 +78,10 @@ def rand_list(rand: Dict[str, torch.Tensor]) -> List[torch.Tensor]:
     return [rand[k] for k in keys]
 
 
-def train_step_cuda(model: KPlanesModel, origins, directions, times, image, rand, anneal: float, device):
-    """collider + get_outputs + get_loss_dict + backward on the CUDA path.  Returns (outputs, loss_dict, grads)."""
+def train_step_cuda(model: KPlanesModel, origins, directions, times, image, rand, anneal: float, device, forced_bins=None):
+    """collider + get_outputs + get_loss_dict + backward on the CUDA path.  Returns (outputs, loss_dict, grads).
+    ``forced_bins``: per PDF level (spacing_bins, euclid_bins) [N,S+1] that REPLACE the bins the PDF kernel resampled
+    ("given the reference's samples": the rest of the step then sees bit-identical sample positions)."""
     model.train()
     model.proposal_sampler.set_anneal(anneal)
     model.proposal_sampler.pdf_sampler.record_inds = True
@@ -92,6 +94,11 @@ def train_step_cuda(model: KPlanesModel, origins, directions, times, image, rand
     def rec(*a, **k):
         r = orig(*a, **k)
         inds.append(model.proposal_sampler.pdf_sampler.last_inds)
+        if forced_bins is not None:
+            from soccernerfs_b200.model_components.ray_samplers import _to_ray_samples
+
+            sb, eb = (t.to(device).contiguous() for t in forced_bins[len(inds) - 1])
+            r = _to_ray_samples(a[0], sb, eb, a[1].spacing_to_euclidean_fn, None)
         return r
 
     model.proposal_sampler.pdf_sampler.generate_ray_samples = rec

@@ -782,3 +782,34 @@ def test_train_step_with_and_without_fused_regularizers():
         for a, b in zip(runs["two-sweep"][1], runs[mode][1]):
             if a.numel():
                 assert rel_err(b, a) < 1e-2
+
+
+def test_reference_checkpoint_loads_on_device():
+    """f3 on the GPU: a reference-layout pipeline state (planes NCHW-contiguous, flat tcnn params) is repacked into the
+    channel-last CUDA model through kp_repack_nchw_to_hwc, exported back through kp_repack_hwc_to_nchw, and the loaded
+    model renders exactly like the one that produced the checkpoint."""
+    from soccernerfs_b200.utils.checkpoint import load_reference_state_dict, to_reference_state_dict
+    from tests.helpers import build_model, ray_bundle
+    from tests.test_oracle_golden import load_tiny_model
+
+    g = load_golden("model_tiny")
+    mp = load_tiny_model(g)
+    a = build_model("tiny", mp, g["aabb"], DEV)
+    torch.manual_seed(5)
+    b = build_model("tiny", mp, g["aabb"], DEV)
+    with torch.no_grad():
+        for p in b.parameters():
+            if p.requires_grad:
+                p.add_(torch.randn_like(p))
+    sd = to_reference_state_dict(a)  # CUDA tensors, reference layouts
+    plane = sd["_model.field.grids.1.2"]
+    assert plane.is_cuda and plane.is_contiguous() and torch.equal(plane, a.field.grids[1][2].detach().contiguous())
+    unused = load_reference_state_dict(b, {"step": 3, "pipeline": sd})
+    assert unused == ["_model.field.direction_encoder.params"]
+    for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(pa, pb), na
+    a.eval(), b.eval()
+    with torch.no_grad():
+        oa = a(ray_bundle(g["origins"], g["directions"], g["times"], DEV))
+        ob = b(ray_bundle(g["origins"], g["directions"], g["times"], DEV))
+    assert torch.equal(oa["rgb"], ob["rgb"]) and torch.equal(oa["depth"], ob["depth"])

@@ -152,7 +152,9 @@ def test_reference_checkpoint_round_trip():
     assert "_model.field.sigma_net.params" in sd and "_model.proposal_networks.1.sigma_net.params" in sd
     sd["_datamanager.train_camera_optimizer.pose_adjustment"] = torch.zeros(3, 6)
     unused = load_reference_state_dict(b, {"step": 7, "pipeline": sd})
-    assert unused == ["_datamanager.train_camera_optimizer.pose_adjustment"]
+    # the parameter-less tcnn SH encoding and foreign (datamanager) keys are reported, not consumed
+    assert unused == ["_model.field.direction_encoder.params", "_datamanager.train_camera_optimizer.pose_adjustment"]
+    assert sd["_model.field.direction_encoder.params"].numel() == 0
     for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
         assert na == nb and torch.equal(pa, pb), na
     assert ops.is_channel_last(b.field.grids[0][0])  # storage layout untouched by the load
@@ -180,3 +182,42 @@ def test_cameras_reject_unsupported_and_out_of_range():
         cams.generate_rays_from_indices(torch.tensor([[0, 36, 0]]))
     with pytest.raises(NotImplementedError):
         cams.generate_rays(camera_indices=0, coords=torch.tensor([[0.25, 0.5]]))  # not a pixel centre
+
+
+def test_reference_optimizer_state_round_trip():
+    """utils/checkpoint.py: Adam moments in the reference's numbering / layouts (planes NCHW, flat tcnn vectors with the
+    SH sign flips) <-> our per-tensor FusedAdam state."""
+    from soccernerfs_b200.data.scene_box import SceneBox
+    from soccernerfs_b200.engine.optimizers import Optimizers
+    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
+    from soccernerfs_b200.utils.checkpoint import (TCNN_SH_SIGNS, _reference_group_layout, load_reference_optimizer_state,
+                                                   to_reference_optimizer_state, tcnn_layer_shapes)
+
+    cfg = KPlanesModelConfig(spacetime_resolution=(8, 8, 8, 4), multiscale_res=(1, 2), num_nerf_samples_per_ray=8,
+                             proposal_net_args_list=[{"feature_dim": 8, "resolution": [8, 8, 8, 4]}] * 2)
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    torch.manual_seed(0)
+    models = [cfg.setup(scene_box=SceneBox(aabb=aabb), num_train_data=1) for _ in range(2)]
+    opts = [Optimizers(m.get_param_groups()) for m in models]
+    for group, opt in opts[0].optimizers.items():  # a populated state on the first model
+        for p in models[0].get_param_groups()[group]:
+            if p.requires_grad:
+                opt.state[p] = {"step": 7, "exp_avg": torch.randn_like(p, memory_format=torch.preserve_format),
+                                "exp_avg_sq": torch.rand_like(p, memory_format=torch.preserve_format)}
+    ref = to_reference_optimizer_state(opts[0], models[0])
+    layout = _reference_group_layout(models[0], "fields")
+    kinds = [k for k, _ in layout]
+    assert kinds == ["tensor"] * 13 + ["empty", "tcnn", "tcnn"]  # aabb, 12 planes, SH encoding, sigma_net, color_net
+    assert set(ref["fields"]["state"]) == set(range(1, 13)) | {14, 15}  # aabb (no grad) and the SH encoding carry no state
+    color = ref["fields"]["state"][15]
+    assert color["exp_avg"].numel() == sum(o * i for o, i in tcnn_layer_shapes([31, 64, 64, 3]))
+    w0 = opts[0].optimizers["fields"].state[models[0].field.color_net.weights[0]]["exp_avg"]
+    assert torch.equal(color["exp_avg"][:32 * 64].view(64, 32)[:, :16], w0[:, :16] * TCNN_SH_SIGNS)
+    assert ref["fields"]["state"][1]["exp_avg"].is_contiguous()  # planes in NCHW order
+    load_reference_optimizer_state(opts[1], models[1], ref)
+    for group in ("fields", "proposal_networks"):
+        for p, q in zip(models[0].get_param_groups()[group], models[1].get_param_groups()[group]):
+            if p.requires_grad:
+                a, b = opts[0].optimizers[group].state[p], opts[1].optimizers[group].state[q]
+                assert b["step"] == 7 and torch.equal(a["exp_avg"], b["exp_avg"]) and torch.equal(a["exp_avg_sq"], b["exp_avg_sq"])
+                assert b["exp_avg"].stride() == q.stride()
