@@ -95,8 +95,9 @@ int kp_color_net_bwd(int view_dependent, const float* cin, const float* h2, cons
                      float* grad_w3, float* grad_w4, float* grad_w5 /* accumulated */,
                      float* scratch_a, float* scratch_b /* [M,H2] each */, void* stream);
 
-/* Dense layer on tcgen05 tensor cores, fp32-accurate through 3xTF32 (building block of the decoders):
- * Y[M,N] = act(X[M,K] W[N,K]^T), act 0 none / 1 ReLU / 2 sigmoid; N <= 64, K <= 128. */
+/* Dense layer on tcgen05 tensor cores, fp32-accurate through the 4-term TF32 split x = hi + lo (building block of the
+ * decoders): Y[M,N] = act(X[M,K] W[N,K]^T), act 0 none / 1 ReLU / 2 sigmoid; N, K <= 256 (K a multiple of 4 beyond one
+ * launch's tile: layers wider than 64 x 128 are cut into sub-matrix launches, partial sums held in Y). */
 int kp_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t M, int N,
                      int K, int act, void* stream);
 /* dX[M,K] = (dY[M,N] W[N,K]) masked by (aux[M,K] > 0) when aux != NULL (ReLU backward of the producing layer). */
@@ -202,6 +203,15 @@ int kp_plane_reg_fused(const float* const* planes, float* const* grads, const in
 int kp_adam_multi(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                   const int64_t* sizes, int P, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int64_t step, float grad_scale, const float* hyper_dev, void* stream);
+
+/* Per-step scalars of a CUDA-graph-replayed step, computed on the device from *step_counter (then incremented):
+ * anneal_out = anneal_table[min(step, max_steps)] (proposal-weight anneal, NS/models/kplanes.py:326-331) and, per
+ * optimizer group g, hyper_out[g] = (lr_table[..] / (1 - beta1^t), 1 / sqrt(1 - beta2^t), grad_scale) with t = step + 1
+ * -- the hyper_dev triple kp_adam_multi reads.  betas_host: HOST float[2*n_groups]; hyper_out_host: HOST array of DEVICE
+ * float[3] pointers; n_groups <= 4. */
+int kp_step_scalars(int64_t* step_counter, const double* lr_table, const float* anneal_table, int64_t max_steps, int n_groups,
+                    const float* betas_host, float grad_scale, float* anneal_out /* device, or NULL */,
+                    float* const* hyper_out_host, void* stream);
 
 /* ---- (f1) Adam over a flat fp32 buffer (torch.optim.Adam math; NS/engine/optimizers.py:74-160,
  *      method_configs.py:546-557: lr 1e-2, eps 1e-12).  step is 1-based. ---------------------------- */

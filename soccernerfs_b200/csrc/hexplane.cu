@@ -12,6 +12,11 @@
 //     6*K [M,C] tensors, and scatter-adds with red.global.add.v4.f32 (16-byte L2 reductions).
 // Also here: the fused proposal density field (kplanes_field.py:434-460): gather (C=8) -> Hadamard ->
 // 8->64->1 MLP -> trunc_exp in one kernel, and its backward.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace kp {
@@ -27,6 +32,7 @@ struct FieldRef {
   int n_scales, n_planes;
   uint32_t use_mask;
   int concat;
+  uint32_t agg_mask;  // scatter: bit k = merge equal texels of neighbouring samples of scale k inside the warp first
 };
 
 static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const* grad_ptrs, const int32_t* plane_hw,
@@ -66,6 +72,18 @@ static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const*
   F.n_planes = n_planes;
   F.use_mask = use_mask;
   F.concat = concat;
+  // Warp aggregation pays where consecutive samples of a ray share texels: the coarse scales.  A ray crosses at most
+  // ~R texels of an R^2 plane with S samples, so neighbours coincide often when R <= ~4 S; finer scales skip the
+  // extra shuffles.  KP_SCATTER_AGG=all|none overrides (A/B measurements).
+  F.agg_mask = 0;
+  const char* agg = getenv("KP_SCATTER_AGG");
+  for (int k = 0; k < n_scales; ++k) {
+    const int r = std::max(F.reso[k][0], std::max(F.reso[k][1], F.reso[k][2]));
+    bool on = r <= 256;
+    if (agg != nullptr && strcmp(agg, "all") == 0) on = true;
+    if (agg != nullptr && strcmp(agg, "none") == 0) on = false;
+    if (on) F.agg_mask |= 1u << k;
+  }
   return 0;
 }
 
@@ -190,15 +208,47 @@ __global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------------
 // Backward scatter: d plane_p[corner] += w_corner * g * prod_{q != p} interp_q.
 // ---------------------------------------------------------------------------------------------------
+// Warp-aggregated reduction: the 32 / LPS samples a warp owns are consecutive samples of a ray, so at the coarse scales
+// neighbouring samples often update the SAME texel corner.  Before the red, every run of neighbouring samples with an
+// equal texel index is summed with a segmented shuffle reduction (lane l talks to lanes l + LPS, l + 2 LPS, ... which
+// hold the same 16-byte channel slice of the next samples) and only the first sample of the run issues one red.v4 with
+// the run's total.  Runs are maximal CONTIGUOUS sequences of equal keys (from a ballot of the run heads), so any key
+// pattern is handled correctly -- non-adjacent duplicates are simply not merged.  `key` < 0 = nothing to add.
+// A warp-uniform test skips the value shuffles when no two neighbours coincide.
+template <int LPS>
+__device__ __forceinline__ void red_add_v4_aggregated(float* __restrict__ plane_grad, int key, float4 v, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int prev = __shfl_up_sync(full, key, LPS);
+  const bool head = (lane < LPS) || (prev != key);
+  const unsigned heads = __ballot_sync(full, head);
+  if (heads != full) {  // some sample continues its neighbour's run
+    // first lane of the next run after my sample's lanes (32 if none): additions may only reach below it
+    const int my_end = (lane / LPS + 1) * LPS;
+    const unsigned later = my_end < 32 ? (heads >> my_end) : 0u;
+    const int run_end = later ? my_end + __ffs(later) - 1 : 32;
+#pragma unroll
+    for (int d = LPS; d < 32; d <<= 1) {
+      const float x = __shfl_down_sync(full, v.x, d), y = __shfl_down_sync(full, v.y, d);
+      const float z = __shfl_down_sync(full, v.z, d), w = __shfl_down_sync(full, v.w, d);
+      if (lane + d < run_end) { v.x += x; v.y += y; v.z += z; v.w += w; }
+    }
+  }
+  if (head && key >= 0) red_add_v4(plane_grad + (int64_t)key * (LPS * 4), v);
+}
+
 template <int C, int NP>
 __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_constant__ FieldRef F,
                                                             const __grid_constant__ KpPoints P, int64_t M,
                                                             const float* __restrict__ grad_out) {
   constexpr int LPS = C / 4;
   const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t m = gt / LPS;
+  const int64_t m_raw = gt / LPS;
   const int c4 = (int)(gt % LPS) * 4;
-  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  // lanes past the last sample stay alive (the aggregation shuffles are warp-wide) on a clamped sample, adding nothing
+  const bool live = m_raw < M;
+  if (__all_sync(0xffffffffu, !live)) return;
+  const int64_t m = live ? m_raw : M - 1;
   float pt[4];
   load_point(P, m, pt);
   const int out_stride = F.concat ? F.n_scales * C : C;
@@ -239,10 +289,17 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
       if (!((F.use_mask >> p) & 1u) || pr.g == nullptr) continue;
       const float4 gp = mul4(g, mul4(pre[p], suf[p]));
       float* gb = pr.g + c4;
-      if (b[p].w00 != 0.f) red_add_v4(gb + (int64_t)b[p].o00 * C, scale4(gp, b[p].w00));
-      if (b[p].w01 != 0.f) red_add_v4(gb + (int64_t)b[p].o01 * C, scale4(gp, b[p].w01));
-      if (b[p].w10 != 0.f) red_add_v4(gb + (int64_t)b[p].o10 * C, scale4(gp, b[p].w10));
-      if (b[p].w11 != 0.f) red_add_v4(gb + (int64_t)b[p].o11 * C, scale4(gp, b[p].w11));
+      if ((F.agg_mask >> k) & 1u) {  // (warp-uniform: F is a kernel parameter)
+        red_add_v4_aggregated<LPS>(gb, (live && b[p].w00 != 0.f) ? b[p].o00 : -1, scale4(gp, b[p].w00), lane);
+        red_add_v4_aggregated<LPS>(gb, (live && b[p].w01 != 0.f) ? b[p].o01 : -1, scale4(gp, b[p].w01), lane);
+        red_add_v4_aggregated<LPS>(gb, (live && b[p].w10 != 0.f) ? b[p].o10 : -1, scale4(gp, b[p].w10), lane);
+        red_add_v4_aggregated<LPS>(gb, (live && b[p].w11 != 0.f) ? b[p].o11 : -1, scale4(gp, b[p].w11), lane);
+      } else if (live) {
+        if (b[p].w00 != 0.f) red_add_v4(gb + (int64_t)b[p].o00 * C, scale4(gp, b[p].w00));
+        if (b[p].w01 != 0.f) red_add_v4(gb + (int64_t)b[p].o01 * C, scale4(gp, b[p].w01));
+        if (b[p].w10 != 0.f) red_add_v4(gb + (int64_t)b[p].o10 * C, scale4(gp, b[p].w10));
+        if (b[p].w11 != 0.f) red_add_v4(gb + (int64_t)b[p].o11 * C, scale4(gp, b[p].w11));
+      }
     }
   }
 }

@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 }
 
 // The three products of a dense layer.  Shapes covered by the tcgen05 kernels (tc_linear.cu) run on the tensor cores
-// (3xTF32, fp32-accurate); the rest (e.g. the 192->128 first layer of the 32x config) use the SIMT SGEMM above.
+// (4-term TF32 split, fp32-accurate) -- including the 192->128 first layer of the 32x config, which is cut into
+// sub-matrix launches there; anything wider than 256 falls back to the SIMT SGEMM above.
 // Y[M,N] = act(X[M,K] W[N,K]^T)
 template <int EPI>
 static void gemm_fwd(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int64_t M, int N, int K,
@@ -121,7 +122,7 @@ static void gemm_dx(const float* dY, int lddy, const float* W, int ldw, float* d
 // dW[N,K] += dY[M,N]^T X[M,K]   (reduction over M split across blockIdx.z)
 static void gemm_dw(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int64_t M, int N, int K,
                     cudaStream_t st) {
-  if (N <= 128 && K <= 128 && !(N > 64 && K > 64)) {  // operand tiles of both widths must fit shared memory
+  if (N <= 256 && K <= 256) {  // (layers wider than one launch's operand tiles are cut into blocks of dW there)
     kp_tc_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, M, N, K, st);
     return;
   }

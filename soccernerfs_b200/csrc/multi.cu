@@ -266,6 +266,32 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
   }
 }
 
+// Per-step scalars of a graph-replayed training step, from the device-resident step counter: the proposal-weight
+// anneal exponent (NS/models/kplanes.py:326-331), the cosine-decayed learning rate (NS/engine/schedulers.py:126-142,
+// both tabulated by the host once) and Adam's bias corrections (torch.optim.Adam) -- one single-thread kernel instead
+// of ~30 0-d torch ops per step; it also advances the counter.
+struct StepScalars {
+  float* hyper[4];
+  float beta1[4], beta2[4];
+  int n_groups;
+};
+__global__ void step_scalars_kernel(long long* __restrict__ step_counter, const double* __restrict__ lr_table,
+                                    const float* __restrict__ anneal_table, long long max_steps, float grad_scale,
+                                    float* __restrict__ anneal_out, const __grid_constant__ StepScalars S) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long s = *step_counter;
+  const long long idx = s < max_steps ? s : max_steps;
+  if (anneal_out != nullptr) *anneal_out = anneal_table[idx];
+  const double lr = lr_table[idx], t = (double)(s + 1);
+  for (int g = 0; g < S.n_groups; ++g) {
+    const double bc1 = 1.0 - pow((double)S.beta1[g], t), bc2 = 1.0 - pow((double)S.beta2[g], t);
+    S.hyper[g][0] = (float)(lr / bc1);
+    S.hyper[g][1] = (float)rsqrt(bc2);
+    S.hyper[g][2] = grad_scale;
+  }
+  *step_counter = s + 1;
+}
+
 static int fill_reg_table(RegTable& T, const float* const* planes, float* const* grads, const int32_t* hwc,
                           const uint32_t* terms, int begin, int end, bool need_grad) {
   int nb = 0, k = 0;
@@ -319,6 +345,25 @@ extern "C" int kp_plane_reg_multi_bwd(const float* const* planes, float* const* 
     plane_reg_multi_bwd_kernel<<<nb, 256, 0, as_stream(stream)>>>(T, coef_dev + (size_t)begin * 4, accumulate);
     KP_LAUNCH_CHECK("plane_reg_multi_bwd");
   }
+  return 0;
+}
+
+extern "C" int kp_step_scalars(int64_t* step_counter, const double* lr_table, const float* anneal_table, int64_t max_steps,
+                               int n_groups, const float* betas_host, float grad_scale, float* anneal_out,
+                               float* const* hyper_out_host, void* stream) {
+  KP_CHECK(step_counter && lr_table && anneal_table && betas_host && hyper_out_host && n_groups >= 1 && n_groups <= 4,
+           "step_scalars: bad arguments (1..4 optimizer groups)");
+  StepScalars S;
+  S.n_groups = n_groups;
+  for (int g = 0; g < n_groups; ++g) {
+    KP_CHECK(hyper_out_host[g] != nullptr, "step_scalars: hyper_out[%d] is NULL", g);
+    S.hyper[g] = hyper_out_host[g];
+    S.beta1[g] = betas_host[2 * g];
+    S.beta2[g] = betas_host[2 * g + 1];
+  }
+  step_scalars_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<long long*>(step_counter), lr_table, anneal_table,
+                                                      (long long)max_steps, grad_scale, anneal_out, S);
+  KP_LAUNCH_CHECK("step_scalars");
   return 0;
 }
 

@@ -1,4 +1,4 @@
-// Dense layers of the decoders on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate via 3xTF32.
+// Dense layers of the decoders on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate via a 4-term TF32 split.
 //
 //   forward        Y[M,N]   = act( X[M,K] W[N,K]^T )
 //   backward data  dX[M,K]  = ( dY[M,N] W[N,K] ) * (aux > 0)
@@ -36,7 +36,7 @@ template <int B_MN, int R_pad>
 __global__ void __launch_bounds__(256) tc_rowtile_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W,
                                                          int64_t ldw, float* __restrict__ OUT, int64_t ldo, int64_t M, int N,
                                                          int N_pad, int R, int act, const float* __restrict__ aux,
-                                                         int64_t ldaux) {
+                                                         int64_t ldaux, int beta) {
   extern __shared__ uint8_t smem_raw[];
   const int b_rows = B_MN ? R_pad : N_pad, b_cols = B_MN ? N_pad : R_pad;
   float* a_hi = align1024(smem_raw);
@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(256) tc_rowtile_kernel(const float* __restrict
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           x[j] = __uint_as_float(v[j]);
+          // beta: OUT already holds the partial product of an earlier K slice (reduction depths > 128 are split over
+          // launches; the activation is applied by the launch that adds the last slice)
+          if (beta && c0 + j < N) x[j] += dst[j];
           if (!B_MN) {
             if (act == ACT_RELU) x[j] = fmaxf(x[j], 0.f);
             else if (act == ACT_SIGMOID) x[j] = 1.f / (1.f + expf(-x[j]));
@@ -145,6 +148,179 @@ __global__ void __launch_bounds__(256) tc_rowtile_kernel(const float* __restrict
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   tmem_free(tmem_slot, warp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined row-tile GEMM (the kernel the decoders' forward / backward-data products run on):
+//   OUT[128 rows, N] (+)= A[128, R] * B,   R = n_slices slices of KS columns, N <= 128 per CTA column slice
+// Same operands and epilogues as tc_rowtile_kernel, but software-pipelined so that the tensor core never waits for
+// the SIMT staging and vice versa:
+//   * the A tile is staged per KS-column slice into one of TWO shared-memory stages; while the MMAs of slice s run
+//     (asynchronously, completion signalled through an mbarrier per stage) all warps convert / store slice s+1 and
+//     the global loads of slice s+2 are already in flight in registers;
+//   * TWO TMEM accumulators: the epilogue of tile j (tcgen05.ld -> activation / mask -> global stores) overlaps the
+//     MMAs of tile j+1;
+//   * the weights of this CTA's column slice (all n_slices K slices) are staged once per persistent CTA;
+//   * blockIdx.y selects the column slice: output columns [col0, col0 + N) of a wider layer -- rows n0.. of W for the
+//     forward (B K-major), columns k0.. of W for the backward-data product (B MN-major view of the same row-major W).
+// Layers up to R = 192 (3 slices of 64) x 128 columns per slice fit: 2 x 64 KB of A stages + <= 96 KB of weights.
+// ---------------------------------------------------------------------------------------------------------------
+struct PipeArgs {
+  const float* A; int64_t lda;      // [M, R]
+  const float* W; int64_t ldw;      // forward: [N_total, R]; backward data: [R, N_total]
+  float* OUT; int64_t ldo;          // [M, N_total]
+  const float* aux; int64_t ldaux;  // backward data: ReLU mask source [M, N_total] or NULL
+  int64_t M;
+  int N_total, N_slice, N_pad;      // output columns: total, per blockIdx.y slice, padded slice width (32 | 64 | 128)
+  int R, n_slices;                  // reduction depth and its number of KS-column slices
+  int act, beta;
+};
+
+__device__ __forceinline__ void tmem_alloc_cols(uint32_t* slot, int warp, uint32_t ncols) {
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+}
+__device__ __forceinline__ void tmem_free_cols(uint32_t taddr, int warp, uint32_t ncols) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+
+template <int B_MN, int KS>
+__global__ void __launch_bounds__(256) tc_pipe_kernel(const __grid_constant__ PipeArgs P) {
+  extern __shared__ uint8_t smem_raw[];
+  const int R_tot = P.n_slices * KS;
+  const int b_rows = B_MN ? R_tot : P.N_pad, b_cols = B_MN ? P.N_pad : R_tot;
+  float* a_st = align1024(smem_raw);            // [2 stages][hi | lo][128 x KS]
+  float* b_hi = a_st + 4 * 128 * KS;
+  float* b_lo = b_hi + b_rows * b_cols;
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * P.N_slice;
+  const int N = min(P.N_slice, P.N_total - col0);
+  const uint32_t tmem_cols = P.N_pad <= 32 ? 64u : (P.N_pad <= 64 ? 128u : 256u);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tmem_alloc_cols(&tmem_slot, warp, tmem_cols);
+  // weights of this column slice, once per CTA
+  if (B_MN) stage_tile<1>(P.W + col0, P.ldw, b_rows, P.R, N, b_cols, b_hi, b_lo);
+  else stage_tile<0>(P.W + (int64_t)col0 * P.ldw, P.ldw, b_rows, N, P.R, b_cols, b_hi, b_lo);
+  const uint32_t idesc = umma_idesc_tf32(128, P.N_pad, 0, B_MN);
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const int64_t n_tiles = (P.M + 127) / 128;
+  const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int64_t n_steps = my_tiles * P.n_slices;
+
+  auto load_step = [&](TileRegs<KS>& t, int64_t step) {
+    const int64_t tile = blockIdx.x + (step / P.n_slices) * gridDim.x;
+    const int kc = (int)(step % P.n_slices);
+    tile_load<KS>(t, P.A + tile * 128 * P.lda + kc * KS, P.lda, (int)min((int64_t)128, P.M - tile * 128), P.R - kc * KS);
+  };
+  auto epilogue = [&](int64_t j) {  // tile j of this CTA: accumulator j & 1 -> global memory
+    const int64_t tile = blockIdx.x + j * gridDim.x;
+    const int64_t row0 = tile * 128;
+    const int rows_valid = (int)min((int64_t)128, P.M - row0);
+    const uint32_t taddr = tmem_slot + (uint32_t)((j & 1) * P.N_pad) + ((uint32_t)(quad * 32) << 16);
+    for (int c0 = half * 16; c0 < P.N_pad; c0 += 32) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < rows_valid && c0 < N) {
+        float* dst = P.OUT + (row0 + row) * P.ldo + col0 + c0;
+        const float* ax = P.aux ? P.aux + (row0 + row) * P.ldaux + col0 + c0 : nullptr;
+        float x[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          x[jj] = __uint_as_float(v[jj]);
+          if (P.beta && c0 + jj < N) x[jj] += dst[jj];
+          if (!B_MN) {
+            if (P.act == ACT_RELU) x[jj] = fmaxf(x[jj], 0.f);
+            else if (P.act == ACT_SIGMOID) x[jj] = 1.f / (1.f + expf(-x[jj]));
+          }
+        }
+        const bool full = (c0 + 16 <= N) && ((P.ldo & 3) == 0) && (((reinterpret_cast<uintptr_t>(P.OUT) + (size_t)col0 * 4) & 15) == 0);
+        if (full && (ax == nullptr || ((P.ldaux & 3) == 0 && (((reinterpret_cast<uintptr_t>(P.aux) + (size_t)col0 * 4) & 15) == 0)))) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o4 = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            if (B_MN && ax != nullptr) {
+              const float4 m4 = __ldg(reinterpret_cast<const float4*>(ax + 4 * q));
+              if (!(m4.x > 0.f)) o4.x = 0.f;
+              if (!(m4.y > 0.f)) o4.y = 0.f;
+              if (!(m4.z > 0.f)) o4.z = 0.f;
+              if (!(m4.w > 0.f)) o4.w = 0.f;
+            }
+            *reinterpret_cast<float4*>(dst + 4 * q) = o4;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            if (c0 + jj < N) {
+              float o1 = x[jj];
+              if (B_MN && ax != nullptr && !(ax[jj] > 0.f)) o1 = 0.f;
+              dst[jj] = o1;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads ordered before the next __syncthreads
+  };
+
+  TileRegs<KS> regs;
+  if (n_steps > 0) load_step(regs, 0);
+  for (int64_t s = 0; s < n_steps; ++s) {
+    const int st = (int)(s & 1);
+    float* a_hi = a_st + st * (2 * 128 * KS);
+    float* a_lo = a_hi + 128 * KS;
+    // stage st was last read by the MMAs of step s-2, whose completion was awaited at the end of iteration s-1
+    tile_store<0, KS>(regs, a_hi, a_lo);
+    publish_smem_and_sync();  // also orders every thread's epilogue of the previous tile before the MMAs issued below
+    if (s + 1 < n_steps) load_step(regs, s + 1);  // in flight during the MMAs / epilogue below
+    const int64_t j = s / P.n_slices;
+    const int kc = (int)(s % P.n_slices);
+    if (threadIdx.x == 0) {
+      const uint32_t tmem_d = tmem_slot + (uint32_t)((j & 1) * P.N_pad);
+      const uint64_t a_d[2] = {desc_kmajor(smem_u32(a_hi), 128, 0, 0), desc_kmajor(smem_u32(a_lo), 128, 0, 0)};
+      const uint64_t b_d[2] = {B_MN ? desc_mnmajor(smem_u32(b_hi), b_rows, 0) : desc_kmajor(smem_u32(b_hi), b_rows, 0, 0),
+                               B_MN ? desc_mnmajor(smem_u32(b_lo), b_rows, 0) : desc_kmajor(smem_u32(b_lo), b_rows, 0, 0)};
+      const uint32_t b_blk = (uint32_t)(b_rows * 128) >> 4;  // K-major B: 16-byte units between 32-col blocks
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi (small terms first)
+        const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
+#pragma unroll
+        for (int k8 = 0; k8 < KS / 8; ++k8) {
+          const int kk = kc * (KS / 8) + k8;  // K step within the whole reduction
+          const uint32_t a_off = (uint32_t)(((k8 >> 2) * 128 * 128 + (k8 & 3) * 32) >> 4);
+          const uint32_t b_off = B_MN ? (uint32_t)((kk * 1024) >> 4) : (uint32_t)(kk >> 2) * b_blk + (uint32_t)(((kk & 3) * 32) >> 4);
+          umma_tf32(tmem_d, ad0 + a_off, bd0 + b_off, idesc, (kc | t | k8) != 0);
+        }
+      }
+      umma_commit(&bar[st]);
+    }
+    // the previous step: its MMAs have been running under this step's staging; wait for them (frees the other stage)
+    // and, if that step completed a tile, unload the tile while THIS step's MMAs run
+    if (s >= 1) {
+      const int64_t sp = s - 1;
+      mbar_wait(&bar[sp & 1], (uint32_t)((sp >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if ((int)(sp % P.n_slices) == P.n_slices - 1) epilogue(sp / P.n_slices);
+    }
+  }
+  if (n_steps > 0) {
+    const int64_t sp = n_steps - 1;
+    mbar_wait(&bar[sp & 1], (uint32_t)((sp >> 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    epilogue(sp / P.n_slices);
+  }
+  tmem_free_cols(tmem_slot, warp, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -260,17 +436,60 @@ static unsigned persistent_grid(Kern kern, int64_t n_tiles, size_t smem) {
 
 template <int B_MN, int R_PAD>
 static void launch_rowtile(const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo, int64_t M, int N,
-                           int N_pad, int R, int act, const float* aux, int64_t ldaux, cudaStream_t st) {
+                           int N_pad, int R, int act, const float* aux, int64_t ldaux, int beta, cudaStream_t st) {
   const size_t smem = (size_t)(2 * 128 * R_PAD + 2 * N_pad * R_PAD) * sizeof(float) + 1024;
   auto kern = tc_rowtile_kernel<B_MN, R_PAD>;
-  kern<<<persistent_grid(kern, ceil_div(M, 128), smem), 256, smem, st>>>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux);
+  kern<<<persistent_grid(kern, ceil_div(M, 128), smem), 256, smem, st>>>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux,
+                                                                         beta);
+  kp::g_launches += 1;
 }
 template <int B_MN>
 static void dispatch_rowtile(int R_pad, const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo,
-                             int64_t M, int N, int N_pad, int R, int act, const float* aux, int64_t ldaux, cudaStream_t st) {
-  if (R_pad == 32) launch_rowtile<B_MN, 32>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, st);
-  else if (R_pad == 64) launch_rowtile<B_MN, 64>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, st);
-  else launch_rowtile<B_MN, 128>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, st);
+                             int64_t M, int N, int N_pad, int R, int act, const float* aux, int64_t ldaux, int beta,
+                             cudaStream_t st) {
+  if (R_pad == 32) launch_rowtile<B_MN, 32>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, beta, st);
+  else if (R_pad == 64) launch_rowtile<B_MN, 64>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, beta, st);
+  else launch_rowtile<B_MN, 128>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, beta, st);
+}
+
+// One tc_pipe_kernel launch: OUT[M, N_total] = epilogue(A[M, R] * B) with the output columns cut into grid.y slices.
+template <int B_MN>
+static bool launch_pipe(const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo, int64_t M, int N_total,
+                        int R, int act, const float* aux, int64_t ldaux, int beta, cudaStream_t st) {
+  if (getenv("KP_TC_PIPE") != nullptr && atoi(getenv("KP_TC_PIPE")) == 0) return false;
+  const int KS = R <= 32 ? 32 : 64;
+  const int n_slices = (int)ceil_div(R, KS);
+  // widest column slice whose weights fit beside the two A stages (227 KB of dynamic shared memory per CTA)
+  const size_t a_bytes = (size_t)4 * 128 * KS * sizeof(float);
+  int N_slice = std::min(N_total, 128);
+  for (;; N_slice = (N_slice > 64 ? 64 : 32)) {
+    const size_t b_bytes = (size_t)2 * pad_dim(N_slice) * n_slices * KS * sizeof(float);
+    if (a_bytes + b_bytes + 1024 <= 227 * 1024) break;
+    if (N_slice <= 32) return false;
+  }
+  PipeArgs P;
+  P.A = A; P.lda = lda; P.W = W; P.ldw = ldw; P.OUT = OUT; P.ldo = ldo; P.aux = aux; P.ldaux = ldaux; P.M = M;
+  P.N_total = N_total; P.N_slice = N_slice; P.N_pad = pad_dim(std::min(N_slice, N_total)); P.R = R; P.n_slices = n_slices;
+  P.act = act; P.beta = beta;
+  const size_t smem = a_bytes + (size_t)2 * P.N_pad * n_slices * KS * sizeof(float) + 1024;
+  const unsigned gy = (unsigned)ceil_div(N_total, N_slice);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n_tiles = ceil_div(M, 128);
+  // persistent CTAs: one per SM in total (shared memory allows a single CTA per SM), split over the column slices
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_tiles, sms / gy));
+  if (KS == 32) {
+    auto kern = tc_pipe_kernel<B_MN, 32>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<dim3(gx, gy), 256, smem, st>>>(P);
+  } else {
+    auto kern = tc_pipe_kernel<B_MN, 64>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<dim3(gx, gy), 256, smem, st>>>(P);
+  }
+  kp::g_launches += 1;
+  return true;
 }
 
 template <int K_PAD, int N_PAD>
@@ -296,17 +515,38 @@ static void dispatch_wgrad(int N_pad, const float* X, int64_t ldx, const float* 
 
 using namespace kp;
 
-// Which shapes the tensor-core path covers (others use the SIMT SGEMM in mlp.cu): operand tiles must fit shared memory.
-extern "C" int kp_tc_supported(int N, int K) {
-  return (N >= 1 && N <= 128 && K >= 1 && K <= 128 && pad_dim(N) * pad_dim(K) <= 128 * 64) ? 1 : 0;
-}
+// Shapes one launch covers: operand tiles must fit shared memory.
+static bool tc_single(int N, int K) { return N >= 1 && N <= 128 && K >= 1 && K <= 128 && pad_dim(N) * pad_dim(K) <= 128 * 64; }
+
+// Which layers the tensor-core path covers.  Layers wider than one launch's operand tiles (the 192 -> 128 first layer
+// of the 32x config, NS/configs/method_configs.py:523-524) are cut into slices of <= 64 output / input columns and
+// <= 128 reduction columns, each slice one launch on a sub-matrix (pointer offset + leading dimension).
+extern "C" int kp_tc_supported(int N, int K) { return (N >= 1 && N <= 256 && K >= 1 && K <= 256 && (K % 4 == 0 || tc_single(N, K))) ? 1 : 0; }
 
 extern "C" int kp_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t M,
                                 int N, int K, int act, void* stream) {
   if (M == 0) return 0;
   KP_CHECK(X && W && Y && kp_tc_supported(N, K), "tc_linear_fwd: unsupported shape N=%d K=%d", N, K);
   KP_CHECK(act >= 0 && act <= 2, "tc_linear_fwd: act=%d", act);
-  dispatch_rowtile<0>(pad_dim(K), X, ldx, W, ldw, Y, ldy, M, N, pad_dim(N), K, act, nullptr, 0, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  if (K <= 192 && launch_pipe<0>(X, ldx, W, ldw, Y, ldy, M, N, K, act, nullptr, 0, 0, st)) {
+    // pipelined kernel: K sliced inside the kernel, output columns over grid.y
+  } else if (tc_single(N, K)) {
+    dispatch_rowtile<0>(pad_dim(K), X, ldx, W, ldw, Y, ldy, M, N, pad_dim(N), K, act, nullptr, 0, 0, st);
+  } else {
+    // output columns in slices of 64, reduction in slices of 128: Y[:, n0:n1] = act( sum_k X[:, k0:k1] W[n0:n1, k0:k1]^T ),
+    // partial sums kept in Y itself (beta) and the activation applied with the last K slice
+    for (int n0 = 0; n0 < N; n0 += 64) {
+      const int nn = std::min(64, N - n0);
+      for (int k0 = 0; k0 < K; k0 += 128) {
+        const int kk = std::min(128, K - k0);
+        const bool last = k0 + 128 >= K;
+        dispatch_rowtile<0>(pad_dim(kk), X + k0, ldx, W + (int64_t)n0 * ldw + k0, ldw, Y + n0, ldy, M, nn, pad_dim(nn), kk,
+                            last ? act : 0, nullptr, 0, k0 > 0 ? 1 : 0, st);
+      }
+    }
+  }
+  kp::g_launches -= 1;  // every launch was counted; KP_LAUNCH_CHECK counts one more
   KP_LAUNCH_CHECK("tc_linear_fwd");
   return 0;
 }
@@ -316,8 +556,25 @@ extern "C" int kp_tc_linear_bwd_data(const float* dY, int64_t lddy, const float*
                                      int64_t M, int N, int K, const float* aux, int64_t ldaux, void* stream) {
   if (M == 0) return 0;
   KP_CHECK(dY && W && dX && kp_tc_supported(N, K), "tc_linear_bwd_data: unsupported shape N=%d K=%d", N, K);
-  // reduction over N_out (R), output width K_in
-  dispatch_rowtile<1>(pad_dim(N), dY, lddy, W, ldw, dX, lddx, M, K, pad_dim(K), N, 0, aux, ldaux, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  if (N <= 192 && launch_pipe<1>(dY, lddy, W, ldw, dX, lddx, M, K, N, 0, aux, ldaux, 0, st)) {
+    // pipelined kernel: reduction over N_out sliced inside the kernel, output (K_in) columns over grid.y
+  } else if (tc_single(N, K)) {
+    // reduction over N_out (R), output width K_in
+    dispatch_rowtile<1>(pad_dim(N), dY, lddy, W, ldw, dX, lddx, M, K, pad_dim(K), N, 0, aux, ldaux, 0, st);
+  } else {
+    // input columns in slices of 64, reduction (N_out) in slices of 128; the ReLU mask is applied with the last slice
+    for (int k0 = 0; k0 < K; k0 += 64) {
+      const int kk = std::min(64, K - k0);
+      for (int n0 = 0; n0 < N; n0 += 128) {
+        const int nn = std::min(128, N - n0);
+        const bool last = n0 + 128 >= N;
+        dispatch_rowtile<1>(pad_dim(nn), dY + n0, lddy, W + (int64_t)n0 * ldw + k0, ldw, dX + k0, lddx, M, kk, pad_dim(kk), nn, 0,
+                            (last && aux) ? aux + k0 : nullptr, ldaux, n0 > 0 ? 1 : 0, st);
+      }
+    }
+  }
+  kp::g_launches -= 1;
   KP_LAUNCH_CHECK("tc_linear_bwd_data");
   return 0;
 }
@@ -326,13 +583,26 @@ extern "C" int kp_tc_linear_bwd_data(const float* dY, int64_t lddy, const float*
 extern "C" int kp_tc_linear_bwd_weight(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t lddw,
                                        int64_t M, int N, int K, void* stream) {
   if (M == 0) return 0;
-  KP_CHECK(dY && X && dW && N >= 1 && N <= 128 && K >= 1 && K <= 128 && pad_dim(N) + pad_dim(K) <= 192,
-           "tc_linear_bwd_weight: unsupported shape N=%d K=%d", N, K);
-  const int Kp = pad_dim(K), Np = pad_dim(N);
+  KP_CHECK(dY && X && dW && N >= 1 && N <= 256 && K >= 1 && K <= 256, "tc_linear_bwd_weight: unsupported shape N=%d K=%d", N, K);
   cudaStream_t st = as_stream(stream);
-  if (Kp == 32) dispatch_wgrad<32>(Np, X, ldx, dY, lddy, dW, lddw, M, K, N, st);
-  else if (Kp == 64) dispatch_wgrad<64>(Np, X, ldx, dY, lddy, dW, lddw, M, K, N, st);
-  else dispatch_wgrad<128>(Np, X, ldx, dY, lddy, dW, lddw, M, K, N, st);
+  // one launch covers pad(N) + pad(K) <= 192 operand columns; wider layers are cut into [<=128 x <=64] blocks of dW
+  const bool single = N <= 128 && K <= 128 && pad_dim(N) + pad_dim(K) <= 192;
+  const int n_step = single ? N : 128, k_step = single ? K : 64;
+  for (int n0 = 0; n0 < N; n0 += n_step) {
+    const int nn = std::min(n_step, N - n0);
+    for (int k0 = 0; k0 < K; k0 += k_step) {
+      const int kk = std::min(k_step, K - k0);
+      const int Kp = pad_dim(kk), Np = pad_dim(nn);
+      const float* Xs = X + k0;
+      const float* dYs = dY + n0;
+      float* dWs = dW + (int64_t)n0 * lddw + k0;
+      if (Kp == 32) dispatch_wgrad<32>(Np, Xs, ldx, dYs, lddy, dWs, lddw, M, kk, nn, st);
+      else if (Kp == 64) dispatch_wgrad<64>(Np, Xs, ldx, dYs, lddy, dWs, lddw, M, kk, nn, st);
+      else dispatch_wgrad<128>(Np, Xs, ldx, dYs, lddy, dWs, lddw, M, kk, nn, st);
+      kp::g_launches += 1;
+    }
+  }
+  kp::g_launches -= 1;  // KP_LAUNCH_CHECK counts one
   KP_LAUNCH_CHECK("tc_linear_bwd_weight");
   return 0;
 }

@@ -351,7 +351,20 @@ class TrainStep:
                 group["hyper_dev"] = torch.zeros(3, dtype=torch.float32, device=dev)
 
     def _device_scalars(self) -> None:
-        """In-graph prologue: anneal exponent and Adam scalars for the device-resident step counter."""
+        """In-graph prologue: anneal exponent and Adam scalars for the device-resident step counter (and the counter's
+        increment) -- one kernel (kp_step_scalars) on CUDA."""
+        if self._step_t.is_cuda:
+            from ctypes import c_float, c_void_p
+
+            from .. import _lib
+
+            groups = [g for opt in self.optimizers.optimizers.values() for g in opt.param_groups]
+            betas = (c_float * (2 * len(groups)))(*[float(b) for g in groups for b in g["betas"]])
+            hyper = (c_void_p * len(groups))(*[g["hyper_dev"].data_ptr() for g in groups])
+            _lib.call("kp_step_scalars", c_void_p(self._step_t.data_ptr()), c_void_p(self._lr_table.data_ptr()),
+                      c_void_p(self._anneal_table.data_ptr()), int(self.max_steps), len(groups), betas, float(self._grad_scale),
+                      c_void_p(self._anneal_t.data_ptr()), hyper, _lib.stream_ptr())
+            return
         idx = self._step_t.clamp(max=self.max_steps).view(1)  # 1-d index: a 0-d tensor index would .item() (host sync)
         self._anneal_t.copy_(self._anneal_table.gather(0, idx).view(()))
         t = (self._step_t + 1).double()
@@ -369,7 +382,8 @@ class TrainStep:
         self._device_scalars()
         rb = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"], times=s["times"])
         out = self._iteration(rb, {"image": s["image"]})
-        self._step_t += 1
+        if not self._step_t.is_cuda:
+            self._step_t += 1  # (on CUDA kp_step_scalars advanced the counter)
         return out
 
     def _graphable(self, ray_bundle: RayBundle, batch) -> bool:

@@ -1,4 +1,4 @@
-"""tcgen05 (3xTF32) dense layer vs fp32 torch matmul."""
+"""tcgen05 dense layer (4-term TF32 split, fp32-accurate) vs an fp64 torch matmul."""
 import pytest
 import torch
 
@@ -7,7 +7,8 @@ from tests.conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("m,n,k,act", [(128, 64, 32, 0), (300, 64, 128, 1), (1000, 16, 64, 0), (257, 3, 64, 2), (4096, 64, 31, 1)])
+@pytest.mark.parametrize("m,n,k,act", [(128, 64, 32, 0), (300, 64, 128, 1), (1000, 16, 64, 0), (257, 3, 64, 2), (4096, 64, 31, 1),
+                                         (1000, 128, 192, 1), (515, 128, 128, 0), (300, 96, 256, 2)])
 def test_tc_linear_matches_fp32(m, n, k, act):
     from ctypes import c_void_p
 
@@ -27,7 +28,8 @@ def test_tc_linear_matches_fp32(m, n, k, act):
     del c_void_p
 
 
-@pytest.mark.parametrize("m,n,k", [(128, 64, 32), (300, 64, 128), (1000, 16, 64), (257, 3, 64), (4096, 64, 31), (777, 128, 16)])
+@pytest.mark.parametrize("m,n,k", [(128, 64, 32), (300, 64, 128), (1000, 16, 64), (257, 3, 64), (4096, 64, 31), (777, 128, 16),
+                                     (1000, 128, 192), (515, 128, 128), (300, 200, 96)])
 def test_tc_linear_backward_matches_fp32(m, n, k):
     """dX = (dY W) * mask and dW += dY^T X through the MN-major operand views."""
     from soccernerfs_b200 import _lib
