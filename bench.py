@@ -62,9 +62,9 @@ WORKLOADS = {
 }
 WORKLOAD = WORKLOADS["cfg2"]["label"]
 FIELD_KERNELS = ("kp_hexplane_fwd", "kp_hexplane_bwd", "kp_density_field_fwd", "kp_density_field_bwd")
-OTHER_TIMED = ("kp_decoder_fwd_fused", "kp_decoder_bwd_fused", "kp_color_net_bwd", "kp_sigma_net_bwd", "kp_sigma_net_fwd",
-               "kp_color_net_fwd", "kp_adam_multi", "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd", "kp_plane_reg_grad_write",
-               "kp_peer_allreduce", "kp_peer_reduce_scatter", "kp_peer_allgather")
+OTHER_TIMED = ("kp_decoder_fwd_fused", "kp_color_net_bwd", "kp_sigma_net_bwd", "kp_sigma_net_fwd", "kp_color_net_fwd",
+               "kp_adam_multi", "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd", "kp_plane_reg_fused", "kp_peer_allreduce",
+               "kp_peer_sharded_adam")
 
 
 def _peaks():
@@ -282,6 +282,10 @@ def _global_rand(rank, world, seed, dev):
 
 
 def dp_check(trainer, model, rank, world, dev):
+    """(1) after all the steps so far the replicas hold bit-identical parameters; (2) the summed gradient of one more
+    data-parallel step equals the gradient ONE rank computes on the concatenated batch; (3) with the sharded optimizer:
+    one fused reduce-scatter + Adam + all-gather step equals torch's Adam formulas applied to that summed gradient on
+    the owned shard.  The trainer's state is restored afterwards."""
     import torch.distributed as dist
 
     def checksum():
@@ -291,48 +295,96 @@ def dp_check(trainer, model, rank, world, dev):
                 acc += p.detach().contiguous().view(-1).view(torch.int32).to(torch.int64).sum()
         return acc
 
-    # (1) after every step so far the replicas must hold the same bits
     sums = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sums, checksum())
     identical = all(int(s) == int(sums[0]) for s in sums)
-    # (2) all-reduced gradient of one more DP step == gradient of ONE rank on the concatenated batch
     from soccernerfs_b200.data.synthetic import synthetic_rays
 
     gen = torch.Generator().manual_seed(777)
     o, d, t, _ = synthetic_rays(RAYS_PER_RANK * world, gen)
     img = torch.rand(RAYS_PER_RANK * world, 3, generator=gen)
     packed = torch.cat([o, d, t, img], dim=-1).to(dev)
-    keep = [p.detach().clone() for p in model.parameters()]
+    keep = [p.detach().clone(memory_format=torch.preserve_format) for p in model.parameters()]
+
+    def restore():
+        with torch.no_grad():
+            for p, q in zip(model.parameters(), keep):
+                p.copy_(q)
+
     was_graph, trainer.use_cuda_graph = trainer.use_cuda_graph, False
+    sharded, trainer.sharded = trainer.sharded, {}  # (2) runs through the all-reduce path, optimizer switched off
+    step_all = trainer.optimizers.optimizer_step_all
+    trainer.optimizers.optimizer_step_all = lambda **kw: None
     sl = slice(rank * RAYS_PER_RANK, (rank + 1) * RAYS_PER_RANK)
-    with _global_rand(rank, world, 99, dev):
-        rb, batch = _bundle(packed[sl].contiguous())
-        trainer(rb, batch)
-    g_dp = {k: (b.flat / world).clone() for k, b in trainer.buckets.items()}
-    with torch.no_grad():
-        for p, q in zip(model.parameters(), keep):
-            p.copy_(q)
-    saved = (trainer.reduce_grads, trainer.optimizers.optimizer_step_all)
-    trainer.reduce_grads, trainer.optimizers.optimizer_step_all = False, (lambda grad_scale=1.0: None)
     try:
-        with _global_rand(-1, world, 99, dev):
-            rb, batch = _bundle(packed)
-            trainer(rb, batch)
+        with _global_rand(rank, world, 99, dev):
+            trainer(*_bundle(packed[sl].contiguous()))
+        g_sum = {k: b.flat.clone() for k, b in trainer.buckets.items()}
+        reduce_grads, trainer.reduce_grads = trainer.reduce_grads, False
+        try:
+            with _global_rand(-1, world, 99, dev):
+                trainer(*_bundle(packed))
+        finally:
+            trainer.reduce_grads = reduce_grads
     finally:
-        trainer.reduce_grads, trainer.optimizers.optimizer_step_all = saved
+        trainer.optimizers.optimizer_step_all = step_all
+        trainer.sharded = sharded
     rel = {}
     for k, b in trainer.buckets.items():
         ref = b.flat
-        rel[k] = float((g_dp[k] - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
-    with torch.no_grad():
-        for p, q in zip(model.parameters(), keep):
-            p.copy_(q)
-    trainer.use_cuda_graph = was_graph
+        rel[k] = float((g_sum[k] / world - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
     worst = torch.tensor([max(rel.values())], dtype=torch.float64, device=dev)
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    out = {"params_bit_identical_across_ranks": identical, "grad_vs_single_rank_on_concatenated_batch_rel": float(worst),
+           "tolerance": 1e-5, "per_group": rel}
     ok = bool(identical and float(worst) < 1e-5)
-    return {"ok": ok, "params_bit_identical_across_ranks": identical, "grad_vs_single_rank_on_concatenated_batch_rel": float(worst),
-            "tolerance": 1e-5, "per_group": rel}
+    if sharded:  # (3)
+        snap = {k: (g.param_flat.clone(), g.exp_avg.clone(), g.exp_avg_sq.clone()) for k, g in sharded.items()}
+        with _global_rand(rank, world, 99, dev):
+            trainer(*_bundle(packed[sl].contiguous()))
+        worst3 = 0.0
+        for k, g in sharded.items():
+            grp = trainer.optimizers.optimizers[k].param_groups[0]
+            b1, b2 = grp["betas"]
+            step_no = trainer.step  # the step just taken used trainer.step + 1 before the increment
+            lr1 = float(grp["lr_used"]) if "lr_used" in grp else None
+            p0, m0, v0 = snap[k]
+            lo, hi = g.shard_slice()
+            n = hi - lo
+            gr = torch.zeros(n, device=dev)
+            avail = min(hi, g_sum[k].numel()) - lo
+            if avail > 0:
+                gr[:avail] = g_sum[k][lo:lo + avail] / world
+            m1 = m0[:n] + (gr - m0[:n]) * (1.0 - b1)
+            v1 = v0[:n] * b2 + (1.0 - b2) * gr * gr
+            lr = trainer._last_sharded_lr[k]
+            lr_over_bc1 = torch.tensor(lr / (1.0 - b1 ** step_no), dtype=torch.float32, device=dev)
+            inv_sqrt_bc2 = torch.tensor(1.0 / (1.0 - b2 ** step_no) ** 0.5, dtype=torch.float32, device=dev)
+            p_old = torch.zeros(n, device=dev)
+            availp = min(hi, p0.numel()) - lo
+            if availp > 0:
+                p_old[:availp] = p0[lo:lo + availp]
+            p1 = p_old - lr_over_bc1 * m1 / (torch.sqrt(v1) * inv_sqrt_bc2 + grp["eps"])
+            got_p = torch.zeros(n, device=dev)
+            if availp > 0:
+                got_p[:availp] = g.param_flat[lo:lo + availp]
+            e_m = float((g.exp_avg[:n] - m1).abs().max() / m1.abs().max().clamp_min(1e-30))
+            e_v = float((g.exp_avg_sq[:n] - v1).abs().max() / v1.abs().max().clamp_min(1e-30))
+            e_p = float((got_p - p1).abs().max() / max(lr, 1e-12))
+            worst3 = max(worst3, e_m, e_v, e_p * 1e-2)  # parameters: within 1e-3 of one learning-rate step
+            del lr1
+        for k, g in sharded.items():  # put the optimizer state and the parameters back
+            g.param_flat.copy_(snap[k][0])
+            g.exp_avg.copy_(snap[k][1])
+            g.exp_avg_sq.copy_(snap[k][2])
+        w3 = torch.tensor([worst3], dtype=torch.float64, device=dev)
+        dist.all_reduce(w3, op=dist.ReduceOp.MAX)
+        out["sharded_adam_vs_torch_formulas_on_reduced_gradient"] = float(w3)
+        ok = ok and float(w3) < 1e-5
+    restore()
+    trainer.use_cuda_graph = was_graph
+    out["ok"] = ok
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -351,7 +403,8 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
     trainer = TrainStep(model, data_parallel=args.allreduce != "none", use_cuda_graph=not args.eager,
                         overlap_branches=not args.no_overlap, overlap_proposal_backward=prop_overlap,
                         allreduce_mode=args.allreduce if args.allreduce != "none" else "overlap",
-                        allreduce_backend=args.allreduce_backend)
+                        allreduce_backend=args.allreduce_backend,
+                        shard_optimizer={"auto": None, "on": True, "off": False}[args.shard_optimizer])
     n_steps = args.warmup + args.steps
     host = _make_batches(n_steps, RAYS_PER_RANK, seed=1000 + rank)
     resident = [h.to(dev) for h in host]
@@ -395,10 +448,16 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
         trainer(rb, batch)
 
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()  # every rank samples its own GPU
     total_ms, rank_ms = timed_region(step_resident)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        if rank == 0:
+            clocks = dict(allc[0])
+            clocks["per_rank_sm_mhz"] = [c.get("sm_mhz") for c in allc]
+            clocks["reasons"] = sorted({r for c in allc for r in c.get("reasons", [])})
     # a graph replay launches the kernels captured once; count them from one eager iteration of the same step
     was_graph, trainer.use_cuda_graph = trainer.use_cuda_graph, False
     k0 = _lib.launch_count()
@@ -484,8 +543,9 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "kernels": per_kernel, "per_scale": scales, "clocks": clocks,
         "plane_mb": sum(p.numel() for g in model.field.grids for p in g) * 4 / 2**20,
-        "grad_allreduce": ("none (single rank)" if world == 1 else
-                           f"{trainer.allreduce_backend} ({args.allreduce})" if args.allreduce != "none" else "disabled"),
+        "grad_allreduce": ("none (single rank)" if world == 1 else "disabled" if args.allreduce == "none" else
+                           (f"{trainer.allreduce_backend}: fused reduce-scatter + sharded Adam + all-gather kernel" if trainer.sharded
+                            else f"{trainer.allreduce_backend} all-reduce ({args.allreduce}) + replicated Adam")),
     })
     if rank == 0 and scales:
         leg["roofline"] = _roofline(name, per_kernel, step_bytes, scales, peaks, probe)
@@ -774,6 +834,8 @@ def main():
                     help="gradient all-reduce scheduling under data parallelism ('none' is a diagnostic: ranks do not sync)")
     ap.add_argument("--allreduce-backend", choices=["peer", "nccl"], default="peer",
                     help="peer: our in-place NVLink peer-memory kernel; nccl: torch.distributed.all_reduce")
+    ap.add_argument("--shard-optimizer", choices=["auto", "on", "off"], default="auto",
+                    help="N>1, peer backend: reduce-scatter + Adam on the owned shard + all-gather in one kernel (auto = on)")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python each step instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -279,6 +279,16 @@ int kp_peer_allreduce(void* const* arenas /* HOST array [world]: arenas[rank] = 
                       int world, int64_t begin /* float index, multiple of 4 */, int64_t count, int blocks /* <=0: 64 */,
                       void* stream);
 
+/* Sharded optimizer step fused with its collectives (reduce-scatter -> Adam -> all-gather in one kernel per rank):
+ * gradients at float offset grad_begin and parameters at param_begin of every arena's data region, `count` floats
+ * (multiples of 4).  Rank r owns floats [count*r/world, count*(r+1)/world) (at float4 granularity): it sums the world's
+ * gradients for them, updates ITS moments (exp_avg_shard / exp_avg_sq_shard, local buffers covering only the shard) with
+ * torch.optim.Adam's rule (grad_scale, e.g. 1/world, applied to the sum) and writes the new parameters into every
+ * rank's arena.  Same calling discipline as kp_peer_allreduce.  hyper_dev as in kp_adam_multi. */
+int kp_peer_sharded_adam(void* const* arenas, int rank, int world, int64_t grad_begin, int64_t param_begin, int64_t count,
+                         float* exp_avg_shard, float* exp_avg_sq_shard, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int64_t step, float grad_scale, const float* hyper_dev, int blocks, void* stream);
+
 /* ---- (d) measurement: memory-hierarchy probe with the field kernels' own access pattern (8 lanes = one 128-byte
  *      line of a pseudo-random texel; mode 0: 16-byte read-only loads, mode 1: red.global.add.v4.f32).  One launch
  *      touches blocks*32*iters lines of buf[0 : n_lines*32] (iters rounded up to a multiple of 8); bench.py times it

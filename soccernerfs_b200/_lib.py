@@ -78,6 +78,8 @@ SIGNATURES = {
     "kp_peer_free": ([_P], c_int),
     "kp_peer_error": ([_P, POINTER(c_uint32)], c_int),
     "kp_peer_allreduce": ([_P, c_int, c_int, c_int64, c_int64, c_int, _P], c_int),
+    "kp_peer_sharded_adam": ([_P, c_int, c_int, c_int64, c_int64, c_int64, _P, _P, c_float, c_float, c_float, c_float, c_float,
+                             c_int64, c_float, _P, c_int, _P], c_int),
     "kp_line_probe": ([_P, c_int64, c_int, c_int, c_int, c_uint32, _P, POINTER(c_int64), _P], c_int),
     "kp_repack_nchw_to_hwc": ([_P, _P, c_int, c_int, c_int, _P], c_int),
     "kp_repack_hwc_to_nchw": ([_P, _P, c_int, c_int, c_int, _P], c_int),

@@ -13,6 +13,7 @@
 // Cross-GPU ordering uses per-block flag words in the arenas (release/acquire at system scope): a start barrier
 // ("every rank's backward has written its gradients") and an end barrier ("every push has landed").  The flags are
 // monotonically increasing and the counter lives in device memory, so the kernel can be replayed from a CUDA graph.
+#include <math.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -126,9 +127,141 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const __gr
   if (threadIdx.x == 0) *counter = flag;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sharded optimizer step fused with its collectives (reduce-scatter -> Adam -> all-gather in ONE kernel):
+//   rank r owns the r-th 1/N of a parameter group.  For every 16-byte element of its shard it loads the N ranks'
+//   gradients (N-1 over NVLink), sums them in rank order, applies torch.optim.Adam's update to ITS OWN copy of the
+//   moments (which therefore only exist for the shard: 1/N of the optimizer state per GPU) and stores the new
+//   parameter value into all N ranks' parameter buffers (N-1 stores over NVLink).  Same NVLink bytes as the
+//   all-reduce above, but Adam's memory traffic per GPU drops from 7 x the group to 7/N x, and no rank ever
+//   materialises the reduced gradient.  Every parameter element is computed by exactly one rank and broadcast, so the
+//   replicas stay bit-identical.  Parameters and gradients live in the peer arenas at the same element offsets
+//   relative to their region.  Barriers as above: start = "every rank's backward has written its gradients AND no rank
+//   still reads the parameters", end = "every pushed parameter has landed".
+// ---------------------------------------------------------------------------------------------------------------
+struct ShardedAdamArgs {
+  float* grad[kPeerMaxWorld];    // gradient region of every rank's arena, at the group's first element
+  float* param[kPeerMaxWorld];   // parameter region of every rank's arena, at the group's first element
+  uint32_t* sig[kPeerMaxWorld];
+  float* m;                      // this rank's moments for its shard: index 0 = first owned element
+  float* v;
+  int rank, world;
+  int64_t n4;                    // group size in float4 units
+  const float* hyper_dev;        // optional DEVICE {lr / bias_corr1, 1 / sqrt(bias_corr2), grad_scale}
+  float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, wd, grad_scale;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kPeerThreads) peer_sharded_adam_kernel(const __grid_constant__ ShardedAdamArgs a) {
+  __shared__ uint32_t s_flag;
+  PeerArgs b;  // barrier view of the same arenas
+#pragma unroll
+  for (int p = 0; p < kPeerMaxWorld; ++p) b.sig[p] = a.sig[p];
+  b.rank = a.rank;
+  b.world = a.world;
+  uint32_t* counter = a.sig[a.rank] + kSigCounter + blockIdx.x;
+  if (threadIdx.x == 0) s_flag = *counter + 1u;
+  __syncthreads();
+  const uint32_t flag = s_flag;
+  peer_barrier(b, 0, flag);
+  float lr_over_bc1 = a.lr_over_bc1, inv_sqrt_bc2 = a.inv_sqrt_bc2, grad_scale = a.grad_scale;
+  if (a.hyper_dev != nullptr) {
+    lr_over_bc1 = a.hyper_dev[0];
+    inv_sqrt_bc2 = a.hyper_dev[1];
+    grad_scale = a.hyper_dev[2];
+  }
+  const int64_t lo = a.n4 * a.rank / N, hi = a.n4 * (a.rank + 1) / N;
+  const int64_t stride = (int64_t)gridDim.x * kPeerThreads;
+  constexpr int U = 2;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; i0 < hi; i0 += U * stride) {
+    float4 g[U][N], pp[U], mm[U], vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < hi) {
+#pragma unroll
+        for (int p = 0; p < N; ++p) g[u][p] = ld_peer_v4(a.grad[p] + 4 * i);
+        pp[u] = *reinterpret_cast<const float4*>(a.param[a.rank] + 4 * i);
+        mm[u] = *reinterpret_cast<const float4*>(a.m + 4 * (i - lo));
+        vv[u] = *reinterpret_cast<const float4*>(a.v + 4 * (i - lo));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < hi) {
+        float4 s = g[u][0];
+#pragma unroll
+        for (int p = 1; p < N; ++p) { s.x += g[u][p].x; s.y += g[u][p].y; s.z += g[u][p].z; s.w += g[u][p].w; }
+        float* ga = &s.x; float* pa = &pp[u].x; float* ma = &mm[u].x; float* va = &vv[u].x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // torch.optim.Adam (same arithmetic as adam_multi_kernel)
+          const float gr = ga[k] * grad_scale + a.wd * pa[k];
+          ma[k] = ma[k] + (gr - ma[k]) * (1.f - a.beta1);
+          va[k] = va[k] * a.beta2 + (1.f - a.beta2) * gr * gr;
+          pa[k] -= lr_over_bc1 * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + a.eps);
+        }
+        *reinterpret_cast<float4*>(a.m + 4 * (i - lo)) = mm[u];
+        *reinterpret_cast<float4*>(a.v + 4 * (i - lo)) = vv[u];
+#pragma unroll
+        for (int p = 0; p < N; ++p) st_peer_v4(a.param[p] + 4 * i, pp[u]);
+      }
+    }
+  }
+  peer_barrier(b, 1, flag);
+  if (threadIdx.x == 0) *counter = flag;
+}
+
 }  // namespace kp
 
 using namespace kp;
+
+extern "C" int kp_peer_sharded_adam(void* const* arenas, int rank, int world, int64_t grad_begin, int64_t param_begin,
+                                    int64_t count, float* exp_avg_shard, float* exp_avg_sq_shard, float lr, float beta1,
+                                    float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                                    const float* hyper_dev, int blocks, void* stream) {
+  KP_CHECK(arenas != nullptr && exp_avg_shard != nullptr && exp_avg_sq_shard != nullptr, "peer_sharded_adam: NULL argument");
+  KP_CHECK(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "peer_sharded_adam: rank %d / world %d", rank, world);
+  KP_CHECK(grad_begin >= 0 && param_begin >= 0 && count >= 0 && grad_begin % 4 == 0 && param_begin % 4 == 0 && count % 4 == 0,
+           "peer_sharded_adam: offsets / count must be multiples of 4 floats");
+  KP_CHECK(step >= 1, "peer_sharded_adam: step is 1-based");
+  if (count == 0) return 0;
+  if (blocks <= 0) blocks = 64;
+  KP_CHECK(blocks <= kPeerMaxBlocks, "peer_sharded_adam: blocks=%d > %d", blocks, kPeerMaxBlocks);
+  ShardedAdamArgs a;
+  for (int p = 0; p < kPeerMaxWorld; ++p) { a.grad[p] = nullptr; a.param[p] = nullptr; a.sig[p] = nullptr; }
+  for (int p = 0; p < world; ++p) {
+    KP_CHECK(arenas[p] != nullptr, "peer_sharded_adam: arena %d is NULL", p);
+    a.sig[p] = reinterpret_cast<uint32_t*>(arenas[p]);
+    float* data = reinterpret_cast<float*>(reinterpret_cast<char*>(arenas[p]) + KP_PEER_SIGNAL_BYTES);
+    a.grad[p] = data + grad_begin;
+    a.param[p] = data + param_begin;
+  }
+  a.m = exp_avg_shard;
+  a.v = exp_avg_sq_shard;
+  a.rank = rank;
+  a.world = world;
+  a.n4 = count / 4;
+  a.hyper_dev = hyper_dev;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  a.lr_over_bc1 = (float)(lr / bc1);
+  a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
+  cudaStream_t st = as_stream(stream);
+  switch (world) {
+    case 1: peer_sharded_adam_kernel<1><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 2: peer_sharded_adam_kernel<2><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 3: peer_sharded_adam_kernel<3><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 4: peer_sharded_adam_kernel<4><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 5: peer_sharded_adam_kernel<5><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 6: peer_sharded_adam_kernel<6><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 7: peer_sharded_adam_kernel<7><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 8: peer_sharded_adam_kernel<8><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    default: set_error("peer_sharded_adam: world=%d unsupported", world); return 1;
+  }
+  KP_LAUNCH_CHECK("peer_sharded_adam");
+  return 0;
+}
 
 extern "C" int kp_peer_alloc(int64_t data_bytes, void** arena, void* ipc_handle64) {
   KP_CHECK(data_bytes > 0 && arena != nullptr && ipc_handle64 != nullptr, "peer_alloc: bad arguments");

@@ -457,7 +457,8 @@ template <int B_MN>
 static bool launch_pipe(const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo, int64_t M, int N_total,
                         int R, int act, const float* aux, int64_t ldaux, int beta, cudaStream_t st) {
   if (getenv("KP_TC_PIPE") != nullptr && atoi(getenv("KP_TC_PIPE")) == 0) return false;
-  const int KS = R <= 32 ? 32 : 64;
+  int KS = R <= 32 ? 32 : 64;
+  if (getenv("KP_TC_KS") != nullptr && atoi(getenv("KP_TC_KS")) == 32) KS = 32;  // 32 KB stages: two CTAs per SM
   const int n_slices = (int)ceil_div(R, KS);
   // widest column slice whose weights fit beside the two A stages (227 KB of dynamic shared memory per CTA)
   const size_t a_bytes = (size_t)4 * 128 * KS * sizeof(float);
@@ -477,8 +478,12 @@ static bool launch_pipe(const float* A, int64_t lda, const float* W, int64_t ldw
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = ceil_div(M, 128);
-  // persistent CTAs: one per SM in total (shared memory allows a single CTA per SM), split over the column slices
-  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_tiles, sms / gy));
+  // persistent CTAs: as many per SM as shared memory (228 KB per SM, 1 KB reserved per CTA) and TMEM (512 columns) allow,
+  // split over the column slices
+  const int tmem_cols = P.N_pad <= 32 ? 64 : (P.N_pad <= 64 ? 128 : 256);
+  int per_sm = std::max(1, std::min((int)((228 * 1024) / (smem + 1024 + 64)), 512 / tmem_cols));
+  if (getenv("KP_TC_MAX_CTAS") != nullptr) per_sm = std::max(1, std::min(per_sm, atoi(getenv("KP_TC_MAX_CTAS"))));
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sms * per_sm / gy));
   if (KS == 32) {
     auto kern = tc_pipe_kernel<B_MN, 32>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -101,6 +101,68 @@ class GradBucket:
         return begin, end
 
 
+class ShardedAdamGroup:
+    """One parameter group under the sharded optimizer (csrc/peer_allreduce.cu::peer_sharded_adam_kernel): the group's
+    parameters are re-homed into a flat region of the peer arena that mirrors its GradBucket (same order, same dense
+    per-parameter layout), this rank keeps Adam's moments for its 1/world shard only, and ``step`` is ONE kernel that
+    reduce-scatters the gradients, updates the shard and all-gathers the new parameters over NVLink."""
+
+    def __init__(self, bucket: GradBucket, arena: "PeerArena") -> None:
+        assert bucket.arena is arena
+        self.bucket, self.arena = bucket, arena
+        total = bucket.flat.numel()
+        self.count = (total + 63) // 64 * 64  # the arena pads every region to 64 floats; the padding stays zero
+        self.param_flat, self.param_offset = arena.take(total)
+        off = 0
+        with torch.no_grad():
+            for p in bucket.params:
+                v = torch.as_strided(self.param_flat, p.shape, p.stride(), storage_offset=self.param_flat.storage_offset() + off)
+                v.copy_(p.data)
+                p.data = v  # the model now reads / the kernel now writes the arena copy
+                off += p.numel()
+        n4 = self.count // 4
+        self.lo4, self.hi4 = n4 * arena.rank // arena.world, n4 * (arena.rank + 1) // arena.world
+        shard = max(4, (self.hi4 - self.lo4) * 4)
+        dev = bucket.flat.device
+        self.exp_avg = torch.zeros(shard, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(shard, dtype=torch.float32, device=dev)
+
+    def step(self, lr: float, betas, eps: float, weight_decay: float, step: int, grad_scale: float,
+             hyper_dev: Optional[torch.Tensor] = None) -> None:
+        from ctypes import c_void_p
+
+        a = self.arena
+        a._lib.call("kp_peer_sharded_adam", a._ptrs, a.rank, a.world, int(self.bucket.arena_offset), int(self.param_offset),
+                    int(self.count), c_void_p(self.exp_avg.data_ptr()), c_void_p(self.exp_avg_sq.data_ptr()), float(lr),
+                    float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale),
+                    c_void_p(0 if hyper_dev is None else hyper_dev.data_ptr()), a.blocks,
+                    c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def shard_slice(self) -> Tuple[int, int]:
+        """[begin, end) float range of the group this rank owns."""
+        return self.lo4 * 4, self.hi4 * 4
+
+    def gather_moments(self, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Full-length (padded) exp_avg / exp_avg_sq assembled from all ranks' shards (checkpointing; not on the step path)."""
+        world = self.arena.world
+        n4 = self.count // 4
+        longest = max(n4 * (r + 1) // world - n4 * r // world for r in range(world)) * 4
+        out = []
+        for t in (self.exp_avg, self.exp_avg_sq):
+            mine = torch.zeros(longest, dtype=torch.float32, device=t.device)
+            mine[: (self.hi4 - self.lo4) * 4] = t[: (self.hi4 - self.lo4) * 4]
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            full = torch.cat([parts[r][: (n4 * (r + 1) // world - n4 * r // world) * 4] for r in range(world)])
+            out.append(full)
+        return out[0], out[1]
+
+    def scatter_moments(self, exp_avg_full: torch.Tensor, exp_avg_sq_full: torch.Tensor) -> None:
+        b, e = self.shard_slice()
+        self.exp_avg[: e - b].copy_(exp_avg_full[b:e])
+        self.exp_avg_sq[: e - b].copy_(exp_avg_sq_full[b:e])
+
+
 class PeerMemoryUnavailable(RuntimeError):
     """Raised (on every rank alike) when the peer-memory arenas cannot be set up on this node."""
 

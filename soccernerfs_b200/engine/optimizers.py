@@ -20,8 +20,10 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale: float = 1.0):
-        """``grad_scale`` multiplies every gradient before use (e.g. 1/GradScaler scale, or 1/world_size)."""
+    def step(self, closure=None, grad_scale: float = 1.0, use_device_hyper: bool = True):
+        """``grad_scale`` multiplies every gradient before use (e.g. 1/GradScaler scale, or 1/world_size).
+        ``use_device_hyper``: read lr / bias corrections from the group's ``hyper_dev`` device triple when it has one (the
+        graph-replayed step keeps them there); False = the host-side values of this call."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -50,7 +52,7 @@ class FusedAdam(torch.optim.Optimizer):
                                        self.state[p]["step"], grad_scale)
                 else:
                     ops.adam_multi_(ps, gs, ms, vs, group["lr"], b1, b2, group["eps"], group["weight_decay"], steps.pop(),
-                                    grad_scale, hyper_dev=group.get("hyper_dev"))
+                                    grad_scale, hyper_dev=group.get("hyper_dev") if use_device_hyper else None)
         return loss
 
 
@@ -78,9 +80,9 @@ class Optimizers:
         for opt in self.optimizers.values():
             opt.zero_grad(set_to_none=True)
 
-    def optimizer_step_all(self, grad_scale: float = 1.0) -> None:
+    def optimizer_step_all(self, grad_scale: float = 1.0, use_device_hyper: bool = True) -> None:
         for opt in self.optimizers.values():
-            opt.step(grad_scale=grad_scale)
+            opt.step(grad_scale=grad_scale, use_device_hyper=use_device_hyper)
 
     def scheduler_step_all(self, step: int = 0) -> None:
         for sch in self.schedulers.values():

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from ..cameras.rays import RayBundle
-from ..distributed import GradBucket, PeerArena, PeerMemoryUnavailable, world_info
+from ..distributed import GradBucket, PeerArena, PeerMemoryUnavailable, ShardedAdamGroup, world_info
 from ..models.kplanes import KPlanesModel, TrainingCallbackLocation, scale_dict
 from .optimizers import Optimizers, cosine_decay_factor
 
@@ -29,7 +29,8 @@ class TrainStep:
                  warm_up_end: int = 512, data_parallel: bool = False, use_cuda_graph: bool = False,
                  fuse_grad_accumulation: bool = True, overlap_branches: bool = True,
                  overlap_proposal_backward: Optional[bool] = None, allreduce_mode: str = "overlap",
-                 allreduce_backend: str = "peer", fuse_regularizers: bool = True) -> None:
+                 allreduce_backend: str = "peer", fuse_regularizers: bool = True,
+                 shard_optimizer: Optional[bool] = None) -> None:
         """``overlap_branches``: run the two branches of the step that do not depend on the main field's backward on
         their own CUDA streams (same arithmetic, same results): the plane regularisers (forward AND backward depend on
         the planes only) during the forward pass, and the back-propagation through the proposal networks (depends on
@@ -41,7 +42,12 @@ class TrainStep:
         "after-backward" (both buckets reduced on the main stream after the whole backward).
         ``allreduce_backend``: "peer" -- gradient buckets live in NVLink peer memory and are summed by our in-place
         kernel (csrc/peer_allreduce.cu); "nccl" -- ``torch.distributed.all_reduce``.  If the peer arenas cannot be set
-        up on this node (all ranks agree), a warning is printed and NCCL is used; ``self.allreduce_backend`` says which."""
+        up on this node (all ranks agree), a warning is printed and NCCL is used; ``self.allreduce_backend`` says which.
+        ``shard_optimizer`` (None = on whenever the peer backend is active): ZeRO-1-style step fused with its
+        collectives -- parameters also live in the peer arenas, every rank keeps Adam's moments for 1/world of each
+        group only, and ONE kernel per group reduce-scatters the gradients, updates the owned shard and all-gathers the
+        new parameters (``distributed.ShardedAdamGroup``).  Same NVLink bytes as the all-reduce; Adam's HBM traffic and
+        optimizer memory drop by 1/world and the reduced gradient is never materialised."""
         self.model = model
         self.max_steps, self.base_lr, self.warm_up_end = max_steps, lr, warm_up_end
         self.optimizers = Optimizers(model.get_param_groups(), lr=lr, eps=eps, warm_up_end=warm_up_end, max_steps=max_steps)
@@ -70,6 +76,8 @@ class TrainStep:
             if self.reduce_grads and on_cuda and allreduce_backend == "peer":
                 groups = model.get_param_groups()
                 n = sum((sum(p.numel() for p in ps if p.requires_grad) + 63) // 64 * 64 for ps in groups.values())
+                if shard_optimizer is None or shard_optimizer:
+                    n *= 2  # the parameters get a region of their own next to the gradients
                 try:
                     arena = PeerArena(n, blocks=int(os.environ.get("KP_PEER_BLOCKS", "32")))
                 except PeerMemoryUnavailable as e:
@@ -78,6 +86,12 @@ class TrainStep:
             self.arena = arena
             self.allreduce_backend = "peer" if arena is not None else "nccl"
             self.buckets = {name: GradBucket(ps, arena=arena) for name, ps in model.get_param_groups().items()}
+        self.sharded: Dict[str, ShardedAdamGroup] = {}
+        self._last_sharded_lr: Dict[str, float] = {}
+        if self.arena is not None and (shard_optimizer is None or shard_optimizer):
+            self.sharded = {name: ShardedAdamGroup(b, self.arena) for name, b in self.buckets.items()}
+        elif shard_optimizer:
+            raise RuntimeError("shard_optimizer=True needs the peer-memory backend (data_parallel, world > 1, CUDA IPC)")
         on_cuda = next(model.parameters()).is_cuda
         self.overlap = bool(overlap_branches and fuse_grad_accumulation and on_cuda)
         # fused regulariser sweep (values + gradient written into the sinks, no memset of the planes): ids of the planes
@@ -111,6 +125,7 @@ class TrainStep:
         self._prop_stream = torch.cuda.Stream() if (self.overlap and overlap_proposal_backward) else None
         model.proposal_sampler.side_stream = self._prop_stream
         self.use_cuda_graph = use_cuda_graph
+        self._in_graph_body = False
         self.health_check_every = 1000  # steps between polls of the peer all-reduce's error word (a device sync)
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self._graph_out: Dict[bool, Dict[str, torch.Tensor]] = {}
@@ -175,7 +190,23 @@ class TrainStep:
                 fields.all_reduce()
                 prop.all_reduce()
                 grad_scale = 1.0 / self.world
-                self.optimizers.optimizer_step_all(grad_scale=grad_scale)
+                self.optimizers.optimizer_step_all(grad_scale=grad_scale, use_device_hyper=self._in_graph_body)
+                return self._finish(loss_dict, loss, metrics)
+            if self.sharded:
+                # reduce-scatter + Adam on the owned shard + all-gather of the new parameters: one kernel per group on the
+                # communication stream.  The field group's starts as soon as the field's scatter is in the stream (its
+                # in-kernel start barrier also guarantees that no rank still reads the field's parameters) and overlaps
+                # the back-propagation through the proposal networks.
+                if self._field_ready is not None:
+                    comm.wait_event(self._field_ready)
+                else:
+                    comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    self._sharded_step("fields")
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    self._sharded_step("proposal_networks")
+                main.wait_stream(comm)
                 return self._finish(loss_dict, loss, metrics)
             if self._first_span is not None and len(self._scale_ready) == n_scales:
                 # finest scale (most of the bytes) while the other scales are still being scattered, the rest of the
@@ -201,8 +232,15 @@ class TrainStep:
                 prop.all_reduce()
             main.wait_stream(comm)  # join
             grad_scale = 1.0 / self.world
-        self.optimizers.optimizer_step_all(grad_scale=grad_scale)
+        self.optimizers.optimizer_step_all(grad_scale=grad_scale, use_device_hyper=self._in_graph_body)
         return self._finish(loss_dict, loss, metrics)
+
+    def _sharded_step(self, name: str) -> None:
+        opt = self.optimizers.optimizers[name]
+        g = opt.param_groups[0]
+        self._last_sharded_lr[name] = float(g["lr"])
+        self.sharded[name].step(g["lr"], g["betas"], g["eps"], g["weight_decay"], self.step + 1, 1.0 / self.world,
+                                hyper_dev=g.get("hyper_dev") if self._in_graph_body else None)
 
     @staticmethod
     def _finish(loss_dict, loss, metrics):
@@ -259,6 +297,12 @@ class TrainStep:
             finally:
                 for p in self.model.parameters():
                     p.grad = None
+                if self.sharded:  # the parameters live in the arena: move them back to ordinary tensors before it is freed
+                    with torch.no_grad():
+                        for grp in self.sharded.values():
+                            for p in grp.bucket.params:
+                                p.data = p.data.clone(memory_format=torch.preserve_format)
+                    self.sharded = {}
                 self.buckets = {}
                 self.arena.close()
                 self.arena = None
@@ -296,6 +340,17 @@ class TrainStep:
             for st in sd["state"].values():
                 st["step"] = self.step
             sd["param_groups"] = [{k: v for k, v in g.items() if k != "hyper_dev"} for g in sd["param_groups"]]
+            if name in self.sharded:  # assemble the full moments from the ranks' shards (a collective: call on every rank)
+                grp = self.sharded[name]
+                m_full, v_full = grp.gather_moments()
+                index = {id(p): i for i, p in enumerate(opt.param_groups[0]["params"])}
+                off = 0
+                for p in grp.bucket.params:
+                    sd["state"][index[id(p)]] = {
+                        "step": self.step,
+                        "exp_avg": torch.as_strided(m_full, p.shape, p.stride(), off).clone(memory_format=torch.preserve_format),
+                        "exp_avg_sq": torch.as_strided(v_full, p.shape, p.stride(), off).clone(memory_format=torch.preserve_format)}
+                    off += p.numel()
             optimizers[name] = sd
         return {
             "step": self.step,
@@ -315,6 +370,19 @@ class TrainStep:
             for g, h in zip(opt.param_groups, keep):
                 if h is not None:
                     g["hyper_dev"] = h
+            if name in self.sharded:
+                grp = self.sharded[name]
+                m_full = torch.zeros(grp.count, dtype=torch.float32, device=grp.exp_avg.device)
+                v_full = torch.zeros_like(m_full)
+                off = 0
+                for p in grp.bucket.params:
+                    st = opt.state.get(p)
+                    if st:
+                        torch.as_strided(m_full, p.shape, p.stride(), off).copy_(st["exp_avg"])
+                        torch.as_strided(v_full, p.shape, p.stride(), off).copy_(st["exp_avg_sq"])
+                    off += p.numel()
+                grp.scatter_moments(m_full, v_full)
+                opt.state.clear()  # the shard owns the moments
         for name, sch in self.optimizers.schedulers.items():
             if name in state.get("schedulers", {}):
                 sch.load_state_dict(state["schedulers"][name])
@@ -379,6 +447,13 @@ class TrainStep:
 
     def _graph_body(self):
         s = self._static
+        self._in_graph_body = True
+        try:
+            return self._graph_body_inner(s)
+        finally:
+            self._in_graph_body = False
+
+    def _graph_body_inner(self, s):
         self._device_scalars()
         rb = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"], times=s["times"])
         out = self._iteration(rb, {"image": s["image"]})

@@ -104,14 +104,19 @@ def main() -> None:
     gold = load_golden("model_tiny")
     mp = load_tiny_model(gold)
     runs = {}
-    for backend, graph in (("nccl", False), ("nccl-again", False), ("nccl", True), ("peer", False), ("peer", True)):
+    # "peer" = in-place all-reduce + replicated Adam; "peer-sharded" = reduce-scatter + Adam on the shard + all-gather in
+    # one kernel (the default under the peer backend)
+    for backend, graph in (("nccl", False), ("nccl-again", False), ("nccl", True), ("peer", False), ("peer", True),
+                           ("peer-sharded", False), ("peer-sharded", True)):
         model = build_model("tiny", mp, gold["aabb"], "cuda")
         model.config.background_color_train = "black"
         model.proposal_sampler.initial_sampler.train_stratified = False
         model.proposal_sampler.pdf_sampler.train_stratified = False
         step = TrainStep(model, max_steps=100, warm_up_end=4, data_parallel=True, use_cuda_graph=graph,
-                         allreduce_backend=backend.split("-")[0], allreduce_mode="overlap-per-scale" if graph else "overlap")
+                         allreduce_backend=backend.split("-")[0], allreduce_mode="overlap-per-scale" if graph else "overlap",
+                         shard_optimizer=backend == "peer-sharded")
         assert step.allreduce_backend == backend.split("-")[0]
+        assert bool(step.sharded) == (backend == "peer-sharded")
         n_rays = gold["origins"].shape[0]
         lo, hi = rank * n_rays // world, (rank + 1) * n_rays // world  # every rank trains on its own rays
         losses = []
@@ -127,6 +132,18 @@ def main() -> None:
             q = p.clone()
             dist.broadcast(q, src=0)
             assert torch.equal(p, q), "replicas diverged"
+        if backend == "peer-sharded" and not graph:  # checkpoint round trip of the sharded moments (a collective)
+            sd = step.state_dict()
+            st = sd["optimizers"]["fields"]["state"]
+            assert len(st) > 0 and all(v["exp_avg"].shape == v["exp_avg_sq"].shape for v in st.values())
+            before = {k: (g.exp_avg.clone(), g.exp_avg_sq.clone()) for k, g in step.sharded.items()}
+            for g in step.sharded.values():
+                g.exp_avg.zero_()
+                g.exp_avg_sq.zero_()
+            step.load_state_dict(sd)
+            for k, g in step.sharded.items():
+                assert torch.equal(g.exp_avg, before[k][0]) and torch.equal(g.exp_avg_sq, before[k][1]), k
+        step.close()
 
     def param_err(a_params, b_params):
         return max(float((a - b).norm() / (a.norm() + 1e-12)) for a, b in zip(a_params, b_params) if a.numel())
