@@ -17,7 +17,9 @@
  *               aabb HOST float[6] = min xyz, max xyz.  Sample position = o + d*(start+end)/2
  *               (NS/cameras/rays.py:54) normalised by the aabb (NS/data/scene_box.py:56-66) to
  *               [0,1] (norm_mode 0: KPlanesDensityField quirk, kplanes_field.py:439-440) or to
- *               [-1,1] (norm_mode 1: KPlanesField, kplanes_field.py:283-284); time -> t*2-1.
+ *               [-1,1] (norm_mode 1: KPlanesField, kplanes_field.py:283-284), or contracted with
+ *               SceneContraction(order=inf) and halved (norm_mode 2: bounded=False, kplanes_field.py:278-280,
+ *               NS/field_components/spatial_distortions.py:42-88; aabb unused); time -> t*2-1.
  *   point form  pts[M,D] already in grid_sample's [-1,1] convention (D = 3 or 4).
  */
 #ifndef KPLANES_B200_H_
@@ -47,7 +49,7 @@ typedef struct KpPoints {
   const float* times;      /* [N] or NULL */
   int32_t D;               /* 3 (static) or 4 (dynamic) */
   int32_t S;               /* samples per ray (ray form) */
-  int32_t norm_mode;       /* 0: [0,1], 1: [-1,1] */
+  int32_t norm_mode;       /* 0: aabb -> [0,1], 1: aabb -> [-1,1], 2: SceneContraction(L_inf) / 2 (unbounded scenes) */
   float aabb[6];
 } KpPoints;
 

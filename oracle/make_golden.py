@@ -353,6 +353,77 @@ def gen_model(R):
     save("model_tiny", **arrs)
 
 
+def gen_field_variants(R):
+    """Non-default field branches pinned to the reference's own modules: (a) unbounded scene = SceneContraction(order=inf)
+    in KPlanesField and KPlanesDensityField (kplanes_field.py:278-280, 436-438); (b) linear_decoder=True = learned
+    colour basis + linear density (kplanes_field.py:219-246, 303-304, 349-354).  Outputs and plane / weight gradients."""
+    from nerfstudio.field_components.spatial_distortions import SceneContraction
+
+    g = torch.Generator().manual_seed(321)
+    res, ms, c = (12, 10, 14, 5), (1, 2), 8
+    n, s = 96, 6
+    aabb = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]])
+    origins = (torch.rand(n, 3, generator=g) - 0.5) * 1.6
+    d = torch.randn(n, 3, generator=g)
+    directions = d / d.norm(dim=-1, keepdim=True)
+    bins = torch.sort(torch.rand(n, s + 1, generator=g), -1).values * 5.0  # up to 5 units away: well outside the unit cube
+    times = torch.rand(n, 1, generator=g)
+    rb = R.rays.RayBundle(origins=origins, directions=directions, pixel_area=torch.ones(n, 1), times=times,
+                          nears=torch.zeros(n, 1), fars=torch.full((n, 1), 5.0))
+    rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+    arrs = dict(aabb=aabb, origins=origins, directions=directions, bins=bins, times=times)
+
+    def noisy_planes(field_grids):
+        with torch.no_grad():
+            for gs in field_grids:
+                for p_ in gs:
+                    p_.add_(0.3 * torch.randn(p_.shape, generator=g))
+
+    # (a) contraction
+    f = R.kplanes_field.KPlanesField(aabb, spacetime_resolution=res, feat_dim=c, multiscale_res=ms, concat_features_across_scales=True,
+                                     linear_decoder=False, spatial_distortion=SceneContraction(order=float("inf")))
+    noisy_planes(f.grids)
+    out = f(rs)
+    dens, rgb = out[R.kplanes_field.FieldHeadNames.DENSITY], out[R.kplanes_field.FieldHeadNames.RGB]
+    gd, gr = torch.randn(dens.shape, generator=g), torch.randn(rgb.shape, generator=g)
+    ((dens * gd).sum() + (rgb * gr).sum()).backward()
+    arrs.update(con_density=dens, con_rgb=rgb, con_gd=gd, con_gr=gr)
+    for i, gs in enumerate(f.grids):
+        for j, p_ in enumerate(gs):
+            arrs[f"con_grid_{i}_{j}"], arrs[f"con_ggrid_{i}_{j}"] = p_.detach(), p_.grad
+    for name, net in (("sigma", f.sigma_net), ("color", f.color_net)):
+        for i, lin in enumerate(net.layers):
+            arrs[f"con_{name}_w{i}"], arrs[f"con_{name}_gw{i}"] = lin.weight.detach(), lin.weight.grad
+    df = R.kplanes_field.KPlanesDensityField(aabb, resolution=[16, 14, 18, 5], feature_dim=c, linear_decoder=False,
+                                             spatial_distortion=SceneContraction(order=float("inf")))
+    noisy_planes([df.grids])
+    dd, _ = df.get_density(rs)
+    gdd = torch.randn(dd.shape, generator=g)
+    (dd * gdd).sum().backward()
+    arrs.update(pcon_density=dd, pcon_gd=gdd)
+    for j, p_ in enumerate(df.grids):
+        arrs[f"pcon_grid_{j}"], arrs[f"pcon_ggrid_{j}"] = p_.detach(), p_.grad
+    for i, lin in enumerate(df.sigma_net.layers):
+        arrs[f"pcon_w{i}"], arrs[f"pcon_gw{i}"] = lin.weight.detach(), lin.weight.grad
+
+    # (b) linear decoder (bounded)
+    lf = R.kplanes_field.KPlanesField(aabb * 3.0, spacetime_resolution=res, feat_dim=c, multiscale_res=ms,
+                                      concat_features_across_scales=True, linear_decoder=True, linear_decoder_layers=2)
+    noisy_planes(lf.grids)
+    out = lf(rs)
+    dens, rgb = out[R.kplanes_field.FieldHeadNames.DENSITY], out[R.kplanes_field.FieldHeadNames.RGB]
+    gd, gr = torch.randn(dens.shape, generator=g), torch.randn(rgb.shape, generator=g)
+    ((dens * gd).sum() + (rgb * gr).sum()).backward()
+    arrs.update(lin_aabb=aabb * 3.0, lin_density=dens, lin_rgb=rgb, lin_gd=gd, lin_gr=gr)
+    for i, gs in enumerate(lf.grids):
+        for j, p_ in enumerate(gs):
+            arrs[f"lin_grid_{i}_{j}"], arrs[f"lin_ggrid_{i}_{j}"] = p_.detach(), p_.grad
+    for name, net in (("sigma", lf.sigma_net), ("basis", lf.color_basis)):
+        for i, lin in enumerate(net.layers):
+            arrs[f"lin_{name}_w{i}"], arrs[f"lin_{name}_gw{i}"] = lin.weight.detach(), lin.weight.grad
+    save("field_variants", **arrs)
+
+
 def main():
     torch.set_num_threads(1)
     R = load_reference()
@@ -364,7 +435,7 @@ def main():
     gen_importance(R)
     gen_raygen(R)
     gen_samplers_cfg4(R)
-
+    gen_field_variants(R)
 
 
 def _reference_method(path, class_name, method_name, extra_globals):

@@ -98,6 +98,23 @@ __device__ __forceinline__ void load_point(const KpPoints& P, int64_t m, float p
   }
   const int64_t n = m / P.S;
   const float t = __fadd_rn(P.starts[m], P.ends[m]);
+  if (P.norm_mode == 2) {
+    // unbounded scene: SceneContraction(order=inf)(pos) / 2  (kplanes_field.py:278-280 / :436-438,
+    // NS/field_components/spatial_distortions.py:66-71): x if |x|_inf < 1 else (2 - 1/|x|) (x/|x|), then [-2,2] -> [-1,1]
+    float pos[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      pos[d] = __fadd_rn(P.origins[n * 3 + d], __fmul_rn(__fmul_rn(P.directions[n * 3 + d], t), 0.5f));
+    const float mag = fmaxf(fabsf(pos[0]), fmaxf(fabsf(pos[1]), fabsf(pos[2])));
+    const float k = __fsub_rn(2.f, __fdiv_rn(1.f, mag));
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float c = mag < 1.f ? pos[d] : __fmul_rn(k, __fdiv_rn(pos[d], mag));
+      pt[d] = __fmul_rn(c, 0.5f);
+    }
+    pt[3] = (P.D == 4 && P.times != nullptr) ? __fsub_rn(__fmul_rn(P.times[n], 2.f), 1.f) : 0.f;
+    return;
+  }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     float v = __fmul_rn(__fmul_rn(P.directions[n * 3 + d], t), 0.5f);  // x/2 == x*0.5 exactly

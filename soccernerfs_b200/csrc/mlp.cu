@@ -122,7 +122,7 @@ static void gemm_dx(const float* dY, int lddy, const float* W, int ldw, float* d
 // dW[N,K] += dY[M,N]^T X[M,K]   (reduction over M split across blockIdx.z)
 static void gemm_dw(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int64_t M, int N, int K,
                     cudaStream_t st) {
-  if (N <= 256 && K <= 256) {  // (layers wider than one launch's operand tiles are cut into blocks of dW there)
+  if (N <= 1024 && K <= 1024) {  // (layers wider than one launch's operand tiles are cut into blocks of dW there)
     kp_tc_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, M, N, K, st);
     return;
   }

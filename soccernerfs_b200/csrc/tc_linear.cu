@@ -526,7 +526,9 @@ static bool tc_single(int N, int K) { return N >= 1 && N <= 128 && K >= 1 && K <
 // Which layers the tensor-core path covers.  Layers wider than one launch's operand tiles (the 192 -> 128 first layer
 // of the 32x config, NS/configs/method_configs.py:523-524) are cut into slices of <= 64 output / input columns and
 // <= 128 reduction columns, each slice one launch on a sub-matrix (pointer offset + leading dimension).
-extern "C" int kp_tc_supported(int N, int K) { return (N >= 1 && N <= 256 && K >= 1 && K <= 256 && (K % 4 == 0 || tc_single(N, K))) ? 1 : 0; }
+extern "C" int kp_tc_supported(int N, int K) {
+  return (N >= 1 && N <= 1024 && K >= 1 && K <= 1024 && (tc_single(N, K) || K <= 32 || K % 4 == 0)) ? 1 : 0;
+}
 
 extern "C" int kp_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t M,
                                 int N, int K, int act, void* stream) {
@@ -588,7 +590,7 @@ extern "C" int kp_tc_linear_bwd_data(const float* dY, int64_t lddy, const float*
 extern "C" int kp_tc_linear_bwd_weight(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t lddw,
                                        int64_t M, int N, int K, void* stream) {
   if (M == 0) return 0;
-  KP_CHECK(dY && X && dW && N >= 1 && N <= 256 && K >= 1 && K <= 256, "tc_linear_bwd_weight: unsupported shape N=%d K=%d", N, K);
+  KP_CHECK(dY && X && dW && N >= 1 && N <= 1024 && K >= 1 && K <= 1024, "tc_linear_bwd_weight: unsupported shape N=%d K=%d", N, K);
   cudaStream_t st = as_stream(stream);
   // one launch covers pad(N) + pad(K) <= 192 operand columns; wider layers are cut into [<=128 x <=64] blocks of dW
   const bool single = N <= 128 && K <= 128 && pad_dim(N) + pad_dim(K) <= 192;

@@ -132,10 +132,13 @@ class ShardedAdamGroup:
         from ctypes import c_void_p
 
         a = self.arena
+        # a group of hundreds of MB needs more bytes in flight over NVLink than the 32 blocks that suit a 150 MB group
+        # sharing the SMs with the proposal networks' backward
+        blocks = a.blocks if self.count * 4 < (512 << 20) else max(a.blocks, 128)
         a._lib.call("kp_peer_sharded_adam", a._ptrs, a.rank, a.world, int(self.bucket.arena_offset), int(self.param_offset),
                     int(self.count), c_void_p(self.exp_avg.data_ptr()), c_void_p(self.exp_avg_sq.data_ptr()), float(lr),
                     float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale),
-                    c_void_p(0 if hyper_dev is None else hyper_dev.data_ptr()), a.blocks,
+                    c_void_p(0 if hyper_dev is None else hyper_dev.data_ptr()), blocks,
                     c_void_p(torch.cuda.current_stream().cuda_stream))
 
     def shard_slice(self) -> Tuple[int, int]:

@@ -21,6 +21,7 @@ from torch.nn.parameter import Parameter
 from .. import ops
 from ..cameras.rays import Frustums, RaySamples
 from ..data.scene_box import SceneBox
+from ..field_components.embedding import Embedding
 from .base_field import Field, FieldHeadNames
 
 TIME_PLANES = (2, 4, 5)  # XT, YT, ZT in combinations(range(4), 2) order (kplanes_field.py:62-64)
@@ -105,6 +106,17 @@ def _ray_form(ray_samples: RaySamples):
             fr.starts[..., 0].reshape(-1, s), fr.ends[..., 0].reshape(-1, s), times)
 
 
+def _contraction_mode(spatial_distortion) -> bool:
+    """True if ``spatial_distortion`` is the L-infinity SceneContraction the kernels evaluate in place (norm_mode 2)."""
+    if spatial_distortion is None:
+        return False
+    order = getattr(spatial_distortion, "order", "missing")
+    if type(spatial_distortion).__name__ != "SceneContraction" or order != float("inf"):
+        raise NotImplementedError("only SceneContraction(order=float('inf')) -- what KPlanesModel(bounded=False) uses, "
+                                  "NS/models/kplanes.py:203-206 -- is evaluated by the kernels")
+    return True
+
+
 class _AabbHostMixin:
     """Keeps a host copy of the aabb so kernel launches never sync on a device->host read."""
 
@@ -141,27 +153,25 @@ class KPlanesField(Field, _AabbHostMixin):
         freeze_space_planes: bool = False,
     ) -> None:
         super().__init__()
-        # Out-of-scope branches of the reference: fail loudly instead of falling back.
-        if linear_decoder:
-            raise NotImplementedError("KPlanesField(linear_decoder=True) is not built yet (kplanes_field.py:219-246)")
-        if spatial_distortion is not None:
-            raise NotImplementedError("SceneContraction (bounded=False) is not built yet (kplanes_field.py:278-280)")
-        if use_appearance_embedding:
-            raise NotImplementedError("appearance embeddings are not built yet (kplanes_field.py:326-345)")
-        if sigma_net_layers != 1 or rgb_net_layers != 2:
+        if not linear_decoder and (sigma_net_layers != 1 or rgb_net_layers != 2):
             raise NotImplementedError("decoder kernels are built for sigma_net_layers=1, rgb_net_layers=2")
         self.aabb = Parameter(aabb, requires_grad=False)
-        self.spatial_distortion = None
+        self.spatial_distortion = spatial_distortion
+        self._contract = _contraction_mode(spatial_distortion)
         self.multiscale_res_multipliers: Sequence[int] = multiscale_res or [1]
         self.concat_features_across_scales = concat_features_across_scales
-        self.linear_decoder = False
+        self.linear_decoder = linear_decoder
         self.has_time_planes = len(spacetime_resolution) == 4
         self.feature_dim = feat_dim * len(self.multiscale_res_multipliers) if concat_features_across_scales else feat_dim
         self.freeze_time_planes = freeze_time_planes
         self.freeze_space_planes = freeze_space_planes
-        self.use_appearance_embedding = False
+        self.use_appearance_embedding = use_appearance_embedding
         self.appearance_embedding = None
         self.appearance_embedding_dim = 0
+        if use_appearance_embedding:  # normal_(0, 1) initialised per-image codes (kplanes_field.py:196-203)
+            assert num_images is not None
+            self.appearance_embedding_dim = appearance_dim
+            self.appearance_embedding = Embedding(num_images, self.appearance_embedding_dim)
         self.disable_viewing_dependent = disable_viewing_dependent
 
         self.grids = nn.ModuleList()
@@ -171,19 +181,30 @@ class KPlanesField(Field, _AabbHostMixin):
                 resolution.append(spacetime_resolution[3])
             self.grids.append(init_kplanes_field(out_dim=feat_dim, reso=resolution))
 
-        self.geo_feat_dim = 15
-        self.sigma_net = FusedMLP(self.feature_dim, self.geo_feat_dim + 1, sigma_net_hidden_dim, sigma_net_layers)
-        self.in_dim_color = self.geo_feat_dim + (0 if disable_viewing_dependent else 16)
-        self.color_net = FusedMLP(self.in_dim_color, 3, rgb_net_hidden_dim, rgb_net_layers, output_activation="Sigmoid")
+        if self.linear_decoder:
+            # learned colour basis instead of SH + MLP (kplanes_field.py:219-246): directions (+ appearance code) ->
+            # 3 * feature_dim weights that combine the plane features into rgb; density is a linear map of the features
+            assert linear_decoder_layers is not None
+            self.color_basis = FusedMLP(3 + self.appearance_embedding_dim, 3 * self.feature_dim, 128, linear_decoder_layers)
+            self.sigma_net = FusedMLP(self.feature_dim, 1, 128, 0, activation="None")
+        else:
+            self.geo_feat_dim = 15
+            self.sigma_net = FusedMLP(self.feature_dim, self.geo_feat_dim + 1, sigma_net_hidden_dim, sigma_net_layers)
+            self.in_dim_color = self.geo_feat_dim + self.appearance_embedding_dim + (0 if disable_viewing_dependent else 16)
+            self.color_net = FusedMLP(self.in_dim_color, 3, rgb_net_hidden_dim, rgb_net_layers, output_activation="Sigmoid")
 
     # -- helpers ---------------------------------------------------------------------------------------
     def _points(self, ray_samples: RaySamples) -> ops.Points:
         rf = _ray_form(ray_samples)
         if rf is not None:
             o, d, st, en, t = rf
-            return ops.points_from_rays(o, d, st, en, t, self._aabb6(), norm_mode=1, dynamic=self.has_time_planes and t is not None)
+            return ops.points_from_rays(o, d, st, en, t, self._aabb6(), norm_mode=2 if self._contract else 1,
+                                        dynamic=self.has_time_planes and t is not None)
         positions = ray_samples.frustums.get_positions()
-        positions = SceneBox.get_normalized_positions(positions, self.aabb) * 2.0 - 1.0
+        if self._contract:
+            positions = self.spatial_distortion(positions) / 2.0  # from [-2, 2] to [-1, 1]
+        else:
+            positions = SceneBox.get_normalized_positions(positions, self.aabb) * 2.0 - 1.0
         if self.has_time_planes and ray_samples.times is not None:
             positions = torch.cat((positions, ray_samples.times * 2 - 1), dim=-1)
         return ops.points_from_pts(positions.reshape(-1, positions.shape[-1]))
@@ -206,12 +227,68 @@ class KPlanesField(Field, _AabbHostMixin):
         feats = ops.hexplane_features(ms, points, self.concat_features_across_scales,
                                       _use_mask(len(ms[0]), self.freeze_time_planes),
                                       post_backward=getattr(self, "_kp_post_backward", None))
+        if self.linear_decoder:  # density = trunc_exp(linear(features)); the features themselves feed the colour basis
+            density = ops.trunc_exp(ops.linear(feats, self.sigma_net.weights[0]))
+            return density.view(*batch, 1), feats
         o, density = ops.sigma_net(feats, self.sigma_net.weights[0], self.sigma_net.weights[1])
         return density.view(*batch, 1), o[:, : self.geo_feat_dim]
+
+    def _appearance(self, ray_samples: RaySamples, n_rays: int, n_samples: int) -> torch.Tensor:
+        """[M, dim]: every ray's per-image code repeated over its samples in training, the mean code in evaluation
+        (kplanes_field.py:326-345).  NOTE: the reference's own expansion (``view(-1, 1, dim).expand(n_rays, n_samples, -1)``
+        of an already per-sample lookup) raises for more than one sample per ray, so this branch -- off in every preset --
+        cannot be pinned against it; it is implemented per its evident intent (one code per ray = per training image)."""
+        dim = self.appearance_embedding_dim
+        if self.training:
+            assert ray_samples.camera_indices is not None
+            ci = ray_samples.camera_indices[..., 0]
+            if ci.dim() > 1:  # [N, S] broadcast of the bundle's per-ray indices
+                ci = ci.reshape(n_rays, -1)[:, 0]
+            emb = self.appearance_embedding(ci.reshape(n_rays))
+        else:
+            emb = self.appearance_embedding.mean(dim=0)[None, :].expand(n_rays, dim)
+        return emb[:, None, :].expand(n_rays, n_samples, dim).reshape(-1, dim)
+
+    def _get_outputs_composed(self, ray_samples: RaySamples, density_embedding: torch.Tensor) -> torch.Tensor:
+        """The non-default colour branches (linear decoder / appearance embedding), composed from the tensor-core dense
+        layer (ops.linear) exactly as kplanes_field.py:314-358 composes them from tcnn networks."""
+        batch = ray_samples.frustums.shape
+        n_samples = batch[-1]
+        n_rays = 1
+        for b in batch[:-1]:
+            n_rays *= int(b)
+        directions = ray_samples.frustums.directions.reshape(-1, 3)
+        if self.linear_decoder or self.disable_viewing_dependent:
+            color_features = [density_embedding]
+        else:
+            color_features = [ops.sh4(get_normalized_directions(directions)), density_embedding]
+        if self.use_appearance_embedding:
+            emb = self._appearance(ray_samples, n_rays, n_samples)
+            if self.linear_decoder:
+                directions = torch.cat((directions, emb), dim=-1)
+            else:
+                color_features.append(emb)
+        color_features = torch.cat(color_features, dim=-1)
+        if self.linear_decoder:
+            x = directions
+            ws = self.color_basis.weights
+            for i, w in enumerate(ws):
+                x = ops.linear(x, w, "relu" if i + 1 < len(ws) else "none")
+            basis_values = x.view(color_features.shape[0], 3, -1)  # [M, 3, feature_dim]
+            rgb = torch.sigmoid(torch.sum(color_features[:, None, :] * basis_values, dim=-1))
+        else:
+            x = color_features
+            ws = self.color_net.weights
+            for i, w in enumerate(ws):
+                x = ops.linear(x, w, "relu" if i + 1 < len(ws) else "sigmoid")
+            rgb = x
+        return rgb.view(*batch, 3)
 
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None) -> torch.Tensor:
         """-> rgb [N,S,3] (bare tensor, like kplanes_field.py:314-358)."""
         assert density_embedding is not None
+        if self.linear_decoder or self.use_appearance_embedding:
+            return self._get_outputs_composed(ray_samples, density_embedding)
         batch = ray_samples.frustums.shape
         n_samples = batch[-1]
         w3, w4, w5 = self.color_net.weights
@@ -236,6 +313,8 @@ class KPlanesField(Field, _AabbHostMixin):
     def _forward_fused(self, ray_samples: RaySamples):
         """get_density + get_outputs with both decoders in ONE tensor-core kernel (same numbers as the two-call path);
         None when the decoder shape is not covered (e.g. the 192 -> 128 sigma net of the 32x config)."""
+        if self.linear_decoder or self.use_appearance_embedding:
+            return None
         w1, w2 = self.sigma_net.weights
         w3, w4, w5 = self.color_net.weights
         if not ops.decoder_fused_supported(self.feature_dim, w1.shape[0], w3.shape[0]):
@@ -266,10 +345,9 @@ class KPlanesDensityField(Field, _AabbHostMixin):
     def __init__(self, aabb, resolution, feature_dim, spatial_distortion=None, linear_decoder: bool = True,
                  freeze_time_planes: bool = False, freeze_space_planes: bool = False) -> None:
         super().__init__()
-        if spatial_distortion is not None:
-            raise NotImplementedError("SceneContraction (bounded=False) is not built yet (kplanes_field.py:436-438)")
         self.aabb = Parameter(aabb, requires_grad=False)
-        self.spatial_distortion = None
+        self.spatial_distortion = spatial_distortion
+        self._contract = _contraction_mode(spatial_distortion)
         self.has_time_planes = len(resolution) == 4
         self.freeze_time_planes = freeze_time_planes
         self.freeze_space_planes = freeze_space_planes
@@ -301,9 +379,14 @@ class KPlanesDensityField(Field, _AabbHostMixin):
         rf = _ray_form(ray_samples)
         if rf is not None:
             o, d, st, en, t = rf
-            points = ops.points_from_rays(o, d, st, en, t, self._aabb6(), norm_mode=0, dynamic=self.has_time_planes and t is not None)
+            points = ops.points_from_rays(o, d, st, en, t, self._aabb6(), norm_mode=2 if self._contract else 0,
+                                          dynamic=self.has_time_planes and t is not None)
         else:
-            positions = SceneBox.get_normalized_positions(ray_samples.frustums.get_positions(), self.aabb)
+            positions = ray_samples.frustums.get_positions()
+            if self._contract:
+                positions = self.spatial_distortion(positions) / 2.0  # from [-2, 2] to [-1, 1] (kplanes_field.py:436-438)
+            else:
+                positions = SceneBox.get_normalized_positions(positions, self.aabb)
             if self.has_time_planes and ray_samples.times is not None:
                 positions = torch.cat((positions, ray_samples.times * 2 - 1), dim=-1)
             points = ops.points_from_pts(positions.reshape(-1, positions.shape[-1]))

@@ -18,6 +18,7 @@ from torch.nn import Parameter
 
 from .. import ops
 from ..cameras.rays import RayBundle
+from ..field_components.spatial_distortions import SceneContraction
 from ..fields.base_field import FieldHeadNames
 from ..fields.kplanes_field import KPlanesDensityField, KPlanesField
 from ..model_components.losses import (
@@ -155,8 +156,8 @@ class KPlanesModel(Model):
     def populate_modules(self):
         super().populate_modules()
         cfg = self.config
-        if not cfg.bounded:
-            raise NotImplementedError("bounded=False (SceneContraction + NearFarCollider sampling) is not built yet")
+        # unbounded scenes: L-infinity scene contraction (kplanes.py:203-206), evaluated inside the field kernels
+        scene_contraction = None if cfg.bounded else SceneContraction(order=float("inf"))
         self.field = KPlanesField(
             self.scene_box.aabb,
             feat_dim=cfg.feature_dim,
@@ -165,7 +166,7 @@ class KPlanesModel(Model):
             multiscale_res=cfg.multiscale_res,
             use_appearance_embedding=cfg.use_appearance_embedding,
             appearance_dim=cfg.appearance_embedding_dim,
-            spatial_distortion=None,
+            spatial_distortion=scene_contraction,
             linear_decoder=cfg.linear_decoder,
             linear_decoder_layers=cfg.linear_decoder_layers,
             num_images=self.num_train_data,
@@ -182,7 +183,7 @@ class KPlanesModel(Model):
         self.density_fns = []
         num_prop_nets = cfg.num_proposal_iterations
         self.proposal_networks = torch.nn.ModuleList()
-        common = dict(spatial_distortion=None, linear_decoder=cfg.linear_decoder, freeze_time_planes=cfg.freeze_time_planes,
+        common = dict(spatial_distortion=scene_contraction, linear_decoder=cfg.linear_decoder, freeze_time_planes=cfg.freeze_time_planes,
                       freeze_space_planes=cfg.freeze_space_planes)
         if cfg.use_same_proposal_network:
             assert len(cfg.proposal_net_args_list) == 1, "Only one proposal network is allowed."
@@ -199,7 +200,8 @@ class KPlanesModel(Model):
             return np.clip(np.interp(step, [0, cfg.proposal_warmup], [0, cfg.proposal_update_every]), 1,
                            cfg.proposal_update_every)
 
-        initial_sampler = UniformSampler(single_jitter=cfg.use_single_jitter)  # bounded => uniform (kplanes.py:262-264)
+        # bounded => uniform; unbounded => None = ProposalNetworkSampler's piecewise default (kplanes.py:261-264)
+        initial_sampler = UniformSampler(single_jitter=cfg.use_single_jitter) if cfg.bounded else None
         self.proposal_sampler = ProposalNetworkSampler(
             num_nerf_samples_per_ray=cfg.num_nerf_samples_per_ray,
             num_proposal_samples_per_ray=cfg.num_proposal_samples_per_ray,
@@ -208,7 +210,10 @@ class KPlanesModel(Model):
             update_sched=update_schedule,
             initial_sampler=initial_sampler,
         )
-        self.collider = AABBBoxCollider(scene_box=self.scene_box)
+        if cfg.bounded:  # kplanes.py:275-278
+            self.collider = AABBBoxCollider(scene_box=self.scene_box)
+        else:
+            self.collider = NearFarCollider(near_plane=cfg.near_plane, far_plane=cfg.far_plane)
         self.renderer_rgb = RGBRenderer(background_color=cfg.background_color_train)
         self.renderer_accumulation = AccumulationRenderer()
         self.renderer_depth = DepthRenderer()

@@ -391,6 +391,88 @@ class _DecoderFused(torch.autograd.Function):
         return (gx, None, None, *ret)
 
 
+class _Linear(torch.autograd.Function):
+    """y = act(x w^T) on the tensor-core dense-layer kernels (kp_tc_linear_*), any layer shape they cover.  The building
+    block of the non-default decoder branches (linear decoder / colour basis, appearance embedding), which are composed
+    from it in ``fields/kplanes_field.py``; the default decoders use the fused kernels above."""
+
+    @staticmethod
+    def forward(ctx, x, w, act: int):
+        xs, wc = f32c(x.detach()), f32c(w.detach())
+        m, k = xs.shape
+        n = wc.shape[0]
+        if wc.shape[1] != k:
+            raise RuntimeError(f"linear: x [{m},{k}] vs w {tuple(wc.shape)}")
+        y = torch.empty((m, n), dtype=torch.float32, device=xs.device)
+        call("kp_tc_linear_fwd", ptr(xs), k, ptr(wc), k, ptr(y), n, m, n, k, int(act), stream_ptr())
+        ctx.save_for_backward(xs, wc, y)
+        ctx.act, ctx.wsink = int(act), grad_sink(w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xs, wc, y = ctx.saved_tensors
+        m, k = xs.shape
+        n = wc.shape[0]
+        g = f32c(gy)
+        if ctx.act == 1:
+            g = g * (y > 0)
+        elif ctx.act == 2:
+            g = g * y * (1 - y)
+        g = f32c(g)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(xs)
+            call("kp_tc_linear_bwd_data", ptr(g), n, ptr(wc), k, ptr(gx), k, m, n, k, ptr(None), 0, stream_ptr())
+        if ctx.needs_input_grad[1]:
+            sink = ctx.wsink
+            if sink is not None and sink.is_contiguous():
+                target = sink
+            else:
+                target = gw = torch.zeros_like(wc)
+            call("kp_tc_linear_bwd_weight", ptr(g), n, ptr(xs), k, ptr(target), k, m, n, k, stream_ptr())
+        return gx, gw, None
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, act: str = "none") -> torch.Tensor:
+    """act(x [M,K] @ w [N,K]^T); act in {"none", "relu", "sigmoid"} (bias-free: tcnn FullyFusedMLP semantics)."""
+    return _Linear.apply(x, w, {"none": 0, "relu": 1, "sigmoid": 2}[act])
+
+
+class _TruncExp(torch.autograd.Function):
+    """NS/field_components/activations.py:25-41: forward exp(x), backward g * exp(clamp(x, -15, 15))."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(x.clamp(-15, 15))
+
+
+trunc_exp = _TruncExp.apply
+
+
+def sh4(directions01: torch.Tensor) -> torch.Tensor:
+    """Degree-4 spherical harmonics of 2x-1 (tcnn's SphericalHarmonics input convention; basis NS/utils/math.py:25-86)
+    as tensor ops -> [..., 16].  Only the non-default decoder branches use this form; the fused decoder kernel evaluates
+    the same basis in registers."""
+    d = directions01 * 2.0 - 1.0
+    x, y, z = d[..., 0], d[..., 1], d[..., 2]
+    xx, yy, zz = x * x, y * y, z * z
+    comps = [
+        torch.full_like(x, 0.28209479177387814), 0.4886025119029199 * y, 0.4886025119029199 * z, 0.4886025119029199 * x,
+        1.0925484305920792 * x * y, 1.0925484305920792 * y * z, 0.9461746957575601 * zz - 0.31539156525251999,
+        1.0925484305920792 * x * z, 0.5462742152960396 * (xx - yy), 0.5900435899266435 * y * (3 * xx - yy),
+        2.890611442640554 * x * y * z, 0.4570457994644658 * y * (5 * zz - 1), 0.3731763325901154 * z * (5 * zz - 3),
+        0.4570457994644658 * x * (5 * zz - 1), 1.445305721320277 * z * (xx - yy), 0.5900435899266435 * x * (xx - 3 * yy),
+    ]
+    return torch.stack(comps, dim=-1)
+
+
 def decoder_fused_supported(k0: int, h1: int, h2: int) -> bool:
     return bool(_lib.load().kp_decoder_fused_supported(int(k0), int(h1), int(h2)))
 

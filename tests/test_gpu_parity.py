@@ -813,3 +813,146 @@ def test_reference_checkpoint_loads_on_device():
         oa = a(ray_bundle(g["origins"], g["directions"], g["times"], DEV))
         ob = b(ray_bundle(g["origins"], g["directions"], g["times"], DEV))
     assert torch.equal(oa["rgb"], ob["rgb"]) and torch.equal(oa["depth"], ob["depth"])
+
+
+def _variant_samples(g):
+    from soccernerfs_b200.cameras.rays import RayBundle
+
+    n = g["origins"].shape[0]
+    rb = RayBundle(origins=g["origins"].to(DEV), directions=g["directions"].to(DEV), pixel_area=torch.ones(n, 1, device=DEV),
+                   times=g["times"].to(DEV), nears=torch.zeros(n, 1, device=DEV), fars=torch.full((n, 1), 5.0, device=DEV))
+    bins = g["bins"].to(DEV)
+    return rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+
+
+def _load_planes(grids, g, prefix, multi=True):
+    with torch.no_grad():
+        for i, gs in enumerate(grids if multi else [grids]):
+            for j, p in enumerate(gs):
+                p.copy_(g[f"{prefix}_{i}_{j}" if multi else f"{prefix}_{j}"].to(DEV))
+
+
+def test_scene_contraction_fields_vs_reference_fixture():
+    """bounded=False: SceneContraction(order=inf) evaluated inside the gather / scatter / proposal kernels (norm_mode 2)
+    vs the reference's KPlanesField / KPlanesDensityField with its own SceneContraction (tests/golden/field_variants.npz)."""
+    from soccernerfs_b200.field_components.spatial_distortions import SceneContraction
+    from soccernerfs_b200.fields.base_field import FieldHeadNames
+    from soccernerfs_b200.fields.kplanes_field import KPlanesDensityField, KPlanesField
+
+    g = load_golden("field_variants")
+    rs = _variant_samples(g)
+    f = KPlanesField(g["aabb"], spacetime_resolution=(12, 10, 14, 5), feat_dim=8, multiscale_res=(1, 2), concat_features_across_scales=True,
+                     linear_decoder=False, spatial_distortion=SceneContraction(order=float("inf"))).to(DEV)
+    _load_planes(f.grids, g, "con_grid")
+    with torch.no_grad():
+        for name, net in (("sigma", f.sigma_net), ("color", f.color_net)):
+            for i, w in enumerate(net.weights):
+                w.copy_(g[f"con_{name}_w{i}"].to(DEV))
+    out = f(rs)
+    dens, rgb = out[FieldHeadNames.DENSITY], out[FieldHeadNames.RGB]
+    assert rel_err(dens.cpu(), g["con_density"]) < TOL and rel_err(rgb.cpu(), g["con_rgb"]) < TOL
+    ((dens * g["con_gd"].to(DEV)).sum() + (rgb * g["con_gr"].to(DEV)).sum()).backward()
+    for i, gs in enumerate(f.grids):
+        for j, p in enumerate(gs):
+            assert rel_err(p.grad.cpu(), g[f"con_ggrid_{i}_{j}"]) < TOL, (i, j)
+    for name, net in (("sigma", f.sigma_net), ("color", f.color_net)):
+        for i, w in enumerate(net.weights):
+            assert rel_err(w.grad.cpu(), g[f"con_{name}_gw{i}"]) < TOL, (name, i)
+    # the same field through explicit positions (non-ray-form samples) takes the tensor form of the contraction
+    df = KPlanesDensityField(g["aabb"], resolution=[16, 14, 18, 5], feature_dim=8, linear_decoder=False,
+                             spatial_distortion=SceneContraction(order=float("inf"))).to(DEV)
+    _load_planes(df.grids, g, "pcon_grid", multi=False)
+    with torch.no_grad():
+        for i, w in enumerate(df.sigma_net.weights):
+            w.copy_(g[f"pcon_w{i}"].to(DEV))
+    dd, _ = df.get_density(rs)
+    assert rel_err(dd.cpu(), g["pcon_density"]) < TOL
+    (dd * g["pcon_gd"].to(DEV)).sum().backward()
+    for j, p in enumerate(df.grids):
+        assert rel_err(p.grad.cpu(), g[f"pcon_ggrid_{j}"]) < TOL, j
+    for i, w in enumerate(df.sigma_net.weights):
+        assert rel_err(w.grad.cpu(), g[f"pcon_gw{i}"]) < TOL, i
+    positions = rs.frustums.get_positions()
+    dfn = df.density_fn(positions, times=rs.times[:, 0])
+    assert rel_err(dfn.cpu(), g["pcon_density"]) < TOL
+
+
+def test_linear_decoder_field_vs_reference_fixture():
+    """linear_decoder=True (learned colour basis, linear density) composed from the tensor-core dense layer vs the
+    reference's KPlanesField(linear_decoder=True) (tests/golden/field_variants.npz): outputs and all gradients."""
+    from soccernerfs_b200.fields.base_field import FieldHeadNames
+    from soccernerfs_b200.fields.kplanes_field import KPlanesField
+
+    g = load_golden("field_variants")
+    rs = _variant_samples(g)
+    f = KPlanesField(g["lin_aabb"], spacetime_resolution=(12, 10, 14, 5), feat_dim=8, multiscale_res=(1, 2),
+                     concat_features_across_scales=True, linear_decoder=True, linear_decoder_layers=2).to(DEV)
+    _load_planes(f.grids, g, "lin_grid")
+    with torch.no_grad():
+        for name, net in (("sigma", f.sigma_net), ("basis", f.color_basis)):
+            for i, w in enumerate(net.weights):
+                w.copy_(g[f"lin_{name}_w{i}"].to(DEV))
+    out = f(rs)
+    dens, rgb = out[FieldHeadNames.DENSITY], out[FieldHeadNames.RGB]
+    assert rel_err(dens.cpu(), g["lin_density"]) < TOL and rel_err(rgb.cpu(), g["lin_rgb"]) < TOL
+    ((dens * g["lin_gd"].to(DEV)).sum() + (rgb * g["lin_gr"].to(DEV)).sum()).backward()
+    for i, gs in enumerate(f.grids):
+        for j, p in enumerate(gs):
+            assert rel_err(p.grad.cpu(), g[f"lin_ggrid_{i}_{j}"]) < TOL, (i, j)
+    for name, net in (("sigma", f.sigma_net), ("basis", f.color_basis)):
+        for i, w in enumerate(net.weights):
+            assert rel_err(w.grad.cpu(), g[f"lin_{name}_gw{i}"]) < TOL, (name, i)
+
+
+def test_appearance_embedding_and_unbounded_model_run():
+    """use_appearance_embedding (unpinnable: the reference's own branch raises for S > 1, see KPlanesField._appearance):
+    the composed colour net equals the fused default net when the codes' weights are zero, trains the codes, and uses the
+    mean code in eval; KPlanesModel(bounded=False) runs a training step end to end (NearFarCollider + piecewise sampler +
+    contraction)."""
+    from soccernerfs_b200.data.scene_box import SceneBox
+    from soccernerfs_b200.fields.base_field import FieldHeadNames
+    from soccernerfs_b200.fields.kplanes_field import KPlanesField
+    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
+
+    g = load_golden("field_variants")
+    rs = _variant_samples(g)
+    rs.camera_indices = torch.randint(0, 7, (rs.frustums.shape[0], 1, 1), device=DEV).expand(-1, rs.frustums.shape[1], 1)
+    kw = dict(spacetime_resolution=(12, 10, 14, 5), feat_dim=8, multiscale_res=(1, 2), concat_features_across_scales=True,
+              linear_decoder=False)
+    torch.manual_seed(3)
+    base = KPlanesField(g["lin_aabb"], **kw).to(DEV)
+    app = KPlanesField(g["lin_aabb"], use_appearance_embedding=True, appearance_dim=5, num_images=7, **kw).to(DEV)
+    with torch.no_grad():
+        for a, b in zip(app.grids.parameters(), base.grids.parameters()):
+            a.copy_(b)
+        for a, b in zip(app.sigma_net.weights, base.sigma_net.weights):
+            a.copy_(b)
+        app.color_net.weights[0].zero_()
+        app.color_net.weights[0][:, :31].copy_(base.color_net.weights[0])  # the 5 code columns stay zero
+        for a, b in zip(list(app.color_net.weights)[1:], list(base.color_net.weights)[1:]):
+            a.copy_(b)
+    o_app, o_base = app(rs), base(rs)
+    assert rel_err(o_app[FieldHeadNames.RGB], o_base[FieldHeadNames.RGB]) < 1e-5
+    o_app[FieldHeadNames.RGB].sum().backward()
+    assert app.appearance_embedding.embedding.weight.grad is not None  # zero first-layer columns: zero, but connected
+    assert float(app.color_net.weights[0].grad[:, 31:].abs().sum()) > 0
+    app.eval()
+    with torch.no_grad():
+        assert rel_err(app(rs)[FieldHeadNames.RGB], o_base[FieldHeadNames.RGB]) < 1e-5
+    # unbounded model, one training step
+    from soccernerfs_b200.engine.trainer import TrainStep
+    from tests.helpers import ray_bundle
+
+    cfg = KPlanesModelConfig(bounded=False, near_plane=0.05, far_plane=20.0, spacetime_resolution=(16, 16, 16, 6), multiscale_res=(1, 2),
+                             num_nerf_samples_per_ray=16, num_proposal_samples_per_ray=(32, 24),
+                             proposal_net_args_list=[{"feature_dim": 8, "resolution": [24, 24, 24, 6]},
+                                                     {"feature_dim": 8, "resolution": [32, 32, 32, 6]}])
+    model = cfg.setup(scene_box=SceneBox(aabb=g["aabb"]), num_train_data=3).to(DEV)
+    step = TrainStep(model, max_steps=50, warm_up_end=2)
+    gold = load_golden("model_tiny")
+    losses = []
+    for _ in range(4):
+        out = step(ray_bundle(gold["origins"], gold["directions"], gold["times"], DEV), {"image": gold["image"].to(DEV)})
+        losses.append(float(out["loss"]))
+    assert all(l == l and l < 1e3 for l in losses) and losses[-1] < losses[1]
+    step.close()

@@ -86,14 +86,27 @@ def test_cosine_schedule():
     assert cosine_decay_factor(mid, 512, 30000) == pytest.approx(0.5, abs=1e-3)
 
 
-def test_unbuilt_branches_fail_loudly():
-    from soccernerfs_b200.fields.kplanes_field import KPlanesField
+def test_non_default_branches_construct_with_reference_shapes():
+    """linear decoder / appearance embedding / scene contraction (kplanes_field.py:196-246, 278-280): same module names and
+    parameter shapes as the reference; anything the kernels do not evaluate (a non-L-inf contraction) fails loudly."""
+    from soccernerfs_b200.field_components.spatial_distortions import SceneContraction
+    from soccernerfs_b200.fields.kplanes_field import KPlanesDensityField, KPlanesField
 
     aabb = torch.tensor([[-1.0] * 3, [1.0] * 3])
+    kw = dict(spacetime_resolution=(8, 8, 8, 4), feat_dim=8, multiscale_res=(1, 2), concat_features_across_scales=True)
+    lin = KPlanesField(aabb, linear_decoder=True, linear_decoder_layers=2, use_appearance_embedding=True, appearance_dim=5,
+                       num_images=7, **kw)
+    assert [tuple(w.shape) for w in lin.color_basis.weights] == [(128, 8), (128, 128), (48, 128)]  # 3 + 5 -> 128 -> 128 -> 3 * 16
+    assert [tuple(w.shape) for w in lin.sigma_net.weights] == [(1, 16)] and not hasattr(lin, "color_net")
+    assert tuple(lin.appearance_embedding.embedding.weight.shape) == (7, 5)
+    app = KPlanesField(aabb, linear_decoder=False, use_appearance_embedding=True, appearance_dim=5, num_images=7, **kw)
+    assert app.color_net.weights[0].shape == (64, 16 + 15 + 5)
+    con = KPlanesField(aabb, linear_decoder=False, spatial_distortion=SceneContraction(order=float("inf")), **kw)
+    assert con._contract and KPlanesDensityField(aabb, [8, 8, 8, 4], 8, spatial_distortion=SceneContraction(order=float("inf")))._contract
     with pytest.raises(NotImplementedError):
-        KPlanesField(aabb, linear_decoder=True, linear_decoder_layers=1)
-    with pytest.raises(NotImplementedError):
-        KPlanesField(aabb, linear_decoder=False, use_appearance_embedding=True)
+        KPlanesField(aabb, linear_decoder=False, spatial_distortion=SceneContraction(order=None), **kw)
+    x = torch.tensor([[0.5, 0.2, 0.1], [3.0, -1.0, 0.5]])
+    assert torch.allclose(SceneContraction(order=float("inf"))(x), torch.tensor([[0.5, 0.2, 0.1], [5 / 3, -5 / 9, 5 / 18]]))
 
 
 def test_grad_bucket_span_of():
