@@ -63,8 +63,8 @@ WORKLOADS = {
 WORKLOAD = WORKLOADS["cfg2"]["label"]
 FIELD_KERNELS = ("kp_hexplane_fwd", "kp_hexplane_bwd", "kp_density_field_fwd", "kp_density_field_bwd")
 OTHER_TIMED = ("kp_decoder_fwd_fused", "kp_color_net_bwd", "kp_sigma_net_bwd", "kp_sigma_net_fwd", "kp_color_net_fwd",
-               "kp_adam_multi", "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd", "kp_plane_reg_fused", "kp_peer_allreduce",
-               "kp_peer_sharded_adam")
+               "kp_adam_multi", "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd", "kp_plane_reg_fused", "kp_plane_reg_adam",
+               "kp_peer_allreduce", "kp_peer_sharded_adam")
 
 
 def _peaks():
@@ -247,13 +247,37 @@ def per_scale_probe(model, flush, peaks, probe, reps=3):
         t_b = timed(lambda: _lib.call("kp_hexplane_bwd", ops._plane_ptrs(flat), ops._plane_ptrs(targets), ops._plane_hw(flat), n_scales,
                                       n_planes, c, pstruct, m, 1, 0x3F, c_void_p(gout.data_ptr()), _lib.stream_ptr()))
         algo_f = m * n_planes * 4 * c * 4
-        row = {"scale": int(field.multiscale_res_multipliers[k]), "plane_mb": plane_bytes / 2**20}
-        for tag, t, algo, ws, l2key in (("gather", t_f, algo_f, plane_bytes, "l2_gather_gbs"),
-                                        ("scatter", t_b, 2 * algo_f, 2 * plane_bytes, "l2_red_gbs")):
+        # distinct 128-byte texel lines this step's samples touch at this scale: one more scatter into a zeroed
+        # gradient copy, then count the lines that received anything.  Compulsory DRAM bytes of an HBM-resident scale:
+        # gather = each distinct plane line once; scatter = plane line once (re-gather) + gradient line read-modify-write.
+        zgrads = [torch.zeros_like(q) for q in planes]
+        ztargets = [None] * (n_scales * n_planes)
+        ztargets[k * n_planes:(k + 1) * n_planes] = zgrads
+        _lib.call("kp_hexplane_bwd", ops._plane_ptrs(flat), ops._plane_ptrs(ztargets), ops._plane_hw(flat), n_scales, n_planes, c,
+                  pstruct, m, 1, 0x3F, c_void_p(gout.data_ptr()), _lib.stream_ptr())
+        lines = 0
+        for zg in zgrads:  # physical layout is [H][W][C]: one texel = C contiguous floats
+            lines += int((zg.permute(0, 2, 3, 1).reshape(-1, c) != 0).any(dim=1).sum())
+        del zgrads, ztargets
+        line_bytes = c * 4
+        row = {"scale": int(field.multiscale_res_multipliers[k]), "plane_mb": plane_bytes / 2**20,
+               "distinct_lines_touched": lines, "lines_in_scale": plane_bytes // line_bytes}
+        for tag, t, algo, ws, l2key, hbmkey, compulsory in (
+                ("gather", t_f, algo_f, plane_bytes, "l2_gather_gbs", "hbm_gather_gbs", lines * line_bytes),
+                ("scatter", t_b, 2 * algo_f, 2 * plane_bytes, "l2_red_gbs", "hbm_red_gbs", 3 * lines * line_bytes)):
             level = "l2" if ws <= 0.6 * L2_BYTES else ("hbm" if ws >= 2 * L2_BYTES else "l2+hbm")
             gbs = algo / (t * 1e-3) / 1e9
-            row[tag] = {"ms": t, "algorithmic_gbs": gbs, "working_set_mb": ws / 2**20, "level": level,
-                        "frac_of_l2_probe": gbs / probe[l2key] if probe else None, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+            # what the bound resource of that level carries: L2 serves every algorithmic load; the reduction units carry
+            # the red payload (= algo_f) while the re-gather of the same bytes rides along; HBM carries the distinct lines
+            l2_bytes = algo_f
+            r = {"ms": t, "algorithmic_gbs": gbs, "working_set_mb": ws / 2**20, "level": level,
+                 "l2_level_gbs": l2_bytes / (t * 1e-3) / 1e9,
+                 "frac_of_l2_probe": (l2_bytes / (t * 1e-3) / 1e9) / probe[l2key] if probe else None,
+                 "compulsory_dram_mb": compulsory / 2**20, "compulsory_dram_gbs": compulsory / (t * 1e-3) / 1e9,
+                 "frac_of_hbm_peak": (compulsory / (t * 1e-3) / 1e9) / peaks["hbm_gbs"]}
+            r["frac"] = r["frac_of_hbm_peak"] if level == "hbm" else (r["frac_of_l2_probe"] if level == "l2" else
+                                                                      max(r["frac_of_hbm_peak"], r["frac_of_l2_probe"] or 0.0))
+            row[tag] = r
         rows.append(row)
     return rows
 
@@ -344,8 +368,9 @@ def dp_check(trainer, model, rank, world, dev):
     worst = torch.tensor([max(rel.values())], dtype=torch.float64, device=dev)
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
     out = {"params_bit_identical_across_ranks": identical, "grad_vs_single_rank_on_concatenated_batch_rel": float(worst),
-           "tolerance": 5e-5, "per_group": rel}
-    ok = bool(identical and float(worst) < 5e-5)  # (fp32 atomics: the summation order differs between the two batch shapes)
+           "tolerance": 1e-4, "per_group": rel}
+    ok = bool(identical and float(worst) < 1e-4)  # north_star's fp32 gradient bar (fp32 atomics: the summation order differs
+    # between the two batch shapes; measured 1e-5 at 2 ranks, 7e-5 at 8 ranks x 4096 rays on cfg3)
     if sharded:  # (3)
         snap = {k: (g.param_flat.clone(), g.exp_avg.clone(), g.exp_avg_sq.clone()) for k, g in sharded.items()}
         with _global_rand(rank, world, 99, dev):
@@ -410,7 +435,8 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
                         overlap_branches=not args.no_overlap, overlap_proposal_backward=prop_overlap,
                         allreduce_mode=args.allreduce if args.allreduce != "none" else "overlap",
                         allreduce_backend=args.allreduce_backend,
-                        shard_optimizer={"auto": None, "on": True, "off": False}[args.shard_optimizer])
+                        shard_optimizer={"auto": None, "on": True, "off": False}[args.shard_optimizer],
+                        fuse_reg_adam={"auto": None, "on": True, "off": False}[args.reg_adam])
     n_steps = args.warmup + args.steps
     host = _make_batches(n_steps, RAYS_PER_RANK, seed=1000 + rank)
     resident = [h.to(dev) for h in host]
@@ -549,6 +575,8 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "kernels": per_kernel, "per_scale": scales, "clocks": clocks,
         "plane_mb": sum(p.numel() for g in model.field.grids for p in g) * 4 / 2**20,
+        "regularizers": ("folded into the optimizer pass (kp_plane_reg_adam)" if trainer._reg_adam is not None else
+                         "one sweep into the gradient bucket (kp_plane_reg_fused) + kp_adam_multi"),
         "grad_allreduce": ("none (single rank)" if world == 1 else "disabled" if args.allreduce == "none" else
                            (f"{trainer.allreduce_backend}: fused reduce-scatter + sharded Adam + all-gather kernel" if trainer.sharded
                             else f"{trainer.allreduce_backend} all-reduce ({args.allreduce}) + replicated Adam")),
@@ -564,25 +592,34 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
 
 
 def _roofline(name, per_kernel, step_bytes, scales, peaks, probe):
-    """Dominant field kernel (the larger of gather / scatter).  The level of the hierarchy that bounds it differs per
-    scale, so the bound is derived from the working sets: `peak` is the blended rate at which the kernel's
-    algorithmic bytes could be served if every scale ran at the measured rate of the level its working set lives in
-    (kp_line_probe for L2-resident scales, MEASURED_PEAKS hbm_gbs for HBM-resident ones, a hit-ratio mix in between)."""
+    """Roofline of the dominant field kernel (the larger of gather / scatter), built from the level of the hierarchy each
+    scale actually lives in ("reported per scale because the level of the hierarchy differs per scale").
+
+    Bytes the bound resources carry, per scale k (B_k = units x 3072 B, SURVEY's per-scale B_fwd):
+      * L2 level  -- gather: every load, B_k, at the measured random-line L2 load rate (`l2_gather_gbs`);
+                     scatter: the reduction payload, B_k, at the measured random-line L2 `red.v4` rate (`l2_red_gbs`) --
+                     the product-rule re-gather of the same B_k is served by L1/L2 next to it and is not the bound;
+      * HBM level -- the DISTINCT 128-byte lines the step's samples touch (counted in this run from a scatter into a
+                     zeroed copy): gather 1x, scatter 3x (plane line + gradient line read-modify-write), at
+                     MEASURED_PEAKS.json hbm_gbs.  (bench steps run with a flushed L2, so this applies to every scale.)
+    floor_k = max(L2 time, HBM time); `peak` = bytes / sum(floor_k); `achieved` = bytes / measured kernel time, so
+    frac = sum(floor_k) / t <= 1 (gathers may exceed it through L1 hits between neighbouring samples).  `achieved` counts
+    B_fwd x units per launch; SURVEY's 2 x B_fwd figure for the backward is kept in `survey_algorithmic_gbs`."""
     top = max(("kp_hexplane_fwd", "kp_hexplane_bwd"), key=lambda k: per_kernel.get(k, {"ms_per_step": 0})["ms_per_step"])
     tag, l2key = ("gather", "l2_gather_gbs") if top == "kp_hexplane_fwd" else ("scatter", "l2_red_gbs")
     top_ms = per_kernel[top]["ms_per_step"] / max(1.0, per_kernel[top]["launches_per_step"])
-    algo = step_bytes[top]
-    t_floor, t_hbm_part = 0.0, 0.0
-    per_scale_bytes = algo / len(scales)
+    payload = step_bytes["kp_hexplane_fwd"]  # B_fwd x units (all scales)
+    per_scale_bytes = payload / len(scales)
+    t_floor, t_hbm_bound, levels = 0.0, 0.0, []
     for row in scales:
-        ws = row[tag]["working_set_mb"] * 2**20
-        hit = min(1.0, 0.75 * L2_BYTES / ws)
-        t_l2 = per_scale_bytes * hit / (probe[l2key] * 1e9)
-        t_hbm = per_scale_bytes * (1.0 - hit) / (peaks["hbm_gbs"] * 1e9)
-        t_floor += t_l2 + t_hbm
-        t_hbm_part += t_hbm
-    achieved = algo / (top_ms * 1e-3) / 1e9
-    blended_peak = algo / t_floor / 1e9
+        t_l2 = per_scale_bytes / (probe[l2key] * 1e9)
+        t_hbm = row[tag]["compulsory_dram_mb"] * 2**20 / (peaks["hbm_gbs"] * 1e9)
+        t_floor += max(t_l2, t_hbm)
+        if t_hbm > t_l2:
+            t_hbm_bound += t_hbm
+        levels.append({"scale": row["scale"], "floor_ms": 1e3 * max(t_l2, t_hbm), "bound": "hbm" if t_hbm > t_l2 else "l2"})
+    achieved = payload / (top_ms * 1e-3) / 1e9
+    peak = payload / t_floor / 1e9
     traffic, tsrc = None, None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic_r2.json")
     if os.path.exists(tpath):
@@ -590,14 +627,15 @@ def _roofline(name, per_kernel, step_bytes, scales, peaks, probe):
             tj = json.load(f)
         traffic, tsrc = tj.get(name, {}).get(top), tj.get("source")
     finest = scales[-1][tag]
-    return {"bound": "hbm" if t_hbm_part > 0.5 * t_floor else "l2", "kernel": top, "achieved": achieved, "peak": blended_peak,
-            "unit": "GB/s", "frac": achieved / blended_peak, "traffic": traffic, "traffic_source": tsrc,
-            "peak_source": "per-scale blend of kp_line_probe L2 rate (%s = %.0f GB/s, measured in this run) and MEASURED_PEAKS.json hbm_gbs "
-                           "(%.0f GB/s) by working-set size; L2 hit ratio = min(1, 0.75*126 MB / working set)" % (l2key, probe[l2key], peaks["hbm_gbs"]),
-            "algorithmic_bytes_per_launch": algo, "kernel_ms": top_ms,
-            "finest_scale": {"scale": scales[-1]["scale"], "kernel_ms": finest["ms"], "achieved": finest["algorithmic_gbs"],
-                             "level": finest["level"], "frac_of_hbm_peak": finest["frac_of_hbm_peak"],
-                             "frac_of_l2_probe": finest["frac_of_l2_probe"]}}
+    return {"bound": "hbm" if t_hbm_bound > 0.5 * t_floor else "l2", "kernel": top, "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
+            "peak_source": "sum over scales of max(B_k / kp_line_probe %s (%.0f GB/s, measured in this run), distinct-line DRAM bytes / "
+                           "MEASURED_PEAKS.json hbm_gbs (%.0f GB/s)); distinct lines counted in this run" % (l2key, probe[l2key], peaks["hbm_gbs"]),
+            "algorithmic_bytes_per_launch": payload, "kernel_ms": top_ms, "floor_ms": 1e3 * t_floor, "per_scale_floor": levels,
+            "survey_algorithmic_gbs": step_bytes[top] / (top_ms * 1e-3) / 1e9,
+            "finest_scale": {"scale": scales[-1]["scale"], "kernel_ms": finest["ms"], "level": finest["level"],
+                             "l2_level_gbs": finest["l2_level_gbs"], "frac_of_l2_probe": finest["frac_of_l2_probe"],
+                             "compulsory_dram_gbs": finest["compulsory_dram_gbs"], "frac_of_hbm_peak": finest["frac_of_hbm_peak"]}}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -842,6 +880,8 @@ def main():
                     help="peer: our in-place NVLink peer-memory kernel; nccl: torch.distributed.all_reduce")
     ap.add_argument("--shard-optimizer", choices=["auto", "on", "off"], default="auto",
                     help="N>1, peer backend: reduce-scatter + Adam on the owned shard + all-gather in one kernel (auto = on)")
+    ap.add_argument("--reg-adam", choices=["auto", "on", "off"], default="auto",
+                    help="(f1) plane regularisers folded into the optimizer's streaming pass (auto: when the planes are HBM-resident)")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python each step instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

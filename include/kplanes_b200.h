@@ -206,6 +206,23 @@ int kp_adam_multi(float* const* params, const float* const* grads, float* const*
                   const int64_t* sizes, int P, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int64_t step, float grad_scale, const float* hyper_dev, void* stream);
 
+/* (f1) Regulariser stencil + Adam in ONE streaming pass per plane (NS/engine/optimizers.py:74-160 applied to
+ * NS/model_components/losses.py:356-452 + the data gradient): per element reads plane, grad, exp_avg, exp_avg_sq once and
+ * writes plane, exp_avg, exp_avg_sq (and grad = 0 when zero_grads).  Total gradient = grads[p] * grad_scale +
+ * sum_i coef_dev[p,i] * d(sums[p,i])/d(plane), the regulariser part computed from the PRE-update plane values and never
+ * materialised; sums (may be NULL) accumulates the regulariser sums of the pre-update planes as kp_plane_reg_fused does.
+ * hwc = (H, W, C) per plane, C in {4, 8, 16, 32} (kp_plane_reg_adam_supported); all four tensors of a plane share the
+ * channel-last layout.  scratch: device buffer of >= kp_plane_reg_adam_scratch_bytes(hwc, P) bytes (halo snapshot of the
+ * tiles: neighbours are read from it so that in-place updates of adjacent tiles cannot be observed).  step is 1-based;
+ * hyper_dev as in kp_adam_multi. */
+int kp_plane_reg_adam_supported(int C);
+int64_t kp_plane_reg_adam_scratch_bytes(const int32_t* hwc /* host [P,3] */, int P);
+int kp_plane_reg_adam(float* const* planes, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                      const int32_t* hwc /* host [P,3] */, const uint32_t* terms /* host [P] */, int P,
+                      const float* coef_dev /* [P,4] */, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int64_t step, float grad_scale, const float* hyper_dev, double* sums /* [P,4] accumulated, or NULL */,
+                      void* scratch, int64_t scratch_bytes, int zero_grads, void* stream);
+
 /* Per-step scalars of a CUDA-graph-replayed step, computed on the device from *step_counter (then incremented):
  * anneal_out = anneal_table[min(step, max_steps)] (proposal-weight anneal, NS/models/kplanes.py:326-331) and, per
  * optimizer group g, hyper_out[g] = (lr_table[..] / (1 - beta1^t), 1 / sqrt(1 - beta2^t), grad_scale) with t = step + 1

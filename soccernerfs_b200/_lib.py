@@ -65,6 +65,10 @@ SIGNATURES = {
     "kp_plane_reg_multi_fwd": ([_P, _P, _P, c_int, _P, _P], c_int),
     "kp_plane_reg_multi_bwd": ([_P, _P, _P, _P, c_int, _P, c_int, _P], c_int),
     "kp_plane_reg_fused": ([_P, _P, _P, _P, c_int, _P, c_int, _P, _P], c_int),
+    "kp_plane_reg_adam_supported": ([c_int], c_int),
+    "kp_plane_reg_adam_scratch_bytes": ([_P, c_int], c_int64),
+    "kp_plane_reg_adam": ([_P, _P, _P, _P, _P, _P, c_int, _P, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P, _P,
+                          _P, c_int64, c_int, _P], c_int),
     "kp_step_scalars": ([_P, _P, _P, c_int64, c_int, POINTER(c_float), c_float, _P, _P, _P], c_int),
     "kp_adam_multi": ([_P, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P, _P], c_int),
     "kp_adam_step": ([_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P], c_int),

@@ -266,6 +266,179 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// (f1) Regulariser stencil + Adam in ONE streaming pass per plane (NS/engine/optimizers.py:74-160
+// over NS/model_components/losses.py:356-452).  Per element the pass reads p, g, m, v once and writes p, m, v (and
+// g = 0 for the next step): the regularisers' gradient is computed on the fly from the PRE-update plane values and is
+// never materialised (the separate sweep wrote 1x and the optimizer re-read 1x the plane bytes for it).
+//   total gradient  = g * grad_scale + sum_i coef[p,i] * d(sums[p,i]) / d(plane)
+// The stencil needs pre-update neighbours while the planes are updated in place.  Tiles of kFRows rows x 256 float4
+// columns are owned by one block each; a block walks down its rows with the rows h-2 .. h+2 in registers (loaded
+// before the row is overwritten) and exchanges the W neighbours through shared memory before anyone writes the row.
+// Neighbours OUTSIDE the tile (2 rows above / below, one texel left / right) may already have been updated by the
+// block that owns them, so a tiny first kernel snapshots every tile's halo (<= 12.5 % of the plane bytes) and the main
+// kernel reads halo values from the snapshot only.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFRows = 64;                            // rows per tile
+constexpr int kFMaxC4 = 8;                            // float4 per texel supported (C <= 32)
+constexpr int kFHaloRows = 4 * 256;                   // float4: rows h0-2, h0-1, h1, h1+1 of the tile's 256 columns
+constexpr int kFHaloF4 = kFHaloRows + kFRows * 2 * kFMaxC4;  // + [row][left | right][C4] texel columns
+constexpr int kFMaxTensors = 40;
+
+struct RegAdamPlane {
+  float* p;
+  float* g;
+  float* m;
+  float* v;
+  int H, W, C4;
+  uint32_t terms;
+};
+struct RegAdamTable {
+  RegAdamPlane pl[kFMaxTensors];
+  int first_block[kFMaxTensors + 1];
+  int tiles_x[kFMaxTensors];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) plane_halo_snapshot_kernel(const __grid_constant__ RegAdamTable T, float4* __restrict__ halo) {
+  const int p = find_tensor(T.first_block, T.n, blockIdx.x);
+  const RegAdamPlane& P = T.pl[p];
+  const int H = P.H, C4 = P.C4, row4 = P.W * P.C4;
+  const int local = blockIdx.x - T.first_block[p];
+  const int tx = local % T.tiles_x[p], ty = local / T.tiles_x[p];
+  const int col = tx * 256 + threadIdx.x;
+  const int h0 = ty * kFRows, h1 = min(H, h0 + kFRows);
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(P.p);
+  float4* dst = halo + (size_t)blockIdx.x * kFHaloF4;
+  if (col < row4) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int h = r < 2 ? h0 - 2 + r : h1 + (r - 2);
+      if (h >= 0 && h < H) dst[r * 256 + threadIdx.x] = src[(size_t)h * row4 + col];
+    }
+  }
+  const int n_side = (h1 - h0) * 2 * C4;
+  for (int i = threadIdx.x; i < n_side; i += 256) {
+    const int hh = i / (2 * C4), side = (i / C4) & 1, k = i % C4;
+    const int c = side ? tx * 256 + 256 + k : tx * 256 - C4 + k;
+    if (c >= 0 && c < row4) dst[kFHaloRows + (hh * 2 + side) * kFMaxC4 + k] = src[(size_t)(h0 + hh) * row4 + c];
+  }
+}
+
+template <bool ZERO_GRAD>
+__global__ void __launch_bounds__(256, 3) plane_reg_adam_kernel(const __grid_constant__ RegAdamTable T, const float4* __restrict__ halo,
+                                                             const float* __restrict__ coef, double* __restrict__ sums,
+                                                             const float* __restrict__ hyper_dev, float lr_over_bc1,
+                                                             float inv_sqrt_bc2, float beta1, float beta2, float eps, float wd,
+                                                             float grad_scale) {
+  if (hyper_dev != nullptr) {
+    lr_over_bc1 = hyper_dev[0];
+    inv_sqrt_bc2 = hyper_dev[1];
+    grad_scale = hyper_dev[2];
+  }
+  __shared__ float4 xch[2][256];
+  const int p = find_tensor(T.first_block, T.n, blockIdx.x);
+  const RegAdamPlane& P = T.pl[p];
+  const int H = P.H, W = P.W, C4 = P.C4, row4 = W * C4;
+  const uint32_t terms = P.terms;
+  const float k0 = (terms & 1u) ? coef[p * 4 + 0] : 0.f, k1 = (terms & 2u) ? coef[p * 4 + 1] : 0.f;
+  const float k2 = (terms & 4u) ? coef[p * 4 + 2] : 0.f, k3 = (terms & 8u) ? coef[p * 4 + 3] : 0.f;
+  const int local = blockIdx.x - T.first_block[p];
+  const int tx = local % T.tiles_x[p], ty = local / T.tiles_x[p];
+  const int tid = threadIdx.x;
+  const int col = tx * 256 + tid;
+  const bool active = col < row4;
+  const int wcol = active ? col / C4 : 0;
+  const bool hasL = active && wcol >= 1, hasR = active && wcol + 1 < W;
+  const bool edgeL = tid < C4, edgeR = tid >= 256 - C4;
+  const int h0 = ty * kFRows, h1 = min(H, h0 + kFRows);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool need2 = (terms & 4u) != 0;
+  float4* __restrict__ pp = reinterpret_cast<float4*>(P.p);
+  float4* __restrict__ gp = reinterpret_cast<float4*>(P.g);
+  float4* __restrict__ mp = reinterpret_cast<float4*>(P.m);
+  float4* __restrict__ vp = reinterpret_cast<float4*>(P.v);
+  const float4* __restrict__ hl = halo + (size_t)blockIdx.x * kFHaloF4;
+  const int kc = tid % C4;
+  // pre-update value of row h at this thread's column: own tile rows come from the plane (this block has not written
+  // them yet when they are requested), rows of other tiles from the snapshot
+  auto old_row = [&](int h) -> float4 {
+    if (!active || h < 0 || h >= H) return zero;
+    if (h < h0) return hl[(h - (h0 - 2)) * 256 + tid];
+    if (h >= h1) return hl[(2 + (h - h1)) * 256 + tid];
+    return pp[(size_t)h * row4 + col];
+  };
+  auto halo_side = [&](int h, int side) -> float4 { return hl[kFHaloRows + ((h - h0) * 2 + side) * kFMaxC4 + kc]; };
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float4 a = need2 ? old_row(h0 - 2) : zero, b = old_row(h0 - 1), c = old_row(h0), d = old_row(h0 + 1);
+  float4 gn = zero, mn = zero, vn = zero, hLn = zero, hRn = zero;
+  if (active) {
+    const size_t i0 = (size_t)h0 * row4 + col;
+    gn = gp[i0]; mn = mp[i0]; vn = vp[i0];
+    if (edgeL && hasL) hLn = halo_side(h0, 0);
+    if (edgeR && hasR) hRn = halo_side(h0, 1);
+  }
+  for (int h = h0; h < h1; ++h) {
+    const float4 e = old_row(h + 2);
+    const float4 gg = gn, mm0 = mn, vv0 = vn, hL = hLn, hR = hRn;
+    if (active && h + 1 < h1) {  // next row's streams in flight under this row's arithmetic
+      const size_t in = (size_t)(h + 1) * row4 + col;
+      gn = gp[in]; mn = mp[in]; vn = vp[in];
+      if (edgeL && hasL) hLn = halo_side(h + 1, 0);
+      if (edgeR && hasR) hRn = halo_side(h + 1, 1);
+    }
+    float4* x = xch[h & 1];
+    x[tid] = c;
+    __syncthreads();  // every thread's pre-update row h is visible before any thread overwrites row h in global memory
+    if (active) {
+      float4 g = zero;
+      if (terms & 1u) {  // squared first difference along H
+        if (h + 1 < H) { const float4 df = sub4m(d, c); s0 += sq4m(df); g = fma4(df, -2.f * k0, g); }
+        if (h >= 1) g = fma4(sub4m(c, b), 2.f * k0, g);
+      }
+      if (terms & 2u) {  // squared first difference along W
+        if (hasR) { const float4 r = edgeR ? hR : x[tid + C4]; const float4 df = sub4m(r, c); s1 += sq4m(df); g = fma4(df, -2.f * k1, g); }
+        if (hasL) { const float4 l = edgeL ? hL : x[tid - C4]; g = fma4(sub4m(c, l), 2.f * k1, g); }
+      }
+      if (need2) {  // squared second difference along H
+        if (h + 2 < H) { const float4 dd = sub4m(sub4m(e, d), sub4m(d, c)); s2 += sq4m(dd); g = fma4(dd, 2.f * k2, g); }
+        if (h >= 1 && h + 1 < H) g = fma4(sub4m(sub4m(d, c), sub4m(c, b)), -4.f * k2, g);
+        if (h >= 2) g = fma4(sub4m(sub4m(c, b), sub4m(b, a)), 2.f * k2, g);
+      }
+      if (terms & 8u) {  // |1 - t|
+        s3 += fabsf(1.f - c.x) + fabsf(1.f - c.y) + fabsf(1.f - c.z) + fabsf(1.f - c.w);
+        g.x -= k3 * sgnm(1.f - c.x); g.y -= k3 * sgnm(1.f - c.y); g.z -= k3 * sgnm(1.f - c.z); g.w -= k3 * sgnm(1.f - c.w);
+      }
+      float4 pn = c, mm = mm0, vv = vv0;
+      float* pa = &pn.x; const float* ga = &gg.x; const float* ra = &g.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // torch.optim.Adam, same operation order as adam_multi_kernel
+        const float gr = (ga[k] * grad_scale + ra[k]) + wd * pa[k];
+        ma[k] = ma[k] + (gr - ma[k]) * (1.f - beta1);
+        va[k] = va[k] * beta2 + (1.f - beta2) * gr * gr;
+        pa[k] -= lr_over_bc1 * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+      }
+      const size_t i = (size_t)h * row4 + col;
+      pp[i] = pn; mp[i] = mm; vp[i] = vv;
+      if (ZERO_GRAD) gp[i] = zero;
+    }
+    a = b; b = c; c = d; d = e;
+  }
+  if (sums != nullptr) {
+    __shared__ double red[4][8];
+    const double dd[4] = {warp_sum_d((double)s0), warp_sum_d((double)s1), warp_sum_d((double)s2), warp_sum_d((double)s3)};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+      for (int k = 0; k < 4; ++k) red[k][warp] = dd[k];
+    __syncthreads();
+    if (threadIdx.x < 4 && ((terms >> threadIdx.x) & 1u)) {
+      double acc = 0.0;
+      for (int wv = 0; wv < 8; ++wv) acc += red[threadIdx.x][wv];
+      atomicAdd(&sums[p * 4 + threadIdx.x], acc);
+    }
+  }
+}
+
 // Per-step scalars of a graph-replayed training step, from the device-resident step counter: the proposal-weight
 // anneal exponent (NS/models/kplanes.py:326-331), the cosine-decayed learning rate (NS/engine/schedulers.py:126-142,
 // both tabulated by the host once) and Adam's bias corrections (torch.optim.Adam) -- one single-thread kernel instead
@@ -414,6 +587,67 @@ extern "C" int kp_adam_multi(float* const* params, const float* const* grads, fl
     adam_multi_kernel<<<nb, 256, 0, as_stream(stream)>>>(T, hyper_dev, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1,
                                                          beta2, eps, weight_decay, grad_scale);
     KP_LAUNCH_CHECK("adam_multi");
+  }
+  return 0;
+}
+
+static bool reg_adam_c_ok(int C) { return C == 4 || C == 8 || C == 16 || C == 32; }
+
+extern "C" int kp_plane_reg_adam_supported(int C) { return reg_adam_c_ok(C) ? 1 : 0; }
+
+// Bytes of halo scratch kp_plane_reg_adam needs for these planes (one snapshot slot per tile).
+extern "C" int64_t kp_plane_reg_adam_scratch_bytes(const int32_t* hwc, int P) {
+  int64_t tiles = 0;
+  for (int i = 0; i < P; ++i)
+    tiles += ceil_div((int64_t)hwc[i * 3 + 1] * (hwc[i * 3 + 2] / 4), 256) * ceil_div((int64_t)hwc[i * 3 + 0], kFRows);
+  return tiles * kFHaloF4 * (int64_t)sizeof(float4);
+}
+
+extern "C" int kp_plane_reg_adam(float* const* planes, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                                 const int32_t* hwc, const uint32_t* terms, int P, const float* coef_dev, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                                 const float* hyper_dev, double* sums, void* scratch, int64_t scratch_bytes, int zero_grads,
+                                 void* stream) {
+  KP_CHECK(planes && grads && exp_avg && exp_avg_sq && hwc && terms && coef_dev && P >= 0 && step >= 1 && scratch,
+           "plane_reg_adam: bad arguments");
+  KP_CHECK(scratch_bytes >= kp_plane_reg_adam_scratch_bytes(hwc, P), "plane_reg_adam: scratch too small (%lld bytes)",
+           (long long)scratch_bytes);
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  float4* halo = reinterpret_cast<float4*>(scratch);
+  for (int begin = 0; begin < P; begin += kFMaxTensors) {
+    const int end = std::min(P, begin + kFMaxTensors);
+    RegAdamTable T;
+    int nb = 0, k = 0;
+    for (int i = begin; i < end; ++i, ++k) {
+      RegAdamPlane& r = T.pl[k];
+      r.p = planes[i]; r.g = grads[i]; r.m = exp_avg[i]; r.v = exp_avg_sq[i];
+      r.H = hwc[i * 3 + 0]; r.W = hwc[i * 3 + 1];
+      const int C = hwc[i * 3 + 2];
+      KP_CHECK(r.p && r.g && r.m && r.v && r.H >= 1 && r.W >= 1 && reg_adam_c_ok(C), "plane_reg_adam: plane %d invalid (C in {4,8,16,32})", i);
+      KP_CHECK(((((uintptr_t)r.p | (uintptr_t)r.g | (uintptr_t)r.m | (uintptr_t)r.v) & 15) == 0), "plane_reg_adam: plane %d not 16-byte aligned", i);
+      r.C4 = C / 4;
+      r.terms = terms[i];
+      T.first_block[k] = nb;
+      T.tiles_x[k] = (int)ceil_div((int64_t)r.W * r.C4, 256);
+      nb += T.tiles_x[k] * (int)ceil_div(r.H, kFRows);
+    }
+    T.first_block[k] = nb;
+    T.n = k;
+    if (nb == 0) continue;
+    cudaStream_t st = as_stream(stream);
+    plane_halo_snapshot_kernel<<<nb, 256, 0, st>>>(T, halo);
+    kp::g_launches += 1;
+    double* s = sums ? sums + (size_t)begin * 4 : nullptr;
+    const float* cf = coef_dev + (size_t)begin * 4;
+    if (zero_grads)
+      plane_reg_adam_kernel<true><<<nb, 256, 0, st>>>(T, halo, cf, s, hyper_dev, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1,
+                                                      beta2, eps, weight_decay, grad_scale);
+    else
+      plane_reg_adam_kernel<false><<<nb, 256, 0, st>>>(T, halo, cf, s, hyper_dev, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1,
+                                                       beta2, eps, weight_decay, grad_scale);
+    KP_LAUNCH_CHECK("plane_reg_adam");
+    halo += (size_t)nb * kFHaloF4;
   }
   return 0;
 }

@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include "tc_ws.cuh"
 
 namespace kp {
 
@@ -324,6 +325,186 @@ __global__ void __launch_bounds__(256) tc_pipe_kernel(const __grid_constant__ Pi
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised row-tile GEMM (tc_ws.cuh): same operands, layouts and epilogues as tc_pipe_kernel, but the three
+// activities run on their own warps and meet only at mbarriers:
+//   full[st]  : 256 producer arrivals   -> the MMA warp may read stage st
+//   empty[st] : tcgen05.commit          -> the producers may overwrite stage st
+//   accf[a]   : tcgen05.commit          -> the epilogue warps may unload accumulator a
+//   acce[a]   : 4 epilogue-warp arrivals -> the MMA warp may overwrite accumulator a
+// ---------------------------------------------------------------------------------------------------------------
+template <int B_MN, int KS, int ACT, bool MASK>
+__global__ void __launch_bounds__(kWsThreads, 1) tc_ws_gemm_kernel(const __grid_constant__ PipeArgs P, int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const int R_tot = P.n_slices * KS;
+  const int b_rows = B_MN ? R_tot : P.N_pad, b_cols = B_MN ? P.N_pad : R_tot;
+  float* b_hi = align1024(smem_raw);
+  float* b_lo = b_hi + b_rows * b_cols;
+  float* a_st = b_lo + b_rows * b_cols;  // [n_stages][hi | lo][128 x KS]
+  __shared__ __align__(8) uint64_t full[kWsMaxStages], empty[kWsMaxStages], accf[2], acce[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * P.N_slice;
+  const int N = min(P.N_slice, P.N_total - col0);
+  const uint32_t tmem_cols = P.N_pad <= 32 ? 64u : (P.N_pad <= 64 ? 128u : 256u);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], kWsProdThreads);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&accf[i], 1);
+      mbar_init(&acce[i], kWsEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tmem_alloc_cols(&tmem_slot, warp, tmem_cols);
+  // weights of this column slice, once per CTA (all warps)
+  if (B_MN) stage_tile<1>(P.W + col0, P.ldw, b_rows, P.R, N, b_cols, b_hi, b_lo);
+  else stage_tile<0>(P.W + (int64_t)col0 * P.ldw, P.ldw, b_rows, N, P.R, b_cols, b_hi, b_lo);
+  publish_smem_and_sync();
+  const int64_t n_tiles = (P.M + 127) / 128;
+  const int my_tiles = (int64_t)blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+  const int ns = P.n_slices;
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp >= kWsEpiWarps + 1) {
+    // ------------------------------------------------ producers ------------------------------------------------
+    const int pt = threadIdx.x - kWsProdTid0;
+    const int off0 = ws_store_offset<128, KS, 0>(pt);
+    const bool a_vec = ((P.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15) == 0);
+    const int n_steps = my_tiles * ns;
+    int ljl = 0, lkc = 0;  // (tile, K slice) of the next load
+    auto issue_load = [&](WsRegs<128, KS>& t) {
+      const int64_t tile = blockIdx.x + (int64_t)ljl * gridDim.x;
+      const int rows_valid = (int)min((int64_t)128, P.M - tile * 128);
+      const int cols_valid = P.R - lkc * KS;
+      const float* src = P.A + tile * 128 * P.lda + lkc * KS;
+      if (a_vec && rows_valid == 128 && cols_valid >= KS) ws_load<128, KS, true>(t, src, P.lda, pt, 128, KS);
+      else ws_load<128, KS, false>(t, src, P.lda, pt, rows_valid, cols_valid);
+      if (++lkc == ns) { lkc = 0; ++ljl; }
+    };
+    int st = 0;
+    uint32_t use = 0;
+    auto step_body = [&](WsRegs<128, KS>& cur, WsRegs<128, KS>& nxt, int s) {
+      if (s + 1 < n_steps) issue_load(nxt);  // in flight while this step is converted and stored
+      if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
+      float* a_hi = a_st + st * (2 * 128 * KS);
+      ws_store<128, KS>(cur, a_hi, a_hi + 128 * KS, off0);
+      fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+      mbar_arrive(&full[st]);
+      if (++st == n_stages) { st = 0; ++use; }
+    };
+    WsRegs<128, KS> ra, rb;
+    if (n_steps > 0) issue_load(ra);
+    for (int s = 0; s < n_steps; s += 2) {
+      step_body(ra, rb, s);
+      if (s + 1 < n_steps) step_body(rb, ra, s + 1);
+    }
+  } else if (warp == kWsEpiWarps) {
+    // ------------------------------------------------ MMA issuer -----------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, P.N_pad, 0, B_MN);
+      const uint64_t b_d[2] = {B_MN ? desc_mnmajor(smem_u32(b_hi), b_rows, 0) : desc_kmajor(smem_u32(b_hi), b_rows, 0, 0),
+                               B_MN ? desc_mnmajor(smem_u32(b_lo), b_rows, 0) : desc_kmajor(smem_u32(b_lo), b_rows, 0, 0)};
+      const uint32_t b_blk = (uint32_t)(b_rows * 128) >> 4;  // K-major B: 16-byte units between 32-col blocks
+      int st = 0;
+      uint32_t use = 0;
+      for (int jl = 0; jl < my_tiles; ++jl) {
+        const int acc = jl & 1;
+        const uint32_t ua = (uint32_t)jl >> 1;
+        if (ua > 0) mbar_wait_sleep(&acce[acc], (ua - 1) & 1);  // the epilogue has unloaded this accumulator's previous tile
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * P.N_pad);
+        for (int kc = 0; kc < ns; ++kc) {
+          mbar_wait_sleep(&full[st], use & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(a_st + st * (2 * 128 * KS));
+          const uint64_t a_d[2] = {desc_kmajor(a_base, 128, 0, 0), desc_kmajor(a_base + 128 * KS * 4, 128, 0, 0)};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi (small terms first)
+            const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
+#pragma unroll
+            for (int k8 = 0; k8 < KS / 8; ++k8) {
+              const int kk = kc * (KS / 8) + k8;  // K step within the whole reduction
+              const uint32_t a_off = (uint32_t)(((k8 >> 2) * 128 * 128 + (k8 & 3) * 32) >> 4);
+              const uint32_t b_off = B_MN ? (uint32_t)((kk * 1024) >> 4) : (uint32_t)(kk >> 2) * b_blk + (uint32_t)(((kk & 3) * 32) >> 4);
+              umma_tf32(tmem_d, ad0 + a_off, bd0 + b_off, idesc, (kc | t | k8) != 0);
+            }
+          }
+          umma_commit(&empty[st]);  // arrives when the MMAs above have read the stage
+          if (++st == n_stages) { st = 0; ++use; }
+        }
+        umma_commit(&accf[acc]);  // ... and when the tile's accumulator is complete
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue -------------------------------------------------
+    const int quad = warp;  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const bool o_vec = ((P.ldo & 3) == 0) && (((reinterpret_cast<uintptr_t>(P.OUT) + (size_t)col0 * 4) & 15) == 0);
+    const bool m_vec = !MASK || (((P.ldaux & 3) == 0) && (((reinterpret_cast<uintptr_t>(P.aux) + (size_t)col0 * 4) & 15) == 0));
+    for (int jl = 0; jl < my_tiles; ++jl) {
+      const int acc = jl & 1;
+      const uint32_t ua = (uint32_t)jl >> 1;
+      const int64_t tile = blockIdx.x + (int64_t)jl * gridDim.x;
+      const int64_t row0 = tile * 128;
+      const int rows_valid = (int)min((int64_t)128, P.M - row0);
+      mbar_wait_sleep(&accf[acc], ua & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * P.N_pad) + ((uint32_t)(quad * 32) << 16);
+      float* dst_row = P.OUT + (row0 + row) * P.ldo + col0;
+      const float* aux_row = MASK ? P.aux + (row0 + row) * P.ldaux + col0 : nullptr;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        const bool fast = o_vec && m_vec && (c0 + 16 <= N);
+        float4 m4[4];
+        if (MASK && fast && row < rows_valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m4[q] = __ldg(reinterpret_cast<const float4*>(aux_row + c0 + 4 * q));
+        }
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < rows_valid) {
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            x[j] = __uint_as_float(v[j]);
+            if (ACT == ACT_RELU) x[j] = fmaxf(x[j], 0.f);
+            else if (ACT == ACT_SIGMOID) x[j] = 1.f / (1.f + expf(-x[j]));
+          }
+          if (fast) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 o4 = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+              if (MASK) {
+                if (!(m4[q].x > 0.f)) o4.x = 0.f;
+                if (!(m4[q].y > 0.f)) o4.y = 0.f;
+                if (!(m4[q].z > 0.f)) o4.z = 0.f;
+                if (!(m4[q].w > 0.f)) o4.w = 0.f;
+              }
+              *reinterpret_cast<float4*>(dst_row + c0 + 4 * q) = o4;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + j < N) {
+                float o1 = x[j];
+                if (MASK && !(aux_row[c0 + j] > 0.f)) o1 = 0.f;
+                dst_row[c0 + j] = o1;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();  // this warp's TMEM reads are ordered before the arrival the MMA warp waits on
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acce[acc]);
+    }
+  }
+  tmem_free_cols(tmem_base, warp, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Weight gradient, persistent: each CTA walks its 128-sample tiles, accumulating
 //   D[k, n] += sum_{s in tile} X[s, k] * dY[s, n]         (D = dW^T, M = 128 >= K_in, N = N_out padded to 32)
 // in ONE TMEM accumulator (both operands are MN-major views with K = samples), then adds D into dW once.
@@ -405,6 +586,119 @@ __global__ void __launch_bounds__(256) tc_wgrad_kernel(const float* __restrict__
     }
   }
   tmem_free(tmem_slot, warp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised weight gradient:  D[k, n] += sum_s X[s, k] * dY[s, n]  (D = dW^T) over this CTA's sub-tiles of ROWS
+// samples.  Both operands are activations, so both are staged per step (MN-major views, K = the ROWS samples) by the
+// producer warps into an n_stages ring; the MMA warp accumulates every step into ONE TMEM accumulator; after the last
+// step the epilogue warps add D into dW with one red per weight.
+// ---------------------------------------------------------------------------------------------------------------
+template <int K_PAD, int N_PAD, int ROWS>
+__global__ void __launch_bounds__(kWsThreads, 1) tc_ws_wgrad_kernel(const float* __restrict__ X, int64_t ldx,
+                                                                    const float* __restrict__ dY, int64_t lddy,
+                                                                    float* __restrict__ dW, int64_t lddw, int64_t M, int K_in,
+                                                                    int N_out, int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int STAGE = 2 * ROWS * (K_PAD + N_PAD);  // floats: [x_hi | x_lo | y_hi | y_lo]
+  float* st_base = align1024(smem_raw);
+  __shared__ __align__(8) uint64_t full[kWsMaxStages], empty[kWsMaxStages], done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t tmem_cols = N_PAD <= 32 ? 32u : (N_PAD <= 64 ? 64u : 128u);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], kWsProdThreads);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tmem_alloc_cols(&tmem_slot, warp, tmem_cols);
+  publish_smem_and_sync();
+  const uint32_t tmem_d = tmem_slot;
+  const int64_t n_sub = (M + ROWS - 1) / ROWS;
+  const int my_steps = (int64_t)blockIdx.x < n_sub ? (int)((n_sub - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+
+  if (warp >= kWsEpiWarps + 1) {
+    const int pt = threadIdx.x - kWsProdTid0;
+    const int offx = ws_store_offset<ROWS, K_PAD, 1>(pt), offy = ws_store_offset<ROWS, N_PAD, 1>(pt);
+    const bool x_vec = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && K_in >= K_PAD;
+    const bool y_vec = ((lddy & 3) == 0) && ((reinterpret_cast<uintptr_t>(dY) & 15) == 0) && N_out >= N_PAD;
+    int lstep = 0;
+    auto issue_load = [&](WsRegs<ROWS, K_PAD>& tx, WsRegs<ROWS, N_PAD>& ty) {
+      const int64_t sub = blockIdx.x + (int64_t)lstep * gridDim.x;
+      const int rv = (int)min((int64_t)ROWS, M - sub * ROWS);
+      if (x_vec && rv == ROWS) ws_load<ROWS, K_PAD, true>(tx, X + sub * ROWS * ldx, ldx, pt, ROWS, K_PAD);
+      else ws_load<ROWS, K_PAD, false>(tx, X + sub * ROWS * ldx, ldx, pt, rv, K_in);
+      if (y_vec && rv == ROWS) ws_load<ROWS, N_PAD, true>(ty, dY + sub * ROWS * lddy, lddy, pt, ROWS, N_PAD);
+      else ws_load<ROWS, N_PAD, false>(ty, dY + sub * ROWS * lddy, lddy, pt, rv, N_out);
+      ++lstep;
+    };
+    int st = 0;
+    uint32_t use = 0;
+    auto step_body = [&](WsRegs<ROWS, K_PAD>& cx, WsRegs<ROWS, N_PAD>& cy, WsRegs<ROWS, K_PAD>& nx, WsRegs<ROWS, N_PAD>& ny, int s) {
+      if (s + 1 < my_steps) issue_load(nx, ny);
+      if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
+      float* b = st_base + (size_t)st * STAGE;
+      ws_store<ROWS, K_PAD>(cx, b, b + ROWS * K_PAD, offx);
+      ws_store<ROWS, N_PAD>(cy, b + 2 * ROWS * K_PAD, b + 2 * ROWS * K_PAD + ROWS * N_PAD, offy);
+      fence_async_smem();
+      mbar_arrive(&full[st]);
+      if (++st == n_stages) { st = 0; ++use; }
+    };
+    WsRegs<ROWS, K_PAD> xa, xb;
+    WsRegs<ROWS, N_PAD> ya, yb;
+    if (my_steps > 0) issue_load(xa, ya);
+    for (int s = 0; s < my_steps; s += 2) {
+      step_body(xa, ya, xb, yb, s);
+      if (s + 1 < my_steps) step_body(xb, yb, xa, ya, s + 1);
+    }
+  } else if (warp == kWsEpiWarps) {
+    if (lane == 0) {
+      // M = 128 rows of D; when K_PAD < 128 the MN blocks beyond the X tile read whatever follows in shared memory
+      // (the allocation keeps ROWS x 128 floats of slack): those D rows (k >= K_in) are never read back.
+      const uint32_t idesc = umma_idesc_tf32(128, N_PAD, 1, 1);
+      int st = 0;
+      uint32_t use = 0;
+      for (int s = 0; s < my_steps; ++s) {
+        mbar_wait_sleep(&full[st], use & 1);
+        tc_fence_after();
+        const uint32_t b = smem_u32(st_base + (size_t)st * STAGE);
+        const uint64_t a_d[2] = {desc_mnmajor(b, ROWS, 0), desc_mnmajor(b + ROWS * K_PAD * 4, ROWS, 0)};
+        const uint64_t b_d[2] = {desc_mnmajor(b + 2 * ROWS * K_PAD * 4, ROWS, 0),
+                                 desc_mnmajor(b + (2 * ROWS * K_PAD + ROWS * N_PAD) * 4, ROWS, 0)};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi
+          const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
+#pragma unroll
+          for (int r8 = 0; r8 < ROWS / 8; ++r8)  // K-steps of 8 samples (1024 bytes each)
+            umma_tf32(tmem_d, ad0 + (uint32_t)(r8 * 64), bd0 + (uint32_t)(r8 * 64), idesc, (uint32_t)((s | t | r8) != 0));
+        }
+        umma_commit(&empty[st]);
+        if (++st == n_stages) { st = 0; ++use; }
+      }
+      umma_commit(&done);
+    }
+  } else if (my_steps > 0) {
+    mbar_wait_sleep(&done, 0);
+    tc_fence_after();
+    const int quad = warp;
+    const int k = quad * 32 + lane;  // D row = input feature index
+    const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
+    for (int c0 = 0; c0 < N_PAD; c0 += 16) {
+      if (c0 >= N_out) break;
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (k < K_in) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < N_out) red_add_f32(dW + (int64_t)(c0 + j) * lddw + k, __uint_as_float(v[j]));
+      }
+    }
+  }
+  tmem_free_cols(tmem_d, warp, tmem_cols);
 }
 
 static int pad_dim(int x) { return x <= 32 ? 32 : (x <= 64 ? 64 : 128); }  // operand tile widths: 32 | 64 | 128
@@ -497,9 +791,92 @@ static bool launch_pipe(const float* A, int64_t lda, const float* W, int64_t ldw
   return true;
 }
 
+// One tc_ws_gemm_kernel launch (same contract as launch_pipe).  Returns false when the shape does not fit.
+template <int B_MN, int KS, int ACT, bool MASK>
+static void launch_ws_inst(const PipeArgs& P, int n_stages, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = tc_ws_gemm_kernel<B_MN, KS, ACT, MASK>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, kWsThreads, smem, st>>>(P, n_stages);
+}
+template <int B_MN>
+static bool launch_ws(const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo, int64_t M, int N_total,
+                      int R, int act, const float* aux, int64_t ldaux, cudaStream_t st) {
+  if (getenv("KP_TC_WS") != nullptr && atoi(getenv("KP_TC_WS")) == 0) return false;
+  const size_t budget = 227 * 1024 - 1024;
+  int KS = 0, n_slices = 0, N_slice = 0, N_pad = 0, n_stages = 0;
+  // widest column slice, then the K-slice width that gives the deeper ring (>= 2 stages needed)
+  for (int cand = std::min(N_total, 128);; cand = (cand > 64 ? 64 : 32)) {
+    const int np = pad_dim(cand);
+    for (int ks : {64, 32}) {
+      if (ks == 64 && R <= 32) continue;
+      const int nsl = (int)ceil_div(R, ks);
+      const size_t b_bytes = (size_t)2 * np * nsl * ks * sizeof(float);
+      const size_t stage = (size_t)2 * 128 * ks * sizeof(float);
+      if (b_bytes + 2 * stage > budget) continue;
+      const int stages = (int)std::min<size_t>(kWsMaxStages, (budget - b_bytes) / stage);
+      if (KS == 0 || (ks == 32 && n_stages < 3 && stages > n_stages)) { KS = ks; n_slices = nsl; N_slice = cand; N_pad = np; n_stages = stages; }
+    }
+    if (KS != 0 || cand <= 32) break;
+  }
+  if (KS == 0) return false;
+  PipeArgs P;
+  P.A = A; P.lda = lda; P.W = W; P.ldw = ldw; P.OUT = OUT; P.ldo = ldo; P.aux = aux; P.ldaux = ldaux; P.M = M;
+  P.N_total = N_total; P.N_slice = N_slice; P.N_pad = N_pad; P.R = R; P.n_slices = n_slices; P.act = act; P.beta = 0;
+  const size_t smem = (size_t)2 * N_pad * n_slices * KS * sizeof(float) + (size_t)n_stages * 2 * 128 * KS * sizeof(float) + 1024;
+  const unsigned gy = (unsigned)ceil_div(N_total, N_slice);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n_tiles = ceil_div(M, 128);
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sms / gy));
+  const dim3 grid(gx, gy);
+  if (getenv("KP_TC_DEBUG") != nullptr)
+    fprintf(stderr, "[kp tc ws] B_MN=%d R=%d N=%d: KS=%d slices=%d N_slice=%d stages=%d smem=%zu grid=(%u,%u)\n", B_MN, R, N_total, KS,
+            n_slices, N_slice, n_stages, smem, gx, gy);
+  const bool mask = aux != nullptr;
+  if (B_MN) {
+    if (KS == 64) { if (mask) launch_ws_inst<1, 64, 0, true>(P, n_stages, grid, smem, st); else launch_ws_inst<1, 64, 0, false>(P, n_stages, grid, smem, st); }
+    else { if (mask) launch_ws_inst<1, 32, 0, true>(P, n_stages, grid, smem, st); else launch_ws_inst<1, 32, 0, false>(P, n_stages, grid, smem, st); }
+  } else {
+    if (KS == 64) {
+      if (act == ACT_RELU) launch_ws_inst<0, 64, ACT_RELU, false>(P, n_stages, grid, smem, st);
+      else if (act == ACT_SIGMOID) launch_ws_inst<0, 64, ACT_SIGMOID, false>(P, n_stages, grid, smem, st);
+      else launch_ws_inst<0, 64, ACT_NONE, false>(P, n_stages, grid, smem, st);
+    } else {
+      if (act == ACT_RELU) launch_ws_inst<0, 32, ACT_RELU, false>(P, n_stages, grid, smem, st);
+      else if (act == ACT_SIGMOID) launch_ws_inst<0, 32, ACT_SIGMOID, false>(P, n_stages, grid, smem, st);
+      else launch_ws_inst<0, 32, ACT_NONE, false>(P, n_stages, grid, smem, st);
+    }
+  }
+  kp::g_launches += 1;
+  return true;
+}
+
+template <int K_PAD, int N_PAD>
+static bool launch_ws_wgrad(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dW, int64_t lddw, int64_t M, int K,
+                            int N, cudaStream_t st) {
+  if (getenv("KP_TC_WS") != nullptr && atoi(getenv("KP_TC_WS")) == 0) return false;
+  constexpr int ROWS = 64;
+  const size_t stage = (size_t)2 * ROWS * (K_PAD + N_PAD) * sizeof(float);
+  const size_t slack = (size_t)ROWS * 128 * sizeof(float);  // the A operand always spans 4 MN blocks (M = 128)
+  const size_t budget = 227 * 1024 - 1024 - slack;
+  const int n_stages = (int)std::min<size_t>(kWsMaxStages, budget / stage);
+  if (n_stages < 2) return false;
+  const size_t smem = (size_t)n_stages * stage + slack + 1024;
+  auto kern = tc_ws_wgrad_kernel<K_PAD, N_PAD, ROWS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, ROWS), sms));
+  kern<<<grid, kWsThreads, smem, st>>>(X, ldx, dY, lddy, dW, lddw, M, K, N, n_stages);
+  return true;
+}
+
 template <int K_PAD, int N_PAD>
 static void launch_wgrad(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dW, int64_t lddw, int64_t M, int K,
                          int N, cudaStream_t st) {
+  if (launch_ws_wgrad<K_PAD, N_PAD>(X, ldx, dY, lddy, dW, lddw, M, K, N, st)) return;
   // the A operand always spans 4 MN blocks (M = 128): keep 4 blocks of slack after x_lo inside the allocation
   size_t smem = (size_t)(2 * 128 * K_PAD + 2 * 128 * N_PAD) * sizeof(float);
   const size_t need = (size_t)(128 * K_PAD + 128 * 128) * sizeof(float);
@@ -536,7 +913,9 @@ extern "C" int kp_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int
   KP_CHECK(X && W && Y && kp_tc_supported(N, K), "tc_linear_fwd: unsupported shape N=%d K=%d", N, K);
   KP_CHECK(act >= 0 && act <= 2, "tc_linear_fwd: act=%d", act);
   cudaStream_t st = as_stream(stream);
-  if (K <= 192 && launch_pipe<0>(X, ldx, W, ldw, Y, ldy, M, N, K, act, nullptr, 0, 0, st)) {
+  if (K <= 192 && launch_ws<0>(X, ldx, W, ldw, Y, ldy, M, N, K, act, nullptr, 0, st)) {
+    // warp-specialised pipeline
+  } else if (K <= 192 && launch_pipe<0>(X, ldx, W, ldw, Y, ldy, M, N, K, act, nullptr, 0, 0, st)) {
     // pipelined kernel: K sliced inside the kernel, output columns over grid.y
   } else if (tc_single(N, K)) {
     dispatch_rowtile<0>(pad_dim(K), X, ldx, W, ldw, Y, ldy, M, N, pad_dim(N), K, act, nullptr, 0, 0, st);
@@ -564,7 +943,9 @@ extern "C" int kp_tc_linear_bwd_data(const float* dY, int64_t lddy, const float*
   if (M == 0) return 0;
   KP_CHECK(dY && W && dX && kp_tc_supported(N, K), "tc_linear_bwd_data: unsupported shape N=%d K=%d", N, K);
   cudaStream_t st = as_stream(stream);
-  if (N <= 192 && launch_pipe<1>(dY, lddy, W, ldw, dX, lddx, M, K, N, 0, aux, ldaux, 0, st)) {
+  if (N <= 192 && launch_ws<1>(dY, lddy, W, ldw, dX, lddx, M, K, N, 0, aux, ldaux, st)) {
+    // warp-specialised pipeline
+  } else if (N <= 192 && launch_pipe<1>(dY, lddy, W, ldw, dX, lddx, M, K, N, 0, aux, ldaux, 0, st)) {
     // pipelined kernel: reduction over N_out sliced inside the kernel, output (K_in) columns over grid.y
   } else if (tc_single(N, K)) {
     // reduction over N_out (R), output width K_in

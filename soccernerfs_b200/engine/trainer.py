@@ -25,12 +25,14 @@ from .optimizers import Optimizers, cosine_decay_factor
 
 
 class TrainStep:
+    REG_ADAM_AUTO_BYTES = 512 << 20  # fuse_reg_adam=None: planes at least this large use the fused regulariser + Adam pass
+
     def __init__(self, model: KPlanesModel, max_steps: int = 30000, lr: float = 1e-2, eps: float = 1e-12,
                  warm_up_end: int = 512, data_parallel: bool = False, use_cuda_graph: bool = False,
                  fuse_grad_accumulation: bool = True, overlap_branches: bool = True,
                  overlap_proposal_backward: Optional[bool] = None, allreduce_mode: str = "overlap",
                  allreduce_backend: str = "peer", fuse_regularizers: bool = True,
-                 shard_optimizer: Optional[bool] = None) -> None:
+                 shard_optimizer: Optional[bool] = None, fuse_reg_adam: Optional[bool] = None) -> None:
         """``overlap_branches``: run the two branches of the step that do not depend on the main field's backward on
         their own CUDA streams (same arithmetic, same results): the plane regularisers (forward AND backward depend on
         the planes only) during the forward pass, and the back-propagation through the proposal networks (depends on
@@ -47,7 +49,12 @@ class TrainStep:
         collectives -- parameters also live in the peer arenas, every rank keeps Adam's moments for 1/world of each
         group only, and ONE kernel per group reduce-scatters the gradients, updates the owned shard and all-gathers the
         new parameters (``distributed.ShardedAdamGroup``).  Same NVLink bytes as the all-reduce; Adam's HBM traffic and
-        optimizer memory drop by 1/world and the reduced gradient is never materialised."""
+        optimizer memory drop by 1/world and the reduced gradient is never materialised.
+        ``fuse_reg_adam`` (None = on when applicable -- gradient sinks, all six regularisers, CUDA, no gradient collective
+        -- and the planes are HBM-resident, >= REG_ADAM_AUTO_BYTES): the plane regularisers are not evaluated as a branch of the step at all -- their gradient is computed
+        from the pre-update planes INSIDE the optimizer's streaming pass (``kp_plane_reg_adam``),
+        which also leaves the planes' gradient buffers zeroed for the next step; the six loss values come out of the same
+        pass and are added to the reported loss after it."""
         self.model = model
         self.max_steps, self.base_lr, self.warm_up_end = max_steps, lr, warm_up_end
         self.optimizers = Optimizers(model.get_param_groups(), lr=lr, eps=eps, warm_up_end=warm_up_end, max_steps=max_steps)
@@ -99,6 +106,22 @@ class TrainStep:
         self._reg_written = None
         if fuse_grad_accumulation and self.buckets and on_cuda and model.fused_regularizers_applicable() and fuse_regularizers:
             self._reg_written = frozenset(id(p) for p in model.regularized_planes() if p.requires_grad)
+        # (f1) regulariser stencil folded into the optimizer pass
+        self._reg_adam = None
+        if (fuse_reg_adam is None or fuse_reg_adam) and self._reg_written is not None and not self.reduce_grads:
+            from .optimizers import PlaneRegAdamPlan
+
+            plan = PlaneRegAdamPlan(model)
+            # automatic: only where the planes are HBM-resident (the sweep costs 2 of ~9 passes over them).  While they
+            # mostly fit the 126 MB L2 the regulariser sweep hides on its side stream and folding it into the optimizer
+            # pass would put it ON the critical path.
+            plane_bytes = sum(p.numel() for p in plan.planes) * 4
+            if plan.supported and (fuse_reg_adam or plane_bytes >= self.REG_ADAM_AUTO_BYTES):
+                self._reg_adam = plan
+                self._reg_adam_first = True
+        if fuse_reg_adam and self._reg_adam is None:
+            raise RuntimeError("fuse_reg_adam=True needs CUDA, the gradient sinks, the fused regularisers (dynamic scene, all six "
+                               "regulariser coefficients), plane feature dims in {4,8,16,32} and no gradient collective")
         self._field_ready = None
         self._scale_ready: Dict[int, "torch.cuda.Event"] = {}
         self._comm_stream = None
@@ -136,8 +159,13 @@ class TrainStep:
     def _iteration(self, ray_bundle: RayBundle, batch: Dict[str, torch.Tensor], grad_scale_override=None):
         model = self.model
         if self.buckets:
+            # planes whose gradient is written in full by the regulariser sweep, or (f1) left zeroed by the previous
+            # step's fused regulariser + Adam pass, are not memset
+            skip = self._reg_written
+            if self._reg_adam is not None and self._reg_adam_first:
+                skip, self._reg_adam_first = None, False  # first step: nothing has zeroed the planes' gradients yet
             for b in self.buckets.values():
-                b.attach_zeroed(sink=self.fuse_grad_accumulation, skip=self._reg_written)
+                b.attach_zeroed(sink=self.fuse_grad_accumulation, skip=skip)
         else:
             self.optimizers.zero_grad_all()
         self._field_ready = None
@@ -147,7 +175,9 @@ class TrainStep:
         self._reg_mark = ops.PLANE_REG_BACKWARDS
         regs = None
         main = torch.cuda.current_stream() if self.overlap else None
-        if self.overlap or self._reg_written:
+        if self._reg_adam is not None:
+            regs = {}  # evaluated inside the optimizer pass; merged into the loss dict after it
+        elif self.overlap or self._reg_written:
             # regulariser branch: values and gradients (straight into the sinks) on its own stream, under the forward
             # pass; joined before the main backward, whose scatter kernels update the same gradients atomically
             if self.overlap:
@@ -165,7 +195,7 @@ class TrainStep:
                 if regs:
                     regs_vec = torch.stack(list(regs.values()))  # the loss head adds these into the total
         outputs = model(ray_bundle)
-        if self.overlap or self._reg_written:
+        if self._reg_adam is None and (self.overlap or self._reg_written):
             if self.overlap:
                 main.wait_stream(self._reg_stream)
             if regs:
@@ -232,7 +262,11 @@ class TrainStep:
                 prop.all_reduce()
             main.wait_stream(comm)  # join
             grad_scale = 1.0 / self.world
-        self.optimizers.optimizer_step_all(grad_scale=grad_scale, use_device_hyper=self._in_graph_body)
+        self.optimizers.optimizer_step_all(grad_scale=grad_scale, use_device_hyper=self._in_graph_body, plane_reg=self._reg_adam)
+        if self._reg_adam is not None:
+            regs = self._reg_adam.values()
+            loss_dict.update(regs)
+            loss = loss.detach() + torch.stack(list(regs.values())).sum()
         return self._finish(loss_dict, loss, metrics)
 
     def _sharded_step(self, name: str) -> None:

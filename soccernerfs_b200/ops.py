@@ -932,6 +932,37 @@ def adam_step_(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
          float(grad_scale), stream_ptr())
 
 
+def plane_reg_adam_supported(c: int) -> bool:
+    return bool(_lib.load().kp_plane_reg_adam_supported(int(c)))
+
+
+def plane_reg_adam_scratch_bytes(planes: Sequence[torch.Tensor]) -> int:
+    hwc, _ = _reg_tables(planes, [0] * len(planes))
+    return int(_lib.load().kp_plane_reg_adam_scratch_bytes(hwc, len(planes)))
+
+
+def plane_reg_adam_(planes, grads, exp_avgs, exp_avg_sqs, terms, coef_dev, lr, beta1, beta2, eps, weight_decay, step,
+                    grad_scale, scratch: torch.Tensor, sums: Optional[torch.Tensor] = None, zero_grads: bool = True,
+                    hyper_dev: Optional[torch.Tensor] = None) -> None:
+    """(f1) regulariser stencil + Adam in one streaming pass per plane (kp_plane_reg_adam): planes / grads / moments are
+    channel-last [1,C,H,W] tensors sharing one layout; ``coef_dev`` [P,4] weights the four regulariser sums' gradients,
+    which are computed from the pre-update planes and added to ``grads * grad_scale``; ``sums`` [P,4] float64 (optional)
+    accumulates the sums themselves (the loss values); ``zero_grads`` leaves the gradient buffers zeroed for the next
+    step.  ``scratch``: uint8 CUDA tensor of >= plane_reg_adam_scratch_bytes(planes) bytes."""
+    n = len(planes)
+    if n == 0:
+        return
+    for p, g, m, v in zip(planes, grads, exp_avgs, exp_avg_sqs):
+        if not is_channel_last(p) or not (g.stride() == p.stride() == m.stride() == v.stride()) or g.dtype != torch.float32:
+            raise RuntimeError("plane_reg_adam_: plane / grad / moments must share one channel-last fp32 layout")
+        ptr_cl(p)
+    hwc, tm = _reg_tables(planes, terms)
+    call("kp_plane_reg_adam", _plane_ptrs(planes), _plane_ptrs(grads), _plane_ptrs(exp_avgs), _plane_ptrs(exp_avg_sqs), hwc, tm, n,
+         ptr(f32c(coef_dev)), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
+         ptr(hyper_dev), ptr(sums), c_void_p(scratch.data_ptr()), int(scratch.numel() * scratch.element_size()), int(zero_grads),
+         stream_ptr())
+
+
 def adam_multi_(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
                 hyper_dev: Optional[torch.Tensor] = None) -> None:
     """One launch of torch.optim.Adam's update over a list of dense fp32 tensors (same layout per tuple)."""

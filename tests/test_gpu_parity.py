@@ -750,6 +750,50 @@ def test_fused_regularizer_sweep_matches_autograd_path():
         assert rel_err(p.grad, 2 * r) < 1e-6
 
 
+def test_plane_reg_adam_matches_regulariser_sweep_plus_adam():
+    """(f1) kp_plane_reg_adam -- regulariser stencil + Adam in one in-place streaming pass with a halo snapshot -- against
+    the two-pass path (kp_plane_reg_fused adds the regulariser gradient, kp_adam_multi steps): same sums, same planes and
+    moments after two steps, gradient buffers left zeroed.  Shapes cross tile boundaries in both directions (rows not a
+    multiple of 64, rows of 256+ float4, C = 8 and 32) so every halo path is exercised."""
+    from soccernerfs_b200 import ops
+
+    torch.manual_seed(3)
+    T_H, T_W, T_SMOOTH, T_L1 = 1, 2, 4, 8
+    specs = [((1, 32, 150, 70), T_H | T_W), ((1, 32, 100, 64), T_W | T_SMOOTH | T_L1), ((1, 8, 130, 200), T_H | T_W),
+             ((1, 8, 67, 128), T_W | T_SMOOTH | T_L1), ((1, 32, 5, 3), T_H | T_W), ((1, 16, 64, 64), T_W | T_SMOOTH | T_L1)]
+    planes = [(0.3 + 0.2 * torch.rand(sh, device=DEV)).contiguous(memory_format=torch.channels_last) for sh, _ in specs]
+    terms = [t for _, t in specs]
+    coef = (torch.rand(len(planes), 4, device=DEV) * 1e-2).contiguous()
+    lr, b1, b2, eps = 1e-2, 0.9, 0.999, 1e-12
+
+    def fresh():
+        return ([p.clone(memory_format=torch.preserve_format) for p in planes],
+                [torch.zeros_like(p, memory_format=torch.preserve_format) for p in planes],
+                [torch.zeros_like(p, memory_format=torch.preserve_format) for p in planes])
+
+    pa, ma, va = fresh()
+    pb, mb, vb = fresh()
+    scratch = torch.empty(ops.plane_reg_adam_scratch_bytes(planes), dtype=torch.uint8, device=DEV)
+    gb = [torch.zeros_like(p, memory_format=torch.preserve_format) for p in planes]
+    for step in (1, 2):
+        data = [1e-3 * torch.randn_like(p, memory_format=torch.preserve_format) for p in planes]
+        # two passes: the regulariser sweep adds onto the data gradient, then Adam
+        ga = [d.clone(memory_format=torch.preserve_format) * 0.5 for d in data]
+        sums_a = ops.plane_reg_fused(pa, terms, coef, ga, accumulate=True)
+        ops.adam_multi_(pa, ga, ma, va, lr, b1, b2, eps, 0.0, step, 1.0)
+        # one pass: data gradient scaled by grad_scale inside, regulariser gradient from the pre-update planes
+        for g_, d in zip(gb, data):
+            assert float(g_.abs().max()) == 0.0  # zeroed by the previous pass
+            g_.copy_(d)
+        sums_b = torch.zeros(len(planes), 4, dtype=torch.float64, device=DEV)
+        ops.plane_reg_adam_(pb, gb, mb, vb, terms, coef, lr, b1, b2, eps, 0.0, step, 0.5, scratch, sums=sums_b, zero_grads=True)
+        assert rel_err(sums_b.float(), sums_a.float()) < 1e-6
+        for i in range(len(planes)):
+            assert rel_err(mb[i], ma[i]) < 1e-5, (step, i)
+            assert rel_err(vb[i], va[i]) < 1e-5, (step, i)
+            assert float((pb[i] - pa[i]).abs().max()) < 1e-5 * lr * 100, (step, i)
+
+
 def test_train_step_with_and_without_fused_regularizers():
     """TrainStep(fuse_regularizers=True) (no memset of the planes' gradients, one regulariser sweep) follows the
     two-sweep step: same losses over 6 steps, eagerly and from the graph."""
@@ -760,14 +804,16 @@ def test_train_step_with_and_without_fused_regularizers():
     g = load_golden("model_tiny")
     mp = load_tiny_model(g)
     runs = {}
-    for mode in ("two-sweep", "fused", "fused-serial", "fused-graph"):
+    for mode in ("two-sweep", "fused", "fused-serial", "fused-graph", "reg-adam", "reg-adam-graph"):
         model = build_model("tiny", mp, g["aabb"], DEV)
         model.config.background_color_train = "black"
         model.proposal_sampler.initial_sampler.train_stratified = False
         model.proposal_sampler.pdf_sampler.train_stratified = False
         step = TrainStep(model, max_steps=100, warm_up_end=4, use_cuda_graph=mode.endswith("graph"),
-                         overlap_branches=mode != "fused-serial", fuse_regularizers=mode != "two-sweep")
+                         overlap_branches=mode != "fused-serial", fuse_regularizers=mode != "two-sweep",
+                         fuse_reg_adam=mode.startswith("reg-adam"))
         assert (step._reg_written is not None) == (mode != "two-sweep")
+        assert (step._reg_adam is not None) == mode.startswith("reg-adam")
         losses = []
         for i in range(6):
             out = step(ray_bundle(g["origins"], g["directions"], g["times"], DEV), {"image": g["image"].to(DEV)})
@@ -775,7 +821,7 @@ def test_train_step_with_and_without_fused_regularizers():
         torch.cuda.synchronize()
         runs[mode] = (losses, [p.detach().clone() for p in model.parameters()])
         step.close()
-    for mode in ("fused", "fused-serial", "fused-graph"):
+    for mode in ("fused", "fused-serial", "fused-graph", "reg-adam", "reg-adam-graph"):
         for a, b in zip(runs["two-sweep"][0], runs[mode][0]):
             for x, y in zip(a, b):
                 assert abs(x - y) <= 2e-4 * abs(x) and x > 0, (mode, a, b)
