@@ -74,14 +74,16 @@ static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const*
   F.concat = concat;
   // Warp aggregation pays where consecutive samples of a ray share texels: the coarse scales.  A ray crosses at most
   // ~R texels of an R^2 plane with S samples, so neighbours coincide often when R <= ~4 S; finer scales skip the
-  // extra shuffles.  KP_SCATTER_AGG=all|none overrides (A/B measurements).
+  // extra shuffles.
   F.agg_mask = 0;
   const char* agg = getenv("KP_SCATTER_AGG");
   for (int k = 0; k < n_scales; ++k) {
     const int r = std::max(F.reso[k][0], std::max(F.reso[k][1], F.reso[k][2]));
-    bool on = r <= 256;
+    // measured on B200 (gpurun_out r2_bench_agg_*: scatter 0.477 ms without, 0.511 ms with the coarse scales merged): the
+    // shuffle work costs more than the reds it removes, so merging is opt-in (KP_SCATTER_AGG=auto: coarse scales, =all)
+    bool on = false;
+    if (agg != nullptr && strcmp(agg, "auto") == 0) on = r <= 256;
     if (agg != nullptr && strcmp(agg, "all") == 0) on = true;
-    if (agg != nullptr && strcmp(agg, "none") == 0) on = false;
     if (on) F.agg_mask |= 1u << k;
   }
   return 0;

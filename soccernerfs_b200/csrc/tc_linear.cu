@@ -22,6 +22,7 @@
 // 128 bytes, 32-byte chunk q of row r at chunk q ^ (r & 3)), so a tile is staged in the swizzle of the view it is
 // consumed in.
 #include <stdlib.h>
+#include <string.h>
 
 #include "tc_common.cuh"
 #include "tc_ws.cuh"
@@ -332,15 +333,17 @@ __global__ void __launch_bounds__(256) tc_pipe_kernel(const __grid_constant__ Pi
 //   accf[a]   : tcgen05.commit          -> the epilogue warps may unload accumulator a
 //   acce[a]   : 4 epilogue-warp arrivals -> the MMA warp may overwrite accumulator a
 // ---------------------------------------------------------------------------------------------------------------
-template <int B_MN, int KS, int ACT, bool MASK>
-__global__ void __launch_bounds__(kWsThreads, 1) tc_ws_gemm_kernel(const __grid_constant__ PipeArgs P, int n_stages) {
+template <int B_MN, int KS, int ACT, bool MASK, bool TMA>
+__global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
+    tc_ws_gemm_kernel(const __grid_constant__ PipeArgs P, const __grid_constant__ CUtensorMap tmA, int n_stages) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int kProdWarp0 = TMA ? kWsEpiWarps + 2 : kWsEpiWarps + 1;
   const int R_tot = P.n_slices * KS;
   const int b_rows = B_MN ? R_tot : P.N_pad, b_cols = B_MN ? P.N_pad : R_tot;
   float* b_hi = align1024(smem_raw);
   float* b_lo = b_hi + b_rows * b_cols;
   float* a_st = b_lo + b_rows * b_cols;  // [n_stages][hi | lo][128 x KS]
-  __shared__ __align__(8) uint64_t full[kWsMaxStages], empty[kWsMaxStages], accf[2], acce[2];
+  __shared__ __align__(8) uint64_t full[kWsMaxStages], empty[kWsMaxStages], tfull[kWsMaxStages], accf[2], acce[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.y * P.N_slice;
@@ -350,6 +353,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_gemm_kernel(const __grid_
     for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], kWsProdThreads);
       mbar_init(&empty[i], 1);
+      mbar_init(&tfull[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&accf[i], 1);
@@ -367,9 +371,42 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_gemm_kernel(const __grid_
   const int ns = P.n_slices;
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp >= kWsEpiWarps + 1) {
-    // ------------------------------------------------ producers ------------------------------------------------
-    const int pt = threadIdx.x - kWsProdTid0;
+  if (TMA && warp >= kProdWarp0) {
+    // ------------------------------------------------ producers (TMA-fed): derive lo from the landed hi tile ----
+    const int pt = threadIdx.x - 32 * kProdWarp0;
+    const int n_steps = my_tiles * ns;
+    int st = 0;
+    uint32_t use = 0;
+    for (int s = 0; s < n_steps; ++s) {
+      mbar_wait_sleep(&tfull[st], use & 1);  // the TMA boxes of this step have landed (async-proxy writes visible)
+      float* a_hi = a_st + st * (2 * 128 * KS);
+      ws_derive_lo<128 * KS / 4>(a_hi, a_hi + 128 * KS, pt);
+      fence_async_smem();
+      mbar_arrive(&full[st]);
+      if (++st == n_stages) { st = 0; ++use; }
+    }
+  } else if (TMA && warp == kTmaWarp) {
+    // ------------------------------------------------ TMA issuer -----------------------------------------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      int st = 0;
+      uint32_t use = 0;
+      for (int jl = 0; jl < my_tiles; ++jl) {
+        const int64_t tile = blockIdx.x + (int64_t)jl * gridDim.x;
+        for (int kc = 0; kc < ns; ++kc) {
+          if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);  // the MMAs that read this stage have completed
+          float* a_hi = a_st + st * (2 * 128 * KS);
+          mbar_expect_tx(&tfull[st], 128 * KS * 4);
+#pragma unroll
+          for (int kb = 0; kb < KS / 32; ++kb)
+            tma_load_2d(a_hi + kb * (128 * 32), &tmA, kc * KS + kb * 32, (int)(tile * 128), &tfull[st]);
+          if (++st == n_stages) { st = 0; ++use; }
+        }
+      }
+    }
+  } else if (!TMA && warp >= kProdWarp0) {
+    // ------------------------------------------------ producers (register-fed) ---------------------------------
+    const int pt = threadIdx.x - 32 * kProdWarp0;
     const int off0 = ws_store_offset<128, KS, 0>(pt);
     const bool a_vec = ((P.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15) == 0);
     const int n_steps = my_tiles * ns;
@@ -385,20 +422,26 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_gemm_kernel(const __grid_
     };
     int st = 0;
     uint32_t use = 0;
-    auto step_body = [&](WsRegs<128, KS>& cur, WsRegs<128, KS>& nxt, int s) {
-      if (s + 1 < n_steps) issue_load(nxt);  // in flight while this step is converted and stored
-      if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
-      float* a_hi = a_st + st * (2 * 128 * KS);
-      ws_store<128, KS>(cur, a_hi, a_hi + 128 * KS, off0);
-      fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-      mbar_arrive(&full[st]);
-      if (++st == n_stages) { st = 0; ++use; }
-    };
-    WsRegs<128, KS> ra, rb;
-    if (n_steps > 0) issue_load(ra);
-    for (int s = 0; s < n_steps; s += 2) {
-      step_body(ra, rb, s);
-      if (s + 1 < n_steps) step_body(rb, ra, s + 1);
+    // register ring of D steps: D x (128 x KS x 4 bytes) of loads in flight per CTA, so the global-memory latency is
+    // spread over D steps of conversion work instead of being paid once per step
+    constexpr int D = KS == 32 ? 4 : 2;
+    WsRegs<128, KS> ring[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      if (d < n_steps) issue_load(ring[d]);
+    for (int s = 0; s < n_steps; s += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (s + d < n_steps) {
+          if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
+          float* a_hi = a_st + st * (2 * 128 * KS);
+          ws_store<128, KS>(ring[d], a_hi, a_hi + 128 * KS, off0);
+          fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+          mbar_arrive(&full[st]);
+          if (++st == n_stages) { st = 0; ++use; }
+          if (s + d + D < n_steps) issue_load(ring[d]);  // refill this slot: step s + d + D
+        }
+      }
     }
   } else if (warp == kWsEpiWarps) {
     // ------------------------------------------------ MMA issuer -----------------------------------------------
@@ -420,15 +463,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_gemm_kernel(const __grid_
           tc_fence_after();
           const uint32_t a_base = smem_u32(a_st + st * (2 * 128 * KS));
           const uint64_t a_d[2] = {desc_kmajor(a_base, 128, 0, 0), desc_kmajor(a_base + 128 * KS * 4, 128, 0, 0)};
+          // forward: lo*lo + lo*hi + hi*lo + hi*hi (small terms first): the pre-activations decide ReLU branches, so all
+          // four terms are kept.  Backward products (B_MN) feed no branch: the 2^-22-relative lo*lo term is dropped.
+          constexpr int T0 = B_MN ? 1 : 0;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi (small terms first)
+          for (int t = T0; t < 4; ++t) {
             const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
 #pragma unroll
             for (int k8 = 0; k8 < KS / 8; ++k8) {
               const int kk = kc * (KS / 8) + k8;  // K step within the whole reduction
               const uint32_t a_off = (uint32_t)(((k8 >> 2) * 128 * 128 + (k8 & 3) * 32) >> 4);
               const uint32_t b_off = B_MN ? (uint32_t)((kk * 1024) >> 4) : (uint32_t)(kk >> 2) * b_blk + (uint32_t)(((kk & 3) * 32) >> 4);
-              umma_tf32(tmem_d, ad0 + a_off, bd0 + b_off, idesc, (kc | t | k8) != 0);
+              umma_tf32(tmem_d, ad0 + a_off, bd0 + b_off, idesc, (kc | (t - T0) | k8) != 0);
             }
           }
           umma_commit(&empty[st]);  // arrives when the MMAs above have read the stage
@@ -440,9 +486,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_gemm_kernel(const __grid_
   } else {
     // ------------------------------------------------ epilogue -------------------------------------------------
     const int quad = warp;  // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;
     const bool o_vec = ((P.ldo & 3) == 0) && (((reinterpret_cast<uintptr_t>(P.OUT) + (size_t)col0 * 4) & 15) == 0);
     const bool m_vec = !MASK || (((P.ldaux & 3) == 0) && (((reinterpret_cast<uintptr_t>(P.aux) + (size_t)col0 * 4) & 15) == 0));
+    const bool fastv = o_vec && m_vec;
+    float* epi = a_st + (size_t)n_stages * (2 * 128 * KS) + quad * (32 * 36);  // this warp's transpose buffer
     for (int jl = 0; jl < my_tiles; ++jl) {
       const int acc = jl & 1;
       const uint32_t ua = (uint32_t)jl >> 1;
@@ -452,49 +499,65 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_gemm_kernel(const __grid_
       mbar_wait_sleep(&accf[acc], ua & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * P.N_pad) + ((uint32_t)(quad * 32) << 16);
-      float* dst_row = P.OUT + (row0 + row) * P.ldo + col0;
-      const float* aux_row = MASK ? P.aux + (row0 + row) * P.ldaux + col0 : nullptr;
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        const bool fast = o_vec && m_vec && (c0 + 16 <= N);
-        float4 m4[4];
-        if (MASK && fast && row < rows_valid) {
+      // Accumulator rows arrive one per lane (tcgen05.ld 32x32b).  Storing them like that would touch 32 different 128-byte
+      // lines per STG (ncu: the epilogue's uncoalesced LDG/STG kept l1tex at 58 % and bounded the kernel), so each 32 x 32
+      // block goes through a padded shared-memory transpose: afterwards a lane owns 16 bytes of a row and a warp-wide
+      // LDG / STG covers 4 rows x 128 contiguous bytes.
+      const int rows_w = min(32, rows_valid - quad * 32);  // valid rows among this warp's 32 (may be <= 0)
+      const int rr = lane >> 3, cc = (lane & 7) * 4;
+      float* out_w = P.OUT + (row0 + quad * 32) * P.ldo + col0;
+      const float* aux_w = MASK ? P.aux + (row0 + quad * 32) * P.ldaux + col0 : nullptr;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        const int c = c0 + cc;
+        const bool vec = fastv && (c + 4 <= N);
+        float4 m4[8];
+        if (MASK && vec) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) m4[q] = __ldg(reinterpret_cast<const float4*>(aux_row + c0 + 4 * q));
+          for (int it = 0; it < 8; ++it)
+            if (it * 4 + rr < rows_w) m4[it] = __ldg(reinterpret_cast<const float4*>(aux_w + (int64_t)(it * 4 + rr) * P.ldaux + c));
         }
-        uint32_t v[16];
+        uint32_t v[32];
         tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld16(taddr + (uint32_t)c0 + 16u, v + 16);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < rows_valid) {
-          float x[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            x[j] = __uint_as_float(v[j]);
-            if (ACT == ACT_RELU) x[j] = fmaxf(x[j], 0.f);
-            else if (ACT == ACT_SIGMOID) x[j] = 1.f / (1.f + expf(-x[j]));
-          }
-          if (fast) {
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(epi + lane * 36 + 4 * q) =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 o4 = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-              if (MASK) {
-                if (!(m4[q].x > 0.f)) o4.x = 0.f;
-                if (!(m4[q].y > 0.f)) o4.y = 0.f;
-                if (!(m4[q].z > 0.f)) o4.z = 0.f;
-                if (!(m4[q].w > 0.f)) o4.w = 0.f;
-              }
-              *reinterpret_cast<float4*>(dst_row + c0 + 4 * q) = o4;
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rr;
+          if (r < rows_w && c < N) {
+            float4 x = *reinterpret_cast<const float4*>(epi + r * 36 + cc);
+            if (ACT == ACT_RELU) {
+              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+            } else if (ACT == ACT_SIGMOID) {
+              x.x = 1.f / (1.f + expf(-x.x)); x.y = 1.f / (1.f + expf(-x.y)); x.z = 1.f / (1.f + expf(-x.z)); x.w = 1.f / (1.f + expf(-x.w));
             }
-          } else {
+            float* dst = out_w + (int64_t)r * P.ldo + c;
+            if (vec) {
+              if (MASK) {
+                if (!(m4[it].x > 0.f)) x.x = 0.f;
+                if (!(m4[it].y > 0.f)) x.y = 0.f;
+                if (!(m4[it].z > 0.f)) x.z = 0.f;
+                if (!(m4[it].w > 0.f)) x.w = 0.f;
+              }
+              *reinterpret_cast<float4*>(dst) = x;
+            } else {
+              const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (c0 + j < N) {
-                float o1 = x[j];
-                if (MASK && !(aux_row[c0 + j] > 0.f)) o1 = 0.f;
-                dst_row[c0 + j] = o1;
+              for (int j = 0; j < 4; ++j) {
+                if (c + j < N) {
+                  float o1 = xs[j];
+                  if (MASK && !(aux_w[(int64_t)r * P.ldaux + c + j] > 0.f)) o1 = 0.f;
+                  dst[j] = o1;
+                }
               }
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();  // this warp's TMEM reads are ordered before the arrival the MMA warp waits on
       __syncwarp();
@@ -594,15 +657,16 @@ __global__ void __launch_bounds__(256) tc_wgrad_kernel(const float* __restrict__
 // producer warps into an n_stages ring; the MMA warp accumulates every step into ONE TMEM accumulator; after the last
 // step the epilogue warps add D into dW with one red per weight.
 // ---------------------------------------------------------------------------------------------------------------
-template <int K_PAD, int N_PAD, int ROWS>
-__global__ void __launch_bounds__(kWsThreads, 1) tc_ws_wgrad_kernel(const float* __restrict__ X, int64_t ldx,
-                                                                    const float* __restrict__ dY, int64_t lddy,
-                                                                    float* __restrict__ dW, int64_t lddw, int64_t M, int K_in,
-                                                                    int N_out, int n_stages) {
+template <int K_PAD, int N_PAD, int ROWS, bool TMA>
+__global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
+    tc_ws_wgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy, float* __restrict__ dW,
+                       int64_t lddw, int64_t M, int K_in, int N_out, int n_stages, const __grid_constant__ CUtensorMap tmX,
+                       const __grid_constant__ CUtensorMap tmY) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int STAGE = 2 * ROWS * (K_PAD + N_PAD);  // floats: [x_hi | x_lo | y_hi | y_lo]
+  constexpr int kProdWarp0 = TMA ? kWsEpiWarps + 2 : kWsEpiWarps + 1;
   float* st_base = align1024(smem_raw);
-  __shared__ __align__(8) uint64_t full[kWsMaxStages], empty[kWsMaxStages], done;
+  __shared__ __align__(8) uint64_t full[kWsMaxStages], empty[kWsMaxStages], tfull[kWsMaxStages], done;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t tmem_cols = N_PAD <= 32 ? 32u : (N_PAD <= 64 ? 64u : 128u);
@@ -610,6 +674,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_wgrad_kernel(const float*
     for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], kWsProdThreads);
       mbar_init(&empty[i], 1);
+      mbar_init(&tfull[i], 1);
     }
     mbar_init(&done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -620,8 +685,41 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_wgrad_kernel(const float*
   const int64_t n_sub = (M + ROWS - 1) / ROWS;
   const int my_steps = (int64_t)blockIdx.x < n_sub ? (int)((n_sub - 1 - blockIdx.x) / gridDim.x + 1) : 0;
 
-  if (warp >= kWsEpiWarps + 1) {
-    const int pt = threadIdx.x - kWsProdTid0;
+  if (TMA && warp >= kProdWarp0) {
+    // producers (TMA-fed): derive both lo operands from the landed hi tiles
+    const int pt = threadIdx.x - 32 * kProdWarp0;
+    int st = 0;
+    uint32_t use = 0;
+    for (int s = 0; s < my_steps; ++s) {
+      mbar_wait_sleep(&tfull[st], use & 1);
+      float* b = st_base + (size_t)st * STAGE;
+      ws_derive_lo<ROWS * K_PAD / 4>(b, b + ROWS * K_PAD, pt);
+      ws_derive_lo<ROWS * N_PAD / 4>(b + 2 * ROWS * K_PAD, b + 2 * ROWS * K_PAD + ROWS * N_PAD, pt);
+      fence_async_smem();
+      mbar_arrive(&full[st]);
+      if (++st == n_stages) { st = 0; ++use; }
+    }
+  } else if (TMA && warp == kTmaWarp) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmY);
+      int st = 0;
+      uint32_t use = 0;
+      for (int s = 0; s < my_steps; ++s) {
+        const int64_t sub = blockIdx.x + (int64_t)s * gridDim.x;
+        if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
+        float* b = st_base + (size_t)st * STAGE;
+        mbar_expect_tx(&tfull[st], ROWS * (K_PAD + N_PAD) * 4);
+#pragma unroll
+        for (int kb = 0; kb < K_PAD / 32; ++kb) tma_load_2d(b + kb * (ROWS * 32), &tmX, kb * 32, (int)(sub * ROWS), &tfull[st]);
+#pragma unroll
+        for (int kb = 0; kb < N_PAD / 32; ++kb)
+          tma_load_2d(b + 2 * ROWS * K_PAD + kb * (ROWS * 32), &tmY, kb * 32, (int)(sub * ROWS), &tfull[st]);
+        if (++st == n_stages) { st = 0; ++use; }
+      }
+    }
+  } else if (!TMA && warp >= kProdWarp0) {
+    const int pt = threadIdx.x - 32 * kProdWarp0;
     const int offx = ws_store_offset<ROWS, K_PAD, 1>(pt), offy = ws_store_offset<ROWS, N_PAD, 1>(pt);
     const bool x_vec = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && K_in >= K_PAD;
     const bool y_vec = ((lddy & 3) == 0) && ((reinterpret_cast<uintptr_t>(dY) & 15) == 0) && N_out >= N_PAD;
@@ -637,22 +735,26 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_wgrad_kernel(const float*
     };
     int st = 0;
     uint32_t use = 0;
-    auto step_body = [&](WsRegs<ROWS, K_PAD>& cx, WsRegs<ROWS, N_PAD>& cy, WsRegs<ROWS, K_PAD>& nx, WsRegs<ROWS, N_PAD>& ny, int s) {
-      if (s + 1 < my_steps) issue_load(nx, ny);
-      if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
-      float* b = st_base + (size_t)st * STAGE;
-      ws_store<ROWS, K_PAD>(cx, b, b + ROWS * K_PAD, offx);
-      ws_store<ROWS, N_PAD>(cy, b + 2 * ROWS * K_PAD, b + 2 * ROWS * K_PAD + ROWS * N_PAD, offy);
-      fence_async_smem();
-      mbar_arrive(&full[st]);
-      if (++st == n_stages) { st = 0; ++use; }
-    };
-    WsRegs<ROWS, K_PAD> xa, xb;
-    WsRegs<ROWS, N_PAD> ya, yb;
-    if (my_steps > 0) issue_load(xa, ya);
-    for (int s = 0; s < my_steps; s += 2) {
-      step_body(xa, ya, xb, yb, s);
-      if (s + 1 < my_steps) step_body(xb, yb, xa, ya, s + 1);
+    constexpr int D = 2;  // register ring: two steps of loads in flight
+    WsRegs<ROWS, K_PAD> rx[D];
+    WsRegs<ROWS, N_PAD> ry[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      if (d < my_steps) issue_load(rx[d], ry[d]);
+    for (int s = 0; s < my_steps; s += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (s + d < my_steps) {
+          if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
+          float* b = st_base + (size_t)st * STAGE;
+          ws_store<ROWS, K_PAD>(rx[d], b, b + ROWS * K_PAD, offx);
+          ws_store<ROWS, N_PAD>(ry[d], b + 2 * ROWS * K_PAD, b + 2 * ROWS * K_PAD + ROWS * N_PAD, offy);
+          fence_async_smem();
+          mbar_arrive(&full[st]);
+          if (++st == n_stages) { st = 0; ++use; }
+          if (s + d + D < my_steps) issue_load(rx[d], ry[d]);
+        }
+      }
     }
   } else if (warp == kWsEpiWarps) {
     if (lane == 0) {
@@ -669,11 +771,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) tc_ws_wgrad_kernel(const float*
         const uint64_t b_d[2] = {desc_mnmajor(b + 2 * ROWS * K_PAD * 4, ROWS, 0),
                                  desc_mnmajor(b + (2 * ROWS * K_PAD + ROWS * N_PAD) * 4, ROWS, 0)};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi
+        for (int t = 1; t < 4; ++t) {  // lo*hi + hi*lo + hi*hi (lo*lo, 2^-22 relative, dropped: the sum feeds no branch)
           const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
 #pragma unroll
           for (int r8 = 0; r8 < ROWS / 8; ++r8)  // K-steps of 8 samples (1024 bytes each)
-            umma_tf32(tmem_d, ad0 + (uint32_t)(r8 * 64), bd0 + (uint32_t)(r8 * 64), idesc, (uint32_t)((s | t | r8) != 0));
+            umma_tf32(tmem_d, ad0 + (uint32_t)(r8 * 64), bd0 + (uint32_t)(r8 * 64), idesc, (uint32_t)((s | (t - 1) | r8) != 0));
         }
         umma_commit(&empty[st]);
         if (++st == n_stages) { st = 0; ++use; }
@@ -793,16 +895,25 @@ static bool launch_pipe(const float* A, int64_t lda, const float* W, int64_t ldw
 
 // One tc_ws_gemm_kernel launch (same contract as launch_pipe).  Returns false when the shape does not fit.
 template <int B_MN, int KS, int ACT, bool MASK>
-static void launch_ws_inst(const PipeArgs& P, int n_stages, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = tc_ws_gemm_kernel<B_MN, KS, ACT, MASK>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<grid, kWsThreads, smem, st>>>(P, n_stages);
+static void launch_ws_inst(const PipeArgs& P, const CUtensorMap* tm, int n_stages, dim3 grid, size_t smem, cudaStream_t st) {
+  if (tm != nullptr) {
+    auto kern = tc_ws_gemm_kernel<B_MN, KS, ACT, MASK, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kTmaThreads, smem, st>>>(P, *tm, n_stages);
+  } else {
+    auto kern = tc_ws_gemm_kernel<B_MN, KS, ACT, MASK, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CUtensorMap dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    kern<<<grid, kWsThreads, smem, st>>>(P, dummy, n_stages);
+  }
 }
 template <int B_MN>
 static bool launch_ws(const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo, int64_t M, int N_total,
                       int R, int act, const float* aux, int64_t ldaux, cudaStream_t st) {
   if (getenv("KP_TC_WS") != nullptr && atoi(getenv("KP_TC_WS")) == 0) return false;
-  const size_t budget = 227 * 1024 - 1024;
+  const size_t epi_bytes = (size_t)kWsEpiWarps * 32 * 36 * sizeof(float);  // the epilogue warps' transpose buffers
+  const size_t budget = 227 * 1024 - 1024 - epi_bytes;
   int KS = 0, n_slices = 0, N_slice = 0, N_pad = 0, n_stages = 0;
   // widest column slice, then the K-slice width that gives the deeper ring (>= 2 stages needed)
   for (int cand = std::min(N_total, 128);; cand = (cand > 64 ? 64 : 32)) {
@@ -822,7 +933,7 @@ static bool launch_ws(const float* A, int64_t lda, const float* W, int64_t ldw, 
   PipeArgs P;
   P.A = A; P.lda = lda; P.W = W; P.ldw = ldw; P.OUT = OUT; P.ldo = ldo; P.aux = aux; P.ldaux = ldaux; P.M = M;
   P.N_total = N_total; P.N_slice = N_slice; P.N_pad = N_pad; P.R = R; P.n_slices = n_slices; P.act = act; P.beta = 0;
-  const size_t smem = (size_t)2 * N_pad * n_slices * KS * sizeof(float) + (size_t)n_stages * 2 * 128 * KS * sizeof(float) + 1024;
+  const size_t smem = (size_t)2 * N_pad * n_slices * KS * sizeof(float) + (size_t)n_stages * 2 * 128 * KS * sizeof(float) + epi_bytes + 1024;
   const unsigned gy = (unsigned)ceil_div(N_total, N_slice);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -834,18 +945,22 @@ static bool launch_ws(const float* A, int64_t lda, const float* W, int64_t ldw, 
     fprintf(stderr, "[kp tc ws] B_MN=%d R=%d N=%d: KS=%d slices=%d N_slice=%d stages=%d smem=%zu grid=(%u,%u)\n", B_MN, R, N_total, KS,
             n_slices, N_slice, n_stages, smem, gx, gy);
   const bool mask = aux != nullptr;
+  // activation tiles through the TMA engine when the matrix can be described by a tensor map (16-byte aligned rows)
+  CUtensorMap tmA;
+  const bool use_tma = !(getenv("KP_TC_TMA") != nullptr && atoi(getenv("KP_TC_TMA")) == 0) && make_tmap_2d(&tmA, A, M, R, lda, 128, false);
+  const CUtensorMap* tm = use_tma ? &tmA : nullptr;
   if (B_MN) {
-    if (KS == 64) { if (mask) launch_ws_inst<1, 64, 0, true>(P, n_stages, grid, smem, st); else launch_ws_inst<1, 64, 0, false>(P, n_stages, grid, smem, st); }
-    else { if (mask) launch_ws_inst<1, 32, 0, true>(P, n_stages, grid, smem, st); else launch_ws_inst<1, 32, 0, false>(P, n_stages, grid, smem, st); }
+    if (KS == 64) { if (mask) launch_ws_inst<1, 64, 0, true>(P, tm, n_stages, grid, smem, st); else launch_ws_inst<1, 64, 0, false>(P, tm, n_stages, grid, smem, st); }
+    else { if (mask) launch_ws_inst<1, 32, 0, true>(P, tm, n_stages, grid, smem, st); else launch_ws_inst<1, 32, 0, false>(P, tm, n_stages, grid, smem, st); }
   } else {
     if (KS == 64) {
-      if (act == ACT_RELU) launch_ws_inst<0, 64, ACT_RELU, false>(P, n_stages, grid, smem, st);
-      else if (act == ACT_SIGMOID) launch_ws_inst<0, 64, ACT_SIGMOID, false>(P, n_stages, grid, smem, st);
-      else launch_ws_inst<0, 64, ACT_NONE, false>(P, n_stages, grid, smem, st);
+      if (act == ACT_RELU) launch_ws_inst<0, 64, ACT_RELU, false>(P, tm, n_stages, grid, smem, st);
+      else if (act == ACT_SIGMOID) launch_ws_inst<0, 64, ACT_SIGMOID, false>(P, tm, n_stages, grid, smem, st);
+      else launch_ws_inst<0, 64, ACT_NONE, false>(P, tm, n_stages, grid, smem, st);
     } else {
-      if (act == ACT_RELU) launch_ws_inst<0, 32, ACT_RELU, false>(P, n_stages, grid, smem, st);
-      else if (act == ACT_SIGMOID) launch_ws_inst<0, 32, ACT_SIGMOID, false>(P, n_stages, grid, smem, st);
-      else launch_ws_inst<0, 32, ACT_NONE, false>(P, n_stages, grid, smem, st);
+      if (act == ACT_RELU) launch_ws_inst<0, 32, ACT_RELU, false>(P, tm, n_stages, grid, smem, st);
+      else if (act == ACT_SIGMOID) launch_ws_inst<0, 32, ACT_SIGMOID, false>(P, tm, n_stages, grid, smem, st);
+      else launch_ws_inst<0, 32, ACT_NONE, false>(P, tm, n_stages, grid, smem, st);
     }
   }
   kp::g_launches += 1;
@@ -863,13 +978,23 @@ static bool launch_ws_wgrad(const float* X, int64_t ldx, const float* dY, int64_
   const int n_stages = (int)std::min<size_t>(kWsMaxStages, budget / stage);
   if (n_stages < 2) return false;
   const size_t smem = (size_t)n_stages * stage + slack + 1024;
-  auto kern = tc_ws_wgrad_kernel<K_PAD, N_PAD, ROWS>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, ROWS), sms));
-  kern<<<grid, kWsThreads, smem, st>>>(X, ldx, dY, lddy, dW, lddw, M, K, N, n_stages);
+  CUtensorMap tmX, tmY;
+  const bool use_tma = !(getenv("KP_TC_TMA") != nullptr && atoi(getenv("KP_TC_TMA")) == 0) &&
+                       make_tmap_2d(&tmX, X, M, K, ldx, ROWS, true) && make_tmap_2d(&tmY, dY, M, N, lddy, ROWS, true);
+  if (use_tma) {
+    auto kern = tc_ws_wgrad_kernel<K_PAD, N_PAD, ROWS, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kTmaThreads, smem, st>>>(X, ldx, dY, lddy, dW, lddw, M, K, N, n_stages, tmX, tmY);
+  } else {
+    memset(&tmX, 0, sizeof(tmX));
+    auto kern = tc_ws_wgrad_kernel<K_PAD, N_PAD, ROWS, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kWsThreads, smem, st>>>(X, ldx, dY, lddy, dW, lddw, M, K, N, n_stages, tmX, tmX);
+  }
   return true;
 }
 

@@ -14,6 +14,8 @@
 // hi is the TF32 the tensor core reads from an fp32 word anyway (low 13 mantissa bits ignored), so one LOP3 replaces the
 // rounding conversion; lo = x - hi is exact and the tensor core's truncation of lo costs <= 2^-21 relative.
 #pragma once
+#include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
+
 #include "tc_common.cuh"
 
 namespace kp {
@@ -114,6 +116,67 @@ __device__ __forceinline__ void ws_store(const WsRegs<ROWS, COLS>& t, float* __r
     *reinterpret_cast<float4*>(s_hi + off0 + u * ROWSTEP * 32) = hi;
     *reinterpret_cast<float4*>(s_lo + off0 + u * ROWSTEP * 32) = lo;
   }
+}
+
+// ---- TMA-fed variant --------------------------------------------------------------------------------------------------
+// The activation sub-tile is brought in by the TMA engine (cp.async.bulk.tensor.2d, one [ROWS x 32-column] box per 32-col
+// block, written straight into the swizzled UMMA layout: SWIZZLE_128B for K-major operands, SWIZZLE_128B_ATOM_32B for the
+// MN-major views) and completes on an mbarrier: no registers, no scoreboards, any number of stages in flight, rows /
+// columns past the matrix zero-filled by the hardware.  The raw fp32 words ARE the hi operand (kind::tf32 ignores the low
+// 13 mantissa bits); the producer warps only derive lo = x - (x & 0xffffe000) from shared memory, linearly (lo has the
+// same layout as hi, so the swizzle never appears in SIMT code).
+constexpr int kTmaThreads = kWsThreads + 32;     // + the TMA-issuing warp
+constexpr int kTmaWarp = kWsEpiWarps + 1;        // warp 5
+constexpr int kTmaProdTid0 = 32 * (kWsEpiWarps + 2);
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c_inner, int c_outer, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// lo = x - trunc_tf32(x) for N4 float4 of a staged operand (256 producer threads, linear, conflict-free)
+template <int N4>
+__device__ __forceinline__ void ws_derive_lo(const float* __restrict__ s_hi, float* __restrict__ s_lo, int pt) {
+  static_assert(N4 % kWsProdThreads == 0, "operand size");
+  const float4* h = reinterpret_cast<const float4*>(s_hi);
+  float4* l = reinterpret_cast<float4*>(s_lo);
+#pragma unroll
+  for (int u = 0; u < N4 / kWsProdThreads; ++u) {
+    const float4 x = h[pt + u * kWsProdThreads];
+    const float4 hi = hi4(x);
+    l[pt + u * kWsProdThreads] = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+  }
+}
+
+// Host: tensor map of a row-major fp32 matrix [rows x cols] (leading dimension ld floats) read in boxes of
+// [box_rows x 32 columns].  Returns false when the matrix cannot be described (alignment) or the driver lacks the entry point.
+static inline bool make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                                bool mn_view) {
+  typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<Fn>(p);
+  }();
+  if (fn == nullptr || rows < 1 || cols < 1 || box_rows < 1 || box_rows > 256) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * 4) & 15) != 0 || rows >= (int64_t(1) << 31)) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            mn_view ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace kp
