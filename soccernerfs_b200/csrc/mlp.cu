@@ -96,11 +96,14 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 // (4-term TF32 split, fp32-accurate) -- including the 192->128 first layer of the 32x config, which is cut into
 // sub-matrix launches there; anything wider than 256 falls back to the SIMT SGEMM above.
 // Y[M,N] = act(X[M,K] W[N,K]^T)
+static int g_tc_status = 0;  // first non-zero status of a tensor-core entry point called from this file (checked by the callers)
+
 template <int EPI>
 static void gemm_fwd(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int64_t M, int N, int K,
                      cudaStream_t st) {
   if (kp_tc_supported(N, K)) {
-    kp_tc_linear_fwd(X, ldx, W, ldw, Y, ldy, M, N, K, EPI == EPI_RELU ? 1 : (EPI == EPI_SIGMOID ? 2 : 0), st);
+    const int rc = kp_tc_linear_fwd(X, ldx, W, ldw, Y, ldy, M, N, K, EPI == EPI_RELU ? 1 : (EPI == EPI_SIGMOID ? 2 : 0), st);
+    if (rc != 0 && g_tc_status == 0) g_tc_status = rc;
     return;
   }
   dim3 grid((unsigned)ceil_div(M, TI), (unsigned)ceil_div(N, TJ), 1);
@@ -112,7 +115,8 @@ template <int EPI>
 static void gemm_dx(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int64_t M, int N, int K,
                     const float* aux, int ldaux, cudaStream_t st) {
   if (kp_tc_supported(N, K)) {
-    kp_tc_linear_bwd_data(dY, lddy, W, ldw, dX, lddx, M, N, K, EPI == EPI_RELU_MASK ? aux : nullptr, ldaux, st);
+    const int rc = kp_tc_linear_bwd_data(dY, lddy, W, ldw, dX, lddx, M, N, K, EPI == EPI_RELU_MASK ? aux : nullptr, ldaux, st);
+    if (rc != 0 && g_tc_status == 0) g_tc_status = rc;
     return;
   }
   dim3 grid((unsigned)ceil_div(M, TI), (unsigned)ceil_div(K, TJ), 1);
@@ -123,7 +127,8 @@ static void gemm_dx(const float* dY, int lddy, const float* W, int ldw, float* d
 static void gemm_dw(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int64_t M, int N, int K,
                     cudaStream_t st) {
   if (N <= 1024 && K <= 1024) {  // (layers wider than one launch's operand tiles are cut into blocks of dW there)
-    kp_tc_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, M, N, K, st);
+    const int rc = kp_tc_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, M, N, K, st);
+    if (rc != 0 && g_tc_status == 0) g_tc_status = rc;
     return;
   }
   const int64_t chunk = 1024;
@@ -218,6 +223,7 @@ extern "C" int kp_sigma_net_fwd(const float* feats, const float* w1, const float
   gemm_fwd<EPI_NONE>(h1, H, w2, H, o, 16, M, 16, H, st);
   density_from_o_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(o, M, density);
   KP_LAUNCH_CHECK("sigma_net_fwd");
+  if (g_tc_status != 0) { const int rc = g_tc_status; g_tc_status = 0; return rc; }  // (kp_last_error holds the message)
   return 0;
 }
 
@@ -238,6 +244,7 @@ extern "C" int kp_sigma_net_bwd(const float* feats, const float* w1, const float
   gemm_dw(scratch, H, feats, K, grad_w1, K, M, H, K, st);
   gemm_dx<EPI_NONE>(scratch, H, w1, K, grad_feats, K, M, H, K, nullptr, 0, st);
   KP_LAUNCH_CHECK("sigma_net_bwd");
+  if (g_tc_status != 0) { const int rc = g_tc_status; g_tc_status = 0; return rc; }  // (kp_last_error holds the message)
   return 0;
 }
 
@@ -254,6 +261,7 @@ extern "C" int kp_color_net_fwd(const float* directions, int S, const float* o, 
   gemm_fwd<EPI_RELU>(h2, H2, w4, H2, h3, H2, M, H2, H2, st);
   gemm_fwd<EPI_SIGMOID>(h3, H2, w5, H2, rgb, 3, M, 3, H2, st);
   KP_LAUNCH_CHECK("color_net_fwd");
+  if (g_tc_status != 0) { const int rc = g_tc_status; g_tc_status = 0; return rc; }  // (kp_last_error holds the message)
   return 0;
 }
 
@@ -277,5 +285,6 @@ extern "C" int kp_color_net_bwd(int view_dependent, const float* cin, const floa
   cudaMemsetAsync(grad_o, 0, (size_t)M * 16 * sizeof(float), st);
   gemm_dx<EPI_NONE>(scratch_b, H2, w3 + geo_off, kin, grad_o, 16, M, H2, 15, nullptr, 0, st);  // d_geo
   KP_LAUNCH_CHECK("color_net_bwd");
+  if (g_tc_status != 0) { const int rc = g_tc_status; g_tc_status = 0; return rc; }  // (kp_last_error holds the message)
   return 0;
 }

@@ -913,7 +913,7 @@ static bool launch_ws(const float* A, int64_t lda, const float* W, int64_t ldw, 
                       int R, int act, const float* aux, int64_t ldaux, cudaStream_t st) {
   if (getenv("KP_TC_WS") != nullptr && atoi(getenv("KP_TC_WS")) == 0) return false;
   const size_t epi_bytes = (size_t)kWsEpiWarps * 32 * 36 * sizeof(float);  // the epilogue warps' transpose buffers
-  const size_t budget = 227 * 1024 - 1024 - epi_bytes;
+  const size_t budget = 227 * 1024 - 2048 - epi_bytes;  // - 1 KB alignment slack - static shared memory (barriers)
   int KS = 0, n_slices = 0, N_slice = 0, N_pad = 0, n_stages = 0;
   // widest column slice, then the K-slice width that gives the deeper ring (>= 2 stages needed)
   for (int cand = std::min(N_total, 128);; cand = (cand > 64 ? 64 : 32)) {
@@ -974,7 +974,7 @@ static bool launch_ws_wgrad(const float* X, int64_t ldx, const float* dY, int64_
   constexpr int ROWS = 64;
   const size_t stage = (size_t)2 * ROWS * (K_PAD + N_PAD) * sizeof(float);
   const size_t slack = (size_t)ROWS * 128 * sizeof(float);  // the A operand always spans 4 MN blocks (M = 128)
-  const size_t budget = 227 * 1024 - 1024 - slack;
+  const size_t budget = 227 * 1024 - 2048 - slack;  // - 1 KB alignment slack - static shared memory (barriers)
   const int n_stages = (int)std::min<size_t>(kWsMaxStages, budget / stage);
   if (n_stages < 2) return false;
   const size_t smem = (size_t)n_stages * stage + slack + 1024;
