@@ -64,7 +64,9 @@ WORKLOAD = WORKLOADS["cfg2"]["label"]
 FIELD_KERNELS = ("kp_hexplane_fwd", "kp_hexplane_bwd", "kp_density_field_fwd", "kp_density_field_bwd")
 OTHER_TIMED = ("kp_decoder_fwd_fused", "kp_color_net_bwd", "kp_sigma_net_bwd", "kp_sigma_net_fwd", "kp_color_net_fwd",
                "kp_adam_multi", "kp_plane_reg_multi_fwd", "kp_plane_reg_multi_bwd", "kp_plane_reg_fused", "kp_plane_reg_adam",
-               "kp_peer_allreduce", "kp_peer_sharded_adam")
+               "kp_peer_allreduce", "kp_peer_sharded_adam", "kp_peer_sharded_adam_sparse", "kp_hexplane_bwd_flags",
+               "kp_plane_reg_fused_range")
+ALIASES = {"kp_hexplane_bwd_flags": "kp_hexplane_bwd"}  # same kernel, with the touched-line marks switched on
 
 
 def _peaks():
@@ -436,7 +438,8 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
                         allreduce_mode=args.allreduce if args.allreduce != "none" else "overlap",
                         allreduce_backend=args.allreduce_backend,
                         shard_optimizer={"auto": None, "on": True, "off": False}[args.shard_optimizer],
-                        fuse_reg_adam={"auto": None, "on": True, "off": False}[args.reg_adam])
+                        fuse_reg_adam={"auto": None, "on": True, "off": False}[args.reg_adam],
+                        sparse_grad_exchange={"auto": None, "on": True, "off": False}[args.sparse_exchange])
     n_steps = args.warmup + args.steps
     host = _make_batches(n_steps, RAYS_PER_RANK, seed=1000 + rank)
     resident = [h.to(dev) for h in host]
@@ -549,7 +552,7 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
     _lib.TIMED.clear()
     kernel_ms = {}
     for kname, a, b in _lib.EVENTS:
-        kernel_ms.setdefault(kname, []).append(a.elapsed_time(b))
+        kernel_ms.setdefault(ALIASES.get(kname, kname), []).append(a.elapsed_time(b))
     _lib.EVENTS.clear()
     scales = per_scale_probe(model, flush, peaks, probe) if rank == 0 else None
 
@@ -578,7 +581,8 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
         "regularizers": ("folded into the optimizer pass (kp_plane_reg_adam)" if trainer._reg_adam is not None else
                          "one sweep into the gradient bucket (kp_plane_reg_fused) + kp_adam_multi"),
         "grad_allreduce": ("none (single rank)" if world == 1 else "disabled" if args.allreduce == "none" else
-                           (f"{trainer.allreduce_backend}: fused reduce-scatter + sharded Adam + all-gather kernel" if trainer.sharded
+                           (f"{trainer.allreduce_backend}: fused reduce-scatter + sharded Adam + all-gather kernel"
+                            + (" (field group: only the marked 128-byte gradient lines are pulled)" if trainer._sparse else "") if trainer.sharded
                             else f"{trainer.allreduce_backend} all-reduce ({args.allreduce}) + replicated Adam")),
     })
     if rank == 0 and scales:
@@ -882,6 +886,8 @@ def main():
                     help="N>1, peer backend: reduce-scatter + Adam on the owned shard + all-gather in one kernel (auto = on)")
     ap.add_argument("--reg-adam", choices=["auto", "on", "off"], default="auto",
                     help="(f1) plane regularisers folded into the optimizer's streaming pass (auto: when the planes are HBM-resident)")
+    ap.add_argument("--sparse-exchange", choices=["auto", "on", "off"], default="auto",
+                    help="N>1, sharded optimizer: pull only the gradient lines the scatter marked (auto: HBM-resident planes)")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python each step instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

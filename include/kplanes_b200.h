@@ -63,6 +63,12 @@ int kp_hexplane_fwd(const float* const* plane_ptrs, const int32_t* plane_hw, int
 int kp_hexplane_bwd(const float* const* plane_ptrs, float* const* grad_plane_ptrs, const int32_t* plane_hw,
                     int n_scales, int n_planes, int C, const KpPoints* points, int64_t M, int concat,
                     uint32_t use_mask, const float* grad_out, void* stream);
+/* Same, and additionally marks every texel that received a reduction: touched_ptrs (HOST array of device pointers, same
+ * order, entries may be NULL) point to one byte per texel of the plane, set to 1 (never cleared here).  The data-parallel
+ * step exchanges only the marked 128-byte lines of the HBM-resident scales (kp_peer_sharded_adam_sparse). */
+int kp_hexplane_bwd_flags(const float* const* plane_ptrs, float* const* grad_plane_ptrs, uint8_t* const* touched_ptrs,
+                          const int32_t* plane_hw, int n_scales, int n_planes, int C, const KpPoints* points, int64_t M,
+                          int concat, uint32_t use_mask, const float* grad_out, void* stream);
 
 /* ---- (a6) proposal density field: KPlanesDensityField.get_density, kplanes_field.py:434-460:
  *      single-scale planes (C = 4|8|16) -> Hadamard -> [hidden x C] ReLU (or linear) -> [1 x hidden] ->
@@ -198,6 +204,11 @@ int kp_plane_reg_multi_bwd(const float* const* planes, float* const* grads, cons
 int kp_plane_reg_fused(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms, int P,
                        const float* coef_dev /* [P,4] */, int accumulate, double* sums /* [P,4] accumulated, or NULL */,
                        void* stream);
+/* Same; write_range_dev (DEVICE int64 [P,2], or NULL = everything): the gradient of plane p is written only for its float4
+ * elements [begin, end) -- sums still cover the whole plane.  Used by the data-parallel step with the sparse gradient
+ * exchange, where every rank contributes the regularisers' gradient for its own shard of the bucket only. */
+int kp_plane_reg_fused_range(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms, int P,
+                             const float* coef_dev, int accumulate, double* sums, const int64_t* write_range_dev, void* stream);
 
 /* Adam over a list of dense fp32 tensors in one launch.  hyper_dev (optional, DEVICE float[3] = lr/bias_corr1,
  * 1/sqrt(bias_corr2), grad_scale) overrides the host-computed scalars so a captured CUDA graph can be replayed
@@ -307,6 +318,15 @@ int kp_peer_allreduce(void* const* arenas /* HOST array [world]: arenas[rank] = 
 int kp_peer_sharded_adam(void* const* arenas, int rank, int world, int64_t grad_begin, int64_t param_begin, int64_t count,
                          float* exp_avg_shard, float* exp_avg_sq_shard, float lr, float beta1, float beta2, float eps,
                          float weight_decay, int64_t step, float grad_scale, const float* hyper_dev, int blocks, void* stream);
+/* Sparse variant for HBM-resident plane groups: touched_begin (float offset in the data region, like grad_begin) locates
+ * one byte per 128-byte line of the gradient region in every arena: 0 = line is all zeros (not read over NVLink), 1 =
+ * reduced into this step (kp_hexplane_bwd_flags), 2 = always dense.  The owner reads its own shard's lines unconditionally
+ * and, after the end barrier, every rank zeroes its marked lines outside its shard and clears their marks (the bucket needs
+ * no memset).  grad_begin and count must be multiples of 32 floats. */
+int kp_peer_sharded_adam_sparse(void* const* arenas, int rank, int world, int64_t grad_begin, int64_t param_begin,
+                                int64_t touched_begin, int64_t count, float* exp_avg_shard, float* exp_avg_sq_shard, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                                const float* hyper_dev, int blocks, void* stream);
 
 /* ---- (d) measurement: memory-hierarchy probe with the field kernels' own access pattern (8 lanes = one 128-byte
  *      line of a pseudo-random texel; mode 0: 16-byte read-only loads, mode 1: red.global.add.v4.f32).  One launch

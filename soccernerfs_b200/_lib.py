@@ -36,6 +36,7 @@ SIGNATURES = {
     "kp_launch_count": ([], ctypes.c_longlong),
     "kp_hexplane_fwd": ([_P, _P, c_int, c_int, c_int, POINTER(KpPoints), c_int64, c_int, c_uint32, _P, _P], c_int),
     "kp_hexplane_bwd": ([_P, _P, _P, c_int, c_int, c_int, POINTER(KpPoints), c_int64, c_int, c_uint32, _P, _P], c_int),
+    "kp_hexplane_bwd_flags": ([_P, _P, _P, _P, c_int, c_int, c_int, POINTER(KpPoints), c_int64, c_int, c_uint32, _P, _P], c_int),
     "kp_density_field_fwd": ([_P, _P, c_int, c_int, _P, _P, c_int, c_int, POINTER(KpPoints), c_int64, c_uint32, _P, _P], c_int),
     "kp_density_field_bwd": ([_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, POINTER(KpPoints), c_int64, c_uint32, _P, _P, _P, _P], c_int),
     "kp_sigma_net_fwd": ([_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P], c_int),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "kp_plane_reg_multi_fwd": ([_P, _P, _P, c_int, _P, _P], c_int),
     "kp_plane_reg_multi_bwd": ([_P, _P, _P, _P, c_int, _P, c_int, _P], c_int),
     "kp_plane_reg_fused": ([_P, _P, _P, _P, c_int, _P, c_int, _P, _P], c_int),
+    "kp_plane_reg_fused_range": ([_P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P], c_int),
     "kp_plane_reg_adam_supported": ([c_int], c_int),
     "kp_plane_reg_adam_scratch_bytes": ([_P, c_int], c_int64),
     "kp_plane_reg_adam": ([_P, _P, _P, _P, _P, _P, c_int, _P, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P, _P,
@@ -84,6 +86,8 @@ SIGNATURES = {
     "kp_peer_allreduce": ([_P, c_int, c_int, c_int64, c_int64, c_int, _P], c_int),
     "kp_peer_sharded_adam": ([_P, c_int, c_int, c_int64, c_int64, c_int64, _P, _P, c_float, c_float, c_float, c_float, c_float,
                              c_int64, c_float, _P, c_int, _P], c_int),
+    "kp_peer_sharded_adam_sparse": ([_P, c_int, c_int, c_int64, c_int64, c_int64, c_int64, _P, _P, c_float, c_float, c_float, c_float,
+                                    c_float, c_int64, c_float, _P, c_int, _P], c_int),
     "kp_line_probe": ([_P, c_int64, c_int, c_int, c_int, c_uint32, _P, POINTER(c_int64), _P], c_int),
     "kp_repack_nchw_to_hwc": ([_P, _P, c_int, c_int, c_int, _P], c_int),
     "kp_repack_hwc_to_nchw": ([_P, _P, c_int, c_int, c_int, _P], c_int),

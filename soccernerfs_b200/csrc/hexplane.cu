@@ -24,6 +24,7 @@ namespace kp {
 struct PlaneRef {
   const float* p;
   float* g;
+  uint8_t* f;  // scatter only, optional: one "touched" byte per texel (set to 1 for every texel that receives a reduction)
   int H, W, ca, cb;
 };
 struct FieldRef {
@@ -46,6 +47,7 @@ static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const*
       PlaneRef& r = F.pl[k * KP_MAX_PLANES + p];
       r.p = plane_ptrs[k * n_planes + p];
       r.g = grad_ptrs ? grad_ptrs[k * n_planes + p] : nullptr;
+      r.f = nullptr;
       r.H = plane_hw[(k * n_planes + p) * 2 + 0];
       r.W = plane_hw[(k * n_planes + p) * 2 + 1];
       r.ca = (D == 4) ? comb4[p][0] : comb3[p][0];
@@ -319,6 +321,14 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
         if (b[p].w10 != 0.f) red_add_v4(gb + (int64_t)b[p].o10 * C, scale4(gp, b[p].w10));
         if (b[p].w11 != 0.f) red_add_v4(gb + (int64_t)b[p].o11 * C, scale4(gp, b[p].w11));
       }
+      // sparse gradient exchange: mark the texels this sample reduced into (one lane of the sample's C/4; plain byte
+      // stores of the same value, so no ordering between writers is needed)
+      if (pr.f != nullptr && live && c4 == 0) {
+        if (b[p].w00 != 0.f) pr.f[b[p].o00] = 1;
+        if (b[p].w01 != 0.f) pr.f[b[p].o01] = 1;
+        if (b[p].w10 != 0.f) pr.f[b[p].o10] = 1;
+        if (b[p].w11 != 0.f) pr.f[b[p].o11] = 1;
+      }
     }
   }
 }
@@ -587,15 +597,25 @@ extern "C" int kp_hexplane_fwd(const float* const* plane_ptrs, const int32_t* pl
   return dispatch_hexplane(false, C, F, *points, M, nullptr, out, as_stream(stream));
 }
 
-extern "C" int kp_hexplane_bwd(const float* const* plane_ptrs, float* const* grad_plane_ptrs, const int32_t* plane_hw,
-                               int n_scales, int n_planes, int C, const KpPoints* points, int64_t M, int concat,
-                               uint32_t use_mask, const float* grad_out, void* stream) {
+extern "C" int kp_hexplane_bwd_flags(const float* const* plane_ptrs, float* const* grad_plane_ptrs, uint8_t* const* touched_ptrs,
+                                     const int32_t* plane_hw, int n_scales, int n_planes, int C, const KpPoints* points, int64_t M,
+                                     int concat, uint32_t use_mask, const float* grad_out, void* stream) {
   if (check_points(points, M)) return 1;
   KP_CHECK(grad_out != nullptr || M == 0, "hexplane_bwd: grad_out is NULL");
   KP_CHECK(grad_plane_ptrs != nullptr, "hexplane_bwd: grad_plane_ptrs is NULL");
   FieldRef F;
   if (fill_field(F, plane_ptrs, grad_plane_ptrs, plane_hw, n_scales, n_planes, points->D, use_mask, concat)) return 1;
+  if (touched_ptrs != nullptr)
+    for (int k = 0; k < n_scales; ++k)
+      for (int p = 0; p < n_planes; ++p) F.pl[k * KP_MAX_PLANES + p].f = touched_ptrs[k * n_planes + p];
   return dispatch_hexplane(true, C, F, *points, M, grad_out, nullptr, as_stream(stream));
+}
+
+extern "C" int kp_hexplane_bwd(const float* const* plane_ptrs, float* const* grad_plane_ptrs, const int32_t* plane_hw,
+                               int n_scales, int n_planes, int C, const KpPoints* points, int64_t M, int concat,
+                               uint32_t use_mask, const float* grad_out, void* stream) {
+  return kp_hexplane_bwd_flags(plane_ptrs, grad_plane_ptrs, nullptr, plane_hw, n_scales, n_planes, C, points, M, concat, use_mask,
+                               grad_out, stream);
 }
 
 template <int C>

@@ -149,6 +149,7 @@ struct ShardedAdamArgs {
   int64_t n4;                    // group size in float4 units
   const float* hyper_dev;        // optional DEVICE {lr / bias_corr1, 1 / sqrt(bias_corr2), grad_scale}
   float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, wd, grad_scale;
+  uint8_t* touched[kPeerMaxWorld];  // sparse variant: one byte per 128-byte line of every rank's gradient region
 };
 
 template <int N>
@@ -212,6 +213,111 @@ __global__ void __launch_bounds__(kPeerThreads) peer_sharded_adam_kernel(const _
   if (threadIdx.x == 0) *counter = flag;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse variant for HBM-resident plane groups (the 32x preset: 2.3 GB of planes, of which one step's 4096 rays touch
+// ~15-30 % of the 128-byte lines of the fine scales).  A dense reduce-scatter pulls (N-1)/N of the group over NVLink
+// although most of it is zeros.  Here every rank keeps one "touched" byte per 128-byte line of its gradient region:
+//   0 = the line is all zeros (nobody reads it),  1 = the scatter reduced into it this step,  2 = always dense (MLP
+//   weights).  The owner of a shard reads its OWN lines unconditionally (the regularisers' gradient for the shard is
+//   dense and is written, pre-multiplied by N, only into the owner's bucket) and a peer's line only if that peer marked
+//   it.  After the end barrier every rank clears its marked lines outside its own shard (zero the line, flag back to 0),
+//   so the bucket needs no memset.  The all-gather of the new parameters stays dense: Adam moves every parameter.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_peer_u8(const uint8_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kPeerThreads) peer_sharded_adam_sparse_kernel(const __grid_constant__ ShardedAdamArgs a) {
+  __shared__ uint32_t s_flag;
+  PeerArgs b;
+#pragma unroll
+  for (int p = 0; p < kPeerMaxWorld; ++p) b.sig[p] = a.sig[p];
+  b.rank = a.rank;
+  b.world = a.world;
+  uint32_t* counter = a.sig[a.rank] + kSigCounter + blockIdx.x;
+  if (threadIdx.x == 0) s_flag = *counter + 1u;
+  __syncthreads();
+  const uint32_t flag = s_flag;
+  peer_barrier(b, 0, flag);
+  float lr_over_bc1 = a.lr_over_bc1, inv_sqrt_bc2 = a.inv_sqrt_bc2, grad_scale = a.grad_scale;
+  if (a.hyper_dev != nullptr) {
+    lr_over_bc1 = a.hyper_dev[0];
+    inv_sqrt_bc2 = a.hyper_dev[1];
+    grad_scale = a.hyper_dev[2];
+  }
+  const int64_t lo = a.n4 * a.rank / N, hi = a.n4 * (a.rank + 1) / N;
+  const int64_t stride = (int64_t)gridDim.x * kPeerThreads;
+  constexpr int U = N <= 4 ? 4 : 2;  // elements in flight per thread (U*N 16-byte peer loads)
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; i0 < hi; i0 += U * stride) {
+    uint32_t t[U][N];
+    float4 s[U], pp[U], mm[U], vv[U];
+    // 1. the peers' marks (N-1 bytes per element over NVLink; 8 lanes share a byte)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+#pragma unroll
+      for (int p = 0; p < N; ++p) t[u][p] = (i < hi && p != a.rank) ? ld_peer_u8(a.touched[p] + (i >> 3)) : 0u;
+    }
+    // 2. own gradient + optimizer state (local), and the marked lines of the peers
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < hi) {
+        s[u] = *reinterpret_cast<const float4*>(a.grad[a.rank] + 4 * i);
+        pp[u] = *reinterpret_cast<const float4*>(a.param[a.rank] + 4 * i);
+        mm[u] = *reinterpret_cast<const float4*>(a.m + 4 * (i - lo));
+        vv[u] = *reinterpret_cast<const float4*>(a.v + 4 * (i - lo));
+      }
+    }
+    float4 g[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+#pragma unroll
+      for (int p = 0; p < N; ++p) g[u][p] = t[u][p] ? ld_peer_v4(a.grad[p] + 4 * i) : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < hi) {
+        float4 sum = s[u];
+#pragma unroll
+        for (int p = 0; p < N; ++p) { sum.x += g[u][p].x; sum.y += g[u][p].y; sum.z += g[u][p].z; sum.w += g[u][p].w; }
+        float* ga = &sum.x; float* pa = &pp[u].x; float* ma = &mm[u].x; float* va = &vv[u].x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // torch.optim.Adam (same arithmetic as adam_multi_kernel)
+          const float gr = ga[k] * grad_scale + a.wd * pa[k];
+          ma[k] = ma[k] + (gr - ma[k]) * (1.f - a.beta1);
+          va[k] = va[k] * a.beta2 + (1.f - a.beta2) * gr * gr;
+          pa[k] -= lr_over_bc1 * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + a.eps);
+        }
+        *reinterpret_cast<float4*>(a.m + 4 * (i - lo)) = mm[u];
+        *reinterpret_cast<float4*>(a.v + 4 * (i - lo)) = vv[u];
+#pragma unroll
+        for (int p = 0; p < N; ++p) st_peer_v4(a.param[p] + 4 * i, pp[u]);
+      }
+    }
+  }
+  peer_barrier(b, 1, flag);  // every pushed parameter has landed AND every rank has finished reading the gradients
+  // 3. clean-up of this rank's own bucket outside its shard: marked lines back to zero, marks back to 0
+  float* gown = a.grad[a.rank];
+  uint8_t* town = a.touched[a.rank];
+  for (int64_t j = (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; j < a.n4; j += stride) {
+    if (j >= lo && j < hi) continue;
+    const uint32_t f = town[j >> 3];
+    if (f == 1u) {
+      *reinterpret_cast<float4*>(gown + 4 * j) = zero;
+      if ((j & 7) == 0) town[j >> 3] = 0;
+    }
+  }
+  if (threadIdx.x == 0) *counter = flag;
+}
+
 }  // namespace kp
 
 using namespace kp;
@@ -260,6 +366,55 @@ extern "C" int kp_peer_sharded_adam(void* const* arenas, int rank, int world, in
     default: set_error("peer_sharded_adam: world=%d unsupported", world); return 1;
   }
   KP_LAUNCH_CHECK("peer_sharded_adam");
+  return 0;
+}
+
+extern "C" int kp_peer_sharded_adam_sparse(void* const* arenas, int rank, int world, int64_t grad_begin, int64_t param_begin,
+                                           int64_t touched_begin, int64_t count, float* exp_avg_shard, float* exp_avg_sq_shard,
+                                           float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                                           float grad_scale, const float* hyper_dev, int blocks, void* stream) {
+  KP_CHECK(arenas != nullptr && exp_avg_shard != nullptr && exp_avg_sq_shard != nullptr, "peer_sharded_adam_sparse: NULL argument");
+  KP_CHECK(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "peer_sharded_adam_sparse: rank %d / world %d", rank, world);
+  KP_CHECK(grad_begin >= 0 && param_begin >= 0 && touched_begin >= 0 && count >= 0 && grad_begin % 32 == 0 && param_begin % 4 == 0 &&
+               touched_begin % 4 == 0 && count % 32 == 0,
+           "peer_sharded_adam_sparse: the gradient region must start and end on a 128-byte line");
+  KP_CHECK(step >= 1, "peer_sharded_adam_sparse: step is 1-based");
+  if (count == 0) return 0;
+  if (blocks <= 0) blocks = 64;
+  KP_CHECK(blocks <= kPeerMaxBlocks, "peer_sharded_adam_sparse: blocks=%d > %d", blocks, kPeerMaxBlocks);
+  ShardedAdamArgs a;
+  for (int p = 0; p < kPeerMaxWorld; ++p) { a.grad[p] = nullptr; a.param[p] = nullptr; a.sig[p] = nullptr; a.touched[p] = nullptr; }
+  for (int p = 0; p < world; ++p) {
+    KP_CHECK(arenas[p] != nullptr, "peer_sharded_adam_sparse: arena %d is NULL", p);
+    a.sig[p] = reinterpret_cast<uint32_t*>(arenas[p]);
+    float* data = reinterpret_cast<float*>(reinterpret_cast<char*>(arenas[p]) + KP_PEER_SIGNAL_BYTES);
+    a.grad[p] = data + grad_begin;
+    a.param[p] = data + param_begin;
+    a.touched[p] = reinterpret_cast<uint8_t*>(data + touched_begin);
+  }
+  a.m = exp_avg_shard;
+  a.v = exp_avg_sq_shard;
+  a.rank = rank;
+  a.world = world;
+  a.n4 = count / 4;
+  a.hyper_dev = hyper_dev;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  a.lr_over_bc1 = (float)(lr / bc1);
+  a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale;
+  cudaStream_t st = as_stream(stream);
+  switch (world) {
+    case 1: peer_sharded_adam_sparse_kernel<1><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 2: peer_sharded_adam_sparse_kernel<2><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 3: peer_sharded_adam_sparse_kernel<3><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 4: peer_sharded_adam_sparse_kernel<4><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 5: peer_sharded_adam_sparse_kernel<5><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 6: peer_sharded_adam_sparse_kernel<6><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 7: peer_sharded_adam_sparse_kernel<7><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    case 8: peer_sharded_adam_sparse_kernel<8><<<blocks, kPeerThreads, 0, st>>>(a); break;
+    default: set_error("peer_sharded_adam_sparse: world=%d unsupported", world); return 1;
+  }
+  KP_LAUNCH_CHECK("peer_sharded_adam_sparse");
   return 0;
 }
 

@@ -38,6 +38,37 @@ class GradBucket:
             self.views.append(v)
             off += p.numel()
 
+    def enable_touched_marks(self, line_planes) -> bool:
+        """Sparse gradient exchange (csrc/peer_allreduce.cu::peer_sharded_adam_sparse_kernel): one byte per 128-byte line of
+        the bucket, kept in the peer arena next to it.  ``line_planes``: the parameters whose scatter kernel marks the lines
+        it reduces into (channel-last planes with 32 features: one texel = one line); every other parameter of the bucket
+        is marked "always dense".  Returns False (nothing changed) when the bucket's layout does not line up with 128-byte
+        lines."""
+        if self.arena is None or self.flat.numel() == 0:
+            return False
+        off, offsets = 0, []
+        for p in self.params:
+            offsets.append(off)
+            off += p.numel()
+        wanted = {id(p) for p in line_planes}
+        for p, o in zip(self.params, offsets):
+            if o % 32 or p.numel() % 32:
+                return False
+            if id(p) in wanted and not (p.dim() == 4 and p.shape[1] == 32 and p.stride(1) == 1):
+                return False
+        n_lines = (self.flat.numel() + 63) // 64 * 64 // 32
+        raw, self.touched_offset = self.arena.take((n_lines + 3) // 4)
+        self.touched = raw.view(torch.uint8)[:n_lines]
+        self.touched.zero_()
+        for p, o in zip(self.params, offsets):
+            lines = self.touched[o // 32: (o + p.numel()) // 32]
+            if id(p) in wanted:
+                p._kp_touched = lines
+            else:
+                lines.fill_(2)
+        self.param_offsets = dict((id(p), o) for p, o in zip(self.params, offsets))
+        return True
+
     def _zero_spans(self, skip) -> List[Tuple[int, int]]:
         """Element ranges of the bucket NOT covered by the parameters in ``skip`` (ids), merged."""
         key = frozenset(skip)
@@ -73,6 +104,8 @@ class GradBucket:
         for p in self.params:
             if hasattr(p, "_kp_grad_sink"):
                 del p._kp_grad_sink
+            if hasattr(p, "_kp_touched"):
+                del p._kp_touched
 
     def all_reduce(self, group=None, async_op: bool = False, span: Optional[Tuple[int, int]] = None):
         """Sum the bucket (or its [begin, end) element range ``span``) over the process group."""
@@ -128,13 +161,22 @@ class ShardedAdamGroup:
         self.exp_avg_sq = torch.zeros(shard, dtype=torch.float32, device=dev)
 
     def step(self, lr: float, betas, eps: float, weight_decay: float, step: int, grad_scale: float,
-             hyper_dev: Optional[torch.Tensor] = None) -> None:
+             hyper_dev: Optional[torch.Tensor] = None, sparse: bool = False) -> None:
+        """``sparse``: peers' gradient lines are read only where marked (``GradBucket.enable_touched_marks``); this rank's
+        own shard must then hold the regularisers' gradient pre-multiplied by the world size (see TrainStep)."""
         from ctypes import c_void_p
 
         a = self.arena
         # a group of hundreds of MB needs more bytes in flight over NVLink than the 32 blocks that suit a 150 MB group
         # sharing the SMs with the proposal networks' backward
         blocks = a.blocks if self.count * 4 < (512 << 20) else max(a.blocks, 128)
+        if sparse:
+            a._lib.call("kp_peer_sharded_adam_sparse", a._ptrs, a.rank, a.world, int(self.bucket.arena_offset), int(self.param_offset),
+                        int(self.bucket.touched_offset), int(self.count), c_void_p(self.exp_avg.data_ptr()),
+                        c_void_p(self.exp_avg_sq.data_ptr()), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                        float(weight_decay), int(step), float(grad_scale), c_void_p(0 if hyper_dev is None else hyper_dev.data_ptr()),
+                        blocks, c_void_p(torch.cuda.current_stream().cuda_stream))
+            return
         a._lib.call("kp_peer_sharded_adam", a._ptrs, a.rank, a.world, int(self.bucket.arena_offset), int(self.param_offset),
                     int(self.count), c_void_p(self.exp_avg.data_ptr()), c_void_p(self.exp_avg_sq.data_ptr()), float(lr),
                     float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale),

@@ -32,7 +32,8 @@ class TrainStep:
                  fuse_grad_accumulation: bool = True, overlap_branches: bool = True,
                  overlap_proposal_backward: Optional[bool] = None, allreduce_mode: str = "overlap",
                  allreduce_backend: str = "peer", fuse_regularizers: bool = True,
-                 shard_optimizer: Optional[bool] = None, fuse_reg_adam: Optional[bool] = None) -> None:
+                 shard_optimizer: Optional[bool] = None, fuse_reg_adam: Optional[bool] = None,
+                 sparse_grad_exchange: Optional[bool] = None) -> None:
         """``overlap_branches``: run the two branches of the step that do not depend on the main field's backward on
         their own CUDA streams (same arithmetic, same results): the plane regularisers (forward AND backward depend on
         the planes only) during the forward pass, and the back-propagation through the proposal networks (depends on
@@ -54,7 +55,13 @@ class TrainStep:
         -- and the planes are HBM-resident, >= REG_ADAM_AUTO_BYTES): the plane regularisers are not evaluated as a branch of the step at all -- their gradient is computed
         from the pre-update planes INSIDE the optimizer's streaming pass (``kp_plane_reg_adam``),
         which also leaves the planes' gradient buffers zeroed for the next step; the six loss values come out of the same
-        pass and are added to the reported loss after it."""
+        pass and are added to the reported loss after it.
+        ``sparse_grad_exchange`` (sharded optimizer only; None = on when the field planes are HBM-resident, >=
+        REG_ADAM_AUTO_BYTES): the field's scatter marks the 128-byte gradient lines it reduces into and the fused
+        reduce-scatter reads a peer's line only if marked (one step's rays touch 15-30 % of the lines of the 16x / 32x
+        scales); the regularisers' dense gradient is written by the shard's owner alone, pre-multiplied by the world size,
+        and every rank clears its marked lines after the exchange, so the 2.3 GB bucket is neither memset nor pulled over
+        NVLink in full.  Same sums in a different association order (atomics already make the order free)."""
         self.model = model
         self.max_steps, self.base_lr, self.warm_up_end = max_steps, lr, warm_up_end
         self.optimizers = Optimizers(model.get_param_groups(), lr=lr, eps=eps, warm_up_end=warm_up_end, max_steps=max_steps)
@@ -85,6 +92,7 @@ class TrainStep:
                 n = sum((sum(p.numel() for p in ps if p.requires_grad) + 63) // 64 * 64 for ps in groups.values())
                 if shard_optimizer is None or shard_optimizer:
                     n *= 2  # the parameters get a region of their own next to the gradients
+                    n += n // 64 + 1024  # + one "touched" byte per 128-byte gradient line (sparse exchange)
                 try:
                     arena = PeerArena(n, blocks=int(os.environ.get("KP_PEER_BLOCKS", "32")))
                 except PeerMemoryUnavailable as e:
@@ -100,12 +108,26 @@ class TrainStep:
         elif shard_optimizer:
             raise RuntimeError("shard_optimizer=True needs the peer-memory backend (data_parallel, world > 1, CUDA IPC)")
         on_cuda = next(model.parameters()).is_cuda
+        self._sparse, self._bucket_dirty = False, True
+        self._sparse_wanted = sparse_grad_exchange
         self.overlap = bool(overlap_branches and fuse_grad_accumulation and on_cuda)
         # fused regulariser sweep (values + gradient written into the sinks, no memset of the planes): ids of the planes
         # it writes in full, or None when not applicable
         self._reg_written = None
         if fuse_grad_accumulation and self.buckets and on_cuda and model.fused_regularizers_applicable() and fuse_regularizers:
             self._reg_written = frozenset(id(p) for p in model.regularized_planes() if p.requires_grad)
+        # sparse gradient exchange of the field group (needs the fused regulariser sweep: it is what keeps the rest of the
+        # bucket free of dense contributions)
+        if "fields" in self.sharded and self._reg_written is not None and sparse_grad_exchange is not False:
+            grids = getattr(model.field, "grids", None)
+            planes = [p for g in grids for p in g] if grids is not None else []
+            big = sum(p.numel() for p in planes) * 4 >= self.REG_ADAM_AUTO_BYTES
+            if planes and (sparse_grad_exchange or big) and self.buckets["fields"].enable_touched_marks(planes):
+                self._sparse = True
+                self._setup_sparse_regularizers()
+        if sparse_grad_exchange and not self._sparse:
+            raise RuntimeError("sparse_grad_exchange=True needs the sharded optimizer, the fused regularisers and 32-feature planes "
+                               "laid out on 128-byte lines")
         # (f1) regulariser stencil folded into the optimizer pass
         self._reg_adam = None
         if (fuse_reg_adam is None or fuse_reg_adam) and self._reg_written is not None and not self.reduce_grads:
@@ -155,6 +177,37 @@ class TrainStep:
         self._seen: Dict[bool, int] = {}
         self._static: Optional[Dict[str, torch.Tensor]] = None
 
+    def _setup_sparse_regularizers(self) -> None:
+        """Per regularised plane: the float4 range of it that lies inside this rank's shard of the "fields" bucket (proposal
+        planes: everything -- their bucket is exchanged densely) and the factor on its gradient (world for field planes)."""
+        from ..model_components.losses import regularizer_plan
+
+        model, dev = self.model, self.buckets["fields"].flat.device
+        planes, _, _ = regularizer_plan(model.field.grids, [p.grids for p in model.proposal_networks])
+        bucket, grp = self.buckets["fields"], self.sharded["fields"]
+        lo, hi = grp.shard_slice()
+        rng, scale = [], []
+        for p in planes:
+            off = bucket.param_offsets.get(id(p))
+            if off is None:
+                rng.append((0, p.numel() // 4))
+                scale.append(1.0)
+            else:
+                a, b = max(lo, off) - off, min(hi, off + p.numel()) - off
+                rng.append((a // 4, b // 4) if b > a else (0, 0))
+                scale.append(float(self.world))
+        self._reg_range = torch.tensor(rng, dtype=torch.int64, device=dev)
+        self._reg_scale = torch.tensor(scale, dtype=torch.float32, device=dev)
+
+    def _clean_field_bucket(self) -> None:
+        """Before a sparse step that follows anything else (first step, a dense diagnostic iteration): the invariant "a line
+        of the field bucket is zero unless marked" is re-established by one full memset."""
+        b = self.buckets["fields"]
+        b.flat.zero_()
+        t = b.touched
+        t.copy_(torch.where(t == 1, torch.zeros_like(t), t))
+        self._bucket_dirty = False
+
     # ---- the iteration body (eager, or recorded into a graph) ------------------------------------------
     def _iteration(self, ray_bundle: RayBundle, batch: Dict[str, torch.Tensor], grad_scale_override=None):
         model = self.model
@@ -164,6 +217,11 @@ class TrainStep:
             skip = self._reg_written
             if self._reg_adam is not None and self._reg_adam_first:
                 skip, self._reg_adam_first = None, False  # first step: nothing has zeroed the planes' gradients yet
+            sparse_now = self._sparse and self.reduce_grads and "fields" in self.sharded
+            if sparse_now and self._bucket_dirty:
+                self._clean_field_bucket()
+            if self._sparse and not sparse_now:
+                self._bucket_dirty = True  # a dense iteration (diagnostics) leaves reduced sums in the bucket
             for b in self.buckets.values():
                 b.attach_zeroed(sink=self.fuse_grad_accumulation, skip=skip)
         else:
@@ -185,7 +243,11 @@ class TrainStep:
             with torch.cuda.stream(self._reg_stream) if self.overlap else contextlib.nullcontext():
                 if self._reg_written:
                     # one sweep per plane: loss values + gradient WRITTEN into the bucket (which was not memset there)
-                    regs = model.regularizers_into_grads(accumulate=False)
+                    if self._sparse and self.reduce_grads and "fields" in self.sharded:
+                        # field planes: only this rank's shard of the bucket, pre-multiplied by the world size
+                        regs = model.regularizers_into_grads(accumulate=False, write_range=self._reg_range, grad_scale=self._reg_scale)
+                    else:
+                        regs = model.regularizers_into_grads(accumulate=False)
                 else:
                     regs = model.regularizer_losses()
                     if regs:
@@ -274,7 +336,8 @@ class TrainStep:
         g = opt.param_groups[0]
         self._last_sharded_lr[name] = float(g["lr"])
         self.sharded[name].step(g["lr"], g["betas"], g["eps"], g["weight_decay"], self.step + 1, 1.0 / self.world,
-                                hyper_dev=g.get("hyper_dev") if self._in_graph_body else None)
+                                hyper_dev=g.get("hyper_dev") if self._in_graph_body else None,
+                                sparse=self._sparse and name == "fields")
 
     @staticmethod
     def _finish(loss_dict, loss, metrics):

@@ -225,18 +225,24 @@ def regularizer_plan(ms_grids_nerf, ms_grids_prop):
     return planes, terms, rows
 
 
-def kplanes_regularizers_into_grads(ms_grids_nerf, ms_grids_prop, loss_coefficients, accumulate: bool = False):
+def kplanes_regularizers_into_grads(ms_grids_nerf, ms_grids_prop, loss_coefficients, accumulate: bool = False,
+                                    write_range=None, grad_scale=None):
     """The training step's form of ``kplanes_regularizers``: ONE sweep per plane that returns the six SCALED loss values
     (detached; keyed like the reference's loss dict) and writes (``accumulate=False``: the sweep replaces the gradient
     buffer's memset) or adds the scaled regularisers' gradient into every plane's gradient sink (``ops.grad_sink``).
-    Planes without a sink (frozen / no bucket attached) only contribute their value."""
+    Planes without a sink (frozen / no bucket attached) only contribute their value.
+    ``write_range`` (int64 [P,2] device tensor) / ``grad_scale`` ([P] device tensor): the data-parallel step with the sparse
+    gradient exchange writes each plane's gradient only inside this rank's shard of the bucket, pre-multiplied by the world
+    size (the reduction then divides the sum by it)."""
     planes, terms, rows = regularizer_plan(ms_grids_nerf, ms_grids_prop)
     dev = planes[0].device
     scale = [float(loss_coefficients.get(n, 0.0)) for n in REG_NAMES]
     norm = _const(rows, dev)  # [P,6,4]
     coef = _const([[sum(scale[j] * r[j][i] for j in range(6)) for i in range(4)] for r in rows], dev)  # [P,4]
+    if grad_scale is not None:  # [P] per-plane factor on the GRADIENT only (the values below stay unscaled)
+        coef = coef * grad_scale[:, None]
     targets = [ops.grad_sink(p) for p in planes]
-    sums = ops.plane_reg_fused(planes, terms, coef, targets, accumulate)
+    sums = ops.plane_reg_fused(planes, terms, coef, targets, accumulate, write_range=write_range)
     vals = (sums.float()[:, None, :] * norm).sum(dim=(0, 2)) * _const(scale, dev)  # [6], already scaled
     return {name: vals[i] for i, name in enumerate(REG_NAMES) if name in loss_coefficients}, targets
 

@@ -146,6 +146,8 @@ class _Hexplane(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points: Points, n_scales: int, concat: bool, use_mask: int, post_backward, *planes):
         ctx.sinks = [grad_sink(p) for p in planes]
+        # sparse gradient exchange: per-texel "touched" bytes of the planes whose gradient sink is a marked bucket
+        ctx.touched = [getattr(p, "_kp_touched", None) if s is not None else None for p, s in zip(planes, ctx.sinks)]
         ctx.post_backward = post_backward
         planes = [as_channel_last(p.detach()) for p in planes]
         n_planes = len(planes) // n_scales
@@ -165,20 +167,27 @@ class _Hexplane(torch.autograd.Function):
         need = [ctx.needs_input_grad[5 + i] and bool((use_mask >> (i % n_planes)) & 1) for i in range(len(planes))]
         targets, grads = _targets(planes, ctx.sinks, need)
         hook = ctx.post_backward
+        marks = _plane_ptrs(ctx.touched) if any(t is not None for t in ctx.touched) else None
+
+        def scatter(tg):
+            if marks is not None:
+                call("kp_hexplane_bwd_flags", _plane_ptrs(planes), _plane_ptrs(tg), marks, _plane_hw(planes), n_scales, n_planes, c,
+                     points.struct(), points.M, int(concat), use_mask, ptr(g), stream_ptr())
+            else:
+                call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(tg), _plane_hw(planes), n_scales, n_planes, c,
+                     points.struct(), points.M, int(concat), use_mask, ptr(g), stream_ptr())
+
         if any(need):
             g = f32c(grad_out)
             if hook is not None and getattr(hook, "per_scale", False) and n_scales > 1:
                 # one scatter launch per scale, finest (largest planes) first: hook(k) can start reducing scale k's
                 # gradients while the remaining scales are scattered
                 for k in reversed(range(n_scales)):
-                    sub = [t if i // n_planes == k else None for i, t in enumerate(targets)]
-                    call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(sub), _plane_hw(planes), n_scales, n_planes, c,
-                         points.struct(), points.M, int(concat), use_mask, ptr(g), stream_ptr())
+                    scatter([t if i // n_planes == k else None for i, t in enumerate(targets)])
                     hook(k)
                 hook = None
             else:
-                call("kp_hexplane_bwd", _plane_ptrs(planes), _plane_ptrs(targets), _plane_hw(planes), n_scales, n_planes, c,
-                     points.struct(), points.M, int(concat), use_mask, ptr(g), stream_ptr())
+                scatter(targets)
         if hook is not None:
             hook()  # e.g. start the gradient all-reduce of the field bucket while the proposals back-propagate
         return (None, None, None, None, None, *grads)
@@ -881,7 +890,8 @@ class _PlaneReg(torch.autograd.Function):
 
 
 def plane_reg_fused(planes: Sequence[torch.Tensor], terms: Sequence[int], coef_dev: torch.Tensor,
-                    targets: Sequence[Optional[torch.Tensor]], accumulate: bool, want_sums: bool = True) -> Optional[torch.Tensor]:
+                    targets: Sequence[Optional[torch.Tensor]], accumulate: bool, want_sums: bool = True,
+                    write_range: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """One sweep per plane: -> sums [P,4] (float64) of the regulariser terms, and targets[p] (channel-last gradient
     buffers, entries may be None) = / += sum_i coef_dev[p,i] * d(sums[p,i])/d(plane).  No autograd: this is the training
     step's form, where the gradient goes straight into the parameter's bucket (and, with accumulate=False, replaces the
@@ -893,6 +903,12 @@ def plane_reg_fused(planes: Sequence[torch.Tensor], terms: Sequence[int], coef_d
             raise RuntimeError("plane_reg_fused: a gradient target must have the plane's channel-last layout")
     sums = torch.zeros((len(planes), 4), dtype=torch.float64, device=planes[0].device) if want_sums else None
     hwc, tm = _reg_tables(planes, terms)
+    if write_range is not None:  # int64 [P,2] on the device: float4 element range of each plane whose gradient is written
+        if write_range.dtype != torch.int64 or tuple(write_range.shape) != (len(planes), 2):
+            raise RuntimeError("plane_reg_fused: write_range must be int64 [P,2]")
+        call("kp_plane_reg_fused_range", _plane_ptrs(planes), _plane_ptrs(list(targets)), hwc, tm, len(planes), ptr(f32c(coef_dev)),
+             int(accumulate), ptr(sums), ptr(write_range), stream_ptr())
+        return sums
     call("kp_plane_reg_fused", _plane_ptrs(planes), _plane_ptrs(list(targets)), hwc, tm, len(planes), ptr(f32c(coef_dev)),
          int(accumulate), ptr(sums), stream_ptr())
     return sums
