@@ -26,6 +26,8 @@ struct PlaneRef {
   float* g;
   uint8_t* f;  // scatter only, optional: one "touched" byte per texel (set to 1 for every texel that receives a reduction)
   int H, W, ca, cb;
+  int stream;  // 1: the plane is far larger than L2 -- its lines are loaded / reduced with the L2 evict_first policy so that
+               // they do not push the coarse scales and the (heavily re-used) space-time planes out of the 126 MB L2
 };
 struct FieldRef {
   PlaneRef pl[KP_MAX_SCALES * KP_MAX_PLANES];
@@ -36,8 +38,26 @@ struct FieldRef {
   uint32_t agg_mask;  // scatter: bit k = merge equal texels of neighbouring samples of scale k inside the warp first
 };
 
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg4_stream(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void red_add_v4_stream(float* addr, float4 v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+               "l"(pol)
+               : "memory");
+}
+
 static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const* grad_ptrs, const int32_t* plane_hw,
-                      int n_scales, int n_planes, int D, uint32_t use_mask, int concat) {
+                      int n_scales, int n_planes, int D, uint32_t use_mask, int concat, int feature_dim = 32) {
   KP_CHECK(n_scales >= 1 && n_scales <= KP_MAX_SCALES, "n_scales=%d out of range [1,%d]", n_scales, KP_MAX_SCALES);
   KP_CHECK((n_planes == 3 && D == 3) || (n_planes == 6 && D == 4), "n_planes=%d / D=%d must be 3/3 or 6/4", n_planes, D);
   static const int comb4[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
@@ -48,6 +68,7 @@ static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const*
       r.p = plane_ptrs[k * n_planes + p];
       r.g = grad_ptrs ? grad_ptrs[k * n_planes + p] : nullptr;
       r.f = nullptr;
+      r.stream = 0;
       r.H = plane_hw[(k * n_planes + p) * 2 + 0];
       r.W = plane_hw[(k * n_planes + p) * 2 + 1];
       r.ca = (D == 4) ? comb4[p][0] : comb3[p][0];
@@ -88,6 +109,17 @@ static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const*
     if (agg != nullptr && strcmp(agg, "all") == 0) on = true;
     if (on) F.agg_mask |= 1u << k;
   }
+  // L2 policy (ncu, 32x preset: the gather read 1.74 GB and the scatter moved 6.1 GB of DRAM for ~0.5 / ~1.4 GB of distinct
+  // lines -- the once-per-step lines of the big space planes kept evicting the re-used coarse scales): planes of at least
+  // kStreamBytes are streamed with evict_first.  KP_L2_STREAM_MB overrides the threshold (0 = never).
+  long long stream_bytes = 16ll << 20;  // (sweep on B200, 32x preset: off 1.35 ms, 96 MB 1.28, 32 MB 1.25, 16 MB 1.19, 4 MB 1.22 ms scatter)
+  if (getenv("KP_L2_STREAM_MB") != nullptr) stream_bytes = atoll(getenv("KP_L2_STREAM_MB")) << 20;
+  if (stream_bytes > 0)
+    for (int k = 0; k < n_scales; ++k)
+      for (int p = 0; p < n_planes; ++p) {
+        PlaneRef& r = F.pl[k * KP_MAX_PLANES + p];
+        r.stream = ((long long)r.H * r.W * feature_dim * 4 >= stream_bytes) ? 1 : 0;
+      }
   return 0;
 }
 
@@ -195,6 +227,7 @@ __global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_const
   float pt[4];
   load_point(P, m, pt);
   const int out_stride = F.concat ? F.n_scales * C : C;
+  const uint64_t pol = l2_policy_evict_first();
   float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < F.n_scales; ++k) {
     Axis ax[4];
@@ -207,10 +240,17 @@ __global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_const
       b[p] = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
       if ((F.use_mask >> p) & 1u) {
         const float* base = pr.p + c4;
-        v[p][0] = ldg4(base + (int64_t)b[p].o00 * C);
-        v[p][1] = ldg4(base + (int64_t)b[p].o01 * C);
-        v[p][2] = ldg4(base + (int64_t)b[p].o10 * C);
-        v[p][3] = ldg4(base + (int64_t)b[p].o11 * C);
+        if (pr.stream) {  // (uniform: a property of the plane)
+          v[p][0] = ldg4_stream(base + (int64_t)b[p].o00 * C, pol);
+          v[p][1] = ldg4_stream(base + (int64_t)b[p].o01 * C, pol);
+          v[p][2] = ldg4_stream(base + (int64_t)b[p].o10 * C, pol);
+          v[p][3] = ldg4_stream(base + (int64_t)b[p].o11 * C, pol);
+        } else {
+          v[p][0] = ldg4(base + (int64_t)b[p].o00 * C);
+          v[p][1] = ldg4(base + (int64_t)b[p].o01 * C);
+          v[p][2] = ldg4(base + (int64_t)b[p].o10 * C);
+          v[p][3] = ldg4(base + (int64_t)b[p].o11 * C);
+        }
       }
     }
     float4 acc = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -273,6 +313,7 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
   float pt[4];
   load_point(P, m, pt);
   const int out_stride = F.concat ? F.n_scales * C : C;
+  const uint64_t pol = l2_policy_evict_first();
   for (int k = 0; k < F.n_scales; ++k) {
     // a scale without any gradient target is skipped whole (per-scale launches: the caller scatters one scale at a
     // time so that a finished scale can be all-reduced while the next one is scattered)
@@ -292,8 +333,12 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
       val[p] = make_float4(1.f, 1.f, 1.f, 1.f);
       if ((F.use_mask >> p) & 1u) {
         const float* base = pr.p + c4;
-        val[p] = bilerp_combine(b[p], ldg4(base + (int64_t)b[p].o00 * C), ldg4(base + (int64_t)b[p].o01 * C),
-                                ldg4(base + (int64_t)b[p].o10 * C), ldg4(base + (int64_t)b[p].o11 * C));
+        if (pr.stream)
+          val[p] = bilerp_combine(b[p], ldg4_stream(base + (int64_t)b[p].o00 * C, pol), ldg4_stream(base + (int64_t)b[p].o01 * C, pol),
+                                  ldg4_stream(base + (int64_t)b[p].o10 * C, pol), ldg4_stream(base + (int64_t)b[p].o11 * C, pol));
+        else
+          val[p] = bilerp_combine(b[p], ldg4(base + (int64_t)b[p].o00 * C), ldg4(base + (int64_t)b[p].o01 * C),
+                                  ldg4(base + (int64_t)b[p].o10 * C), ldg4(base + (int64_t)b[p].o11 * C));
       }
     }
     // prefix/suffix products: others[p] = prod_{q != p} val[q]
@@ -315,6 +360,11 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
         red_add_v4_aggregated<LPS>(gb, (live && b[p].w01 != 0.f) ? b[p].o01 : -1, scale4(gp, b[p].w01), lane);
         red_add_v4_aggregated<LPS>(gb, (live && b[p].w10 != 0.f) ? b[p].o10 : -1, scale4(gp, b[p].w10), lane);
         red_add_v4_aggregated<LPS>(gb, (live && b[p].w11 != 0.f) ? b[p].o11 : -1, scale4(gp, b[p].w11), lane);
+      } else if (live && pr.stream) {
+        if (b[p].w00 != 0.f) red_add_v4_stream(gb + (int64_t)b[p].o00 * C, scale4(gp, b[p].w00), pol);
+        if (b[p].w01 != 0.f) red_add_v4_stream(gb + (int64_t)b[p].o01 * C, scale4(gp, b[p].w01), pol);
+        if (b[p].w10 != 0.f) red_add_v4_stream(gb + (int64_t)b[p].o10 * C, scale4(gp, b[p].w10), pol);
+        if (b[p].w11 != 0.f) red_add_v4_stream(gb + (int64_t)b[p].o11 * C, scale4(gp, b[p].w11), pol);
       } else if (live) {
         if (b[p].w00 != 0.f) red_add_v4(gb + (int64_t)b[p].o00 * C, scale4(gp, b[p].w00));
         if (b[p].w01 != 0.f) red_add_v4(gb + (int64_t)b[p].o01 * C, scale4(gp, b[p].w01));
@@ -593,7 +643,7 @@ extern "C" int kp_hexplane_fwd(const float* const* plane_ptrs, const int32_t* pl
   if (check_points(points, M)) return 1;
   KP_CHECK(out != nullptr || M == 0, "hexplane_fwd: out is NULL");
   FieldRef F;
-  if (fill_field(F, plane_ptrs, nullptr, plane_hw, n_scales, n_planes, points->D, use_mask, concat)) return 1;
+  if (fill_field(F, plane_ptrs, nullptr, plane_hw, n_scales, n_planes, points->D, use_mask, concat, C)) return 1;
   return dispatch_hexplane(false, C, F, *points, M, nullptr, out, as_stream(stream));
 }
 
@@ -604,7 +654,7 @@ extern "C" int kp_hexplane_bwd_flags(const float* const* plane_ptrs, float* cons
   KP_CHECK(grad_out != nullptr || M == 0, "hexplane_bwd: grad_out is NULL");
   KP_CHECK(grad_plane_ptrs != nullptr, "hexplane_bwd: grad_plane_ptrs is NULL");
   FieldRef F;
-  if (fill_field(F, plane_ptrs, grad_plane_ptrs, plane_hw, n_scales, n_planes, points->D, use_mask, concat)) return 1;
+  if (fill_field(F, plane_ptrs, grad_plane_ptrs, plane_hw, n_scales, n_planes, points->D, use_mask, concat, C)) return 1;
   if (touched_ptrs != nullptr)
     for (int k = 0; k < n_scales; ++k)
       for (int p = 0; p < n_planes; ++p) F.pl[k * KP_MAX_PLANES + p].f = touched_ptrs[k * n_planes + p];
@@ -670,7 +720,7 @@ extern "C" int kp_density_field_fwd(const float* const* plane_ptrs, const int32_
   if (check_points(points, M)) return 1;
   KP_CHECK(w1 && w2 && hidden >= 1 && hidden <= 256, "density_field_fwd: bad MLP arguments");
   FieldRef F;
-  if (fill_field(F, plane_ptrs, nullptr, plane_hw, 1, n_planes, points->D, use_mask, 0)) return 1;
+  if (fill_field(F, plane_ptrs, nullptr, plane_hw, 1, n_planes, points->D, use_mask, 0, C)) return 1;
   return dispatch_density(false, C, F, *points, M, w1, w2, hidden, relu, density, nullptr, nullptr, nullptr,
                           as_stream(stream));
 }
@@ -683,7 +733,7 @@ extern "C" int kp_density_field_bwd(const float* const* plane_ptrs, float* const
   KP_CHECK(w1 && w2 && grad_w1 && grad_w2 && grad_density, "density_field_bwd: NULL argument");
   KP_CHECK(grad_plane_ptrs != nullptr, "density_field_bwd: grad_plane_ptrs is NULL");
   FieldRef F;
-  if (fill_field(F, plane_ptrs, grad_plane_ptrs, plane_hw, 1, n_planes, points->D, use_mask, 0)) return 1;
+  if (fill_field(F, plane_ptrs, grad_plane_ptrs, plane_hw, 1, n_planes, points->D, use_mask, 0, C)) return 1;
   return dispatch_density(true, C, F, *points, M, w1, w2, hidden, relu, nullptr, grad_density, grad_w1, grad_w2,
                           as_stream(stream));
 }

@@ -303,19 +303,27 @@ __global__ void __launch_bounds__(kPeerThreads) peer_sharded_adam_sparse_kernel(
       }
     }
   }
-  peer_barrier(b, 1, flag);  // every pushed parameter has landed AND every rank has finished reading the gradients
-  // 3. clean-up of this rank's own bucket outside its shard: marked lines back to zero, marks back to 0
-  float* gown = a.grad[a.rank];
-  uint8_t* town = a.touched[a.rank];
-  for (int64_t j = (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; j < a.n4; j += stride) {
+  peer_barrier(b, 1, flag);  // every pushed parameter has landed
+  if (threadIdx.x == 0) *counter = flag;
+}
+
+// Clean-up of this rank's own bucket outside its shard: marked lines back to zero, marks back to 0.  A SEPARATE launch
+// after the exchange kernel: the in-kernel barriers pair block k of every rank with block k of the others, so only the
+// completion of the whole exchange kernel (all of this rank's blocks past their end barrier, hence all of every peer's
+// blocks past their reads) guarantees that nobody still reads the lines being zeroed.
+__global__ void __launch_bounds__(kPeerThreads) peer_touched_cleanup_kernel(float* __restrict__ gown, uint8_t* __restrict__ town,
+                                                                            int64_t n4, int64_t lo, int64_t hi) {
+  const int64_t stride = (int64_t)gridDim.x * kPeerThreads;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t j = (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; j < n4; j += stride) {
     if (j >= lo && j < hi) continue;
     const uint32_t f = town[j >> 3];
+    __syncwarp();  // the 8 lanes of a line have read its mark before lane 0 of the line clears it
     if (f == 1u) {
       *reinterpret_cast<float4*>(gown + 4 * j) = zero;
       if ((j & 7) == 0) town[j >> 3] = 0;
     }
   }
-  if (threadIdx.x == 0) *counter = flag;
 }
 
 }  // namespace kp
@@ -413,6 +421,14 @@ extern "C" int kp_peer_sharded_adam_sparse(void* const* arenas, int rank, int wo
     case 7: peer_sharded_adam_sparse_kernel<7><<<blocks, kPeerThreads, 0, st>>>(a); break;
     case 8: peer_sharded_adam_sparse_kernel<8><<<blocks, kPeerThreads, 0, st>>>(a); break;
     default: set_error("peer_sharded_adam_sparse: world=%d unsupported", world); return 1;
+  }
+  kp::g_launches += 1;
+  {
+    const int64_t lo = a.n4 * rank / world, hi = a.n4 * (rank + 1) / world;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    peer_touched_cleanup_kernel<<<sms * 2, kPeerThreads, 0, st>>>(a.grad[rank], a.touched[rank], a.n4, lo, hi);
   }
   KP_LAUNCH_CHECK("peer_sharded_adam_sparse");
   return 0;

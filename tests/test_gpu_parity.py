@@ -794,6 +794,55 @@ def test_plane_reg_adam_matches_regulariser_sweep_plus_adam():
             assert float((pb[i] - pa[i]).abs().max()) < 1e-5 * lr * 100, (step, i)
 
 
+def test_fused_regularizer_sweep_write_range_and_touched_marks():
+    """The two pieces the sparse gradient exchange adds to single-GPU kernels: (1) kp_plane_reg_fused_range writes the
+    gradient only inside a per-plane float4 range (sums unchanged); (2) kp_hexplane_bwd_flags marks exactly the texels that
+    received a reduction and produces the same gradients as the unmarked scatter."""
+    from soccernerfs_b200 import ops
+
+    torch.manual_seed(5)
+    specs = [((1, 32, 70, 40), 3), ((1, 32, 30, 64), 14), ((1, 8, 50, 128), 3)]
+    planes = [(0.3 + 0.2 * torch.rand(sh, device=DEV)).contiguous(memory_format=torch.channels_last) for sh, _ in specs]
+    terms = [t for _, t in specs]
+    coef = (torch.rand(len(planes), 4, device=DEV) * 1e-2).contiguous()
+    full = [torch.zeros_like(p, memory_format=torch.preserve_format) for p in planes]
+    sums_full = ops.plane_reg_fused(planes, terms, coef, full, accumulate=False)
+    rng = torch.tensor([[100, 5000], [0, 0], [37, 12000]], dtype=torch.int64, device=DEV)
+    part = [torch.full_like(p, 7.0, memory_format=torch.preserve_format) for p in planes]
+    sums_part = ops.plane_reg_fused(planes, terms, coef, part, accumulate=False, write_range=rng)
+    assert torch.equal(sums_full, sums_part)
+    for f, q, (a, b) in zip(full, part, rng.tolist()):
+        fl = f.permute(0, 2, 3, 1).reshape(-1, 4)  # physical order, float4 rows
+        ql = q.permute(0, 2, 3, 1).reshape(-1, 4)
+        assert torch.equal(ql[a:b], fl[a:b])
+        assert bool((ql[:a] == 7.0).all()) and bool((ql[b:] == 7.0).all())
+
+    # (2) marks
+    n, c = 3000, 32
+    ms = [[(torch.rand(1, c, h, w, device=DEV)).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+           for (w, h) in ((24, 20), (24, 16), (24, 9), (20, 16), (20, 9), (16, 9))]]
+    pts = torch.rand(n, 4, device=DEV) * 2 - 1
+    gout = torch.randn(n, c, device=DEV)
+    feats = ops.hexplane_features(ms, ops.points_from_pts(pts), concat=True)
+    ref = torch.autograd.grad(feats, ms[0], gout)
+    sinks, marks = [], []
+    for p in ms[0]:
+        p._kp_grad_sink = torch.zeros_like(p, memory_format=torch.preserve_format)
+        p.grad = p._kp_grad_sink  # a sink is honoured only while it is the parameter's .grad
+        p._kp_touched = torch.zeros(p.shape[2] * p.shape[3], dtype=torch.uint8, device=DEV)
+        sinks.append(p._kp_grad_sink)
+        marks.append(p._kp_touched)
+    feats = ops.hexplane_features(ms, ops.points_from_pts(pts), concat=True)
+    feats.backward(gout)
+    for r, s_, m_ in zip(ref, sinks, marks):
+        assert rel_err(s_, r) < 1e-5
+        touched = (s_.permute(0, 2, 3, 1).reshape(-1, c) != 0).any(dim=1)
+        assert bool((m_.bool() | ~touched).all())  # every texel that holds a gradient is marked
+        assert int(m_.max()) == 1 and int(m_.bool().sum()) <= 4 * n
+    for p in ms[0]:
+        del p._kp_grad_sink, p._kp_touched
+
+
 def test_train_step_with_and_without_fused_regularizers():
     """TrainStep(fuse_regularizers=True) (no memset of the planes' gradients, one regulariser sweep) follows the
     two-sweep step: same losses over 6 steps, eagerly and from the graph."""
