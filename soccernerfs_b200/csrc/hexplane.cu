@@ -111,10 +111,15 @@ static int fill_field(FieldRef& F, const float* const* plane_ptrs, float* const*
   }
   // L2 policy (ncu, 32x preset: the gather read 1.74 GB and the scatter moved 6.1 GB of DRAM for ~0.5 / ~1.4 GB of distinct
   // lines -- the once-per-step lines of the big space planes kept evicting the re-used coarse scales): planes of at least
-  // kStreamBytes are streamed with evict_first.  KP_L2_STREAM_MB overrides the threshold (0 = never).
+  // stream_bytes are streamed with evict_first.  KP_L2_STREAM_MB overrides the threshold (0 = never).
   long long stream_bytes = 16ll << 20;  // (sweep on B200, 32x preset: off 1.35 ms, 96 MB 1.28, 32 MB 1.25, 16 MB 1.19, 4 MB 1.22 ms scatter)
   if (getenv("KP_L2_STREAM_MB") != nullptr) stream_bytes = atoll(getenv("KP_L2_STREAM_MB")) << 20;
-  if (stream_bytes > 0)
+  // only when the field as a whole is far beyond L2 (>= 512 MB): a 152 MB field keeps a 75 % L2 hit rate without any
+  // policy, and streaming its largest scale costs more misses than it saves (ncu: gather DRAM reads 193 -> 269 MB)
+  long long total_bytes = 0;
+  for (int k = 0; k < n_scales; ++k)
+    for (int p = 0; p < n_planes; ++p) total_bytes += (long long)F.pl[k * KP_MAX_PLANES + p].H * F.pl[k * KP_MAX_PLANES + p].W * feature_dim * 4;
+  if (stream_bytes > 0 && total_bytes >= (512ll << 20))
     for (int k = 0; k < n_scales; ++k)
       for (int p = 0; p < n_planes; ++p) {
         PlaneRef& r = F.pl[k * KP_MAX_PLANES + p];
