@@ -168,19 +168,20 @@ __global__ void __launch_bounds__(256) plane_reg_fused_kernel(const __grid_const
   if (active) {
     const float* base = t + (size_t)col * 4;
     const size_t rstride = (size_t)row4 * 4;
+    float* __restrict__ gbase = P.g;  // never aliases the planes: lets the loads of later rows move above the stores
     auto row_at = [&](int h) -> float4 { return (h >= 0 && h < H) ? ldg4(base + (size_t)h * rstride) : zero; };
-    float4 a = need2 ? row_at(h0 - 2) : zero, b = row_at(h0 - 1), c = row_at(h0), d = row_at(h0 + 1);
-#pragma unroll 4
-    for (int h = h0; h < h1; ++h) {
-      const float4 e = need2 ? row_at(h + 2) : zero;
+    const bool hasL = wcol >= 1, hasR = wcol + 1 < W, needW = (terms & 2u) != 0;
+    // one row: c = row h, b / a = rows h-1 / h-2, d / e = rows h+1 / h+2, l / r = W neighbours of row h
+    auto do_row = [&](int h, const float4& a, const float4& b, const float4& c, const float4& d, const float4& e, const float4& l,
+                      const float4& r) {
       float4 g = zero;
       if (terms & 1u) {  // squared first difference along H
         if (h + 1 < H) { const float4 df = sub4m(d, c); s0 += sq4m(df); g = fma4(df, -2.f * k0, g); }
         if (h >= 1) g = fma4(sub4m(c, b), 2.f * k0, g);
       }
-      if (terms & 2u) {  // squared first difference along W
-        if (wcol + 1 < W) { const float4 df = sub4m(ldg4(base + (size_t)h * rstride + C4 * 4), c); s1 += sq4m(df); g = fma4(df, -2.f * k1, g); }
-        if (wcol >= 1) g = fma4(sub4m(c, ldg4(base + (size_t)h * rstride - C4 * 4)), 2.f * k1, g);
+      if (needW) {  // squared first difference along W
+        if (hasR) { const float4 df = sub4m(r, c); s1 += sq4m(df); g = fma4(df, -2.f * k1, g); }
+        if (hasL) g = fma4(sub4m(c, l), 2.f * k1, g);
       }
       if (need2) {  // squared second difference along H
         if (h + 2 < H) { const float4 dd = sub4m(sub4m(e, d), sub4m(d, c)); s2 += sq4m(dd); g = fma4(dd, 2.f * k2, g); }
@@ -191,16 +192,33 @@ __global__ void __launch_bounds__(256) plane_reg_fused_kernel(const __grid_const
         s3 += fabsf(1.f - c.x) + fabsf(1.f - c.y) + fabsf(1.f - c.z) + fabsf(1.f - c.w);
         g.x -= k3 * sgnm(1.f - c.x); g.y -= k3 * sgnm(1.f - c.y); g.z -= k3 * sgnm(1.f - c.z); g.w -= k3 * sgnm(1.f - c.w);
       }
-      if (P.g != nullptr) {
+      if (gbase != nullptr) {
         const long long e4 = (long long)h * row4 + col;
         if (write_range == nullptr || (e4 >= wr0 && e4 < wr1)) {
-          float4* gp = reinterpret_cast<float4*>(P.g + (size_t)h * rstride + (size_t)col * 4);
+          float4* gp = reinterpret_cast<float4*>(gbase + (size_t)h * rstride + (size_t)col * 4);
           if (ACCUMULATE) { const float4 cur = *gp; g.x += cur.x; g.y += cur.y; g.z += cur.z; g.w += cur.w; }
           *gp = g;
         }
       }
-      a = b; b = c; c = d; d = e;
-      if (!need2) d = row_at(h + 2);
+    };
+    float4 a = need2 ? row_at(h0 - 2) : zero, b = row_at(h0 - 1), c = row_at(h0), d = row_at(h0 + 1);
+    // four rows per iteration: the four next rows and the eight W neighbours are loaded up front (12 independent 16-byte
+    // loads in flight per thread -- the one-row-at-a-time version ran at 1.1 TB/s)
+    for (int h = h0; h < h1; h += 4) {
+      float4 nr[4], l[4], r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nr[i] = row_at(h + 2 + i);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool in = h + i < h1;
+        l[i] = (needW && hasL && in) ? ldg4(base + (size_t)(h + i) * rstride - C4 * 4) : zero;
+        r[i] = (needW && hasR && in) ? ldg4(base + (size_t)(h + i) * rstride + C4 * 4) : zero;
+      }
+      do_row(h, a, b, c, d, nr[0], l[0], r[0]);
+      if (h + 1 < h1) do_row(h + 1, b, c, d, nr[0], nr[1], l[1], r[1]);
+      if (h + 2 < h1) do_row(h + 2, c, d, nr[0], nr[1], nr[2], l[2], r[2]);
+      if (h + 3 < h1) do_row(h + 3, d, nr[0], nr[1], nr[2], nr[3], l[3], r[3]);
+      a = nr[0]; b = nr[1]; c = nr[2]; d = nr[3];
     }
   }
   if (sums != nullptr) {

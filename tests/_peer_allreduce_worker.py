@@ -106,17 +106,21 @@ def main() -> None:
     runs = {}
     # "peer" = in-place all-reduce + replicated Adam; "peer-sharded" = reduce-scatter + Adam on the shard + all-gather in
     # one kernel (the default under the peer backend)
+    # "peer-sparse" = the sharded step with the sparse gradient exchange (scatter marks touched lines, only marked lines are
+    # pulled, owner-only regulariser gradient, in-kernel clean-up instead of the bucket memset)
     for backend, graph in (("nccl", False), ("nccl-again", False), ("nccl", True), ("peer", False), ("peer", True),
-                           ("peer-sharded", False), ("peer-sharded", True)):
+                           ("peer-sharded", False), ("peer-sharded", True), ("peer-sparse", False), ("peer-sparse", True)):
         model = build_model("tiny", mp, gold["aabb"], "cuda")
         model.config.background_color_train = "black"
         model.proposal_sampler.initial_sampler.train_stratified = False
         model.proposal_sampler.pdf_sampler.train_stratified = False
         step = TrainStep(model, max_steps=100, warm_up_end=4, data_parallel=True, use_cuda_graph=graph,
                          allreduce_backend=backend.split("-")[0], allreduce_mode="overlap-per-scale" if graph else "overlap",
-                         shard_optimizer=backend == "peer-sharded")
+                         shard_optimizer=backend in ("peer-sharded", "peer-sparse"),
+                         sparse_grad_exchange=backend == "peer-sparse")
         assert step.allreduce_backend == backend.split("-")[0]
-        assert bool(step.sharded) == (backend == "peer-sharded")
+        assert bool(step.sharded) == (backend in ("peer-sharded", "peer-sparse"))
+        assert step._sparse == (backend == "peer-sparse")
         n_rays = gold["origins"].shape[0]
         lo, hi = rank * n_rays // world, (rank + 1) * n_rays // world  # every rank trains on its own rays
         losses = []
