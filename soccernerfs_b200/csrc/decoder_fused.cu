@@ -40,7 +40,7 @@ __device__ __forceinline__ void store_act16(const float* x, int row, int col0, f
     const int ch = (col0 >> 2) + q, kb = ch >> 3, c = ch & 7;
     const int off = kb * (128 * 32) + row * 32 + ((c ^ (row & 7)) << 2);
     float4 hi, lo;
-    hi.x = to_tf32(x[4 * q]); hi.y = to_tf32(x[4 * q + 1]); hi.z = to_tf32(x[4 * q + 2]); hi.w = to_tf32(x[4 * q + 3]);
+    hi.x = tf32_hi(x[4 * q]); hi.y = tf32_hi(x[4 * q + 1]); hi.z = tf32_hi(x[4 * q + 2]); hi.w = tf32_hi(x[4 * q + 3]);
     lo.x = x[4 * q] - hi.x; lo.y = x[4 * q + 1] - hi.y; lo.z = x[4 * q + 2] - hi.z; lo.w = x[4 * q + 3] - hi.w;
     *reinterpret_cast<float4*>(s_hi + off) = hi;
     *reinterpret_cast<float4*>(s_lo + off) = lo;

@@ -6,6 +6,10 @@
 // staged reduction-major so both micro-tile operands are 16-byte LDS) instantiated for the three products a
 // dense layer needs -- Y = X W^T, dX = dY W, dW += dY^T X (split over the M reduction, atomically
 // accumulated) -- with the activations / masks fused in the epilogues.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace kp {
@@ -210,6 +214,114 @@ __global__ void sigmoid_grad_kernel(const float* __restrict__ rgb, const float* 
   dpre[idx] = v;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of a NARROW output layer (sigma net: 16 outputs, colour net: 3) in plain fp32 SIMT, one pass:
+//   dOut[M,NO] is formed on the fly from the upstream gradients (never written),
+//   dH[M,K] = (dOut . W) * (H > 0)            (the hidden layer's ReLU mask)
+//   dW[NO,K] += dOut^T . H
+// With NO <= 16 the two products are 8*NO FMAs per 16 bytes of H: far below the memory time of streaming H in and dH
+// out, so the tensor-core route (two GEMM launches that each stream H again, plus a kernel that materialises dOut)
+// only added launches and passes over memory.  K/4 lanes own one row (coalesced 16-byte accesses); every lane keeps its
+// four columns of W and of the dW accumulator in registers; block-level reduction of dW in shared memory, one red per
+// weight per block.
+//   MODE 0: dOut[:, 0:15] = grad_geo (or 0), dOut[:,15] += grad_density * exp(clamp(o[:,15], -15, 15))   (_TruncExp backward)
+//   MODE 1: dOut[:, j] = grad_rgb * rgb * (1 - rgb)                                                       (sigmoid backward)
+// ---------------------------------------------------------------------------------------------------------------
+template <int NO, int K, int MODE>
+__global__ void __launch_bounds__(128) narrow_layer_bwd_kernel(const float* __restrict__ H, float* __restrict__ dH,
+                                                               const float* __restrict__ W, float* __restrict__ dW, int64_t M,
+                                                               const float* __restrict__ a0, const float* __restrict__ a1,
+                                                               const float* __restrict__ a2) {
+  constexpr int LPR = K / 4;      // lanes per row
+  constexpr int RPW = 32 / LPR;   // rows per warp pass
+  static_assert(LPR == 16 || LPR == 32, "K must be 64 or 128");
+  __shared__ float s_acc[NO * K];
+  for (int i = threadIdx.x; i < NO * K; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane % LPR, sub = lane / LPR;
+  float4 w[NO], acc[NO];
+#pragma unroll
+  for (int j = 0; j < NO; ++j) {
+    w[j] = ldg4(W + (size_t)j * K + 4 * q);
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  constexpr int U = NO <= 4 ? 4 : 1;  // rows in flight per lane: all loads of U rows are issued before the arithmetic
+  for (int64_t base = gw * RPW * U; base < M; base += warps_total * RPW * U) {
+    float d[U][NO];
+    float4 h[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t s = base + u * RPW + sub;
+      h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NO; ++j) d[u][j] = 0.f;
+      if (s < M) {
+        if (MODE == 0) {
+#pragma unroll
+          for (int j4 = 0; j4 < NO / 4; ++j4) {
+            const float4 g = a2 != nullptr ? ldg4(a2 + s * NO + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            d[u][4 * j4] = g.x; d[u][4 * j4 + 1] = g.y; d[u][4 * j4 + 2] = g.z; d[u][4 * j4 + 3] = g.w;
+          }
+          if (a1 != nullptr) d[u][NO - 1] += __ldg(a1 + s) * expf(fminf(fmaxf(__ldg(a0 + s * NO + NO - 1), -15.f), 15.f));
+        } else {
+#pragma unroll
+          for (int j = 0; j < NO; ++j) {
+            const float sg = __ldg(a0 + s * NO + j);
+            d[u][j] = __ldg(a1 + s * NO + j) * sg * (1.f - sg);
+          }
+        }
+        h[u] = ldg4(H + s * K + 4 * q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t s = base + u * RPW + sub;
+      if (s >= M) continue;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NO; ++j) {
+        o = fma4(w[j], d[u][j], o);
+        acc[j] = fma4(h[u], d[u][j], acc[j]);
+      }
+      if (!(h[u].x > 0.f)) o.x = 0.f;
+      if (!(h[u].y > 0.f)) o.y = 0.f;
+      if (!(h[u].z > 0.f)) o.z = 0.f;
+      if (!(h[u].w > 0.f)) o.w = 0.f;
+      *reinterpret_cast<float4*>(dH + s * K + 4 * q) = o;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NO; ++j) {
+    atomicAdd(&s_acc[j * K + 4 * q + 0], acc[j].x);
+    atomicAdd(&s_acc[j * K + 4 * q + 1], acc[j].y);
+    atomicAdd(&s_acc[j * K + 4 * q + 2], acc[j].z);
+    atomicAdd(&s_acc[j * K + 4 * q + 3], acc[j].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NO * K; i += blockDim.x) red_add_f32(dW + i, s_acc[i]);
+}
+
+template <int NO, int MODE>
+static bool launch_narrow_bwd(int K, const float* H, float* dH, const float* W, float* dW, int64_t M, const float* a0,
+                              const float* a1, const float* a2, cudaStream_t st) {
+  if (getenv("KP_NARROW_BWD") != nullptr && atoi(getenv("KP_NARROW_BWD")) == 0) return false;
+  if (K != 64 && K != 128) return false;
+  if ((((uintptr_t)H | (uintptr_t)dH | (uintptr_t)W) & 15) != 0 || (a2 != nullptr && ((uintptr_t)a2 & 15) != 0)) return false;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int rpw = 32 / (K / 4);
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 4 * rpw), (int64_t)sms * 4));
+  if (K == 64) narrow_layer_bwd_kernel<NO, 64, MODE><<<grid, 128, 0, st>>>(H, dH, W, dW, M, a0, a1, a2);
+  else narrow_layer_bwd_kernel<NO, 128, MODE><<<grid, 128, 0, st>>>(H, dH, W, dW, M, a0, a1, a2);
+  kp::g_launches += 1;
+  return true;
+}
+
 }  // namespace kp
 
 using namespace kp;
@@ -237,10 +349,15 @@ extern "C" int kp_sigma_net_bwd(const float* feats, const float* w1, const float
   // H >= 16, and d_o is consumed (dW2, d_h1) before d_h1 overwrites scratch -- so d_o needs its own storage.
   // We therefore keep d_o in grad_feats' first M*16 floats (K >= 16), which is only written by the last GEMM.
   KP_CHECK(K >= 16 && grad_feats != nullptr, "sigma_net_bwd: needs grad_feats with K >= 16");
-  float* d_o = grad_feats;
-  sigma_dout_kernel<<<(unsigned)ceil_div(M * 16, 256), 256, 0, st>>>(o, grad_density, grad_geo, M, d_o);
-  gemm_dw(d_o, 16, h1, H, grad_w2, H, M, 16, H, st);
-  gemm_dx<EPI_RELU_MASK>(d_o, 16, w2, H, scratch, H, M, 16, H, h1, H, st);   // d_h1
+  // (the 16-output version of the narrow SIMT kernel needs 64 dW accumulator registers per lane and measured slower than
+  //  the tensor-core route: 0.221 vs 0.158 ms for the whole sigma backward at cfg2 -- opt-in with KP_NARROW_BWD=2)
+  const bool narrow16 = getenv("KP_NARROW_BWD") != nullptr && atoi(getenv("KP_NARROW_BWD")) == 2;
+  if (!narrow16 || !launch_narrow_bwd<16, 0>(H, h1, scratch, w2, grad_w2, M, o, grad_density, grad_geo, st)) {
+    float* d_o = grad_feats;
+    sigma_dout_kernel<<<(unsigned)ceil_div(M * 16, 256), 256, 0, st>>>(o, grad_density, grad_geo, M, d_o);
+    gemm_dw(d_o, 16, h1, H, grad_w2, H, M, 16, H, st);
+    gemm_dx<EPI_RELU_MASK>(d_o, 16, w2, H, scratch, H, M, 16, H, h1, H, st);   // d_h1
+  }
   gemm_dw(scratch, H, feats, K, grad_w1, K, M, H, K, st);
   gemm_dx<EPI_NONE>(scratch, H, w1, K, grad_feats, K, M, H, K, nullptr, 0, st);
   KP_LAUNCH_CHECK("sigma_net_bwd");
@@ -275,10 +392,12 @@ extern "C" int kp_color_net_bwd(int view_dependent, const float* cin, const floa
            "color_net_bwd: bad arguments");
   cudaStream_t st = as_stream(stream);
   const int ldc = view_dependent ? 32 : 16, kin = view_dependent ? 31 : 15, geo_off = view_dependent ? 16 : 0;
-  float* dpre = scratch_b;  // [M,4]
-  sigmoid_grad_kernel<<<(unsigned)ceil_div(M * 4, 256), 256, 0, st>>>(rgb, grad_rgb, M, dpre);
-  gemm_dw(dpre, 4, h3, H2, grad_w5, H2, M, 3, H2, st);
-  gemm_dx<EPI_RELU_MASK>(dpre, 4, w5, H2, scratch_a, H2, M, 3, H2, h3, H2, st);       // d_h3 -> a
+  if (!launch_narrow_bwd<3, 1>(H2, h3, scratch_a, w5, grad_w5, M, rgb, grad_rgb, nullptr, st)) {  // d_h3 -> a, dW5, one pass
+    float* dpre = scratch_b;  // [M,4]
+    sigmoid_grad_kernel<<<(unsigned)ceil_div(M * 4, 256), 256, 0, st>>>(rgb, grad_rgb, M, dpre);
+    gemm_dw(dpre, 4, h3, H2, grad_w5, H2, M, 3, H2, st);
+    gemm_dx<EPI_RELU_MASK>(dpre, 4, w5, H2, scratch_a, H2, M, 3, H2, h3, H2, st);       // d_h3 -> a
+  }
   gemm_dw(scratch_a, H2, h2, H2, grad_w4, H2, M, H2, H2, st);
   gemm_dx<EPI_RELU_MASK>(scratch_a, H2, w4, H2, scratch_b, H2, M, H2, H2, h2, H2, st);  // d_h2 -> b
   gemm_dw(scratch_b, H2, cin, ldc, grad_w3, kin, M, H2, kin, st);

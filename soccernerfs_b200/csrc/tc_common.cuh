@@ -161,7 +161,9 @@ __device__ __forceinline__ void tile_load(TileRegs<COLS_PAD>& t, const float* __
     }
   }
 }
-__device__ __forceinline__ float tf32_hi(float x) { return to_tf32(x); }  // round-to-nearest: |x - hi| <= 2^-12 |x|
+// hi part of the split: the low 13 mantissa bits cleared -- exactly what kind::tf32 reads of an fp32 word, in ONE LOP3
+// (cvt.rna.tf32 is emulated with ~5 instructions per element on sm_100a and was 16.7 % of the staging kernels' instructions)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 template <int MN_VIEW, int COLS_PAD>
 __device__ __forceinline__ void tile_store(const TileRegs<COLS_PAD>& t, float* __restrict__ s_hi, float* __restrict__ s_lo) {
   constexpr int CPR = COLS_PAD / 4, U = CPR / 2, ROWSTEP = 256 / CPR;
