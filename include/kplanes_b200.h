@@ -271,6 +271,14 @@ int kp_generate_rays(const float* c2w /* [n_cams,3,4] */, const float* intrinsic
  *      difference to the neighbours, <= alpha zeroed; ones for an image without neighbours. ---- */
 int kp_ist_map(const float* images, int B, int64_t HW, const int32_t* nbr_offsets, const int32_t* nbrs, float alpha,
                void* out_fp16, void* stream);
+/* ISG map of DynamicDataset.compute_isg (NS/data/datasets/dynamic_dataset.py:215-326) on device images [B,H,W,3] fp32:
+ * per camera the per-pixel, per-channel lower median over its frames (cam_offsets int32 [n_cams+1] / cam_images int32:
+ * CSR lists of image indices per camera; at most 256 frames per camera), then per image (image_cam int32 [B] = its
+ * camera slot) the Geman-McClure residual (1/3) * sum_c d_c^2 / (d_c^2 + gamma_sq), fp16 [B,H,W].  median_scratch: device
+ * float [n_cams, H*W, 3].  Bit-identical to the reference's torch ops. */
+int kp_isg_map(const float* images, int B, int64_t HW, const int32_t* cam_offsets, const int32_t* cam_images,
+               const int32_t* image_cam, int n_cams, int max_frames_per_cam, float gamma_sq, float* median_scratch,
+               void* out_fp16, void* stream);
 
 /* ---- (a14b) loss head: the reductions, coefficients, total and PSNR that KPlanesModel.get_loss_dict /
  *      get_metrics_dict (NS/models/kplanes.py:392-452) and the trainer's sum(loss_dict.values())

@@ -220,7 +220,7 @@ __device__ __forceinline__ float4 bilerp_combine(const Bilerp& b, float4 v00, fl
 // ---------------------------------------------------------------------------------------------------
 // Forward gather.  C/4 lanes per sample, float4 per lane.
 // ---------------------------------------------------------------------------------------------------
-template <int C, int NP>
+template <int C, int NP, bool STREAM>
 __global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_constant__ FieldRef F,
                                                             const __grid_constant__ KpPoints P, int64_t M,
                                                             float* __restrict__ out) {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_const
   float pt[4];
   load_point(P, m, pt);
   const int out_stride = F.concat ? F.n_scales * C : C;
-  const uint64_t pol = l2_policy_evict_first();
+  const uint64_t pol = STREAM ? l2_policy_evict_first() : 0ull;
   float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < F.n_scales; ++k) {
     Axis ax[4];
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_const
       b[p] = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
       if ((F.use_mask >> p) & 1u) {
         const float* base = pr.p + c4;
-        if (pr.stream) {  // (uniform: a property of the plane)
+        if (STREAM && pr.stream) {  // (uniform: a property of the plane; STREAM = false compiles the policy code out)
           v[p][0] = ldg4_stream(base + (int64_t)b[p].o00 * C, pol);
           v[p][1] = ldg4_stream(base + (int64_t)b[p].o01 * C, pol);
           v[p][2] = ldg4_stream(base + (int64_t)b[p].o10 * C, pol);
@@ -302,7 +302,7 @@ __device__ __forceinline__ void red_add_v4_aggregated(float* __restrict__ plane_
   if (head && key >= 0) red_add_v4(plane_grad + (int64_t)key * (LPS * 4), v);
 }
 
-template <int C, int NP>
+template <int C, int NP, bool STREAM>
 __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_constant__ FieldRef F,
                                                             const __grid_constant__ KpPoints P, int64_t M,
                                                             const float* __restrict__ grad_out) {
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
   float pt[4];
   load_point(P, m, pt);
   const int out_stride = F.concat ? F.n_scales * C : C;
-  const uint64_t pol = l2_policy_evict_first();
+  const uint64_t pol = STREAM ? l2_policy_evict_first() : 0ull;
   for (int k = 0; k < F.n_scales; ++k) {
     // a scale without any gradient target is skipped whole (per-scale launches: the caller scatters one scale at a
     // time so that a finished scale can be all-reduced while the next one is scattered)
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
       val[p] = make_float4(1.f, 1.f, 1.f, 1.f);
       if ((F.use_mask >> p) & 1u) {
         const float* base = pr.p + c4;
-        if (pr.stream)
+        if (STREAM && pr.stream)
           val[p] = bilerp_combine(b[p], ldg4_stream(base + (int64_t)b[p].o00 * C, pol), ldg4_stream(base + (int64_t)b[p].o01 * C, pol),
                                   ldg4_stream(base + (int64_t)b[p].o10 * C, pol), ldg4_stream(base + (int64_t)b[p].o11 * C, pol));
         else
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(128, 4) hexplane_bwd_kernel(const __grid_const
         red_add_v4_aggregated<LPS>(gb, (live && b[p].w01 != 0.f) ? b[p].o01 : -1, scale4(gp, b[p].w01), lane);
         red_add_v4_aggregated<LPS>(gb, (live && b[p].w10 != 0.f) ? b[p].o10 : -1, scale4(gp, b[p].w10), lane);
         red_add_v4_aggregated<LPS>(gb, (live && b[p].w11 != 0.f) ? b[p].o11 : -1, scale4(gp, b[p].w11), lane);
-      } else if (live && pr.stream) {
+      } else if (STREAM && live && pr.stream) {
         if (b[p].w00 != 0.f) red_add_v4_stream(gb + (int64_t)b[p].o00 * C, scale4(gp, b[p].w00), pol);
         if (b[p].w01 != 0.f) red_add_v4_stream(gb + (int64_t)b[p].o01 * C, scale4(gp, b[p].w01), pol);
         if (b[p].w10 != 0.f) red_add_v4_stream(gb + (int64_t)b[p].o10 * C, scale4(gp, b[p].w10), pol);
@@ -603,12 +603,20 @@ static int launch_hexplane(bool bwd, const FieldRef& F, const KpPoints& P, int64
   const int64_t blocks = ceil_div(M * LPS, 128);
   if (blocks == 0) return 0;
   KP_CHECK(blocks < (1ll << 31), "hexplane: M too large");
+  bool any_stream = false;  // the L2-policy variant only where a plane asks for it (it costs registers: 0.162 -> 0.181 ms at cfg2)
+  for (int k = 0; k < F.n_scales; ++k)
+    for (int p = 0; p < F.n_planes; ++p) any_stream |= F.pl[k * KP_MAX_PLANES + p].stream != 0;
   if (F.n_planes == 6) {
-    if (!bwd) hexplane_fwd_kernel<C, 6><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, out);
-    else hexplane_bwd_kernel<C, 6><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, grad_out);
+    if (any_stream) {
+      if (!bwd) hexplane_fwd_kernel<C, 6, true><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, out);
+      else hexplane_bwd_kernel<C, 6, true><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, grad_out);
+    } else {
+      if (!bwd) hexplane_fwd_kernel<C, 6, false><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, out);
+      else hexplane_bwd_kernel<C, 6, false><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, grad_out);
+    }
   } else {
-    if (!bwd) hexplane_fwd_kernel<C, 3><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, out);
-    else hexplane_bwd_kernel<C, 3><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, grad_out);
+    if (!bwd) hexplane_fwd_kernel<C, 3, false><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, out);
+    else hexplane_bwd_kernel<C, 3, false><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, grad_out);
   }
   KP_LAUNCH_CHECK("hexplane");
   return 0;

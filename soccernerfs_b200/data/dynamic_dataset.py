@@ -1,8 +1,8 @@
 """Importance-sampling weight maps of the dynamic dataset: IST (temporal difference) and ISG (global median).
 
 Arithmetic of ``DynamicDataset.compute_ist`` (NS/data/datasets/dynamic_dataset.py:328-470) and ``compute_isg``
-(:215-326) on an image batch, without the file caching / tqdm / debug-map code around it.  Host-side torch ops like the reference's (it runs them once per image-cache reload, not per training step); IST also
-has a device path (``compute_ist_cuda`` -> ``kp_ist_map``) used when the images are on the GPU.
+(:215-326) on an image batch, without the file caching / tqdm / debug-map code around it.  Host-side torch ops like the reference's (it runs them once per image-cache reload, not per training step); both maps
+also have a device path (``kp_ist_map`` / ``kp_isg_map``) used when the images are on the GPU.
 """
 from __future__ import annotations
 
@@ -63,7 +63,12 @@ def compute_ist(images: torch.Tensor, cam_ids: torch.Tensor, cam_times: torch.Te
 
 
 def compute_isg(images: torch.Tensor, cam_ids: torch.Tensor, isg_gamma: float, device="cpu") -> torch.Tensor:
-    """images [B,H,W,3], cam_ids [B] -> fp16 [B,H,W]: Geman-McClure residual to the per-camera median image."""
+    """images [B,H,W,3], cam_ids [B] -> fp16 [B,H,W]: Geman-McClure residual to the per-camera median image.  Images on
+    the GPU take the device path (``kp_isg_map``), bit-identical to this host version."""
+    if images.is_cuda:
+        from .. import ops
+
+        return ops.isg_map(images, cam_ids, isg_gamma)
     b, h, w = images.shape[:3]
     cam_ids = cam_ids.reshape(-1)
     medians = {}

@@ -765,6 +765,32 @@ def generate_rays(c2w: torch.Tensor, intrinsics: torch.Tensor, cam_times: Option
     return origins, directions, pixel_area, norm, times
 
 
+def isg_map(images: torch.Tensor, cam_ids: torch.Tensor, gamma: float) -> torch.Tensor:
+    """ISG weight map on the device (kp_isg_map): images [B,H,W,3] fp32 CUDA, cam_ids [B] -> fp16 [B,H,W]."""
+    if images.dim() != 4 or images.shape[-1] != 3:
+        raise ValueError("isg_map: images must be [B,H,W,3]")
+    img = f32c(images)
+    b, h, w = img.shape[:3]
+    ids = cam_ids.reshape(-1).cpu()
+    uniq = torch.unique(ids)
+    slot = {int(c): k for k, c in enumerate(uniq.tolist())}
+    groups = [torch.where(ids == c)[0] for c in uniq]
+    offsets = torch.tensor([0] + list(torch.cumsum(torch.tensor([len(g) for g in groups]), 0).tolist()), dtype=torch.int32)
+    cam_images = torch.cat(groups).to(torch.int32)
+    image_cam = torch.tensor([slot[int(c)] for c in ids.tolist()], dtype=torch.int32)
+    dev = img.device
+    offsets, cam_images, image_cam = offsets.to(dev), cam_images.to(dev), image_cam.to(dev)
+    scratch = torch.empty(len(uniq) * h * w * 3, dtype=torch.float32, device=dev)
+    out = torch.empty((b, h, w), dtype=torch.float16, device=dev)
+    import numpy as np
+
+    gamma_sq = float(np.float32(float(gamma) ** 2))  # python double gamma**2, then cast to fp32 like torch's scalar add
+    call("kp_isg_map", ptr(img), b, h * w, c_void_p(offsets.data_ptr()), c_void_p(cam_images.data_ptr()),
+         c_void_p(image_cam.data_ptr()), len(uniq), max(len(g) for g in groups), gamma_sq, ptr(scratch), c_void_p(out.data_ptr()),
+         stream_ptr())
+    return out
+
+
 def ist_map(images: torch.Tensor, nbr_offsets: torch.Tensor, nbrs: torch.Tensor, alpha: float) -> torch.Tensor:
     """IST importance map (dynamic_dataset.py:328-470): images [B,H,W,3] fp32 (CUDA), CSR neighbour lists int32 (CUDA)
     -> fp16 [B,H,W]."""

@@ -81,3 +81,19 @@ def test_ist_map_kernel_bit_exact_vs_reference_fixture():
     assert ist.is_cuda and ist.dtype == torch.float16 and ist.shape == g["ist"].shape
     assert torch.equal(ist.float().cpu(), g["ist"])
     assert bool((ist[11] == 1).all())  # the only frame of its camera: uniform map
+
+
+@pytest.mark.gpu
+def test_isg_map_kernel_bit_exact_vs_reference_fixture():
+    """(f4) kp_isg_map == the ISG map the reference's own compute_isg produced (per-camera median + Geman-McClure, fp16)."""
+    from soccernerfs_b200.data.dynamic_dataset import compute_isg
+
+    g = load_golden("importance")
+    isg = compute_isg(g["images"].cuda(), g["cam_ids"], 5e-2)
+    assert isg.is_cuda and isg.dtype == torch.float16 and isg.shape == g["isg"].shape
+    assert torch.equal(isg.float().cpu(), g["isg"])
+    # a larger random case (even and odd frame counts per camera) against the host implementation
+    gen = torch.Generator().manual_seed(7)
+    images = torch.rand(23, 20, 31, 3, generator=gen)
+    cam_ids = torch.tensor([0] * 8 + [1] * 9 + [2] * 5 + [3])
+    assert torch.equal(compute_isg(images.cuda(), cam_ids, 5e-2).cpu(), compute_isg(images, cam_ids, 5e-2))
