@@ -1,4 +1,4 @@
-// Dense layers of the decoders on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate via a 4-term TF32 split.
+// Dense layers of the decoders on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate via a TF32 split.
 //
 //   forward        Y[M,N]   = act( X[M,K] W[N,K]^T )
 //   backward data  dX[M,K]  = ( dY[M,N] W[N,K] ) * (aux > 0)
@@ -6,11 +6,13 @@
 //
 // all fp32 row-major, bias-free (tcnn FullyFusedMLP semantics, NS/fields/kplanes_field.py:249-273).  The decoders'
 // parity bar is 1e-4 relative in fp32, which a single TF32 pass (10-bit mantissa) cannot meet, so each operand is
-// split x = hi + lo (hi = cvt.rna.tf32(x), lo = x - hi exactly) and all four partial products
-// lo*lo + lo*hi + hi*lo + hi*hi are accumulated in the fp32 TMEM accumulator; the only loss is the tensor core's
-// truncation of lo to 11 bits (~2^-23 relative), i.e. fp32-class accuracy -- which matters because a ReLU whose
-// pre-activation is rounded across zero flips a sample's whole gradient.  The MLPs are tiny in FLOPs, so the 4x MMA
-// count is irrelevant; what matters is that no FFMA / LDS issue slots are spent on them.
+// split x = hi + lo (activations: hi = x with the 13 low mantissa bits cleared -- what kind::tf32 reads of an fp32 word
+// anyway -- and lo = x - hi exactly; weights: hi = cvt.rna.tf32(x)) and the partial products are accumulated in the fp32
+// TMEM accumulator: all four (lo*lo + lo*hi + hi*lo + hi*hi) in the forward, where a pre-activation rounded across zero
+// would flip a ReLU and with it a sample's whole gradient; three (lo*lo dropped, 2^-22 relative) in the backward products,
+// which feed no branch.  The only other loss is the tensor core's truncation of lo (<= 2^-21 relative): fp32-class.
+// The kernels the layers run on are the warp-specialised, TMA-fed pipelines of tc_ws.cuh (tc_ws_gemm_kernel,
+// tc_ws_wgrad_kernel below); tc_rowtile_kernel is the single-stage kernel kept for layers wider than those take.
 //
 // Shared-memory operand tiles: a [ROWS x COLS] fp32 tile is stored as COLS/32 blocks of [ROWS x 32]; each block is
 // ROWS/8 atoms of 8 rows x 128 bytes with the 128-byte swizzle (16-byte chunk c of row r at chunk c ^ (r & 7)).
@@ -153,19 +155,9 @@ __global__ void __launch_bounds__(256) tc_rowtile_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Pipelined row-tile GEMM (the kernel the decoders' forward / backward-data products run on):
-//   OUT[128 rows, N] (+)= A[128, R] * B,   R = n_slices slices of KS columns, N <= 128 per CTA column slice
-// Same operands and epilogues as tc_rowtile_kernel, but software-pipelined so that the tensor core never waits for
-// the SIMT staging and vice versa:
-//   * the A tile is staged per KS-column slice into one of TWO shared-memory stages; while the MMAs of slice s run
-//     (asynchronously, completion signalled through an mbarrier per stage) all warps convert / store slice s+1 and
-//     the global loads of slice s+2 are already in flight in registers;
-//   * TWO TMEM accumulators: the epilogue of tile j (tcgen05.ld -> activation / mask -> global stores) overlaps the
-//     MMAs of tile j+1;
-//   * the weights of this CTA's column slice (all n_slices K slices) are staged once per persistent CTA;
-//   * blockIdx.y selects the column slice: output columns [col0, col0 + N) of a wider layer -- rows n0.. of W for the
-//     forward (B K-major), columns k0.. of W for the backward-data product (B MN-major view of the same row-major W).
-// Layers up to R = 192 (3 slices of 64) x 128 columns per slice fit: 2 x 64 KB of A stages + <= 96 KB of weights.
+// Arguments of the row-tile GEMM pipelines:  OUT[128 rows, N] = epilogue(A[128, R] * B), R = n_slices slices of KS columns,
+// output columns cut into grid.y slices of N_slice <= 128 (rows n0.. of W for the forward, columns k0.. of W for the
+// backward-data product, which reads the same row-major W through an MN-major view).
 // ---------------------------------------------------------------------------------------------------------------
 struct PipeArgs {
   const float* A; int64_t lda;      // [M, R]
@@ -190,144 +182,9 @@ __device__ __forceinline__ void tmem_free_cols(uint32_t taddr, int warp, uint32_
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
 }
 
-template <int B_MN, int KS>
-__global__ void __launch_bounds__(256) tc_pipe_kernel(const __grid_constant__ PipeArgs P) {
-  extern __shared__ uint8_t smem_raw[];
-  const int R_tot = P.n_slices * KS;
-  const int b_rows = B_MN ? R_tot : P.N_pad, b_cols = B_MN ? P.N_pad : R_tot;
-  float* a_st = align1024(smem_raw);            // [2 stages][hi | lo][128 x KS]
-  float* b_hi = a_st + 4 * 128 * KS;
-  float* b_lo = b_hi + b_rows * b_cols;
-  __shared__ __align__(8) uint64_t bar[2];
-  __shared__ uint32_t tmem_slot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col0 = blockIdx.y * P.N_slice;
-  const int N = min(P.N_slice, P.N_total - col0);
-  const uint32_t tmem_cols = P.N_pad <= 32 ? 64u : (P.N_pad <= 64 ? 128u : 256u);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  tmem_alloc_cols(&tmem_slot, warp, tmem_cols);
-  // weights of this column slice, once per CTA
-  if (B_MN) stage_tile<1>(P.W + col0, P.ldw, b_rows, P.R, N, b_cols, b_hi, b_lo);
-  else stage_tile<0>(P.W + (int64_t)col0 * P.ldw, P.ldw, b_rows, N, P.R, b_cols, b_hi, b_lo);
-  const uint32_t idesc = umma_idesc_tf32(128, P.N_pad, 0, B_MN);
-  const int quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane;
-  const int64_t n_tiles = (P.M + 127) / 128;
-  const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-  const int64_t n_steps = my_tiles * P.n_slices;
-
-  auto load_step = [&](TileRegs<KS>& t, int64_t step) {
-    const int64_t tile = blockIdx.x + (step / P.n_slices) * gridDim.x;
-    const int kc = (int)(step % P.n_slices);
-    tile_load<KS>(t, P.A + tile * 128 * P.lda + kc * KS, P.lda, (int)min((int64_t)128, P.M - tile * 128), P.R - kc * KS);
-  };
-  auto epilogue = [&](int64_t j) {  // tile j of this CTA: accumulator j & 1 -> global memory
-    const int64_t tile = blockIdx.x + j * gridDim.x;
-    const int64_t row0 = tile * 128;
-    const int rows_valid = (int)min((int64_t)128, P.M - row0);
-    const uint32_t taddr = tmem_slot + (uint32_t)((j & 1) * P.N_pad) + ((uint32_t)(quad * 32) << 16);
-    for (int c0 = half * 16; c0 < P.N_pad; c0 += 32) {
-      uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < rows_valid && c0 < N) {
-        float* dst = P.OUT + (row0 + row) * P.ldo + col0 + c0;
-        const float* ax = P.aux ? P.aux + (row0 + row) * P.ldaux + col0 + c0 : nullptr;
-        float x[16];
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          x[jj] = __uint_as_float(v[jj]);
-          if (P.beta && c0 + jj < N) x[jj] += dst[jj];
-          if (!B_MN) {
-            if (P.act == ACT_RELU) x[jj] = fmaxf(x[jj], 0.f);
-            else if (P.act == ACT_SIGMOID) x[jj] = 1.f / (1.f + expf(-x[jj]));
-          }
-        }
-        const bool full = (c0 + 16 <= N) && ((P.ldo & 3) == 0) && (((reinterpret_cast<uintptr_t>(P.OUT) + (size_t)col0 * 4) & 15) == 0);
-        if (full && (ax == nullptr || ((P.ldaux & 3) == 0 && (((reinterpret_cast<uintptr_t>(P.aux) + (size_t)col0 * 4) & 15) == 0)))) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 o4 = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-            if (B_MN && ax != nullptr) {
-              const float4 m4 = __ldg(reinterpret_cast<const float4*>(ax + 4 * q));
-              if (!(m4.x > 0.f)) o4.x = 0.f;
-              if (!(m4.y > 0.f)) o4.y = 0.f;
-              if (!(m4.z > 0.f)) o4.z = 0.f;
-              if (!(m4.w > 0.f)) o4.w = 0.f;
-            }
-            *reinterpret_cast<float4*>(dst + 4 * q) = o4;
-          }
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            if (c0 + jj < N) {
-              float o1 = x[jj];
-              if (B_MN && ax != nullptr && !(ax[jj] > 0.f)) o1 = 0.f;
-              dst[jj] = o1;
-            }
-          }
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM reads ordered before the next __syncthreads
-  };
-
-  TileRegs<KS> regs;
-  if (n_steps > 0) load_step(regs, 0);
-  for (int64_t s = 0; s < n_steps; ++s) {
-    const int st = (int)(s & 1);
-    float* a_hi = a_st + st * (2 * 128 * KS);
-    float* a_lo = a_hi + 128 * KS;
-    // stage st was last read by the MMAs of step s-2, whose completion was awaited at the end of iteration s-1
-    tile_store<0, KS>(regs, a_hi, a_lo);
-    publish_smem_and_sync();  // also orders every thread's epilogue of the previous tile before the MMAs issued below
-    if (s + 1 < n_steps) load_step(regs, s + 1);  // in flight during the MMAs / epilogue below
-    const int64_t j = s / P.n_slices;
-    const int kc = (int)(s % P.n_slices);
-    if (threadIdx.x == 0) {
-      const uint32_t tmem_d = tmem_slot + (uint32_t)((j & 1) * P.N_pad);
-      const uint64_t a_d[2] = {desc_kmajor(smem_u32(a_hi), 128, 0, 0), desc_kmajor(smem_u32(a_lo), 128, 0, 0)};
-      const uint64_t b_d[2] = {B_MN ? desc_mnmajor(smem_u32(b_hi), b_rows, 0) : desc_kmajor(smem_u32(b_hi), b_rows, 0, 0),
-                               B_MN ? desc_mnmajor(smem_u32(b_lo), b_rows, 0) : desc_kmajor(smem_u32(b_lo), b_rows, 0, 0)};
-      const uint32_t b_blk = (uint32_t)(b_rows * 128) >> 4;  // K-major B: 16-byte units between 32-col blocks
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi (small terms first)
-        const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
-#pragma unroll
-        for (int k8 = 0; k8 < KS / 8; ++k8) {
-          const int kk = kc * (KS / 8) + k8;  // K step within the whole reduction
-          const uint32_t a_off = (uint32_t)(((k8 >> 2) * 128 * 128 + (k8 & 3) * 32) >> 4);
-          const uint32_t b_off = B_MN ? (uint32_t)((kk * 1024) >> 4) : (uint32_t)(kk >> 2) * b_blk + (uint32_t)(((kk & 3) * 32) >> 4);
-          umma_tf32(tmem_d, ad0 + a_off, bd0 + b_off, idesc, (kc | t | k8) != 0);
-        }
-      }
-      umma_commit(&bar[st]);
-    }
-    // the previous step: its MMAs have been running under this step's staging; wait for them (frees the other stage)
-    // and, if that step completed a tile, unload the tile while THIS step's MMAs run
-    if (s >= 1) {
-      const int64_t sp = s - 1;
-      mbar_wait(&bar[sp & 1], (uint32_t)((sp >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if ((int)(sp % P.n_slices) == P.n_slices - 1) epilogue(sp / P.n_slices);
-    }
-  }
-  if (n_steps > 0) {
-    const int64_t sp = n_steps - 1;
-    mbar_wait(&bar[sp & 1], (uint32_t)((sp >> 1) & 1));
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    epilogue(sp / P.n_slices);
-  }
-  tmem_free_cols(tmem_slot, warp, tmem_cols);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Warp-specialised row-tile GEMM (tc_ws.cuh): same operands, layouts and epilogues as tc_pipe_kernel, but the three
-// activities run on their own warps and meet only at mbarriers:
+// Warp-specialised row-tile GEMM (tc_ws.cuh): same operands, layouts and epilogues as tc_rowtile_kernel, but loading,
+// MMA issue and unloading run on their own warps and meet only at mbarriers:
 //   full[st]  : 256 producer arrivals   -> the MMA warp may read stage st
 //   empty[st] : tcgen05.commit          -> the producers may overwrite stage st
 //   accf[a]   : tcgen05.commit          -> the epilogue warps may unload accumulator a
@@ -568,90 +425,6 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Weight gradient, persistent: each CTA walks its 128-sample tiles, accumulating
-//   D[k, n] += sum_{s in tile} X[s, k] * dY[s, n]         (D = dW^T, M = 128 >= K_in, N = N_out padded to 32)
-// in ONE TMEM accumulator (both operands are MN-major views with K = samples), then adds D into dW once.
-// ---------------------------------------------------------------------------------------------------------------
-template <int K_pad, int N_pad>
-__global__ void __launch_bounds__(256) tc_wgrad_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY,
-                                                       int64_t lddy, float* __restrict__ dW, int64_t lddw, int64_t M,
-                                                       int K_in, int N_out) {
-  extern __shared__ uint8_t smem_raw[];
-  float* x_hi = align1024(smem_raw);
-  float* x_lo = x_hi + 128 * K_pad;
-  float* y_hi = x_lo + 128 * K_pad;
-  float* y_lo = y_hi + 128 * N_pad;
-  __shared__ __align__(8) uint64_t mma_bar;
-  __shared__ uint32_t tmem_slot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  tmem_alloc(&tmem_slot, warp);
-  const int64_t n_tiles = (M + 127) / 128;
-  uint32_t parity = 0, accumulate = 0;
-  uint32_t tmem_d = 0;
-  TileRegs<K_pad> px;
-  TileRegs<N_pad> py;
-  if ((int64_t)blockIdx.x < n_tiles) {
-    const int rv = (int)min((int64_t)128, M - (int64_t)blockIdx.x * 128);
-    tile_load<K_pad>(px, X + (int64_t)blockIdx.x * 128 * ldx, ldx, rv, K_in);
-    tile_load<N_pad>(py, dY + (int64_t)blockIdx.x * 128 * lddy, lddy, rv, N_out);
-  }
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    tile_store<1, K_pad>(px, x_hi, x_lo);
-    tile_store<1, N_pad>(py, y_hi, y_lo);
-    publish_smem_and_sync();
-    {
-      const int64_t nxt = tile + gridDim.x;
-      if (nxt < n_tiles) {
-        const int rv = (int)min((int64_t)128, M - nxt * 128);
-        tile_load<K_pad>(px, X + nxt * 128 * ldx, ldx, rv, K_in);
-        tile_load<N_pad>(py, dY + nxt * 128 * lddy, lddy, rv, N_out);
-      }
-    }
-    tmem_d = tmem_slot;
-    if (threadIdx.x == 0) {
-      // M = 128 rows of D; when K_pad < 128 the MN blocks beyond the X tile read whatever follows in shared memory:
-      // those D rows (k >= K_in) are never read back.
-      const uint32_t idesc = umma_idesc_tf32(128, N_pad, 1, 1);
-      const uint64_t a_d[2] = {desc_mnmajor(smem_u32(x_hi), 128, 0), desc_mnmajor(smem_u32(x_lo), 128, 0)};
-      const uint64_t b_d[2] = {desc_mnmajor(smem_u32(y_hi), 128, 0), desc_mnmajor(smem_u32(y_lo), 128, 0)};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {  // lo*lo + lo*hi + hi*lo + hi*hi
-        const uint64_t ad0 = a_d[t <= 1], bd0 = b_d[t == 0 || t == 2];
-#pragma unroll
-        for (int r8 = 0; r8 < 16; ++r8) {  // 128 samples = 16 K-steps of 8 rows (1024 bytes each)
-          umma_tf32(tmem_d, ad0 + (uint32_t)(r8 * 64), bd0 + (uint32_t)(r8 * 64), idesc, accumulate | (uint32_t)((t | r8) != 0));
-        }
-      }
-      accumulate = 1;
-      umma_commit(&mma_bar);
-    }
-    mbar_wait(&mma_bar, parity);  // operands consumed: the staging buffers may be overwritten
-    parity ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  }
-  if (blockIdx.x < n_tiles) {
-    const int quad = warp & 3, half = warp >> 2;
-    const int k = quad * 32 + lane;  // D row = input feature index
-    const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
-    for (int c0 = half * 16; c0 < N_pad; c0 += 32) {
-      uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (k < K_in) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < N_out) red_add_f32(dW + (int64_t)(c0 + j) * lddw + k, __uint_as_float(v[j]));
-      }
-    }
-  }
-  tmem_free(tmem_slot, warp);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // Warp-specialised weight gradient:  D[k, n] += sum_s X[s, k] * dY[s, n]  (D = dW^T) over this CTA's sub-tiles of ROWS
 // samples.  Both operands are activations, so both are staged per step (MN-major views, K = the ROWS samples) by the
 // producer warps into an n_stages ring; the MMA warp accumulates every step into ONE TMEM accumulator; after the last
@@ -848,52 +621,8 @@ static void dispatch_rowtile(int R_pad, const float* A, int64_t lda, const float
   else launch_rowtile<B_MN, 128>(A, lda, W, ldw, OUT, ldo, M, N, N_pad, R, act, aux, ldaux, beta, st);
 }
 
-// One tc_pipe_kernel launch: OUT[M, N_total] = epilogue(A[M, R] * B) with the output columns cut into grid.y slices.
-template <int B_MN>
-static bool launch_pipe(const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo, int64_t M, int N_total,
-                        int R, int act, const float* aux, int64_t ldaux, int beta, cudaStream_t st) {
-  if (getenv("KP_TC_PIPE") != nullptr && atoi(getenv("KP_TC_PIPE")) == 0) return false;
-  int KS = R <= 32 ? 32 : 64;
-  if (getenv("KP_TC_KS") != nullptr && atoi(getenv("KP_TC_KS")) == 32) KS = 32;  // 32 KB stages: two CTAs per SM
-  const int n_slices = (int)ceil_div(R, KS);
-  // widest column slice whose weights fit beside the two A stages (227 KB of dynamic shared memory per CTA)
-  const size_t a_bytes = (size_t)4 * 128 * KS * sizeof(float);
-  int N_slice = std::min(N_total, 128);
-  for (;; N_slice = (N_slice > 64 ? 64 : 32)) {
-    const size_t b_bytes = (size_t)2 * pad_dim(N_slice) * n_slices * KS * sizeof(float);
-    if (a_bytes + b_bytes + 1024 <= 227 * 1024) break;
-    if (N_slice <= 32) return false;
-  }
-  PipeArgs P;
-  P.A = A; P.lda = lda; P.W = W; P.ldw = ldw; P.OUT = OUT; P.ldo = ldo; P.aux = aux; P.ldaux = ldaux; P.M = M;
-  P.N_total = N_total; P.N_slice = N_slice; P.N_pad = pad_dim(std::min(N_slice, N_total)); P.R = R; P.n_slices = n_slices;
-  P.act = act; P.beta = beta;
-  const size_t smem = a_bytes + (size_t)2 * P.N_pad * n_slices * KS * sizeof(float) + 1024;
-  const unsigned gy = (unsigned)ceil_div(N_total, N_slice);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t n_tiles = ceil_div(M, 128);
-  // persistent CTAs: as many per SM as shared memory (228 KB per SM, 1 KB reserved per CTA) and TMEM (512 columns) allow,
-  // split over the column slices
-  const int tmem_cols = P.N_pad <= 32 ? 64 : (P.N_pad <= 64 ? 128 : 256);
-  int per_sm = std::max(1, std::min((int)((228 * 1024) / (smem + 1024 + 64)), 512 / tmem_cols));
-  if (getenv("KP_TC_MAX_CTAS") != nullptr) per_sm = std::max(1, std::min(per_sm, atoi(getenv("KP_TC_MAX_CTAS"))));
-  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sms * per_sm / gy));
-  if (KS == 32) {
-    auto kern = tc_pipe_kernel<B_MN, 32>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3(gx, gy), 256, smem, st>>>(P);
-  } else {
-    auto kern = tc_pipe_kernel<B_MN, 64>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3(gx, gy), 256, smem, st>>>(P);
-  }
-  kp::g_launches += 1;
-  return true;
-}
-
-// One tc_ws_gemm_kernel launch (same contract as launch_pipe).  Returns false when the shape does not fit.
+// One tc_ws_gemm_kernel launch: OUT[M, N_total] = epilogue(A[M, R] * B) with the output columns cut into grid.y slices.
+// Returns false when the shape does not fit.
 template <int B_MN, int KS, int ACT, bool MASK>
 static void launch_ws_inst(const PipeArgs& P, const CUtensorMap* tm, int n_stages, dim3 grid, size_t smem, cudaStream_t st) {
   if (tm != nullptr) {
@@ -911,7 +640,6 @@ static void launch_ws_inst(const PipeArgs& P, const CUtensorMap* tm, int n_stage
 template <int B_MN>
 static bool launch_ws(const float* A, int64_t lda, const float* W, int64_t ldw, float* OUT, int64_t ldo, int64_t M, int N_total,
                       int R, int act, const float* aux, int64_t ldaux, cudaStream_t st) {
-  if (getenv("KP_TC_WS") != nullptr && atoi(getenv("KP_TC_WS")) == 0) return false;
   const size_t epi_bytes = (size_t)kWsEpiWarps * 32 * 36 * sizeof(float);  // the epilogue warps' transpose buffers
   const size_t budget = 227 * 1024 - 2048 - epi_bytes;  // - 1 KB alignment slack - static shared memory (barriers)
   int KS = 0, n_slices = 0, N_slice = 0, N_pad = 0, n_stages = 0;
@@ -970,7 +698,6 @@ static bool launch_ws(const float* A, int64_t lda, const float* W, int64_t ldw, 
 template <int K_PAD, int N_PAD>
 static bool launch_ws_wgrad(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dW, int64_t lddw, int64_t M, int K,
                             int N, cudaStream_t st) {
-  if (getenv("KP_TC_WS") != nullptr && atoi(getenv("KP_TC_WS")) == 0) return false;
   constexpr int ROWS = 64;
   const size_t stage = (size_t)2 * ROWS * (K_PAD + N_PAD) * sizeof(float);
   const size_t slack = (size_t)ROWS * 128 * sizeof(float);  // the A operand always spans 4 MN blocks (M = 128)
@@ -1001,14 +728,8 @@ static bool launch_ws_wgrad(const float* X, int64_t ldx, const float* dY, int64_
 template <int K_PAD, int N_PAD>
 static void launch_wgrad(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dW, int64_t lddw, int64_t M, int K,
                          int N, cudaStream_t st) {
-  if (launch_ws_wgrad<K_PAD, N_PAD>(X, ldx, dY, lddy, dW, lddw, M, K, N, st)) return;
-  // the A operand always spans 4 MN blocks (M = 128): keep 4 blocks of slack after x_lo inside the allocation
-  size_t smem = (size_t)(2 * 128 * K_PAD + 2 * 128 * N_PAD) * sizeof(float);
-  const size_t need = (size_t)(128 * K_PAD + 128 * 128) * sizeof(float);
-  if (smem < need) smem = need;
-  smem += 1024;
-  auto kern = tc_wgrad_kernel<K_PAD, N_PAD>;
-  kern<<<persistent_grid(kern, ceil_div(M, 128), smem), 256, smem, st>>>(X, ldx, dY, lddy, dW, lddw, M, K, N);
+  if (!launch_ws_wgrad<K_PAD, N_PAD>(X, ldx, dY, lddy, dW, lddw, M, K, N, st))
+    set_error("tc_linear_bwd_weight: operand tiles [%d + %d columns] do not fit the pipeline", K_PAD, N_PAD);
 }
 template <int K_PAD>
 static void dispatch_wgrad(int N_pad, const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dW, int64_t lddw,
@@ -1039,9 +760,7 @@ extern "C" int kp_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int
   KP_CHECK(act >= 0 && act <= 2, "tc_linear_fwd: act=%d", act);
   cudaStream_t st = as_stream(stream);
   if (K <= 192 && launch_ws<0>(X, ldx, W, ldw, Y, ldy, M, N, K, act, nullptr, 0, st)) {
-    // warp-specialised pipeline
-  } else if (K <= 192 && launch_pipe<0>(X, ldx, W, ldw, Y, ldy, M, N, K, act, nullptr, 0, 0, st)) {
-    // pipelined kernel: K sliced inside the kernel, output columns over grid.y
+    // warp-specialised pipeline: K sliced inside the kernel, output columns over grid.y
   } else if (tc_single(N, K)) {
     dispatch_rowtile<0>(pad_dim(K), X, ldx, W, ldw, Y, ldy, M, N, pad_dim(N), K, act, nullptr, 0, 0, st);
   } else {
@@ -1069,9 +788,7 @@ extern "C" int kp_tc_linear_bwd_data(const float* dY, int64_t lddy, const float*
   KP_CHECK(dY && W && dX && kp_tc_supported(N, K), "tc_linear_bwd_data: unsupported shape N=%d K=%d", N, K);
   cudaStream_t st = as_stream(stream);
   if (N <= 192 && launch_ws<1>(dY, lddy, W, ldw, dX, lddx, M, K, N, 0, aux, ldaux, st)) {
-    // warp-specialised pipeline
-  } else if (N <= 192 && launch_pipe<1>(dY, lddy, W, ldw, dX, lddx, M, K, N, 0, aux, ldaux, 0, st)) {
-    // pipelined kernel: reduction over N_out sliced inside the kernel, output (K_in) columns over grid.y
+    // warp-specialised pipeline: reduction over N_out sliced inside the kernel, output (K_in) columns over grid.y
   } else if (tc_single(N, K)) {
     // reduction over N_out (R), output width K_in
     dispatch_rowtile<1>(pad_dim(N), dY, lddy, W, ldw, dX, lddx, M, K, pad_dim(K), N, 0, aux, ldaux, 0, st);

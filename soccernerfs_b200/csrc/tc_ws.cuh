@@ -1,7 +1,8 @@
 // Warp-specialised tcgen05 pipelines for the decoder layers (sm_100a): producer warps / one MMA-issuing warp / epilogue
 // warps, coupled through mbarriers only -- no block-wide barrier inside the main loop.
 //
-// Why (ncu, profiles/ncu_r2_tc_cfg3_before.csv): the lock-step kernels (tc_pipe_kernel / tc_wgrad_kernel in tc_linear.cu) ran
+// Why (ncu, profiles/ncu_r2_decoder_cfg3_before.txt): the lock-step kernels these replace (tc_pipe_kernel / tc_wgrad_kernel,
+// removed; tc_rowtile_kernel in tc_linear.cu is what is left of that design, for layers wider than the pipelines take) ran
 // every phase -- global loads, hi/lo split + swizzled stores, MMA issue, TMEM unload -- on the same 8 warps one after the
 // other: 12.5 % active warps, 77 M warp instructions for the 192->128 layer (16.7 % of them an emulated cvt.rna.tf32),
 // tensor pipe 5-15 % busy.  Here
