@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
     int st = 0;
     uint32_t use = 0;
     for (int s = 0; s < n_steps; ++s) {
-      mbar_wait_sleep(&tfull[st], use & 1);  // the TMA boxes of this step have landed (async-proxy writes visible)
+      mbar_wait_spin(&tfull[st], use & 1);  // the TMA boxes of this step have landed (async-proxy writes visible)
       float* a_hi = a_st + st * (2 * 128 * KS);
       ws_derive_lo<128 * KS / 4>(a_hi, a_hi + 128 * KS, pt);
       fence_async_smem();
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
       for (int jl = 0; jl < my_tiles; ++jl) {
         const int64_t tile = blockIdx.x + (int64_t)jl * gridDim.x;
         for (int kc = 0; kc < ns; ++kc) {
-          if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);  // the MMAs that read this stage have completed
+          if (use > 0) mbar_wait_spin(&empty[st], (use - 1) & 1);  // the MMAs that read this stage have completed
           float* a_hi = a_st + st * (2 * 128 * KS);
           mbar_expect_tx(&tfull[st], 128 * KS * 4);
 #pragma unroll
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         if (s + d < n_steps) {
-          if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
+          if (use > 0) mbar_wait_spin(&empty[st], (use - 1) & 1);
           float* a_hi = a_st + st * (2 * 128 * KS);
           ws_store<128, KS>(ring[d], a_hi, a_hi + 128 * KS, off0);
           fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
@@ -312,11 +312,11 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
       for (int jl = 0; jl < my_tiles; ++jl) {
         const int acc = jl & 1;
         const uint32_t ua = (uint32_t)jl >> 1;
-        if (ua > 0) mbar_wait_sleep(&acce[acc], (ua - 1) & 1);  // the epilogue has unloaded this accumulator's previous tile
+        if (ua > 0) mbar_wait_spin(&acce[acc], (ua - 1) & 1);  // the epilogue has unloaded this accumulator's previous tile
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * P.N_pad);
         for (int kc = 0; kc < ns; ++kc) {
-          mbar_wait_sleep(&full[st], use & 1);
+          mbar_wait_spin(&full[st], use & 1);
           tc_fence_after();
           const uint32_t a_base = smem_u32(a_st + st * (2 * 128 * KS));
           const uint64_t a_d[2] = {desc_kmajor(a_base, 128, 0, 0), desc_kmajor(a_base + 128 * KS * 4, 128, 0, 0)};
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
     int st = 0;
     uint32_t use = 0;
     for (int s = 0; s < my_steps; ++s) {
-      mbar_wait_sleep(&tfull[st], use & 1);
+      mbar_wait_spin(&tfull[st], use & 1);
       float* b = st_base + (size_t)st * STAGE;
       ws_derive_lo<ROWS * K_PAD / 4>(b, b + ROWS * K_PAD, pt);
       ws_derive_lo<ROWS * N_PAD / 4>(b + 2 * ROWS * K_PAD, b + 2 * ROWS * K_PAD + ROWS * N_PAD, pt);
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
       uint32_t use = 0;
       for (int s = 0; s < my_steps; ++s) {
         const int64_t sub = blockIdx.x + (int64_t)s * gridDim.x;
-        if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
+        if (use > 0) mbar_wait_spin(&empty[st], (use - 1) & 1);
         float* b = st_base + (size_t)st * STAGE;
         mbar_expect_tx(&tfull[st], ROWS * (K_PAD + N_PAD) * 4);
 #pragma unroll
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         if (s + d < my_steps) {
-          if (use > 0) mbar_wait_sleep(&empty[st], (use - 1) & 1);
+          if (use > 0) mbar_wait_spin(&empty[st], (use - 1) & 1);
           float* b = st_base + (size_t)st * STAGE;
           ws_store<ROWS, K_PAD>(rx[d], b, b + ROWS * K_PAD, offx);
           ws_store<ROWS, N_PAD>(ry[d], b + 2 * ROWS * K_PAD, b + 2 * ROWS * K_PAD + ROWS * N_PAD, offy);
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(TMA ? kTmaThreads : kWsThreads, 1)
       int st = 0;
       uint32_t use = 0;
       for (int s = 0; s < my_steps; ++s) {
-        mbar_wait_sleep(&full[st], use & 1);
+        mbar_wait_spin(&full[st], use & 1);
         tc_fence_after();
         const uint32_t b = smem_u32(st_base + (size_t)st * STAGE);
         const uint64_t a_d[2] = {desc_mnmajor(b, ROWS, 0), desc_mnmajor(b + ROWS * K_PAD * 4, ROWS, 0)};
