@@ -251,6 +251,7 @@ def density_field(planes: Sequence[torch.Tensor], w1: torch.Tensor, w2: torch.Te
 class _SigmaNet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, w1, w2):
+        ctx.set_materialize_grads(False)
         ctx.wsinks = (grad_sink(w1), grad_sink(w2))
         x, w1c, w2c = f32c(feats.detach()), f32c(w1.detach()), f32c(w2.detach())
         m, k = x.shape
@@ -346,6 +347,7 @@ class _DecoderFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feats, directions, samples_per_ray: int, w1, w2, w3, w4, w5):
+        ctx.set_materialize_grads(False)  # an unused output (o in training) arrives as None, not as a [M,16] zero fill + add
         ctx.wsinks = tuple(grad_sink(w) for w in (w1, w2, w3, w4, w5))
         x = f32c(feats.detach())
         ws = [f32c(w.detach()) for w in (w1, w2, w3, w4, w5)]
@@ -823,6 +825,7 @@ class _LossHead(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, coefs, extra, pred, image, dist, *il):
+        ctx.set_materialize_grads(False)
         pred_c, image_c = f32c(pred.detach()), f32c(image.detach())
         n = pred_c.shape[0]
         dist_c = None if dist is None else f32c(dist.detach()).view(-1)
