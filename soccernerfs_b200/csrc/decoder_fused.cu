@@ -289,6 +289,136 @@ __global__ void __launch_bounds__(256, 1) decoder_fwd_fused_kernel(const __grid_
   tmem_free(tmem_slot, warp);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Colour net alone (layers 3-5 of the chain above) for decoders whose sigma net does not fit the fully fused kernel (the
+// 32x preset: 192 -> 128 -> 16): input = the sigma net's output o [M, ldo] (15 geometry features), optional view
+// directions; h2 / h3 / cin are written only when given (training).  Same layer chain, same epilogues, one launch instead
+// of color_input + three GEMM launches that each stream [M,64] activations through HBM.
+// ---------------------------------------------------------------------------------------------------------------
+struct ColorArgs {
+  const float* o;     // [M, ldo]
+  const float* dirs;  // [N, 3] or nullptr
+  const float *w3, *w4, *w5;
+  float *cin, *h2, *h3, *rgb;
+  int64_t M;
+  int ldo, S;
+};
+
+__global__ void __launch_bounds__(256, 1) color_fwd_fused_kernel(const __grid_constant__ ColorArgs A) {
+  extern __shared__ uint8_t smem_raw[];
+  float* w3_hi = align1024(smem_raw);  // [64 x 32]
+  float* w3_lo = w3_hi + 64 * 32;
+  float* w4_hi = w3_lo + 64 * 32;      // [64 x 64]
+  float* w4_lo = w4_hi + 64 * 64;
+  float* w5_hi = w4_lo + 64 * 64;      // [16 x 64] (3 valid rows)
+  float* w5_lo = w5_hi + 16 * 64;
+  float* act_hi = w5_lo + 16 * 64;     // [128 x 64]
+  float* act_lo = act_hi + 128 * 64;
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool view_dep = A.dirs != nullptr;
+  const int kin = view_dep ? 31 : 15;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tmem_alloc(&tmem_slot, warp);
+  stage_weight<64, 32>(A.w3, kin, 64, kin, w3_hi, w3_lo);
+  stage_weight<64, 64>(A.w4, 64, 64, 64, w4_hi, w4_lo);
+  stage_weight<16, 64>(A.w5, 64, 3, 64, w5_hi, w5_lo);
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const int64_t n_tiles = (A.M + 127) / 128;
+  const int cin_w = view_dep ? 32 : 16;
+  uint32_t parity = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * 128;
+    const int rows_valid = (int)min((int64_t)128, A.M - row0);
+    const bool valid = row < rows_valid;
+    const int64_t grow = row0 + row;
+    const uint32_t tbase = tmem_slot + ((uint32_t)(quad * 32) << 16);
+    float x[32];
+    uint32_t v[16];
+    // colour input = [SH(16) | geo(15) | 0] (view dependent) or [geo(15) | 0 | zeros(16)]: warps 0-3 bring the geometry
+    // features, warps 4-7 the SH basis (or the zero half)
+    if (half == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = (valid && j < 15) ? __ldg(A.o + grow * A.ldo + j) : 0.f;
+      store_act16(x, row, view_dep ? 16 : 0, act_hi, act_lo);
+      if (A.cin != nullptr && valid) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(A.cin + grow * cin_w + (view_dep ? 16 : 0) + 4 * q) =
+              make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+      }
+    } else {
+      if (view_dep) {
+        const int64_t ray = valid ? grow / A.S : 0;
+        sh16(A.dirs[ray * 3 + 0], A.dirs[ray * 3 + 1], A.dirs[ray * 3 + 2], x);
+        store_act16(x, row, 0, act_hi, act_lo);
+        if (A.cin != nullptr && valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(A.cin + grow * 32 + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = 0.f;
+        store_act16(x, row, 16, act_hi, act_lo);
+      }
+    }
+    publish_smem_and_sync();
+    if (threadIdx.x == 0) {  // h2 = relu(cin W3^T)
+      issue_layer<4>(tmem_slot, act_hi, act_lo, w3_hi, w3_lo, 64, 64, false);
+      umma_commit(&mma_bar);
+    }
+    mbar_wait(&mma_bar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {  // epilogue of h2 then of h3
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        tmem_ld16(tbase + (uint32_t)(half * 32 + part * 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[part * 16 + j] = fmaxf(__uint_as_float(v[j]), 0.f);
+      }
+      store_act16(x, row, half * 32, act_hi, act_lo);
+      store_act16(x + 16, row, half * 32 + 16, act_hi, act_lo);
+      float* hbuf = layer == 0 ? A.h2 : A.h3;
+      if (hbuf != nullptr && valid) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(hbuf + grow * 64 + half * 32 + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+      }
+      publish_smem_and_sync();
+      if (threadIdx.x == 0) {
+        if (layer == 0) issue_layer<8>(tmem_slot, act_hi, act_lo, w4_hi, w4_lo, 64, 64, false);  // h3 = relu(h2 W4^T)
+        else issue_layer<8>(tmem_slot, act_hi, act_lo, w5_hi, w5_lo, 16, 16, false);             // rgb = sigmoid(h3 W5^T)
+        umma_commit(&mma_bar);
+      }
+      mbar_wait(&mma_bar, parity);
+      parity ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (half == 0) {
+      tmem_ld16(tbase, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A.rgb[grow * 3 + c] = 1.f / (1.f + expf(-__uint_as_float(v[c])));
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  tmem_free(tmem_slot, warp);
+}
+
 }  // namespace kp
 
 using namespace kp;
@@ -324,5 +454,22 @@ extern "C" int kp_decoder_fwd_fused(const float* feats, int K0, const float* dir
     decoder_fwd_fused_kernel<128><<<grid, 256, smem, st>>>(a);
   }
   KP_LAUNCH_CHECK("decoder_fwd_fused");
+  return 0;
+}
+
+// Internal (called by kp_color_net_fwd in mlp.cu when the hidden width is 64): the colour net forward in one launch.
+int kp_color_fwd_fused_launch(const float* directions, int S, const float* o, int ldo, const float* w3, const float* w4,
+                              const float* w5, int64_t M, float* cin, float* h2, float* h3, float* rgb, cudaStream_t st) {
+  ColorArgs a;
+  a.o = o; a.dirs = directions; a.w3 = w3; a.w4 = w4; a.w5 = w5; a.cin = cin; a.h2 = h2; a.h3 = h3; a.rgb = rgb;
+  a.M = M; a.ldo = ldo; a.S = S;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, 128), sms);
+  const size_t smem = (size_t)(2 * 64 * 32 + 2 * 64 * 64 + 2 * 16 * 64 + 2 * 128 * 64) * 4 + 1024;
+  cudaFuncSetAttribute(color_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  color_fwd_fused_kernel<<<grid, 256, smem, st>>>(a);
+  kp::g_launches += 1;
   return 0;
 }

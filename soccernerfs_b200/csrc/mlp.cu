@@ -12,6 +12,9 @@
 
 #include "common.cuh"
 
+int kp_color_fwd_fused_launch(const float* directions, int S, const float* o, int ldo, const float* w3, const float* w4,
+                              const float* w5, int64_t M, float* cin, float* h2, float* h3, float* rgb, cudaStream_t st);
+
 namespace kp {
 
 enum { EPI_NONE = 0, EPI_RELU = 1, EPI_SIGMOID = 2, EPI_RELU_MASK = 3, EPI_ATOMIC = 4 };
@@ -372,6 +375,12 @@ extern "C" int kp_color_net_fwd(const float* directions, int S, const float* o, 
   KP_CHECK(o && w3 && w4 && w5 && cin && h2 && h3 && rgb && H2 >= 1 && ldgeo >= 15, "color_net_fwd: bad arguments");
   KP_CHECK(directions == nullptr || (S >= 1 && M % S == 0), "color_net_fwd: M must be a multiple of S");
   cudaStream_t st = as_stream(stream);
+  if (H2 == 64 && !(getenv("KP_COLOR_FUSED") != nullptr && atoi(getenv("KP_COLOR_FUSED")) == 0)) {
+    // the whole colour net in one tcgen05 launch (decoder_fused.cu): weights resident, activations chained on chip
+    kp_color_fwd_fused_launch(directions, S, o, ldgeo, w3, w4, w5, M, cin, h2, h3, rgb, st);
+    KP_LAUNCH_CHECK("color_net_fwd");
+    return 0;
+  }
   const int ldc = directions ? 32 : 16, kin = directions ? 31 : 15;
   color_input_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(directions, S, o, ldgeo, M, cin);
   gemm_fwd<EPI_RELU>(cin, ldc, w3, kin, h2, H2, M, H2, kin, st);
