@@ -314,6 +314,21 @@ class PeerArena:
             self._own = 0
 
 
+def plane_write_ranges(plane_offsets, plane_sizes, lo: int, hi: int) -> List[Tuple[int, int]]:
+    """Sparse gradient exchange: for planes occupying floats [off, off + size) of a flat bucket (``off`` None = the plane
+    lives in another, densely exchanged bucket) the float4 range of each plane that lies inside this rank's shard
+    [lo, hi) of the bucket -- what ``kp_plane_reg_fused_range`` may write.  Planes outside the shard get (0, 0), planes of
+    other buckets their full range."""
+    out = []
+    for off, size in zip(plane_offsets, plane_sizes):
+        if off is None:
+            out.append((0, size // 4))
+            continue
+        a, b = max(lo, off) - off, min(hi, off + size) - off
+        out.append((a // 4, b // 4) if b > a else (0, 0))
+    return out
+
+
 def shard_slice(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [begin, end) slice of ``n_items`` owned by ``rank`` (remainder spread over the first ranks)."""
     base, rem = divmod(n_items, world)

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from ..cameras.rays import RayBundle
-from ..distributed import GradBucket, PeerArena, PeerMemoryUnavailable, ShardedAdamGroup, world_info
+from ..distributed import GradBucket, PeerArena, PeerMemoryUnavailable, ShardedAdamGroup, plane_write_ranges, world_info
 from ..models.kplanes import KPlanesModel, TrainingCallbackLocation, scale_dict
 from .optimizers import Optimizers, cosine_decay_factor
 
@@ -186,16 +186,9 @@ class TrainStep:
         planes, _, _ = regularizer_plan(model.field.grids, [p.grids for p in model.proposal_networks])
         bucket, grp = self.buckets["fields"], self.sharded["fields"]
         lo, hi = grp.shard_slice()
-        rng, scale = [], []
-        for p in planes:
-            off = bucket.param_offsets.get(id(p))
-            if off is None:
-                rng.append((0, p.numel() // 4))
-                scale.append(1.0)
-            else:
-                a, b = max(lo, off) - off, min(hi, off + p.numel()) - off
-                rng.append((a // 4, b // 4) if b > a else (0, 0))
-                scale.append(float(self.world))
+        offsets = [bucket.param_offsets.get(id(p)) for p in planes]
+        rng = plane_write_ranges(offsets, [p.numel() for p in planes], lo, hi)
+        scale = [1.0 if off is None else float(self.world) for off in offsets]
         self._reg_range = torch.tensor(rng, dtype=torch.int64, device=dev)
         self._reg_scale = torch.tensor(scale, dtype=torch.float32, device=dev)
 

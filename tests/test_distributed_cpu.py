@@ -83,3 +83,28 @@ def test_grad_bucket_span_allreduce_gloo():
         out = mgr.dict()
         mp.spawn(_span_worker, args=(world, 30100 + os.getpid() % 500, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_plane_write_ranges_partition_the_bucket():
+    """Sparse exchange host logic: over all ranks the per-plane write ranges tile every plane of the sharded bucket exactly
+    once (float4 granularity, shard boundaries inside planes), and planes of other buckets are always written in full."""
+    from soccernerfs_b200.distributed import plane_write_ranges
+
+    sizes = [64 * 64 * 32, 50 * 64 * 32, 128 * 128 * 32, 1024, 256 * 8 * 150]
+    offsets, off = [], 0
+    for i, n in enumerate(sizes):
+        offsets.append(None if i == 4 else off)  # the last plane lives in another bucket
+        off += 0 if i == 4 else n
+    total = off + 8192  # MLP weights after the planes
+    count = (total + 63) // 64 * 64
+    for world in (2, 3, 8):
+        n4 = count // 4
+        covered = [torch.zeros(n // 4, dtype=torch.int32) for n in sizes]
+        for rank in range(world):
+            lo, hi = n4 * rank // world * 4, n4 * (rank + 1) // world * 4
+            for k, (a, b) in enumerate(plane_write_ranges(offsets, sizes, lo, hi)):
+                assert 0 <= a <= b <= sizes[k] // 4
+                covered[k][a:b] += 1
+        for k in range(4):
+            assert bool((covered[k] == 1).all()), (world, k)
+        assert bool((covered[4] == world).all())
