@@ -439,7 +439,8 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
                         allreduce_backend=args.allreduce_backend,
                         shard_optimizer={"auto": None, "on": True, "off": False}[args.shard_optimizer],
                         fuse_reg_adam={"auto": None, "on": True, "off": False}[args.reg_adam],
-                        sparse_grad_exchange={"auto": None, "on": True, "off": False}[args.sparse_exchange])
+                        sparse_grad_exchange={"auto": None, "on": True, "off": False}[args.sparse_exchange],
+                        branch_small_kernels=not args.no_branches, prioritize_main_stream=not args.no_stream_priority)
     n_steps = args.warmup + args.steps
     host = _make_batches(n_steps, RAYS_PER_RANK, seed=1000 + rank)
     resident = [h.to(dev) for h in host]
@@ -696,6 +697,109 @@ def eval_leg(model, frames, warmup, rank, world, dev):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# cfg4 leg: BASELINE configs[3] -- the samplers / compositing / loss kernels NeRFPlayer-nerfacto shares with K-Planes
+# ----------------------------------------------------------------------------------------------------------------------
+def cfg4_leg(rank, world, dev, steps, warmup, rays=RAYS_PER_RANK):
+    """The part of the reference's ``nerfplayer-nerfacto`` training step that runs on THIS repo's kernels: piecewise
+    lin-disp initial sampler with one jitter per ray, two PDF resampling rounds (256 -> 96 -> 48 samples,
+    NS/models/nerfacto.py:88-90,125), get_weights, RGB / accumulation / expected-depth renderers, interlevel and
+    distortion losses -- forward and backward -- on the unbounded stadium shape (near 0.05, far 1000,
+    NS/models/nerfplayer_nerfacto.py:67-70).  The NeRFPlayer hash-grid fields themselves are outside SURVEY.md 8 and are
+    stood in for by an analytic density / colour (a few elementwise torch ops, counted in the step); rays are sharded
+    over the ranks with no collective.  Replayed from a CUDA graph like the training legs."""
+    import torch.distributed as dist
+
+    from soccernerfs_b200 import _lib
+    from soccernerfs_b200.cameras.rays import RayBundle
+    from soccernerfs_b200.model_components.losses import distortion_loss, interlevel_loss
+    from soccernerfs_b200.model_components.ray_samplers import ProposalNetworkSampler
+    from soccernerfs_b200.model_components.renderers import AccumulationRenderer, DepthRenderer, RGBRenderer
+    from soccernerfs_b200.model_components.scene_colliders import NearFarCollider
+
+    gen = torch.Generator().manual_seed(4000 + rank)
+    # cameras on a ring of radius 60 m around a 105 x 68 m pitch, looking at players near the ground
+    ang = torch.rand(rays, generator=gen) * 6.2831853
+    origins = torch.stack([60 * torch.cos(ang), 45 * torch.sin(ang), 12 + 6 * torch.rand(rays, generator=gen)], -1)
+    target = torch.stack([(torch.rand(rays, generator=gen) - 0.5) * 105, (torch.rand(rays, generator=gen) - 0.5) * 68,
+                          torch.rand(rays, generator=gen) * 2.0], -1)
+    directions = torch.nn.functional.normalize(target - origins, dim=-1)
+    static = {"origins": origins.to(dev), "directions": directions.to(dev), "times": torch.rand(rays, 1, generator=gen).to(dev),
+              "image": torch.rand(rays, 3, generator=gen).to(dev)}
+    theta = [torch.full((1,), v, device=dev, requires_grad=True) for v in (0.6, 0.8, 1.0, 1.0)]  # stand-in field parameters
+    freq = [torch.tensor(f, device=dev) for f in ([0.11, 0.07, 0.9], [0.13, 0.09, 1.1], [0.17, 0.05, 1.3])]
+
+    def density_fn(level):
+        def fn(positions):
+            return theta[level] * torch.exp(-(positions * freq[level]).sin().square().sum(-1, keepdim=True)) * 0.05
+        return fn
+
+    sampler = ProposalNetworkSampler(num_proposal_samples_per_ray=(256, 96), num_nerf_samples_per_ray=48,
+                                     num_proposal_network_iterations=2, single_jitter=True, update_sched=lambda step: 0).to(dev)
+    sampler.train()
+    collider = NearFarCollider(near_plane=0.05, far_plane=1000.0)
+    collider.train()
+    rgb_r, acc_r, depth_r = RGBRenderer("random"), AccumulationRenderer(), DepthRenderer("expected")
+    out = {}
+
+    def body():
+        for t in theta:
+            t.grad = None
+        rb = RayBundle(origins=static["origins"], directions=static["directions"], pixel_area=torch.ones(rays, 1, device=dev),
+                       times=static["times"])
+        rb = collider.set_nears_and_fars(rb)
+        rs, w_list, rs_list = sampler(rb, density_fns=[density_fn(0), density_fn(1)])
+        pos = rs.frustums.get_positions()
+        w = rs.get_weights(density_fn(2)(pos))
+        w_list, rs_list = w_list + [w], rs_list + [rs]
+        rgb = rgb_r(rgb=torch.sigmoid(theta[3] * (pos * 0.21).sin()), weights=w)
+        out["accumulation"], out["depth"] = acc_r(weights=w), depth_r(weights=w, ray_samples=rs)
+        loss = torch.nn.functional.mse_loss(rgb, static["image"]) + interlevel_loss(w_list, rs_list) \
+            + 1e-3 * distortion_loss(w_list, rs_list)
+        loss.backward()
+        out["loss"] = loss.detach()
+
+    # warm-up and capture on ONE non-default stream: autograd pins the leaves' AccumulateGrad nodes to the stream they were
+    # first used on, and a capture must not touch the legacy default stream
+    work = torch.cuda.Stream()
+    work.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(work):
+        for _ in range(3):
+            body()
+        torch.cuda.synchronize()
+        k0 = _lib.launch_count()
+        body()
+        launches_per_step = _lib.launch_count() - k0
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=work, capture_error_mode="thread_local"):
+        body()
+    for _ in range(max(warmup, 3)):
+        graph.replay()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    loss = float(out["loss"])
+    if not (loss == loss and all(t.grad is not None and bool(torch.isfinite(t.grad).all()) for t in theta)):
+        raise RuntimeError(f"cfg4 leg: non-finite loss / gradient (loss {loss})")
+    return {"metric": "shared sampler + compositing + loss kernels, train rays/sec (fwd+bwd)", "value": world * rays / (ms * 1e-3),
+            "unit": "rays/s", "ms_per_step": ms, "steps": steps, "scaling": "weak",
+            "workload": "nerfplayer-nerfacto sampling/compositing (BASELINE config 4): piecewise lin-disp sampler + 2 PDF rounds, single "
+                        f"jitter, 256/96/48 samples, near 0.05 / far 1000, {rays} rays/rank; analytic stand-in for the hash-grid fields",
+            "parallelism": f"ray-sharded x{world}, no collective", "kp_launches_per_step": launches_per_step,
+            "last_loss": loss, "launch": "replayed from a CUDA graph"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # baselines
 # ----------------------------------------------------------------------------------------------------------------------
 def gpu_torch_baseline(dev, steps=5, warmup=3, rays=RAYS_PER_RANK):
@@ -813,6 +917,10 @@ def run_ours(args):
                 line["eval"] = ev
             del model3
             torch.cuda.empty_cache()
+    if "cfg4" in legs:
+        c4 = cfg4_leg(rank, world, dev, steps=max(args.steps, 20), warmup=args.warmup)
+        if rank == 0:
+            line["cfg4"] = c4
     if rank != 0:
         return
     if world == 1 and "torch" in legs:
@@ -868,9 +976,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--legs", default="cfg2,cfg3,eval,torch",
+    ap.add_argument("--legs", default="cfg2,cfg3,eval,cfg4,torch",
                     help="comma list of the extra objects of the JSON line: cfg3 (32x training leg), eval (full-frame inference, "
-                         "needs cfg3), torch (reference step as torch CUDA ops, N=1).  cfg2 (the headline) always runs.")
+                         "needs cfg3), cfg4 (the sampler / compositing kernels on the nerfplayer-nerfacto shape), torch (reference step as torch CUDA ops, N=1).  cfg2 (the headline) always runs.")
     ap.add_argument("--eval-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-long-run", action="store_true")
@@ -888,6 +996,10 @@ def main():
                     help="(f1) plane regularisers folded into the optimizer's streaming pass (auto: when the planes are HBM-resident)")
     ap.add_argument("--sparse-exchange", choices=["auto", "on", "off"], default="auto",
                     help="N>1, sharded optimizer: pull only the gradient lines the scatter marked (auto: HBM-resident planes)")
+    ap.add_argument("--no-branches", action="store_true",
+                    help="diagnostic: keep the small loss / auxiliary-output kernels on the main stream (round-2 behaviour)")
+    ap.add_argument("--no-stream-priority", action="store_true",
+                    help="diagnostic: capture the step on a default-priority stream (round-2 behaviour)")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python each step instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -58,6 +58,13 @@ __device__ __forceinline__ float4 fma4(float4 a, float s, float4 c) {
   return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w));
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2: one issue slot for two IEEE fp32 operations -- the 3-register scalar FFMA issues
+// every other cycle per scheduler, so instruction-bound fp32 code doubles its FMA rate; each half rounds exactly like the
+// scalar instruction, so results are bit-identical).
+__device__ __forceinline__ float2 dup2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 lo2(float4 a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ float2 hi2(float4 a) { return make_float2(a.z, a.w); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

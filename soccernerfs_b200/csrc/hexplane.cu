@@ -413,38 +413,101 @@ __device__ __forceinline__ void density_features(const FieldRef& F, const float 
   }
 }
 
+// Packed variant: val2[p][c/2] = (feature 2c', feature 2c'+1) of plane p; every product is an FMUL2 / FFMA2 whose halves round
+// exactly like bilerp_combine's scalar operations.
+template <int C, int NP>
+__device__ __forceinline__ void density_features2(const FieldRef& F, const float pt[4], float2 val2[NP][C / 2], Axis ax[4]) {
+  axes_setup(F, 0, pt, ax);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const PlaneRef& pr = F.pl[p];
+    const Bilerp b = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
+    if ((F.use_mask >> p) & 1u) {
+      const float2 w00 = dup2(b.w00), w01 = dup2(b.w01), w10 = dup2(b.w10), w11 = dup2(b.w11);
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q) {
+        const float* base = pr.p + q * 4;
+        const float4 v00 = ldg4(base + (int64_t)b.o00 * C), v01 = ldg4(base + (int64_t)b.o01 * C);
+        const float4 v10 = ldg4(base + (int64_t)b.o10 * C), v11 = ldg4(base + (int64_t)b.o11 * C);
+        float2 lo = __fmul2_rn(lo2(v00), w00), hi = __fmul2_rn(hi2(v00), w00);
+        lo = __ffma2_rn(lo2(v01), w01, lo); hi = __ffma2_rn(hi2(v01), w01, hi);
+        lo = __ffma2_rn(lo2(v10), w10, lo); hi = __ffma2_rn(hi2(v10), w10, hi);
+        lo = __ffma2_rn(lo2(v11), w11, lo); hi = __ffma2_rn(hi2(v11), w11, hi);
+        val2[p][q * 2] = lo;
+        val2[p][q * 2 + 1] = hi;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C / 2; ++c) val2[p][c] = make_float2(1.f, 1.f);
+    }
+  }
+}
+
+// Shared-memory weights of the 8 -> hidden -> 1 network in the layout the packed MLP reads: hidden units in PAIRS,
+// s_w1p[jp][c] = (w1[2jp][c], w1[2jp+1][c]), s_w2p[jp] = (w2[2jp], w2[2jp+1]); an odd last unit is paired with zeros (its
+// partner adds fma(0, 0, raw) = raw).
+template <int C>
+__device__ __forceinline__ void stage_paired_weights(const float* __restrict__ w1, const float* __restrict__ w2, int hidden,
+                                                     float2* s_w1p, float2* s_w2p) {
+  const int hp = (hidden + 1) / 2;
+  for (int i = threadIdx.x; i < hp * C; i += blockDim.x) {
+    const int jp = i / C, c = i % C;
+    s_w1p[i] = make_float2(w1[(2 * jp) * C + c], 2 * jp + 1 < hidden ? w1[(2 * jp + 1) * C + c] : 0.f);
+  }
+  for (int i = threadIdx.x; i < hp; i += blockDim.x) s_w2p[i] = make_float2(w2[2 * i], 2 * i + 1 < hidden ? w2[2 * i + 1] : 0.f);
+}
+
+// pre-activations of hidden units (2jp, 2jp+1): the same fma chain over c as the scalar loop, two units per FFMA2
+template <int C>
+__device__ __forceinline__ float2 paired_preact(const float2* __restrict__ wrow, const float2 f2[C]) {
+  float2 pre = make_float2(0.f, 0.f);
+  const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+  for (int c = 0; c < C; c += 2) {
+    const float4 w = w4[c / 2];
+    pre = __ffma2_rn(lo2(w), f2[c], pre);
+    pre = __ffma2_rn(hi2(w), f2[c + 1], pre);
+  }
+  return pre;
+}
+
 template <int C, int NP>
 __global__ void __launch_bounds__(128) density_field_fwd_kernel(const __grid_constant__ FieldRef F,
                                                                  const __grid_constant__ KpPoints P, int64_t M,
                                                                  const float* __restrict__ w1, const float* __restrict__ w2,
                                                                  int hidden, int relu, float* __restrict__ density) {
-  extern __shared__ float smem[];
-  float* s_w1 = smem;               // [hidden][C]
-  float* s_w2 = smem + hidden * C;  // [hidden]
-  for (int i = threadIdx.x; i < hidden * C; i += blockDim.x) s_w1[i] = w1[i];
-  for (int i = threadIdx.x; i < hidden; i += blockDim.x) s_w2[i] = w2[i];
+  extern __shared__ __align__(16) float smem[];
+  const int hp = (hidden + 1) / 2;
+  float2* s_w1p = reinterpret_cast<float2*>(smem);  // [hp][C]
+  float2* s_w2p = s_w1p + hp * C;                   // [hp]
+  stage_paired_weights<C>(w1, w2, hidden, s_w1p, s_w2p);
   __syncthreads();
   for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
     float pt[4];
     load_point(P, m, pt);
-    float val[NP][C];
+    float2 val2[NP][C / 2];
     Axis ax[4];
-    density_features<C, NP>(F, pt, val, ax);
-    float f[C];
+    density_features2<C, NP>(F, pt, val2, ax);
+    float2 f2[C];  // (f[c], f[c]): the multiplicand of both units of a pair
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float a = 1.f;
+    for (int c = 0; c < C / 2; ++c) {
+      float2 a = make_float2(1.f, 1.f);
 #pragma unroll
-      for (int p = 0; p < NP; ++p) a *= val[p][c];
-      f[c] = a;
+      for (int p = 0; p < NP; ++p) a = __fmul2_rn(a, val2[p][c]);
+      f2[2 * c] = dup2(a.x);
+      f2[2 * c + 1] = dup2(a.y);
     }
     float raw = 0.f;
-    for (int j = 0; j < hidden; ++j) {
-      float pre = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) pre = fmaf(s_w1[j * C + c], f[c], pre);
-      if (relu) pre = fmaxf(pre, 0.f);
-      raw = fmaf(s_w2[j], pre, raw);
+#pragma unroll 2
+    for (int jp = 0; jp < hp; ++jp) {
+      float2 pre = paired_preact<C>(s_w1p + jp * C, f2);
+      if (relu) {
+        pre.x = fmaxf(pre.x, 0.f);
+        pre.y = fmaxf(pre.y, 0.f);
+      }
+      const float2 w2p = s_w2p[jp];
+      raw = fmaf(w2p.x, pre.x, raw);
+      raw = fmaf(w2p.y, pre.y, raw);
     }
     density[m] = expf(raw);
   }
@@ -453,6 +516,8 @@ __global__ void __launch_bounds__(128) density_field_fwd_kernel(const __grid_con
 // Backward.  Weight gradients: each warp stages its 32 samples' pre-activations / features / upstream
 // gradients in shared memory, then lane l owns hidden units {2l, 2l+1} (for hidden=64) and reduces over the
 // 32 samples into registers; registers are flushed with one atomicAdd per weight per block at the end.
+// All three fp32 products (forward recompute, d_features, d_weights) run as packed FFMA2 -- the kernel is FMA-issue
+// bound (83 M warp instructions per launch in round 1's ncu capture), every half rounds like the scalar fma it replaces.
 template <int C, int NP, int HIDDEN>
 __global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_constant__ FieldRef F,
                                                                  const __grid_constant__ KpPoints P, int64_t M,
@@ -460,29 +525,29 @@ __global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_
                                                                  int relu, const float* __restrict__ grad_density,
                                                                  float* __restrict__ grad_w1, float* __restrict__ grad_w2) {
   constexpr int WARPS = 4;
-  constexpr int JPL = HIDDEN / 32;  // hidden units per lane
-  extern __shared__ float smem[];
-  float* s_w1 = smem;                            // [HIDDEN][C]
-  float* s_w2 = s_w1 + HIDDEN * C;               // [HIDDEN]
-  float* s_pre = s_w2 + HIDDEN;                  // [WARPS][32][HIDDEN+1]
-  float* s_f = s_pre + WARPS * 32 * (HIDDEN + 1);  // [WARPS][32][C]
-  float* s_g = s_f + WARPS * 32 * C;             // [WARPS][32]
-  float* s_acc = s_g + WARPS * 32;               // [HIDDEN*C + HIDDEN] block accumulators
+  constexpr int HP = HIDDEN / 2;
+  static_assert(HIDDEN == 64, "lane l owns the unit pair (2l, 2l+1)");
+  extern __shared__ __align__(16) float smem[];
+  float* s_w1 = smem;                                      // [HIDDEN][C]   (rows: the d_features product pairs over c)
+  float2* s_w1p = reinterpret_cast<float2*>(s_w1 + HIDDEN * C);  // [HP][C]  unit pairs (forward recompute)
+  float2* s_w2p = s_w1p + HP * C;                          // [HP]
+  float* s_pre = reinterpret_cast<float*>(s_w2p + HP);     // [WARPS][32][HIDDEN+2]  (even row stride: float2 accesses)
+  float* s_f = s_pre + WARPS * 32 * (HIDDEN + 2);          // [WARPS][32][C]
+  float* s_g = s_f + WARPS * 32 * C;                       // [WARPS][32]
+  float* s_acc = s_g + WARPS * 32;                         // [HIDDEN*C + HIDDEN] block accumulators
   for (int i = threadIdx.x; i < HIDDEN * C; i += blockDim.x) s_w1[i] = w1[i];
-  for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s_w2[i] = w2[i];
+  stage_paired_weights<C>(w1, w2, HIDDEN, s_w1p, s_w2p);
   for (int i = threadIdx.x; i < HIDDEN * C + HIDDEN; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* my_pre = s_pre + warp * 32 * (HIDDEN + 1);
+  constexpr int PS = HIDDEN + 2;  // row stride of the staged pre-activations
+  float* my_pre = s_pre + warp * 32 * PS;
   float* my_f = s_f + warp * 32 * C;
   float* my_g = s_g + warp * 32;
-  float acc_w1[JPL][C], acc_w2[JPL];
+  float2 acc_w1[C];                       // (d w1[2l][c], d w1[2l+1][c])
+  float2 acc_w2 = make_float2(0.f, 0.f);  // (d w2[2l], d w2[2l+1])
 #pragma unroll
-  for (int j = 0; j < JPL; ++j) {
-    acc_w2[j] = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc_w1[j][c] = 0.f;
-  }
+  for (int c = 0; c < C; ++c) acc_w1[c] = make_float2(0.f, 0.f);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t M_pad = (M + 31) / 32 * 32;
   for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M_pad; m += stride) {
@@ -494,65 +559,80 @@ __global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_
     if (__all_sync(0xffffffffu, g_up == 0.f)) continue;
     const bool valid = (m < M) && (g_up != 0.f);
     float pt[4] = {0.f, 0.f, 0.f, 0.f};
-    float val[NP][C];
+    float2 val2[NP][C / 2];
     Axis ax[4];
-    float f[C], df[C];
+    float2 fpair[C / 2];  // (f[2c'], f[2c'+1])
+    float2 df2[C / 2];    // d loss / d f, same pairing
     float graw = 0.f;
+    float2* pre_row = reinterpret_cast<float2*>(my_pre + lane * PS);
     if (valid) {
       load_point(P, m, pt);
-      density_features<C, NP>(F, pt, val, ax);
+      density_features2<C, NP>(F, pt, val2, ax);
+      float2 f2[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float a = 1.f;
+      for (int c = 0; c < C / 2; ++c) {
+        float2 a = make_float2(1.f, 1.f);
 #pragma unroll
-        for (int p = 0; p < NP; ++p) a *= val[p][c];
-        f[c] = a;
-        df[c] = 0.f;
+        for (int p = 0; p < NP; ++p) a = __fmul2_rn(a, val2[p][c]);
+        fpair[c] = a;
+        f2[2 * c] = dup2(a.x);
+        f2[2 * c + 1] = dup2(a.y);
+        df2[c] = make_float2(0.f, 0.f);
       }
       float raw = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < HIDDEN; ++j) {
-        float pre = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) pre = fmaf(s_w1[j * C + c], f[c], pre);
-        my_pre[lane * (HIDDEN + 1) + j] = pre;
-        raw = fmaf(s_w2[j], relu ? fmaxf(pre, 0.f) : pre, raw);
+#pragma unroll 2
+      for (int jp = 0; jp < HP; ++jp) {
+        const float2 pre = paired_preact<C>(s_w1p + jp * C, f2);
+        pre_row[jp] = pre;
+        const float2 w2p = s_w2p[jp];
+        raw = fmaf(w2p.x, relu ? fmaxf(pre.x, 0.f) : pre.x, raw);
+        raw = fmaf(w2p.y, relu ? fmaxf(pre.y, 0.f) : pre.y, raw);
       }
       // trunc_exp backward (activations.py:37-39)
       graw = g_up * expf(fminf(fmaxf(raw, -15.f), 15.f));
-#pragma unroll 4
-      for (int j = 0; j < HIDDEN; ++j) {
-        const float pre = my_pre[lane * (HIDDEN + 1) + j];
-        const float dpre = (relu && !(pre > 0.f)) ? 0.f : graw * s_w2[j];
+#pragma unroll 2
+      for (int jp = 0; jp < HP; ++jp) {
+        const float2 pre = pre_row[jp];
+        const float2 w2p = s_w2p[jp];
+        const float dpre0 = (relu && !(pre.x > 0.f)) ? 0.f : graw * w2p.x;
+        const float dpre1 = (relu && !(pre.y > 0.f)) ? 0.f : graw * w2p.y;
+        const float4* r0 = reinterpret_cast<const float4*>(s_w1 + (2 * jp) * C);
+        const float4* r1 = reinterpret_cast<const float4*>(s_w1 + (2 * jp + 1) * C);
+        // df[c] = fma(dpre_j, w1[j][c], df[c]) in unit order j = 2jp, 2jp+1 (the scalar loop's order), two c per FFMA2
 #pragma unroll
-        for (int c = 0; c < C; ++c) df[c] = fmaf(dpre, s_w1[j * C + c], df[c]);
+        for (int q = 0; q < C / 4; ++q) {
+          const float4 w = r0[q];
+          df2[2 * q] = __ffma2_rn(dup2(dpre0), lo2(w), df2[2 * q]);
+          df2[2 * q + 1] = __ffma2_rn(dup2(dpre0), hi2(w), df2[2 * q + 1]);
+        }
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+          const float4 w = r1[q];
+          df2[2 * q] = __ffma2_rn(dup2(dpre1), lo2(w), df2[2 * q]);
+          df2[2 * q + 1] = __ffma2_rn(dup2(dpre1), hi2(w), df2[2 * q + 1]);
+        }
       }
     } else {
-      for (int j = 0; j < HIDDEN; ++j) my_pre[lane * (HIDDEN + 1) + j] = 0.f;
+      for (int jp = 0; jp < HP; ++jp) pre_row[jp] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < C; ++c) f[c] = 0.f;
+      for (int c = 0; c < C / 2; ++c) fpair[c] = make_float2(0.f, 0.f);
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) my_f[lane * C + c] = f[c];
+    for (int c = 0; c < C / 2; ++c) reinterpret_cast<float2*>(my_f + lane * C)[c] = fpair[c];
     my_g[lane] = graw;
     __syncwarp();
-    // weight-gradient reduction over the warp's 32 samples
+    // weight-gradient reduction over the warp's 32 samples: lane l accumulates units (2l, 2l+1)
+    const float2 w2l = s_w2p[lane];
 #pragma unroll 2
     for (int s = 0; s < 32; ++s) {
       const float gs = my_g[s];
-      float fs[C];
+      const float2 pre = reinterpret_cast<const float2*>(my_pre + s * PS)[lane];
+      const float2 h = make_float2(relu ? fmaxf(pre.x, 0.f) : pre.x, relu ? fmaxf(pre.y, 0.f) : pre.y);
+      const float2 dpre = make_float2((relu && !(pre.x > 0.f)) ? 0.f : gs * w2l.x, (relu && !(pre.y > 0.f)) ? 0.f : gs * w2l.y);
+      acc_w2 = __ffma2_rn(dup2(gs), h, acc_w2);
+      const float* fs = my_f + s * C;
 #pragma unroll
-      for (int c = 0; c < C; ++c) fs[c] = my_f[s * C + c];
-#pragma unroll
-      for (int j = 0; j < JPL; ++j) {
-        const int jj = lane + 32 * j;
-        const float pre = my_pre[s * (HIDDEN + 1) + jj];
-        const float h = relu ? fmaxf(pre, 0.f) : pre;
-        const float dpre = (relu && !(pre > 0.f)) ? 0.f : gs * s_w2[jj];
-        acc_w2[j] = fmaf(gs, h, acc_w2[j]);
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc_w1[j][c] = fmaf(dpre, fs[c], acc_w1[j][c]);
-      }
+      for (int c = 0; c < C; ++c) acc_w1[c] = __ffma2_rn(dpre, dup2(fs[c]), acc_w1[c]);
     }
     __syncwarp();
     // plane gradients
@@ -562,34 +642,38 @@ __global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_
         const PlaneRef& pr = F.pl[p];
         if (!((F.use_mask >> p) & 1u) || pr.g == nullptr) continue;
         const Bilerp bp = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
-        float gp[C];
+        float2 gp[C / 2];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          float a = df[c];
+        for (int c = 0; c < C / 2; ++c) {
+          float2 a = df2[c];
 #pragma unroll
           for (int q = 0; q < NP; ++q)
-            if (q != p) a *= val[q][c];
+            if (q != p) a = __fmul2_rn(a, val2[q][c]);
           gp[c] = a;
         }
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) {
-          const float4 g4 = make_float4(gp[q * 4], gp[q * 4 + 1], gp[q * 4 + 2], gp[q * 4 + 3]);
+          const float2 glo = gp[2 * q], ghi = gp[2 * q + 1];
           float* gb = pr.g + q * 4;
-          if (bp.w00 != 0.f) red_add_v4(gb + (int64_t)bp.o00 * C, scale4(g4, bp.w00));
-          if (bp.w01 != 0.f) red_add_v4(gb + (int64_t)bp.o01 * C, scale4(g4, bp.w01));
-          if (bp.w10 != 0.f) red_add_v4(gb + (int64_t)bp.o10 * C, scale4(g4, bp.w10));
-          if (bp.w11 != 0.f) red_add_v4(gb + (int64_t)bp.o11 * C, scale4(g4, bp.w11));
+          auto red = [&](int32_t off, float w) {
+            const float2 a = __fmul2_rn(glo, dup2(w)), b2 = __fmul2_rn(ghi, dup2(w));
+            red_add_v4(gb + (int64_t)off * C, make_float4(a.x, a.y, b2.x, b2.y));
+          };
+          if (bp.w00 != 0.f) red(bp.o00, bp.w00);
+          if (bp.w01 != 0.f) red(bp.o01, bp.w01);
+          if (bp.w10 != 0.f) red(bp.o10, bp.w10);
+          if (bp.w11 != 0.f) red(bp.o11, bp.w11);
         }
       }
     }
   }
   // flush register accumulators: warps -> block smem -> global
+  atomicAdd(&s_acc[HIDDEN * C + 2 * lane], acc_w2.x);
+  atomicAdd(&s_acc[HIDDEN * C + 2 * lane + 1], acc_w2.y);
 #pragma unroll
-  for (int j = 0; j < JPL; ++j) {
-    const int jj = lane + 32 * j;
-    atomicAdd(&s_acc[HIDDEN * C + jj], acc_w2[j]);
-#pragma unroll
-    for (int c = 0; c < C; ++c) atomicAdd(&s_acc[jj * C + c], acc_w1[j][c]);
+  for (int c = 0; c < C; ++c) {
+    atomicAdd(&s_acc[(2 * lane) * C + c], acc_w1[c].x);
+    atomicAdd(&s_acc[(2 * lane + 1) * C + c], acc_w1[c].y);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < HIDDEN * C; i += blockDim.x) red_add_f32(grad_w1 + i, s_acc[i]);
@@ -690,7 +774,7 @@ static int launch_density(bool bwd, const FieldRef& F, const KpPoints& P, int64_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (!bwd) {
-    const size_t smem = (size_t)(hidden * C + hidden) * sizeof(float);
+    const size_t smem = (size_t)((hidden + 1) / 2) * (C + 1) * sizeof(float2);  // unit pairs (stage_paired_weights)
     const int64_t blocks = std::min<int64_t>(ceil_div(M, 128), (int64_t)sms * 16);
     if (F.n_planes == 6)
       density_field_fwd_kernel<C, 6><<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, hidden, relu, density);
@@ -699,8 +783,8 @@ static int launch_density(bool bwd, const FieldRef& F, const KpPoints& P, int64_
   } else {
     KP_CHECK(hidden == 64, "density_field_bwd: hidden=%d unsupported (64)", hidden);
     constexpr int HIDDEN = 64;
-    const size_t smem =
-        (size_t)(HIDDEN * C + HIDDEN + 4 * 32 * (HIDDEN + 1) + 4 * 32 * C + 4 * 32 + HIDDEN * C + HIDDEN) * sizeof(float);
+    const size_t smem =  // w1 rows + w1 unit pairs + w2 pairs + staged pre-activations / features / gradients + accumulators
+        (size_t)(HIDDEN * C + HIDDEN * C + HIDDEN + 4 * 32 * (HIDDEN + 2) + 4 * 32 * C + 4 * 32 + HIDDEN * C + HIDDEN) * sizeof(float);
     const int64_t blocks = std::min<int64_t>(ceil_div(M, 128), (int64_t)sms * 4);
     if (F.n_planes == 6) {
       auto kern = density_field_bwd_kernel<C, 6, HIDDEN>;

@@ -7,7 +7,7 @@ reference's ``CosineDecayScheduler`` lambda (NS/engine/schedulers.py:126-142).
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable
+from typing import Callable, Dict, Iterable, Optional
 
 import numpy as np
 import torch
@@ -96,11 +96,17 @@ class Optimizers:
         for opt in self.optimizers.values():
             opt.zero_grad(set_to_none=True)
 
-    def optimizer_step_all(self, grad_scale: float = 1.0, use_device_hyper: bool = True, plane_reg: "PlaneRegAdamPlan" = None) -> None:
+    def optimizer_step_all(self, grad_scale: float = 1.0, use_device_hyper: bool = True, plane_reg: "PlaneRegAdamPlan" = None,
+                           before: Optional[Dict[str, Callable[[], None]]] = None) -> None:
+        """``before[name]()`` runs right before group ``name`` is stepped (e.g. a stream join only that group needs);
+        groups with such a hook are stepped last."""
         if plane_reg is not None:
             plane_reg.begin_step()
-        for opt in self.optimizers.values():
-            opt.step(grad_scale=grad_scale, use_device_hyper=use_device_hyper, plane_reg=plane_reg)
+        before = before or {}
+        for name in sorted(self.optimizers, key=lambda n: n in before):  # (stable: the other groups keep their order)
+            if name in before:
+                before[name]()
+            self.optimizers[name].step(grad_scale=grad_scale, use_device_hyper=use_device_hyper, plane_reg=plane_reg)
 
     def scheduler_step_all(self, step: int = 0) -> None:
         for sch in self.schedulers.values():

@@ -33,13 +33,18 @@ class TrainStep:
                  overlap_proposal_backward: Optional[bool] = None, allreduce_mode: str = "overlap",
                  allreduce_backend: str = "peer", fuse_regularizers: bool = True,
                  shard_optimizer: Optional[bool] = None, fuse_reg_adam: Optional[bool] = None,
-                 sparse_grad_exchange: Optional[bool] = None) -> None:
+                 sparse_grad_exchange: Optional[bool] = None, prioritize_main_stream: bool = True,
+                 branch_small_kernels: bool = True) -> None:
         """``overlap_branches``: run the two branches of the step that do not depend on the main field's backward on
         their own CUDA streams (same arithmetic, same results): the plane regularisers (forward AND backward depend on
         the planes only) during the forward pass, and the back-propagation through the proposal networks (depends on
         the interlevel loss only) next to the decoder/scatter backward.  Needs the gradient sinks.
         ``overlap_proposal_backward``: None = automatic -- on for a single process; off under data parallelism, where
         the proposal backward is instead kept AFTER the field scatter so that it hides the field bucket's all-reduce.
+        ``prioritize_main_stream``: capture the graphed step on a high-priority stream, so that the side branches (default
+        priority) only get what the critical path leaves free.  ``branch_small_kernels``: the outputs no loss reads
+        (accumulation, depths, median colour) and the distortion / interlevel terms run as parallel branches of the step
+        (forward and backward) instead of one after the other in front of the loss head.
         ``allreduce_mode``: "overlap" (field bucket reduced on a communication stream as soon as the scatter is enqueued),
         "overlap-per-scale" (scatter launched per scale, finest first, and the finest scale reduced under the others),
         "after-backward" (both buckets reduced on the main stream after the whole backward).
@@ -152,7 +157,7 @@ class TrainStep:
         if self.reduce_grads:
             # high priority: when the scatter finishes, the all-reduce kernel's blocks are placed BEFORE the proposal
             # backward's persistent blocks fill every SM (they would otherwise keep it out until they retire)
-            self._comm_stream = torch.cuda.Stream(priority=-1) if on_cuda else None
+            self._comm_stream = torch.cuda.Stream(priority=-2) if on_cuda else None
         # The overlap hook marks "every gradient of the field bucket is in the stream" right after the scatter kernel was
         # enqueued.  That is only true with the gradient sinks (the kernels write the bucket themselves); without them
         # autograd's AccumulateGrad adds the returned gradients AFTER the hook, so the bucket is reduced after the backward.
@@ -169,7 +174,13 @@ class TrainStep:
             overlap_proposal_backward = not self.reduce_grads
         self._prop_stream = torch.cuda.Stream() if (self.overlap and overlap_proposal_backward) else None
         model.proposal_sampler.side_stream = self._prop_stream
+        # [0]: outputs no loss reads (accumulation / depths / median colour); [1..]: distortion and interlevel terms, forward
+        # and (autograd replays a node on its forward's stream) backward, as parallel branches
+        self._branch_streams = [torch.cuda.Stream() for _ in range(4)] if (self.overlap and branch_small_kernels) else None
+        model._kp_branch_streams = self._branch_streams
         self.use_cuda_graph = use_cuda_graph
+        # the captured step's own stream: above the side branches (priority 0), below the communication stream (-2)
+        self._capture_stream = torch.cuda.Stream(priority=-1) if (on_cuda and use_cuda_graph and prioritize_main_stream) else None
         self._in_graph_body = False
         self.health_check_every = 1000  # steps between polls of the peer all-reduce's error word (a device sync)
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
@@ -261,8 +272,14 @@ class TrainStep:
         if loss is None:
             loss = sum(loss_dict.values())
         loss.backward()
+        join_prop = None
         if self._prop_stream is not None and getattr(model.proposal_sampler, "side_stream_used", False):
-            main.wait_stream(self._prop_stream)  # proposal-network backward ran on the sampler's side stream
+            # the proposal networks' backward ran on the sampler's side stream: only THEIR optimizer group waits for it,
+            # so the field group's optimizer pass (HBM-bound) can run next to its tail
+            if self.reduce_grads or "proposal_networks" not in self.optimizers.optimizers:
+                main.wait_stream(self._prop_stream)
+            else:
+                join_prop = {"proposal_networks": lambda: torch.cuda.current_stream().wait_stream(self._prop_stream)}
         grad_scale = 1.0
         if self.reduce_grads:
             main = torch.cuda.current_stream()
@@ -317,7 +334,8 @@ class TrainStep:
                 prop.all_reduce()
             main.wait_stream(comm)  # join
             grad_scale = 1.0 / self.world
-        self.optimizers.optimizer_step_all(grad_scale=grad_scale, use_device_hyper=self._in_graph_body, plane_reg=self._reg_adam)
+        self.optimizers.optimizer_step_all(grad_scale=grad_scale, use_device_hyper=self._in_graph_body, plane_reg=self._reg_adam,
+                                           before=join_prop)
         if self._reg_adam is not None:
             regs = self._reg_adam.values()
             loss_dict.update(regs)
@@ -332,8 +350,9 @@ class TrainStep:
                                 hyper_dev=g.get("hyper_dev") if self._in_graph_body else None,
                                 sparse=self._sparse and name == "fields")
 
-    @staticmethod
-    def _finish(loss_dict, loss, metrics):
+    def _finish(self, loss_dict, loss, metrics):
+        if self._branch_streams:
+            torch.cuda.current_stream().wait_stream(self._branch_streams[0])  # the auxiliary outputs of get_outputs
         loss_dict = {k: v.detach() for k, v in loss_dict.items()}
         loss_dict["loss"] = loss.detach()
         loss_dict["psnr"] = metrics["psnr"]
@@ -379,6 +398,8 @@ class TrainStep:
         if getattr(self.model.field, "_kp_post_backward", None) is not None:
             self.model.field._kp_post_backward = None
         self.model.proposal_sampler.side_stream = None
+        self.model._kp_branch_streams = None
+        self._prop_stream = None
         self._graphs.clear()
         self._graph_out.clear()
         if self.arena is not None:
@@ -582,7 +603,7 @@ class TrainStep:
         if updated not in self._graphs:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            with torch.cuda.graph(g, stream=self._capture_stream, capture_error_mode="thread_local"):
                 self._graph_out[updated] = self._graph_body()
             self._graphs[updated] = g
         self._graphs[updated].replay()

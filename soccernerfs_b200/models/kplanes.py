@@ -150,8 +150,35 @@ def scale_dict(dictionary: Dict, coefficients: Dict[str, float]) -> Dict:
     return dictionary
 
 
+class _branch:
+    """``with _branch(streams, i):`` runs the body on ``streams[i % len(streams)]`` (forked from the current stream);
+    ``join_now()`` makes the current stream wait for it; branch 0 is joined by the owner of the streams (the training step
+    does, before it returns).  ``streams`` None / empty: a no-op."""
+
+    def __init__(self, streams, index: int) -> None:
+        self.stream = streams[index % len(streams)] if streams else None
+
+    def __enter__(self):
+        if self.stream is not None:
+            self.main = torch.cuda.current_stream()
+            self.stream.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.stream is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join_now(self) -> None:
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
 class KPlanesModel(Model):
     config: KPlanesModelConfig
+    _kp_branch_streams = None  # engine/trainer.py: CUDA streams for the independent small branches of a training step
 
     def populate_modules(self):
         super().populate_modules()
@@ -257,15 +284,18 @@ class KPlanesModel(Model):
             self.config.background_color_train if self.training else self.config.background_color_eval
         )
         rgb = self.renderer_rgb(rgb=field_out[FieldHeadNames.RGB], weights=weights)
-        accumulation = self.renderer_accumulation(weights)
-        depth = self.renderer_depth(weights, ray_samples)
-        median_rgb = self.medianrgb_renderer(rgb=field_out[FieldHeadNames.RGB], weights=weights)
-        outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth, "median_rgb": median_rgb}
-        if self.training:
-            outputs["weights_list"] = weights_list
-            outputs["ray_samples_list"] = ray_samples_list
-        for i in range(self.config.num_proposal_iterations):
-            outputs[f"prop_depth_{i}"] = self.renderer_depth(weights=weights_list[i], ray_samples=ray_samples_list[i])
+        # outputs no loss term reads (accumulation, depths, median colour): on the trainer's auxiliary stream when it
+        # gave us one, next to the loss kernels instead of in front of them
+        with _branch(self._kp_branch_streams if (self.training and rgb.is_cuda) else None, 0):
+            accumulation = self.renderer_accumulation(weights)
+            depth = self.renderer_depth(weights, ray_samples)
+            median_rgb = self.medianrgb_renderer(rgb=field_out[FieldHeadNames.RGB], weights=weights)
+            outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth, "median_rgb": median_rgb}
+            if self.training:
+                outputs["weights_list"] = weights_list
+                outputs["ray_samples_list"] = ray_samples_list
+            for i in range(self.config.num_proposal_iterations):
+                outputs[f"prop_depth_{i}"] = self.renderer_depth(weights=weights_list[i], ray_samples=ray_samples_list[i])
         if ray_bundle.metadata is not None and "directions_norm" in ray_bundle.metadata:
             outputs["directions_norm"] = ray_bundle.metadata["directions_norm"]
         return outputs
@@ -307,8 +337,21 @@ class KPlanesModel(Model):
         if (self.training and rgb.is_cuda and "weights_list" in outputs and "rgb_loss" in coef
                 and len(outputs["weights_list"]) - 1 <= 4 and image.shape == rgb.shape):
             wl, rl = outputs["weights_list"], outputs["ray_samples_list"]
-            dist = distortion_per_ray(wl, rl) if "distortion_loss" in coef else None
-            il = interlevel_terms(wl, rl) if "interlevel_loss" in coef else []
+            # the distortion term and the interlevel terms are independent warp-per-ray kernels of a few microseconds
+            # each: as parallel branches (trainer-provided streams) they and their backward kernels overlap; autograd
+            # replays every backward on its forward's stream
+            br, forks = self._kp_branch_streams, []
+            with _branch(br, 1) as b:
+                dist = distortion_per_ray(wl, rl) if "distortion_loss" in coef else None
+            forks.append(b)
+            il = []
+            if "interlevel_loss" in coef:
+                for lvl in range(len(wl) - 1):
+                    with _branch(br, 2 + lvl) as b:
+                        il += interlevel_terms([wl[lvl], wl[-1]], [rl[lvl], rl[-1]])
+                    forks.append(b)
+            for b in forks:  # (joined only after every branch was forked: a join in between would serialise them)
+                b.join_now()
             extra = outputs.get("_scaled_regularizers_vec")
             head = ops.loss_head(rgb, image, dist, il, coef["rgb_loss"], coef.get("distortion_loss", 0.0),
                                  coef.get("interlevel_loss", 0.0), extra) + (extra is not None,)
