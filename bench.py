@@ -646,7 +646,7 @@ def _roofline(name, per_kernel, step_bytes, scales, peaks, probe):
 # ----------------------------------------------------------------------------------------------------------------------
 # eval leg: BASELINE configs[4]
 # ----------------------------------------------------------------------------------------------------------------------
-def eval_leg(model, frames, warmup, rank, world, dev):
+def eval_leg(model, frames, warmup, rank, world, dev, ray_tile=4, graph=True):
     """Full-frame inference with the 32x field: 1920x1080 rays per frame in chunks of 32768, rays generated on the device
     and finished tiles copied to pinned host frames (engine/frame_renderer.py).  One "step" = one frame; with N ranks the
     tiles are shared round-robin (no collective)."""
@@ -667,7 +667,7 @@ def eval_leg(model, frames, warmup, rank, world, dev):
     up = torch.cross(right, fwd, dim=-1)
     c2w = torch.cat([torch.stack([right, up, -fwd], dim=-1), pos[..., None]], dim=-1)  # camera looks along -z
     cams = Cameras(c2w.to(dev), 1600.0, 1600.0, w / 2, h / 2, w, h, times=torch.linspace(0, 1, n_frames).to(dev))
-    renderer = FrameRenderer(model, cams, rank=rank, world=world)
+    renderer = FrameRenderer(model, cams, rank=rank, world=world, ray_tile=ray_tile, use_cuda_graph=graph)
     for i in range(warmup):
         renderer.render(i)
     if world > 1:
@@ -692,6 +692,7 @@ def eval_leg(model, frames, warmup, rank, world, dev):
             "value": rays / (ms * 1e-3), "unit": "rays/s", "frames": frames, "warmup": warmup, "ms_per_frame": ms / frames,
             "scaling": "strong", "workload": "kplanes-32x(cfg3 field) full-frame inference (BASELINE config 5): 1920x1080 rays/frame, "
                                              "chunk 32768, 256/128/64 samples, rays generated on the device",
+            "gather_ray_tile": ray_tile, "launch": "one CUDA graph replay per tile" if graph else "eager",
             "parallelism": f"tile-sharded x{world} (round-robin chunks, no collective)",
             "d2h_bytes_per_frame": h * w * (3 + 1 + 1) * 4, "checksum": checksum, "gpu_launches": launches}
 
@@ -912,7 +913,7 @@ def run_ours(args):
             cfg3.pop("clocks", None)
             line["cfg3"] = cfg3
         if model3 is not None:
-            ev = eval_leg(model3, frames=args.eval_frames, warmup=1, rank=rank, world=world, dev=dev)
+            ev = eval_leg(model3, frames=args.eval_frames, warmup=1, rank=rank, world=world, dev=dev, ray_tile=args.eval_ray_tile, graph=not args.eval_eager)
             if rank == 0:
                 line["eval"] = ev
             del model3
@@ -980,6 +981,9 @@ def main():
                     help="comma list of the extra objects of the JSON line: cfg3 (32x training leg), eval (full-frame inference, "
                          "needs cfg3), cfg4 (the sampler / compositing kernels on the nerfplayer-nerfacto shape), torch (reference step as torch CUDA ops, N=1).  cfg2 (the headline) always runs.")
     ap.add_argument("--eval-frames", type=int, default=2)
+    ap.add_argument("--eval-eager", action="store_true", help="full-frame inference: launch every tile's kernels from Python")
+    ap.add_argument("--eval-ray-tile", type=int, default=4,
+                    help="full-frame inference: neighbouring rays per warp of the gather (KpPoints.ray_tile; 0 = samples of one ray)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-long-run", action="store_true")
     ap.add_argument("--no-ref-schedule", action="store_true")

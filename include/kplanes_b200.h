@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 2
+#define KP_ABI_VERSION 3
 #define KP_MAX_SCALES 8
 #define KP_MAX_PLANES 6
 
@@ -51,6 +51,10 @@ typedef struct KpPoints {
   int32_t S;               /* samples per ray (ray form) */
   int32_t norm_mode;       /* 0: aabb -> [0,1], 1: aabb -> [-1,1], 2: SceneContraction(L_inf) / 2 (unbounded scenes) */
   float aabb[6];
+  int32_t ray_tile;        /* ray form, gather only: > 1 = the threads of a warp take the SAME sample index of ray_tile
+                              neighbouring rays instead of consecutive samples of one ray (full-frame inference: neighbouring
+                              pixels read the same texels, which then coalesce inside one request).  Results are written
+                              at the samples' own rows: only the thread -> sample assignment changes.  0/1 = off. */
 } KpPoints;
 
 /* ---- (a1-a3) multiscale hexplane field: replaces interpolate_kplanes, NS/fields/kplanes_field.py:77-126

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkplanes_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 LAUNCH_COUNT = 0  # number of C-ABI kernel-launching calls made (bench.py reports it as gpu_launches evidence)
@@ -25,6 +25,7 @@ class KpPoints(Structure):
     _fields_ = [
         ("pts", c_void_p), ("origins", c_void_p), ("directions", c_void_p), ("starts", c_void_p), ("ends", c_void_p),
         ("times", c_void_p), ("D", c_int32), ("S", c_int32), ("norm_mode", c_int32), ("aabb", c_float * 6),
+        ("ray_tile", c_int32),
     ]
 
 
@@ -183,7 +184,7 @@ def hw_array(planes: Sequence[torch.Tensor]):
 
 
 def make_points(*, pts=None, origins=None, directions=None, starts=None, ends=None, times=None, D=4, S=1,
-                norm_mode=1, aabb=None) -> KpPoints:
+                norm_mode=1, aabb=None, ray_tile=0) -> KpPoints:
     kp = KpPoints()
     kp.pts = ptr(pts).value
     kp.origins = ptr(origins).value
@@ -192,6 +193,7 @@ def make_points(*, pts=None, origins=None, directions=None, starts=None, ends=No
     kp.ends = ptr(ends).value
     kp.times = ptr(times).value
     kp.D, kp.S, kp.norm_mode = D, S, norm_mode
+    kp.ray_tile = int(ray_tile)
     vals = [0.0] * 6 if aabb is None else [float(v) for v in aabb]
     for i in range(6):
         kp.aabb[i] = vals[i]

@@ -43,6 +43,16 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// 256-bit read-only load (sm_100: LDG.E.ENL2.256): a whole 8-channel texel in one request instead of two
+struct __align__(32) float8 { float4 a, b; };
+__device__ __forceinline__ float8 ldg8(const float* p) {
+  float8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+               : "l"(p));
+  return r;
+}
+
 // Vector reduction (no return value) into global memory: one 16-byte L2 atomic instead of four.
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

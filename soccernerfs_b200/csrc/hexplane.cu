@@ -226,9 +226,20 @@ __global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_const
                                                             float* __restrict__ out) {
   constexpr int LPS = C / 4;
   const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t m = gt / LPS;
+  int64_t m = gt / LPS;
   const int c4 = (int)(gt % LPS) * 4;
   if (m >= M) return;
+  if (P.ray_tile > 1 && P.pts == nullptr) {
+    // coherent rays (neighbouring pixels of a frame): slot m -> sample s of ray (tile * T + j), j fastest, so the 32 / LPS
+    // samples of a warp are the SAME sample index of neighbouring rays.  At every scale whose texels are wider than the
+    // pixel footprint they read the same texel lines, which coalesce inside the request (one L2 line request per warp
+    // instead of one per sample).  The last tile may hold fewer rays.
+    const int64_t n_rays = M / P.S, tile_sz = (int64_t)P.ray_tile * P.S;
+    const int64_t tile = m / tile_sz;
+    const int r = (int)(m - tile * tile_sz);
+    const int t_here = (int)min((int64_t)P.ray_tile, n_rays - tile * P.ray_tile);
+    m = (tile * P.ray_tile + r % t_here) * P.S + r / t_here;
+  }
   float pt[4];
   load_point(P, m, pt);
   const int out_stride = F.concat ? F.n_scales * C : C;
@@ -415,7 +426,7 @@ __device__ __forceinline__ void density_features(const FieldRef& F, const float 
 
 // Packed variant: val2[p][c/2] = (feature 2c', feature 2c'+1) of plane p; every product is an FMUL2 / FFMA2 whose halves round
 // exactly like bilerp_combine's scalar operations.
-template <int C, int NP>
+template <int C, int NP, bool WIDE>
 __device__ __forceinline__ void density_features2(const FieldRef& F, const float pt[4], float2 val2[NP][C / 2], Axis ax[4]) {
   axes_setup(F, 0, pt, ax);
 #pragma unroll
@@ -424,6 +435,23 @@ __device__ __forceinline__ void density_features2(const FieldRef& F, const float
     const Bilerp b = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
     if ((F.use_mask >> p) & 1u) {
       const float2 w00 = dup2(b.w00), w01 = dup2(b.w01), w10 = dup2(b.w10), w11 = dup2(b.w11);
+      if constexpr (C == 8 && WIDE) {
+        // one texel = 32 bytes = ONE 256-bit load per corner: half the load instructions and L1 wavefronts of the kernel
+        // (it is L1-bound: 69 % l1tex in ncu, every lane of a request on a different line)
+        const float8 t00 = ldg8(pr.p + (int64_t)b.o00 * 8), t01 = ldg8(pr.p + (int64_t)b.o01 * 8);
+        const float8 t10 = ldg8(pr.p + (int64_t)b.o10 * 8), t11 = ldg8(pr.p + (int64_t)b.o11 * 8);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 v00 = q ? t00.b : t00.a, v01 = q ? t01.b : t01.a, v10 = q ? t10.b : t10.a, v11 = q ? t11.b : t11.a;
+          float2 lo = __fmul2_rn(lo2(v00), w00), hi = __fmul2_rn(hi2(v00), w00);
+          lo = __ffma2_rn(lo2(v01), w01, lo); hi = __ffma2_rn(hi2(v01), w01, hi);
+          lo = __ffma2_rn(lo2(v10), w10, lo); hi = __ffma2_rn(hi2(v10), w10, hi);
+          lo = __ffma2_rn(lo2(v11), w11, lo); hi = __ffma2_rn(hi2(v11), w11, hi);
+          val2[p][q * 2] = lo;
+          val2[p][q * 2 + 1] = hi;
+        }
+        continue;
+      }
 #pragma unroll
       for (int q = 0; q < C / 4; ++q) {
         const float* base = pr.p + q * 4;
@@ -471,7 +499,7 @@ __device__ __forceinline__ float2 paired_preact(const float2* __restrict__ wrow,
   return pre;
 }
 
-template <int C, int NP>
+template <int C, int NP, bool WIDE>
 __global__ void __launch_bounds__(128) density_field_fwd_kernel(const __grid_constant__ FieldRef F,
                                                                  const __grid_constant__ KpPoints P, int64_t M,
                                                                  const float* __restrict__ w1, const float* __restrict__ w2,
@@ -487,7 +515,7 @@ __global__ void __launch_bounds__(128) density_field_fwd_kernel(const __grid_con
     load_point(P, m, pt);
     float2 val2[NP][C / 2];
     Axis ax[4];
-    density_features2<C, NP>(F, pt, val2, ax);
+    density_features2<C, NP, WIDE>(F, pt, val2, ax);
     float2 f2[C];  // (f[c], f[c]): the multiplicand of both units of a pair
 #pragma unroll
     for (int c = 0; c < C / 2; ++c) {
@@ -518,7 +546,7 @@ __global__ void __launch_bounds__(128) density_field_fwd_kernel(const __grid_con
 // 32 samples into registers; registers are flushed with one atomicAdd per weight per block at the end.
 // All three fp32 products (forward recompute, d_features, d_weights) run as packed FFMA2 -- the kernel is FMA-issue
 // bound (83 M warp instructions per launch in round 1's ncu capture), every half rounds like the scalar fma it replaces.
-template <int C, int NP, int HIDDEN>
+template <int C, int NP, int HIDDEN, bool WIDE>
 __global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_constant__ FieldRef F,
                                                                  const __grid_constant__ KpPoints P, int64_t M,
                                                                  const float* __restrict__ w1, const float* __restrict__ w2,
@@ -567,7 +595,7 @@ __global__ void __launch_bounds__(128, 4) density_field_bwd_kernel(const __grid_
     float2* pre_row = reinterpret_cast<float2*>(my_pre + lane * PS);
     if (valid) {
       load_point(P, m, pt);
-      density_features2<C, NP>(F, pt, val2, ax);
+      density_features2<C, NP, WIDE>(F, pt, val2, ax);
       float2 f2[C];
 #pragma unroll
       for (int c = 0; c < C / 2; ++c) {
@@ -773,27 +801,37 @@ static int launch_density(bool bwd, const FieldRef& F, const KpPoints& P, int64_
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // 8-channel texels are read with one 256-bit load each when every plane is 32-byte aligned (torch allocations and the
+  // gradient / parameter buckets are; a view at an odd offset falls back to two 128-bit loads)
+  bool wide = C == 8;
+  for (int p = 0; p < F.n_planes; ++p) wide = wide && (reinterpret_cast<uintptr_t>(F.pl[p].p) & 31) == 0;
   if (!bwd) {
     const size_t smem = (size_t)((hidden + 1) / 2) * (C + 1) * sizeof(float2);  // unit pairs (stage_paired_weights)
     const int64_t blocks = std::min<int64_t>(ceil_div(M, 128), (int64_t)sms * 16);
-    if (F.n_planes == 6)
-      density_field_fwd_kernel<C, 6><<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, hidden, relu, density);
-    else
-      density_field_fwd_kernel<C, 3><<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, hidden, relu, density);
+    auto launch = [&](auto kern) { kern<<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, hidden, relu, density); };
+    if (F.n_planes == 6) {
+      if (wide) launch(density_field_fwd_kernel<C, 6, true>);
+      else launch(density_field_fwd_kernel<C, 6, false>);
+    } else {
+      if (wide) launch(density_field_fwd_kernel<C, 3, true>);
+      else launch(density_field_fwd_kernel<C, 3, false>);
+    }
   } else {
     KP_CHECK(hidden == 64, "density_field_bwd: hidden=%d unsupported (64)", hidden);
     constexpr int HIDDEN = 64;
     const size_t smem =  // w1 rows + w1 unit pairs + w2 pairs + staged pre-activations / features / gradients + accumulators
         (size_t)(HIDDEN * C + HIDDEN * C + HIDDEN + 4 * 32 * (HIDDEN + 2) + 4 * 32 * C + 4 * 32 + HIDDEN * C + HIDDEN) * sizeof(float);
     const int64_t blocks = std::min<int64_t>(ceil_div(M, 128), (int64_t)sms * 4);
+    auto launch = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, relu, grad_density, gw1, gw2);
+    };
     if (F.n_planes == 6) {
-      auto kern = density_field_bwd_kernel<C, 6, HIDDEN>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, relu, grad_density, gw1, gw2);
+      if (wide) launch(density_field_bwd_kernel<C, 6, HIDDEN, true>);
+      else launch(density_field_bwd_kernel<C, 6, HIDDEN, false>);
     } else {
-      auto kern = density_field_bwd_kernel<C, 3, HIDDEN>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<(unsigned)blocks, 128, smem, st>>>(F, P, M, w1, w2, relu, grad_density, gw1, gw2);
+      if (wide) launch(density_field_bwd_kernel<C, 3, HIDDEN, true>);
+      else launch(density_field_bwd_kernel<C, 3, HIDDEN, false>);
     }
   }
   KP_LAUNCH_CHECK("density_field");

@@ -199,7 +199,8 @@ class KPlanesField(Field, _AabbHostMixin):
         if rf is not None:
             o, d, st, en, t = rf
             return ops.points_from_rays(o, d, st, en, t, self._aabb6(), norm_mode=2 if self._contract else 1,
-                                        dynamic=self.has_time_planes and t is not None)
+                                        dynamic=self.has_time_planes and t is not None,
+                                        ray_tile=0 if torch.is_grad_enabled() else int(getattr(self, "coherent_ray_tile", 0)))
         positions = ray_samples.frustums.get_positions()
         if self._contract:
             positions = self.spatial_distortion(positions) / 2.0  # from [-2, 2] to [-1, 1]

@@ -2,6 +2,8 @@
 K-Planes needs from NS/configs/base_config.py:33-58 (``PrintableConfig`` / ``InstantiateConfig``)."""
 from __future__ import annotations
 
+import contextlib
+
 from abc import abstractmethod
 from collections import defaultdict
 from dataclasses import dataclass, field
@@ -47,6 +49,22 @@ class ModelConfig(InstantiateConfig):
     collider_params: Optional[Dict[str, float]] = to_immutable_dict({"near_plane": 2.0, "far_plane": 6.0})
     loss_coefficients: Dict[str, float] = to_immutable_dict({"rgb_loss_coarse": 1.0, "rgb_loss_fine": 1.0})
     eval_num_rays_per_chunk: int = 4096
+
+
+@contextlib.contextmanager
+def coherent_rays(model, tile: int = 4):
+    """Tell the model's field that consecutive rays of the bundles it is about to see are neighbouring pixels of one frame:
+    its gather then lets a warp take one sample index of ``tile`` neighbouring rays (``KpPoints.ray_tile``), whose texel
+    reads coalesce.  Inference only (the field ignores it while gradients are enabled); no effect on results."""
+    field = getattr(model, "field", None)
+    old = getattr(field, "coherent_ray_tile", 0) if field is not None else 0
+    if field is not None:
+        field.coherent_ray_tile = tile
+    try:
+        yield
+    finally:
+        if field is not None:
+            field.coherent_ray_tile = old
 
 
 class Model(nn.Module):
@@ -104,11 +122,12 @@ class Model(nn.Module):
         chunk = self.config.eval_num_rays_per_chunk
         height, width = camera_ray_bundle.origins.shape[:2]
         pieces: Dict[str, List[torch.Tensor]] = defaultdict(list)
-        for begin in range(0, len(camera_ray_bundle), chunk):
-            part = self.forward(ray_bundle=camera_ray_bundle.get_row_major_sliced_ray_bundle(begin, begin + chunk))
-            for name, value in part.items():
-                if torch.is_tensor(value):
-                    pieces[name].append(value)
+        with coherent_rays(self):  # row-major chunks: neighbouring rays are neighbouring pixels
+            for begin in range(0, len(camera_ray_bundle), chunk):
+                part = self.forward(ray_bundle=camera_ray_bundle.get_row_major_sliced_ray_bundle(begin, begin + chunk))
+                for name, value in part.items():
+                    if torch.is_tensor(value):
+                        pieces[name].append(value)
         return {name: torch.cat(values).view(height, width, -1) for name, values in pieces.items()}
 
     def get_image_metrics_and_images(self, outputs, batch) -> Tuple[Dict[str, float], Dict[str, torch.Tensor]]:

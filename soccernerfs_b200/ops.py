@@ -110,6 +110,7 @@ class Points:
     S: int = 1
     norm_mode: int = 1
     aabb: Tuple[float, ...] = (0.0,) * 6
+    ray_tile: int = 0  # gather only (KpPoints.ray_tile): warps take one sample index of this many neighbouring rays
 
     @property
     def M(self) -> int:
@@ -121,7 +122,7 @@ class Points:
     def struct(self) -> _lib.KpPoints:
         return _lib.make_points(pts=self.pts, origins=self.origins, directions=self.directions, starts=self.starts,
                                 ends=self.ends, times=self.times, D=self.D, S=self.S, norm_mode=self.norm_mode,
-                                aabb=self.aabb)
+                                aabb=self.aabb, ray_tile=self.ray_tile)
 
 
 def points_from_pts(pts: torch.Tensor) -> Points:
@@ -129,13 +130,13 @@ def points_from_pts(pts: torch.Tensor) -> Points:
     return Points(D=pts.shape[-1], pts=pts.view(-1, pts.shape[-1]))
 
 
-def points_from_rays(origins, directions, starts, ends, times, aabb, norm_mode: int, dynamic: bool) -> Points:
+def points_from_rays(origins, directions, starts, ends, times, aabb, norm_mode: int, dynamic: bool, ray_tile: int = 0) -> Points:
     """origins/directions [N,3], starts/ends [N,S], times [N] or None."""
     return Points(
         D=4 if dynamic else 3, origins=f32c(origins.detach()), directions=f32c(directions.detach()),
         starts=f32c(starts.detach()), ends=f32c(ends.detach()),
         times=None if (times is None or not dynamic) else f32c(times.detach()).view(-1),
-        S=starts.shape[-1], norm_mode=norm_mode, aabb=tuple(aabb),
+        S=starts.shape[-1], norm_mode=norm_mode, aabb=tuple(aabb), ray_tile=ray_tile,
     )
 
 

@@ -26,7 +26,7 @@ def test_library_loaded_and_abi():
     from soccernerfs_b200 import _lib
 
     lib = _lib.load()
-    assert lib.kp_abi_version() == 2
+    assert lib.kp_abi_version() == 3
 
 
 def test_hexplane_vs_reference_fixture():
@@ -44,6 +44,33 @@ def test_hexplane_vs_reference_fixture():
     assert rel_err(interpolate_kplanes(pts, grids, False).cpu(), g["out_sum"]) < TOL
     g3 = [[_nchw_to_param(g[f"grid3_{j}"]) for j in range(3)]]
     assert rel_err(interpolate_kplanes(pts[:, :3].contiguous(), g3, True).cpu(), g["out_static"]) < TOL
+
+
+def test_gather_ray_tile_only_changes_the_thread_mapping():
+    """KpPoints.ray_tile (full-frame inference: a warp takes one sample index of neighbouring rays) writes every sample's
+    features at its own row: bit-identical to the default mapping, also when the ray count is not a multiple of the tile and
+    for both channel widths."""
+    from soccernerfs_b200 import ops
+
+    gen = torch.Generator().manual_seed(11)
+    combos = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+    for c, n_rays, s in ((32, 1027, 48), (8, 515, 7)):
+        reso = [(8, 8, 8, 5), (16, 16, 16, 5)]
+        planes = [[torch.rand(1, c, r[b], r[a], generator=gen).to(DEV).contiguous(memory_format=torch.channels_last)
+                   for a, b in combos] for r in reso]
+        o = (torch.rand(n_rays, 3, generator=gen) - 0.5).to(DEV)
+        d = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=gen), dim=-1).to(DEV)
+        edges = torch.sort(torch.rand(n_rays, s + 1, generator=gen) * 2.0, dim=-1).values.to(DEV)
+        t = torch.rand(n_rays, generator=gen).to(DEV)
+        aabb = (-1.0, -1.0, -1.0, 1.0, 1.0, 1.0)
+        outs = []
+        for tile in (0, 4, 16):
+            pts = ops.points_from_rays(o, d, edges[:, :-1].contiguous(), edges[:, 1:].contiguous(), t, aabb, norm_mode=1,
+                                       dynamic=True, ray_tile=tile)
+            with torch.no_grad():
+                outs.append(ops.hexplane_features(planes, pts, True))
+        assert outs[0].abs().sum() > 0
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (c, n_rays, s)
 
 
 def test_hexplane_freeze_flags():
@@ -601,10 +628,17 @@ def test_frame_renderer_equals_chunked_camera_bundle():
     model.config.eval_num_rays_per_chunk = 200
     with torch.no_grad():
         ref = model.get_outputs_for_camera_ray_bundle(full)
-    one = FrameRenderer(model, cams, chunk=200).render(0)
+    one = FrameRenderer(model, cams, chunk=200).render(0)  # one CUDA-graph replay per tile (two tile sizes: 200 and 160)
+    eager = FrameRenderer(model, cams, chunk=200, use_cuda_graph=False, ray_tile=0).render(0)
     for k in ("rgb", "depth", "accumulation"):
         assert one[k].shape[:2] == (h, w) and one[k].is_pinned()
         assert torch.equal(one[k], ref[k].cpu()), k
+        assert torch.equal(eager[k], ref[k].cpu()), k
+    again = FrameRenderer(model, cams, chunk=200)
+    again.render(0)
+    second = again.render(0)  # replays of the captured tiles (static index buffer refilled per tile)
+    for k in ("rgb", "depth", "accumulation"):
+        assert torch.equal(second[k], ref[k].cpu()), k
     total = {k: torch.zeros_like(v) for k, v in one.items()}
     for r in range(3):
         part = FrameRenderer(model, cams, chunk=200, rank=r, world=3).render(0)
