@@ -54,7 +54,8 @@ typedef struct KpPoints {
   int32_t ray_tile;        /* ray form, gather only: > 1 = the threads of a warp take the SAME sample index of ray_tile
                               neighbouring rays instead of consecutive samples of one ray (full-frame inference: neighbouring
                               pixels read the same texels, which then coalesce inside one request).  Results are written
-                              at the samples' own rows: only the thread -> sample assignment changes.  0/1 = off. */
+                              at the samples' own rows: only the thread -> sample assignment changes.  0/1 = off; < 0 = off and the
+                              4-channels-per-lane kernel forced (tests compare the two mappings). */
 } KpPoints;
 
 /* ---- (a1-a3) multiscale hexplane field: replaces interpolate_kplanes, NS/fields/kplanes_field.py:77-126

@@ -53,6 +53,12 @@ __device__ __forceinline__ float8 ldg8(const float* p) {
   return r;
 }
 
+__device__ __forceinline__ void stg8(float* p, float4 a, float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+               "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+
 // Vector reduction (no return value) into global memory: one 16-byte L2 atomic instead of four.
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

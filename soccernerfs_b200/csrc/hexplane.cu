@@ -50,6 +50,13 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p, uint64_t pol) {
                : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ float8 ldg8_stream(const float* p, uint64_t pol) {
+  float8 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ void red_add_v4_stream(float* addr, float4 v, uint64_t pol) {
   asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
                "l"(pol)
@@ -280,6 +287,95 @@ __global__ void __launch_bounds__(128, 4) hexplane_fwd_kernel(const __grid_const
     }
   }
   if (!F.concat) *reinterpret_cast<float4*>(out + m * out_stride + c4) = total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Forward gather, WIDE mapping (C = 32): 4 lanes per sample, 8 channels per lane -- one 256-bit load per corner and packed
+// FMUL2 / FFMA2 interpolation.  Per sample the coordinate set-up (identical on every lane of the sample) is done 4x instead
+// of 8x and every load / math instruction covers twice the channels: about half the warp instructions of the float4
+// kernel above.  Same arithmetic per channel, bit-identical output; where it is used is decided (from measurements) in
+// launch_hexplane.
+// The planes of a scale are gathered in two groups of NP/2 so that 12 (not 24) 32-byte loads are in flight per lane.
+// ---------------------------------------------------------------------------------------------------
+template <int NP, bool STREAM>
+__global__ void __launch_bounds__(128, 3) hexplane_fwd_wide_kernel(const __grid_constant__ FieldRef F,
+                                                                 const __grid_constant__ KpPoints P, int64_t M,
+                                                                 float* __restrict__ out) {
+  constexpr int C = 32, LPS = 4, G = NP / 2 > 0 ? (NP + 1) / 2 : 1;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t m = gt / LPS;
+  const int c8 = (int)(gt % LPS) * 8;
+  if (m >= M) return;
+  if (P.ray_tile > 1 && P.pts == nullptr) {
+    const int64_t n_rays = M / P.S, tile_sz = (int64_t)P.ray_tile * P.S;
+    const int64_t tile = m / tile_sz;
+    const int r = (int)(m - tile * tile_sz);
+    const int t_here = (int)min((int64_t)P.ray_tile, n_rays - tile * P.ray_tile);
+    m = (tile * P.ray_tile + r % t_here) * P.S + r / t_here;
+  }
+  float pt[4];
+  load_point(P, m, pt);
+  const int out_stride = F.concat ? F.n_scales * C : C;
+  const uint64_t pol = STREAM ? l2_policy_evict_first() : 0ull;
+  float2 total[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  for (int k = 0; k < F.n_scales; ++k) {
+    Axis ax[4];
+    axes_setup(F, k, pt, ax);
+    float2 acc[4] = {make_float2(1.f, 1.f), make_float2(1.f, 1.f), make_float2(1.f, 1.f), make_float2(1.f, 1.f)};
+#pragma unroll
+    for (int g0 = 0; g0 < NP; g0 += G) {
+      Bilerp b[G];
+      float8 v[G][4];
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int p = g0 + i;
+        if (p >= NP) continue;
+        const PlaneRef& pr = F.pl[k * KP_MAX_PLANES + p];
+        b[i] = bilerp_from_axes(ax[plane_ca<NP>(p)], ax[plane_cb<NP>(p)], pr.W);
+        if ((F.use_mask >> p) & 1u) {
+          const float* base = pr.p + c8;
+          if (STREAM && pr.stream) {
+            v[i][0] = ldg8_stream(base + (int64_t)b[i].o00 * C, pol);
+            v[i][1] = ldg8_stream(base + (int64_t)b[i].o01 * C, pol);
+            v[i][2] = ldg8_stream(base + (int64_t)b[i].o10 * C, pol);
+            v[i][3] = ldg8_stream(base + (int64_t)b[i].o11 * C, pol);
+          } else {
+            v[i][0] = ldg8(base + (int64_t)b[i].o00 * C);
+            v[i][1] = ldg8(base + (int64_t)b[i].o01 * C);
+            v[i][2] = ldg8(base + (int64_t)b[i].o10 * C);
+            v[i][3] = ldg8(base + (int64_t)b[i].o11 * C);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int p = g0 + i;
+        if (p >= NP || !((F.use_mask >> p) & 1u)) continue;
+        const float2 w00 = dup2(b[i].w00), w01 = dup2(b[i].w01), w10 = dup2(b[i].w10), w11 = dup2(b[i].w11);
+        // bilerp_combine per channel pair: v00*w00, then fma(v01,w01,.), fma(v10,w10,.), fma(v11,w11,.)
+        auto pair = [&](float2 x00, float2 x01, float2 x10, float2 x11) {
+          float2 r = __fmul2_rn(x00, w00);
+          r = __ffma2_rn(x01, w01, r);
+          r = __ffma2_rn(x10, w10, r);
+          return __ffma2_rn(x11, w11, r);
+        };
+        acc[0] = __fmul2_rn(acc[0], pair(lo2(v[i][0].a), lo2(v[i][1].a), lo2(v[i][2].a), lo2(v[i][3].a)));
+        acc[1] = __fmul2_rn(acc[1], pair(hi2(v[i][0].a), hi2(v[i][1].a), hi2(v[i][2].a), hi2(v[i][3].a)));
+        acc[2] = __fmul2_rn(acc[2], pair(lo2(v[i][0].b), lo2(v[i][1].b), lo2(v[i][2].b), lo2(v[i][3].b)));
+        acc[3] = __fmul2_rn(acc[3], pair(hi2(v[i][0].b), hi2(v[i][1].b), hi2(v[i][2].b), hi2(v[i][3].b)));
+      }
+    }
+    if (F.concat) {
+      stg8(out + m * out_stride + k * C + c8, make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y),
+           make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) total[q] = __fadd2_rn(total[q], acc[q]);
+    }
+  }
+  if (!F.concat)
+    stg8(out + m * out_stride + c8, make_float4(total[0].x, total[0].y, total[1].x, total[1].y),
+         make_float4(total[2].x, total[2].y, total[3].x, total[3].y));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -718,6 +814,30 @@ static int launch_hexplane(bool bwd, const FieldRef& F, const KpPoints& P, int64
   bool any_stream = false;  // the L2-policy variant only where a plane asks for it (it costs registers: 0.162 -> 0.181 ms at cfg2)
   for (int k = 0; k < F.n_scales; ++k)
     for (int p = 0; p < F.n_planes; ++p) any_stream |= F.pl[k * KP_MAX_PLANES + p].stream != 0;
+  if constexpr (C == 32) {
+    // wide mapping (4 lanes x 8 channels per sample).  Measured on B200 (gpurun_out/s3k_bench*): L2-resident field (cfg2
+    // training) 0.165 -> 0.150 ms; coherent rays of full-frame inference 361.9 -> 352.3 ms per frame; HBM-resident field with
+    // random rays (cfg3 training) 0.359 -> 0.405 ms -- there the float4 kernel keeps more requests in flight.  Hence: wide
+    // unless the field streams from HBM (any_stream) with incoherent rays.  KP_GATHER_WIDE=0/1 overrides.  Needs 32-byte
+    // aligned planes and output rows.
+    static const int wide_env = getenv("KP_GATHER_WIDE") != nullptr ? atoi(getenv("KP_GATHER_WIDE")) : -1;
+    const bool coherent = P.ray_tile > 1 && P.pts == nullptr;
+    bool wide = !bwd && (wide_env == 1 || (wide_env != 0 && (coherent || !any_stream))) && P.ray_tile >= 0;  // (< 0: float4 kernel, tests)
+    wide = wide && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
+    for (int k = 0; k < F.n_scales && wide; ++k)
+      for (int p = 0; p < F.n_planes; ++p) wide = wide && (reinterpret_cast<uintptr_t>(F.pl[k * KP_MAX_PLANES + p].p) & 31) == 0;
+    if (wide) {
+      const int64_t wb = ceil_div(M * 4, 128);
+      if (F.n_planes == 6) {
+        if (any_stream) hexplane_fwd_wide_kernel<6, true><<<(unsigned)wb, 128, 0, st>>>(F, P, M, out);
+        else hexplane_fwd_wide_kernel<6, false><<<(unsigned)wb, 128, 0, st>>>(F, P, M, out);
+      } else {
+        hexplane_fwd_wide_kernel<3, false><<<(unsigned)wb, 128, 0, st>>>(F, P, M, out);
+      }
+      KP_LAUNCH_CHECK("hexplane (wide)");
+      return 0;
+    }
+  }
   if (F.n_planes == 6) {
     if (any_stream) {
       if (!bwd) hexplane_fwd_kernel<C, 6, true><<<(unsigned)blocks, 128, 0, st>>>(F, P, M, out);

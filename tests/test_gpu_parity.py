@@ -64,13 +64,13 @@ def test_gather_ray_tile_only_changes_the_thread_mapping():
         t = torch.rand(n_rays, generator=gen).to(DEV)
         aabb = (-1.0, -1.0, -1.0, 1.0, 1.0, 1.0)
         outs = []
-        for tile in (0, 4, 16):
+        for tile in (-1, 0, 4, 16):  # -1: the float4-per-lane kernel; >= 0 with C = 32: the 8-channels-per-lane kernel
             pts = ops.points_from_rays(o, d, edges[:, :-1].contiguous(), edges[:, 1:].contiguous(), t, aabb, norm_mode=1,
                                        dynamic=True, ray_tile=tile)
             with torch.no_grad():
                 outs.append(ops.hexplane_features(planes, pts, True))
         assert outs[0].abs().sum() > 0
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (c, n_rays, s)
+        assert all(torch.equal(outs[0], o_) for o_ in outs[1:]), (c, n_rays, s)
 
 
 def test_hexplane_freeze_flags():
