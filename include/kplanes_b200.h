@@ -214,6 +214,12 @@ int kp_plane_reg_fused(const float* const* planes, float* const* grads, const in
  * exchange, where every rank contributes the regularisers' gradient for its own shard of the bucket only. */
 int kp_plane_reg_fused_range(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms, int P,
                              const float* coef_dev, int accumulate, double* sums, const int64_t* write_range_dev, void* stream);
+/* Shard form of the same sweep: the SUMS are restricted to [begin, end) as well (every term is counted where its centre
+ * element lives), and tiles without an element of the range are skipped -- a rank reads only its shard of the planes
+ * (+ halo).  The per-rank sums of a partition of the plane add up to kp_plane_reg_fused's.  Replaces, per rank, 1/world of
+ * the regulariser evaluation every DDP replica of the reference repeats in full (NS/models/kplanes.py:430-446). */
+int kp_plane_reg_fused_shard(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms, int P,
+                             const float* coef_dev, int accumulate, double* sums, const int64_t* write_range_dev, void* stream);
 
 /* Adam over a list of dense fp32 tensors in one launch.  hyper_dev (optional, DEVICE float[3] = lr/bias_corr1,
  * 1/sqrt(bias_corr2), grad_scale) overrides the host-computed scalars so a captured CUDA graph can be replayed

@@ -17,12 +17,14 @@ args = ap.parse_args()
 from soccernerfs_b200.engine.trainer import TrainStep
 from torch.profiler import profile, ProfilerActivity
 
-dev = torch.device("cuda", 0)
+rank, world, local = bench._dist_setup()  # (under torchrun: the data-parallel step; rank 0 writes its own timeline)
+dev = torch.device("cuda", local)
 model = bench.build_model(args.workload, dev)
+torch.manual_seed(42 + rank)
 model.proposal_sampler.update_sched = lambda step: 0
-trainer = TrainStep(model, use_cuda_graph=True, branch_small_kernels=not args.no_branches,
+trainer = TrainStep(model, use_cuda_graph=True, data_parallel=world > 1, branch_small_kernels=not args.no_branches,
                     prioritize_main_stream=not args.no_stream_priority)
-host = bench._make_batches(8, bench.RAYS_PER_RANK, seed=1000)
+host = bench._make_batches(8, bench.RAYS_PER_RANK, seed=1000 + rank)
 res = [h.to(dev) for h in host]
 for i in range(8):
     trainer(*bench._bundle(res[i % 8]))
@@ -31,6 +33,12 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for i in range(args.steps):
         trainer(*bench._bundle(res[i % 8]))
         torch.cuda.synchronize()
+if world > 1:
+    import torch.distributed as dist
+    dist.barrier()
+if rank != 0:
+    torch.cuda.synchronize()
+    os._exit(0)
 rows = []
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
@@ -48,3 +56,6 @@ try:
     prof.export_chrome_trace(os.path.join(ROOT, "gpurun_out", f"{args.tag}_trace.json"))
 except Exception as ex:  # noqa: BLE001
     print("trace export failed:", ex)
+if world > 1:
+    sys.stdout.flush()
+    os._exit(0)  # (captured graphs keep the peer arenas / communicator busy at interpreter shutdown, as in bench.py)

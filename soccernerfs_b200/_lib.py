@@ -68,6 +68,7 @@ SIGNATURES = {
     "kp_plane_reg_multi_bwd": ([_P, _P, _P, _P, c_int, _P, c_int, _P], c_int),
     "kp_plane_reg_fused": ([_P, _P, _P, _P, c_int, _P, c_int, _P, _P], c_int),
     "kp_plane_reg_fused_range": ([_P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P], c_int),
+    "kp_plane_reg_fused_shard": ([_P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P], c_int),
     "kp_plane_reg_adam_supported": ([c_int], c_int),
     "kp_plane_reg_adam_scratch_bytes": ([_P, c_int], c_int64),
     "kp_plane_reg_adam": ([_P, _P, _P, _P, _P, _P, c_int, _P, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P, _P,

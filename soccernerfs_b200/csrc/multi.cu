@@ -146,7 +146,7 @@ struct RegTile {
 template <bool ACCUMULATE>
 __global__ void __launch_bounds__(256) plane_reg_fused_kernel(const __grid_constant__ RegTable T, const __grid_constant__ RegTile G,
                                                               const float* __restrict__ coef, double* __restrict__ sums,
-                                                              const long long* __restrict__ write_range) {
+                                                              const long long* __restrict__ write_range, int sums_in_range) {
   const int p = find_tensor(G.first_block, T.n, blockIdx.x);
   const RegPlane& P = T.pl[p];
   const float* __restrict__ t = P.t;
@@ -164,6 +164,13 @@ __global__ void __launch_bounds__(256) plane_reg_fused_kernel(const __grid_const
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool need2 = (terms & 4u) != 0;
   const long long wr0 = write_range ? write_range[2 * p] : 0, wr1 = write_range ? write_range[2 * p + 1] : 0;
+  const bool shard_sums = write_range != nullptr && sums_in_range != 0;
+  if (shard_sums) {
+    // shard mode: a tile without any element of [wr0, wr1) has nothing to write and nothing to count (block-uniform exit)
+    const long long lo = (long long)h0 * row4 + tx * 256;
+    const long long hi = (long long)(h1 - 1) * row4 + min(row4, tx * 256 + 256) - 1;
+    if (hi < wr0 || lo >= wr1) return;
+  }
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (active) {
     const float* base = t + (size_t)col * 4;
@@ -175,26 +182,28 @@ __global__ void __launch_bounds__(256) plane_reg_fused_kernel(const __grid_const
     auto do_row = [&](int h, const float4& a, const float4& b, const float4& c, const float4& d, const float4& e, const float4& l,
                       const float4& r) {
       float4 g = zero;
+      const long long e4 = (long long)h * row4 + col;
+      const bool in_range = write_range == nullptr || (e4 >= wr0 && e4 < wr1);
+      const bool cnt = !shard_sums || in_range;  // shard mode: every term is counted by the rank that owns its element
       if (terms & 1u) {  // squared first difference along H
-        if (h + 1 < H) { const float4 df = sub4m(d, c); s0 += sq4m(df); g = fma4(df, -2.f * k0, g); }
+        if (h + 1 < H) { const float4 df = sub4m(d, c); if (cnt) s0 += sq4m(df); g = fma4(df, -2.f * k0, g); }
         if (h >= 1) g = fma4(sub4m(c, b), 2.f * k0, g);
       }
       if (needW) {  // squared first difference along W
-        if (hasR) { const float4 df = sub4m(r, c); s1 += sq4m(df); g = fma4(df, -2.f * k1, g); }
+        if (hasR) { const float4 df = sub4m(r, c); if (cnt) s1 += sq4m(df); g = fma4(df, -2.f * k1, g); }
         if (hasL) g = fma4(sub4m(c, l), 2.f * k1, g);
       }
       if (need2) {  // squared second difference along H
-        if (h + 2 < H) { const float4 dd = sub4m(sub4m(e, d), sub4m(d, c)); s2 += sq4m(dd); g = fma4(dd, 2.f * k2, g); }
+        if (h + 2 < H) { const float4 dd = sub4m(sub4m(e, d), sub4m(d, c)); if (cnt) s2 += sq4m(dd); g = fma4(dd, 2.f * k2, g); }
         if (h >= 1 && h + 1 < H) g = fma4(sub4m(sub4m(d, c), sub4m(c, b)), -4.f * k2, g);
         if (h >= 2) g = fma4(sub4m(sub4m(c, b), sub4m(b, a)), 2.f * k2, g);
       }
       if (terms & 8u) {  // |1 - t|
-        s3 += fabsf(1.f - c.x) + fabsf(1.f - c.y) + fabsf(1.f - c.z) + fabsf(1.f - c.w);
+        if (cnt) s3 += fabsf(1.f - c.x) + fabsf(1.f - c.y) + fabsf(1.f - c.z) + fabsf(1.f - c.w);
         g.x -= k3 * sgnm(1.f - c.x); g.y -= k3 * sgnm(1.f - c.y); g.z -= k3 * sgnm(1.f - c.z); g.w -= k3 * sgnm(1.f - c.w);
       }
       if (gbase != nullptr) {
-        const long long e4 = (long long)h * row4 + col;
-        if (write_range == nullptr || (e4 >= wr0 && e4 < wr1)) {
+        if (in_range) {
           float4* gp = reinterpret_cast<float4*>(gbase + (size_t)h * rstride + (size_t)col * 4);
           if (ACCUMULATE) { const float4 cur = *gp; g.x += cur.x; g.y += cur.y; g.z += cur.z; g.w += cur.w; }
           *gp = g;
@@ -567,14 +576,31 @@ extern "C" int kp_step_scalars(int64_t* step_counter, const double* lr_table, co
   return 0;
 }
 
+static int plane_reg_fused_impl(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms, int P,
+                                const float* coef_dev, int accumulate, double* sums, const int64_t* write_range_dev,
+                                int sums_in_range, void* stream);
+
 extern "C" int kp_plane_reg_fused(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms,
                                   int P, const float* coef_dev, int accumulate, double* sums, void* stream) {
-  return kp_plane_reg_fused_range(planes, grads, hwc, terms, P, coef_dev, accumulate, sums, nullptr, stream);
+  return plane_reg_fused_impl(planes, grads, hwc, terms, P, coef_dev, accumulate, sums, nullptr, 0, stream);
 }
 
 extern "C" int kp_plane_reg_fused_range(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms,
                                         int P, const float* coef_dev, int accumulate, double* sums, const int64_t* write_range_dev,
                                         void* stream) {
+  return plane_reg_fused_impl(planes, grads, hwc, terms, P, coef_dev, accumulate, sums, write_range_dev, 0, stream);
+}
+
+extern "C" int kp_plane_reg_fused_shard(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms,
+                                        int P, const float* coef_dev, int accumulate, double* sums, const int64_t* write_range_dev,
+                                        void* stream) {
+  KP_CHECK(write_range_dev != nullptr, "plane_reg_fused_shard: needs the per-plane ranges");
+  return plane_reg_fused_impl(planes, grads, hwc, terms, P, coef_dev, accumulate, sums, write_range_dev, 1, stream);
+}
+
+static int plane_reg_fused_impl(const float* const* planes, float* const* grads, const int32_t* hwc, const uint32_t* terms, int P,
+                                const float* coef_dev, int accumulate, double* sums, const int64_t* write_range_dev,
+                                int sums_in_range, void* stream) {
   KP_CHECK(planes && hwc && terms && coef_dev && P >= 0, "plane_reg_fused: bad arguments");
   for (int begin = 0; begin < P; begin += kMaxTensors) {
     const int end = std::min(P, begin + kMaxTensors);
@@ -591,8 +617,8 @@ extern "C" int kp_plane_reg_fused_range(const float* const* planes, float* const
     if (nb == 0) continue;
     double* s = sums ? sums + (size_t)begin * 4 : nullptr;
     const long long* wr = write_range_dev ? reinterpret_cast<const long long*>(write_range_dev) + (size_t)begin * 2 : nullptr;
-    if (accumulate) plane_reg_fused_kernel<true><<<nb, 256, 0, as_stream(stream)>>>(T, G, coef_dev + (size_t)begin * 4, s, wr);
-    else plane_reg_fused_kernel<false><<<nb, 256, 0, as_stream(stream)>>>(T, G, coef_dev + (size_t)begin * 4, s, wr);
+    if (accumulate) plane_reg_fused_kernel<true><<<nb, 256, 0, as_stream(stream)>>>(T, G, coef_dev + (size_t)begin * 4, s, wr, sums_in_range);
+    else plane_reg_fused_kernel<false><<<nb, 256, 0, as_stream(stream)>>>(T, G, coef_dev + (size_t)begin * 4, s, wr, sums_in_range);
     KP_LAUNCH_CHECK("plane_reg_fused");
   }
   return 0;

@@ -311,17 +311,29 @@ __global__ void __launch_bounds__(kPeerThreads) peer_sharded_adam_sparse_kernel(
 // after the exchange kernel: the in-kernel barriers pair block k of every rank with block k of the others, so only the
 // completion of the whole exchange kernel (all of this rank's blocks past their end barrier, hence all of every peer's
 // blocks past their reads) guarantees that nobody still reads the lines being zeroed.
+// One thread per line, four lines in flight per thread: the marks are read as consecutive bytes across the warp and only
+// marked lines are touched, each with eight 16-byte stores that cover the whole 128-byte line (the first version walked
+// every float4 of the bucket with a dependent mark load per step: 0.27 ms for 2.3 GB).
 __global__ void __launch_bounds__(kPeerThreads) peer_touched_cleanup_kernel(float* __restrict__ gown, uint8_t* __restrict__ town,
                                                                             int64_t n4, int64_t lo, int64_t hi) {
+  const int64_t n_lines = (n4 + 7) >> 3;
   const int64_t stride = (int64_t)gridDim.x * kPeerThreads;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t j = (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; j < n4; j += stride) {
-    if (j >= lo && j < hi) continue;
-    const uint32_t f = town[j >> 3];
-    __syncwarp();  // the 8 lanes of a line have read its mark before lane 0 of the line clears it
-    if (f == 1u) {
-      *reinterpret_cast<float4*>(gown + 4 * j) = zero;
-      if ((j & 7) == 0) town[j >> 3] = 0;
+  constexpr int U = 4;
+  for (int64_t l0 = (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; l0 < n_lines; l0 += stride * U) {
+    uint8_t f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) f[u] = (l0 + u * stride < n_lines) ? town[l0 + u * stride] : (uint8_t)0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (f[u] != 1u) continue;
+      const int64_t line = l0 + u * stride, j0 = line << 3;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int64_t j = j0 + q;
+        if (j < n4 && !(j >= lo && j < hi)) *reinterpret_cast<float4*>(gown + 4 * j) = zero;
+      }
+      if (!(j0 >= lo && j0 < hi)) town[line] = 0;  // the mark goes with the line's first float4, like the reduction's own clean-up
     }
   }
 }
@@ -428,7 +440,7 @@ extern "C" int kp_peer_sharded_adam_sparse(void* const* arenas, int rank, int wo
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    peer_touched_cleanup_kernel<<<sms * 2, kPeerThreads, 0, st>>>(a.grad[rank], a.touched[rank], a.n4, lo, hi);
+    peer_touched_cleanup_kernel<<<sms * 8, kPeerThreads, 0, st>>>(a.grad[rank], a.touched[rank], a.n4, lo, hi);
   }
   KP_LAUNCH_CHECK("peer_sharded_adam_sparse");
   return 0;

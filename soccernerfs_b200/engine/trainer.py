@@ -176,7 +176,10 @@ class TrainStep:
         model.proposal_sampler.side_stream = self._prop_stream
         # [0]: outputs no loss reads (accumulation / depths / median colour); [1..]: distortion and interlevel terms, forward
         # and (autograd replays a node on its forward's stream) backward, as parallel branches
-        self._branch_streams = [torch.cuda.Stream() for _ in range(4)] if (self.overlap and branch_small_kernels) else None
+        # (same priority as the captured step's stream: at the default priority they queue behind every block of the
+        # regulariser sweep -- CUPTI, cfg3 at 2 ranks: the loss kernels waited 0.37 ms for it)
+        self._branch_streams = ([torch.cuda.Stream(priority=-1 if prioritize_main_stream else 0) for _ in range(4)]
+                                if (self.overlap and branch_small_kernels) else None)
         model._kp_branch_streams = self._branch_streams
         self.use_cuda_graph = use_cuda_graph
         # the captured step's own stream: above the side branches (priority 0), below the communication stream (-2)
@@ -202,6 +205,15 @@ class TrainStep:
         scale = [1.0 if off is None else float(self.world) for off in offsets]
         self._reg_range = torch.tensor(rng, dtype=torch.int64, device=dev)
         self._reg_scale = torch.tensor(scale, dtype=torch.float32, device=dev)
+        # The loss VALUES are sharded like the gradient (kp_plane_reg_fused_shard): every rank sums the regulariser terms of
+        # its own shard only -- 1/world of the 2.3 GB the full sweep reads (CUPTI, cfg3 at 2 ranks: the full sweep took
+        # 2.0 ms and the loss head waited 0.9 ms for it) -- and the six scaled values are summed over the ranks in a few
+        # floats of the arena after the exchange.  Planes of the densely exchanged group are swept in full by every rank:
+        # their share is 1/world.
+        self._reg_sum_scale = torch.tensor([1.0 / self.world if off is None else 1.0 for off in offsets], dtype=torch.float64,
+                                           device=dev)
+        self._reg_vals, self._reg_vals_off = self.arena.take(64)
+        self._reg_vals.zero_()
 
     def _clean_field_bucket(self) -> None:
         """Before a sparse step that follows anything else (first step, a dense diagnostic iteration): the invariant "a line
@@ -248,8 +260,14 @@ class TrainStep:
                 if self._reg_written:
                     # one sweep per plane: loss values + gradient WRITTEN into the bucket (which was not memset there)
                     if self._sparse and self.reduce_grads and "fields" in self.sharded:
-                        # field planes: only this rank's shard of the bucket, pre-multiplied by the world size
-                        regs = model.regularizers_into_grads(accumulate=False, write_range=self._reg_range, grad_scale=self._reg_scale)
+                        # field planes: only this rank's shard of the bucket, pre-multiplied by the world size; the values
+                        # are this rank's share too and go to the arena slot that is summed over the ranks after the exchange
+                        part = model.regularizers_into_grads(accumulate=False, write_range=self._reg_range, grad_scale=self._reg_scale,
+                                                             sums_in_range=True, sum_scale=self._reg_sum_scale)
+                        self._reg_names = list(part.keys())
+                        if part:
+                            self._reg_vals[: len(part)].copy_(torch.stack(list(part.values())))
+                        regs = {}  # merged into the loss dict after the exchange (like the f1 path)
                     else:
                         regs = model.regularizers_into_grads(accumulate=False)
                 else:
@@ -308,7 +326,13 @@ class TrainStep:
                 comm.wait_stream(main)
                 with torch.cuda.stream(comm):
                     self._sharded_step("proposal_networks")
+                    if self._sparse and getattr(self, "_reg_names", None):
+                        self.arena.all_reduce(self._reg_vals_off, 64)  # the regularisers' values: sum of the ranks' shares
                 main.wait_stream(comm)
+                if self._sparse and getattr(self, "_reg_names", None):
+                    vals = self._reg_vals[: len(self._reg_names)].clone()
+                    loss_dict.update({n: vals[i] for i, n in enumerate(self._reg_names)})
+                    loss = loss.detach() + vals.sum()
                 return self._finish(loss_dict, loss, metrics)
             if self._first_span is not None and len(self._scale_ready) == n_scales:
                 # finest scale (most of the bytes) while the other scales are still being scattered, the rest of the

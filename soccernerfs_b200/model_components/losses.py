@@ -226,14 +226,16 @@ def regularizer_plan(ms_grids_nerf, ms_grids_prop):
 
 
 def kplanes_regularizers_into_grads(ms_grids_nerf, ms_grids_prop, loss_coefficients, accumulate: bool = False,
-                                    write_range=None, grad_scale=None):
+                                    write_range=None, grad_scale=None, sums_in_range: bool = False, sum_scale=None):
     """The training step's form of ``kplanes_regularizers``: ONE sweep per plane that returns the six SCALED loss values
     (detached; keyed like the reference's loss dict) and writes (``accumulate=False``: the sweep replaces the gradient
     buffer's memset) or adds the scaled regularisers' gradient into every plane's gradient sink (``ops.grad_sink``).
     Planes without a sink (frozen / no bucket attached) only contribute their value.
     ``write_range`` (int64 [P,2] device tensor) / ``grad_scale`` ([P] device tensor): the data-parallel step with the sparse
     gradient exchange writes each plane's gradient only inside this rank's shard of the bucket, pre-multiplied by the world
-    size (the reduction then divides the sum by it)."""
+    size (the reduction then divides the sum by it).  ``sums_in_range``: the loss VALUES are this rank's share as well (the
+    sweep reads only its shard; the caller sums the returned values over the ranks); ``sum_scale`` ([P] device tensor) then
+    weights each plane's share (1/world for a plane every rank sweeps in full)."""
     planes, terms, rows = regularizer_plan(ms_grids_nerf, ms_grids_prop)
     dev = planes[0].device
     scale = [float(loss_coefficients.get(n, 0.0)) for n in REG_NAMES]
@@ -242,7 +244,9 @@ def kplanes_regularizers_into_grads(ms_grids_nerf, ms_grids_prop, loss_coefficie
     if grad_scale is not None:  # [P] per-plane factor on the GRADIENT only (the values below stay unscaled)
         coef = coef * grad_scale[:, None]
     targets = [ops.grad_sink(p) for p in planes]
-    sums = ops.plane_reg_fused(planes, terms, coef, targets, accumulate, write_range=write_range)
+    sums = ops.plane_reg_fused(planes, terms, coef, targets, accumulate, write_range=write_range, sums_in_range=sums_in_range)
+    if sum_scale is not None:
+        sums = sums * sum_scale.to(sums.dtype)[:, None]
     vals = (sums.float()[:, None, :] * norm).sum(dim=(0, 2)) * _const(scale, dev)  # [6], already scaled
     return {name: vals[i] for i, name in enumerate(REG_NAMES) if name in loss_coefficients}, targets
 

@@ -398,7 +398,8 @@ class KPlanesModel(Model):
     def regularized_planes(self) -> List[Parameter]:
         return [p for g in self.field.grids for p in g] + [p for net in self.proposal_networks for p in net.grids]
 
-    def regularizers_into_grads(self, accumulate: bool = False, write_range=None, grad_scale=None) -> Dict[str, torch.Tensor]:
+    def regularizers_into_grads(self, accumulate: bool = False, write_range=None, grad_scale=None, sums_in_range: bool = False,
+                                sum_scale=None) -> Dict[str, torch.Tensor]:
         """Training-step form of ``regularizer_losses`` (kplanes.py:430-446): the six SCALED, detached loss values from
         ONE sweep per plane that also writes (or adds) the scaled regularisers' gradient into every plane's gradient
         sink -- no autograd graph, no separate backward sweep, and no memset of the planes' part of the bucket."""
@@ -406,7 +407,8 @@ class KPlanesModel(Model):
 
         vals, _ = kplanes_regularizers_into_grads(self.field.grids, [p.grids for p in self.proposal_networks],
                                                   self.config.loss_coefficients, accumulate=accumulate,
-                                                  write_range=write_range, grad_scale=grad_scale)
+                                                  write_range=write_range, grad_scale=grad_scale,
+                                                  sums_in_range=sums_in_range, sum_scale=sum_scale)
         ops.PLANE_REG_BACKWARDS += 1
         return vals
 

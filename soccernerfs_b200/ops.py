@@ -921,7 +921,7 @@ class _PlaneReg(torch.autograd.Function):
 
 def plane_reg_fused(planes: Sequence[torch.Tensor], terms: Sequence[int], coef_dev: torch.Tensor,
                     targets: Sequence[Optional[torch.Tensor]], accumulate: bool, want_sums: bool = True,
-                    write_range: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+                    write_range: Optional[torch.Tensor] = None, sums_in_range: bool = False) -> Optional[torch.Tensor]:
     """One sweep per plane: -> sums [P,4] (float64) of the regulariser terms, and targets[p] (channel-last gradient
     buffers, entries may be None) = / += sum_i coef_dev[p,i] * d(sums[p,i])/d(plane).  No autograd: this is the training
     step's form, where the gradient goes straight into the parameter's bucket (and, with accumulate=False, replaces the
@@ -936,8 +936,10 @@ def plane_reg_fused(planes: Sequence[torch.Tensor], terms: Sequence[int], coef_d
     if write_range is not None:  # int64 [P,2] on the device: float4 element range of each plane whose gradient is written
         if write_range.dtype != torch.int64 or tuple(write_range.shape) != (len(planes), 2):
             raise RuntimeError("plane_reg_fused: write_range must be int64 [P,2]")
-        call("kp_plane_reg_fused_range", _plane_ptrs(planes), _plane_ptrs(list(targets)), hwc, tm, len(planes), ptr(f32c(coef_dev)),
-             int(accumulate), ptr(sums), ptr(write_range), stream_ptr())
+        # sums_in_range: the shard form -- sums restricted to the range too, tiles outside it skipped
+        call("kp_plane_reg_fused_shard" if sums_in_range else "kp_plane_reg_fused_range", _plane_ptrs(planes),
+             _plane_ptrs(list(targets)), hwc, tm, len(planes), ptr(f32c(coef_dev)), int(accumulate), ptr(sums), ptr(write_range),
+             stream_ptr())
         return sums
     call("kp_plane_reg_fused", _plane_ptrs(planes), _plane_ptrs(list(targets)), hwc, tm, len(planes), ptr(f32c(coef_dev)),
          int(accumulate), ptr(sums), stream_ptr())

@@ -851,6 +851,21 @@ def test_fused_regularizer_sweep_write_range_and_touched_marks():
         assert torch.equal(ql[a:b], fl[a:b])
         assert bool((ql[:a] == 7.0).all()) and bool((ql[b:] == 7.0).all())
 
+    # (1b) shard form: the SUMS are restricted to the range as well, so the shares of a partition add up to the full sums
+    # (every term counted exactly once), and the gradient inside each range equals the full sweep's
+    sizes4 = [p.numel() // 4 for p in planes]
+    cuts = [[0, n4 // 3 + 5, 2 * n4 // 3 - 7, n4] for n4 in sizes4]
+    total = torch.zeros_like(sums_full)
+    for r in range(3):
+        rng_r = torch.tensor([[c_[r], c_[r + 1]] for c_ in cuts], dtype=torch.int64, device=DEV)
+        part_r = [torch.full_like(p, 7.0, memory_format=torch.preserve_format) for p in planes]
+        total += ops.plane_reg_fused(planes, terms, coef, part_r, accumulate=False, write_range=rng_r, sums_in_range=True)
+        for f, q, (a, b) in zip(full, part_r, rng_r.tolist()):
+            fl, ql = f.permute(0, 2, 3, 1).reshape(-1, 4), q.permute(0, 2, 3, 1).reshape(-1, 4)
+            assert torch.equal(ql[a:b], fl[a:b])
+            assert bool((ql[:a] == 7.0).all()) and bool((ql[b:] == 7.0).all())
+    assert torch.allclose(total, sums_full, rtol=1e-6, atol=0.0), (total, sums_full)
+
     # (2) marks
     n, c = 3000, 32
     ms = [[(torch.rand(1, c, h, w, device=DEV)).contiguous(memory_format=torch.channels_last).requires_grad_(True)
