@@ -309,21 +309,8 @@ class KPlanesModel(Model):
         else:
             with torch.no_grad():  # PSNR with data_range 1.0 (torchmetrics.PeakSignalNoiseRatio in the reference)
                 metrics_dict["psnr"] = -10.0 * torch.log10(torch.mean((outputs["rgb"] - image) ** 2))
-        if "depth_image" in batch.keys() and self.training and self.config.loss_coefficients["depth_loss"] > 0:
-            metrics_dict["depth_loss"] = 0.0
-            sigma = self._get_sigma().to(self.device)
-            termination_depth = batch["depth_image"].to(self.device)
-            for i in range(len(outputs["weights_list"])):
-                metrics_dict["depth_loss"] += depth_loss(
-                    weights=outputs["weights_list"][i],
-                    ray_samples=outputs["ray_samples_list"][i],
-                    termination_depth=termination_depth,
-                    predicted_depth=outputs["depth"],
-                    sigma=sigma,
-                    directions_norm=outputs["directions_norm"],
-                    is_euclidean=self.config.is_euclidean_depth,
-                    depth_loss_type=self.config.depth_loss_type,
-                ) / len(outputs["weights_list"])
+        if self.training and "depth_image" in batch and self.config.loss_coefficients["depth_loss"] > 0:
+            metrics_dict["depth_loss"] = self._mean_depth_loss(outputs, batch["depth_image"].to(self.device))
         return metrics_dict
 
     def _loss_head(self, outputs, image):
@@ -492,6 +479,17 @@ class KPlanesModel(Model):
             images_dict["depth"] = torch.cat([colormaps.apply_depth_colormap(ground_truth_depth), depth], dim=1)
         images_dict["median_rgb"] = outputs["median_rgb"]
         return metrics_dict, images_dict
+
+    def _mean_depth_loss(self, outputs, termination_depth: torch.Tensor) -> torch.Tensor:
+        """Depth supervision averaged over every sampling level, proposal levels included (kplanes.py:395-410): each
+        level's weights are compared with the sensor depth along its own samples."""
+        levels = list(zip(outputs["weights_list"], outputs["ray_samples_list"]))
+        sigma = self._get_sigma().to(self.device)
+        per_level = [depth_loss(weights=w, ray_samples=rs, termination_depth=termination_depth, predicted_depth=outputs["depth"],
+                                sigma=sigma, directions_norm=outputs["directions_norm"],
+                                is_euclidean=self.config.is_euclidean_depth, depth_loss_type=self.config.depth_loss_type)
+                     for w, rs in levels]
+        return sum(per_level) / len(per_level)
 
     def _get_sigma(self):
         if not self.config.should_decay_sigma:

@@ -610,6 +610,43 @@ def test_ray_generation_vs_reference_fixture():
         Cameras(g["c2w"], 50.0, 50.0, 32.0, 18.0, w, h, distortion_params=torch.ones(5, 6))
 
 
+def test_depth_supervision_goes_through_every_sampling_level():
+    """kplanes.py:395-410 / :447-449: with a depth image in the batch the depth loss is the mean over ALL levels (proposal
+    levels included) of losses.depth_loss, scaled by its coefficient; the step with such a batch is not graph-capturable
+    (only origins / directions / times / image have static buffers) and must take the eager iteration, not drop the key."""
+    from soccernerfs_b200.engine.trainer import TrainStep
+    from soccernerfs_b200.model_components.losses import depth_loss
+    from tests.helpers import build_model, ray_bundle
+    from tests.test_oracle_golden import load_tiny_model
+
+    g = load_golden("model_tiny")
+    model = build_model("tiny", load_tiny_model(g), g["aabb"], DEV)
+    model.train()
+    n = g["origins"].shape[0]
+    rb = ray_bundle(g["origins"], g["directions"], g["times"], DEV)
+    rb.metadata = {"directions_norm": torch.ones(n, 1, device=DEV)}
+    batch = {"image": g["image"].to(DEV), "depth_image": (1.0 + torch.rand(n, 1, generator=torch.Generator().manual_seed(1))).to(DEV)}
+    torch.manual_seed(0)
+    outputs = model(rb)
+    metrics = model.get_metrics_dict(outputs, batch)
+    sigma = model._get_sigma().to(DEV)
+    ref = sum(depth_loss(weights=w, ray_samples=rs, termination_depth=batch["depth_image"], predicted_depth=outputs["depth"],
+                         sigma=sigma, directions_norm=outputs["directions_norm"], is_euclidean=model.config.is_euclidean_depth,
+                         depth_loss_type=model.config.depth_loss_type)
+              for w, rs in zip(outputs["weights_list"], outputs["ray_samples_list"])) / len(outputs["weights_list"])
+    assert len(outputs["weights_list"]) == model.config.num_proposal_iterations + 1
+    assert rel_err(metrics["depth_loss"].detach(), ref.detach()) < 1e-6 and float(ref.detach()) > 0
+    losses = model.get_loss_dict(outputs, batch, metrics)
+    assert rel_err(losses["depth_loss"], model.config.loss_coefficients["depth_loss"] * ref) < 1e-6
+    step = TrainStep(model, max_steps=100, warm_up_end=4, use_cuda_graph=True)
+    try:
+        assert not step._graphable(rb, batch)
+        out = step(rb, batch)
+        assert "depth_loss" in out and bool(torch.isfinite(out["loss"]))
+    finally:
+        step.close()
+
+
 def test_frame_renderer_equals_chunked_camera_bundle():
     """config 5: the tile queue (device ray generation + chunked forward + async copies to pinned frames) gives the
     same image as generate_rays(keep_shape=True) -> get_outputs_for_camera_ray_bundle, also when 3 ranks share it."""
