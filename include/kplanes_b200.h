@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 3
+#define KP_ABI_VERSION 4
 #define KP_MAX_SCALES 8
 #define KP_MAX_PLANES 6
 
@@ -264,14 +264,20 @@ int kp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
 int kp_repack_nchw_to_hwc(const float* src, float* dst, int C, int H, int W, void* stream);
 int kp_repack_hwc_to_nchw(const float* src, float* dst, int C, int H, int W, void* stream);
 
-/* ---- (f2) pixel -> ray generation: Cameras._generate_rays_from_coords, NS/cameras/cameras.py:505-741 (perspective,
- *      no distortion), as driven by RayGenerator.forward (NS/model_components/ray_generators.py:43-59) when
+/* ---- (f2) pixel -> ray generation: Cameras._generate_rays_from_coords, NS/cameras/cameras.py:505-741,
+ *      as driven by RayGenerator.forward (NS/model_components/ray_generators.py:43-59) when
  *      ray_indices [N,3] = (camera,row,col) is given, or by Cameras.generate_rays(camera_indices=cam) for the
  *      row-major pixel range [first_pixel, first_pixel+N) of camera `cam` (image width `width`) when it is NULL.
  *      pixel_offset is get_image_coords' 0.5.  Outputs as in the reference's RayBundle: origins/directions [N,3],
- *      pixel_area [N], directions_norm [N] (metadata), times [N] (cameras.times[cam]). ---- */
+ *      pixel_area [N], directions_norm [N] (metadata), times [N] (cameras.times[cam]).
+ *      distortion (ABI 4): OpenCV k1,k2,k3,k4,p1,p2 per camera, undone by radial_and_tangential_undistort's 10 Newton
+ *      iterations (NS/cameras/camera_utils.py:298-401) for every non-equirectangular camera (cameras.py:635-654); NULL =
+ *      none.  cam_types (ABI 4): CameraType values per camera, 1 perspective / 2 fisheye / 3 equirectangular
+ *      (cameras.py:42-47, direction models :665-697); NULL = all perspective.  Both NULL: the undistorted perspective
+ *      kernel. ---- */
 int kp_generate_rays(const float* c2w /* [n_cams,3,4] */, const float* intrinsics /* [n_cams,4] fx,fy,cx,cy */,
-                     const float* cam_times /* [n_cams] or NULL */, int n_cams, const int64_t* ray_indices /* or NULL */,
+                     const float* cam_times /* [n_cams] or NULL */, const float* distortion /* [n_cams,6] or NULL */,
+                     const int32_t* cam_types /* [n_cams] or NULL */, int n_cams, const int64_t* ray_indices /* or NULL */,
                      int cam, int width, int64_t first_pixel, int64_t N, float pixel_offset, float* origins,
                      float* directions, float* pixel_area, float* directions_norm /* or NULL */, float* times /* or NULL */,
                      void* stream);

@@ -20,6 +20,7 @@ NS = /root/reference/nerfstudio/nerfstudio.  All functions take/return torch ten
 from __future__ import annotations
 
 import itertools
+import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -692,10 +693,41 @@ def model_loss_dict(mp: ModelParams, out: Dict, image: torch.Tensor, training: b
 # --------------------------------------------------------------------------------------------
 # Synthetic scene shapes -- shared by tests, smoke and bench so inputs are identical
 # --------------------------------------------------------------------------------------------
-def generate_rays(c2w, fx, fy, cx, cy, cam_times, cam_idx, y_idx, x_idx, pixel_offset: float = 0.5):
-    """Perspective, undistorted case of Cameras._generate_rays_from_coords (NS/cameras/cameras.py:505-741), for rays
-    given as (camera, row, col) like RayGenerator.forward (NS/model_components/ray_generators.py:43-59).
-    c2w [C,3,4]; fx,fy,cx,cy [C,1]; cam_times [C,1] | None; indices int64 [N].
+def undistort(coords: torch.Tensor, k: torch.Tensor, eps: float = 1e-3, max_iterations: int = 10) -> torch.Tensor:
+    """radial_and_tangential_undistort (NS/cameras/camera_utils.py:363-401): Newton's method on the OpenCV forward model
+    (residual and Jacobian of _compute_residual_and_jacobian, :298-360), started at the distorted point, a step only
+    where |det J| > eps.  coords [..., 2], k [..., 6] = (k1, k2, k3, k4, p1, p2), broadcastable."""
+    k1, k2, k3, k4, p1, p2 = (k[..., i] for i in range(6))
+    xd, yd = coords[..., 0], coords[..., 1]
+    x, y = xd, yd
+    for _ in range(max_iterations):
+        r = x * x + y * y
+        d = 1.0 + r * (k1 + r * (k2 + r * (k3 + r * k4)))
+        fx = d * x + 2 * p1 * x * y + p2 * (r + 2 * x * x) - xd
+        fy = d * y + 2 * p2 * x * y + p1 * (r + 2 * y * y) - yd
+        d_r = k1 + r * (2.0 * k2 + r * (3.0 * k3 + r * 4.0 * k4))
+        d_x, d_y = 2.0 * x * d_r, 2.0 * y * d_r
+        fx_x = d + d_x * x + 2.0 * p1 * y + 6.0 * p2 * x
+        fx_y = d_y * x + 2.0 * p1 * x + 2.0 * p2 * y
+        fy_x = d_x * y + 2.0 * p2 * y + 2.0 * p1 * x
+        fy_y = d + d_y * y + 2.0 * p2 * x + 6.0 * p1 * y
+        den = fy_x * fx_y - fx_x * fy_y
+        ok = torch.abs(den) > eps
+        x = x + torch.where(ok, (fx * fy_y - fy * fx_y) / den, torch.zeros_like(den))
+        y = y + torch.where(ok, (fy * fx_x - fx * fy_x) / den, torch.zeros_like(den))
+    return torch.stack([x, y], dim=-1)
+
+
+CAMERA_PERSPECTIVE, CAMERA_FISHEYE, CAMERA_EQUIRECTANGULAR = 1, 2, 3  # CameraType, NS/cameras/cameras.py:42-47
+
+
+def generate_rays(c2w, fx, fy, cx, cy, cam_times, cam_idx, y_idx, x_idx, pixel_offset: float = 0.5,
+                  distortion_params=None, camera_type=None):
+    """Cameras._generate_rays_from_coords (NS/cameras/cameras.py:505-741), for rays given as (camera, row, col) like
+    RayGenerator.forward (NS/model_components/ray_generators.py:43-59).
+    c2w [C,3,4]; fx,fy,cx,cy [C,1]; cam_times [C,1] | None; indices int64 [N]; distortion_params [C,6] | None (OpenCV
+    k1,k2,k3,k4,p1,p2, undone for every non-equirectangular camera, :635-654); camera_type int [C,1] | None (all
+    perspective): per-type direction models :665-697.
     -> origins [N,3], directions [N,3], pixel_area [N,1], directions_norm [N,1], times [N,1] | None."""
     y = y_idx.float() + pixel_offset  # get_image_coords(pixel_offset=0.5), cameras.py:299-326
     x = x_idx.float() + pixel_offset
@@ -704,7 +736,21 @@ def generate_rays(c2w, fx, fy, cx, cy, cam_times, cam_idx, y_idx, x_idx, pixel_o
     coord_x = torch.stack([(x - cx_ + 1) / fx_, -(y - cy_) / fy_], -1)
     coord_y = torch.stack([(x - cx_) / fx_, -(y - cy_ + 1) / fy_], -1)
     coord_stack = torch.stack([coord, coord_x, coord_y], dim=0)  # [3,N,2]
+    ctype = None if camera_type is None else camera_type.reshape(-1)[cam_idx]  # [N]
+    if distortion_params is not None:
+        und = undistort(coord_stack, distortion_params[cam_idx][None])
+        keep = None if ctype is None else (ctype == CAMERA_EQUIRECTANGULAR)
+        coord_stack = und if keep is None else torch.where(keep[None, :, None], coord_stack, und)
     dirs = torch.cat([coord_stack, -torch.ones_like(coord_stack[..., :1])], dim=-1)  # perspective: (u, v, -1), :665-670
+    if ctype is not None:
+        theta = torch.clip(torch.sqrt(torch.sum(coord_stack**2, dim=-1)), 0.0, math.pi)  # fisheye, :672-683
+        st = torch.sin(theta)
+        fish = torch.stack([coord_stack[..., 0] * st / theta, coord_stack[..., 1] * st / theta, -torch.cos(theta)], dim=-1)
+        lon = -torch.pi * coord_stack[..., 0]  # equirectangular, :685-697
+        lat = torch.pi * (0.5 - coord_stack[..., 1])
+        equi = torch.stack([-torch.sin(lon) * torch.sin(lat), torch.cos(lat), -torch.cos(lon) * torch.sin(lat)], dim=-1)
+        sel = ctype[None, :, None]
+        dirs = torch.where(sel == CAMERA_FISHEYE, fish, torch.where(sel == CAMERA_EQUIRECTANGULAR, equi, dirs))
     c2w_r = c2w[cam_idx]  # [N,3,4]
     rotation = c2w_r[..., :3, :3]
     dirs = torch.sum(dirs[..., None, :] * rotation, dim=-1)  # :708-710

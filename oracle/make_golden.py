@@ -434,6 +434,7 @@ def main():
     gen_model(R)
     gen_importance(R)
     gen_raygen(R)
+    gen_raygen_lens(R)
     gen_samplers_cfg4(R)
     gen_field_variants(R)
 
@@ -535,6 +536,59 @@ def gen_raygen(R):
          directions_norm=rb.metadata["directions_norm"], frame_cam=torch.tensor(3),
          frame_origins=frame.origins, frame_directions=frame.directions, frame_pixel_area=frame.pixel_area,
          frame_times=frame.times, frame_directions_norm=frame.metadata["directions_norm"])
+
+
+def gen_raygen_lens(R):
+    """(f2) the lens models of the reference's Cameras (cameras.py:635-697): OpenCV radial + tangential distortion undone
+    by camera_utils.radial_and_tangential_undistort, fisheye and equirectangular direction models, mixed in ONE camera
+    batch the way the reference's per-ray masks allow; also disable_distortion=True and a batch that is perspective with
+    distortion only (what the dataparsers build from k1..p2 of transforms.json, broadcaststyle_dataparser.py:481-509)."""
+    from nerfstudio.cameras.cameras import Cameras, CameraType
+
+    g = torch.Generator().manual_seed(808)
+    n_cams, h, w = 6, 40, 72
+    rot = torch.linalg.qr(torch.randn(n_cams, 3, 3, generator=g)).Q
+    rot = rot * torch.sign(torch.linalg.det(rot))[:, None, None]
+    pos = torch.randn(n_cams, 3, 1, generator=g) * 2.0
+    c2w = torch.cat([rot, pos], dim=-1).float()
+    fx = 50.0 + 20.0 * torch.rand(n_cams, 1, generator=g)
+    fy = 50.0 + 20.0 * torch.rand(n_cams, 1, generator=g)
+    cx = w / 2 + torch.randn(n_cams, 1, generator=g)
+    cy = h / 2 + torch.randn(n_cams, 1, generator=g)
+    # camera 5 is equirectangular: fx = fy = height = width / 2 (cameras.py:689)
+    fx[5], fy[5], cx[5], cy[5] = h, h, w / 2, h / 2
+    times = torch.rand(n_cams, 1, generator=g)
+    types = torch.tensor([[CameraType.PERSPECTIVE.value], [CameraType.FISHEYE.value], [CameraType.PERSPECTIVE.value],
+                          [CameraType.FISHEYE.value], [CameraType.PERSPECTIVE.value], [CameraType.EQUIRECTANGULAR.value]])
+    # k1, k2, k3, k4, p1, p2: broadcast-camera magnitudes, one camera with zeros, one strong enough that |det| crosses eps
+    dist = torch.tensor([[-0.12, 0.03, -0.004, 0.0005, 0.002, -0.001],
+                         [0.05, -0.01, 0.002, 0.0, 0.0, 0.0],
+                         [0.0, 0.0, 0.0, 0.0, 0.0, 0.0],
+                         [-0.2, 0.05, 0.0, 0.0, -0.003, 0.004],
+                         [-0.9, 0.3, 0.0, 0.0, 0.01, 0.01],
+                         [0.1, 0.1, 0.1, 0.1, 0.1, 0.1]])
+    cams = Cameras(camera_to_worlds=c2w, fx=fx, fy=fy, cx=cx, cy=cy, width=w, height=h, times=times,
+                   distortion_params=dist, camera_type=types)
+    n = 311
+    ray_indices = torch.stack([torch.randint(0, n_cams, (n,), generator=g), torch.randint(0, h, (n,), generator=g),
+                               torch.randint(0, w, (n,), generator=g)], dim=-1)
+    coords = cams.get_image_coords()[ray_indices[:, 1], ray_indices[:, 2]]
+    rb = cams.generate_rays(camera_indices=ray_indices[:, 0].unsqueeze(-1), coords=coords)
+    rb_off = cams.generate_rays(camera_indices=ray_indices[:, 0].unsqueeze(-1), coords=coords, disable_distortion=True)
+    out = dict(c2w=c2w, fx=fx, fy=fy, cx=cx, cy=cy, times=times, hw=torch.tensor([h, w]), types=types, dist=dist,
+               ray_indices=ray_indices, origins=rb.origins, directions=rb.directions, pixel_area=rb.pixel_area,
+               ray_times=rb.times, directions_norm=rb.metadata["directions_norm"],
+               nodist_directions=rb_off.directions, nodist_pixel_area=rb_off.pixel_area)
+    for cam in (0, 3, 4, 5):  # whole frames: distorted perspective, distorted fisheye, strong distortion, equirectangular
+        fr = cams.generate_rays(camera_indices=cam, keep_shape=True)
+        out[f"frame{cam}_directions"], out[f"frame{cam}_pixel_area"] = fr.directions, fr.pixel_area
+        out[f"frame{cam}_directions_norm"] = fr.metadata["directions_norm"]
+    # what the dataparsers build: perspective cameras sharing ONE distortion row
+    persp = Cameras(camera_to_worlds=c2w, fx=fx, fy=fy, cx=cx, cy=cy, width=w, height=h, times=times,
+                    distortion_params=dist[0], camera_type=CameraType.PERSPECTIVE)
+    rbp = persp.generate_rays(camera_indices=ray_indices[:, 0].unsqueeze(-1), coords=coords)
+    out["persp_directions"], out["persp_pixel_area"] = rbp.directions, rbp.pixel_area
+    save("raygen_lens", **out)
 
 
 def gen_samplers_cfg4(R):

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkplanes_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 LAUNCH_COUNT = 0  # number of C-ABI kernel-launching calls made (bench.py reports it as gpu_launches evidence)
@@ -76,7 +76,7 @@ SIGNATURES = {
     "kp_step_scalars": ([_P, _P, _P, c_int64, c_int, POINTER(c_float), c_float, _P, _P, _P], c_int),
     "kp_adam_multi": ([_P, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P, _P], c_int),
     "kp_adam_step": ([_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P], c_int),
-    "kp_generate_rays": ([_P, _P, _P, c_int, _P, c_int, c_int, c_int64, c_int64, c_float, _P, _P, _P, _P, _P, _P], c_int),
+    "kp_generate_rays": ([_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int64, c_int64, c_float, _P, _P, _P, _P, _P, _P], c_int),
     "kp_ist_map": ([_P, c_int, c_int64, _P, _P, c_float, _P, _P], c_int),
     "kp_isg_map": ([_P, c_int, c_int64, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P], c_int),
     "kp_loss_head_fwd": ([_P, _P, c_int64, _P, _P, _P, c_int, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P, _P], c_int),

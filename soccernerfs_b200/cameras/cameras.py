@@ -1,18 +1,22 @@
-"""Cameras: the subset of NS/cameras/cameras.py the K-Planes path's callers use -- a flat batch of PERSPECTIVE cameras
-without lens distortion -- with ray generation on the device (``kp_generate_rays``).
+"""Cameras: the subset of NS/cameras/cameras.py the K-Planes path's callers use -- a flat batch of perspective,
+fisheye or equirectangular cameras (mixed types allowed) with optional OpenCV lens distortion, as the reference's
+dataparsers build them (broadcaststyle_dataparser.py:465-509) -- with ray generation on the device
+(``kp_generate_rays``).
 
 Same constructor argument names, attribute names (``camera_to_worlds, fx, fy, cx, cy, width, height, times``) and
 ``generate_rays`` call forms as the reference (cameras.py:38-120, 327-502):
   * ``generate_rays(camera_indices=c[:, None], coords=coords)`` -- RayGenerator.forward, ray_generators.py:43-59
   * ``generate_rays(camera_indices=i, keep_shape=True)``          -- a whole frame (scripts/render.py, eval)
 plus ``generate_tile(camera_index, start, end)`` (a row-major pixel range of a frame without materialising coords).
-Fisheye / equirectangular cameras, non-zero distortion parameters, camera-optimizer deltas and multi-dimensional
-camera batches are not built: they raise NotImplementedError instead of taking another route.
+All-zero distortion parameters are dropped at construction: the reference's Newton iteration leaves such points
+unchanged bit for bit (residual 0, step 0), so those cameras take the plain perspective kernel.  Camera-optimizer
+deltas (``camera_opt_to_camera``, ``distortion_params_delta``) and multi-dimensional camera batches are not built: they
+raise NotImplementedError instead of taking another route.
 """
 from __future__ import annotations
 
 from enum import Enum, auto
-from typing import Optional, Union
+from typing import List, Optional, Union
 
 import torch
 
@@ -45,16 +49,10 @@ class Cameras:
             c2w = c2w[None]
         if c2w.dim() != 3 or c2w.shape[-2:] != (3, 4):
             raise NotImplementedError("Cameras: a flat batch [num_cameras, 3, 4] of camera-to-world matrices is supported")
-        if isinstance(camera_type, CameraType):
-            if camera_type != CameraType.PERSPECTIVE:
-                raise NotImplementedError(f"camera type {camera_type} is not built (perspective only)")
-        elif torch.is_tensor(camera_type):
-            if bool((camera_type != CameraType.PERSPECTIVE.value).any()):
-                raise NotImplementedError("non-perspective cameras are not built")
-        if distortion_params is not None and bool((distortion_params != 0).any()):
-            raise NotImplementedError("lens distortion is not built (all distortion parameters must be zero)")
         dev = c2w.device
         n = c2w.shape[0]
+        self.camera_type = self._parse_camera_type(camera_type, n, dev)
+        self.distortion_params = self._parse_distortion(distortion_params, n, dev)
         self.camera_to_worlds = c2w.float().contiguous()
         self.fx, self.fy, self.cx, self.cy = (_col(v, n, dev) for v in (fx, fy, cx, cy))
         h = height if height is not None else (self.cy * 2).to(torch.int64)
@@ -62,9 +60,53 @@ class Cameras:
         self.height, self.width = _col(h, n, dev, torch.int64), _col(w, n, dev, torch.int64)
         self.times = None if times is None else times.to(dev).float().reshape(n, 1).contiguous()
         self.ids = ids
-        self.distortion_params = None
-        self.camera_type = torch.full((n, 1), CameraType.PERSPECTIVE.value, dtype=torch.int64, device=dev)
         self._intrinsics = None
+        # what the kernel takes: NULL for "all perspective" / "no distortion" (the plain kernel), else per-camera tables
+        plain = bool((self.camera_type == CameraType.PERSPECTIVE.value).all())
+        self._cam_types = None if plain else self.camera_type.view(-1).to(torch.int32).contiguous()
+        self._distortion = self.distortion_params
+
+    @staticmethod
+    def _parse_camera_type(camera_type, n: int, dev) -> torch.Tensor:
+        """cameras.py:178-218: CameraType | List[CameraType] | int | integer tensor -> int64 [n,1]; values outside the
+        enum raise like the reference does at ray generation (cameras.py:699-701)."""
+        if isinstance(camera_type, CameraType):
+            t = torch.tensor([camera_type.value])
+        elif isinstance(camera_type, (list, tuple)) and len(camera_type) and isinstance(camera_type[0], CameraType):
+            t = torch.tensor([c.value for c in camera_type])
+        elif isinstance(camera_type, int):
+            t = torch.tensor([camera_type])
+        elif torch.is_tensor(camera_type):
+            if torch.is_floating_point(camera_type):
+                raise AssertionError(f"camera_type tensor must be of type int, not: {camera_type.dtype}")
+            t = camera_type
+        else:
+            raise ValueError('Invalid camera_type. Must be CameraType, List[CameraType], int, or torch.Tensor["num_cameras"]. '
+                             "Received: " + str(type(camera_type)))
+        t = t.reshape(-1, 1).to(device=dev, dtype=torch.int64)
+        if t.shape[0] not in (1, n):
+            raise ValueError(f"camera_type has {t.shape[0]} entries for {n} cameras")
+        t = t.expand(n, 1).contiguous()
+        valid = [c.value for c in CameraType]
+        for v in torch.unique(t.cpu()).tolist():
+            if v not in valid:
+                raise ValueError(f"Camera type {v} not supported.")
+        return t
+
+    @staticmethod
+    def _parse_distortion(distortion_params, n: int, dev) -> Optional[torch.Tensor]:
+        """[6] or [n,6] OpenCV (k1,k2,k3,k4,p1,p2), camera_utils.get_distortion_params order -> fp32 [n,6] | None."""
+        if distortion_params is None:
+            return None
+        d = torch.as_tensor(distortion_params, dtype=torch.float32)
+        if d.shape[-1] != 6 or d.dim() > 2:
+            raise ValueError("distortion_params must be [6] or [num_cameras, 6] (k1, k2, k3, k4, p1, p2)")
+        d = d.reshape(-1, 6)
+        if d.shape[0] not in (1, n):
+            raise ValueError(f"distortion_params has {d.shape[0]} rows for {n} cameras")
+        if not bool((d != 0).any()):
+            return None
+        return d.expand(n, 6).to(dev).contiguous()
 
     # -- bookkeeping -----------------------------------------------------------------------------------
     @property
@@ -92,7 +134,8 @@ class Cameras:
 
     def to(self, device) -> "Cameras":
         out = Cameras(self.camera_to_worlds.to(device), self.fx.to(device), self.fy.to(device), self.cx.to(device),
-                      self.cy.to(device), self.width.to(device), self.height.to(device), times=self.times, ids=self.ids)
+                      self.cy.to(device), self.width.to(device), self.height.to(device),
+                      distortion_params=self.distortion_params, camera_type=self.camera_type, times=self.times, ids=self.ids)
         return out
 
     def get_image_coords(self, pixel_offset: float = 0.5, index=None) -> torch.Tensor:
@@ -103,6 +146,10 @@ class Cameras:
             h, w = int(self.height[index]), int(self.width[index])
         yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
         return torch.stack([yy, xx], dim=-1) + pixel_offset
+
+    def _lens(self, disable_distortion: bool) -> Optional[torch.Tensor]:
+        """cameras.py:636: ``disable_distortion`` skips the undistortion, not the camera-type direction model."""
+        return None if disable_distortion else self._distortion
 
     def _packed_intrinsics(self) -> torch.Tensor:
         if self._intrinsics is None:
@@ -132,7 +179,7 @@ class Cameras:
             cam = camera_indices
             if coords is None:  # the whole frame of one camera, [H,W] rays (cameras.py:405-440 case 1)
                 h, w = int(self.height[cam]), int(self.width[cam])
-                rb = self.generate_tile(cam, 0, h * w, aabb_box=aabb_box)
+                rb = self.generate_tile(cam, 0, h * w, aabb_box=aabb_box, disable_distortion=disable_distortion)
                 return rb.reshape((h, w)) if keep_shape in (None, True) else rb
             camera_indices = torch.full((*coords.shape[:-1], 1), cam, dtype=torch.int64, device=coords.device)
         if coords is None:
@@ -147,7 +194,8 @@ class Cameras:
         if not bool(((coords.to(dev).reshape(-1, 2) - yx) == 0.5).all()):
             raise NotImplementedError("generate_rays: coords must be pixel centres (integer + 0.5)")
         tri = torch.cat([camera_indices.to(dev).reshape(-1, 1).to(torch.int64), yx], dim=-1).contiguous()
-        out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, ray_indices=tri)
+        out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, ray_indices=tri,
+                                distortion=self._lens(disable_distortion), cam_types=self._cam_types)
         return self._bundle(out, camera_indices.to(dev), shape, aabb_box)
 
     def generate_rays_from_indices(self, ray_indices: torch.Tensor, aabb_box: Optional[SceneBox] = None) -> RayBundle:
@@ -163,13 +211,16 @@ class Cameras:
             if bool((row < 0).any() or (col < 0).any() or (row >= h).any() or (col >= w).any()):
                 raise IndexError("pixel index outside its camera's image")
         tri = ray_indices.to(self.device).to(torch.int64).contiguous()
-        out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, ray_indices=tri)
+        out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, ray_indices=tri,
+                                distortion=self._distortion, cam_types=self._cam_types)
         return self._bundle(out, tri[:, 0:1], (tri.shape[0],), aabb_box)
 
-    def generate_tile(self, camera_index: int, start: int, end: int, aabb_box: Optional[SceneBox] = None) -> RayBundle:
+    def generate_tile(self, camera_index: int, start: int, end: int, aabb_box: Optional[SceneBox] = None,
+                      disable_distortion: bool = False) -> RayBundle:
         """Rays of the row-major pixels [start, end) of one camera's frame (flat)."""
         w = int(self.width[camera_index])
         out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, cam=int(camera_index), width=w,
-                                first_pixel=int(start), n=int(end - start))
+                                first_pixel=int(start), n=int(end - start), distortion=self._lens(disable_distortion),
+                                cam_types=self._cam_types)
         ci = torch.full((end - start, 1), int(camera_index), dtype=torch.int64, device=self.device)
         return self._bundle(out, ci, (end - start,), aabb_box)

@@ -746,10 +746,12 @@ def _reg_tables(planes, terms):
 
 def generate_rays(c2w: torch.Tensor, intrinsics: torch.Tensor, cam_times: Optional[torch.Tensor],
                   ray_indices: Optional[torch.Tensor] = None, cam: int = 0, width: int = 1, first_pixel: int = 0,
-                  n: Optional[int] = None, pixel_offset: float = 0.5):
-    """Pixel -> ray generation (cameras.py:505-741, perspective / undistorted).  Either ``ray_indices`` int64 [N,3]
-    (camera,row,col) or a row-major pixel range of camera ``cam``.  -> origins [N,3], directions [N,3], pixel_area [N],
-    directions_norm [N], times [N] | None."""
+                  n: Optional[int] = None, pixel_offset: float = 0.5, distortion: Optional[torch.Tensor] = None,
+                  cam_types: Optional[torch.Tensor] = None):
+    """Pixel -> ray generation (cameras.py:505-741).  Either ``ray_indices`` int64 [N,3] (camera,row,col) or a row-major
+    pixel range of camera ``cam``.  ``distortion`` fp32 [n_cams,6] (OpenCV k1..k4,p1,p2) and ``cam_types`` int32 [n_cams]
+    (CameraType values) select the lens kernel; both None = undistorted perspective cameras.
+    -> origins [N,3], directions [N,3], pixel_area [N], directions_norm [N], times [N] | None."""
     c2w_c, intr = f32c(c2w), f32c(intrinsics)
     if ray_indices is not None:
         if ray_indices.dtype != torch.int64 or not ray_indices.is_contiguous():
@@ -762,7 +764,15 @@ def generate_rays(c2w: torch.Tensor, intrinsics: torch.Tensor, cam_times: Option
     norm = torch.empty((n,), dtype=torch.float32, device=dev)
     times = None if cam_times is None else torch.empty((n,), dtype=torch.float32, device=dev)
     ct = None if cam_times is None else f32c(cam_times).view(-1)
-    call("kp_generate_rays", ptr(c2w_c), ptr(intr), ptr(ct), c2w_c.shape[0], ptr(ray_indices), int(cam), int(width),
+    n_cams = c2w_c.shape[0]
+    if distortion is not None:
+        distortion = f32c(distortion)
+        if tuple(distortion.shape) != (n_cams, 6) or distortion.device != dev:
+            raise ValueError(f"generate_rays: distortion must be [{n_cams}, 6] on {dev}")
+    if cam_types is not None:
+        if cam_types.dtype != torch.int32 or not cam_types.is_contiguous() or cam_types.numel() != n_cams or cam_types.device != dev:
+            raise ValueError(f"generate_rays: cam_types must be contiguous int32 [{n_cams}] on {dev}")
+    call("kp_generate_rays", ptr(c2w_c), ptr(intr), ptr(ct), ptr(distortion), ptr(cam_types), n_cams, ptr(ray_indices), int(cam), int(width),
          int(first_pixel), int(n), float(pixel_offset), ptr(origins), ptr(directions), ptr(pixel_area), ptr(norm), ptr(times),
          stream_ptr())
     return origins, directions, pixel_area, norm, times

@@ -26,7 +26,7 @@ def test_library_loaded_and_abi():
     from soccernerfs_b200 import _lib
 
     lib = _lib.load()
-    assert lib.kp_abi_version() == 3
+    assert lib.kp_abi_version() == 4
 
 
 def test_hexplane_vs_reference_fixture():
@@ -606,8 +606,56 @@ def test_ray_generation_vs_reference_fixture():
     # fraction of bit-identical direction components (the arithmetic follows the reference's order)
     same = (frame.directions.cpu() == g["frame_directions"]).float().mean()
     assert same > 0.9, float(same)
-    with pytest.raises(NotImplementedError):
-        Cameras(g["c2w"], 50.0, 50.0, 32.0, 18.0, w, h, distortion_params=torch.ones(5, 6))
+
+
+def test_lens_ray_generation_vs_reference_fixture():
+    """(f2) kp_generate_rays' lens kernel vs rays of the reference's own Cameras (fixture raygen_lens): OpenCV distortion
+    undone by 10 Newton iterations, fisheye and equirectangular direction models, the three camera types mixed in one
+    batch; explicit triplets, whole frames through the tile form, disable_distortion, and the dataparsers' perspective
+    batch with one shared distortion row.  The undistortion is rounded operation by operation in the reference's order,
+    so perspective rays differ from the reference only where the plain kernel's do (rotation sum / norm); sin / cos of
+    the fisheye and equirectangular models are CUDA's instead of the host libm's."""
+    from soccernerfs_b200.cameras.cameras import Cameras, CameraType
+
+    g = load_golden("raygen_lens")
+    h, w = (int(v) for v in g["hw"])
+    args = [g[k].to(DEV) for k in ("c2w", "fx", "fy", "cx", "cy")]
+    cams = Cameras(*args, w, h, times=g["times"].to(DEV), distortion_params=g["dist"], camera_type=g["types"])
+    ri = g["ray_indices"].to(DEV)
+    coords = cams.get_image_coords().to(DEV)[ri[:, 1], ri[:, 2]]
+    for rb in (cams.generate_rays_from_indices(ri), cams.generate_rays(camera_indices=ri[:, 0:1], coords=coords)):
+        assert torch.equal(rb.origins.cpu(), g["origins"]) and torch.equal(rb.times.cpu(), g["ray_times"])
+        assert rel_err(rb.directions.cpu(), g["directions"]) < 1e-6
+        assert rel_err(rb.pixel_area.cpu(), g["pixel_area"]) < 1e-5
+        assert rel_err(rb.metadata["directions_norm"].cpu(), g["directions_norm"]) < 1e-6
+    rb = cams.generate_rays(camera_indices=ri[:, 0:1], coords=coords, disable_distortion=True)
+    assert rel_err(rb.directions.cpu(), g["nodist_directions"]) < 1e-6 and rel_err(rb.pixel_area.cpu(), g["nodist_pixel_area"]) < 1e-5
+    for c in (0, 3, 4, 5):
+        frame = cams.generate_rays(camera_indices=c, keep_shape=True)
+        assert frame.directions.shape == (h, w, 3)
+        assert rel_err(frame.directions.cpu(), g[f"frame{c}_directions"]) < 1e-6, c
+        assert rel_err(frame.metadata["directions_norm"].cpu(), g[f"frame{c}_directions_norm"]) < 1e-6, c
+        ref = g[f"frame{c}_pixel_area"]
+        assert rel_err(frame.pixel_area.cpu(), ref) < 1e-5, c  # the bar's norm (max error / max value)
+        # stricter than the bar, per element: a product of two differences of unit vectors, 1e-2 each, so a 1-ulp
+        # direction difference is 1e-5 of it (measured 1.5e-5 with the kernel body compiled for the host)
+        assert ((frame.pixel_area.cpu() - ref).abs() / ref.abs().clamp_min(1e-12)).max() < 2e-4, c
+    persp = Cameras(*args, w, h, times=g["times"].to(DEV), distortion_params=g["dist"][0], camera_type=CameraType.PERSPECTIVE)
+    assert persp._cam_types is None and persp._distortion is not None
+    rb = persp.generate_rays_from_indices(ri)
+    assert rel_err(rb.directions.cpu(), g["persp_directions"]) < 1e-6 and rel_err(rb.pixel_area.cpu(), g["persp_pixel_area"]) < 1e-5
+    same = (rb.directions.cpu() == g["persp_directions"]).float().mean()
+    assert same > 0.85, float(same)
+    # an all-zero distortion table and all-perspective types are the plain kernel: bit-identical rays
+    g0 = load_golden("raygen")
+    a0 = [g0[k].to(DEV) for k in ("c2w", "fx", "fy", "cx", "cy")]
+    h0, w0 = (int(v) for v in g0["hw"])
+    plain = Cameras(*a0, w0, h0, times=g0["times"].to(DEV))
+    tiny = Cameras(*a0, w0, h0, times=g0["times"].to(DEV), distortion_params=torch.full((6,), 1e-30),
+                   camera_type=torch.ones(5, 1, dtype=torch.int64))
+    assert tiny._distortion is not None
+    ra, rb = plain.generate_rays_from_indices(g0["ray_indices"].to(DEV)), tiny.generate_rays_from_indices(g0["ray_indices"].to(DEV))
+    assert torch.equal(ra.directions, rb.directions) and torch.equal(ra.pixel_area, rb.pixel_area)
 
 
 def test_depth_supervision_goes_through_every_sampling_level():

@@ -174,7 +174,9 @@ def test_reference_checkpoint_round_trip():
 
 
 def test_cameras_reject_unsupported_and_out_of_range():
-    """cameras/cameras.py host-side contract: only undistorted perspective cameras; host indices are range-checked."""
+    """cameras/cameras.py host-side contract: camera types / distortion parsed like cameras.py:178-218 (all-zero
+    distortion and all-perspective batches select the plain kernel), camera-optimizer deltas rejected, host indices
+    range-checked."""
     import pytest
     import torch
 
@@ -184,11 +186,30 @@ def test_cameras_reject_unsupported_and_out_of_range():
     cams = Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, times=torch.tensor([0.1, 0.2]))
     assert cams.shape == (2,) and len(cams) == 2 and cams.get_image_coords().shape == (36, 64, 2)
     assert float(cams.get_image_coords()[3, 5, 0]) == 3.5 and float(cams.get_image_coords()[3, 5, 1]) == 5.5
+    assert cams._cam_types is None and cams._distortion is None  # the plain perspective kernel
+    assert torch.equal(cams.camera_type, torch.ones(2, 1, dtype=torch.int64))
+    fish = Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, camera_type=CameraType.FISHEYE)
+    assert fish._cam_types.dtype == torch.int32 and fish._cam_types.tolist() == [2, 2] and fish._distortion is None
+    mixed = Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, camera_type=[CameraType.PERSPECTIVE, CameraType.EQUIRECTANGULAR],
+                    distortion_params=torch.tensor([0.1, 0, 0, 0, 0, 0.01]))  # one row shared by all cameras
+    assert mixed._cam_types.tolist() == [1, 3] and mixed.distortion_params.shape == (2, 6)
+    assert mixed._lens(disable_distortion=True) is None and mixed._lens(False) is mixed._distortion
+    for ct in (torch.tensor([1, 2]), torch.tensor([[1], [2]]), 2):
+        assert Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, camera_type=ct).camera_type.shape == (2, 1)
+    zero = Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, distortion_params=torch.zeros(2, 6))
+    assert zero.distortion_params is None  # Newton on an all-zero model is the identity: dropped
+    with pytest.raises(ValueError):
+        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, camera_type=torch.tensor([1, 7]))  # cameras.py:699-701
+    with pytest.raises(AssertionError):
+        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, camera_type=torch.tensor([1.0, 2.0]))  # cameras.py:203-205
+    with pytest.raises(ValueError):
+        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, camera_type="fisheye")
+    with pytest.raises(ValueError):
+        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, distortion_params=torch.ones(2, 4))
+    with pytest.raises(ValueError):
+        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, distortion_params=torch.ones(3, 6))
     with pytest.raises(NotImplementedError):
-        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, camera_type=CameraType.FISHEYE)
-    with pytest.raises(NotImplementedError):
-        Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, distortion_params=torch.full((2, 6), 0.1))
-    Cameras(c2w, 50.0, 50.0, 32.0, 18.0, 64, 36, distortion_params=torch.zeros(2, 6))  # all-zero distortion is fine
+        cams.generate_rays(camera_indices=0, coords=torch.tensor([[0.5, 0.5]]), distortion_params_delta=torch.zeros(1, 6))
     with pytest.raises(IndexError):
         cams.generate_rays_from_indices(torch.tensor([[2, 0, 0]]))
     with pytest.raises(IndexError):

@@ -157,6 +157,46 @@ def test_ray_generation_matches_reference():
     assert rel_err(pa.view(h, w, 1), g["frame_pixel_area"]) < 1e-5
 
 
+def test_lens_models_match_reference():
+    """(f2) OpenCV undistortion (camera_utils.py:298-401) and the fisheye / equirectangular direction models
+    (cameras.py:665-697), mixed in one camera batch, vs rays of the reference's own Cameras (fixture raygen_lens);
+    disable_distortion and the dataparsers' shared-distortion perspective batch included.  The restatement evaluates
+    the reference's expressions in the reference's order: bit-identical on the CPU."""
+    g = load_golden("raygen_lens")
+    cam = (g["c2w"], g["fx"], g["fy"], g["cx"], g["cy"], g["times"])
+    ri = g["ray_indices"]
+    idx = (ri[:, 0], ri[:, 1], ri[:, 2])
+    assert set(g["types"].reshape(-1).tolist()) == {1, 2, 3}
+    o, d, pa, nrm, t = ko.generate_rays(*cam, *idx, distortion_params=g["dist"], camera_type=g["types"])
+    assert torch.equal(o, g["origins"]) and torch.equal(t, g["ray_times"])
+    assert torch.equal(d, g["directions"]) and torch.equal(pa, g["pixel_area"]) and torch.equal(nrm, g["directions_norm"])
+    _, d, pa, _, _ = ko.generate_rays(*cam, *idx, camera_type=g["types"])  # disable_distortion=True, cameras.py:636
+    assert torch.equal(d, g["nodist_directions"]) and torch.equal(pa, g["nodist_pixel_area"])
+    assert not torch.equal(g["nodist_directions"], g["directions"])
+    _, d, pa, _, _ = ko.generate_rays(*cam, *idx, distortion_params=g["dist"][0:1].expand(6, 6))
+    assert torch.equal(d, g["persp_directions"]) and torch.equal(pa, g["persp_pixel_area"])
+    h, w = (int(v) for v in g["hw"])
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    for c in (0, 3, 4, 5):
+        ci = torch.full((h * w,), c, dtype=torch.int64)
+        _, d, pa, nrm, _ = ko.generate_rays(*cam, ci, yy.reshape(-1), xx.reshape(-1), distortion_params=g["dist"],
+                                            camera_type=g["types"])
+        assert torch.equal(d.view(h, w, 3), g[f"frame{c}_directions"]), c
+        assert torch.equal(pa.view(h, w, 1), g[f"frame{c}_pixel_area"]), c
+        assert torch.equal(nrm.view(h, w, 1), g[f"frame{c}_directions_norm"]), c
+    # zero distortion: the Newton step is exactly zero (the reason Cameras drops an all-zero table)
+    pts = torch.randn(64, 2, generator=torch.Generator().manual_seed(3))
+    assert torch.equal(ko.undistort(pts, torch.zeros(1, 6)), pts)
+    # and undistortion inverts the OpenCV forward model where it converges (mild distortion, points inside the frame)
+    k = g["dist"][0]
+    und = ko.undistort(0.4 * pts.clamp(-1, 1), k[None])
+    x, y = und[:, 0], und[:, 1]
+    r = x * x + y * y
+    dd = 1.0 + r * (k[0] + r * (k[1] + r * (k[2] + r * k[3])))
+    fwd = torch.stack([dd * x + 2 * k[4] * x * y + k[5] * (r + 2 * x * x), dd * y + 2 * k[5] * x * y + k[4] * (r + 2 * y * y)], -1)
+    assert (fwd - 0.4 * pts.clamp(-1, 1)).abs().max() < 1e-6
+
+
 def test_cfg4_piecewise_single_jitter_samplers_match_reference():
     """BASELINE config 4: UniformLinDispPiecewiseSampler + PDFSampler with single_jitter=True and the expected-depth
     renderer, vs the reference's own classes (fixture samplers_cfg4)."""
