@@ -134,6 +134,13 @@ int kp_decoder_fwd_fused(const float* feats, int K0, const float* directions /* 
 int kp_aabb_intersect(const float* origins, const float* directions, int64_t N, const float* aabb_host6,
                       float near_plane, float* nears, float* fars, void* stream);
 
+/* ---- (f2) nerfstudio.utils.math._intersect_aabb, NS/utils/math.py:201-238 (max_bound = invalid_value = 1e10), what
+ *      Cameras.generate_rays(aabb_box=...) fills RayBundle.nears / fars with for a crop-box render
+ *      (NS/cameras/cameras.py:478-497, scripts/render.py:101-106).  aabb_host6 = x,y,z min then max (HOST).
+ *      Bit-identical to the reference's torch ops, NaN propagation of torch.min / max / clamp included. ---- */
+int kp_intersect_aabb(const float* origins, const float* directions, int64_t N, const float* aabb_host6,
+                      float* t_min, float* t_max, void* stream);
+
 /* ---- (a7) SpacedSampler / UniformSampler, NS/model_components/ray_samplers.py:79-126.
  *      lin_bins [S+1] = torch.linspace(0,1,S+1) (device).  t_rand [N,S+1] or [N,1] (rand_stride 0)
  *      or NULL (eval).  spacing: 0 uniform (x), 1 UniformLinDispPiecewise (ray_samplers.py:236-246).

@@ -718,6 +718,20 @@ def undistort(coords: torch.Tensor, k: torch.Tensor, eps: float = 1e-3, max_iter
     return torch.stack([x, y], dim=-1)
 
 
+def intersect_aabb(origins: torch.Tensor, directions: torch.Tensor, aabb6: torch.Tensor):
+    """nerfstudio.utils.math._intersect_aabb (NS/utils/math.py:201-238) with intersect_aabb's constants (:267-270,
+    max_bound = invalid_value = 1e10): what Cameras.generate_rays(aabb_box=...) stores as nears / fars
+    (cameras.py:478-497).  origins / directions [N,3], aabb6 [6] = min then max -> t_min [N], t_max [N]."""
+    tx_min = (aabb6[:3] - origins) / directions
+    tx_max = (aabb6[3:] - origins) / directions
+    t_min = torch.max(torch.min(tx_min, tx_max), dim=-1).values
+    t_max = torch.min(torch.max(tx_min, tx_max), dim=-1).values
+    t_min = torch.clamp(t_min, min=0, max=1e10)
+    t_max = torch.clamp(t_max, min=0, max=1e10)
+    miss = t_max <= t_min
+    return torch.where(miss, 1e10, t_min), torch.where(miss, 1e10, t_max)
+
+
 CAMERA_PERSPECTIVE, CAMERA_FISHEYE, CAMERA_EQUIRECTANGULAR = 1, 2, 3  # CameraType, NS/cameras/cameras.py:42-47
 
 

@@ -435,6 +435,7 @@ def main():
     gen_importance(R)
     gen_raygen(R)
     gen_raygen_lens(R)
+    gen_raygen_crop(R)
     gen_samplers_cfg4(R)
     gen_field_variants(R)
 
@@ -589,6 +590,46 @@ def gen_raygen_lens(R):
     rbp = persp.generate_rays(camera_indices=ray_indices[:, 0].unsqueeze(-1), coords=coords)
     out["persp_directions"], out["persp_pixel_area"] = rbp.directions, rbp.pixel_area
     save("raygen_lens", **out)
+
+
+def gen_raygen_crop(R):
+    """(f2) crop-box rendering (scripts/render.py:101-106): Cameras.generate_rays(camera_indices=i, aabb_box=SceneBox)
+    stores nears / fars from nerfstudio.utils.math.intersect_aabb (cameras.py:478-497; nerfacc is absent, so its
+    _intersect_aabb branch runs, math.py:260-270) -- one whole frame of the raygen fixture's cameras against a box most
+    rays miss, and the function alone on rays built to hit every branch (axis-parallel directions with 0 components,
+    origins inside the box, on a face, rays pointing away, a 0/0 slab)."""
+    from nerfstudio.cameras.cameras import Cameras
+    from nerfstudio.data.scene_box import SceneBox
+    from nerfstudio.utils import math as ns_math
+
+    g0 = np.load(os.path.join(OUT, "raygen.npz"))
+    t = {k: torch.from_numpy(g0[k]) for k in ("c2w", "fx", "fy", "cx", "cy", "times")}
+    h, w = (int(v) for v in g0["hw"])
+    cams = Cameras(camera_to_worlds=t["c2w"], fx=t["fx"], fy=t["fy"], cx=t["cx"], cy=t["cy"], width=w, height=h, times=t["times"])
+    cam = int(g0["frame_cam"])
+    o, d = torch.from_numpy(g0["frame_origins"])[0, 0], torch.from_numpy(g0["frame_directions"])
+    centre = o + 3.0 * d[h // 2, w // 3]  # a box in front of the camera, off the optical axis
+    box = torch.stack([centre - torch.tensor([0.9, 0.7, 0.8]), centre + torch.tensor([0.9, 0.7, 0.8])])
+    frame = cams.generate_rays(camera_indices=cam, aabb_box=SceneBox(aabb=box))
+    assert frame.nears.shape == (h, w, 1)
+    hit = (frame.nears < 1e10).float().mean()
+    assert 0.05 < float(hit) < 0.95, float(hit)
+    g = torch.Generator().manual_seed(909)
+    n = 512
+    aabb = torch.tensor([-1.0, -0.5, -2.0, 1.5, 0.75, 0.25])
+    origins = (torch.rand(n, 3, generator=g) - 0.5) * 6.0
+    directions = torch.randn(n, 3, generator=g)
+    directions = directions / directions.norm(dim=-1, keepdim=True)
+    origins[:64] = (torch.rand(64, 3, generator=g) - 0.5) * torch.tensor([2.0, 1.0, 2.0]) + torch.tensor([0.25, 0.125, -0.875])
+    directions[64:96] = torch.eye(3)[torch.randint(0, 3, (32,), generator=g)] * torch.tensor([1.0, -1.0, 1.0])  # zeros: +-inf slabs
+    origins[96:104, 0] = -1.0  # on the x-min face ...
+    directions[96:104] = torch.tensor([0.0, 0.6, 0.8])  # ... moving inside it: 0/0 = NaN in the x slab
+    origins[104:112] = torch.tensor([3.0, 0.0, -1.0])
+    directions[104:112] = torch.tensor([1.0, 0.0, 0.0])  # pointing away: both crossings negative -> clamped to 0 -> a miss
+    t_min, t_max = ns_math.intersect_aabb(origins, directions, aabb)
+    assert bool(torch.isnan(t_min).any()) and bool((t_min == 1e10).any()) and bool((t_min < 1e10).any())
+    save("raygen_crop", frame_cam=torch.tensor(cam), box=box, frame_nears=frame.nears, frame_fars=frame.fars,
+         aabb=aabb, origins=origins, directions=directions, t_min=t_min, t_max=t_max)
 
 
 def gen_samplers_cfg4(R):

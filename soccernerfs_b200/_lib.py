@@ -51,6 +51,7 @@ SIGNATURES = {
     "kp_decoder_fused_supported": ([c_int, c_int, c_int], c_int),
     "kp_decoder_fwd_fused": ([_P, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P], c_int),
     "kp_aabb_intersect": ([_P, _P, c_int64, POINTER(c_float), c_float, _P, _P, _P], c_int),
+    "kp_intersect_aabb": ([_P, _P, c_int64, POINTER(c_float), _P, _P, _P], c_int),
     "kp_uniform_bins": ([_P, _P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P], c_int),
     "kp_pdf_resample": ([_P, _P, c_int, _P, _P, c_int, _P, _P, c_int64, c_int, c_float, c_float, c_int, _P, _P, _P, _P, _P, c_float,
                          _P, _P, _P, _P], c_int),

@@ -163,10 +163,21 @@ class Cameras:
                        times=None if times is None else times.view(*shape, 1),
                        metadata={"directions_norm": norm.view(*shape, 1)})
         if aabb_box is not None:
-            # cameras.py:478-497 fills nears/fars with utils.math.intersect_aabb; the K-Planes path sets them with its
-            # own collider (AABBBoxCollider) afterwards, so this option is not built
-            raise NotImplementedError("generate_rays(aabb_box=...) is not built; apply the model's collider to the bundle")
+            # cameras.py:478-497: nears / fars from utils.math.intersect_aabb (a crop-box render, scripts/render.py:101-106);
+            # a bundle that carries them passes the model's collider unchanged (scene_colliders.py:41-45)
+            t_min, t_max = ops.intersect_aabb(origins, directions, self.box6(aabb_box))
+            rb.nears, rb.fars = t_min.view(*shape, 1), t_max.view(*shape, 1)
         return rb
+
+    @staticmethod
+    def box6(aabb_box) -> tuple:
+        """A SceneBox (or six floats already on the host) -> (x, y, z min, x, y, z max) host floats.  Reading a device
+        box synchronises: callers inside a CUDA-graph capture convert once beforehand and pass the tuple."""
+        if isinstance(aabb_box, (tuple, list)):
+            if len(aabb_box) != 6:
+                raise ValueError("aabb_box as a sequence must hold six floats (min then max)")
+            return tuple(float(v) for v in aabb_box)
+        return tuple(float(v) for v in aabb_box.aabb.detach().flatten().tolist())
 
     # -- ray generation -------------------------------------------------------------------------------
     def generate_rays(self, camera_indices: Union[torch.Tensor, int], coords: Optional[torch.Tensor] = None,
@@ -198,7 +209,7 @@ class Cameras:
                                 distortion=self._lens(disable_distortion), cam_types=self._cam_types)
         return self._bundle(out, camera_indices.to(dev), shape, aabb_box)
 
-    def generate_rays_from_indices(self, ray_indices: torch.Tensor, aabb_box: Optional[SceneBox] = None) -> RayBundle:
+    def generate_rays_from_indices(self, ray_indices: torch.Tensor, aabb_box=None) -> RayBundle:
         """(camera,row,col) triplets -> rays, what RayGenerator.forward computes, without building coords.
         Indices that arrive on the host (the pixel samplers produce them there) are range-checked like the reference's
         tensor indexing would; device-resident indices are trusted (checking them would cost a synchronisation) and the

@@ -32,6 +32,36 @@ __global__ void aabb_kernel(const float* __restrict__ o, const float* __restrict
   fars[i] = tf;
 }
 
+// torch.minimum / torch.maximum semantics: a NaN operand gives NaN (fminf / fmaxf would drop it)
+__device__ __forceinline__ float min_nan(float a, float b) { return (a != a || b != b) ? NAN : fminf(a, b); }
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b != b) ? NAN : fmaxf(a, b); }
+
+// _intersect_aabb (NS/utils/math.py:201-238, max_bound = invalid_value = 1e10): the slab test Cameras.generate_rays
+// applies for aabb_box (cameras.py:478-497; nerfacc's ray_aabb_intersect is its first choice, :260-270, and is not in
+// the image).  Plain division by the direction (no epsilon), entry / exit clamped to [0, 1e10], a miss gives 1e10 twice.
+__global__ void __launch_bounds__(256) ray_box_kernel(const float* __restrict__ o, const float* __restrict__ d, int64_t N,
+                                                      float a0, float a1, float a2, float b0, float b1, float b2,
+                                                      float* __restrict__ t_min, float* __restrict__ t_max) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float amin[3] = {a0, a1, a2}, amax[3] = {b0, b1, b2};
+  float lo[3], hi[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float ta = __fdiv_rn(__fsub_rn(amin[k], o[i * 3 + k]), d[i * 3 + k]);
+    const float tb = __fdiv_rn(__fsub_rn(amax[k], o[i * 3 + k]), d[i * 3 + k]);
+    lo[k] = min_nan(ta, tb);
+    hi[k] = max_nan(ta, tb);
+  }
+  float tn = max_nan(max_nan(lo[0], lo[1]), lo[2]);
+  float tf = min_nan(min_nan(hi[0], hi[1]), hi[2]);
+  tn = min_nan(max_nan(tn, 0.0f), 1e10f);  // torch.clamp(min=0, max=max_bound), NaN kept
+  tf = min_nan(max_nan(tf, 0.0f), 1e10f);
+  const bool miss = tf <= tn;
+  t_min[i] = miss ? 1e10f : tn;
+  t_max[i] = miss ? 1e10f : tf;
+}
+
 // spacing functions (ray_samplers.py:129-150 uniform; :236-246 piecewise uniform / linear-in-disparity)
 __device__ __forceinline__ float spacing_fn(float x, int mode) {
   if (mode == 0) return x;
@@ -215,6 +245,16 @@ extern "C" int kp_aabb_intersect(const float* origins, const float* directions, 
   aabb_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, as_stream(stream)>>>(origins, directions, N, aabb[0], aabb[1], aabb[2],
                                                                         aabb[3], aabb[4], aabb[5], near_plane, nears, fars);
   KP_LAUNCH_CHECK("aabb_intersect");
+  return 0;
+}
+
+extern "C" int kp_intersect_aabb(const float* origins, const float* directions, int64_t N, const float* aabb,
+                                 float* t_min, float* t_max, void* stream) {
+  if (N == 0) return 0;
+  KP_CHECK(origins && directions && aabb && t_min && t_max, "intersect_aabb: NULL argument");
+  ray_box_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, as_stream(stream)>>>(origins, directions, N, aabb[0], aabb[1], aabb[2],
+                                                                           aabb[3], aabb[4], aabb[5], t_min, t_max);
+  KP_LAUNCH_CHECK("intersect_aabb");
   return 0;
 }
 

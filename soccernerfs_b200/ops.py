@@ -507,6 +507,17 @@ def aabb_intersect(origins, directions, aabb6: Sequence[float], near_plane: floa
     return nears, fars
 
 
+def intersect_aabb(origins, directions, aabb6: Sequence[float]):
+    """nerfstudio.utils.math._intersect_aabb (math.py:201-238) on the device: origins / directions [N,3], aabb6 = min then
+    max (host floats) -> t_min [N], t_max [N]; 1e10 twice for a ray that misses the box."""
+    o, d = f32c(origins), f32c(directions)
+    n = o.shape[0]
+    t_min = torch.empty((n,), dtype=torch.float32, device=o.device)
+    t_max = torch.empty_like(t_min)
+    call("kp_intersect_aabb", ptr(o), ptr(d), n, (c_float * 6)(*[float(v) for v in aabb6]), ptr(t_min), ptr(t_max), stream_ptr())
+    return t_min, t_max
+
+
 _LINSPACE_CACHE = {}
 
 

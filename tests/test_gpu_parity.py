@@ -733,6 +733,74 @@ def test_frame_renderer_equals_chunked_camera_bundle():
         assert torch.equal(total[k], one[k]), k
 
 
+def test_crop_box_render_vs_reference_fixture():
+    """(f2) crop-box rendering, scripts/render.py:101-106: kp_intersect_aabb bit-identical to the reference's slab test
+    (NaN / 1e10 / infinite-slab rays included), Cameras.generate_rays(aabb_box=...) stores the same nears / fars as the
+    reference's Cameras for a whole frame, the model keeps them (the collider only fills missing bounds,
+    scene_colliders.py:41-45), and the tile queue with ``aabb_box`` renders the same image as the bundle form."""
+    from soccernerfs_b200 import ops
+    from soccernerfs_b200.cameras.cameras import Cameras
+    from soccernerfs_b200.data.scene_box import SceneBox
+    from soccernerfs_b200.engine.frame_renderer import FrameRenderer
+    from tests.helpers import build_model
+    from tests.test_oracle_golden import _same_with_nans, load_tiny_model
+
+    g = load_golden("raygen_crop")
+    t_min, t_max = ops.intersect_aabb(g["origins"].to(DEV), g["directions"].to(DEV), g["aabb"].tolist())
+    assert _same_with_nans(t_min.cpu(), g["t_min"]) and _same_with_nans(t_max.cpu(), g["t_max"])
+    e0, e1 = ops.intersect_aabb(torch.zeros(0, 3, device=DEV), torch.zeros(0, 3, device=DEV), g["aabb"].tolist())
+    assert e0.shape == (0,) and e1.shape == (0,)
+    # the reference's own property test (tests/utils/test_aabb_intersection.py:120-147): entry and exit points of the
+    # rays that hit lie on the box's boundary
+    hit = (g["t_min"] < 1e10) & ~torch.isnan(g["t_min"])
+    o, d, a = g["origins"][hit], g["directions"][hit], g["aabb"]
+    assert int(hit.sum()) > 10 and bool((t_max.cpu()[hit] >= t_min.cpu()[hit]).all())
+    for t in (t_max.cpu()[hit],):  # exits are always on a face (entries are 0 for origins inside the box)
+        p = o + d * t[:, None]
+        inside = ((p >= a[:3] - 1e-4) & (p <= a[3:] + 1e-4)).all(dim=-1)
+        on_face = (torch.minimum((p - a[:3]).abs(), (p - a[3:]).abs()).min(dim=-1).values < 1e-4)
+        assert bool((inside & on_face).all())
+
+    r = load_golden("raygen")
+    h, w = (int(v) for v in r["hw"])
+    cams = Cameras(*[r[k].to(DEV) for k in ("c2w", "fx", "fy", "cx", "cy")], w, h, times=r["times"].to(DEV))
+    cam = int(g["frame_cam"])
+    box = SceneBox(aabb=g["box"].to(DEV))
+    frame = cams.generate_rays(camera_indices=cam, aabb_box=box)
+    assert frame.nears.shape == (h, w, 1) and frame.fars.shape == (h, w, 1)
+    # our directions differ from the reference's in the last bit on ~10 % of the rays, so do the bounds: 1e-5 relative
+    # where both hit, and the same hit / miss decision except on rays within rounding of grazing the box
+    ours_hit, ref_hit = frame.nears.cpu() < 1e10, g["frame_nears"] < 1e10
+    both = ours_hit & ref_hit
+    assert float((ours_hit != ref_hit).float().mean()) < 2e-3
+    assert rel_err(frame.nears.cpu()[both], g["frame_nears"][both]) < 1e-5 and rel_err(frame.fars.cpu()[both], g["frame_fars"][both]) < 1e-5
+    # given the reference's rays the bounds are bit-identical
+    t0, t1 = ops.intersect_aabb(r["frame_origins"].reshape(-1, 3).to(DEV), r["frame_directions"].reshape(-1, 3).to(DEV), Cameras.box6(box))
+    assert torch.equal(t0.cpu().view(h, w, 1), g["frame_nears"]) and torch.equal(t1.cpu().view(h, w, 1), g["frame_fars"])
+
+    gm = load_golden("model_tiny")
+    model = build_model("tiny", load_tiny_model(gm), gm["aabb"], DEV)
+    model.eval()
+    hh, ww = 24, 40
+    c2w = torch.tensor([[[1.0, 0, 0, 0.1], [0, 1.0, 0, -0.2], [0, 0, 1.0, 2.5]]])
+    cams = Cameras(c2w.to(DEV), 40.0, 40.0, ww / 2, hh / 2, ww, hh, times=torch.tensor([0.4]).to(DEV))
+    crop = SceneBox(aabb=torch.tensor([[-0.4, -0.5, -0.3], [0.5, 0.2, 0.6]]))
+    full = cams.generate_rays(camera_indices=0, aabb_box=crop)
+    frac = float((full.nears < 1e10).float().mean())
+    assert 0.02 < frac < 0.9, frac
+    model.config.eval_num_rays_per_chunk = 200
+    with torch.no_grad():
+        ref = model.get_outputs_for_camera_ray_bundle(full)
+        uncropped = model.get_outputs_for_camera_ray_bundle(cams.generate_rays(camera_indices=0))
+    kept = model.collider(full)  # bounds already set: the collider returns the bundle as it is
+    assert kept.nears is full.nears and kept.fars is full.fars
+    assert not torch.equal(ref["rgb"], uncropped["rgb"])
+    for graph in (True, False):
+        out = FrameRenderer(model, cams, chunk=200, use_cuda_graph=graph, aabb_box=crop).render(0)
+        for k in ("rgb", "depth", "accumulation"):
+            assert torch.equal(out[k], ref[k].cpu()), (k, graph)
+
+
 def test_compositing_edge_shapes_and_non_finite_densities():
     """Ragged / degenerate inputs the reference code accepts: one ray, one sample; S not a multiple of the warp; an
     infinite density (alpha = 1, everything behind it gets weight 0) and a NaN (nan_to_num -> 0), rays.py:137-149."""

@@ -197,6 +197,23 @@ def test_lens_models_match_reference():
     assert (fwd - 0.4 * pts.clamp(-1, 1)).abs().max() < 1e-6
 
 
+def _same_with_nans(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a, nan=0.0), torch.nan_to_num(b, nan=0.0))
+
+
+def test_crop_box_bounds_match_reference():
+    """(f2) the slab test behind Cameras.generate_rays(aabb_box=...) (math.py:201-272, cameras.py:478-497) vs the
+    reference's own function: hits, misses (1e10 twice), axis-parallel rays (infinite slabs) and the 0/0 slab (NaN)."""
+    g = load_golden("raygen_crop")
+    t_min, t_max = ko.intersect_aabb(g["origins"], g["directions"], g["aabb"])
+    assert _same_with_nans(t_min, g["t_min"]) and _same_with_nans(t_max, g["t_max"])
+    assert int(torch.isnan(g["t_min"]).sum()) == 8 and 0 < int((g["t_min"] == 1e10).sum()) < t_min.numel() - 8
+    r = load_golden("raygen")
+    h, w = (int(v) for v in r["hw"])
+    t_min, t_max = ko.intersect_aabb(r["frame_origins"].reshape(-1, 3), r["frame_directions"].reshape(-1, 3), g["box"].reshape(-1))
+    assert torch.equal(t_min.view(h, w, 1), g["frame_nears"]) and torch.equal(t_max.view(h, w, 1), g["frame_fars"])
+
+
 def test_cfg4_piecewise_single_jitter_samplers_match_reference():
     """BASELINE config 4: UniformLinDispPiecewiseSampler + PDFSampler with single_jitter=True and the expected-depth
     renderer, vs the reference's own classes (fixture samplers_cfg4)."""
