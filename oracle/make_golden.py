@@ -424,6 +424,48 @@ def gen_field_variants(R):
     save("field_variants", **arrs)
 
 
+def gen_field_depths(R):
+    """Decoder depths / widths other than the presets' (KPlanesModelConfig.sigma_net_layers / rgb_net_layers /
+    *_hidden_dim, kplanes.py:96-103 -> tcnn n_hidden_layers / n_neurons, kplanes_field.py:249-273), by the reference's own
+    KPlanesField: (a) two hidden sigma layers of 32 and one hidden colour layer of 48, view-dependent; (b) no hidden
+    sigma layer at all and three hidden colour layers, disable_viewing_dependent.  Outputs and all gradients."""
+    g = torch.Generator().manual_seed(654)
+    res, ms, c = (12, 10, 14, 5), (1, 2), 8
+    n, s = 80, 5
+    aabb = torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]])
+    origins = (torch.rand(n, 3, generator=g) - 0.5) * 1.6
+    d = torch.randn(n, 3, generator=g)
+    directions = d / d.norm(dim=-1, keepdim=True)
+    bins = torch.sort(torch.rand(n, s + 1, generator=g), -1).values * 1.5
+    times = torch.rand(n, 1, generator=g)
+    rb = R.rays.RayBundle(origins=origins, directions=directions, pixel_area=torch.ones(n, 1), times=times,
+                          nears=torch.zeros(n, 1), fars=torch.full((n, 1), 1.5))
+    rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+    arrs = dict(aabb=aabb, origins=origins, directions=directions, bins=bins, times=times)
+    variants = {"a": dict(sigma_net_layers=2, sigma_net_hidden_dim=32, rgb_net_layers=1, rgb_net_hidden_dim=48),
+                "b": dict(sigma_net_layers=0, rgb_net_layers=3, rgb_net_hidden_dim=64, disable_viewing_dependent=True)}
+    for tag, kw in variants.items():
+        f = R.kplanes_field.KPlanesField(aabb, spacetime_resolution=res, feat_dim=c, multiscale_res=ms,
+                                         concat_features_across_scales=True, linear_decoder=False, **kw)
+        with torch.no_grad():
+            for gs in f.grids:
+                for p_ in gs:
+                    p_.add_(0.3 * torch.randn(p_.shape, generator=g))
+        out = f(rs)
+        dens, rgb = out[R.kplanes_field.FieldHeadNames.DENSITY], out[R.kplanes_field.FieldHeadNames.RGB]
+        gd, gr = torch.randn(dens.shape, generator=g), torch.randn(rgb.shape, generator=g)
+        ((dens * gd).sum() + (rgb * gr).sum()).backward()
+        arrs.update({f"{tag}_density": dens, f"{tag}_rgb": rgb, f"{tag}_gd": gd, f"{tag}_gr": gr})
+        for i, gs in enumerate(f.grids):
+            for j, p_ in enumerate(gs):
+                arrs[f"{tag}_grid_{i}_{j}"], arrs[f"{tag}_ggrid_{i}_{j}"] = p_.detach(), p_.grad
+        for name, net in (("sigma", f.sigma_net), ("color", f.color_net)):
+            assert len(net.layers) == kw[f"{'sigma' if name == 'sigma' else 'rgb'}_net_layers"] + 1
+            for i, lin in enumerate(net.layers):
+                arrs[f"{tag}_{name}_w{i}"], arrs[f"{tag}_{name}_gw{i}"] = lin.weight.detach(), lin.weight.grad
+    save("field_depths", **arrs)
+
+
 def main():
     torch.set_num_threads(1)
     R = load_reference()
@@ -438,6 +480,7 @@ def main():
     gen_raygen_crop(R)
     gen_samplers_cfg4(R)
     gen_field_variants(R)
+    gen_field_depths(R)
 
 
 def _reference_method(path, class_name, method_name, extra_globals):

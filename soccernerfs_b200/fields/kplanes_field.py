@@ -153,8 +153,11 @@ class KPlanesField(Field, _AabbHostMixin):
         freeze_space_planes: bool = False,
     ) -> None:
         super().__init__()
-        if not linear_decoder and (sigma_net_layers != 1 or rgb_net_layers != 2):
-            raise NotImplementedError("decoder kernels are built for sigma_net_layers=1, rgb_net_layers=2")
+        if sigma_net_layers < 0 or rgb_net_layers < 0:
+            raise ValueError("sigma_net_layers / rgb_net_layers count hidden layers and cannot be negative")
+        # the fused decoder kernels cover the depths every preset uses (kplanes.py:96-103: one hidden sigma layer, two
+        # hidden colour layers); other depths run the same networks layer by layer on the tensor-core dense layer
+        self._preset_depth = sigma_net_layers == 1 and rgb_net_layers == 2
         self.aabb = Parameter(aabb, requires_grad=False)
         self.spatial_distortion = spatial_distortion
         self._contract = _contraction_mode(spatial_distortion)
@@ -231,6 +234,13 @@ class KPlanesField(Field, _AabbHostMixin):
         if self.linear_decoder:  # density = trunc_exp(linear(features)); the features themselves feed the colour basis
             density = ops.trunc_exp(ops.linear(feats, self.sigma_net.weights[0]))
             return density.view(*batch, 1), feats
+        if len(self.sigma_net.weights) != 2:  # any other depth (kplanes_field.py:249-273 with n_hidden_layers != 1)
+            o = feats
+            ws = self.sigma_net.weights
+            for i, w in enumerate(ws):
+                o = ops.linear(o, w, "relu" if i + 1 < len(ws) else "none")
+            density = ops.trunc_exp(o[:, self.geo_feat_dim:self.geo_feat_dim + 1])  # kplanes_field.py:308-311
+            return density.reshape(*batch, 1), o[:, : self.geo_feat_dim]
         o, density = ops.sigma_net(feats, self.sigma_net.weights[0], self.sigma_net.weights[1])
         return density.view(*batch, 1), o[:, : self.geo_feat_dim]
 
@@ -251,8 +261,9 @@ class KPlanesField(Field, _AabbHostMixin):
         return emb[:, None, :].expand(n_rays, n_samples, dim).reshape(-1, dim)
 
     def _get_outputs_composed(self, ray_samples: RaySamples, density_embedding: torch.Tensor) -> torch.Tensor:
-        """The non-default colour branches (linear decoder / appearance embedding), composed from the tensor-core dense
-        layer (ops.linear) exactly as kplanes_field.py:314-358 composes them from tcnn networks."""
+        """The non-default colour branches (linear decoder / appearance embedding / a colour net of another depth than the
+        presets'), composed from the tensor-core dense layer (ops.linear) exactly as kplanes_field.py:314-358 composes
+        them from tcnn networks."""
         batch = ray_samples.frustums.shape
         n_samples = batch[-1]
         n_rays = 1
@@ -288,7 +299,7 @@ class KPlanesField(Field, _AabbHostMixin):
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None) -> torch.Tensor:
         """-> rgb [N,S,3] (bare tensor, like kplanes_field.py:314-358)."""
         assert density_embedding is not None
-        if self.linear_decoder or self.use_appearance_embedding:
+        if self.linear_decoder or self.use_appearance_embedding or len(self.color_net.weights) != 3:
             return self._get_outputs_composed(ray_samples, density_embedding)
         batch = ray_samples.frustums.shape
         n_samples = batch[-1]
@@ -314,7 +325,7 @@ class KPlanesField(Field, _AabbHostMixin):
     def _forward_fused(self, ray_samples: RaySamples):
         """get_density + get_outputs with both decoders in ONE tensor-core kernel (same numbers as the two-call path);
         None when the decoder shape is not covered (e.g. the 192 -> 128 sigma net of the 32x config)."""
-        if self.linear_decoder or self.use_appearance_embedding:
+        if self.linear_decoder or self.use_appearance_embedding or not self._preset_depth:
             return None
         w1, w2 = self.sigma_net.weights
         w3, w4, w5 = self.color_net.weights

@@ -1174,6 +1174,63 @@ def test_scene_contraction_fields_vs_reference_fixture():
     assert rel_err(dfn.cpu(), g["pcon_density"]) < TOL
 
 
+def test_decoder_depths_vs_reference_fixture():
+    """sigma_net_layers / rgb_net_layers / hidden widths other than the presets' (KPlanesModelConfig, kplanes.py:96-103):
+    the same networks layer by layer on the tensor-core dense layer vs the reference's own KPlanesField (fixture
+    field_depths: 2 hidden sigma layers of 32 + 1 hidden colour layer of 48 with view dependence; no hidden sigma layer
+    + 3 hidden colour layers without it): outputs and all gradients; the model config reaches the field."""
+    from soccernerfs_b200.data.scene_box import SceneBox
+    from soccernerfs_b200.fields.base_field import FieldHeadNames
+    from soccernerfs_b200.fields.kplanes_field import KPlanesField
+    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
+
+    g = load_golden("field_depths")
+    n = g["origins"].shape[0]
+    from soccernerfs_b200.cameras.rays import RayBundle
+
+    rb = RayBundle(origins=g["origins"].to(DEV), directions=g["directions"].to(DEV), pixel_area=torch.ones(n, 1, device=DEV),
+                   times=g["times"].to(DEV), nears=torch.zeros(n, 1, device=DEV), fars=torch.full((n, 1), 1.5, device=DEV))
+    bins = g["bins"].to(DEV)
+    rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+    variants = {"a": dict(sigma_net_layers=2, sigma_net_hidden_dim=32, rgb_net_layers=1, rgb_net_hidden_dim=48),
+                "b": dict(sigma_net_layers=0, rgb_net_layers=3, rgb_net_hidden_dim=64, disable_viewing_dependent=True)}
+    for tag, kw in variants.items():
+        f = KPlanesField(g["aabb"], spacetime_resolution=(12, 10, 14, 5), feat_dim=8, multiscale_res=(1, 2),
+                         concat_features_across_scales=True, linear_decoder=False, **kw).to(DEV)
+        assert len(f.sigma_net.weights) == kw["sigma_net_layers"] + 1 and len(f.color_net.weights) == kw["rgb_net_layers"] + 1
+        _load_planes(f.grids, g, f"{tag}_grid")
+        with torch.no_grad():
+            for name, net in (("sigma", f.sigma_net), ("color", f.color_net)):
+                for i, w in enumerate(net.weights):
+                    w.copy_(g[f"{tag}_{name}_w{i}"].to(DEV))
+        out = f(rs)
+        dens, rgb = out[FieldHeadNames.DENSITY], out[FieldHeadNames.RGB]
+        assert rel_err(dens.cpu(), g[f"{tag}_density"]) < TOL and rel_err(rgb.cpu(), g[f"{tag}_rgb"]) < TOL, tag
+        ((dens * g[f"{tag}_gd"].to(DEV)).sum() + (rgb * g[f"{tag}_gr"].to(DEV)).sum()).backward()
+        for i, gs in enumerate(f.grids):
+            for j, p in enumerate(gs):
+                assert rel_err(p.grad.cpu(), g[f"{tag}_ggrid_{i}_{j}"]) < TOL, (tag, i, j)
+        for name, net in (("sigma", f.sigma_net), ("color", f.color_net)):
+            for i, w in enumerate(net.weights):
+                assert rel_err(w.grad.cpu(), g[f"{tag}_{name}_gw{i}"]) < TOL, (tag, name, i)
+    cfg = KPlanesModelConfig(spacetime_resolution=(8, 8, 8, 4), multiscale_res=(1, 2), sigma_net_layers=2, rgb_net_layers=3,
+                             sigma_net_hidden_dim=32, proposal_net_args_list=[{"feature_dim": 8, "resolution": [8, 8, 8, 4]}] * 2)
+    model = cfg.setup(scene_box=SceneBox(aabb=g["aabb"]), num_train_data=1).to(DEV)
+    assert [tuple(w.shape) for w in model.field.sigma_net.weights] == [(32, 64), (32, 32), (16, 32)]
+    assert len(model.field.color_net.weights) == 4
+    from soccernerfs_b200.engine.trainer import TrainStep
+    from tests.helpers import ray_bundle
+
+    gold = load_golden("model_tiny")
+    step = TrainStep(model, max_steps=50, warm_up_end=2)
+    try:
+        losses = [float(step(ray_bundle(gold["origins"], gold["directions"], gold["times"], DEV), {"image": gold["image"].to(DEV)})["loss"])
+                  for _ in range(4)]
+    finally:
+        step.close()
+    assert all(l == l and l < 1e3 for l in losses) and losses[-1] < losses[1], losses
+
+
 def test_linear_decoder_field_vs_reference_fixture():
     """linear_decoder=True (learned colour basis, linear density) composed from the tensor-core dense layer vs the
     reference's KPlanesField(linear_decoder=True) (tests/golden/field_variants.npz): outputs and all gradients."""

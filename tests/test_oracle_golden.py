@@ -197,6 +197,29 @@ def test_lens_models_match_reference():
     assert (fwd - 0.4 * pts.clamp(-1, 1)).abs().max() < 1e-6
 
 
+def test_decoder_depths_match_reference():
+    """sigma_net_layers / rgb_net_layers / hidden widths other than the presets' (kplanes.py:96-103): the oracle's field
+    with such weight stacks vs the reference's own KPlanesField (fixture field_depths), outputs and all gradients."""
+    g = load_golden("field_depths")
+    n, s = g["bins"].shape[0], g["bins"].shape[1] - 1
+    for tag, n_sigma, n_color, view in (("a", 3, 2, True), ("b", 1, 4, False)):
+        grids = [[g[f"{tag}_grid_{i}_{j}"].clone().requires_grad_(True) for j in range(6)] for i in range(2)]
+        sw = [g[f"{tag}_sigma_w{i}"].clone().requires_grad_(True) for i in range(n_sigma)]
+        cw = [g[f"{tag}_color_w{i}"].clone().requires_grad_(True) for i in range(n_color)]
+        p = ko.FieldParams(aabb=g["aabb"], grids=grids, sigma_w=sw, color_w=cw, concat=True, view_dependent=view)
+        smp = ko.Samples(origins=g["origins"], directions=g["directions"], starts=g["bins"][:, :-1], ends=g["bins"][:, 1:],
+                         spacing_bins=g["bins"], nears=torch.zeros(n, 1), fars=torch.full((n, 1), 1.5), times=g["times"])
+        dens, rgb, _ = ko.field_forward(p, smp)
+        assert dens.shape == (n, s, 1) and rel_err(dens, g[f"{tag}_density"]) < 2e-6 and rel_err(rgb, g[f"{tag}_rgb"]) < 2e-6
+        ((dens * g[f"{tag}_gd"]).sum() + (rgb * g[f"{tag}_gr"]).sum()).backward()
+        for i in range(2):
+            for j in range(6):
+                assert rel_err(grids[i][j].grad, g[f"{tag}_ggrid_{i}_{j}"]) < 2e-6, (tag, i, j)
+        for name, ws in (("sigma", sw), ("color", cw)):
+            for i, w in enumerate(ws):
+                assert rel_err(w.grad, g[f"{tag}_{name}_gw{i}"]) < 2e-6, (tag, name, i)
+
+
 def _same_with_nans(a: torch.Tensor, b: torch.Tensor) -> bool:
     return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a, nan=0.0), torch.nan_to_num(b, nan=0.0))
 
