@@ -304,6 +304,21 @@ int kp_isg_map(const float* images, int B, int64_t HW, const int32_t* cam_offset
                const int32_t* image_cam, int n_cams, int max_frames_per_cam, float gamma_sq, float* median_scratch,
                void* out_fp16, void* stream);
 
+/* ---- (f4) importance pixel sampling: the per-image torch.multinomial calls of DynamicBasedPixelSampler.sample_method
+ *      (NS/data/pixel_samplers.py:340-426) for all images of a step at once.  weights_fp16 [B,HW]: the IST / ISG maps
+ *      (device).  sel: DEVICE int32 [n_sel,3] = (image, k, first output row) per visited image, as the reference's loop
+ *      assigns them (the host walks the shuffled image order and skips all-zero maps, :381-393); k <= k_max.  For each
+ *      entry k pixels are drawn proportionally to the image's weights -- without replacement if the map has >= k non-zero
+ *      pixels, else with replacement (:396-398) -- and written as int64 (image, row, col) triplets to rows
+ *      [first, first + k) of out, without replacement in decreasing order of the race key (torch.multinomial's order).
+ *      Exponential race on Philox4x32-10 keyed by `seed` (csrc/pixel_sampler_math.cuh): the reference's DISTRIBUTION, not
+ *      its random stream.  An entry whose map is all zero gets rows of -1 (the reference's loop skips such images; so
+ *      does the host side here).  scratch: kp_importance_pixels_scratch_bytes(n_sel, k_max) device bytes.  6 launches + 1 memset,
+ *      no host synchronisation. ---- */
+int64_t kp_importance_pixels_scratch_bytes(int n_sel, int k_max);
+int kp_importance_pixels(const void* weights_fp16, int B, int64_t HW, int width, const int32_t* sel, int n_sel, int k_max,
+                         uint64_t seed, void* scratch, int64_t* out, void* stream);
+
 /* ---- (a14b) loss head: the reductions, coefficients, total and PSNR that KPlanesModel.get_loss_dict /
  *      get_metrics_dict (NS/models/kplanes.py:392-452) and the trainer's sum(loss_dict.values())
  *      (NS/engine/trainer.py:398-400) apply to the per-ray / per-sample loss kernels' outputs, one launch per

@@ -5,6 +5,12 @@ importance sampler ``DynamicBasedPixelSampler.sample_method`` (:340-426).  Bit-e
 making the SAME random calls in the SAME order (``random.shuffle``, ``torch.multinomial`` per image, ``torch.rand`` for
 the uniform remainder), so a shared seed reproduces the reference's indices exactly.  Host-side by design (SURVEY.md
 8a, row a18).
+
+The importance sampler also has a DEVICE path (``kp_importance_pixels``), taken when the weight maps
+live on the GPU: the host keeps the reference's control flow (shuffled image order, all-zero maps skipped, k per image) and
+the per-image ``torch.multinomial`` calls -- ~200 ms of host time per 4096-ray step at 540x960 -- become six kernel
+launches for the whole step without a host synchronisation.  It draws from the same distribution with its own
+counter-based random stream, so it reproduces the reference's statistics, not its exact indices.
 """
 from __future__ import annotations
 
@@ -61,9 +67,47 @@ class PixelSampler:
 class DynamicBasedPixelSampler(PixelSampler):
     """Samples ``is_pixel_ratio`` of the batch proportionally to the IST/ISG weight maps, the rest uniformly."""
 
-    def __init__(self, num_rays_per_batch: int, keep_full_image: bool = False, **kwargs) -> None:
+    def __init__(self, num_rays_per_batch: int, keep_full_image: bool = False, device_sampler: Optional[bool] = None,
+                 **kwargs) -> None:
+        """``device_sampler``: None = the device path whenever the weight maps are CUDA tensors; False = always the
+        reference's host loop (bit-exact indices for a shared seed; on CUDA maps it synchronises per image like the
+        reference would); True = require the device path."""
         self.dataset = kwargs["dataset"]
+        self.device_sampler = device_sampler
+        self._nonzero_maps = None  # (identity of the weight tensor, host bool [B]: which maps have a non-zero pixel)
         super().__init__(num_rays_per_batch, keep_full_image, **kwargs)
+
+    def _maps_with_mass(self, weights: torch.Tensor) -> list:
+        """Which images have a non-zero pixel (the reference skips the others, :391-393).  The maps are dataset-level
+        constants, so this one reduction + read-back is cached until the tensor changes."""
+        key = (weights.data_ptr(), weights._version, tuple(weights.shape))
+        if self._nonzero_maps is None or self._nonzero_maps[0] != key:
+            flags = (weights.reshape(weights.shape[0], -1) != 0).any(dim=1).cpu().tolist()
+            self._nonzero_maps = (key, flags)
+        return self._nonzero_maps[1]
+
+    def _sample_ist_device(self, weights: torch.Tensor, num_ist: int, per_image: int, num_images: int,
+                           image_width: int) -> torch.Tensor:
+        """The importance part of the batch on the device -> int64 [sampled, 3] (image, row, col)."""
+        from .. import ops
+
+        has_mass = self._maps_with_mass(weights)
+        order = list(range(num_images))
+        random.shuffle(order)
+        sel, sampled = [], 0
+        for i in order:  # the reference's walk (:381-404) without its sampling
+            if sampled >= num_ist:
+                break
+            k = per_image if sampled + per_image <= num_ist else num_ist - sampled
+            if not has_mass[i]:
+                continue
+            sel.append((i, k, sampled))
+            sampled += k
+        if not sel:
+            return torch.zeros((0, 3), dtype=torch.int64, device=weights.device)
+        seed = random.getrandbits(63)  # from the same (seedable) python generator that shuffled the images
+        return ops.importance_pixels(weights, torch.tensor(sel, dtype=torch.int32), max(k for _, k, _ in sel), sampled,
+                                     image_width, seed)
 
     def sample_method(self, batch_size: int, num_images: int, image_height: int, image_width: int,
                       mask: Optional[torch.Tensor] = None, batch: Optional[Dict] = None,
@@ -73,6 +117,17 @@ class DynamicBasedPixelSampler(PixelSampler):
             return super().sample_method(batch_size, num_images, image_height, image_width, mask=mask, device=device)
         sampled = 0
         use_ist = batch["iter_steps"] > self.dataset.iters_to_start_ist and batch["ist_weights"] is not None
+        on_device = use_ist and (self.device_sampler or (self.device_sampler is None and batch["ist_weights"].is_cuda))
+        if on_device:
+            weights = batch["ist_weights"]
+            if not weights.is_cuda or weights.dtype != torch.float16:
+                raise RuntimeError("device_sampler=True needs fp16 CUDA weight maps (there is no CPU path)")
+            num_ist = floor(self.dataset.is_pixel_ratio * batch_size)
+            per_image = 10 * (-(-num_ist // num_images))
+            indices = self._sample_ist_device(weights.contiguous(), num_ist, per_image, num_images, image_width)
+            uniform = super().sample_method(batch_size - indices.shape[0], num_images, image_height, image_width, mask=mask,
+                                            device=weights.device)
+            return torch.cat((indices, uniform.to(weights.device)), dim=0)
         if use_ist:
             num_ist = floor(self.dataset.is_pixel_ratio * batch_size)
             per_image = 10 * (-(-num_ist // num_images))

@@ -789,6 +789,38 @@ def generate_rays(c2w: torch.Tensor, intrinsics: torch.Tensor, cam_times: Option
     return origins, directions, pixel_area, norm, times
 
 
+_SAMPLER_SCRATCH = {}
+
+
+def importance_pixels(weights: torch.Tensor, sel: torch.Tensor, k_max: int, n_out: int, image_width: int, seed: int) -> torch.Tensor:
+    """Importance pixel sampling on the device (kp_importance_pixels): weights fp16 CUDA [B,H,W] or [B,HW]; sel int32
+    [n_sel,3] = (image, k, first output row) on the host (uploaded here) or already on the device; -> int64 [n_out,3]
+    (image, row, col).  Per entry k pixels proportional to the image's weights, without replacement when the map has
+    >= k non-zero pixels, else with replacement -- DynamicBasedPixelSampler's torch.multinomial calls
+    (NS/data/pixel_samplers.py:396-398) for the whole step in six launches, no host synchronisation."""
+    if weights.dtype != torch.float16 or not weights.is_cuda or not weights.is_contiguous():
+        raise RuntimeError("importance_pixels: weights must be a contiguous fp16 CUDA tensor (there is no CPU path)")
+    b = weights.shape[0]
+    hw = weights.numel() // max(b, 1)
+    if sel.dtype != torch.int32 or sel.dim() != 2 or sel.shape[1] != 3:
+        raise ValueError("importance_pixels: sel must be int32 [n_sel, 3] = (image, k, first output row)")
+    dev = weights.device
+    n_sel = sel.shape[0]
+    out = torch.empty((n_out, 3), dtype=torch.int64, device=dev)
+    if n_sel == 0 or n_out == 0:
+        return out
+    if not sel.is_cuda:
+        sel = sel.contiguous().pin_memory().to(dev, non_blocking=True)
+    nbytes = int(_lib.load().kp_importance_pixels_scratch_bytes(n_sel, int(k_max)))
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    scratch = _SAMPLER_SCRATCH.get(key)
+    if scratch is None or scratch.numel() < nbytes:
+        scratch = _SAMPLER_SCRATCH[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    call("kp_importance_pixels", c_void_p(weights.data_ptr()), b, hw, int(image_width), c_void_p(sel.data_ptr()), n_sel, int(k_max),
+         int(seed) & 0xFFFFFFFFFFFFFFFF, c_void_p(scratch.data_ptr()), ptr(out), stream_ptr())
+    return out
+
+
 def isg_map(images: torch.Tensor, cam_ids: torch.Tensor, gamma: float) -> torch.Tensor:
     """ISG weight map on the device (kp_isg_map): images [B,H,W,3] fp32 CUDA, cam_ids [B] -> fp16 [B,H,W]."""
     if images.dim() != 4 or images.shape[-1] != 3:
