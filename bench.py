@@ -18,6 +18,9 @@ Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[1] ("K-Planes defau
   "l2_peaks"           the achievable rate of the field kernels' own access pattern (random 128-byte lines) in L2 and in
                        HBM, measured live with kp_line_probe: the denominators of the per-scale fractions;
   "gpu_torch_baseline" the reference's own step as plain torch ops on the same GPU (N=1 only): the like-for-like "before";
+  "pixel_sampler"      (N=1 only) the importance pixel sampler of the preset's shape (4096-ray batch, 10 % importance
+                       pixels = 41 maps of 540x960 x 10 pixels): kp_importance_pixels on the device next to the reference's
+                       per-image torch.multinomial loop on the host cores;
   "cpu_baseline"       the oracle port on the host cores (N=1 only);
   "dp_check"           (N>1) parameters bit-identical across ranks after all steps, and the all-reduced gradient equal to
                        a single-rank gradient on the concatenated batch.
@@ -846,6 +849,60 @@ def gpu_torch_baseline(dev, steps=5, warmup=3, rays=RAYS_PER_RANK):
                     "cumsum / autograd / torch.optim.Adam; fp32 torch MLP in place of tiny-cuda-nn)"}
 
 
+def pixel_sampler_leg(dev, reps=20, host_reps=2):
+    """DynamicBasedPixelSampler.sample_method (NS/data/pixel_samplers.py:340-426) on the `ns-train k-planes` preset's shape
+    (method_configs.py:491-511: 4096 rays, is_pixel_ratio 0.1; 540x960 maps after downscale 2): the device path
+    (kp_importance_pixels, 6 launches, CUDA events) and the reference's host loop (41 torch.multinomial calls over 518 400
+    categories) on the same fp16 maps, half of them sparse (IST-like, 1 % non-zero) and half dense (ISG-like)."""
+    import random
+    import types
+
+    from soccernerfs_b200 import _lib
+    from soccernerfs_b200.data.pixel_samplers import DynamicBasedPixelSampler
+
+    gen = torch.Generator().manual_seed(4)
+    b, h, w, n = 410, 540, 960, RAYS_PER_RANK  # >= 409 cached images: the walk visits 41 of them, 10 pixels each
+    distinct = 42  # 42 distinct maps tiled over the cache keep the host-side setup short
+    maps = torch.zeros(distinct, h * w, dtype=torch.float16)
+    idx = torch.randint(0, h * w, (distinct, 5000), generator=gen)
+    maps.scatter_(1, idx, (torch.rand(distinct, 5000, generator=gen) * 0.8 + 0.15).half())
+    maps[distinct // 2:] = (torch.rand(distinct - distinct // 2, h * w, generator=gen) * 0.3 + 1e-3).half()
+    maps = maps[torch.arange(b) % distinct].view(b, h, w)
+    state = types.SimpleNamespace(iters_to_start_ist=0, is_pixel_ratio=0.1)
+    host = DynamicBasedPixelSampler(n, dataset=state, device_sampler=False)
+    random.seed(5)
+    host.sample_method(n, b, h, w, batch={"ist_weights": maps, "iter_steps": 1})
+    t0 = time.perf_counter()
+    for _ in range(host_reps):
+        ref = host.sample_method(n, b, h, w, batch={"ist_weights": maps, "iter_steps": 1})
+    host_ms = (time.perf_counter() - t0) * 1e3 / host_reps
+    dmaps = maps.to(dev)
+    sampler = DynamicBasedPixelSampler(n, dataset=state)
+    batch = {"ist_weights": dmaps, "iter_steps": 1}
+    for _ in range(3):
+        out = sampler.sample_method(n, b, h, w, batch=batch)
+    torch.cuda.synchronize()
+    k0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        out = sampler.sample_method(n, b, h, w, batch=batch)
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - w0) * 1e3 / reps
+    dev_ms = e0.elapsed_time(e1) / reps
+    num_ist = int(0.1 * n)
+    o = out[:num_ist]
+    ok = bool((dmaps[o[:, 0], o[:, 1], o[:, 2]] > 0).all()) and out.shape == ref.shape
+    if not ok:
+        raise RuntimeError("pixel sampler leg: an importance pixel with zero weight")
+    return {"workload": f"{n}-ray batch, {num_ist} importance pixels = 41 of {b} maps ({h}x{w} fp16) x 10 pixels + uniform remainder",
+            "device_ms": dev_ms, "device_wall_ms": wall_ms, "host_reference_ms": host_ms, "host_cores": torch.get_num_threads(),
+            "speedup": host_ms / wall_ms, "launches_per_batch": (_lib.launch_count() - k0) / reps,
+            "note": "same distribution, own random stream (Philox exponential race + radix select); the host path stays for bit-exact indices"}
+
+
 def cpu_baseline(rays_per_step: int, steps: int, warmup: int):
     """The oracle port of the reference's CPU torch path (oracle/kplanes_oracle.py) timed on the host cores:
     same cfg2 model and scene shape, full fwd+bwd+Adam steps on a bounded number of steps."""
@@ -927,6 +984,8 @@ def run_ours(args):
     if world == 1 and "torch" in legs:
         line["gpu_torch_baseline"] = gpu_torch_baseline(dev)
         line["gpu_torch_baseline"]["speedup_of_value"] = line["value"] / line["gpu_torch_baseline"]["value"]
+    if world == 1 and "sampler" in legs:
+        line["pixel_sampler"] = pixel_sampler_leg(dev)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(rays_per_step=RAYS_PER_RANK, steps=2, warmup=1)
     for leg in (line, line.get("cfg3") or {}):
@@ -977,7 +1036,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--legs", default="cfg2,cfg3,eval,cfg4,torch",
+    ap.add_argument("--legs", default="cfg2,cfg3,eval,cfg4,torch,sampler",
                     help="comma list of the extra objects of the JSON line: cfg3 (32x training leg), eval (full-frame inference, "
                          "needs cfg3), cfg4 (the sampler / compositing kernels on the nerfplayer-nerfacto shape), torch (reference step as torch CUDA ops, N=1).  cfg2 (the headline) always runs.")
     ap.add_argument("--eval-frames", type=int, default=2)
