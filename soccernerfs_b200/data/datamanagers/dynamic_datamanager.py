@@ -5,11 +5,17 @@ preset overrides at NS/configs/method_configs.py:491-511).  The reference's own 
 dataparsers, ray generator) is a caller of the hot path and is used unchanged when this package is plugged into
 nerfstudio; ``importance_weights`` / ``make_pixel_sampler`` below give the same behaviour to users of
 this package alone (synthetic data, tests).
+
+``DeviceImageCache`` + ``DynamicDataManager`` are the B200 form of the caller side: the reference keeps the collated image
+batch on the host (``CacheDataloader``, NS/data/utils/dataloaders.py:43-232), samples pixels there and ships rays to the GPU
+every step; a broadcast-style training set (19 cameras x 25 frames at 960x540: 2.9 GB fp32, plus 0.5 GB of weight maps) is
+1.6 % of one B200's HBM, so here the whole cache, its weight maps, the pixel sampler, the pixel gather and the ray generator
+live on the device and ``next_train`` (NS/data/datamanagers/base_datamanager.py:486-494) moves nothing over PCIe.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, Literal, Optional
+from typing import Any, Dict, Iterator, Literal, Optional, Tuple
 
 import torch
 
@@ -67,3 +73,69 @@ def make_pixel_sampler(config: DynamicDataManagerConfig, num_rays_per_batch: int
     if config.use_importance_sampling:
         return DynamicBasedPixelSampler(num_rays_per_batch, dataset=ImportanceState(config), **kwargs)
     return PixelSampler(num_rays_per_batch, **kwargs)
+
+
+class DeviceImageCache:
+    """``CacheDataloader`` in its cache-all-images mode (dataloaders.py:66-92, 208-232) with the collated batch on the
+    device: ``image`` [B,H,W,3] fp32, ``image_idx`` [B], the IST / ISG maps computed once by ``kp_ist_map`` /
+    ``kp_isg_map`` when importance sampling is on (``ist_weights`` fp16 [B,H,W]), optional ``depth_image`` / ``mask``;
+    iterating yields that batch with ``iter_steps`` counted up like the reference's loader (:230-231)."""
+
+    def __init__(self, images: torch.Tensor, config: DynamicDataManagerConfig, cam_ids: Optional[torch.Tensor] = None,
+                 cam_times: Optional[torch.Tensor] = None, device="cuda", image_idx: Optional[torch.Tensor] = None,
+                 extras: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        if images.dim() != 4 or images.shape[-1] != 3:
+            raise ValueError("DeviceImageCache: images must be [B,H,W,3]")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("DeviceImageCache keeps the image batch on a CUDA device (there is no CPU path)")
+        b = images.shape[0]
+        self.batch: Dict[str, Any] = {
+            "image": images.to(dev, dtype=torch.float32).contiguous(),
+            "image_idx": (torch.arange(b) if image_idx is None else image_idx).to(dev),
+        }
+        for k, v in (extras or {}).items():
+            self.batch[k] = v.to(dev)
+        if config.use_importance_sampling:
+            if cam_ids is None or (cam_times is None and not config.isg):
+                raise ValueError("importance sampling needs the cameras' ids (and times for IST)")
+            self.batch["ist_weights"] = importance_weights(config, self.batch["image"], cam_ids, cam_times, device=dev)
+        self.iter_step = 0
+
+    def __iter__(self) -> Iterator[Dict[str, Any]]:
+        while True:
+            self.iter_step += 1
+            self.batch["iter_steps"] = self.iter_step
+            yield self.batch
+
+
+class DynamicDataManager:
+    """The train side of ``DynamicDataManager`` / ``VanillaDataManager.next_train`` (dynamic_datamanager.py:60-113,
+    base_datamanager.py:486-494) on a device-resident image cache: pixel sampler -> pixel gather -> ray generator, every
+    tensor a CUDA tensor.  ``cameras``: one camera per cached image (nerfstudio's convention: ``image_idx`` indexes them),
+    carrying ``times`` and ``ids``."""
+
+    def __init__(self, config: DynamicDataManagerConfig, cameras, images: torch.Tensor, device="cuda",
+                 extras: Optional[Dict[str, torch.Tensor]] = None, **sampler_kwargs: Any) -> None:
+        from ...model_components.ray_generators import RayGenerator
+
+        self.config = config
+        self.device = torch.device(device)
+        self.cameras = cameras.to(self.device)
+        if len(self.cameras) != images.shape[0]:
+            raise ValueError(f"{images.shape[0]} images for {len(self.cameras)} cameras")
+        ids = getattr(cameras, "ids", None)
+        self.image_cache = DeviceImageCache(images, config, cam_ids=ids, cam_times=cameras.times, device=self.device,
+                                            extras=extras)
+        self.iter_train_image_dataloader = iter(self.image_cache)
+        self.train_pixel_sampler = make_pixel_sampler(config, config.train_num_rays_per_batch, **sampler_kwargs)
+        self.train_ray_generator = RayGenerator(self.cameras)
+        self.train_count = 0
+
+    def next_train(self, step: int) -> Tuple[Any, Dict[str, Any]]:
+        """-> (RayBundle, batch): base_datamanager.py:486-494."""
+        self.train_count += 1
+        image_batch = next(self.iter_train_image_dataloader)
+        batch = self.train_pixel_sampler.sample(image_batch)
+        ray_bundle = self.train_ray_generator(batch["indices"])
+        return ray_bundle, batch

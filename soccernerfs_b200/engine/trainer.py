@@ -598,12 +598,18 @@ class TrainStep:
 
     def _graphable(self, ray_bundle: RayBundle, batch) -> bool:
         """The captured step has static buffers for origins / directions / times / image only.  Anything else a batch or
-        bundle may carry and the model would USE (depth supervision, masks, per-ray metadata, camera indices for an
-        appearance embedding, real pixel areas, a static scene without times) runs through the eager iteration instead
-        of being dropped silently."""
-        if set(batch.keys()) - {"image"}:
+        bundle may carry and the model would USE (depth supervision and the directions_norm it needs, unknown per-ray
+        metadata, camera indices for an appearance embedding, preset near / far bounds of a crop box, a static scene
+        without times) runs through the eager iteration instead of being dropped silently.  What a datamanager's batch
+        carries and the model never reads (kplanes.py:392-449 reads ``image`` and ``depth_image`` only: ``indices``,
+        ``ist_weights``, ``mask`` ...) does not matter, nor does ``directions_norm`` without depth supervision."""
+        if "image" not in batch or "depth_image" in batch:
             return False
-        if ray_bundle.times is None or ray_bundle.metadata:
+        if ray_bundle.times is None or ray_bundle.nears is not None or ray_bundle.fars is not None:
+            return False
+        if ray_bundle.metadata and set(ray_bundle.metadata.keys()) - {"directions_norm"}:
+            return False
+        if getattr(self.model.field, "use_appearance_embedding", False):
             return False
         return True
 

@@ -195,3 +195,77 @@ def test_device_sampler_full_resolution_maps():
     print(f"\ndevice importance sampler: {t0.elapsed_time(t1) / 10:.3f} ms for 41 maps of {h}x{w} x 10 pixels")
     assert bool((maps[res[:, 0], res[:, 1], res[:, 2]] > 0).all()) and torch.equal(res[:, 0].cpu(), imgs.repeat_interleave(10))
     assert t0.elapsed_time(t1) / 10 < 20.0  # the host loop it replaces takes ~200 ms
+
+
+def _ring_cameras(n_cams, n_frames, h, w):
+    """One camera per image (nerfstudio's convention): n_cams cameras on a ring looking at the origin, n_frames each."""
+    from soccernerfs_b200.cameras.cameras import Cameras
+
+    c2w, times, ids = [], [], []
+    for c in range(n_cams):
+        ang = 2 * np.pi * c / n_cams
+        pos = torch.tensor([np.cos(ang), np.sin(ang), 0.35], dtype=torch.float32) * 1.2
+        z = pos / pos.norm()  # the camera looks along -z
+        x = torch.linalg.cross(torch.tensor([0.0, 0.0, 1.0]), z)
+        x = x / x.norm()
+        y = torch.linalg.cross(z, x)
+        m = torch.stack([x, y, z, pos], dim=-1)
+        for f in range(n_frames):
+            c2w.append(m)
+            times.append(f / (n_frames - 1))
+            ids.append(float(c))
+    return Cameras(torch.stack(c2w), 50.0, 50.0, w / 2, h / 2, w, h, times=torch.tensor(times)[:, None], ids=torch.tensor(ids)[:, None])
+
+
+def test_device_datamanager_feeds_the_graphed_train_step():
+    """DynamicDataManager.next_train on a device-resident image cache (IST maps by kp_ist_map, importance + uniform pixel
+    sampling, pixel gather, ray generation: all CUDA tensors) and its batches through the CUDA-graph train step: the keys a
+    datamanager adds (indices, ist_weights) and the bundle's directions_norm do not push the step off the graph."""
+    from soccernerfs_b200.data.datamanagers.dynamic_datamanager import DynamicDataManager, DynamicDataManagerConfig
+    from soccernerfs_b200.data.dynamic_dataset import compute_ist
+    from soccernerfs_b200.data.scene_box import SceneBox
+    from soccernerfs_b200.engine.trainer import TrainStep
+    from soccernerfs_b200.models.kplanes import KPlanesModelConfig
+
+    n_cams, n_frames, h, w = 4, 5, 36, 64
+    cams = _ring_cameras(n_cams, n_frames, h, w)
+    images = torch.full((n_cams * n_frames, h, w, 3), 0.2)
+    for c in range(n_cams):
+        for f in range(n_frames):  # a bright square that moves with time
+            x0 = 4 + 9 * f + c
+            images[c * n_frames + f, 10:22, x0: x0 + 12] = torch.tensor([0.9, 0.8, 0.1])
+    cfg = DynamicDataManagerConfig(train_num_rays_per_batch=512, is_pixel_ratio=0.25, ist_range=0.3, iters_to_start_is=3)
+    random.seed(1)
+    torch.manual_seed(1)
+    dm = DynamicDataManager(cfg, cams, images, device=DEV)
+    cache = dm.image_cache.batch
+    assert cache["image"].is_cuda and cache["ist_weights"].is_cuda and cache["ist_weights"].dtype == torch.float16
+    host_maps = compute_ist(images, cams.ids, cams.times, cfg.ist_range)
+    assert torch.equal(cache["ist_weights"].cpu(), host_maps) and int((host_maps > 0).sum()) > 1000
+    for step in range(6):
+        rb, batch = dm.next_train(step)
+        idx = batch["indices"]
+        assert idx.is_cuda and rb.origins.is_cuda and batch["image"].is_cuda and idx.shape == (512, 3)
+        assert torch.equal(batch["image"], cache["image"][idx[:, 0], idx[:, 1], idx[:, 2]])
+        assert torch.equal(rb.times, dm.cameras.times[idx[:, 0]]) and torch.equal(rb.camera_indices, idx[:, 0:1])
+        if step >= 3:  # iter_steps = step + 1 > iters_to_start_is: a quarter of the batch follows the maps
+            assert bool((batch["ist_weights"][:128] > 0).all())
+            # on the moving square (bright) or where it is in a neighbouring frame (background): 20-50 % bright expected,
+            # against 2 % of bright pixels under uniform sampling
+            assert float((batch["image"][:128].max(dim=-1).values > 0.5).float().mean()) > 0.06
+    model_cfg = KPlanesModelConfig(spacetime_resolution=(16, 16, 16, 5), multiscale_res=(1, 2), num_nerf_samples_per_ray=16,
+                                   num_proposal_samples_per_ray=(32, 24),
+                                   proposal_net_args_list=[{"feature_dim": 8, "resolution": [24, 24, 24, 5]},
+                                                           {"feature_dim": 8, "resolution": [32, 32, 32, 5]}])
+    model = model_cfg.setup(scene_box=SceneBox(aabb=torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]])), num_train_data=len(cams)).to(DEV)
+    trainer = TrainStep(model, max_steps=100, warm_up_end=2, use_cuda_graph=True)
+    losses = []
+    try:
+        for step in range(16):
+            rb, batch = dm.next_train(6 + step)
+            assert trainer._graphable(rb, batch)
+            losses.append(float(trainer(rb, batch)["loss"]))
+        assert trainer._graphs, "the step never reached its CUDA-graph replay"
+    finally:
+        trainer.close()
+    assert all(l == l and l < 1e3 for l in losses) and min(losses[8:]) < losses[0], losses
