@@ -897,7 +897,30 @@ def pixel_sampler_leg(dev, reps=20, host_reps=2):
     ok = bool((dmaps[o[:, 0], o[:, 1], o[:, 2]] > 0).all()) and out.shape == ref.shape
     if not ok:
         raise RuntimeError("pixel sampler leg: an importance pixel with zero weight")
-    return {"workload": f"{n}-ray batch, {num_ist} importance pixels = 41 of {b} maps ({h}x{w} fp16) x 10 pixels + uniform remainder",
+    # the whole caller side of a step on the device: DynamicDataManager.next_train = pixel sampler + pixel gather from the
+    # resident image cache (2.5 GB fp32) + ray generation, nothing over PCIe
+    from soccernerfs_b200.cameras.cameras import Cameras
+    from soccernerfs_b200.data.datamanagers.dynamic_datamanager import DynamicDataManager, DynamicDataManagerConfig
+
+    c2w = torch.eye(4)[:3][None].repeat(b, 1, 1)
+    c2w[:, :3, 3] = torch.randn(b, 3, generator=gen)
+    cams = Cameras(c2w, 1200.0, 1200.0, w / 2, h / 2, w, h, times=torch.rand(b, 1, generator=gen), ids=torch.arange(b).float()[:, None])
+    dm = DynamicDataManager(DynamicDataManagerConfig(train_num_rays_per_batch=n, use_importance_sampling=False), cams,
+                            torch.rand((b, h, w, 3), device=dev), device=dev)
+    dm.image_cache.batch["ist_weights"] = dmaps
+    dm.train_pixel_sampler = sampler
+    for _ in range(3):
+        rb, col = dm.next_train(0)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(reps):
+        rb, col = dm.next_train(0)
+    torch.cuda.synchronize()
+    next_train_ms = (time.perf_counter() - w0) * 1e3 / reps
+    if rb.origins.shape != (n, 3) or col["image"].shape != (n, 3) or not bool((col["ist_weights"][:num_ist] > 0).all()):
+        raise RuntimeError("pixel sampler leg: next_train returned an inconsistent batch")
+    return {"next_train_ms": next_train_ms,
+            "next_train": "DynamicDataManager.next_train on the device-resident cache: sampler + pixel gather + ray generation, wall clock","workload": f"{n}-ray batch, {num_ist} importance pixels = 41 of {b} maps ({h}x{w} fp16) x 10 pixels + uniform remainder",
             "device_ms": dev_ms, "device_wall_ms": wall_ms, "host_reference_ms": host_ms, "host_cores": torch.get_num_threads(),
             "speedup": host_ms / wall_ms, "launches_per_batch": (_lib.launch_count() - k0) / reps,
             "note": "same distribution, own random stream (Philox exponential race + radix select); the host path stays for bit-exact indices"}
