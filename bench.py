@@ -1008,7 +1008,12 @@ def run_ours(args):
         line["gpu_torch_baseline"] = gpu_torch_baseline(dev)
         line["gpu_torch_baseline"]["speedup_of_value"] = line["value"] / line["gpu_torch_baseline"]["value"]
     if world == 1 and "sampler" in legs:
-        line["pixel_sampler"] = pixel_sampler_leg(dev)
+        try:  # an accessory of the line: its failure is reported in the line, the headline still goes out
+            line["pixel_sampler"] = pixel_sampler_leg(dev)
+        except Exception as e:  # noqa: BLE001
+            line["pixel_sampler"] = {"error": repr(e)}
+            print(f"[bench] pixel_sampler leg failed: {e!r}", file=sys.stderr, flush=True)
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(rays_per_step=RAYS_PER_RANK, steps=2, warmup=1)
     for leg in (line, line.get("cfg3") or {}):
