@@ -523,6 +523,16 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
     last_loss = float(loss_host[n_steps - 1])
 
     leg = {}
+    # ---- arm 3 (N=1, headline config): the data side on the device too ---------------------------------------
+    # DynamicDataManager.next_train (importance + uniform pixel sampling on a resident 418-image cache, pixel gather, ray
+    # generation) feeding the same graphed step: the whole training iteration of the preset with nothing crossing PCIe
+    # but the loss.  An accessory of the line: a failure is reported inside it.
+    if world == 1 and name == "cfg2" and "sampler" in set(args.legs.split(",")):
+        try:
+            leg["device_pipeline"] = _device_pipeline_arm(trainer, timed_region, loss_host, dev, args)
+        except Exception as e:  # noqa: BLE001
+            leg["device_pipeline"] = {"error": repr(e)}
+            print(f"[bench] device pipeline arm failed: {e!r}", file=sys.stderr, flush=True)
     # ---- N>1: a longer run (the 20-step region is too short to separate ranks' skew from the collective) --------
     if world > 1 and not args.no_long_run:
         long_ms, long_rank = timed_region(step_resident, steps=100, warmup=3)
@@ -597,6 +607,62 @@ def train_leg(name, args, rank, world, local, dev, peaks, probe, keep_model=Fals
     del trainer, model, resident, flush
     torch.cuda.empty_cache()
     return leg, None
+
+
+def _device_pipeline_arm(trainer, timed_region, loss_host, dev, args):
+    """cfg2 fed by the device-resident datamanager: broadcast-style cameras (19 on a ring x 22 frames = 418 images of
+    960x540, NS/data/dataparsers/broadcaststyle_dataparser.py:196-232), 2.6 GB of fp32 images + 0.4 GB of fp16 weight maps
+    (1 % non-zero, IST-like) in HBM, is_pixel_ratio 0.1 after iters_to_start_is."""
+    import math
+    import types
+
+    from soccernerfs_b200.cameras.cameras import Cameras
+    from soccernerfs_b200.data.datamanagers.dynamic_datamanager import DynamicDataManager, DynamicDataManagerConfig
+    from soccernerfs_b200.data.pixel_samplers import DynamicBasedPixelSampler
+
+    n_cams, n_frames, h, w = 19, 22, 540, 960
+    b = n_cams * n_frames
+    c2w, times, ids = [], [], []
+    for c in range(n_cams):
+        ang = 2 * math.pi * c / n_cams
+        pos = torch.tensor([math.cos(ang), math.sin(ang), 0.35])
+        z = pos / pos.norm()
+        x = torch.linalg.cross(torch.tensor([0.0, 0.0, 1.0]), z)
+        x = x / x.norm()
+        m = torch.stack([x, torch.linalg.cross(z, x), z, pos], dim=-1)
+        for f in range(n_frames):
+            c2w.append(m), times.append(f / (n_frames - 1)), ids.append(float(c))
+    cams = Cameras(torch.stack(c2w), 800.0, 800.0, w / 2, h / 2, w, h, times=torch.tensor(times)[:, None], ids=torch.tensor(ids)[:, None])
+    gen = torch.Generator(device=dev).manual_seed(12)
+    images = torch.rand((b, h, w, 3), device=dev, generator=gen)
+    maps = torch.where(torch.rand((b, h, w), device=dev, generator=gen) < 0.01,
+                       torch.rand((b, h, w), device=dev, generator=gen) * 0.8 + 0.15, 0.0).half()
+    cfg = DynamicDataManagerConfig(train_num_rays_per_batch=RAYS_PER_RANK, use_importance_sampling=False)
+    state = types.SimpleNamespace(iters_to_start_ist=0, is_pixel_ratio=0.1)
+    out = {"workload": f"{b} cached images of {w}x{h} (fp32, {images.numel() * 4 / 2**30:.1f} GB) + fp16 weight maps in HBM; "
+                       f"{RAYS_PER_RANK} rays/step, 10 % importance pixels"}
+    rays = RAYS_PER_RANK * args.steps
+    for key, prefetch in (("serial", False), ("prefetch", True)):
+        dm = DynamicDataManager(cfg, cams, images, device=dev, prefetch=prefetch)
+        dm.image_cache.batch["ist_weights"] = maps  # synthetic maps (kp_ist_map's own cost is a once-per-cache cost)
+        dm.train_pixel_sampler = DynamicBasedPixelSampler(RAYS_PER_RANK, dataset=state)
+
+        def step_pipeline(i, dm=dm):
+            rb, batch = dm.next_train(i)
+            res = trainer(rb, batch)
+            loss_host[i].copy_(res["loss"], non_blocking=True)
+
+        ms, _ = timed_region(step_pipeline)
+        out[key] = {"value": rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / args.steps}
+        torch.cuda.current_stream().synchronize()
+        del dm
+    if not bool(torch.isfinite(loss_host).all()):
+        raise RuntimeError("device pipeline arm: non-finite loss")
+    out["value"] = max(out["serial"]["value"], out["prefetch"]["value"])
+    out["h2d_bytes_per_step"] = 41 * 3 * 4  # the (image, k, first row) table of the importance sampler
+    del images, maps
+    torch.cuda.empty_cache()
+    return out
 
 
 def _roofline(name, per_kernel, step_bytes, scales, peaks, probe):

@@ -116,7 +116,10 @@ class DynamicDataManager:
     carrying ``times`` and ``ids``."""
 
     def __init__(self, config: DynamicDataManagerConfig, cameras, images: torch.Tensor, device="cuda",
-                 extras: Optional[Dict[str, torch.Tensor]] = None, **sampler_kwargs: Any) -> None:
+                 extras: Optional[Dict[str, torch.Tensor]] = None, prefetch: bool = False, **sampler_kwargs: Any) -> None:
+        """``prefetch``: the batch ``next_train`` returns was produced on a side stream while the previous step ran, and
+        the next one is enqueued there before returning -- the ~0.5 ms of sampler / gather / ray-generation kernels and
+        their launch latencies leave the training stream (same batches in the same order as without it)."""
         from ...model_components.ray_generators import RayGenerator
 
         self.config = config
@@ -131,11 +134,41 @@ class DynamicDataManager:
         self.train_pixel_sampler = make_pixel_sampler(config, config.train_num_rays_per_batch, **sampler_kwargs)
         self.train_ray_generator = RayGenerator(self.cameras)
         self.train_count = 0
+        self._side = torch.cuda.Stream(device=self.device) if prefetch else None
+        self._ready = None  # (ray_bundle, batch, event) produced ahead on the side stream
+
+    def _produce(self) -> Tuple[Any, Dict[str, Any]]:
+        image_batch = next(self.iter_train_image_dataloader)
+        batch = self.train_pixel_sampler.sample(image_batch)
+        ray_bundle = self.train_ray_generator(batch["indices"])
+        return ray_bundle, batch
+
+    def _produce_ahead(self, main: torch.cuda.Stream) -> None:
+        self._side.wait_stream(main)  # after whatever the training stream did to the cache so far
+        with torch.cuda.stream(self._side):
+            ray_bundle, batch = self._produce()
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._ready = (ray_bundle, batch, done)
+
+    @staticmethod
+    def _tensors(ray_bundle, batch):
+        for t in (ray_bundle.origins, ray_bundle.directions, ray_bundle.pixel_area, ray_bundle.camera_indices,
+                  ray_bundle.nears, ray_bundle.fars, ray_bundle.times, *(ray_bundle.metadata or {}).values(), *batch.values()):
+            if torch.is_tensor(t) and t.is_cuda:
+                yield t
 
     def next_train(self, step: int) -> Tuple[Any, Dict[str, Any]]:
         """-> (RayBundle, batch): base_datamanager.py:486-494."""
         self.train_count += 1
-        image_batch = next(self.iter_train_image_dataloader)
-        batch = self.train_pixel_sampler.sample(image_batch)
-        ray_bundle = self.train_ray_generator(batch["indices"])
+        if self._side is None:
+            return self._produce()
+        main = torch.cuda.current_stream(self.device)
+        if self._ready is None:
+            self._produce_ahead(main)
+        ray_bundle, batch, done = self._ready
+        main.wait_event(done)
+        for t in self._tensors(ray_bundle, batch):
+            t.record_stream(main)  # allocated on the side stream, consumed on the training stream
+        self._produce_ahead(main)
         return ray_bundle, batch

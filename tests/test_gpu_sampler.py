@@ -253,6 +253,18 @@ def test_device_datamanager_feeds_the_graphed_train_step():
             # on the moving square (bright) or where it is in a neighbouring frame (background): 20-50 % bright expected,
             # against 2 % of bright pixels under uniform sampling
             assert float((batch["image"][:128].max(dim=-1).values > 0.5).float().mean()) > 0.06
+    # prefetch on a side stream: the same batches in the same order
+    seqs = []
+    for prefetch in (False, True):
+        random.seed(2)
+        torch.manual_seed(2)
+        d2 = DynamicDataManager(cfg, cams, images, device=DEV, prefetch=prefetch)
+        seqs.append([d2.next_train(i) for i in range(6)])
+    torch.cuda.synchronize()
+    for (rb_a, b_a), (rb_b, b_b) in zip(*seqs):
+        assert torch.equal(b_a["indices"], b_b["indices"]) and torch.equal(b_a["image"], b_b["image"])
+        assert torch.equal(rb_a.origins, rb_b.origins) and torch.equal(rb_a.directions, rb_b.directions)
+    dm = d2  # train from the prefetching manager
     model_cfg = KPlanesModelConfig(spacetime_resolution=(16, 16, 16, 5), multiscale_res=(1, 2), num_nerf_samples_per_ray=16,
                                    num_proposal_samples_per_ray=(32, 24),
                                    proposal_net_args_list=[{"feature_dim": 8, "resolution": [24, 24, 24, 5]},
