@@ -475,6 +475,7 @@ def main():
     gen_losses(R)
     gen_model(R)
     gen_importance(R)
+    gen_pixel_samplers(R)
     gen_raygen(R)
     gen_raygen_lens(R)
     gen_raygen_crop(R)
@@ -546,6 +547,24 @@ def gen_importance(R):
     torch.manual_seed(4321)
     uni = ps.PixelSampler(32).sample_method(32, b, h, w)
     save("importance", images=images, cam_ids=cam_ids, cam_times=cam_times, ist=ist.float(), isg=isg.float(), uniform=uni, **out)
+
+
+def gen_pixel_samplers(R):
+    """The two other pixel samplers DynamicDataManager._get_pixel_sampler can return (dynamic_datamanager.py:97-113):
+    EquirectangularPixelSampler (pixel_samplers.py:228-267) and PatchPixelSampler (:270-327), by the reference's own
+    classes under a fixed torch seed (the outputs are functions of torch's CPU random stream only)."""
+    from nerfstudio.data import pixel_samplers as ps
+
+    out = {}
+    torch.manual_seed(2468)
+    out["equirect"] = ps.EquirectangularPixelSampler(96).sample_method(96, 7, 40, 80)
+    torch.manual_seed(1357)
+    patch = ps.PatchPixelSampler(100, patch_size=4)
+    out["patch_rays"] = torch.tensor(patch.num_rays_per_batch)
+    out["patch"] = patch.sample_method(patch.num_rays_per_batch, 5, 30, 50)
+    patch.set_num_rays_per_batch(50)
+    out["patch_rays_after_set"] = torch.tensor(patch.num_rays_per_batch)
+    save("pixel_samplers", **out)
 
 
 def gen_raygen(R):

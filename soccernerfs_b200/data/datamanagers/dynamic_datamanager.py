@@ -20,7 +20,7 @@ from typing import Any, Dict, Iterator, Literal, Optional, Tuple
 import torch
 
 from ..dynamic_dataset import compute_isg, compute_ist
-from ..pixel_samplers import DynamicBasedPixelSampler, PixelSampler
+from ..pixel_samplers import DynamicBasedPixelSampler, EquirectangularPixelSampler, PatchPixelSampler, PixelSampler
 
 
 @dataclass
@@ -43,6 +43,8 @@ class DynamicDataManagerConfig:
     """Iterations before starting IST sampling."""
     pick_mode: Literal["normal", "randsteps", "lowfps"] = "normal"
     """Method for picking images in random loading."""
+    patch_size: int = 1
+    """Size of patch to sample from. If >1, patch-based sampling will be used (VanillaDataManagerConfig)."""
 
 
 class ImportanceState:
@@ -68,8 +70,13 @@ def importance_weights(config: DynamicDataManagerConfig, images: torch.Tensor, c
     return compute_ist(images, cam_ids, cam_times, config.ist_range, device=device)
 
 
-def make_pixel_sampler(config: DynamicDataManagerConfig, num_rays_per_batch: int, **kwargs: Any) -> PixelSampler:
-    """DynamicDataManager._get_pixel_sampler (dynamic_datamanager.py:97-113) without the patch / equirect cases."""
+def make_pixel_sampler(config: DynamicDataManagerConfig, num_rays_per_batch: int, cameras=None, **kwargs: Any) -> PixelSampler:
+    """DynamicDataManager._get_pixel_sampler (dynamic_datamanager.py:97-113): patches if ``patch_size > 1``, sphere-uniform
+    sampling if every camera is equirectangular, else the importance sampler (if enabled) or the uniform one."""
+    if config.patch_size > 1:
+        return PatchPixelSampler(num_rays_per_batch, patch_size=config.patch_size, **kwargs)
+    if cameras is not None and bool((cameras.camera_type == 3).all()):  # CameraType.EQUIRECTANGULAR
+        return EquirectangularPixelSampler(num_rays_per_batch, **kwargs)
     if config.use_importance_sampling:
         return DynamicBasedPixelSampler(num_rays_per_batch, dataset=ImportanceState(config), **kwargs)
     return PixelSampler(num_rays_per_batch, **kwargs)
@@ -131,7 +138,8 @@ class DynamicDataManager:
         self.image_cache = DeviceImageCache(images, config, cam_ids=ids, cam_times=cameras.times, device=self.device,
                                             extras=extras)
         self.iter_train_image_dataloader = iter(self.image_cache)
-        self.train_pixel_sampler = make_pixel_sampler(config, config.train_num_rays_per_batch, **sampler_kwargs)
+        self.train_pixel_sampler = make_pixel_sampler(config, config.train_num_rays_per_batch, cameras=self.cameras,
+                                                      **sampler_kwargs)
         self.train_ray_generator = RayGenerator(self.cameras)
         self.train_count = 0
         self._side = torch.cuda.Stream(device=self.device) if prefetch else None

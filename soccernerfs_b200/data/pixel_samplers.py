@@ -64,6 +64,53 @@ class PixelSampler:
         raise ValueError("image_batch['image'] must be a torch.Tensor")
 
 
+class EquirectangularPixelSampler(PixelSampler):
+    """Uniform over the SPHERE for equirectangular images (pixel_samplers.py:228-267): rows follow the density
+    sin(phi) / 2 by inverse-transform sampling, columns and images are uniform.  Three ``torch.rand(batch_size)`` draws in
+    the reference's order (image, row, column).  With a mask the reference falls back to the base sampler."""
+
+    def sample_method(self, batch_size: int, num_images: int, image_height: int, image_width: int,
+                      mask: Optional[torch.Tensor] = None, batch: Optional[Dict] = None,
+                      device: Union[torch.device, str] = "cpu") -> torch.Tensor:
+        if isinstance(mask, torch.Tensor):
+            return super().sample_method(batch_size, num_images, image_height, image_width, mask=mask, device=device)
+        image_u = torch.rand(batch_size, device=device)
+        row_u = torch.acos(1 - 2 * torch.rand(batch_size, device=device)) / torch.pi  # polar angle / pi in [0, 1]
+        col_u = torch.rand(batch_size, device=device)
+        extent = torch.tensor([num_images, image_height, image_width], device=device)
+        return torch.floor(torch.stack((image_u, row_u, col_u), dim=-1) * extent).long()
+
+
+class PatchPixelSampler(PixelSampler):
+    """Square patches for patch-based losses (pixel_samplers.py:270-327): ``batch_size // patch_size**2`` top-left corners
+    drawn uniformly (one ``torch.rand((n, 3))``), every patch expanded row-major.  The ray count is rounded down to whole
+    patches."""
+
+    def __init__(self, num_rays_per_batch: int, keep_full_image: bool = False, **kwargs) -> None:
+        self.patch_size = int(kwargs["patch_size"])
+        per_patch = self.patch_size**2
+        super().__init__(num_rays_per_batch // per_patch * per_patch, keep_full_image, **kwargs)
+
+    def set_num_rays_per_batch(self, num_rays_per_batch: int):
+        per_patch = self.patch_size**2
+        self.num_rays_per_batch = num_rays_per_batch // per_patch * per_patch
+
+    def sample_method(self, batch_size: int, num_images: int, image_height: int, image_width: int,
+                      mask: Optional[torch.Tensor] = None, batch: Optional[Dict] = None,
+                      device: Union[torch.device, str] = "cpu") -> torch.Tensor:
+        if mask is not None:  # (the reference tests ``if mask:``; a mask means the base sampler)
+            return super().sample_method(batch_size, num_images, image_height, image_width, mask=mask, device=device)
+        p = self.patch_size
+        n = batch_size // (p * p)
+        extent = torch.tensor([num_images, image_height - p, image_width - p], device=device)
+        corners = torch.rand((n, 3), device=device) * extent
+        offsets = torch.arange(p, device=device)
+        grid = corners.view(n, 1, 1, 3).repeat(1, p, p, 1)
+        grid[..., 1] += offsets.view(1, p, 1)
+        grid[..., 2] += offsets.view(1, 1, p)
+        return torch.floor(grid).long().reshape(-1, 3)
+
+
 class DynamicBasedPixelSampler(PixelSampler):
     """Samples ``is_pixel_ratio`` of the batch proportionally to the IST/ISG weight maps, the rest uniformly."""
 

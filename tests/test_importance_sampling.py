@@ -97,3 +97,37 @@ def test_isg_map_kernel_bit_exact_vs_reference_fixture():
     images = torch.rand(23, 20, 31, 3, generator=gen)
     cam_ids = torch.tensor([0] * 8 + [1] * 9 + [2] * 5 + [3])
     assert torch.equal(compute_isg(images.cuda(), cam_ids, 5e-2).cpu(), compute_isg(images, cam_ids, 5e-2))
+
+
+def test_equirectangular_and_patch_samplers_match_reference():
+    """EquirectangularPixelSampler / PatchPixelSampler (NS/data/pixel_samplers.py:228-327) vs the reference's own classes
+    under the same torch seed (fixture pixel_samplers): identical indices; and the sampler choice of
+    DynamicDataManager._get_pixel_sampler (dynamic_datamanager.py:97-113)."""
+    import types
+
+    from soccernerfs_b200.data.datamanagers.dynamic_datamanager import DynamicDataManagerConfig, make_pixel_sampler
+    from soccernerfs_b200.data.pixel_samplers import (DynamicBasedPixelSampler, EquirectangularPixelSampler, PatchPixelSampler,
+                                                      PixelSampler)
+
+    g = load_golden("pixel_samplers")
+    torch.manual_seed(2468)
+    eq = EquirectangularPixelSampler(96).sample_method(96, 7, 40, 80)
+    assert eq.dtype == torch.int64 and torch.equal(eq, g["equirect"])
+    assert int(eq[:, 1].max()) < 40 and int(eq[:, 2].max()) < 80 and int(eq[:, 0].max()) < 7
+    torch.manual_seed(1357)
+    patch = PatchPixelSampler(100, patch_size=4)
+    assert patch.num_rays_per_batch == int(g["patch_rays"]) == 96  # whole 4x4 patches only
+    idx = patch.sample_method(patch.num_rays_per_batch, 5, 30, 50)
+    assert torch.equal(idx, g["patch"])
+    blocks = idx.view(-1, 4, 4, 3)
+    assert bool((blocks[..., 0] == blocks[:, :1, :1, 0]).all())  # one image per patch, rows / columns contiguous
+    assert torch.equal(blocks[:, :, 0, 1] - blocks[:, :1, 0, 1], torch.arange(4).expand(blocks.shape[0], 4))
+    assert torch.equal(blocks[:, 0, :, 2] - blocks[:, 0, :1, 2], torch.arange(4).expand(blocks.shape[0], 4))
+    patch.set_num_rays_per_batch(50)
+    assert patch.num_rays_per_batch == int(g["patch_rays_after_set"]) == 48
+    cams = lambda t: types.SimpleNamespace(camera_type=torch.tensor(t)[:, None])  # noqa: E731
+    cfg = DynamicDataManagerConfig()
+    assert type(make_pixel_sampler(cfg, 64, cameras=cams([3, 3]))) is EquirectangularPixelSampler
+    assert type(make_pixel_sampler(cfg, 64, cameras=cams([1, 3]))) is DynamicBasedPixelSampler
+    assert type(make_pixel_sampler(DynamicDataManagerConfig(patch_size=2), 64, cameras=cams([3, 3]))) is PatchPixelSampler
+    assert type(make_pixel_sampler(DynamicDataManagerConfig(use_importance_sampling=False), 64)) is PixelSampler
