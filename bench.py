@@ -21,6 +21,9 @@ Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[1] ("K-Planes defau
   "pixel_sampler"      (N=1 only) the importance pixel sampler of the preset's shape (4096-ray batch, 10 % importance
                        pixels = 41 maps of 540x960 x 10 pixels): kp_importance_pixels on the device next to the reference's
                        per-image torch.multinomial loop on the host cores;
+  "device_pipeline"    (N=1 only) the headline step fed by the device-resident datamanager (importance + uniform pixel
+                       sampling on a 418-image cache in HBM, pixel gather, ray generation): rays/s of next_train + step,
+                       serial and with the batch prefetched on a side stream;
   "cpu_baseline"       the oracle port on the host cores (N=1 only);
   "dp_check"           (N>1) parameters bit-identical across ranks after all steps, and the all-reduced gradient equal to
                        a single-rank gradient on the concatenated batch.
