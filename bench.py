@@ -1053,7 +1053,7 @@ def run_ours(args):
             "per_scale": cfg2["per_scale"], "rank_ms_per_step": cfg2["rank_ms_per_step"], "clocks": cfg2["clocks"],
             "l2_peaks": probe, "hbm_peak": {"gbs": peaks["hbm_gbs"], "source": peak_kind},
         }
-        for k in ("long_run", "reference_schedule", "dp_check"):
+        for k in ("long_run", "reference_schedule", "dp_check", "device_pipeline"):
             if k in cfg2:
                 line[k] = cfg2[k]
     if "cfg3" in legs:
