@@ -58,6 +58,8 @@ class Cameras:
         h = height if height is not None else (self.cy * 2).to(torch.int64)
         w = width if width is not None else (self.cx * 2).to(torch.int64)
         self.height, self.width = _col(h, n, dev, torch.int64), _col(w, n, dev, torch.int64)
+        # host copies: reading a size back from the device would synchronise every tile of a frame
+        self._height_host, self._width_host = self.height.view(-1).tolist(), self.width.view(-1).tolist()
         self.times = None if times is None else times.to(dev).float().reshape(n, 1).contiguous()
         self.ids = ids
         self._intrinsics = None
@@ -189,7 +191,7 @@ class Cameras:
         if isinstance(camera_indices, int):
             cam = camera_indices
             if coords is None:  # the whole frame of one camera, [H,W] rays (cameras.py:405-440 case 1)
-                h, w = int(self.height[cam]), int(self.width[cam])
+                h, w = self._height_host[cam], self._width_host[cam]
                 rb = self.generate_tile(cam, 0, h * w, aabb_box=aabb_box, disable_distortion=disable_distortion)
                 return rb.reshape((h, w)) if keep_shape in (None, True) else rb
             camera_indices = torch.full((*coords.shape[:-1], 1), cam, dtype=torch.int64, device=coords.device)
@@ -229,7 +231,7 @@ class Cameras:
     def generate_tile(self, camera_index: int, start: int, end: int, aabb_box: Optional[SceneBox] = None,
                       disable_distortion: bool = False) -> RayBundle:
         """Rays of the row-major pixels [start, end) of one camera's frame (flat)."""
-        w = int(self.width[camera_index])
+        w = self._width_host[camera_index]
         out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, cam=int(camera_index), width=w,
                                 first_pixel=int(start), n=int(end - start), distortion=self._lens(disable_distortion),
                                 cam_types=self._cam_types)

@@ -152,7 +152,10 @@ class DynamicDataManager:
         return ray_bundle, batch
 
     def _produce_ahead(self, main: torch.cuda.Stream) -> None:
-        self._side.wait_stream(main)  # after whatever the training stream did to the cache so far
+        if self._ready is None:
+            self._side.wait_stream(main)  # the cache and its weight maps were built on the calling stream
+        # later batches read only those constants and allocate their own outputs: no dependency on the training stream,
+        # so the producer is NOT made to wait for the step in flight (that would serialise it behind the step again)
         with torch.cuda.stream(self._side):
             ray_bundle, batch = self._produce()
             done = torch.cuda.Event()

@@ -21,6 +21,21 @@ from typing import Dict, Optional, Union
 import torch
 
 
+_EXTENTS: Dict = {}
+
+
+def _extent(values, device) -> torch.Tensor:
+    """``torch.tensor([num_images, H, W], device=device)``, cached: building it from a Python list is a blocking
+    host-to-device copy, i.e. a stream synchronisation per step once the sampler runs on the GPU."""
+    key = (tuple(int(v) for v in values), str(device))
+    t = _EXTENTS.get(key)
+    if t is None:
+        if len(_EXTENTS) > 64:
+            _EXTENTS.clear()
+        t = _EXTENTS[key] = torch.tensor(list(key[0]), device=device)
+    return t
+
+
 class PixelSampler:
     def __init__(self, num_rays_per_batch: int, keep_full_image: bool = False, **kwargs) -> None:
         self.kwargs = kwargs
@@ -39,7 +54,7 @@ class PixelSampler:
             chosen = random.sample(range(len(nonzero_indices)), k=batch_size)
             return nonzero_indices[chosen]
         return torch.floor(
-            torch.rand((batch_size, 3), device=device) * torch.tensor([num_images, image_height, image_width], device=device)
+            torch.rand((batch_size, 3), device=device) * _extent((num_images, image_height, image_width), device)
         ).long()
 
     def collate_image_dataset_batch(self, batch: Dict, num_rays_per_batch: int, keep_full_image: bool = False):
@@ -77,7 +92,7 @@ class EquirectangularPixelSampler(PixelSampler):
         image_u = torch.rand(batch_size, device=device)
         row_u = torch.acos(1 - 2 * torch.rand(batch_size, device=device)) / torch.pi  # polar angle / pi in [0, 1]
         col_u = torch.rand(batch_size, device=device)
-        extent = torch.tensor([num_images, image_height, image_width], device=device)
+        extent = _extent((num_images, image_height, image_width), device)
         return torch.floor(torch.stack((image_u, row_u, col_u), dim=-1) * extent).long()
 
 
@@ -102,7 +117,7 @@ class PatchPixelSampler(PixelSampler):
             return super().sample_method(batch_size, num_images, image_height, image_width, mask=mask, device=device)
         p = self.patch_size
         n = batch_size // (p * p)
-        extent = torch.tensor([num_images, image_height - p, image_width - p], device=device)
+        extent = _extent((num_images, image_height - p, image_width - p), device)
         corners = torch.rand((n, 3), device=device) * extent
         offsets = torch.arange(p, device=device)
         grid = corners.view(n, 1, 1, 3).repeat(1, p, p, 1)
