@@ -89,35 +89,68 @@ struct WalkState {
   int need, take_all;
 };
 
-__device__ __forceinline__ WalkState block_walk(const SamplerArgs& a, int j, int passes, int k, uint32_t* s_prev, WalkState* s_state) {
-  for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) s_prev[i] = a.hist[(int64_t)j * 1024 + i];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    WalkState st;
-    select_walk(s_prev, passes, k, &st.prefix, &st.need, &st.take_all, &st.nnz);
-    *s_state = st;
+// select_walk (pixel_sampler_math.cuh) by the whole 256-thread block: thread b holds bin b of a pass's histogram, a block
+// suffix scan gives the number of keys in higher bins, and the one bin where that count crosses `need` announces itself.
+// (A single thread walking the 4 x 256 bins took 15 us per block -- more than the sweep over the map it precedes.)
+struct WalkScratch {
+  uint32_t warp_sum[8];
+  uint32_t bin, above;
+};
+
+__device__ __forceinline__ WalkState block_walk(const SamplerArgs& a, int j, int passes, int k, WalkScratch* s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WalkState st;
+  st.prefix = 0, st.nnz = 0, st.need = k, st.take_all = 0;
+  for (int p = 0; p < passes; ++p) {
+    const uint32_t h = a.hist[((int64_t)j * 4 + p) * 256 + tid];
+    uint32_t incl = h;  // keys in bins tid .. end of this warp's 32 bins
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    if (lane == 0) s->warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t total = 0, higher_warps = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t t = s->warp_sum[w];
+      total += t;
+      higher_warps += w > warp ? t : 0u;
+    }
+    const uint32_t above = incl - h + higher_warps;  // keys in bins > tid
+    if (p == 0) {
+      st.nnz = total;
+      st.take_all = total <= (uint32_t)k ? 1 : 0;
+    }
+    if (st.take_all) break;  // uniform over the block
+    const uint32_t need = (uint32_t)st.need;
+    // bin 0 is also where the serial walk stops when the count never reaches `need`
+    const bool mine = tid == 0 ? above < need : (above < need && above + h >= need);
+    if (mine) s->bin = (uint32_t)tid, s->above = above;
+    __syncthreads();
+    st.prefix = (st.prefix << 8) | s->bin;
+    st.need -= (int)s->above;
+    __syncthreads();  // warp_sum / bin / above are rewritten by the next pass
   }
-  __syncthreads();
-  return *s_state;
+  return st;
 }
 
 template <int PASS>
 __global__ void __launch_bounds__(256) sampler_hist_kernel(const __grid_constant__ SamplerArgs a) {
   __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_prev[PASS > 0 ? PASS * 256 : 1];
-  __shared__ WalkState s_state;
+  __shared__ WalkScratch s_walk;
   const int j = blockIdx.y;
   const Selected s = load_sel(a, j);
   if (s.k == 0) return;
   s_hist[threadIdx.x] = 0;
   uint32_t prefix = 0;
   if (PASS > 0) {
-    const WalkState st = block_walk(a, j, PASS, s.k, s_prev, &s_state);
+    const WalkState st = block_walk(a, j, PASS, s.k, &s_walk);
     if (st.take_all) return;  // at most k non-zero pixels: no threshold to find
     prefix = st.prefix;
-  } else {
-    __syncthreads();
   }
+  __syncthreads();
   constexpr int shift = 24 - 8 * PASS;
   for_each_nonzero(a, s.img, [&](int64_t, float, uint32_t bits) {
     bool mine = true;
@@ -130,12 +163,11 @@ __global__ void __launch_bounds__(256) sampler_hist_kernel(const __grid_constant
 }
 
 __global__ void __launch_bounds__(256) sampler_collect_kernel(const __grid_constant__ SamplerArgs a) {
-  __shared__ uint32_t s_prev[4 * 256];
-  __shared__ WalkState s_state;
+  __shared__ WalkScratch s_walk;
   const int j = blockIdx.y;
   const Selected s = load_sel(a, j);
   if (s.k == 0) return;
-  const WalkState st = block_walk(a, j, 4, s.k, s_prev, &s_state);
+  const WalkState st = block_walk(a, j, 4, s.k, &s_walk);
   const int64_t base = (int64_t)j * a.k_max;
   const int n_above = s.k - st.need;  // keys strictly above the threshold (select_walk)
   for_each_nonzero(a, s.img, [&](int64_t pix, float w, uint32_t bits) {
@@ -165,14 +197,13 @@ constexpr int kSortedInSmem = 2048;
 
 // One block per selected image: order the collected pixels and write the (image, row, col) triplets.
 __global__ void __launch_bounds__(256) sampler_finalize_kernel(const __grid_constant__ SamplerArgs a) {
-  __shared__ uint32_t s_prev[256];
-  __shared__ WalkState s_state;
+  __shared__ WalkScratch s_walk;
   __shared__ int32_t s_pix[kSortedInSmem];
   __shared__ float s_w[kSortedInSmem];
   const int j = blockIdx.x;
   const Selected s = load_sel(a, j);
   if (s.k == 0) return;
-  const WalkState st = block_walk(a, j, 1, s.k, s_prev, &s_state);
+  const WalkState st = block_walk(a, j, 1, s.k, &s_walk);
   const int64_t base = (int64_t)j * a.k_max;
   const int n_c = st.take_all ? (int)st.nnz : s.k;
   if (st.nnz == 0) {  // an all-zero map has nothing to draw from (the reference's loop skips it, :391-393): rows of -1
