@@ -810,6 +810,13 @@ def importance_pixels(weights: torch.Tensor, sel: torch.Tensor, k_max: int, n_ou
     if n_sel == 0 or n_out == 0:
         return out
     if not sel.is_cuda:
+        # a table that arrives on the host is checked like tensor indexing would be (rows the kernel writes must lie inside
+        # `out`); a device-resident table is trusted -- checking it would cost a synchronisation
+        img, k, first = sel[:, 0], sel[:, 1], sel[:, 2]
+        if int(img.min()) < 0 or int(img.max()) >= b:
+            raise IndexError(f"importance_pixels: image index out of range [0, {b})")
+        if int(k.min()) < 0 or int(k.max()) > int(k_max) or int(first.min()) < 0 or int((first + k).max()) > n_out:
+            raise IndexError("importance_pixels: a table entry's rows [first, first + k) leave the output or k exceeds k_max")
         sel = sel.contiguous().pin_memory().to(dev, non_blocking=True)
     nbytes = int(_lib.load().kp_importance_pixels_scratch_bytes(n_sel, int(k_max)))
     key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
