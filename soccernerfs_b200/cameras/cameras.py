@@ -68,6 +68,16 @@ class Cameras:
         self._cam_types = None if plain else self.camera_type.view(-1).to(torch.int32).contiguous()
         self._distortion = self.distortion_params
 
+    @classmethod
+    def from_reference(cls, cameras, device=None) -> "Cameras":
+        """A flat batch of the reference's ``Cameras`` (NS/cameras/cameras.py:56-146; same field names, read by duck
+        typing) -> this class, on ``device`` (default: where the reference object lives)."""
+        dev = cameras.camera_to_worlds.device if device is None else device
+        to = lambda t: None if t is None else t.to(dev)  # noqa: E731
+        return cls(to(cameras.camera_to_worlds), to(cameras.fx), to(cameras.fy), to(cameras.cx), to(cameras.cy),
+                   width=to(cameras.width), height=to(cameras.height), distortion_params=getattr(cameras, "distortion_params", None),
+                   camera_type=cameras.camera_type, times=getattr(cameras, "times", None), ids=getattr(cameras, "ids", None))
+
     @staticmethod
     def _parse_camera_type(camera_type, n: int, dev) -> torch.Tensor:
         """cameras.py:178-218: CameraType | List[CameraType] | int | integer tensor -> int64 [n,1]; values outside the

@@ -135,3 +135,32 @@ def test_method_specification_retargets_the_reference_trainer_config():
     assert spec.config.method_name == "k-planes" and spec.config.pipeline.model._target is KPlanesModel
     assert base.pipeline.model._target is rk.KPlanesModel  # the reference's preset object itself is not modified
     assert spec.config.pipeline.datamanager == dm
+
+
+def test_cameras_from_reference_cameras():
+    """Cameras.from_reference reads the reference's own Cameras (NS/cameras/cameras.py:56-146) by its field names: poses,
+    intrinsics, sizes, per-camera types, OpenCV distortion, times and ids arrive unchanged (host logic only)."""
+    from soccernerfs_b200.cameras.cameras import Cameras
+
+    ref_loader.load_reference()
+    from nerfstudio.cameras.cameras import Cameras as RefCameras
+    from nerfstudio.cameras.cameras import CameraType as RefCameraType
+
+    g = torch.Generator().manual_seed(3)
+    n = 4
+    c2w = torch.cat([torch.linalg.qr(torch.randn(n, 3, 3, generator=g)).Q, torch.randn(n, 3, 1, generator=g)], dim=-1)
+    dist = torch.tensor([[0.1, -0.02, 0.0, 0.0, 0.001, 0.002]]).repeat(n, 1)
+    ref = RefCameras(camera_to_worlds=c2w, fx=torch.rand(n, 1, generator=g) * 100 + 500, fy=600.0, cx=480.0, cy=270.0, width=960,
+                     height=540, distortion_params=dist, times=torch.rand(n, 1, generator=g), ids=torch.arange(n).float()[:, None],
+                     camera_type=[RefCameraType.PERSPECTIVE, RefCameraType.FISHEYE, RefCameraType.PERSPECTIVE, RefCameraType.EQUIRECTANGULAR])
+    ours = Cameras.from_reference(ref)
+    assert len(ours) == n and torch.equal(ours.camera_to_worlds, ref.camera_to_worlds)
+    for name in ("fx", "fy", "cx", "cy", "times"):
+        assert torch.equal(getattr(ours, name), getattr(ref, name)), name
+    assert torch.equal(ours.width, ref.width.long()) and torch.equal(ours.height, ref.height.long())
+    assert torch.equal(ours.camera_type, ref.camera_type.long()) and ours._cam_types.tolist() == [1, 2, 1, 3]
+    assert torch.equal(ours.distortion_params, ref.distortion_params) and torch.equal(ours.ids, ref.ids)
+    assert ours._height_host == [540] * n and ours._width_host == [960] * n
+    plain = Cameras.from_reference(RefCameras(camera_to_worlds=c2w, fx=500.0, fy=500.0, cx=480.0, cy=270.0,
+                                              distortion_params=torch.zeros(6)))  # what the dataparsers build without k1..p2
+    assert plain._distortion is None and plain._cam_types is None and plain._width_host == [960] * n
