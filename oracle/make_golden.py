@@ -429,6 +429,7 @@ def gen_field_depths(R):
     *_hidden_dim, kplanes.py:96-103 -> tcnn n_hidden_layers / n_neurons, kplanes_field.py:249-273), by the reference's own
     KPlanesField: (a) two hidden sigma layers of 32 and one hidden colour layer of 48, view-dependent; (b) no hidden
     sigma layer at all and three hidden colour layers, disable_viewing_dependent.  Outputs and all gradients."""
+    torch.manual_seed(97531)  # the reference fields' initial weights come from the global generator
     g = torch.Generator().manual_seed(654)
     res, ms, c = (12, 10, 14, 5), (1, 2), 8
     n, s = 80, 5
@@ -475,12 +476,13 @@ def main():
     gen_losses(R)
     gen_model(R)
     gen_importance(R)
-    gen_pixel_samplers(R)
     gen_raygen(R)
+    gen_samplers_cfg4(R)
+    gen_field_variants(R)  # (its reference modules draw their initial weights from torch's GLOBAL generator, whose state
+    # here is what the generators above left: later additions go below, and seed the global generator themselves)
     gen_raygen_lens(R)
     gen_raygen_crop(R)
-    gen_samplers_cfg4(R)
-    gen_field_variants(R)
+    gen_pixel_samplers(R)
     gen_field_depths(R)
 
 
