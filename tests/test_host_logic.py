@@ -255,3 +255,37 @@ def test_reference_optimizer_state_round_trip():
                 a, b = opts[0].optimizers[group].state[p], opts[1].optimizers[group].state[q]
                 assert b["step"] == 7 and torch.equal(a["exp_avg"], b["exp_avg"]) and torch.equal(a["exp_avg_sq"], b["exp_avg_sq"])
                 assert b["exp_avg"].stride() == q.stride()
+
+
+def test_graph_capture_eligibility_of_a_batch():
+    """TrainStep._graphable: the captured step has static buffers for origins / directions / times / image only, so a
+    batch or bundle carrying something the model would USE (depth supervision, preset near / far bounds, unknown per-ray
+    metadata, an appearance embedding's camera indices, no times) takes the eager iteration; what a datamanager adds and
+    the model never reads (indices, ist_weights, mask, directions_norm without depth supervision) does not."""
+    import types
+
+    import torch
+
+    from soccernerfs_b200.cameras.rays import RayBundle
+    from soccernerfs_b200.engine.trainer import TrainStep
+
+    n = 4
+    me = types.SimpleNamespace(model=types.SimpleNamespace(field=types.SimpleNamespace(use_appearance_embedding=False)))
+    ok = lambda rb, batch: TrainStep._graphable(me, rb, batch)  # noqa: E731
+
+    def bundle(**kw):
+        base = dict(origins=torch.zeros(n, 3), directions=torch.ones(n, 3), pixel_area=torch.ones(n, 1), times=torch.zeros(n, 1))
+        base.update(kw)
+        return RayBundle(**base)
+
+    image = {"image": torch.zeros(n, 3)}
+    assert ok(bundle(), image)
+    assert ok(bundle(metadata={"directions_norm": torch.ones(n, 1)}, camera_indices=torch.zeros(n, 1, dtype=torch.long)),
+              {**image, "indices": torch.zeros(n, 3), "ist_weights": torch.zeros(n), "mask": torch.ones(n, 1)})
+    assert not ok(bundle(), {**image, "depth_image": torch.ones(n, 1)})
+    assert not ok(bundle(), {"indices": torch.zeros(n, 3)})
+    assert not ok(bundle(times=None), image)
+    assert not ok(bundle(nears=torch.zeros(n, 1), fars=torch.ones(n, 1)), image)
+    assert not ok(bundle(metadata={"directions_norm": torch.ones(n, 1), "something_else": torch.ones(n, 1)}), image)
+    me.model.field.use_appearance_embedding = True
+    assert not ok(bundle(), image)
