@@ -168,8 +168,9 @@ class DynamicBasedPixelSampler(PixelSampler):
         if not sel:
             return torch.zeros((0, 3), dtype=torch.int64, device=weights.device)
         seed = random.getrandbits(63)  # from the same (seedable) python generator that shuffled the images
-        return ops.importance_pixels(weights, torch.tensor(sel, dtype=torch.int32), max(k for _, k, _ in sel), sampled,
-                                     image_width, seed)
+        # (a non-contiguous map tensor is copied here, AFTER the cached non-zero test above was keyed on the caller's tensor)
+        return ops.importance_pixels(weights.contiguous(), torch.tensor(sel, dtype=torch.int32), max(k for _, k, _ in sel),
+                                     sampled, image_width, seed)
 
     def sample_method(self, batch_size: int, num_images: int, image_height: int, image_width: int,
                       mask: Optional[torch.Tensor] = None, batch: Optional[Dict] = None,
@@ -186,7 +187,7 @@ class DynamicBasedPixelSampler(PixelSampler):
                 raise RuntimeError("device_sampler=True needs fp16 CUDA weight maps (there is no CPU path)")
             num_ist = floor(self.dataset.is_pixel_ratio * batch_size)
             per_image = 10 * (-(-num_ist // num_images))
-            indices = self._sample_ist_device(weights.contiguous(), num_ist, per_image, num_images, image_width)
+            indices = self._sample_ist_device(weights, num_ist, per_image, num_images, image_width)
             uniform = super().sample_method(batch_size - indices.shape[0], num_images, image_height, image_width, mask=mask,
                                             device=weights.device)
             return torch.cat((indices, uniform.to(weights.device)), dim=0)
