@@ -75,14 +75,24 @@ def test_host_build_of_the_sampler_math_matches_the_restatement(host_binary):
 
 
 def test_radix_select_with_tied_keys(host_binary):
-    """Equal weights met by equal random words give equal keys: the select must ask for exactly the missing number of
-    ties.  16 pixels of one Philox group pattern cannot tie by construction, so ties are forced through the histogram
-    walk itself with a hand-made histogram chain."""
-    # emulate via the python restatement of the walk on synthetic keys: many duplicates
-    keys = np.array([7, 7, 7, 5, 5, 3, 9, 9, 1], dtype=np.uint32) << np.uint32(20)
-    for k in range(1, len(keys)):
-        t, need = ds.select_threshold(keys, k)
-        assert np.count_nonzero(keys > t) + need == k and need <= np.count_nonzero(keys == t)
+    """Equal keys at the threshold: the four-pass select of the host build (histograms + select_walk exactly as the kernels
+    run them) must arrive at the k-th largest key and ask for exactly the missing number of ties -- hand-made keys with
+    many duplicates, differing in every byte position."""
+    rng = np.random.default_rng(9)
+    base = np.array([0x3F800000, 0x3F800001, 0x3F800100, 0x3F810000, 0x40000000, 0x3F7FFFFF, 0x00000001], dtype=np.uint32)
+    keys = np.concatenate([np.repeat(base, rng.integers(1, 9, size=len(base))), np.zeros(5, dtype=np.uint32)])
+    rng.shuffle(keys)
+    n_keys = int(np.count_nonzero(keys))
+    for k in range(1, n_keys):
+        req = struct.pack("<iiQi", len(keys), -1, 0, k) + keys.tobytes()
+        res = subprocess.run([host_binary], input=req, stdout=subprocess.PIPE, check=True).stdout
+        prefix, need, take_all, nnz = struct.unpack("<IiiI", res[4 * len(keys):])
+        t, nd = ds.select_threshold(keys[keys > 0], k)
+        assert (prefix, need, take_all, nnz) == (t, nd, 0, n_keys), k
+        assert np.count_nonzero(keys > prefix) + need == k and 1 <= need <= np.count_nonzero(keys == prefix)
+    req = struct.pack("<iiQi", len(keys), -1, 0, n_keys) + keys.tobytes()  # k == number of keys: everything is taken
+    res = subprocess.run([host_binary], input=req, stdout=subprocess.PIPE, check=True).stdout
+    assert struct.unpack("<IiiI", res[4 * len(keys):])[2:] == (1, n_keys)
 
 
 def test_race_has_the_multinomial_distribution():

@@ -1,11 +1,13 @@
 // Host build of soccernerfs_b200/csrc/pixel_sampler_math.cuh (the device sampler's arithmetic is plain C++):
 //   g++ -O1 -ffp-contract=off -I <repo>/soccernerfs_b200/csrc pixel_sampler_host.cpp -o pixel_sampler_host
 // stdin (binary): int32 n, int32 image, uint64 seed, int32 k, float32 weights[n]
+//                 (image == -1: the payload is uint32 key bits instead of weights, 0 = no key: hand-made keys with ties)
 // stdout (binary): uint32 key_bits[n] (0 where the weight is 0), then what a four-pass radix select over those keys
 //                  arrives at: uint32 threshold, int32 need, int32 take_all, uint32 nnz
 // tests/test_device_sampler_math.py compares both with oracle/device_sampler.py.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "pixel_sampler_math.cuh"
@@ -17,7 +19,11 @@ int main() {
   std::vector<float> w(n);
   if (fread(w.data(), 4, n, stdin) != (size_t)n) return 1;
   std::vector<uint32_t> bits(n, 0u);
-  for (int64_t g = 0; g * 4 < n; ++g) {
+  if (image == -1) {
+    memcpy(bits.data(), w.data(), 4 * (size_t)n);
+    for (int i = 0; i < n; ++i) w[i] = bits[i] ? 1.f : 0.f;
+  }
+  for (int64_t g = 0; image != -1 && g * 4 < n; ++g) {
     const kp::Philox4 r = kp::philox4x32_10((uint32_t)g, (uint32_t)image, kp::kSamplerStreamRace, (uint32_t)(g >> 32),
                                             (uint32_t)seed, (uint32_t)(seed >> 32));
     for (int q = 0; q < 4 && g * 4 + q < n; ++q)
