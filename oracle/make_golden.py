@@ -1,6 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the REAL reference modules.
 
 Run in the build container (needs /root/reference):   python -m oracle.make_golden
+                                                        python -m oracle.make_golden --check   (regenerate into a scratch
+                                                        directory and compare with the committed fixtures, array by array)
 
 Every fixture stores the seeded inputs and the outputs the reference's own code produced for them
 (``oracle/ref_loader.py`` explains the five stub modules).  ``tests/test_oracle_golden.py`` then pins
@@ -738,5 +740,37 @@ def gen_samplers_cfg4(R):
     save("samplers_cfg4", **arrs)
 
 
+def check() -> list:
+    """Regenerate every fixture into a scratch directory and compare it with the committed one (same keys, arrays equal
+    bit for bit, NaNs in the same places).  -> names of the fixtures that differ or are missing on either side."""
+    import tempfile
+
+    global OUT
+    committed = OUT
+    with tempfile.TemporaryDirectory() as tmp:
+        # gen_raygen_crop reads raygen.npz from OUT: the scratch copy it finds there was written by this very run
+        OUT = tmp
+        try:
+            main()
+        finally:
+            OUT = committed
+        names = sorted({f for d in (committed, tmp) for f in os.listdir(d) if f.endswith(".npz")})
+        bad = []
+        for f in names:
+            pa, pb = os.path.join(committed, f), os.path.join(tmp, f)
+            if not (os.path.exists(pa) and os.path.exists(pb)):
+                bad.append(f)
+                continue
+            a, b = np.load(pa), np.load(pb)
+            if set(a.files) != set(b.files) or not all(
+                    a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == "f") for k in a.files):
+                bad.append(f)
+    return bad
+
+
 if __name__ == "__main__":
+    if "--check" in sys.argv[1:]:
+        differing = check()
+        print("fixtures that do not reproduce:", differing if differing else "none")
+        sys.exit(1 if differing else 0)
     main()

@@ -164,3 +164,15 @@ def test_cameras_from_reference_cameras():
     plain = Cameras.from_reference(RefCameras(camera_to_worlds=c2w, fx=500.0, fy=500.0, cx=480.0, cy=270.0,
                                               distortion_params=torch.zeros(6)))  # what the dataparsers build without k1..p2
     assert plain._distortion is None and plain._cam_types is None and plain._width_host == [960] * n
+
+
+def test_committed_fixtures_reproduce_from_the_reference():
+    """oracle/make_golden.py run against the reference checkout regenerates every committed tests/golden/*.npz bit for bit
+    (what pins the oracle, and through it the CUDA path, to the reference's own outputs)."""
+    from oracle import make_golden
+
+    threads = torch.get_num_threads()
+    try:
+        assert make_golden.check() == []
+    finally:
+        torch.set_num_threads(threads)
