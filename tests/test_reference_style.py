@@ -166,3 +166,29 @@ def test_tensor_dataclass_broadcast_reshape_index():
     assert t[..., 1].a.shape == (4, 3) and t[0].shape == (6,) and t[0, ...].a.shape == (6, 3)
     u = Holder(a=torch.ones((2, 3, 4, 5)), b=torch.ones((4, 5)), d={"t1": torch.ones((2, 3, 4, 5))})
     assert u[0, ...].shape == (3, 4) and u[0, ...].a.shape == (3, 4, 5)
+
+
+# ---- tests/cameras/test_cameras.py:124-159 (the oracle's ray generation; the kernels are pinned to the same reference
+#      rays numerically by tests/test_gpu_parity.py::test_lens_ray_generation_vs_reference_fixture) ------------------------
+def test_equirectangular_camera():
+    height = 100  # width is twice the height
+    c2w = torch.eye(4)[None, :3, :]
+    one = torch.ones(1, 1)
+    yy, xx = torch.meshgrid(torch.arange(height), torch.arange(2 * height), indexing="ij")
+    cam = torch.zeros(height * 2 * height, dtype=torch.int64)
+    origins, directions, pixel_area, _, _ = ko.generate_rays(
+        c2w, one * height, one * height, one * height, one * 0.5 * height, None, cam, yy.reshape(-1), xx.reshape(-1),
+        camera_type=torch.tensor([[ko.CAMERA_EQUIRECTANGULAR]]))
+    assert torch.allclose(origins[0], torch.tensor([0.0, 0.0, 0.0]))
+    directions = directions.view(height, 2 * height, 3)
+    threshold = 0.9
+    x, y, z = torch.tensor([1.0, 0.0, 0.0]), torch.tensor([0.0, 1.0, 0.0]), torch.tensor([0.0, 0.0, 1.0])
+    # top pixels point up
+    assert directions[0, 0] @ y > threshold and directions[0, height] @ y > threshold and directions[0, -1] @ y > threshold
+    # middle pixels point horizontally; the middle of the image is camera forwards
+    assert directions[height // 2, 0] @ z > threshold and directions[height // 2, height // 2] @ -x > threshold
+    assert directions[height // 2, height] @ -z > threshold and directions[height // 2, 3 * height // 2] @ x > threshold
+    assert directions[height // 2, -1] @ z > threshold
+    # bottom pixels point down
+    assert directions[-1, 0] @ -y > threshold and directions[-1, height] @ -y > threshold and directions[-1, -1] @ -y > threshold
+    assert bool((pixel_area > 0).all())
