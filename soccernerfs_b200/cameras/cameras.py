@@ -211,14 +211,19 @@ class Cameras:
         if camera_indices.shape[-1] != 1 or coords.shape[:-1] != shape:
             raise ValueError("camera_indices must be [..., 1] and coords [..., 2] with the same batch shape")
         dev = self.device
-        # coords are (y, x) pixel-centre coordinates = integer index + 0.5 (image_coords[y, x]); the kernel adds the
-        # offset itself, so hand it the integer part
-        yx = torch.floor(coords.to(dev)).to(torch.int64).reshape(-1, 2)
-        if not bool(((coords.to(dev).reshape(-1, 2) - yx) == 0.5).all()):
-            raise NotImplementedError("generate_rays: coords must be pixel centres (integer + 0.5)")
-        tri = torch.cat([camera_indices.to(dev).reshape(-1, 1).to(torch.int64), yx], dim=-1).contiguous()
+        # coords are (y, x) image coordinates = integer index + one sub-pixel offset: 0.5 for pixel centres
+        # (image_coords[y, x], what RayGenerator and the eval loaders pass), 0 for integer coordinates (the reference's own
+        # tests/cameras/test_cameras.py:119-122).  The kernel adds the offset itself -- (float)index + offset is exactly the
+        # coordinate again -- so hand it the integer part.  Coordinates with differing fractional parts are not built.
+        flat = coords.to(dev).to(torch.float32).reshape(-1, 2)
+        whole = torch.floor(flat)
+        frac = flat - whole
+        offset = float(frac[0, 0]) if flat.numel() else 0.5
+        if not bool((frac == offset).all()):
+            raise NotImplementedError("generate_rays: coords must share one sub-pixel offset (pixel centres: integer + 0.5)")
+        tri = torch.cat([camera_indices.to(dev).reshape(-1, 1).to(torch.int64), whole.to(torch.int64)], dim=-1).contiguous()
         out = ops.generate_rays(self.camera_to_worlds, self._packed_intrinsics(), self.times, ray_indices=tri,
-                                distortion=self._lens(disable_distortion), cam_types=self._cam_types)
+                                pixel_offset=offset, distortion=self._lens(disable_distortion), cam_types=self._cam_types)
         return self._bundle(out, camera_indices.to(dev), shape, aabb_box)
 
     def generate_rays_from_indices(self, ray_indices: torch.Tensor, aabb_box=None) -> RayBundle:

@@ -215,7 +215,29 @@ def test_cameras_reject_unsupported_and_out_of_range():
     with pytest.raises(IndexError):
         cams.generate_rays_from_indices(torch.tensor([[0, 36, 0]]))
     with pytest.raises(NotImplementedError):
-        cams.generate_rays(camera_indices=0, coords=torch.tensor([[0.25, 0.5]]))  # not a pixel centre
+        cams.generate_rays(camera_indices=0, coords=torch.tensor([[0.25, 0.5]]))  # two different sub-pixel offsets
+    # one shared sub-pixel offset goes to the kernel as its pixel_offset with the integer parts as indices: pixel centres
+    # (0.5) and the integer coordinates of the reference's own test (tests/cameras/test_cameras.py:119-122, offset 0)
+    from soccernerfs_b200 import ops
+
+    seen = {}
+
+    def fake_generate_rays(c2w_, intr, times, ray_indices=None, pixel_offset=0.5, **kw):
+        seen.update(ray_indices=ray_indices.clone(), pixel_offset=pixel_offset, kw=kw)
+        n = ray_indices.shape[0]
+        return torch.zeros(n, 3), torch.zeros(n, 3), torch.ones(n), torch.ones(n), torch.zeros(n)
+
+    real, ops.generate_rays = ops.generate_rays, fake_generate_rays
+    try:
+        rb = cams.generate_rays(camera_indices=1, coords=torch.ones(10, 2))
+        assert seen["pixel_offset"] == 0.0 and seen["ray_indices"].tolist() == [[1, 1, 1]] * 10 and rb.origins.shape == (10, 3)
+        assert seen["kw"]["distortion"] is None and seen["kw"]["cam_types"] is None
+        cams.generate_rays(camera_indices=torch.tensor([[0], [1]]), coords=torch.tensor([[3.5, 5.5], [0.5, 63.5]]))
+        assert seen["pixel_offset"] == 0.5 and seen["ray_indices"].tolist() == [[0, 3, 5], [1, 0, 63]]
+        mixed.generate_rays(camera_indices=0, coords=torch.tensor([[2.25, 7.25]]), disable_distortion=True)
+        assert seen["pixel_offset"] == 0.25 and seen["kw"]["distortion"] is None and seen["kw"]["cam_types"] is not None
+    finally:
+        ops.generate_rays = real
 
 
 def test_reference_optimizer_state_round_trip():
